@@ -1,0 +1,462 @@
+/*
+ * CPU oracle (C99, fp64, OpenMP) for the Nystroem graph-Laplacian filter path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library, and only as the
+ * checker or as the timed CPU baseline.  The product (libglcuda.so) never links
+ * or calls it.
+ *
+ * Parity status: the reference has no tests/golden vectors for this path and
+ * its PETSc/SLEPc/MPI C code cannot be built here; this restatement is pinned
+ * against the reference's importable Python modules (python/sampling and
+ * python/affinity_methods) through tests/golden/ and against oracle_np.py.
+ * Stages after the eigensolve are "unpinned by the reference" (commented out
+ * at hpc/image_processing.c:240-275); they restate that block as written.
+ *
+ * Citations are file:line relative to the reference root.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+static double now_s(void)
+{
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    return 0.0;
+#endif
+}
+
+/* ------------------------------------------------------------------------- */
+/* a-1 sampling                                                              */
+/* ------------------------------------------------------------------------- */
+
+/* hpc/sampling.c:6-23.  Returns the rewritten sample count; writes at most cap
+ * indices. */
+ORC_API unsigned orc_uniform_sampling(int width, int height, unsigned requested, uint32_t* out, unsigned cap)
+{
+    const unsigned dist = (unsigned)sqrt((double)((width * height) / requested));
+    const unsigned xy0 = dist / 2;
+    unsigned c = 0;
+    for (unsigned i = xy0; i < (unsigned)(height - 1); i += dist)
+        for (unsigned j = xy0; j < (unsigned)(width - 1); j += dist) {
+            if (out && c < cap) out[c] = (uint32_t)width * i + j;
+            ++c;
+        }
+    return c;
+}
+
+/* MT19937 (Matsumoto-Nishimura): the stream numpy's legacy np.random.seed /
+ * randint consume in python/sampling/random.py:10-12. */
+typedef struct { uint32_t mt[624]; int pos; } mt_state;
+
+static void mt_seed(mt_state* s, uint32_t seed)
+{
+    s->mt[0] = seed;
+    for (int i = 1; i < 624; ++i)
+        s->mt[i] = 1812433253u * (s->mt[i - 1] ^ (s->mt[i - 1] >> 30)) + (uint32_t)i;
+    s->pos = 624;
+}
+
+static uint32_t mt_next(mt_state* s)
+{
+    if (s->pos >= 624) {
+        for (int k = 0; k < 624; ++k) {
+            uint32_t y = (s->mt[k] & 0x80000000u) | (s->mt[(k + 1) % 624] & 0x7fffffffu);
+            s->mt[k] = s->mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        s->pos = 0;
+    }
+    uint32_t y = s->mt[s->pos++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+static int cmp_u32(const void* a, const void* b)
+{
+    uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+    return (x > y) - (x < y);
+}
+
+/* python/sampling/random.py:8-16 after np.random.seed(seed): first `requested`
+ * distinct masked-rejection draws in [0, n), sorted. */
+ORC_API unsigned orc_random_sampling(int width, int height, unsigned requested, uint32_t seed, uint32_t* out)
+{
+    const uint32_t n = (uint32_t)width * (uint32_t)height;
+    uint32_t rng = n - 1, mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    uint8_t* seen = (uint8_t*)calloc((size_t)n, 1);
+    mt_state st; mt_seed(&st, seed);
+    unsigned cnt = 0;
+    while (cnt < requested) {
+        uint32_t v = mt_next(&st) & mask;
+        if (v > rng) continue;
+        if (!seen[v]) { seen[v] = 1; out[cnt++] = v; }
+    }
+    free(seen);
+    qsort(out, cnt, sizeof(uint32_t), cmp_u32);
+    return cnt;
+}
+
+/* ------------------------------------------------------------------------- */
+/* synthetic image: integer-only, identical to oracle_np.synthetic_image      */
+/* ------------------------------------------------------------------------- */
+static uint32_t hash32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+ORC_API void orc_synthetic_image(int width, int height, int channels, uint32_t seed, uint8_t* out)
+{
+    static const int per[3][2] = {{97, 131}, {113, 89}, {71, 149}};
+    const uint32_t salt = seed * 0x9e3779b1u;
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < height; ++r)
+        for (int c = 0; c < width; ++c)
+            for (int ch = 0; ch < channels; ++ch) {
+                const int pr = per[ch][0], pc = per[ch][1];
+                int tr = 64 - abs(((r % pr) * 256) / pr - 128);
+                int tc = 64 - abs(((c % pc) * 256) / pc - 128);
+                int smooth = (80 * tr * tc + 4096 * 80) / 4096 - 80;
+                int edges = 24 * (((r >> 6) + (c >> 6)) & 1);
+                uint64_t idx = ((uint64_t)r * (uint64_t)width + (uint64_t)c) * (uint64_t)channels + (uint64_t)ch;
+                int noise = (int)(hash32((uint32_t)idx + salt) % 33u) - 16;
+                int v = 128 + smooth + edges + noise;
+                out[idx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+}
+
+/* ------------------------------------------------------------------------- */
+/* a-2 affinity                                                              */
+/* ------------------------------------------------------------------------- */
+enum { ORC_BILATERAL = 0, ORC_PHOTOMETRIC = 1, ORC_SPATIAL = 2 };
+
+typedef struct {
+    int width, height, channels;
+    int kind;            /* ORC_* */
+    double h_loc, h_val; /* hpc/affinity.c:117-118: 40, 30 */
+    double gain;         /* hpc/display.c:73: 3.0 */
+    double power;        /* MatPow is a no-op (hpc/utils.c:721) => 1.0 */
+    int m;               /* eigenpairs; <0 or >=p => p-1 (hpc/image_processing.c:102-106) */
+    int gram_schmidt;    /* orthonormalise Phi with hpc/gram_schmidt.c:29-64 */
+    int row0, row1;      /* pixel rows that take part (bounded sample); 0,height = whole image */
+} orc_params;
+
+/* hpc/affinity.c:59-113: exp(-|dx|^2/h_loc^2) * exp(-dv^2/h_val^2), two exps
+ * multiplied, as the reference does (:99,107,110). */
+static inline double kern(const orc_params* P, const uint8_t* img, uint32_t a, uint32_t b)
+{
+    const int W = P->width, C = P->channels;
+    double k = 1.0;
+    if (P->kind != ORC_PHOTOMETRIC) {
+        double dr = (double)(a / W) - (double)(b / W), dc = (double)(a % W) - (double)(b % W);
+        k *= exp(-(dr * dr + dc * dc) / (P->h_loc * P->h_loc));
+    }
+    if (P->kind != ORC_SPATIAL) {
+        double d2 = 0.0;
+        for (int ch = 0; ch < C; ++ch) {
+            double dv = (double)img[(size_t)a * C + ch] - (double)img[(size_t)b * C + ch];
+            d2 += dv * dv;
+        }
+        k *= exp(-d2 / (P->h_val * P->h_val));
+    }
+    return k;
+}
+
+/* ------------------------------------------------------------------------- */
+/* symmetric eigensolver: Householder tridiagonalisation + implicit-shift QL  */
+/* (the textbook EISPACK tred2/tql2 pair), fp64.  a: n x n row-major, on exit */
+/* its columns are the eigenvectors; d: eigenvalues ascending.               */
+/* ------------------------------------------------------------------------- */
+static void tridiagonalise(double* a, int n, double* d, double* e)
+{
+    for (int i = n - 1; i > 0; --i) {
+        int l = i - 1;
+        double h = 0.0, scale = 0.0;
+        if (l > 0) {
+            for (int k = 0; k <= l; ++k) scale += fabs(a[i * n + k]);
+            if (scale == 0.0) {
+                e[i] = a[i * n + l];
+            } else {
+                for (int k = 0; k <= l; ++k) { a[i * n + k] /= scale; h += a[i * n + k] * a[i * n + k]; }
+                double f = a[i * n + l];
+                double g = (f >= 0.0 ? -sqrt(h) : sqrt(h));
+                e[i] = scale * g;
+                h -= f * g;
+                a[i * n + l] = f - g;
+                f = 0.0;
+                for (int j = 0; j <= l; ++j) {
+                    a[j * n + i] = a[i * n + j] / h;
+                    g = 0.0;
+                    for (int k = 0; k <= j; ++k) g += a[j * n + k] * a[i * n + k];
+                    for (int k = j + 1; k <= l; ++k) g += a[k * n + j] * a[i * n + k];
+                    e[j] = g / h;
+                    f += e[j] * a[i * n + j];
+                }
+                double hh = f / (h + h);
+                for (int j = 0; j <= l; ++j) {
+                    f = a[i * n + j];
+                    e[j] = g = e[j] - hh * f;
+                    for (int k = 0; k <= j; ++k) a[j * n + k] -= (f * e[k] + g * a[i * n + k]);
+                }
+            }
+        } else {
+            e[i] = a[i * n + l];
+        }
+        d[i] = h;
+    }
+    d[0] = 0.0;
+    e[0] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        int l = i - 1;
+        if (d[i] != 0.0) {
+            for (int j = 0; j <= l; ++j) {
+                double g = 0.0;
+                for (int k = 0; k <= l; ++k) g += a[i * n + k] * a[k * n + j];
+                for (int k = 0; k <= l; ++k) a[k * n + j] -= g * a[k * n + i];
+            }
+        }
+        d[i] = a[i * n + i];
+        a[i * n + i] = 1.0;
+        for (int j = 0; j <= l; ++j) a[j * n + i] = a[i * n + j] = 0.0;
+    }
+}
+
+static int ql_implicit(double* d, double* e, int n, double* z)
+{
+    for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+    e[n - 1] = 0.0;
+    for (int l = 0; l < n; ++l) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; ++m) {
+                double dd = fabs(d[m]) + fabs(d[m + 1]);
+                if (fabs(e[m]) <= 2.3e-16 * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 200) return -1;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? fabs(r) : -fabs(r)));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; --i) {
+                    double f = s * e[i], b = c * e[i];
+                    e[i + 1] = (r = hypot(f, g));
+                    if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+                    s = f / r; c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    d[i + 1] = g + (p = s * r);
+                    g = c * r - b;
+                    for (int k = 0; k < n; ++k) {
+                        f = z[k * n + i + 1];
+                        z[k * n + i + 1] = s * z[k * n + i] + c * f;
+                        z[k * n + i] = c * z[k * n + i] - s * f;
+                    }
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p; e[l] = g; e[m] = 0.0;
+            }
+        } while (m != l);
+    }
+    return 0;
+}
+
+/* Eigen-decomposition of symmetric a (n x n, row-major, overwritten with
+ * eigenvectors in columns), eigenvalues ascending in d. */
+ORC_API int orc_symeig(double* a, int n, double* d)
+{
+    double* e = (double*)malloc(sizeof(double) * n);
+    tridiagonalise(a, n, d, e);
+    int rc = ql_implicit(d, e, n, a);
+    free(e);
+    if (rc) return rc;
+    /* selection sort ascending, swapping columns */
+    for (int i = 0; i < n - 1; ++i) {
+        int k = i; double p = d[i];
+        for (int j = i + 1; j < n; ++j) if (d[j] < p) { k = j; p = d[j]; }
+        if (k != i) {
+            d[k] = d[i]; d[i] = p;
+            for (int r = 0; r < n; ++r) { double t = a[r * n + i]; a[r * n + i] = a[r * n + k]; a[r * n + k] = t; }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* the restored pipeline hpc/image_processing.c:183-275                       */
+/* ------------------------------------------------------------------------- */
+/* timings[0..6] = affinity, laplacian, eigensolve, nystroem(+permutation),
+ * gram-schmidt, filter, total.  z: n*C doubles in raster order (pixels outside
+ * the band keep y).  D: p, mu: m.  Returns 0 on success. */
+ORC_API int orc_pipeline(const uint8_t* img, const orc_params* P, const uint32_t* s, int p,
+                         double* D_out, double* alpha_out, double* mu_out, double* z, double* timings)
+{
+    const int W = P->width, H = P->height, C = P->channels;
+    const size_t n = (size_t)W * H;
+    int m = P->m;
+    if (m < 0 || m >= p) m = p - 1;
+    int row0 = P->row0, row1 = P->row1;
+    if (row1 <= row0) { row0 = 0; row1 = H; }
+    const size_t q0 = (size_t)row0 * W, q1 = (size_t)row1 * W;
+    double t_all = now_s(), t0;
+
+    /* non-sample pixels of the band in ascending raster order (affinity.c:218-235) */
+    uint8_t* is_sample = (uint8_t*)calloc(n, 1);
+    int32_t* sample_pos = (int32_t*)malloc(sizeof(int32_t) * n);
+    for (int i = 0; i < p; ++i) { is_sample[s[i]] = 1; }
+    size_t nb = 0;
+    uint32_t* rest = (uint32_t*)malloc(sizeof(uint32_t) * (q1 - q0));
+    for (size_t q = q0; q < q1; ++q) if (!is_sample[q]) rest[nb++] = (uint32_t)q;
+    (void)sample_pos;
+
+    /* --- affinity: K_A p x p, K_B p x nb, row-major by sample (affinity.c:129-262) */
+    t0 = now_s();
+    double* KA = (double*)malloc(sizeof(double) * (size_t)p * p);
+    double* KB = (double*)malloc(sizeof(double) * (size_t)p * nb);
+    if (!KA || !KB) return -2;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < p; ++i) {
+        for (int j = 0; j < p; ++j) KA[(size_t)i * p + j] = kern(P, img, s[i], s[j]);
+        double* row = KB + (size_t)i * nb;
+        for (size_t k = 0; k < nb; ++k) row[k] = kern(P, img, s[i], rest[k]);
+    }
+    if (timings) timings[0] = now_s() - t0;
+
+    /* --- Laplacian (laplacian.c:14-42) */
+    t0 = now_s();
+    double* D = (double*)malloc(sizeof(double) * p);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < p; ++i) {
+        double a = 0.0, b = 0.0;
+        for (int j = 0; j < p; ++j) a += KA[(size_t)i * p + j];
+        const double* row = KB + (size_t)i * nb;
+        for (size_t k = 0; k < nb; ++k) b += row[k];
+        D[i] = a + b;
+    }
+    double sum = 0.0;
+    for (int i = 0; i < p; ++i) sum += D[i];
+    const double alpha = 1.0 / (sum / p);
+    double* LA = (double*)malloc(sizeof(double) * (size_t)p * p);
+    for (int i = 0; i < p; ++i)
+        for (int j = 0; j < p; ++j)
+            LA[(size_t)i * p + j] = alpha * ((i == j ? D[i] : 0.0) - KA[(size_t)i * p + j]);
+    /* L_B = -alpha K_B: the reference makes a second full copy (laplacian.c:38-39);
+     * here the factor is folded into Wm below. */
+    if (timings) timings[1] = now_s() - t0;
+    if (D_out) memcpy(D_out, D, sizeof(double) * p);
+    if (alpha_out) *alpha_out = alpha;
+
+    /* --- eigensolve: converged m smallest pairs (eigendecomposition.c:121-124) */
+    t0 = now_s();
+    double* mu_all = (double*)malloc(sizeof(double) * p);
+    if (orc_symeig(LA, p, mu_all)) return -3;
+    if (timings) timings[2] = now_s() - t0;
+    if (mu_out) memcpy(mu_out, mu_all, sizeof(double) * m);
+
+    /* --- Nystroem (nystroem.c:25-57) + permutation to raster order (utils.c:134-173):
+     * phi rows live at their raster position inside the band; sample rows = U. */
+    t0 = now_s();
+    const size_t nband = q1 - q0;
+    double* Wm = (double*)malloc(sizeof(double) * (size_t)p * m);  /* -alpha U Lambda^-1 */
+    for (int i = 0; i < p; ++i)
+        for (int j = 0; j < m; ++j) Wm[(size_t)i * m + j] = -alpha * LA[(size_t)i * p + j] / mu_all[j];
+    double* phi = (double*)calloc(nband * (size_t)m, sizeof(double));
+    if (!phi) return -2;
+    {
+        /* phi[rest[k], :] = sum_i KB[i,k] Wm[i,:]  (MatTransposeMatMult, nystroem.c:42) */
+#pragma omp parallel for schedule(dynamic, 64)
+        for (size_t k = 0; k < nb; ++k) {
+            double* out = phi + ((size_t)rest[k] - q0) * m;
+            for (int i = 0; i < p; ++i) {
+                const double kv = KB[(size_t)i * nb + k];
+                const double* w = Wm + (size_t)i * m;
+                for (int j = 0; j < m; ++j) out[j] += kv * w[j];
+            }
+        }
+        for (int i = 0; i < p; ++i)
+            if (s[i] >= q0 && s[i] < q1)
+                for (int j = 0; j < m; ++j) phi[((size_t)s[i] - q0) * m + j] = LA[(size_t)i * p + j];
+    }
+    if (timings) timings[3] = now_s() - t0;
+
+    /* --- optional classical Gram-Schmidt on the columns of phi (gram_schmidt.c:29-64) */
+    t0 = now_s();
+    if (P->gram_schmidt) {
+        double* coef = (double*)malloc(sizeof(double) * m);
+        for (int k = 0; k < m; ++k) {
+#pragma omp parallel for schedule(static)
+            for (int j = 0; j < k; ++j) {
+                double vu = 0.0, uu = 0.0;
+                for (size_t r = 0; r < nband; ++r) {
+                    vu += phi[r * m + k] * phi[r * m + j];
+                    uu += phi[r * m + j] * phi[r * m + j];
+                }
+                coef[j] = vu / uu;
+            }
+            double nrm = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : nrm)
+            for (size_t r = 0; r < nband; ++r) {
+                double acc = 0.0;
+                for (int j = 0; j < k; ++j) acc += coef[j] * phi[r * m + j];
+                double v = phi[r * m + k] - acc;
+                phi[r * m + k] = v;
+                nrm += v * v;
+            }
+            nrm = sqrt(nrm);
+#pragma omp parallel for schedule(static)
+            for (size_t r = 0; r < nband; ++r) phi[r * m + k] /= nrm;
+        }
+        free(coef);
+    }
+    if (timings) timings[4] = now_s() - t0;
+
+    /* --- filter (display.c:58-83): z = y + gain * phi (mu^power o (phi^T y)); clip > 255 */
+    t0 = now_s();
+    for (size_t q = 0; q < n * C; ++q) z[q] = (double)img[q];
+    double* c = (double*)calloc((size_t)m * C, sizeof(double));
+    for (size_t r = 0; r < nband; ++r)
+        for (int ch = 0; ch < C; ++ch) {
+            const double yv = (double)img[(q0 + r) * C + ch];
+            const double* row = phi + r * m;
+            for (int j = 0; j < m; ++j) c[(size_t)j * C + ch] += row[j] * yv;
+        }
+    for (int j = 0; j < m; ++j)
+        for (int ch = 0; ch < C; ++ch) c[(size_t)j * C + ch] *= pow(mu_all[j], P->power);
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < nband; ++r)
+        for (int ch = 0; ch < C; ++ch) {
+            double acc = 0.0;
+            const double* row = phi + r * m;
+            for (int j = 0; j < m; ++j) acc += row[j] * c[(size_t)j * C + ch];
+            double v = z[(q0 + r) * C + ch] + P->gain * acc;
+            z[(q0 + r) * C + ch] = v > 255.0 ? 255.0 : v;
+        }
+    if (timings) { timings[5] = now_s() - t0; timings[6] = now_s() - t_all; }
+
+    free(c); free(phi); free(Wm); free(mu_all); free(LA); free(D); free(KB); free(KA);
+    free(rest); free(sample_pos); free(is_sample);
+    return 0;
+}
+
+ORC_API int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,332 @@
+"""CPU oracle (numpy, fp64) for the Nystroem graph-Laplacian filter path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import it, and only as the checker.  The product path
+(image-processing-graph-laplacian_b200/) never imports or links this.
+
+Parity status: the reference ships no tests or golden vectors for this path
+ and its C pipeline cannot be built here (PETSc/SLEPc/MPI
+absent).  The oracle is pinned instead against outputs of the reference's own
+importable Python modules run in the build container -- python/sampling/* and
+python/affinity_methods/{bilateral,photometric,spatial}.py -- via the fixtures
+written by tests/golden/make_golden.py.  Stages past the eigensolve have no
+runnable reference (hpc/image_processing.c:237-276 is commented out at HEAD):
+for those the parity is "unpinned by the reference", and the oracle restates
+the commented block bug-for-bug as SURVEY.md section 8c defines it.
+
+Each function cites the reference file:line it follows (paths relative to the
+reference root).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ----------------------------------------------------------------------------
+# MT19937 -- the generator behind numpy's legacy np.random.seed / randint, which
+# python/sampling/random.py:10-12 draws from.
+# ----------------------------------------------------------------------------
+
+
+class MT19937:
+    """Plain restatement of the published MT19937 algorithm (Matsumoto &
+    Nishimura 1998): init_genrand(seed) + genrand_int32()."""
+
+    N, M = 624, 397
+
+    def __init__(self, seed: int):
+        mt = np.empty(self.N, dtype=np.uint64)
+        mt[0] = seed & 0xFFFFFFFF
+        for i in range(1, self.N):
+            prev = int(mt[i - 1])
+            mt[i] = (1812433253 * (prev ^ (prev >> 30)) + i) & 0xFFFFFFFF
+        self.mt = mt.astype(np.uint32)
+        self.pos = self.N
+
+    def _twist(self):
+        mt = self.mt
+        N, M = self.N, self.M
+        # three dependency-free phases, the usual way to vectorise the twist
+        for lo, hi in ((0, N - M), (N - M, 2 * (N - M)), (2 * (N - M), N - 1)):
+            hi = min(hi, N - 1)
+            if lo >= hi:
+                continue
+            y = (mt[lo:hi] & np.uint32(0x80000000)) | (mt[lo + 1:hi + 1] & np.uint32(0x7FFFFFFF))
+            src = (np.arange(lo, hi) + M) % N
+            mag = np.where((y & np.uint32(1)) != 0, np.uint32(0x9908B0DF), np.uint32(0))
+            mt[lo:hi] = mt[src] ^ (y >> np.uint32(1)) ^ mag
+        y = (mt[N - 1] & np.uint32(0x80000000)) | (mt[0] & np.uint32(0x7FFFFFFF))
+        mag = np.uint32(0x9908B0DF) if (int(y) & 1) else np.uint32(0)
+        mt[N - 1] = mt[M - 1] ^ (y >> np.uint32(1)) ^ mag
+        self.pos = 0
+
+    def next_u32_block(self) -> np.ndarray:
+        """Return the remaining tempered words of the current block."""
+        if self.pos >= self.N:
+            self._twist()
+        y = self.mt[self.pos:].copy()
+        self.pos = self.N
+        y ^= y >> np.uint32(11)
+        y ^= (y << np.uint32(7)) & np.uint32(0x9D2C5680)
+        y ^= (y << np.uint32(15)) & np.uint32(0xEFC60000)
+        y ^= y >> np.uint32(18)
+        return y
+
+    def stream(self):
+        while True:
+            for v in self.next_u32_block():
+                yield int(v)
+
+
+def _mask_for(rng: int) -> int:
+    mask = rng
+    for sh in (1, 2, 4, 8, 16):
+        mask |= mask >> sh
+    return mask
+
+
+# ----------------------------------------------------------------------------
+# a-1  Sampling
+# ----------------------------------------------------------------------------
+
+
+def uniform_sampling(width: int, height: int, sample_size: int) -> np.ndarray:
+    """hpc/sampling.c:6-23 (UniformSampling); same grid as
+    python/sampling/spatially_uniform.py:9-24.  Returns ascending uint32 raster
+    indices; len() is the rewritten *sample_size."""
+    sample_dist = int(np.sqrt((width * height) // sample_size))  # integer division first (:8)
+    xy0 = sample_dist // 2
+    rows = range(xy0, height - 1, sample_dist)
+    cols = range(xy0, width - 1, sample_dist)
+    out = np.empty(len(rows) * len(cols), dtype=np.uint32)
+    c = 0
+    for i in rows:
+        for j in cols:
+            out[c] = width * i + j
+            c += 1
+    return out
+
+
+def random_sampling(width: int, height: int, sample_size: int, seed: int) -> np.ndarray:
+    """python/sampling/random.py:8-16 with np.random.seed(seed) in front.
+
+    The legacy randint(0, n) draws one MT19937 word, masks it to the smallest
+    2^k-1 >= n-1 and rejects values > n-1; the reference takes the set of the
+    first `sample_size` draws and tops it up one draw at a time until it holds
+    `sample_size` distinct values, then sorts.  That equals: the first
+    `sample_size` distinct accepted values of the stream, sorted."""
+    n = width * height
+    rng = n - 1
+    mask = _mask_for(rng)
+    seen = set()
+    gen = MT19937(seed).stream()
+    # first batch of exactly sample_size accepted draws (duplicates collapse)
+    taken = 0
+    while taken < sample_size:
+        v = next(gen) & mask
+        if v <= rng:
+            seen.add(v)
+            taken += 1
+    while len(seen) < sample_size:
+        v = next(gen) & mask
+        if v <= rng:
+            seen.add(v)
+    return np.sort(np.fromiter(seen, dtype=np.uint32, count=len(seen)))
+
+
+# ----------------------------------------------------------------------------
+# Synthetic images (SURVEY.md 8d asks for one bit-reproducible generator).
+# Integer-only so numpy, C and CUDA agree bit for bit: smooth low-frequency
+# product of triangle waves + 64-pixel checkerboard edges + hashed noise.
+# ----------------------------------------------------------------------------
+
+_SYN_PERIODS = ((97, 131), (113, 89), (71, 149))
+
+
+def _hash32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x = (x * np.uint32(0x7FEB352D)).astype(np.uint32)
+    x ^= x >> np.uint32(15)
+    x = (x * np.uint32(0x846CA68B)).astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def synthetic_image(width: int, height: int, channels: int = 1, seed: int = 1234) -> np.ndarray:
+    """u8 image [H, W] (channels=1) or [H, W, 3]."""
+    r = np.arange(height, dtype=np.int64)[:, None]
+    c = np.arange(width, dtype=np.int64)[None, :]
+    out = np.empty((height, width, channels), dtype=np.uint8)
+    for ch in range(channels):
+        pr, pc = _SYN_PERIODS[ch]
+        tr = 64 - np.abs(((r % pr) * 256) // pr - 128)      # [-64, 64]
+        tc = 64 - np.abs(((c % pc) * 256) // pc - 128)
+        smooth = (80 * tr * tc + 4096 * 80) // 4096 - 80      # floor division on a non-negative number
+        edges = 24 * (((r >> 6) + (c >> 6)) & 1)
+        idx = (r * width + c) * channels + ch
+        with np.errstate(over="ignore"):
+            h = _hash32((idx & 0xFFFFFFFF).astype(np.uint32) + np.uint32((seed * 0x9E3779B1) & 0xFFFFFFFF))
+        noise = (h % np.uint32(33)).astype(np.int64) - 16
+        v = 128 + smooth + edges + noise
+        out[:, :, ch] = np.clip(v, 0, 255).astype(np.uint8)
+    return out[:, :, 0] if channels == 1 else out
+
+
+# ----------------------------------------------------------------------------
+# a-2  Affinity
+# ----------------------------------------------------------------------------
+
+BILATERAL, PHOTOMETRIC, SPATIAL = "bilateral", "photometric", "spatial"
+
+
+def _as_hwc(img: np.ndarray) -> np.ndarray:
+    img = np.asarray(img)
+    return img[:, :, None] if img.ndim == 2 else img
+
+
+def affinity_rows(img, sample_indices, cols, kind=BILATERAL, h_loc=40.0, h_val=30.0):
+    """K(samples, cols) in fp64.
+
+    hpc/affinity.c:59-113 (ComputeBilateralFilter), :8-17 (photometric), :19-57
+    (spatial); Python twins python/affinity_methods/{bilateral,photometric,
+    spatial}.py.  The reference multiplies two exponentials (affinity.c:99,107,
+    110); colour (no counterpart in the reference) sums the
+    squared channel differences in the photometric term."""
+    img = _as_hwc(img).astype(np.float64)
+    H, W, C = img.shape
+    flat = img.reshape(H * W, C)
+    s = np.asarray(sample_indices, dtype=np.int64)
+    q = np.asarray(cols, dtype=np.int64)
+    sr, sc = s // W, s % W          # hpc/utils.c:11-19: num2x = row, num2y = col
+    qr, qc = q // W, q % W
+    K = np.ones((len(s), len(q)), dtype=np.float64)
+    if kind in (BILATERAL, SPATIAL):
+        d2 = (sr[:, None] - qr[None, :]) ** 2 + (sc[:, None] - qc[None, :]) ** 2
+        K *= np.exp(-(d2.astype(np.float64)) / (h_loc * h_loc))
+    if kind in (BILATERAL, PHOTOMETRIC):
+        dv2 = np.zeros((len(s), len(q)), dtype=np.float64)
+        for ch in range(C):
+            dv2 += (flat[s, ch][:, None] - flat[q, ch][None, :]) ** 2
+        K *= np.exp(-dv2 / (h_val * h_val))
+    return K
+
+
+def non_sample_indices(n: int, sample_indices) -> np.ndarray:
+    """Ascending raster order of the pixels that are not samples
+    (hpc/affinity.c:218-235)."""
+    mask = np.ones(n, dtype=bool)
+    mask[np.asarray(sample_indices, dtype=np.int64)] = False
+    return np.nonzero(mask)[0]
+
+
+# ----------------------------------------------------------------------------
+# a-3 .. a-9  Laplacian, eigensolve, Nystroem, permutation, filter
+# ----------------------------------------------------------------------------
+
+
+def laplacian(K_A, rowsum_B):
+    """hpc/laplacian.c:14-42: D_A = rowsum(K_A)+rowsum(K_B); alpha = 1/mean(D_A);
+    L_A = alpha (D_A - K_A).  L_B = -alpha K_B is folded by the callers."""
+    D = K_A.sum(axis=1) + rowsum_B
+    alpha = 1.0 / D.mean()
+    L_A = alpha * (np.diag(D) - K_A)
+    return D, alpha, L_A
+
+
+def smallest_eigenpairs(L_A, m):
+    """Converged m smallest eigenpairs, ascending: what
+    hpc/eigendecomposition.c:121-124 asks SLEPc for and what
+    hpc/inverse_power_it.c:86-252 approximates."""
+    mu, U = np.linalg.eigh(L_A)
+    return mu[:m], U[:, :m]
+
+
+def gram_schmidt(X):
+    """hpc/gram_schmidt.c:29-64 (classical Gram-Schmidt, projections taken
+    against the already-normalised u_j, then normalise).  Column-by-column,
+    fp64.  Returns (Q, norms_before_normalisation)."""
+    X = np.array(X, dtype=np.float64, copy=True)
+    norms = np.empty(X.shape[1])
+    for k in range(X.shape[1]):
+        v = X[:, k].copy()
+        if k:
+            U = X[:, :k]
+            coef = (U.T @ v) / np.einsum("ij,ij->j", U, U)   # <v,u>/<u,u> (:14-16)
+            v = v - U @ coef
+        norms[k] = np.linalg.norm(v)
+        X[:, k] = v / norms[k]
+    return X, norms
+
+
+def run_pipeline(img, sample_indices, m=None, kind=BILATERAL, h_loc=40.0, h_val=30.0,
+                 gain=3.0, power=1.0, orthonormalise=False, chunk=65536, return_phi=False):
+    """The restored block hpc/image_processing.c:183-275 in fp64:
+
+      s -> K_A, K_B (affinity.c:129-262) -> D, alpha, L_A (laplacian.c:14-42) ->
+      (mu, U) m smallest -> Phi[s] = U, Phi[rest] = (-alpha K_B)^T U diag(1/mu)
+      (nystroem.c:25-57 + utils.c:134-173 permutation back to raster order) ->
+      z = y + gain * Phi (mu^power o (Phi^T y)) (display.c:64-73; MatPow is a
+      no-op, utils.c:721, hence power=1), z[z>255] = 255 (display.c:76).
+
+    Returns a dict.  z is float64 [H, W] or [H, W, C]; negatives are NOT clipped
+    (SURVEY 8c-iii)."""
+    imgc = _as_hwc(img)
+    H, W, C = imgc.shape
+    n = H * W
+    s = np.asarray(sample_indices, dtype=np.int64)
+    p = len(s)
+    if m is None or m < 0 or m >= p:
+        m = p - 1                                   # image_processing.c:102-106
+    rest = non_sample_indices(n, s)
+
+    K_A = affinity_rows(imgc, s, s, kind, h_loc, h_val)
+    rowsum_B = np.zeros(p)
+    for a in range(0, len(rest), chunk):
+        rowsum_B += affinity_rows(imgc, s, rest[a:a + chunk], kind, h_loc, h_val).sum(axis=1)
+    D, alpha, L_A = laplacian(K_A, rowsum_B)
+    mu, U = smallest_eigenpairs(L_A, m)
+
+    Wm = (-alpha) * U / mu[None, :]                # p x m  (L_B^T . Phi_A . Lambda^-1, nystroem.c:41-42)
+    y = imgc.reshape(n, C).astype(np.float64)
+
+    phi = None
+    if orthonormalise or return_phi:
+        phi = np.empty((n, m))
+        phi[s] = U
+        for a in range(0, len(rest), chunk):
+            idx = rest[a:a + chunk]
+            phi[idx] = affinity_rows(imgc, s, idx, kind, h_loc, h_val).T @ Wm
+        if orthonormalise:
+            phi, _ = gram_schmidt(phi)
+        c = phi.T @ y
+        z = y + gain * (phi @ ((mu[:, None] ** power) * c))
+    else:
+        # same arithmetic, streamed so Phi (n x m fp64) is never held
+        c = U.T @ y[s]
+        for a in range(0, len(rest), chunk):
+            idx = rest[a:a + chunk]
+            KB = affinity_rows(imgc, s, idx, kind, h_loc, h_val)
+            c += Wm.T @ (KB @ y[idx])
+        w = (mu[:, None] ** power) * c             # m x C
+        z = y.copy()
+        z[s] += gain * (U @ w)
+        Ww = Wm @ w                                # p x C
+        for a in range(0, len(rest), chunk):
+            idx = rest[a:a + chunk]
+            KB = affinity_rows(imgc, s, idx, kind, h_loc, h_val)
+            z[idx] += gain * (KB.T @ Ww)
+    z = np.minimum(z, 255.0)                       # AboveXSetY(z, 255, 255), display.c:76
+    z = z.reshape(H, W, C)
+    out = dict(sample_indices=s.astype(np.uint32), K_A=K_A, D=D, alpha=alpha, L_A=L_A, mu=mu,
+               U=U, z=z[:, :, 0] if np.asarray(img).ndim == 2 else z, m=m, p=p)
+    if return_phi:
+        out["phi"] = phi
+    return out
+
+
+def quantise(z):
+    """OneColMat2pngbytes (hpc/utils.c:492-534) casts double -> png_byte; negative
+    inputs are UB there, so the build clamps to [0,255] then truncates
+    (SURVEY 8c-iii)."""
+    return np.clip(z, 0.0, 255.0).astype(np.uint8)

@@ -1,0 +1,122 @@
+"""CPU tests: the oracle (numpy + C) against the golden fixtures that were
+produced by the reference's own Python modules (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import oracle_c as oc
+from oracle import oracle_np as o
+
+CASES = ["test_uniform100", "cat_small_random50", "barbara_uniform256", "lion_rgb_photometric500",
+         "lion_photometric_h10", "test_spatial_h10", "cat_small_uniform_m20"]
+
+
+def _src(g):
+    img = g["image"]
+    return np.repeat(img[:, :, None], 3, axis=2) if int(g["rgb"]) else img
+
+
+def test_sampling_matches_reference_modules(golden):
+    tab = golden("sampling")
+    assert len(tab) == 28
+    for key, ref in tab.items():
+        parts = key.split("_")
+        W, H = (int(v) for v in parts[1].split("x"))
+        p = int(parts[2])
+        if parts[0] == "uniform":
+            got_np, got_c = o.uniform_sampling(W, H, p), oc.uniform_sampling(W, H, p)
+        else:
+            seed = int(parts[3][1:])
+            got_c = oc.random_sampling(W, H, p, seed)
+            # the pure-python generator is slow: spot-check it on the small shapes only
+            got_np = o.random_sampling(W, H, p, seed) if p <= 500 else got_c
+            assert len(ref) == p
+        assert got_c.dtype == np.uint32
+        assert np.array_equal(got_c, ref), key           # bit-exact
+        assert np.array_equal(got_np, ref), key
+        assert np.all(np.diff(ref.astype(np.int64)) > 0)  # strictly ascending
+
+
+@pytest.mark.parametrize("tag", ["test_uniform100", "cat_small_random50", "lion_photometric_h10", "test_spatial_h10"])
+def test_affinity_matches_reference_modules(golden, tag):
+    g = golden(tag)
+    img, s = g["image"], g["sample_indices"]
+    kind, h_loc, h_val = str(g["kind"]), float(g["h_loc"]), float(g["h_val"])
+    K_A = o.affinity_rows(img, s, s, kind, h_loc, h_val)
+    assert np.allclose(K_A, g["ref_K_A"], rtol=1e-13, atol=1e-300)
+    assert np.allclose(np.diag(K_A), 1.0) and np.allclose(K_A, K_A.T)
+    n = img.size
+    D = o.affinity_rows(img, s, np.arange(n), kind, h_loc, h_val).sum(axis=1)
+    assert np.allclose(D, g["ref_D"], rtol=1e-12)
+    assert np.allclose(g["D"], g["ref_D"], rtol=1e-12)     # the pipeline's D_A = rowsum(K_A)+rowsum(K_B)
+
+
+def test_barbara_rowsums_match_reference_module(golden):
+    g = golden("barbara_uniform256")
+    assert np.allclose(g["D"], g["ref_D"], rtol=1e-12)
+    assert len(g["sample_indices"]) == 256
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_c_oracle_matches_golden(golden, tag):
+    g = golden(tag)
+    src = _src(g)
+    r = oc.run_pipeline(src, g["sample_indices"], m=int(g["m"]), kind=str(g["kind"]),
+                        h_loc=float(g["h_loc"]), h_val=float(g["h_val"]))
+    assert np.allclose(r["D"], g["D"], rtol=1e-11)
+    assert abs(r["alpha"] - float(g["alpha"])) <= 1e-12 * float(g["alpha"])
+    assert np.allclose(r["mu"], g["mu"], rtol=1e-9)
+    z = g["z"].astype(np.float64)
+    assert np.linalg.norm(r["z"] - z) <= 2e-6 * np.linalg.norm(z)      # fixture is stored as float32
+    dz = np.linalg.norm(r["z"] - src)
+    assert np.linalg.norm((r["z"] - src) - (z - src)) <= 1e-4 * dz
+
+
+def test_numpy_oracle_invariants(golden):
+    g = golden("cat_small_random50")
+    r = o.run_pipeline(g["image"], g["sample_indices"], return_phi=True)
+    L_A, mu, phi = r["L_A"], r["mu"], r["phi"]
+    assert np.all(r["D"] > 0)
+    assert np.all(np.abs(np.diag(L_A)) > np.sum(np.abs(L_A), axis=1) - np.abs(np.diag(L_A)))  # strictly diag. dominant
+    assert np.all(mu > 0) and np.all(np.diff(mu) >= 0)
+    G = phi.T @ phi
+    assert np.linalg.norm(G - np.eye(G.shape[0])) < 2e-2      # nearly orthonormal before any GS
+    assert np.array_equal(phi[g["sample_indices"].astype(np.int64)], r["U"])
+    assert np.allclose(r["mu"], g["mu"], rtol=1e-10)
+    assert np.linalg.norm(r["z"] - g["z"]) <= 2e-6 * np.linalg.norm(g["z"])
+
+
+def test_gram_schmidt_oracles_agree(golden):
+    g = golden("test_uniform100")
+    rn = o.run_pipeline(g["image"], g["sample_indices"], orthonormalise=True)
+    rc = oc.run_pipeline(g["image"], g["sample_indices"], orthonormalise=True)
+    assert np.linalg.norm(rn["z"] - rc["z"]) <= 1e-9 * np.linalg.norm(rn["z"])
+    assert np.linalg.norm(rn["z"] - g["z_gs"]) <= 2e-6 * np.linalg.norm(rn["z"])
+    X = np.random.RandomState(0).randn(50, 7)
+    Q, norms = o.gram_schmidt(X)
+    assert np.allclose(Q.T @ Q, np.eye(7), atol=1e-12) and np.all(norms > 0)
+
+
+def test_symeig_against_lapack():
+    A = np.random.RandomState(1).randn(120, 120)
+    A = A + A.T
+    d, V = oc.symeig(A)
+    assert np.allclose(d, np.linalg.eigvalsh(A), atol=1e-11)
+    assert np.allclose(A @ V, V * d, atol=1e-10)
+
+
+def test_synthetic_generators_agree():
+    for ch in (1, 3):
+        a, b = o.synthetic_image(257, 131, ch), oc.synthetic_image(257, 131, ch)
+        assert a.dtype == np.uint8 and np.array_equal(a, b)
+    img = o.synthetic_image(640, 360)
+    assert 60 < img.mean() < 200 and img.std() > 20
+
+
+def test_band_sample_is_a_restriction(golden):
+    """rows=(r0,r1) of the C oracle (bench's bounded CPU sample) only touches band pixels."""
+    g = golden("test_uniform100")
+    img = g["image"]
+    r = oc.run_pipeline(img, g["sample_indices"], rows=(20, 60))
+    z = r["z"]
+    assert np.array_equal(z[:20], img[:20].astype(np.float64)) and np.array_equal(z[60:], img[60:].astype(np.float64))
+    assert not np.array_equal(z[20:60], img[20:60].astype(np.float64))
