@@ -1,0 +1,262 @@
+// a-2: affinity blocks K_A (p x p, fp64) and K_B (band pixels x p_pad, fp16, pixel-major) with the
+// row sums D = K_A.1 + K_B.1 taken from the fp32 kernel values before rounding.
+// Replaces ComputeAffinityMatrices / ComputeDistance / ComputeBilateralFilter,
+// hpc/affinity.c:129-262,115-122,59-113 (photometric :8-17, spatial :19-57).
+//
+// Layout choices (B200-first, not the reference's):
+//   * K_B is stored TRANSPOSED (one row per pixel, samples contiguous): it is the K-major "A" operand
+//     of the extrapolation GEMM (nystroem_gemm.cu) and each pixel row is one 16-byte-vector store target.
+//   * every band pixel gets a row, sample pixels included: their rows of Phi are overwritten with the
+//     eigenvectors afterwards, which removes the reference's Permutation pass (hpc/utils.c:134-173), and
+//     the row sum over ALL pixels is exactly rowsum(K_A) + rowsum(K_B) (hpc/laplacian.c:18-20).
+//   * coordinates and grey values are integers: differences are exact in fp32, the two bandwidth
+//     factors are applied to the exact squared distances, one ex2 per pair (the reference takes two exps
+//     and multiplies, hpc/affinity.c:99,107,110 -- equal up to rounding).
+#include "common.cuh"
+
+#define AFF_THREADS 256
+#define AFF_TP 512               // pixels per tile
+#define AFF_PPT (AFF_TP / 32)    // pixels per thread per 64-sample chunk
+
+// sample features, SoA: [0] row, [1] col, [2..2+C) values; padded samples carry 1e18 so that K == 0
+__global__ void k_sample_features(const uint8_t* __restrict__ img, const uint32_t* __restrict__ samples, int p, int p_pad,
+                                  int width, int channels, float* __restrict__ sf)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p_pad) return;
+    if (i < p) {
+        uint32_t q = samples[i];
+        sf[i] = (float)(q / width);
+        sf[p_pad + i] = (float)(q % width);
+        for (int ch = 0; ch < channels; ++ch) sf[(2 + ch) * p_pad + i] = (float)img[(size_t)q * channels + ch];
+    } else {
+        for (int k = 0; k < 2 + channels; ++k) sf[k * p_pad + i] = 1e18f;
+    }
+}
+
+// K_A in fp64 exactly as the reference writes it: exp(-d2/h_loc^2) * exp(-dv2/h_val^2)
+template <int KIND, int C>
+__global__ void k_affinity_A(const uint8_t* __restrict__ img, const uint32_t* __restrict__ samples, int p, int width,
+                             double inv_hl2, double inv_hv2, double* __restrict__ KA)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= p) return;
+    uint32_t a = samples[i], b = samples[j];
+    double k = 1.0;
+    if (KIND != GL_PHOTOMETRIC) {
+        double dr = (double)(a / width) - (double)(b / width), dc = (double)(a % width) - (double)(b % width);
+        k *= exp(-(dr * dr + dc * dc) * inv_hl2);
+    }
+    if (KIND != GL_SPATIAL) {
+        double d2 = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            double dv = (double)img[(size_t)a * C + ch] - (double)img[(size_t)b * C + ch];
+            d2 += dv * dv;
+        }
+        k *= exp(-d2 * inv_hv2);
+    }
+    KA[(size_t)i * p + j] = k;
+}
+
+// K_B tile kernel.  Thread (tx = tid % 8, ty = tid / 8): 8 consecutive samples of the current 64-sample
+// chunk x pixels ty, ty+32, ... of the tile.  A warp stores 4 pixel rows x 128 contiguous bytes.
+template <int KIND, int C>
+__global__ void __launch_bounds__(AFF_THREADS, 2)
+k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int p_pad, int width, int64_t q0, int64_t q1,
+             float a2, float b2,  // -log2(e)/h_loc^2, -log2(e)/h_val^2
+             __half* __restrict__ KB, float* __restrict__ partial /* [gridDim.x][p_pad] */)
+{
+    extern __shared__ float aff_smem[];
+    float* cta_sum = aff_smem;                 // [p_pad]
+    float* ws = cta_sum + p_pad;               // [2][8 warps][64]
+    float* px = ws + 2 * 8 * 64;               // [(2 + C)][AFF_TP] pixel features
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3, lane = tid & 31, warp = tid >> 5;
+    const int chunks = p_pad >> 6;
+    for (int i = tid; i < p_pad; i += AFF_THREADS) cta_sum[i] = 0.f;
+
+    const int64_t n_band = q1 - q0;
+    const int64_t tiles = (n_band + AFF_TP - 1) / AFF_TP;
+    int flip = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t base = q0 + tile * AFF_TP;
+        __syncthreads();  // previous tile's readers of px are done
+        for (int i = tid; i < AFF_TP; i += AFF_THREADS) {
+            int64_t q = base + i;
+            bool in = q < q1;
+            int64_t qq = in ? q : q1 - 1;
+            px[i] = (float)(qq / width);
+            px[AFF_TP + i] = (float)(qq % width);
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) px[(2 + ch) * AFF_TP + i] = (float)img[(size_t)qq * C + ch];
+        }
+        __syncthreads();
+        for (int ck = 0; ck < chunks; ++ck) {
+            const int s0 = (ck << 6) + (tx << 3);
+            float sr[8], sc[8], sv[C][8];
+            if (KIND != GL_PHOTOMETRIC) {
+                *(float4*)&sr[0] = *(const float4*)&sf[s0];
+                *(float4*)&sr[4] = *(const float4*)&sf[s0 + 4];
+                *(float4*)&sc[0] = *(const float4*)&sf[p_pad + s0];
+                *(float4*)&sc[4] = *(const float4*)&sf[p_pad + s0 + 4];
+            }
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                *(float4*)&sv[ch][0] = *(const float4*)&sf[(2 + ch) * p_pad + s0];
+                *(float4*)&sv[ch][4] = *(const float4*)&sf[(2 + ch) * p_pad + s0 + 4];
+            }
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 2
+            for (int i = 0; i < AFF_PPT; ++i) {
+                const int pi = ty + (i << 5);
+                const int64_t q = base + pi;
+                const float pr = px[pi], pc = px[AFF_TP + pi];
+                float pv[C];
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) pv[ch] = px[(2 + ch) * AFF_TP + pi];
+                float kv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float x = 0.f;
+                    if (KIND != GL_SPATIAL) {
+                        float d = pv[0] - sv[0][k];
+                        float t = d * d;
+#pragma unroll
+                        for (int ch = 1; ch < C; ++ch) {
+                            d = pv[ch] - sv[ch][k];
+                            t = fmaf(d, d, t);
+                        }
+                        x = t * b2;
+                    }
+                    if (KIND != GL_PHOTOMETRIC) {
+                        float dr = pr - sr[k], dc = pc - sc[k];
+                        float t = fmaf(dc, dc, dr * dr);
+                        x = fmaf(t, a2, x);
+                    }
+                    kv[k] = fast_exp2(x);
+                }
+                if (q < q1) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] += kv[k];
+                    __half2 h0 = __floats2half2_rn(kv[0], kv[1]), h1 = __floats2half2_rn(kv[2], kv[3]);
+                    __half2 h2 = __floats2half2_rn(kv[4], kv[5]), h3 = __floats2half2_rn(kv[6], kv[7]);
+                    uint4 pk;
+                    pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+                    *(uint4*)&KB[(size_t)(q - q0) * p_pad + s0] = pk;
+                }
+            }
+            // row sums: fixed-order reduction (deterministic): lanes sharing tx, then the 8 warps
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+                acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+            }
+            float* w = ws + flip * 512;
+            if (lane < 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[warp * 64 + (lane << 3) + k] = acc[k];
+            }
+            __syncthreads();
+            if (tid < 64) {
+                float s = 0.f;
+#pragma unroll
+                for (int wi = 0; wi < 8; ++wi) s += w[wi * 64 + tid];
+                cta_sum[(ck << 6) + tid] += s;
+            }
+            flip ^= 1;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < p_pad; i += AFF_THREADS) partial[(size_t)blockIdx.x * p_pad + i] = cta_sum[i];
+}
+
+__global__ void k_reduce_partials(const float* __restrict__ partial, int nblocks, int p_pad, int p, double* __restrict__ D)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p) return;
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += (double)partial[(size_t)b * p_pad + s];
+    D[s] = acc;
+}
+
+template <int KIND, int C>
+static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float* sf, double* KA, __half* KB, float* partial,
+                           int grid)
+{
+    const int p = (int)ctx->p, p_pad = ctx->p_pad;
+    dim3 ga((unsigned)ceil_div(p, 128), (unsigned)p);
+    k_affinity_A<KIND, C><<<ga, 128, 0, ctx->stream>>>((const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p,
+                                                      ctx->width, 1.0 / (h_loc * h_loc), 1.0 / (h_val * h_val), KA);
+    GL_LAUNCH_CHECK(ctx);
+    const size_t smem = sizeof(float) * ((size_t)p_pad + 2 * 8 * 64 + (size_t)(2 + C) * AFF_TP);
+    GL_CUDA_CHECK(cudaFuncSetAttribute(k_affinity_B<KIND, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const float log2e = 1.4426950408889634f;
+    k_affinity_B<KIND, C><<<grid, AFF_THREADS, smem, ctx->stream>>>(
+        (const uint8_t*)ctx->img->ptr, sf, p_pad, ctx->width, ctx->q0, ctx->q1, (float)(-log2e / (h_loc * h_loc)),
+        (float)(-log2e / (h_val * h_val)), KB, partial);
+    GL_LAUNCH_CHECK(ctx);
+    return GL_OK;
+}
+
+int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A_out, gl_mat** K_B_out)
+{
+    const int p = (int)ctx->p, p_pad = ctx->p_pad, C = ctx->channels;
+    const int64_t n_band = ctx->q1 - ctx->q0;
+    GL_REQUIRE(p_pad <= 16384, "affinity: p = %d too large", p);
+
+    gl_mat* KA = gl_mat_new(ctx, GL_MAT_KA);
+    gl_mat* KB = gl_mat_new(ctx, GL_MAT_KB);
+    gl_buf *sf = nullptr, *partial = nullptr;
+    const int grid = ctx->sm_count * 2;
+    int rc = GL_OK;
+    do {
+        KA->rows = KA->cols = KA->local_rows = p;
+        KA->ld = p;
+        KA->elem_bytes = 8;
+        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)p * p, &KA->buf)) != GL_OK) break;
+        KB->rows = p;                   // logical K_B: p x (n - p); stored transposed for the whole band
+        KB->cols = ctx->n - p;
+        KB->local_rows = n_band;
+        KB->ld = p_pad;
+        KB->elem_bytes = 2;
+        KB->p = p;
+        KB->p_pad = p_pad;
+        KB->q0 = ctx->q0;
+        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)n_band * p_pad, &KB->buf)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)p_pad, &KB->aux)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_pad, &sf)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * p_pad, &partial)) != GL_OK) break;
+
+        k_sample_features<<<(unsigned)ceil_div(p_pad, 256), 256, 0, ctx->stream>>>(
+            (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p, p_pad, ctx->width, C, (float*)sf->ptr);
+        ctx->launches++;
+
+#define AFF_CASE(K, CC)                                                                                              \
+    if (kind == K && C == CC)                                                                                        \
+        rc = launch_affinity<K, CC>(ctx, h_loc, h_val, (const float*)sf->ptr, (double*)KA->buf->ptr, (__half*)KB->buf->ptr, \
+                                    (float*)partial->ptr, grid);
+        AFF_CASE(GL_BILATERAL, 1) else AFF_CASE(GL_BILATERAL, 3) else AFF_CASE(GL_PHOTOMETRIC, 1)
+        else AFF_CASE(GL_PHOTOMETRIC, 3) else AFF_CASE(GL_SPATIAL, 1) else AFF_CASE(GL_SPATIAL, 3)
+#undef AFF_CASE
+        if (rc != GL_OK) break;
+
+        k_reduce_partials<<<(unsigned)ceil_div(p, 128), 128, 0, ctx->stream>>>((const float*)partial->ptr, grid, p_pad, p,
+                                                                               (double*)KB->aux->ptr);
+        GL_LAUNCH_CHECK(ctx);
+        // one p-double allreduce of the band-partial row sums
+        if ((rc = gl_allreduce_f64(ctx, (double*)KB->aux->ptr, (size_t)p)) != GL_OK) break;
+    } while (0);
+    if (sf) gl_buf_release(sf);
+    if (partial) gl_buf_release(partial);
+    if (rc != GL_OK) {
+        gl_mat_destroy(KA);
+        gl_mat_destroy(KB);
+        return rc;
+    }
+    *K_A_out = KA;
+    *K_B_out = KB;
+    return GL_OK;
+}

@@ -1,0 +1,697 @@
+// Context, allocator, matrix handles, image upload and the one-call pipeline of libglcuda.so.
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void gl_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (getenv("GLB200_VERBOSE")) fprintf(stderr, "[libglcuda] %s\n", g_err);
+}
+
+extern "C" {
+
+int gl_version(void) { return 100; }
+const char* gl_last_error(void) { return g_err; }
+
+void gl_default_params(gl_params* p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->affinity_kind = GL_BILATERAL;
+    p->h_loc = 40.0;
+    p->h_val = 30.0;
+    p->sampling_random = 0;
+    p->seed = 0;
+    p->sample_size = 0;
+    p->num_eigvals = -1;
+    p->gain = 3.0;
+    p->power = 1.0;
+    p->gram_schmidt = 0;
+    p->clip_low = 0;
+}
+
+int gl_device_count(int* count)
+{
+    GL_REQUIRE(count, "gl_device_count: null");
+    int n = 0;
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        gl_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return GL_ERR_CUDA;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ++ok;
+    }
+    *count = ok;
+    return GL_OK;
+}
+
+int gl_kernel_launches(gl_ctx* ctx, long long* count)
+{
+    GL_REQUIRE(ctx && count, "gl_kernel_launches: null");
+    *count = ctx->launches;
+    return GL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
+{
+    GL_REQUIRE(out, "gl_ctx_create: null out");
+    GL_REQUIRE(world >= 1 && rank >= 0 && rank < world, "gl_ctx_create: bad rank %d / world %d", rank, world);
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        gl_set_error("no CUDA device (%s); libglcuda has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count 0");
+        return GL_ERR_CUDA;
+    }
+    GL_REQUIRE(device >= 0 && device < n, "gl_ctx_create: device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    GL_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        gl_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return GL_ERR_CUDA;
+    }
+    GL_CUDA_CHECK(cudaSetDevice(device));
+    gl_ctx* ctx = new gl_ctx();
+    ctx->device = device;
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->sm_count = prop.multiProcessorCount;
+    GL_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < GL_T_COUNT; ++i) {
+        GL_CUDA_CHECK(cudaEventCreate(&ctx->ev_begin[i]));
+        GL_CUDA_CHECK(cudaEventCreate(&ctx->ev_end[i]));
+    }
+    const char* v = getenv("GLB200_VERBOSE");
+    ctx->verbose = v ? atoi(v) : 0;
+    if (const char* g = getenv("GLB200_GEMM")) gl_ctx_set_option(ctx, "gemm", g);
+    if (const char* g = getenv("GLB200_CTA_GROUP")) gl_ctx_set_option(ctx, "cta_group", g);
+    *out = ctx;
+    return GL_OK;
+}
+
+int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
+{
+    GL_REQUIRE(ctx && key && value, "gl_ctx_set_option: null");
+    if (!strcmp(key, "gemm")) {
+        if (!strcmp(value, "tcgen05")) ctx->gemm_impl = 0;
+        else if (!strcmp(value, "simple")) ctx->gemm_impl = 1;
+        else GL_REQUIRE(false, "option gemm: want tcgen05|simple, got %s", value);
+    } else if (!strcmp(key, "cta_group")) {
+        int g = atoi(value);
+        GL_REQUIRE(g == 1 || g == 2, "option cta_group: want 1|2");
+        ctx->gemm_cta_group = g;
+    } else if (!strcmp(key, "jacobi_max_sweeps")) {
+        ctx->jacobi_max_sweeps = atoi(value);
+    } else if (!strcmp(key, "jacobi_tol")) {
+        ctx->jacobi_tol = (float)atof(value);
+    } else if (!strcmp(key, "verbose")) {
+        ctx->verbose = atoi(value);
+    } else {
+        GL_REQUIRE(false, "unknown option %s", key);
+    }
+    return GL_OK;
+}
+
+int gl_ctx_sync(gl_ctx* ctx)
+{
+    GL_REQUIRE(ctx, "gl_ctx_sync: null");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_ctx_destroy(gl_ctx* ctx)
+{
+    if (!ctx) return GL_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    gl_comm_destroy(ctx);
+    if (ctx->img) gl_buf_release(ctx->img);
+    if (ctx->samples) gl_buf_release(ctx->samples);
+    for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+    ctx->free_blocks.clear();
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < GL_T_COUNT; ++i) {
+        cudaEventDestroy(ctx->ev_begin[i]);
+        cudaEventDestroy(ctx->ev_end[i]);
+    }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GL_OK;
+}
+
+int gl_ctx_stage_ms(gl_ctx* ctx, float* ms)
+{
+    GL_REQUIRE(ctx && ms, "gl_ctx_stage_ms: null");
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < GL_T_COUNT; ++i) {
+        ms[i] = 0.f;
+        if (ctx->ev_valid[i]) cudaEventElapsedTime(&ms[i], ctx->ev_begin[i], ctx->ev_end[i]);
+    }
+    return GL_OK;
+}
+
+int gl_host_alloc(void** p, size_t bytes)
+{
+    GL_REQUIRE(p, "gl_host_alloc: null");
+    GL_CUDA_CHECK(cudaMallocHost(p, bytes));
+    return GL_OK;
+}
+int gl_host_free(void* p)
+{
+    if (p) GL_CUDA_CHECK(cudaFreeHost(p));
+    return GL_OK;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------
+// allocator: blocks go back to a size-keyed cache; a request is served by the smallest cached
+// block within 12.5 % of the size, so a steady-state pipeline never calls cudaMalloc/cudaFree.
+// -------------------------------------------------------------------------------------------
+int gl_alloc(gl_ctx* ctx, size_t bytes, gl_buf** out)
+{
+    *out = nullptr;
+    if (bytes == 0) bytes = 256;
+    bytes = (size_t)round_up((int64_t)bytes, 512);
+    void* p = nullptr;
+    size_t got = bytes;
+    auto it = ctx->free_blocks.lower_bound(bytes);
+    if (it != ctx->free_blocks.end() && it->first <= bytes + bytes / 8 + 4096) {
+        p = it->second;
+        got = it->first;
+        ctx->bytes_cached -= got;
+        ctx->free_blocks.erase(it);
+    } else {
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            // drop the cache and retry once
+            (void)cudaGetLastError();
+            cudaStreamSynchronize(ctx->stream);
+            for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+            ctx->free_blocks.clear();
+            ctx->bytes_cached = 0;
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            gl_set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return GL_ERR_NOMEM;
+        }
+    }
+    gl_buf* b = new gl_buf();
+    b->ptr = p;
+    b->bytes = got;
+    b->owner = ctx;
+    ctx->bytes_live += got;
+    *out = b;
+    return GL_OK;
+}
+
+void gl_buf_release(gl_buf* b)
+{
+    if (!b) return;
+    if (--b->refs > 0) return;
+    gl_ctx* ctx = b->owner;
+    // stream-ordered reuse: every consumer of this library runs on ctx->stream
+    ctx->free_blocks.emplace(b->bytes, b->ptr);
+    ctx->bytes_cached += b->bytes;
+    ctx->bytes_live -= b->bytes;
+    delete b;
+}
+
+int gl_ensure_pinned(gl_ctx* ctx, size_t bytes)
+{
+    if (ctx->pinned_bytes >= bytes) return GL_OK;
+    if (ctx->pinned) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+    }
+    size_t want = (size_t)round_up((int64_t)bytes, 1 << 16);
+    GL_CUDA_CHECK(cudaMallocHost(&ctx->pinned, want));
+    ctx->pinned_bytes = want;
+    return GL_OK;
+}
+
+gl_mat* gl_mat_new(gl_ctx* ctx, int kind)
+{
+    gl_mat* m = new gl_mat();
+    m->kind = kind;
+    m->ctx = ctx;
+    return m;
+}
+
+// -------------------------------------------------------------------------------------------
+// image
+// -------------------------------------------------------------------------------------------
+static int set_image_geometry(gl_ctx* ctx, int width, int height, int channels)
+{
+    GL_REQUIRE(width > 1 && height > 1, "image %dx%d too small", width, height);
+    GL_REQUIRE(channels == 1 || channels == 3, "channels must be 1 or 3, got %d", channels);
+    GL_REQUIRE((int64_t)width * height < (int64_t)0x7fffffff, "image too large for 32-bit raster indices");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const int64_t n = (int64_t)width * height;
+    if (!ctx->img || ctx->img->bytes < (size_t)(n * channels)) {
+        if (ctx->img) gl_buf_release(ctx->img);
+        ctx->img = nullptr;
+        GL_CHECK(gl_alloc(ctx, (size_t)(n * channels), &ctx->img));
+    }
+    ctx->width = width;
+    ctx->height = height;
+    ctx->channels = channels;
+    ctx->n = n;
+    // contiguous bands of whole image rows
+    ctx->row0 = (int)((int64_t)height * ctx->rank / ctx->world);
+    ctx->row1 = (int)((int64_t)height * (ctx->rank + 1) / ctx->world);
+    ctx->q0 = (int64_t)ctx->row0 * width;
+    ctx->q1 = (int64_t)ctx->row1 * width;
+    return GL_OK;
+}
+
+extern "C" {
+
+int gl_set_image(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channels)
+{
+    GL_REQUIRE(ctx && pixels, "gl_set_image: null");
+    GL_CHECK(set_image_geometry(ctx, width, height, channels));
+    StageTimer t(ctx, GL_T_H2D);
+    GL_CUDA_CHECK(cudaMemcpyAsync(ctx->img->ptr, pixels, (size_t)(ctx->n * channels), cudaMemcpyHostToDevice, ctx->stream));
+    return GL_OK;
+}
+
+int gl_set_image_rows(gl_ctx* ctx, const uint8_t* const* rows, int width, int height)
+{
+    GL_REQUIRE(ctx && rows, "gl_set_image_rows: null");
+    GL_CHECK(set_image_geometry(ctx, width, height, 1));
+    GL_CHECK(gl_ensure_pinned(ctx, (size_t)ctx->n));
+    // the pinned block may still be the source of an earlier async copy
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < height; ++r) memcpy((uint8_t*)ctx->pinned + (size_t)r * width, rows[r], (size_t)width);
+    StageTimer t(ctx, GL_T_H2D);
+    GL_CUDA_CHECK(cudaMemcpyAsync(ctx->img->ptr, ctx->pinned, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    return GL_OK;
+}
+
+int gl_set_synthetic_image(gl_ctx* ctx, int width, int height, int channels, uint32_t seed)
+{
+    GL_REQUIRE(ctx, "gl_set_synthetic_image: null");
+    GL_CHECK(set_image_geometry(ctx, width, height, channels));
+    return gl_impl_synthetic(ctx, seed);
+}
+
+int gl_get_image(gl_ctx* ctx, uint8_t* out)
+{
+    GL_REQUIRE(ctx && out && ctx->img && ctx->n > 0, "gl_get_image: no image");
+    GL_CUDA_CHECK(cudaMemcpyAsync(out, ctx->img->ptr, (size_t)(ctx->n * ctx->channels), cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_get_band(gl_ctx* ctx, int* row0, int* row1)
+{
+    GL_REQUIRE(ctx && row0 && row1 && ctx->n > 0, "gl_get_band: no image");
+    *row0 = ctx->row0;
+    *row1 = ctx->row1;
+    return GL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// samples
+// -------------------------------------------------------------------------------------------
+int gl_sampling_uniform(gl_ctx* ctx, unsigned requested, unsigned* actual)
+{
+    GL_REQUIRE(ctx && ctx->n > 0, "gl_sampling_uniform: set an image first");
+    GL_REQUIRE(requested >= 1, "gl_sampling_uniform: requested must be >= 1");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_SAMPLING);
+    return gl_impl_sampling_uniform(ctx, requested, actual);
+}
+
+int gl_sampling_random(gl_ctx* ctx, unsigned requested, uint32_t seed, unsigned* actual)
+{
+    GL_REQUIRE(ctx && ctx->n > 0, "gl_sampling_random: set an image first");
+    GL_REQUIRE(requested >= 1 && (int64_t)requested <= ctx->n, "gl_sampling_random: requested out of range");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_SAMPLING);
+    return gl_impl_sampling_random(ctx, requested, seed, actual);
+}
+
+int gl_set_samples(gl_ctx* ctx, const uint32_t* indices, unsigned count)
+{
+    GL_REQUIRE(ctx && indices && ctx->n > 0, "gl_set_samples: set an image first");
+    GL_REQUIRE(count >= 2, "gl_set_samples: need at least 2 samples");
+    for (unsigned i = 0; i < count; ++i) {
+        GL_REQUIRE((int64_t)indices[i] < ctx->n, "gl_set_samples: index %u out of range", indices[i]);
+        GL_REQUIRE(i == 0 || indices[i] > indices[i - 1], "gl_set_samples: indices must be strictly ascending");
+    }
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const int p_pad = (int)round_up(count, 64);
+    if (ctx->samples) gl_buf_release(ctx->samples);
+    ctx->samples = nullptr;
+    GL_CHECK(gl_alloc(ctx, sizeof(uint32_t) * p_pad, &ctx->samples));
+    GL_CHECK(gl_ensure_pinned(ctx, sizeof(uint32_t) * p_pad));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    uint32_t* h = (uint32_t*)ctx->pinned;
+    memcpy(h, indices, sizeof(uint32_t) * count);
+    for (int i = count; i < p_pad; ++i) h[i] = 0xffffffffu;
+    GL_CUDA_CHECK(cudaMemcpyAsync(ctx->samples->ptr, h, sizeof(uint32_t) * p_pad, cudaMemcpyHostToDevice, ctx->stream));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->p = count;
+    ctx->p_pad = p_pad;
+    return GL_OK;
+}
+
+int gl_get_samples(gl_ctx* ctx, uint32_t* out, unsigned cap, unsigned* count)
+{
+    GL_REQUIRE(ctx && ctx->samples && ctx->p > 0, "gl_get_samples: no samples");
+    if (count) *count = ctx->p;
+    if (out) {
+        unsigned k = cap < ctx->p ? cap : ctx->p;
+        GL_CUDA_CHECK(cudaMemcpyAsync(out, ctx->samples->ptr, sizeof(uint32_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
+        GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    return GL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// stage entry points (argument checks; the work is in the per-stage files)
+// -------------------------------------------------------------------------------------------
+int gl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A, gl_mat** K_B)
+{
+    GL_REQUIRE(ctx && K_A && K_B, "gl_affinity: null");
+    GL_REQUIRE(ctx->n > 0 && ctx->p >= 2, "gl_affinity: need an image and samples first");
+    GL_REQUIRE(kind >= GL_BILATERAL && kind <= GL_SPATIAL, "gl_affinity: bad kind %d", kind);
+    GL_REQUIRE(h_loc > 0 && h_val > 0, "gl_affinity: bandwidths must be positive");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_AFFINITY);
+    return gl_impl_affinity(ctx, kind, h_loc, h_val, K_A, K_B);
+}
+
+int gl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A, gl_mat** L_B)
+{
+    GL_REQUIRE(ctx && K_A && K_B && L_A && L_B, "gl_laplacian: null");
+    GL_REQUIRE(K_A->kind == GL_MAT_KA && K_B->kind == GL_MAT_KB, "gl_laplacian: wrong handle kinds");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_LAPLACIAN);
+    return gl_impl_laplacian(ctx, K_A, K_B, L_A, L_B);
+}
+
+int gl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv)
+{
+    GL_REQUIRE(ctx && L_A, "gl_eigensolve: null");
+    GL_REQUIRE(L_A->kind == GL_MAT_KA && L_A->rows == L_A->cols, "gl_eigensolve: want a square p x p matrix");
+    if (m < 0 || m >= L_A->rows) m = (int)L_A->rows - 1;  // hpc/image_processing.c:102-106
+    GL_REQUIRE(m >= 1, "gl_eigensolve: m must be >= 1");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_EIGEN);
+    return gl_impl_eigensolve(ctx, L_A, m, eigvecs, eigvals, eigvals_inv);
+}
+
+int gl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi)
+{
+    GL_REQUIRE(ctx && L_B && phi_A && eigvals_inv && phi, "gl_nystroem: null");
+    GL_REQUIRE(L_B->kind == GL_MAT_KB && phi_A->kind == GL_MAT_EIGVEC && eigvals_inv->kind == GL_MAT_DIAG,
+               "gl_nystroem: wrong handle kinds");
+    GL_REQUIRE(phi_A->rows == L_B->p && eigvals_inv->rows == phi_A->cols, "gl_nystroem: shape mismatch");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_NYSTROEM);
+    return gl_impl_nystroem(ctx, L_B, phi_A, eigvals_inv, phi);
+}
+
+int gl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
+{
+    GL_REQUIRE(ctx && phi && phi->kind == GL_MAT_PHI, "gl_orthonormalise: want a Phi handle");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_GRAM_SCHMIDT);
+    return gl_impl_orthonormalise(ctx, phi, norms_out);
+}
+
+int gl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip_low, float* z_f32, uint8_t* z_u8)
+{
+    GL_REQUIRE(ctx && phi && f_eigvals, "gl_filter: null");
+    GL_REQUIRE(phi->kind == GL_MAT_PHI && f_eigvals->kind == GL_MAT_DIAG, "gl_filter: wrong handle kinds");
+    GL_REQUIRE(f_eigvals->rows == phi->m, "gl_filter: %lld eigenvalues for %d columns", (long long)f_eigvals->rows, phi->m);
+    GL_REQUIRE(phi->q0 == ctx->q0 && phi->local_rows == ctx->q1 - ctx->q0, "gl_filter: Phi does not belong to the current image");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return gl_impl_filter(ctx, phi, f_eigvals, gain, clip_low, z_f32, z_u8);
+}
+
+int gl_diag_inverse(gl_ctx* ctx, gl_mat* d, gl_mat** out)
+{
+    GL_REQUIRE(ctx && d && out && d->kind == GL_MAT_DIAG, "gl_diag_inverse: want a diagonal handle");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return gl_impl_diag_map(ctx, d, 0, 0.0, out);
+}
+
+int gl_diag_pow(gl_ctx* ctx, gl_mat* d, double power, gl_mat** out)
+{
+    GL_REQUIRE(ctx && d && out && d->kind == GL_MAT_DIAG, "gl_diag_pow: want a diagonal handle");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return gl_impl_diag_map(ctx, d, 1, power, out);
+}
+
+// -------------------------------------------------------------------------------------------
+// matrices
+// -------------------------------------------------------------------------------------------
+int gl_mat_info_get(const gl_mat* m, gl_mat_info* info)
+{
+    GL_REQUIRE(m && info, "gl_mat_info_get: null");
+    info->kind = m->kind;
+    info->rows = m->rows;
+    info->cols = m->cols;
+    info->local_rows = m->local_rows;
+    info->ld = m->ld;
+    info->elem_bytes = m->elem_bytes;
+    if (!m->scale_on_host && m->dscale) {
+        gl_mat* mm = const_cast<gl_mat*>(m);
+        GL_CUDA_CHECK(cudaSetDevice(m->ctx->device));
+        GL_CUDA_CHECK(cudaMemcpyAsync(&mm->scale, m->dscale->ptr, sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+        GL_CUDA_CHECK(cudaStreamSynchronize(m->ctx->stream));
+        mm->scale_on_host = true;
+    }
+    info->scale = m->scale;
+    return GL_OK;
+}
+
+int gl_mat_retain(gl_mat* m)
+{
+    GL_REQUIRE(m, "gl_mat_retain: null");
+    m->refs++;
+    return GL_OK;
+}
+
+int gl_mat_destroy(gl_mat* m)
+{
+    if (!m) return GL_OK;
+    if (--m->refs > 0) return GL_OK;
+    if (m->buf) gl_buf_release(m->buf);
+    if (m->aux) gl_buf_release(m->aux);
+    if (m->dscale) gl_buf_release(m->dscale);
+    delete m;
+    return GL_OK;
+}
+
+}  // extern "C"
+
+// conversion kernels for gl_mat_download / gl_mat_upload
+__global__ void k_half_to_f64(const __half* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, double scale,
+                              double* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    int64_t r = i / cols, c = i % cols;
+    dst[i] = scale * (double)__half2float(src[r * ld + c]);
+}
+__global__ void k_bf16_to_f64(const __nv_bfloat16* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, double scale,
+                              double* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    int64_t r = i / cols, c = i % cols;
+    dst[i] = scale * (double)__bfloat162float(src[r * ld + c]);
+}
+__global__ void k_colmajor_f32_to_f64(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols,
+                                      double* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    int64_t r = i / cols, c = i % cols;
+    dst[i] = (double)src[c * ld + r];
+}
+__global__ void k_f64_to_colmajor_f32(const double* __restrict__ src, int64_t rows, int64_t cols, int64_t ld,
+                                      float* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    int64_t r = i / cols, c = i % cols;
+    dst[c * ld + r] = (float)src[i];
+}
+__global__ void k_scale_f64(const double* __restrict__ src, int64_t count, double scale, double* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = scale * src[i];
+}
+
+extern "C" {
+
+int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap)
+{
+    GL_REQUIRE(ctx && m && out, "gl_mat_download: null");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    int64_t rows = m->rows, cols = m->cols;
+    if (m->kind == GL_MAT_KB) { rows = m->local_rows; cols = m->p; }
+    if (m->kind == GL_MAT_PHI) { rows = m->local_rows; cols = m->m; }
+    if (m->kind == GL_MAT_DIAG) cols = 1;
+    const int64_t count = rows * cols;
+    GL_REQUIRE((size_t)count <= cap, "gl_mat_download: need room for %lld doubles, got %zu", (long long)count, cap);
+    if (!m->scale_on_host) {
+        gl_mat_info tmp_info;
+        GL_CHECK(gl_mat_info_get(m, &tmp_info));
+    }
+    gl_buf* tmp = nullptr;
+    GL_CHECK(gl_alloc(ctx, sizeof(double) * (size_t)count, &tmp));
+    const int T = 256;
+    const unsigned blocks = (unsigned)ceil_div(count, T);
+    double* d = (double*)tmp->ptr;
+    switch (m->kind) {
+    case GL_MAT_KA:
+    case GL_MAT_DIAG:
+        k_scale_f64<<<blocks, T, 0, ctx->stream>>>((const double*)m->buf->ptr, count, m->scale, d);
+        break;
+    case GL_MAT_KB:
+        k_half_to_f64<<<blocks, T, 0, ctx->stream>>>((const __half*)m->buf->ptr, m->ld, rows, cols, m->scale, d);
+        break;
+    case GL_MAT_PHI:
+        k_bf16_to_f64<<<blocks, T, 0, ctx->stream>>>((const __nv_bfloat16*)m->buf->ptr, m->ld, rows, cols, m->scale, d);
+        break;
+    case GL_MAT_EIGVEC:
+        k_colmajor_f32_to_f64<<<blocks, T, 0, ctx->stream>>>((const float*)m->buf->ptr, m->ld, rows, cols, d);
+        break;
+    default:
+        gl_buf_release(tmp);
+        GL_REQUIRE(false, "gl_mat_download: bad kind %d", m->kind);
+    }
+    GL_LAUNCH_CHECK(ctx);
+    GL_CUDA_CHECK(cudaMemcpyAsync(out, d, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    gl_buf_release(tmp);
+    return GL_OK;
+}
+
+int gl_mat_rowsums(gl_ctx* ctx, const gl_mat* K_B, double* out, size_t cap)
+{
+    GL_REQUIRE(ctx && K_B && out && K_B->kind == GL_MAT_KB && K_B->aux, "gl_mat_rowsums: want a K_B handle");
+    GL_REQUIRE(cap >= (size_t)K_B->p, "gl_mat_rowsums: need room for %d doubles", K_B->p);
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    GL_CUDA_CHECK(cudaMemcpyAsync(out, K_B->aux->ptr, sizeof(double) * K_B->p, cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_mat_upload(gl_ctx* ctx, int kind, const double* data, int64_t rows, int64_t cols, gl_mat** out)
+{
+    GL_REQUIRE(ctx && data && out, "gl_mat_upload: null");
+    GL_REQUIRE(rows > 0 && cols > 0, "gl_mat_upload: empty");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const int64_t count = rows * cols;
+    gl_buf* stage = nullptr;
+    GL_CHECK(gl_alloc(ctx, sizeof(double) * (size_t)count, &stage));
+    GL_CUDA_CHECK(cudaMemcpyAsync(stage->ptr, data, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // `data` may be pageable and freed by the caller
+    gl_mat* m = gl_mat_new(ctx, kind);
+    m->rows = rows;
+    m->cols = cols;
+    m->local_rows = rows;
+    if (kind == GL_MAT_KA) {
+        GL_REQUIRE(rows == cols, "gl_mat_upload: K_A/L_A must be square");
+        m->buf = stage;
+        m->ld = cols;
+        m->elem_bytes = 8;
+    } else if (kind == GL_MAT_DIAG) {
+        GL_REQUIRE(cols == 1, "gl_mat_upload: diagonal is rows x 1");
+        m->buf = stage;
+        m->ld = 1;
+        m->elem_bytes = 8;
+    } else if (kind == GL_MAT_EIGVEC) {
+        m->ld = round_up(rows, 4);
+        m->elem_bytes = 4;
+        int rc = gl_alloc(ctx, sizeof(float) * (size_t)(m->ld * cols), &m->buf);
+        if (rc != GL_OK) { gl_buf_release(stage); delete m; return rc; }
+        cudaMemsetAsync(m->buf->ptr, 0, sizeof(float) * (size_t)(m->ld * cols), ctx->stream);
+        k_f64_to_colmajor_f32<<<(unsigned)ceil_div(count, 256), 256, 0, ctx->stream>>>((const double*)stage->ptr, rows, cols,
+                                                                                      m->ld, (float*)m->buf->ptr);
+        GL_LAUNCH_CHECK(ctx);
+        gl_buf_release(stage);
+    } else {
+        gl_buf_release(stage);
+        delete m;
+        GL_REQUIRE(false, "gl_mat_upload: kind %d cannot be uploaded", kind);
+    }
+    *out = m;
+    return GL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// whole path: the stage order of hpc/image_processing.c:183-275 (restored block)
+// -------------------------------------------------------------------------------------------
+int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out,
+                    double* eigvals_out)
+{
+    GL_REQUIRE(ctx && prm, "gl_run_resident: null");
+    GL_REQUIRE(ctx->n > 0, "gl_run_resident: no image on the device");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaEventRecord(ctx->ev_begin[GL_T_TOTAL], ctx->stream);
+
+    unsigned requested = prm->sample_size ? prm->sample_size : (unsigned)((double)ctx->n * 0.01);  // image_processing.c:187
+    unsigned p = 0;
+    if (prm->sampling_random) GL_CHECK(gl_sampling_random(ctx, requested, prm->seed, &p));
+    else GL_CHECK(gl_sampling_uniform(ctx, requested, &p));
+
+    gl_mat *K_A = nullptr, *K_B = nullptr, *L_A = nullptr, *L_B = nullptr;
+    gl_mat *U = nullptr, *mu = nullptr, *mu_inv = nullptr, *phi = nullptr, *f_mu = nullptr;
+    int rc = GL_OK;
+    do {
+        if ((rc = gl_affinity(ctx, prm->affinity_kind, prm->h_loc, prm->h_val, &K_A, &K_B)) != GL_OK) break;
+        if ((rc = gl_laplacian(ctx, K_A, K_B, &L_A, &L_B)) != GL_OK) break;
+        gl_mat_destroy(K_A); K_A = nullptr;            // image_processing.c:210-211
+        gl_mat_destroy(K_B); K_B = nullptr;
+        if ((rc = gl_eigensolve(ctx, L_A, prm->num_eigvals, &U, &mu, &mu_inv)) != GL_OK) break;
+        gl_mat_destroy(L_A); L_A = nullptr;
+        if ((rc = gl_nystroem(ctx, L_B, U, mu_inv, &phi)) != GL_OK) break;
+        gl_mat_destroy(L_B); L_B = nullptr;
+        gl_mat_destroy(U); U = nullptr;
+        gl_mat_destroy(mu_inv); mu_inv = nullptr;
+        if (prm->gram_schmidt && (rc = gl_orthonormalise(ctx, phi, nullptr)) != GL_OK) break;
+        if ((rc = gl_diag_pow(ctx, mu, prm->power, &f_mu)) != GL_OK) break;  // MatPow(eigvals, .) as intended
+        if ((rc = gl_filter(ctx, phi, f_mu, prm->gain, prm->clip_low, z_f32, z_u8)) != GL_OK) break;
+        if (p_out) *p_out = p;
+        if (m_out) *m_out = (int)mu->rows;
+        if (eigvals_out) rc = gl_mat_download(ctx, mu, eigvals_out, (size_t)mu->rows);
+    } while (0);
+    gl_mat_destroy(K_A); gl_mat_destroy(K_B); gl_mat_destroy(L_A); gl_mat_destroy(L_B);
+    gl_mat_destroy(U); gl_mat_destroy(mu); gl_mat_destroy(mu_inv); gl_mat_destroy(phi); gl_mat_destroy(f_mu);
+    cudaEventRecord(ctx->ev_end[GL_T_TOTAL], ctx->stream);
+    ctx->ev_valid[GL_T_TOTAL] = true;
+    if (rc == GL_OK && (z_f32 || z_u8)) GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, const gl_params* prm, float* z_f32,
+           uint8_t* z_u8, unsigned* p_out, int* m_out, double* eigvals_out)
+{
+    GL_CHECK(gl_set_image(ctx, pixels, width, height, channels));
+    return gl_run_resident(ctx, prm, z_f32, z_u8, p_out, m_out, eigvals_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+// Internal definitions shared by the libglcuda.so translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "../../include/gl_cuda.h"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void gl_set_error(const char* fmt, ...);
+
+#define GL_CUDA_CHECK(expr)                                                                             \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            gl_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+            return GL_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+
+#define GL_CHECK(expr)                   \
+    do {                                 \
+        int _s = (expr);                 \
+        if (_s != GL_OK) return _s;      \
+    } while (0)
+
+#define GL_REQUIRE(cond, ...)            \
+    do {                                 \
+        if (!(cond)) {                   \
+            gl_set_error(__VA_ARGS__);   \
+            return GL_ERR_ARG;           \
+        }                                \
+    } while (0)
+
+#define GL_LAUNCH_CHECK(ctx)                                                                            \
+    do {                                                                                                \
+        (ctx)->launches++;                                                                              \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess) {                                                                        \
+            gl_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return GL_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+// padded column count of Phi / rows of W^T: 64, 128 or a multiple of 256, so that (m_pad / 8) 16-byte column
+// groups are either a power of two <= 32 or a whole number of warps (filter.cu), and GEMM N tiles are full.
+static inline int gl_m_pad(int m) { return m <= 64 ? 64 : (m <= 128 ? 128 : (int)round_up(m, 256)); }
+
+// ---------------------------------------------------------------------------------------------
+// refcounted device buffers + matrices
+// ---------------------------------------------------------------------------------------------
+struct gl_buf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int refs = 1;
+    gl_ctx* owner = nullptr;
+};
+
+struct gl_mat {
+    int kind = 0;
+    int64_t rows = 0, cols = 0;  // logical
+    int64_t local_rows = 0;      // band rows for KB/PHI
+    int64_t ld = 0;              // elements
+    int elem_bytes = 0;
+    double scale = 1.0;
+    gl_buf* buf = nullptr;       // main storage
+    gl_buf* aux = nullptr;       // KB: fp64 row sums D[p] (summed over ranks)
+    gl_buf* dscale = nullptr;    // optional device double holding `scale` (L_B: -alpha), so no host sync is needed
+    bool scale_on_host = true;   // false until the device value has been fetched
+    int refs = 1;
+    gl_ctx* ctx = nullptr;
+    // KB / PHI bookkeeping
+    int64_t q0 = 0;              // first raster pixel of the band
+    int p = 0, p_pad = 0, m = 0, m_pad = 0;
+    float phi_scale = 1.0f;      // PHI: stored value * phi_scale = logical (always 1; scale folded in the epilogue)
+};
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct gl_nccl;  // comm.cu
+
+struct gl_ctx {
+    int device = 0, rank = 0, world = 1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+
+    // image (whole image on every rank)
+    int width = 0, height = 0, channels = 0;
+    int64_t n = 0;
+    int row0 = 0, row1 = 0;  // band of image rows owned by this rank
+    int64_t q0 = 0, q1 = 0;  // raster range of the band
+    gl_buf* img = nullptr;   // u8 [n * channels]
+
+    // samples
+    unsigned p = 0;
+    int p_pad = 0;
+    gl_buf* samples = nullptr;  // u32 [p_pad] (padding = 0xffffffff)
+
+    // size-keyed cache of freed device blocks (no cudaMalloc in steady state)
+    std::multimap<size_t, void*> free_blocks;
+    size_t bytes_cached = 0, bytes_live = 0;
+
+    // stage timers
+    cudaEvent_t ev_begin[GL_T_COUNT] = {}, ev_end[GL_T_COUNT] = {};
+    bool ev_valid[GL_T_COUNT] = {};
+
+    // pinned staging for small D2H/H2D
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+
+    gl_nccl* comm = nullptr;
+
+    // options
+    int gemm_impl = 0;        // 0 = tcgen05 (default), 1 = simple CUDA-core checker kernel
+    int gemm_cta_group = 1;   // 1 or 2
+    int jacobi_max_sweeps = 40;
+    float jacobi_tol = 2e-6f;
+    int verbose = 0;
+};
+
+int gl_alloc(gl_ctx* ctx, size_t bytes, gl_buf** out);
+void gl_buf_release(gl_buf* b);
+gl_mat* gl_mat_new(gl_ctx* ctx, int kind);
+int gl_ensure_pinned(gl_ctx* ctx, size_t bytes);
+
+struct StageTimer {
+    gl_ctx* ctx;
+    int stage;
+    StageTimer(gl_ctx* c, int s) : ctx(c), stage(s) { cudaEventRecord(ctx->ev_begin[s], ctx->stream); }
+    ~StageTimer() {
+        cudaEventRecord(ctx->ev_end[stage], ctx->stream);
+        ctx->ev_valid[stage] = true;
+    }
+};
+
+// collectives (comm.cu): in-place sum over ranks on ctx->stream; no-ops when world == 1
+int gl_allreduce_f64(gl_ctx* ctx, double* dev, size_t count);
+int gl_allreduce_f32(gl_ctx* ctx, float* dev, size_t count);
+void gl_comm_destroy(gl_ctx* ctx);
+
+// stage implementations (one .cu each)
+int gl_impl_sampling_uniform(gl_ctx* ctx, unsigned requested, unsigned* actual);
+int gl_impl_sampling_random(gl_ctx* ctx, unsigned requested, uint32_t seed, unsigned* actual);
+int gl_impl_synthetic(gl_ctx* ctx, uint32_t seed);
+int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A, gl_mat** K_B);
+int gl_impl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A, gl_mat** L_B);
+int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv);
+int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi);
+int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out);
+int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip_low, float* z_f32, uint8_t* z_u8);
+int gl_impl_diag_map(gl_ctx* ctx, gl_mat* d, int op, double arg, gl_mat** out);
+int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
+                   const float* scales, const void* addend, void* D);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float fast_exp2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#endif

@@ -1,0 +1,392 @@
+// a-4 / a-5: the p x p symmetric eigensolve as a hand-written device block-Jacobi kernel.
+// Replaces EigendecompositionSmallest (SLEPc Krylov-Schur, hpc/eigendecomposition.c:12-124) and
+// InversePowerIteration (hpc/inverse_power_it.c:86-252): both ask for the m eigenpairs of L_A nearest
+// zero; this solver returns the CONVERGED pairs, ascending.
+//
+// Method: one-sided (Hestenes) block Jacobi on G = L_A.  Right rotations G <- G J make the columns of G
+// mutually orthogonal; since L_A is symmetric positive definite, at convergence G = U diag(lambda), so
+// lambda_j = |g_j| and u_j = g_j / |g_j| -- no separate eigenvector accumulation.
+//   * columns are grouped in panels of 8; G is stored panel-major ([panel][row][8] fp32) so a pair of
+//     panels is two contiguous streams;
+//   * one CTA owns a panel pair per step: loads it to shared memory (p x 16), forms the 16 x 16 Gram
+//     block, diagonalises it with a two-sided cyclic Jacobi in shared memory, applies the 16 x 16
+//     rotation to the panel and streams it back;
+//   * a round-robin tournament gives (panels - 1) steps per sweep with panels/2 independent pairs per
+//     step; steps are separated by a cooperative grid barrier, the whole solve is ONE kernel launch;
+//   * no atomics on floating-point data and fixed reduction orders: the result is bit-reproducible, so
+//     every GPU of a multi-GPU run can solve redundantly and hold identical eigenvectors.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+#define JB 8           // columns per panel
+#define JP (2 * JB)    // columns per panel pair
+#define J_THREADS 256
+#define J_INNER_MAX 12
+
+__global__ void k_jacobi_init(const double* __restrict__ A, int p, int nb, float* __restrict__ G)
+{
+    // G[panel][r][c] = A[r][panel*8 + c]; zero columns beyond p
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)nb * p * JB;
+    if (idx >= total) return;
+    int c = (int)(idx % JB);
+    int64_t t = idx / JB;
+    int r = (int)(t % p);
+    int panel = (int)(t / p);
+    int col = panel * JB + c;
+    G[idx] = col < p ? (float)A[(size_t)r * p + col] : 0.f;
+}
+
+// round-robin tournament over nb (even) panels: step in [0, nb-1), pair in [0, nb/2)
+__device__ __forceinline__ void tournament(int step, int pair, int nb, int& a, int& b)
+{
+    const int mth = nb - 1;
+    if (pair == 0) {
+        a = mth;
+        b = step % mth;
+    } else {
+        a = (step + pair) % mth;
+        b = (step - pair + mth) % mth;
+    }
+    if (a > b) { int t = a; a = b; b = t; }
+}
+
+__global__ void __launch_bounds__(J_THREADS, 1)
+k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, unsigned* __restrict__ sweep_off,
+         int* __restrict__ sweeps_done)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) float jsm[];
+    float* P = jsm;                          // [p][16]
+    float* red = P + (size_t)p * JP;         // [16][256]
+    float* Bm = red + 16 * 256;              // [16][17]
+    float* Qm = Bm + JP * 17;                // [16][17]
+    float* cs = Qm + JP * 17;                // [8][2]
+    int* role = (int*)(cs + 16);             // [16]  (pair << 1) | is_second
+    int* pq = role + JP;                     // [8][2]
+    __shared__ float s_off;
+    __shared__ unsigned s_cta_off;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int bi = tid >> 4, bj = tid & 15;  // this thread's element of the 16 x 16 block
+    const int npairs = nb >> 1;
+
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int step = 0; step < nb - 1; ++step) {
+            for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+                int I, J;
+                tournament(step, pair, nb, I, J);
+                float* GI = G + (size_t)I * p * JB;
+                float* GJ = G + (size_t)J * p * JB;
+                // ---- load the panel pair (L2 loads: the data was written by other SMs) ----
+                for (int idx = tid; idx < 2 * p; idx += J_THREADS) {
+                    const int r = idx >> 1, h = idx & 1;
+                    float4 a = __ldcg((const float4*)(GI + (size_t)r * JB + h * 4));
+                    float4 b = __ldcg((const float4*)(GJ + (size_t)r * JB + h * 4));
+                    *(float4*)(P + (size_t)r * JP + h * 4) = a;
+                    *(float4*)(P + (size_t)r * JP + JB + h * 4) = b;
+                }
+                if (tid == 0) s_cta_off = 0u;
+                __syncthreads();
+                // ---- Gram block: 16 row groups x (4 x 4 register tiles) ----
+                {
+                    const int rg = tid >> 4, ti = (tid >> 2) & 3, tj = tid & 3;
+                    float acc[4][4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+                    for (int r = rg; r < p; r += 16) {
+                        const float4 a = *(const float4*)(P + (size_t)r * JP + 4 * ti);
+                        const float4 b = *(const float4*)(P + (size_t)r * JP + 4 * tj);
+                        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) red[rg * 256 + (4 * ti + x) * 16 + 4 * tj + y] = acc[x][y];
+                }
+                __syncthreads();
+                {
+                    float s = 0.f;
+#pragma unroll
+                    for (int rg = 0; rg < 16; ++rg) s += red[rg * 256 + tid];
+                    Bm[bi * 17 + bj] = s;
+                    Qm[bi * 17 + bj] = (bi == bj) ? 1.f : 0.f;
+                }
+                __syncthreads();
+                // ---- how far from orthogonal is this pair (drives the sweep loop) ----
+                {
+                    float rel = 0.f;
+                    if (bi < bj) {
+                        const float dii = Bm[bi * 17 + bi], djj = Bm[bj * 17 + bj];
+                        if (dii > 0.f && djj > 0.f) rel = fabsf(Bm[bi * 17 + bj]) * rsqrtf(dii * djj);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) rel = fmaxf(rel, __shfl_xor_sync(0xffffffffu, rel, o));
+                    if (lane == 0) atomicMax(&s_cta_off, __float_as_uint(rel));
+                }
+                __syncthreads();
+                const float pair_off = __uint_as_float(s_cta_off);
+                if (tid == 0) atomicMax(&sweep_off[sweep], s_cta_off);
+                // ---- diagonalise the 16 x 16 block: cyclic two-sided Jacobi, Q accumulates the rotations ----
+                if (pair_off > 0.25f * tol) {
+                    if (tid == 0) s_off = 0.f;
+                    __syncthreads();
+                    for (int isw = 0; isw < J_INNER_MAX; ++isw) {
+                        for (int st = 0; st < JP - 1; ++st) {
+                            if (tid < JB) {
+                                int a, b;
+                                tournament(st, tid, JP, a, b);
+                                const float app = Bm[a * 17 + a], aqq = Bm[b * 17 + b], apq = Bm[a * 17 + b];
+                                float c = 1.f, s = 0.f;
+                                if (app > 0.f && aqq > 0.f) {
+                                    const float rel = fabsf(apq) * rsqrtf(app * aqq);
+                                    if (rel > 1e-9f) {
+                                        const float tau = (aqq - app) / (2.f * apq);
+                                        const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+                                        c = rsqrtf(1.f + t * t);
+                                        s = t * c;
+                                    }
+                                    if (rel > s_off) atomicMax((unsigned*)&s_off, __float_as_uint(rel));
+                                }
+                                cs[2 * tid] = c;
+                                cs[2 * tid + 1] = s;
+                                pq[2 * tid] = a;
+                                pq[2 * tid + 1] = b;
+                                role[a] = tid << 1;
+                                role[b] = (tid << 1) | 1;
+                            }
+                            __syncthreads();
+                            float nb_, nq_;
+                            {
+                                const int ri = role[bi], rj = role[bj];
+                                const int ki = ri >> 1, kj = rj >> 1;
+                                const float ci = cs[2 * ki], si = cs[2 * ki + 1], cj = cs[2 * kj], sj = cs[2 * kj + 1];
+                                const int ip = pq[2 * ki], iq = pq[2 * ki + 1], jp = pq[2 * kj], jq = pq[2 * kj + 1];
+                                float x_ip, x_iq;  // (B J)[ip][bj], (B J)[iq][bj]
+                                if ((rj & 1) == 0) {
+                                    x_ip = cj * Bm[ip * 17 + jp] - sj * Bm[ip * 17 + jq];
+                                    x_iq = cj * Bm[iq * 17 + jp] - sj * Bm[iq * 17 + jq];
+                                    nq_ = cj * Qm[bi * 17 + jp] - sj * Qm[bi * 17 + jq];
+                                } else {
+                                    x_ip = sj * Bm[ip * 17 + jp] + cj * Bm[ip * 17 + jq];
+                                    x_iq = sj * Bm[iq * 17 + jp] + cj * Bm[iq * 17 + jq];
+                                    nq_ = sj * Qm[bi * 17 + jp] + cj * Qm[bi * 17 + jq];
+                                }
+                                nb_ = ((ri & 1) == 0) ? (ci * x_ip - si * x_iq) : (si * x_ip + ci * x_iq);
+                            }
+                            __syncthreads();
+                            Bm[bi * 17 + bj] = nb_;
+                            Qm[bi * 17 + bj] = nq_;
+                            __syncthreads();
+                        }
+                        const float inner_off = s_off;
+                        __syncthreads();
+                        if (tid == 0) s_off = 0.f;
+                        __syncthreads();
+                        if (inner_off <= 0.1f * tol) break;
+                    }
+                    // ---- apply: [G_I G_J] <- [G_I G_J] Q, streamed straight back to global ----
+                    const int cgp = tid & 3;
+                    float q[JP][4];
+#pragma unroll
+                    for (int k = 0; k < JP; ++k)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) q[k][x] = Qm[k * 17 + 4 * cgp + x];
+                    float* dst = (cgp < 2) ? (GI + cgp * 4) : (GJ + (cgp - 2) * 4);
+                    for (int r = tid >> 2; r < p; r += J_THREADS / 4) {
+                        const float4 v0 = *(const float4*)(P + (size_t)r * JP);
+                        const float4 v1 = *(const float4*)(P + (size_t)r * JP + 4);
+                        const float4 v2 = *(const float4*)(P + (size_t)r * JP + 8);
+                        const float4 v3 = *(const float4*)(P + (size_t)r * JP + 12);
+                        const float pv[JP] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w,
+                                              v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+                        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int k = 0; k < JP; ++k)
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) o[x] = fmaf(pv[k], q[k][x], o[x]);
+                        __stcg((float4*)(dst + (size_t)r * JB), make_float4(o[0], o[1], o[2], o[3]));
+                    }
+                }
+                __syncthreads();
+            }
+            grid.sync();
+        }
+        const float off = __uint_as_float(__ldcg(&sweep_off[sweep]));
+        if (off <= tol) { ++sweep; break; }
+    }
+    if (blockIdx.x == 0 && tid == 0) *sweeps_done = sweep;
+}
+
+// lambda_c = |g_c| (fp64 accumulation), one warp per original column
+__global__ void k_jacobi_norms(const float* __restrict__ G, int p, double* __restrict__ lam)
+{
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= p) return;
+    const float* col = G + (size_t)(c / JB) * p * JB + (c % JB);
+    double acc = 0.0;
+    for (int r = threadIdx.x & 31; r < p; r += 32) {
+        double v = (double)col[(size_t)r * JB];
+        acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) lam[c] = sqrt(acc);
+}
+
+// ascending order of the eigenvalues: one CTA, bitonic sort of (lambda, index)
+__global__ void __launch_bounds__(1024, 1) k_jacobi_sort(const double* __restrict__ lam, int p, int N, int* __restrict__ order)
+{
+    extern __shared__ unsigned long long skeys[];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (i < p) {
+            // positive doubles order like their bit patterns; keep 40 bits of the value, 24 of the index
+            unsigned long long bits = (unsigned long long)__double_as_longlong(lam[i]);
+            k = (bits & ~0xffffffull) | (unsigned)i;
+        }
+        skeys[i] = k;
+    }
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = skeys[i], b = skeys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { skeys[i] = b; skeys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < p; i += blockDim.x) order[i] = (int)(skeys[i] & 0xffffffull);
+}
+
+// U[:, j] = g_order[j] / lambda, column-major fp32 with leading dimension ld; mu / 1/mu in fp64
+__global__ void k_jacobi_extract(const float* __restrict__ G, const double* __restrict__ lam, const int* __restrict__ order, int p,
+                                 int m, int ld, float* __restrict__ U, double* __restrict__ mu, double* __restrict__ mu_inv)
+{
+    const int j = blockIdx.x;
+    if (j >= m) return;
+    const int c = order[j];
+    const double l = lam[c];
+    const float inv = (float)(1.0 / l);
+    const float* col = G + (size_t)(c / JB) * p * JB + (c % JB);
+    for (int r = threadIdx.x; r < ld; r += blockDim.x) U[(size_t)j * ld + r] = r < p ? col[(size_t)r * JB] * inv : 0.f;
+    if (threadIdx.x == 0) {
+        mu[j] = l;
+        if (mu_inv) mu_inv[j] = 1.0 / l;
+    }
+}
+
+int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv)
+{
+    const int p = (int)L_A->rows;
+    const int nb = (int)(round_up(p, JP) / JB);  // even number of panels
+    const size_t smem = sizeof(float) * ((size_t)p * JP + 16 * 256 + 2 * JP * 17 + 16) + sizeof(int) * (JP + 2 * JB);
+    if (smem > 227 * 1024) {
+        gl_set_error("eigensolve: p = %d needs %zu bytes of shared memory per CTA (limit 227 KB)", p, smem);
+        return GL_ERR_UNSUPPORTED;
+    }
+    GL_REQUIRE(p < (1 << 24), "eigensolve: p too large");
+    gl_buf *G = nullptr, *lam = nullptr, *order = nullptr, *ctl = nullptr;
+    gl_mat *U = nullptr, *mu = nullptr, *mui = nullptr;
+    int rc = GL_OK;
+    const int max_sweeps = ctx->jacobi_max_sweeps;
+    do {
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)nb * p * JB, &G)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)p, &lam)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(int) * (size_t)p, &order)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(unsigned) * (size_t)(max_sweeps + 4), &ctl)) != GL_OK) break;
+        GL_CUDA_CHECK(cudaMemsetAsync(ctl->ptr, 0, sizeof(unsigned) * (size_t)(max_sweeps + 4), ctx->stream));
+        const int64_t total = (int64_t)nb * p * JB;
+        k_jacobi_init<<<(unsigned)ceil_div(total, 256), 256, 0, ctx->stream>>>((const double*)L_A->buf->ptr, p, nb,
+                                                                               (float*)G->ptr);
+        GL_LAUNCH_CHECK(ctx);
+
+        GL_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        GL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi, J_THREADS, smem));
+        GL_REQUIRE(per_sm >= 1, "eigensolve: kernel does not fit on an SM");
+        int grid = nb / 2;
+        if (grid > per_sm * ctx->sm_count) grid = per_sm * ctx->sm_count;
+        float* Gp = (float*)G->ptr;
+        int p_ = p, nb_ = nb, ms = max_sweeps;
+        float tol = ctx->jacobi_tol;
+        unsigned* off = (unsigned*)ctl->ptr;
+        int* done = (int*)((unsigned*)ctl->ptr + max_sweeps);
+        void* args[] = {&Gp, &p_, &nb_, &ms, &tol, &off, &done};
+        GL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));
+        ctx->launches++;
+
+        k_jacobi_norms<<<(unsigned)ceil_div(p, 8), 256, 0, ctx->stream>>>((const float*)G->ptr, p, (double*)lam->ptr);
+        GL_LAUNCH_CHECK(ctx);
+        int N = 2;
+        while (N < p) N <<= 1;
+        GL_REQUIRE(N <= 8192, "eigensolve: p too large for the single-CTA sort");
+        GL_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        k_jacobi_sort<<<1, 1024, (size_t)N * 8, ctx->stream>>>((const double*)lam->ptr, p, N, (int*)order->ptr);
+        GL_LAUNCH_CHECK(ctx);
+
+        U = gl_mat_new(ctx, GL_MAT_EIGVEC);
+        U->rows = U->local_rows = p;
+        U->cols = m;
+        U->ld = round_up(p, 64);
+        U->elem_bytes = 4;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)U->ld * m, &U->buf)) != GL_OK) break;
+        mu = gl_mat_new(ctx, GL_MAT_DIAG);
+        mu->rows = mu->local_rows = m;
+        mu->cols = m;
+        mu->ld = 1;
+        mu->elem_bytes = 8;
+        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m, &mu->buf)) != GL_OK) break;
+        mui = gl_mat_new(ctx, GL_MAT_DIAG);
+        *mui = *mu;
+        mui->buf = nullptr;
+        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m, &mui->buf)) != GL_OK) break;
+        k_jacobi_extract<<<m, 256, 0, ctx->stream>>>((const float*)G->ptr, (const double*)lam->ptr, (const int*)order->ptr, p, m,
+                                                     (int)U->ld, (float*)U->buf->ptr, (double*)mu->buf->ptr,
+                                                     (double*)mui->buf->ptr);
+        GL_LAUNCH_CHECK(ctx);
+
+        // convergence report (one small D2H; the solve itself never synchronises with the host)
+        GL_CHECK(gl_ensure_pinned(ctx, sizeof(unsigned) * (size_t)(max_sweeps + 4)));
+        GL_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, ctl->ptr, sizeof(unsigned) * (size_t)(max_sweeps + 4), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const unsigned* h = (const unsigned*)ctx->pinned;
+        const int sweeps = (int)h[max_sweeps];
+        float last;
+        memcpy(&last, &h[sweeps > 0 ? sweeps - 1 : 0], sizeof(float));
+        if (ctx->verbose) fprintf(stderr, "[libglcuda] jacobi: p=%d panels=%d grid=%d sweeps=%d last off=%.3g\n", p, nb, grid, sweeps, last);
+        if (last > ctx->jacobi_tol) {
+            gl_set_error("eigensolve: not converged after %d sweeps (off-orthogonality %.3g > %.3g)", sweeps, last, ctx->jacobi_tol);
+            rc = GL_ERR_NOTCONVERGED;
+            break;
+        }
+    } while (0);
+    if (G) gl_buf_release(G);
+    if (lam) gl_buf_release(lam);
+    if (order) gl_buf_release(order);
+    if (ctl) gl_buf_release(ctl);
+    if (rc != GL_OK) {
+        gl_mat_destroy(U);
+        gl_mat_destroy(mu);
+        gl_mat_destroy(mui);
+        return rc;
+    }
+    if (eigvecs) *eigvecs = U; else gl_mat_destroy(U);
+    if (eigvals) *eigvals = mu; else gl_mat_destroy(mu);
+    if (eigvals_inv) *eigvals_inv = mui; else gl_mat_destroy(mui);
+    return GL_OK;
+}

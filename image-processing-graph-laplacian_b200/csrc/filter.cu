@@ -1,0 +1,311 @@
+// a-9: filter application  z = y + gain * Phi (f(lambda) o (Phi^T y)),  z[z > 255] = 255.
+// Replaces ComputeResultFromLaplacian (hpc/display.c:58-83) with pngbytes2OneColMat (hpc/utils.c:461-486),
+// AboveXSetY (:652-703) and OneColMat2pngbytes (:492-534).
+//
+// Two bandwidth-bound passes over Phi (bf16, [band pixels][m_pad], one 16-byte load = 8 columns):
+//   (i)  c = Phi^T y : thread <-> (row lane, column group); 8*C fp32 accumulators per thread, rows streamed with
+//        4 loads in flight per thread; per-CTA partials, fixed-order reduction (deterministic), one small
+//        allreduce over ranks;
+//   (ii) z = y + Phi w,  w = gain * f(lambda) o c held in registers; row dot products reduced with warp shuffles.
+// Algorithmic bytes: 2 * rows * m_pad * 2 (Phi read twice) + rows*C*(1 + 1 + 4) (y twice, z once).
+#include "common.cuh"
+
+#define FL_THREADS 256
+#define FL_RU 4  // rows in flight per thread
+
+struct FilterGeom {
+    int G;      // 16-byte column groups per row = m_pad / 8
+    int TPR;    // threads per row = min(G, 256)
+    int RL;     // row lanes per CTA = 256 / TPR
+    int NG;     // groups per thread = ceil(G / TPR) (1 or 2)
+};
+
+static FilterGeom filter_geom(int m_pad)
+{
+    FilterGeom g;
+    g.G = m_pad / 8;
+    g.TPR = g.G < FL_THREADS ? g.G : FL_THREADS;
+    g.RL = FL_THREADS / g.TPR;
+    g.NG = (g.G + g.TPR - 1) / g.TPR;
+    return g;
+}
+
+__device__ __forceinline__ uint4 ld_stream(const void* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8])
+{
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+// (i) partial[blockIdx][j*C + ch] = sum over this CTA's rows of Phi[row][j] * y[row][ch]
+template <int C, int NG>
+__global__ void __launch_bounds__(FL_THREADS) k_filter_project(const __nv_bfloat16* __restrict__ phi, int64_t rows, int m_pad, int G,
+                                                               int TPR, int RL, const uint8_t* __restrict__ y /* band base */,
+                                                               float* __restrict__ partial)
+{
+    __shared__ float red[FL_THREADS * 8 * C];  // only used when RL > 1 (then NG == 1)
+    const int tid = threadIdx.x;
+    const int rl = tid / TPR, tg = tid - rl * TPR;
+    const bool active = rl < RL;
+    float acc[NG][8][C];
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) acc[g][k][ch] = 0.f;
+
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r_begin = per * blockIdx.x, r_end = min(rows, r_begin + per);
+    if (active) {
+        for (int64_t r0 = r_begin + rl; r0 < r_end; r0 += (int64_t)RL * FL_RU) {
+            uint4 v[FL_RU][NG];
+            float yy[FL_RU][C];
+#pragma unroll
+            for (int u = 0; u < FL_RU; ++u) {
+                const int64_t r = r0 + (int64_t)u * RL;
+                const bool ok = r < r_end;
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const int grp = tg + g * TPR;
+                    v[u][g] = (ok && grp < G) ? ld_stream(phi + (size_t)r * m_pad + (size_t)grp * 8) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) yy[u][ch] = ok ? (float)y[(size_t)r * C + ch] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < FL_RU; ++u)
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    float f[8];
+                    unpack8(v[u][g], f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) acc[g][k][ch] = fmaf(f[k], yy[u][ch], acc[g][k][ch]);
+                }
+        }
+    }
+    float* out = partial + (size_t)blockIdx.x * m_pad * C;
+    if (RL == 1) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int grp = tg + g * TPR;
+            if (grp < G)
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) out[(size_t)(grp * 8 + k) * C + ch] = acc[g][k][ch];
+        }
+    } else {
+        // fixed-order reduction over the row lanes
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) red[((size_t)rl * TPR + tg) * 8 * C + k * C + ch] = acc[0][k][ch];
+        }
+        __syncthreads();
+        for (int i = tid; i < TPR * 8 * C; i += FL_THREADS) {
+            float s = 0.f;
+            for (int l = 0; l < RL; ++l) s += red[(size_t)l * TPR * 8 * C + i];
+            out[i] = s;  // i = (grp*8 + k)*C + ch
+        }
+    }
+}
+
+// c[i] = sum_b partial[b][i]  (fixed order)
+__global__ void k_filter_reduce(const float* __restrict__ partial, int nblocks, int count, float* __restrict__ c)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * count + i];
+    c[i] = (float)s;
+}
+
+// w[j][ch] = gain * f[j] * c[j][ch] for j < m, 0 for padding columns
+__global__ void k_filter_weights(const float* __restrict__ c, const double* __restrict__ f, int m, int m_pad, int C, float gain,
+                                 float* __restrict__ w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m_pad * C) return;
+    const int j = i / C;
+    w[i] = j < m ? (float)((double)gain * f[j] * (double)c[i]) : 0.f;
+}
+
+// (ii) z[row][ch] = y + sum_j Phi[row][j] * w[j][ch]; clip; optional u8
+template <int C, int NG>
+__global__ void __launch_bounds__(FL_THREADS) k_filter_apply(const __nv_bfloat16* __restrict__ phi, int64_t rows, int m_pad, int G,
+                                                             int TPR, int RL, const uint8_t* __restrict__ y,
+                                                             const float* __restrict__ w, int clip_low, float* __restrict__ z,
+                                                             uint8_t* __restrict__ z8)
+{
+    __shared__ float red[FL_RU][FL_THREADS / 32][C];  // cross-warp partials when a row spans several warps
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rl = tid / TPR, tg = tid - rl * TPR;
+    const bool active = rl < RL;
+    float wr[NG][8][C];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const int grp = tg + g * TPR;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) wr[g][k][ch] = (active && grp < G) ? w[(size_t)(grp * 8 + k) * C + ch] : 0.f;
+    }
+    const int seg = TPR < 32 ? TPR : 32;      // lanes of one warp that share a row
+    const int wpr = TPR > 32 ? TPR / 32 : 1;  // warps per row
+
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r_begin = per * blockIdx.x, r_end = min(rows, r_begin + per);
+    const int64_t step = (int64_t)RL * FL_RU;
+    const int64_t iters = (r_end - r_begin + step - 1) / step;
+    for (int64_t itn = 0; itn < iters; ++itn) {
+        const int64_t r0 = r_begin + itn * step + rl;
+        float dot[FL_RU][C];
+        uint4 v[FL_RU][NG];
+#pragma unroll
+        for (int u = 0; u < FL_RU; ++u) {
+            const int64_t r = r0 + (int64_t)u * RL;
+            const bool ok = active && r < r_end;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int grp = tg + g * TPR;
+                v[u][g] = (ok && grp < G) ? ld_stream(phi + (size_t)r * m_pad + (size_t)grp * 8) : make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FL_RU; ++u) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) dot[u][ch] = 0.f;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                float f[8];
+                unpack8(v[u][g], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) dot[u][ch] = fmaf(f[k], wr[g][k][ch], dot[u][ch]);
+            }
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch)
+                for (int o = seg >> 1; o > 0; o >>= 1) dot[u][ch] += __shfl_xor_sync(0xffffffffu, dot[u][ch], o);
+        }
+        if (wpr > 1) {
+            // RL is 1 or 2 here; a row's warps are consecutive
+            if (lane == 0) {
+#pragma unroll
+                for (int u = 0; u < FL_RU; ++u)
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) red[u][warp][ch] = dot[u][ch];
+            }
+            __syncthreads();
+            if (active && tg == 0) {
+#pragma unroll
+                for (int u = 0; u < FL_RU; ++u)
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        float s = 0.f;
+                        for (int k = 0; k < wpr; ++k) s += red[u][rl * wpr + k][ch];
+                        dot[u][ch] = s;
+                    }
+            }
+        }
+        if (active && tg == 0) {
+#pragma unroll
+            for (int u = 0; u < FL_RU; ++u) {
+                const int64_t r = r0 + (int64_t)u * RL;
+                if (r < r_end) {
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        float val = (float)y[(size_t)r * C + ch] + dot[u][ch];
+                        val = fminf(val, 255.f);                  // AboveXSetY(z, 255, 255), display.c:76
+                        if (clip_low) val = fmaxf(val, 0.f);
+                        if (z) z[(size_t)r * C + ch] = val;
+                        if (z8) z8[(size_t)r * C + ch] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);  // clamp then truncate
+                    }
+                }
+            }
+        }
+        if (wpr > 1) __syncthreads();
+    }
+}
+
+template <int C, int NG>
+static int run_filter(gl_ctx* ctx, gl_mat* phi, const FilterGeom& g, const double* f, double gain, int clip_low, int grid,
+                      float* partial, float* c, float* w, float* z, uint8_t* z8)
+{
+    const int64_t rows = phi->local_rows;
+    const int m = phi->m, m_pad = phi->m_pad;
+    const uint8_t* y = (const uint8_t*)ctx->img->ptr + (size_t)phi->q0 * C;
+    const __nv_bfloat16* P = (const __nv_bfloat16*)phi->buf->ptr;
+    k_filter_project<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, partial);
+    GL_LAUNCH_CHECK(ctx);
+    k_filter_reduce<<<(unsigned)ceil_div(m_pad * C, 256), 256, 0, ctx->stream>>>(partial, grid, m_pad * C, c);
+    GL_LAUNCH_CHECK(ctx);
+    GL_CHECK(gl_allreduce_f32(ctx, c, (size_t)m_pad * C));
+    k_filter_weights<<<(unsigned)ceil_div(m_pad * C, 256), 256, 0, ctx->stream>>>(c, f, m, m_pad, C, (float)gain, w);
+    GL_LAUNCH_CHECK(ctx);
+    k_filter_apply<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, w, clip_low, z, z8);
+    GL_LAUNCH_CHECK(ctx);
+    return GL_OK;
+}
+
+int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip_low, float* z_f32, uint8_t* z_u8)
+{
+    const int C = ctx->channels;
+    const int64_t rows = phi->local_rows;
+    const int m_pad = phi->m_pad;
+    const FilterGeom g = filter_geom(m_pad);
+    GL_REQUIRE(g.NG <= 2, "filter: m_pad = %d too wide", m_pad);
+    GL_REQUIRE((g.TPR & (g.TPR - 1)) == 0 || g.TPR % 32 == 0, "filter: unsupported column-group count %d", g.G);
+    int grid = ctx->sm_count * 4;
+    if ((int64_t)grid * g.RL * FL_RU > rows) grid = (int)ceil_div(rows, (int64_t)g.RL * FL_RU);
+    if (grid < 1) grid = 1;
+
+    gl_buf *partial = nullptr, *c = nullptr, *w = nullptr, *z = nullptr, *z8 = nullptr;
+    int rc = GL_OK;
+    do {
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * m_pad * C, &partial)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad * C, &c)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad * C, &w)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)rows * C, &z)) != GL_OK) break;
+        if (z_u8 && (rc = gl_alloc(ctx, (size_t)rows * C, &z8)) != GL_OK) break;
+        {
+            StageTimer t(ctx, GL_T_FILTER);
+            const double* f = (const double*)f_eigvals->buf->ptr;
+            float* zp = (float*)z->ptr;
+            uint8_t* z8p = z8 ? (uint8_t*)z8->ptr : nullptr;
+#define FL_CASE(CC, NGG)                                                                                                      \
+    if (C == CC && g.NG == NGG)                                                                                               \
+        rc = run_filter<CC, NGG>(ctx, phi, g, f, gain, clip_low, grid, (float*)partial->ptr, (float*)c->ptr, (float*)w->ptr, zp, z8p);
+            FL_CASE(1, 1) else FL_CASE(1, 2) else FL_CASE(3, 1) else FL_CASE(3, 2)
+#undef FL_CASE
+        }
+        if (rc != GL_OK) break;
+        {
+            StageTimer t(ctx, GL_T_D2H);
+            if (z_f32)
+                GL_CUDA_CHECK(cudaMemcpyAsync(z_f32 + (size_t)phi->q0 * C, z->ptr, sizeof(float) * (size_t)rows * C,
+                                              cudaMemcpyDeviceToHost, ctx->stream));
+            if (z_u8)
+                GL_CUDA_CHECK(cudaMemcpyAsync(z_u8 + (size_t)phi->q0 * C, z8->ptr, (size_t)rows * C, cudaMemcpyDeviceToHost,
+                                              ctx->stream));
+        }
+        if (z_f32 || z_u8) GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } while (0);
+    if (partial) gl_buf_release(partial);
+    if (c) gl_buf_release(c);
+    if (w) gl_buf_release(w);
+    if (z) gl_buf_release(z);
+    if (z8) gl_buf_release(z8);
+    return rc;
+}

@@ -1,0 +1,597 @@
+// a-6 (+ a-7): Nystroem extrapolation Phi = [Phi_A ; L_B^T . Phi_A . Lambda^-1] as a tcgen05 GEMM.
+// Replaces Nystroem (hpc/nystroem.c:5-69: MatMatMult + MatTransposeMatMult + two row-block copies),
+// InverseDiagMat's use there (hpc/utils.c:559-586) and Permutation (hpc/utils.c:134-173).
+//
+//   Phi[q, j] = sum_s K_B[q, s] * W[s, j],   W = -alpha * U * diag(1/mu)        (p x m)
+//
+//   * A operand  = K_B band, [pixels x p_pad] fp16, K-major  -> M = pixels (128 per CTA tile)
+//   * B operand  = W^T, [m_pad x p_pad] fp16, K-major, scaled by one power of two so that it sits at the
+//                  top of the fp16 range (W itself is ~1e-4 and would be subnormal); unscaled in the epilogue
+//   * D          = fp32 accumulators in TMEM (2 x 256 columns, double buffered), written as bf16 Phi
+//   * TMA (SWIZZLE_128B) feeds a 4-stage shared-memory ring; one elected thread issues tcgen05.mma;
+//     four epilogue warps drain TMEM with tcgen05.ld, convert, stage swizzled rows in shared memory and
+//     TMA-store them while the next tile's MMAs run.
+//   * every pixel's row is written at its raster position, so there is no permutation pass; the p sample
+//     rows are then overwritten with Phi_A (nystroem.c:25-34).
+// A plain CUDA-core kernel (option gemm=simple) computes the same thing for cross-checking in tests.
+#include <cuda.h>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// W^T build
+// ---------------------------------------------------------------------------------------------
+__global__ void k_w_colmax(const float* __restrict__ U, int ld, int p, int m, const double* __restrict__ mu_inv,
+                           const double* __restrict__ neg_alpha, float* __restrict__ colmax)
+{
+    const int j = blockIdx.x;
+    float mx = 0.f;
+    for (int s = threadIdx.x; s < p; s += blockDim.x) mx = fmaxf(mx, fabsf(U[(size_t)j * ld + s]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __shared__ float sh[32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, sh[w]);
+        colmax[j] = mx * (float)fabs(neg_alpha[0] * mu_inv[j]);
+    }
+}
+
+// scales[0] = 2^e (applied to W), scales[1] = 2^-e (applied in the GEMM epilogue); max |W| * 2^e in [2^13, 2^14)
+__global__ void k_w_scale(const float* __restrict__ colmax, int m, float* __restrict__ scales)
+{
+    __shared__ float sh[32];
+    float mx = 0.f;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) mx = fmaxf(mx, colmax[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, sh[w]);
+        int e = 0;
+        if (mx > 0.f && isfinite(mx)) {
+            int ex;
+            frexpf(mx, &ex);  // mx = f * 2^ex, f in [0.5, 1)
+            e = 14 - ex;
+        }
+        e = max(-100, min(100, e));
+        scales[0] = ldexpf(1.f, e);
+        scales[1] = ldexpf(1.f, -e);
+    }
+}
+
+__global__ void k_w_write(const float* __restrict__ U, int ld, int p, int m, int p_pad, int m_pad,
+                          const double* __restrict__ mu_inv, const double* __restrict__ neg_alpha,
+                          const float* __restrict__ scales, __half* __restrict__ Wt)
+{
+    const int j = blockIdx.x;  // row of W^T
+    const float f = j < m ? (float)(neg_alpha[0] * mu_inv[j]) * scales[0] : 0.f;
+    for (int s = threadIdx.x; s < p_pad; s += blockDim.x) {
+        float v = (j < m && s < p) ? U[(size_t)j * ld + s] * f : 0.f;
+        Wt[(size_t)j * p_pad + s] = __float2half_rn(v);
+    }
+}
+
+// Phi rows of the sample pixels <- Phi_A (nystroem.c:25-34); band-local
+__global__ void k_phi_sample_rows(const float* __restrict__ U, int ld, int p, int m, const uint32_t* __restrict__ samples,
+                                  int64_t q0, int64_t q1, int m_pad, __nv_bfloat16* __restrict__ phi)
+{
+    const int i = blockIdx.x;
+    const int64_t q = samples[i];
+    if (q < q0 || q >= q1) return;
+    for (int j = threadIdx.x; j < m; j += blockDim.x)
+        phi[(size_t)(q - q0) * m_pad + j] = __float2bfloat16_rn(U[(size_t)j * ld + i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// checker GEMM on CUDA cores (tests / debugging only; selected with option gemm=simple)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gemm_simple(const T* __restrict__ A, const T* __restrict__ Bt, int64_t M, int N, int K,
+                                                     const float* __restrict__ scales, const __nv_bfloat16* __restrict__ addend,
+                                                     __nv_bfloat16* __restrict__ D)
+{
+    __shared__ float As[32][33], Bs[32][33];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 2 x 2 outputs each
+    const int64_t m0 = (int64_t)blockIdx.y * 32;
+    const int n0 = blockIdx.x * 32;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+            const int r = i >> 5, c = i & 31;
+            As[r][c] = (m0 + r < M) ? to_f32<T>(A[(size_t)(m0 + r) * K + k0 + c]) : 0.f;
+            Bs[r][c] = (n0 + r < N) ? to_f32<T>(Bt[(size_t)(n0 + r) * K + k0 + c]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float a0 = As[ty][k], a1 = As[ty + 16][k], b0 = Bs[tx][k], b1 = Bs[tx + 16][k];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]);
+            acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]);
+            acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+    const float sc = scales[1];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int64_t r = m0 + ty + 16 * a;
+            const int c = n0 + tx + 16 * b;
+            if (r < M && c < N) {
+                float v = acc[a][b] * sc;
+                if (addend) v += __bfloat162float(addend[(size_t)r * N + c]);
+                D[(size_t)r * N + c] = __float2bfloat16_rn(v);
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 GEMM
+// ---------------------------------------------------------------------------------------------
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;       // 64 fp16 = 128 bytes = one SWIZZLE_128B row
+constexpr int MAX_BLOCK_N = 256;
+constexpr int STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int THREADS = 256;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KB
+constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;   // 32 KB
+constexpr int C_SLAB_BYTES = 32 * 128;                     // 32 rows x 64 bf16
+constexpr int C_BYTES = 4 * 2 * C_SLAB_BYTES;              // 4 epilogue warps x 2 buffers
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + C_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must end in a trap (a CUDA error the host reports), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell), bits [46,48)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B, bits [61,64)
+    return d;
+}
+// kind::f16 instruction descriptor: (fp16 x fp16 | bf16 x bf16) -> fp32, both operands K-major
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, uint32_t ab_format /* 0 = f16, 1 = bf16 */)
+{
+    uint32_t d = 0;
+    d |= 1u << 4;                     // D format: f32
+    d |= ab_format << 7;              // A format
+    d |= ab_format << 10;             // B format
+    d |= (uint32_t)(N >> 3) << 17;    // N / 8
+    d |= (uint32_t)(M >> 4) << 24;    // M / 16
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *(uint32_t*)&v;
+}
+
+// One persistent CTA per SM.  warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator,
+// warps 4-7: epilogue (warp w drains TMEM lanes 32*(w%4) .. +31).
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_d, int m_tiles, int n_tiles, int k_blocks, int n_total, int block_n,
+               int ab_bf16, const float* __restrict__ scales, const __nv_bfloat16* __restrict__ addend, int64_t m_rows,
+               int* __restrict__ err)
+{
+    extern __shared__ uint8_t gemm_smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem_a + STAGES * A_STAGE_BYTES;
+    uint8_t* smem_c = smem_b + STAGES * B_STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(smem_c + C_BYTES);
+    // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then the TMEM base address
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t stage_tx = (uint32_t)(A_STAGE_BYTES + block_n * BLOCK_K * 2);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / n_tiles, nt = tile % n_tiles;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1, err, 1);
+                    mbar_expect_tx(bar_full + 8 * stage, stage_tx);
+                    tma_load_2d(smem_u32(smem_a + stage * A_STAGE_BYTES), &map_a, bar_full + 8 * stage, kb * BLOCK_K, mt * BLOCK_M);
+                    tma_load_2d(smem_u32(smem_b + stage * B_STAGE_BYTES), &map_b, bar_full + 8 * stage, kb * BLOCK_K, nt * block_n);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int nt = tile % n_tiles;
+                const int n_size = min(block_n, n_total - nt * block_n);
+                const uint32_t idesc = make_idesc(BLOCK_M, n_size, (uint32_t)ab_bf16);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, err, 2);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_BLOCK_N);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase, err, 3);
+                    tcgen05_fence_after();
+                    const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                    const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+                        umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int wq = warp & 3;  // TMEM lane quarter
+        uint8_t* slab0 = smem_c + wq * 2 * C_SLAB_BYTES;
+        const float sc = scales[1];
+        int it = 0;
+        int buf = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int mt = tile / n_tiles, nt = tile % n_tiles;
+            const int n_size = min(block_n, n_total - nt * block_n);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+            mbar_wait(bar_tfull + 8 * acc, acc_phase, err, 4);
+            tcgen05_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * MAX_BLOCK_N);
+            for (int c0 = 0; c0 < n_size; c0 += 64) {
+                uint8_t* slab = slab0 + buf * C_SLAB_BYTES;
+                // the TMA store that last read this slab must be done with it
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32 * h), v);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+                    if (addend != nullptr) {
+                        // D = addend + scale * acc (orthonormalise.cu: Phi + Phi E); one 64-byte run of this thread's row
+                        const int64_t row = (int64_t)mt * BLOCK_M + wq * 32 + lane;
+                        const bool ok = row < m_rows;
+                        const uint4* src = (const uint4*)(addend + (size_t)(ok ? row : 0) * n_total + nt * block_n + c0 + 32 * h);
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const uint4 a = ok ? src[i4] : make_uint4(0, 0, 0, 0);
+                            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int i = 4 * i4 + j;
+                                pk[i] = pack_bf16(fmaf(__uint_as_float(v[2 * i]), sc, __uint_as_float(aw[j] << 16)),
+                                                  fmaf(__uint_as_float(v[2 * i + 1]), sc, __uint_as_float(aw[j] & 0xffff0000u)));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            pk[i] = pack_bf16(__uint_as_float(v[2 * i]) * sc, __uint_as_float(v[2 * i + 1]) * sc);
+                    }
+                    // row `lane` of the slab, 16-byte chunks 4h .. 4h+3, XOR-swizzled like SWIZZLE_128B
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int chunk = (4 * h + c) ^ (lane & 7);
+                        *(uint4*)(slab + lane * 128 + chunk * 16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&map_d, smem_u32(slab), nt * block_n + c0, mt * BLOCK_M + wq * 32);
+                    tma_store_commit();
+                }
+                buf ^= 1;
+            }
+            // all tcgen05.ld of this accumulator have completed (wait::ld above): hand it back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// 2-D row-major 16-bit tensor [rows][cols] (cols contiguous), box = box_cols x box_rows, SWIZZLE_128B
+static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                       uint32_t box_cols, uint32_t box_rows)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        gl_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return GL_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        gl_set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r, (unsigned long long)rows,
+                     (unsigned long long)cols, (unsigned long long)ld_elems, box_cols, box_rows);
+        return GL_ERR_CUDA;
+    }
+    return GL_OK;
+}
+
+// D[rows][n_pad] (bf16) = scales[1] * A[rows][k_pad] . Bt[n_pad][k_pad]^T (+ addend), A and Bt 16-bit K-major
+// (ab_bf16: 0 = fp16, 1 = bf16).  k_pad % 64 == 0; n_pad is 64, 128 or a multiple of 256 (gl_m_pad).
+int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
+                   const float* scales, const void* addend, void* D)
+{
+    GL_REQUIRE(k_pad % 64 == 0 && n_pad % 64 == 0, "gemm: k_pad %d / n_pad %d must be multiples of 64", k_pad, n_pad);
+    if (ctx->gemm_impl == 1) {
+        dim3 grid((unsigned)ceil_div(n_pad, 32), (unsigned)ceil_div(rows, 32));
+        GL_REQUIRE(ceil_div(rows, 32) < 2147483647ll, "gemm(simple): band too large");
+        if (ab_bf16)
+            k_gemm_simple<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bt, rows, n_pad,
+                                                                         k_pad, scales, (const __nv_bfloat16*)addend,
+                                                                         (__nv_bfloat16*)D);
+        else
+            k_gemm_simple<__half><<<grid, 256, 0, ctx->stream>>>((const __half*)A, (const __half*)Bt, rows, n_pad, k_pad, scales,
+                                                                  (const __nv_bfloat16*)addend, (__nv_bfloat16*)D);
+        GL_LAUNCH_CHECK(ctx);
+        return GL_OK;
+    }
+    const int block_n = n_pad < tc::MAX_BLOCK_N ? n_pad : tc::MAX_BLOCK_N;
+    GL_REQUIRE(n_pad % block_n == 0, "gemm: n_pad %d is not a multiple of the N tile %d", n_pad, block_n);
+    const CUtensorMapDataType dt = ab_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUtensorMap map_a, map_b, map_d;
+    GL_CHECK(make_map_2d(&map_a, dt, A, (uint64_t)rows, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, tc::BLOCK_M));
+    GL_CHECK(make_map_2d(&map_b, dt, Bt, (uint64_t)n_pad, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, (uint32_t)block_n));
+    GL_CHECK(make_map_2d(&map_d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, D, (uint64_t)rows, (uint64_t)n_pad, (uint64_t)n_pad, 64, 32));
+    const int m_tiles = (int)ceil_div(rows, tc::BLOCK_M);
+    const int n_tiles = n_pad / block_n;
+    const int k_blocks = k_pad / tc::BLOCK_K;
+    gl_buf* err = nullptr;
+    GL_CHECK(gl_alloc(ctx, sizeof(int) * 4, &err));
+    cudaMemsetAsync(err->ptr, 0, sizeof(int) * 4, ctx->stream);
+    GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    int grid = ctx->sm_count;
+    if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
+    tc::k_gemm_tcgen05<<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad,
+                                                                           block_n, ab_bf16, scales, (const __nv_bfloat16*)addend,
+                                                                           rows, (int*)err->ptr);
+    gl_buf_release(err);
+    GL_LAUNCH_CHECK(ctx);
+    return GL_OK;
+}
+
+int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi_out)
+{
+    const int p = L_B->p, p_pad = L_B->p_pad;
+    const int m = (int)phi_A->cols;
+    const int m_pad = gl_m_pad(m);
+    const int64_t rows = L_B->local_rows;
+    GL_REQUIRE(L_B->dscale, "nystroem: expected L_B (from gl_laplacian), got a bare K_B");
+    GL_REQUIRE(rows > 0, "nystroem: empty band");
+
+    gl_mat* phi = gl_mat_new(ctx, GL_MAT_PHI);
+    gl_buf *Wt = nullptr, *colmax = nullptr, *scales = nullptr;
+    int rc = GL_OK;
+    do {
+        phi->rows = ctx->n;
+        phi->cols = m;
+        phi->local_rows = rows;
+        phi->ld = m_pad;
+        phi->elem_bytes = 2;
+        phi->p = p;
+        phi->p_pad = p_pad;
+        phi->m = m;
+        phi->m_pad = m_pad;
+        phi->q0 = L_B->q0;
+        if ((rc = gl_alloc(ctx, sizeof(__nv_bfloat16) * (size_t)rows * m_pad, &phi->buf)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)m_pad * p_pad, &Wt)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad, &colmax)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * 4, &scales)) != GL_OK) break;
+
+        const float* U = (const float*)phi_A->buf->ptr;
+        const double* mu_inv = (const double*)eigvals_inv->buf->ptr;
+        const double* neg_alpha = (const double*)L_B->dscale->ptr;
+        k_w_colmax<<<m, 256, 0, ctx->stream>>>(U, (int)phi_A->ld, p, m, mu_inv, neg_alpha, (float*)colmax->ptr);
+        GL_LAUNCH_CHECK(ctx);
+        k_w_scale<<<1, 1024, 0, ctx->stream>>>((const float*)colmax->ptr, m, (float*)scales->ptr);
+        GL_LAUNCH_CHECK(ctx);
+        k_w_write<<<m_pad, 256, 0, ctx->stream>>>(U, (int)phi_A->ld, p, m, p_pad, m_pad, mu_inv, neg_alpha,
+                                                  (const float*)scales->ptr, (__half*)Wt->ptr);
+        GL_LAUNCH_CHECK(ctx);
+
+        if ((rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, p_pad, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
+                                 phi->buf->ptr)) != GL_OK) break;
+        k_phi_sample_rows<<<p, 128, 0, ctx->stream>>>(U, (int)phi_A->ld, p, m, (const uint32_t*)ctx->samples->ptr, phi->q0,
+                                                      phi->q0 + rows, m_pad, (__nv_bfloat16*)phi->buf->ptr);
+        GL_LAUNCH_CHECK(ctx);
+    } while (0);
+    if (Wt) gl_buf_release(Wt);
+    if (colmax) gl_buf_release(colmax);
+    if (scales) gl_buf_release(scales);
+    if (rc != GL_OK) {
+        gl_mat_destroy(phi);
+        return rc;
+    }
+    *phi_out = phi;
+    return GL_OK;
+}

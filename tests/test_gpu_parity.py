@@ -1,0 +1,261 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI against the golden
+fixtures (reference python modules + oracle) and against the oracle on seeded synthetic inputs.
+
+Tolerances (BASELINE.json north_star): sampled indices bit-exact; leading eigenvalues rel <= 1e-4;
+filtered image rel L2 <= 1e-3.  The filtered image differs from the input by only ~0.2-1 %, so the
+tests additionally bound the relative error of the CHANGE z - y."""
+import numpy as np
+import pytest
+
+import ipgl_b200 as gl
+from oracle import oracle_c as oc
+from oracle import oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+TOL_MU, TOL_Z, TOL_DZ = 1e-4, 1e-3, 2e-2
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = gl.Context(0)
+    yield c
+    c.close()
+
+
+def _src(g):
+    img = g["image"]
+    return np.repeat(img[:, :, None], 3, axis=2) if int(g["rgb"]) else img
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / np.linalg.norm(b))
+
+
+# ---------------------------------------------------------------------------------------------
+# a-1 sampling: bit-exact with the reference's python modules
+# ---------------------------------------------------------------------------------------------
+def test_sampling_bit_exact(ctx, golden):
+    tab = golden("sampling")
+    for key, ref in tab.items():
+        parts = key.split("_")
+        W, H = (int(v) for v in parts[1].split("x"))
+        p = int(parts[2])
+        ctx.set_synthetic_image(W, H, 1, 1)
+        if parts[0] == "uniform":
+            got = ctx.sampling(gl.SPATIALLY_UNIFORM, p)
+        else:
+            got = ctx.sampling(gl.RANDOM, p, seed=int(parts[3][1:]))
+        assert got.dtype == np.uint32 and np.array_equal(got, ref), key
+
+
+def test_random_sampling_with_collisions(ctx):
+    # tiny image, many samples: duplicates in the stream are certain, the top-up path must run
+    for (W, H, p, seed) in ((64, 64, 3000, 3), (40, 30, 1100, 11), (128, 64, 4000, 5)):
+        ctx.set_synthetic_image(W, H, 1, 1)
+        assert np.array_equal(ctx.sampling(gl.RANDOM, p, seed=seed), oc.random_sampling(W, H, p, seed))
+
+
+def test_synthetic_image_matches_oracle(ctx):
+    for (W, H, ch) in ((333, 222, 1), (257, 131, 3)):
+        ctx.set_synthetic_image(W, H, ch, 1234)
+        assert np.array_equal(ctx.get_image(), o.synthetic_image(W, H, ch, 1234))
+
+
+# ---------------------------------------------------------------------------------------------
+# a-2 / a-3 affinity + Laplacian against the reference python modules' K
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["test_uniform100", "cat_small_random50", "lion_photometric_h10", "test_spatial_h10",
+                                 "barbara_uniform256"])
+def test_affinity_and_laplacian(ctx, golden, tag):
+    g = golden(tag)
+    img, s = g["image"], g["sample_indices"]
+    kind, h_loc, h_val = str(g["kind"]), float(g["h_loc"]), float(g["h_val"])
+    ctx.set_image(img)
+    ctx.set_samples(s)
+    K_A, K_B = ctx.affinity(kind, h_loc, h_val)
+    if "ref_K_A" in g:
+        assert np.allclose(K_A.download(), g["ref_K_A"], rtol=1e-12, atol=1e-300)   # fp64, same formula as the reference
+    D = K_B.rowsums()
+    assert np.max(np.abs(D - g["ref_D"]) / g["ref_D"]) < 2e-6     # fp32 ex2 kernel values, fp64 final sum
+    # K_B itself (fp16, stored pixel-major): compare a slab against the oracle
+    n = img.size
+    KB = K_B.download()
+    assert KB.shape == (n, len(s))
+    cols = np.arange(0, n, max(1, n // 4096))
+    ref = o.affinity_rows(img, s, cols, kind, h_loc, h_val).T
+    assert np.max(np.abs(KB[cols] - ref)) < 6e-4                  # fp16 rounding of values in [0,1]
+    L_A, L_B = ctx.laplacian(K_A, K_B)
+    alpha = 1.0 / g["ref_D"].mean()
+    assert abs(L_B.info.scale + alpha) < 1e-6 * alpha             # L_B = -alpha K_B, no copy
+    LA = L_A.download()
+    LA_ref = alpha * (np.diag(g["ref_D"]) - o.affinity_rows(img, s, s, kind, h_loc, h_val))
+    assert np.max(np.abs(LA - LA_ref)) < 3e-6 * np.max(np.abs(LA_ref))
+
+
+# ---------------------------------------------------------------------------------------------
+# a-4/5 eigensolver alone
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("p", [17, 50, 256, 529, 1000])
+def test_eigensolver(ctx, p):
+    rng = np.random.RandomState(p)
+    # SPD, diagonally dominant-ish like L_A, with a few close eigenvalues
+    B = rng.rand(p, p) * np.exp(-np.abs(np.subtract.outer(np.arange(p), np.arange(p))) / 3.0)
+    A = np.diag(1.0 + rng.rand(p)) + 0.2 * (B + B.T) / 2
+    A += np.eye(p) * max(0.0, 0.05 - np.linalg.eigvalsh(A)[0])
+    L = ctx.upload(gl.MAT_KA, A)
+    m = p - 1
+    U, mu, mu_inv = ctx.eigensolve(L, m)
+    w, V = np.linalg.eigh(A)
+    got = mu.download()
+    assert got.shape == (m,)
+    assert np.all(np.diff(got) >= 0)
+    assert np.max(np.abs(got - w[:m]) / w[:m]) < 2e-5
+    assert np.allclose(mu_inv.download(), 1.0 / got, rtol=1e-12)
+    Ug = U.download()
+    assert Ug.shape == (p, m)
+    assert np.max(np.abs(Ug.T @ Ug - np.eye(m))) < 5e-5
+    assert np.max(np.abs(A @ Ug - Ug * got)) < 5e-5 * np.max(np.abs(w))
+
+
+# ---------------------------------------------------------------------------------------------
+# whole path against the golden fixtures (BASELINE.json configs 1-3 and friends)
+# ---------------------------------------------------------------------------------------------
+CASES = ["test_uniform100", "cat_small_random50", "barbara_uniform256", "lion_rgb_photometric500",
+         "lion_photometric_h10", "test_spatial_h10", "cat_small_uniform_m20"]
+
+
+def _run_case(ctx, g, **over):
+    src = _src(g)
+    prm = gl.default_params(affinity=str(g["kind"]), sampling=gl.RANDOM if str(g["method"]) == "random" else gl.SPATIALLY_UNIFORM,
+                            h_loc=float(g["h_loc"]), h_val=float(g["h_val"]), sample_size=int(g["p_req"]),
+                            seed=int(g["seed"]), num_eigvals=int(g["m"]), **over)
+    return src, ctx.run(src, prm)
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_pipeline_matches_golden(ctx, golden, tag):
+    g = golden(tag)
+    src, r = _run_case(ctx, g)
+    assert r["p"] == len(g["sample_indices"]) and r["m"] == int(g["m"])
+    assert np.array_equal(ctx.get_samples(), g["sample_indices"])              # bit-exact
+    mu = g["mu"]
+    assert np.max(np.abs(r["mu"] - mu) / mu) <= TOL_MU
+    z = g["z"].astype(np.float64)
+    assert _rel(r["z"], z) <= TOL_Z
+    assert _rel(r["z"] - src, z - src) <= TOL_DZ
+    assert r["z"].max() <= 255.0
+
+
+@pytest.mark.parametrize("tag", ["test_uniform100", "cat_small_random50"])
+def test_tcgen05_gemm_matches_cuda_core_checker(ctx, golden, tag):
+    g = golden(tag)
+    ctx.set_option("gemm", "simple")
+    try:
+        _, a = _run_case(ctx, g)
+    finally:
+        ctx.set_option("gemm", "tcgen05")
+    _, b = _run_case(ctx, g)
+    assert _rel(b["z"], a["z"].astype(np.float64)) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["test_uniform100", "cat_small_random50", "cat_small_uniform_m20"])
+def test_gram_schmidt_stage(ctx, golden, tag):
+    g = golden(tag)
+    src, r = _run_case(ctx, g, gram_schmidt=1)
+    z = g["z_gs"].astype(np.float64)
+    assert _rel(r["z"], z) <= TOL_Z
+    assert _rel(r["z"] - src, z - src) <= TOL_DZ
+
+
+def test_stage_by_stage_phi_properties(ctx, golden):
+    g = golden("cat_small_random50")
+    img, s = g["image"], g["sample_indices"]
+    ctx.set_image(img)
+    ctx.set_samples(s)
+    K_A, K_B = ctx.affinity()
+    L_A, L_B = ctx.laplacian(K_A, K_B)
+    U, mu, mu_inv = ctx.eigensolve(L_A, -1)
+    phi = ctx.nystroem(L_B, U, mu_inv)
+    P = phi.download()
+    assert P.shape == (img.size, len(s) - 1)
+    Ud = U.download()
+    # sample rows of Phi are Phi_A (nystroem.c:25-34), up to bf16 storage
+    assert np.max(np.abs(P[s.astype(np.int64)] - Ud)) <= 2 ** -8 * np.max(np.abs(Ud))
+    G = P.T @ P
+    assert np.linalg.norm(G - np.eye(G.shape[0])) < 3e-2          # nearly orthonormal before GS
+    # projector parity with the oracle (eigenvector signs are arbitrary: never compare Phi entrywise)
+    ref = o.run_pipeline(img, s, return_phi=True)
+    y = img.reshape(-1).astype(np.float64)
+    assert _rel(P @ (P.T @ y), ref["phi"] @ (ref["phi"].T @ y)) < 2e-3
+    norms = ctx.orthonormalise(phi)
+    Q = phi.download()
+    assert np.max(np.abs(Q.T @ Q - np.eye(Q.shape[1]))) < 2e-3    # orthonormal up to bf16 storage
+    _, nref = o.gram_schmidt(ref["phi"])
+    assert np.max(np.abs(norms - nref) / nref) < 5e-3
+    z = ctx.filter(phi, mu)
+    assert z.shape == img.shape and np.isfinite(z).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded synthetic inputs against the oracle, ragged sizes and edge cases
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H,ch,p,kind,method", [
+    (301, 203, 1, 77, "bilateral", "random"),       # ragged: n not a multiple of any tile
+    (640, 360, 1, 300, "bilateral", "uniform"),
+    (257, 129, 3, 130, "bilateral", "random"),      # colour (photometric RGB + spatial)
+    (200, 150, 3, 260, "photometric", "uniform"),
+    (129, 65, 1, 40, "spatial", "uniform"),
+])
+def test_synthetic_against_oracle(ctx, W, H, ch, p, kind, method):
+    img = o.synthetic_image(W, H, ch, seed=W + H)
+    prm = gl.default_params(affinity=kind, sampling=gl.RANDOM if method == "random" else gl.SPATIALLY_UNIFORM,
+                            sample_size=p, seed=42)
+    r = ctx.run(img, prm)
+    s = oc.random_sampling(W, H, p, 42) if method == "random" else oc.uniform_sampling(W, H, p)
+    assert np.array_equal(ctx.get_samples(), s)
+    ref = oc.run_pipeline(img, s, kind=kind)
+    assert np.max(np.abs(r["mu"] - ref["mu"]) / ref["mu"]) <= TOL_MU
+    assert _rel(r["z"], ref["z"]) <= TOL_Z
+    assert _rel(r["z"] - img, ref["z"] - img) <= TOL_DZ
+
+
+def test_filter_options(ctx, golden):
+    g = golden("test_uniform100")
+    img, s = g["image"], g["sample_indices"]
+    for gain, power in ((-1.0, 1.0), (3.0, 6.0), (0.0, 1.0)):
+        prm = gl.default_params(sample_size=100, gain=gain, power=power)
+        r = ctx.run(img, prm)
+        ref = o.run_pipeline(img, s, gain=gain, power=power)
+        assert _rel(r["z"], ref["z"]) <= TOL_Z
+        if gain == 0.0:
+            assert np.array_equal(r["z"], img.astype(np.float32))
+    # u8 output: clamp to [0,255] then truncate
+    prm = gl.default_params(sample_size=100)
+    z8 = np.zeros(img.shape, dtype=np.uint8)
+    r = ctx.run(img, prm, z8_out=z8)
+    assert np.array_equal(z8, o.quantise(r["z"]))
+
+
+def test_errors(ctx):
+    with pytest.raises(gl.GLError):
+        ctx.set_image(np.zeros((1, 1), dtype=np.uint8))
+    ctx.set_synthetic_image(64, 64, 1, 1)
+    with pytest.raises(gl.GLError):
+        ctx.set_samples(np.array([5, 3, 9], dtype=np.uint32))      # not ascending
+    with pytest.raises(gl.GLError):
+        ctx.set_samples(np.array([5, 4096], dtype=np.uint32))      # out of range
+    with pytest.raises(gl.GLError):
+        ctx.sampling(gl.RANDOM, 64 * 64 + 1)
+
+
+def test_repeatability_and_launch_count(ctx, golden):
+    g = golden("cat_small_random50")
+    n0 = ctx.kernel_launches()
+    _, a = _run_case(ctx, g)
+    n1 = ctx.kernel_launches()
+    _, b = _run_case(ctx, g)
+    assert n1 - n0 >= 15
+    assert np.array_equal(a["z"], b["z"]) and np.array_equal(a["mu"], b["mu"])   # deterministic reductions
+    t = ctx.stage_ms()
+    assert t["affinity"] > 0 and t["eigen"] > 0 and t["nystroem"] > 0 and t["filter"] > 0
