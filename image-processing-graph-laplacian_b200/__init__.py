@@ -26,11 +26,13 @@ AFFINITY_KINDS = {BILATERAL: 0, PHOTOMETRIC: 1, SPATIAL: 2}
 RANDOM, SPATIALLY_UNIFORM = "random", "spatially_uniform"
 # gl_mat_kind
 MAT_KA, MAT_KB, MAT_EIGVEC, MAT_DIAG, MAT_PHI = 1, 2, 3, 4, 5
-STAGES = ["h2d", "sampling", "affinity", "laplacian", "eigen", "nystroem", "gram_schmidt", "filter", "d2h", "total"]
+STAGES = ["h2d", "sampling", "affinity", "laplacian", "eigen", "nystroem", "gram_schmidt", "filter", "d2h", "total",
+          "k_affinity_b", "k_gemm", "k_filter_project", "k_filter_apply", "k_jacobi"]
 
 EXPORTS = [
     "gl_version", "gl_last_error", "gl_default_params", "gl_device_count", "gl_kernel_launches",
-    "gl_ctx_create", "gl_ctx_destroy", "gl_ctx_sync", "gl_ctx_stage_ms", "gl_ctx_set_option",
+    "gl_ctx_create", "gl_ctx_destroy", "gl_ctx_sync", "gl_ctx_stage_ms", "gl_ctx_set_option", "gl_ctx_mark",
+    "gl_ctx_mark_elapsed_ms",
     "gl_comm_unique_id", "gl_comm_init",
     "gl_set_image", "gl_set_image_rows", "gl_set_synthetic_image", "gl_get_image", "gl_get_band",
     "gl_sampling_uniform", "gl_sampling_random", "gl_set_samples", "gl_get_samples",
@@ -82,6 +84,8 @@ def lib():
         L.gl_ctx_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.gl_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
         L.gl_kernel_launches.argtypes = [vp, C.POINTER(C.c_longlong)]
+        L.gl_ctx_mark.argtypes = [vp, C.c_int]
+        L.gl_ctx_mark_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.gl_comm_unique_id.argtypes = [vp]
         L.gl_comm_init.argtypes = [vp, vp]
         L.gl_set_image.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
@@ -232,6 +236,14 @@ class Context:
         a = (C.c_float * len(STAGES))()
         _check(lib().gl_ctx_stage_ms(self.h, a))
         return dict(zip(STAGES, list(a)))
+
+    def mark(self, slot):
+        _check(lib().gl_ctx_mark(self.h, slot))
+
+    def elapsed_ms(self, a, b) -> float:
+        ms = C.c_float()
+        _check(lib().gl_ctx_mark_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
 
     def kernel_launches(self) -> int:
         n = C.c_longlong()

@@ -194,6 +194,7 @@ static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float*
     const size_t smem = sizeof(float) * ((size_t)p_pad + 2 * 8 * 64 + (size_t)(2 + C) * AFF_TP);
     GL_CUDA_CHECK(cudaFuncSetAttribute(k_affinity_B<KIND, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const float log2e = 1.4426950408889634f;
+    StageTimer kt(ctx, GL_T_K_AFFINITY_B);
     k_affinity_B<KIND, C><<<grid, AFF_THREADS, smem, ctx->stream>>>(
         (const uint8_t*)ctx->img->ptr, sf, p_pad, ctx->width, ctx->q0, ctx->q1, (float)(-log2e / (h_loc * h_loc)),
         (float)(-log2e / (h_val * h_val)), KB, partial);

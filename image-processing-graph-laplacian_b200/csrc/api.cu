@@ -90,6 +90,7 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
         GL_CUDA_CHECK(cudaEventCreate(&ctx->ev_begin[i]));
         GL_CUDA_CHECK(cudaEventCreate(&ctx->ev_end[i]));
     }
+    for (int i = 0; i < 8; ++i) GL_CUDA_CHECK(cudaEventCreate(&ctx->marks[i]));
     const char* v = getenv("GLB200_VERBOSE");
     ctx->verbose = v ? atoi(v) : 0;
     if (const char* g = getenv("GLB200_GEMM")) gl_ctx_set_option(ctx, "gemm", g);
@@ -144,6 +145,7 @@ int gl_ctx_destroy(gl_ctx* ctx)
         cudaEventDestroy(ctx->ev_begin[i]);
         cudaEventDestroy(ctx->ev_end[i]);
     }
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->marks[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GL_OK;
@@ -157,6 +159,21 @@ int gl_ctx_stage_ms(gl_ctx* ctx, float* ms)
         ms[i] = 0.f;
         if (ctx->ev_valid[i]) cudaEventElapsedTime(&ms[i], ctx->ev_begin[i], ctx->ev_end[i]);
     }
+    return GL_OK;
+}
+
+int gl_ctx_mark(gl_ctx* ctx, int slot)
+{
+    GL_REQUIRE(ctx && slot >= 0 && slot < 8, "gl_ctx_mark: bad slot");
+    GL_CUDA_CHECK(cudaEventRecord(ctx->marks[slot], ctx->stream));
+    return GL_OK;
+}
+
+int gl_ctx_mark_elapsed_ms(gl_ctx* ctx, int a, int b, float* ms)
+{
+    GL_REQUIRE(ctx && ms && a >= 0 && a < 8 && b >= 0 && b < 8, "gl_ctx_mark_elapsed_ms: bad args");
+    GL_CUDA_CHECK(cudaEventSynchronize(ctx->marks[b]));
+    GL_CUDA_CHECK(cudaEventElapsedTime(ms, ctx->marks[a], ctx->marks[b]));
     return GL_OK;
 }
 
@@ -651,7 +668,8 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
     GL_REQUIRE(ctx && prm, "gl_run_resident: null");
     GL_REQUIRE(ctx->n > 0, "gl_run_resident: no image on the device");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
-    cudaEventRecord(ctx->ev_begin[GL_T_TOTAL], ctx->stream);
+    if (!ctx->total_started) cudaEventRecord(ctx->ev_begin[GL_T_TOTAL], ctx->stream);
+    ctx->total_started = false;
 
     unsigned requested = prm->sample_size ? prm->sample_size : (unsigned)((double)ctx->n * 0.01);  // image_processing.c:187
     unsigned p = 0;
@@ -690,7 +708,11 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
 int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, const gl_params* prm, float* z_f32,
            uint8_t* z_u8, unsigned* p_out, int* m_out, double* eigvals_out)
 {
+    GL_REQUIRE(ctx, "gl_run: null");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaEventRecord(ctx->ev_begin[GL_T_TOTAL], ctx->stream);
     GL_CHECK(gl_set_image(ctx, pixels, width, height, channels));
+    ctx->total_started = true;
     return gl_run_resident(ctx, prm, z_f32, z_u8, p_out, m_out, eigvals_out);
 }
 

@@ -98,6 +98,7 @@ struct gl_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     long long launches = 0;
+    bool total_started = false;
 
     // image (whole image on every rank)
     int width = 0, height = 0, channels = 0;
@@ -118,6 +119,7 @@ struct gl_ctx {
     // stage timers
     cudaEvent_t ev_begin[GL_T_COUNT] = {}, ev_end[GL_T_COUNT] = {};
     bool ev_valid[GL_T_COUNT] = {};
+    cudaEvent_t marks[8] = {};
 
     // pinned staging for small D2H/H2D
     void* pinned = nullptr;

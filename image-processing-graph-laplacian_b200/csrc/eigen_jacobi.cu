@@ -326,7 +326,10 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         unsigned* off = (unsigned*)ctl->ptr;
         int* done = (int*)((unsigned*)ctl->ptr + max_sweeps);
         void* args[] = {&Gp, &p_, &nb_, &ms, &tol, &off, &done};
-        GL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));
+        {
+            StageTimer kt(ctx, GL_T_K_JACOBI);
+            GL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));
+        }
         ctx->launches++;
 
         k_jacobi_norms<<<(unsigned)ceil_div(p, 8), 256, 0, ctx->stream>>>((const float*)G->ptr, p, (double*)lam->ptr);

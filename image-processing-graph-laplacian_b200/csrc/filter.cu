@@ -247,14 +247,20 @@ static int run_filter(gl_ctx* ctx, gl_mat* phi, const FilterGeom& g, const doubl
     const int m = phi->m, m_pad = phi->m_pad;
     const uint8_t* y = (const uint8_t*)ctx->img->ptr + (size_t)phi->q0 * C;
     const __nv_bfloat16* P = (const __nv_bfloat16*)phi->buf->ptr;
-    k_filter_project<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, partial);
+    {
+        StageTimer kt(ctx, GL_T_K_FILTER_PROJECT);
+        k_filter_project<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, partial);
+    }
     GL_LAUNCH_CHECK(ctx);
     k_filter_reduce<<<(unsigned)ceil_div(m_pad * C, 256), 256, 0, ctx->stream>>>(partial, grid, m_pad * C, c);
     GL_LAUNCH_CHECK(ctx);
     GL_CHECK(gl_allreduce_f32(ctx, c, (size_t)m_pad * C));
     k_filter_weights<<<(unsigned)ceil_div(m_pad * C, 256), 256, 0, ctx->stream>>>(c, f, m, m_pad, C, (float)gain, w);
     GL_LAUNCH_CHECK(ctx);
-    k_filter_apply<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, w, clip_low, z, z8);
+    {
+        StageTimer kt(ctx, GL_T_K_FILTER_APPLY);
+        k_filter_apply<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, w, clip_low, z, z8);
+    }
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;
 }

@@ -532,6 +532,7 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     int grid = ctx->sm_count;
     if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
+    StageTimer kt(ctx, GL_T_K_GEMM);
     tc::k_gemm_tcgen05<<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad,
                                                                            block_n, ab_bf16, scales, (const __nv_bfloat16*)addend,
                                                                            rows, (int*)err->ptr);

@@ -80,7 +80,11 @@ typedef struct gl_mat_info {
  * hpc/image_processing.c:198-233,249,268). */
 enum gl_stage {
     GL_T_H2D = 0, GL_T_SAMPLING, GL_T_AFFINITY, GL_T_LAPLACIAN, GL_T_EIGEN, GL_T_NYSTROEM,
-    GL_T_GRAM_SCHMIDT, GL_T_FILTER, GL_T_D2H, GL_T_TOTAL, GL_T_COUNT
+    GL_T_GRAM_SCHMIDT, GL_T_FILTER, GL_T_D2H, GL_T_TOTAL,
+    /* single-kernel timers (roofline numerators): the K_B affinity kernel, the extrapolation GEMM kernel,
+     * the two filter passes */
+    GL_T_K_AFFINITY_B, GL_T_K_GEMM, GL_T_K_FILTER_PROJECT, GL_T_K_FILTER_APPLY, GL_T_K_JACOBI,
+    GL_T_COUNT
 };
 
 typedef struct gl_params {
@@ -109,6 +113,9 @@ GL_API int gl_ctx_destroy(gl_ctx* ctx);
 GL_API int gl_ctx_sync(gl_ctx* ctx);
 GL_API int gl_ctx_stage_ms(gl_ctx* ctx, float* ms /* [GL_T_COUNT] */); /* CUDA-event times of the last run of each stage */
 GL_API int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value); /* tuning knobs, see DESIGN.md */
+/* CUDA-event marks on the context stream (slot 0..7) and the device time between two of them. */
+GL_API int gl_ctx_mark(gl_ctx* ctx, int slot);
+GL_API int gl_ctx_mark_elapsed_ms(gl_ctx* ctx, int slot_a, int slot_b, float* ms);
 /* NCCL bootstrap (world > 1): rank 0 makes a 128-byte id, the host shares it, every rank joins. */
 GL_API int gl_comm_unique_id(void* id128);
 GL_API int gl_comm_init(gl_ctx* ctx, const void* id128);

@@ -377,14 +377,29 @@ ORC_API int orc_pipeline(const uint8_t* img, const orc_params* P, const uint32_t
     double* phi = (double*)calloc(nband * (size_t)m, sizeof(double));
     if (!phi) return -2;
     {
-        /* phi[rest[k], :] = sum_i KB[i,k] Wm[i,:]  (MatTransposeMatMult, nystroem.c:42) */
-#pragma omp parallel for schedule(dynamic, 64)
-        for (size_t k = 0; k < nb; ++k) {
-            double* out = phi + ((size_t)rest[k] - q0) * m;
-            for (int i = 0; i < p; ++i) {
-                const double kv = KB[(size_t)i * nb + k];
-                const double* w = Wm + (size_t)i * m;
-                for (int j = 0; j < m; ++j) out[j] += kv * w[j];
+        /* phi[rest[k], :] = sum_i KB[i,k] Wm[i,:]  (MatTransposeMatMult, nystroem.c:42), cache-blocked:
+         * 8 pixels x 256 eigen-columns of accumulators stay in L1 while the p samples stream by. */
+        enum { PB = 8, JBK = 256 };
+#pragma omp parallel for schedule(dynamic, 8)
+        for (size_t k0 = 0; k0 < nb; k0 += PB) {
+            const int pb = (int)((nb - k0) < PB ? (nb - k0) : PB);
+            double acc[PB][JBK];
+            for (int j0 = 0; j0 < m; j0 += JBK) {
+                const int jb = (m - j0) < JBK ? (m - j0) : JBK;
+                for (int b = 0; b < PB; ++b)
+                    for (int j = 0; j < jb; ++j) acc[b][j] = 0.0;
+                for (int i = 0; i < p; ++i) {
+                    const double* kv = KB + (size_t)i * nb + k0;
+                    const double* w = Wm + (size_t)i * m + j0;
+                    for (int b = 0; b < pb; ++b) {
+                        const double kb_ = kv[b];
+                        for (int j = 0; j < jb; ++j) acc[b][j] += kb_ * w[j];
+                    }
+                }
+                for (int b = 0; b < pb; ++b) {
+                    double* out = phi + ((size_t)rest[k0 + b] - q0) * m + j0;
+                    for (int j = 0; j < jb; ++j) out[j] = acc[b][j];
+                }
             }
         }
         for (int i = 0; i < p; ++i)
