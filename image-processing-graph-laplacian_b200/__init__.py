@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -168,6 +169,7 @@ class Mat:
 
     def __init__(self, ctx, handle):
         self.ctx, self.h = ctx, C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+        ctx._mats.add(self)
 
     @property
     def info(self) -> MatInfo:
@@ -195,9 +197,10 @@ class Mat:
         return out
 
     def destroy(self):
-        if self.h:
+        # a handle must not outlive its context (the buffers go back to the context's allocator)
+        if self.h and self.ctx is not None and self.ctx.h:
             lib().gl_mat_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -214,9 +217,12 @@ class Context:
         _check(lib().gl_ctx_create(C.byref(self.h), device, rank, world))
         self.rank, self.world = rank, world
         self.shape = None
+        self._mats = weakref.WeakSet()
 
     def close(self):
         if self.h:
+            for m in list(self._mats):
+                m.destroy()
             lib().gl_ctx_destroy(self.h)
             self.h = None
 

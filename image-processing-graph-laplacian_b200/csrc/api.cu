@@ -530,14 +530,6 @@ __global__ void k_half_to_f64(const __half* __restrict__ src, int64_t ld, int64_
     int64_t r = i / cols, c = i % cols;
     dst[i] = scale * (double)__half2float(src[r * ld + c]);
 }
-__global__ void k_bf16_to_f64(const __nv_bfloat16* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, double scale,
-                              double* __restrict__ dst)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * cols) return;
-    int64_t r = i / cols, c = i % cols;
-    dst[i] = scale * (double)__bfloat162float(src[r * ld + c]);
-}
 __global__ void k_colmajor_f32_to_f64(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols,
                                       double* __restrict__ dst)
 {
@@ -590,7 +582,7 @@ int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap)
         k_half_to_f64<<<blocks, T, 0, ctx->stream>>>((const __half*)m->buf->ptr, m->ld, rows, cols, m->scale, d);
         break;
     case GL_MAT_PHI:
-        k_bf16_to_f64<<<blocks, T, 0, ctx->stream>>>((const __nv_bfloat16*)m->buf->ptr, m->ld, rows, cols, m->scale, d);
+        k_half_to_f64<<<blocks, T, 0, ctx->stream>>>((const __half*)m->buf->ptr, m->ld, rows, cols, m->scale, d);
         break;
     case GL_MAT_EIGVEC:
         k_colmajor_f32_to_f64<<<blocks, T, 0, ctx->stream>>>((const float*)m->buf->ptr, m->ld, rows, cols, d);

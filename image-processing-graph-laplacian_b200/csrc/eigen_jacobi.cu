@@ -62,9 +62,9 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, unsign
     extern __shared__ __align__(16) float jsm[];
     float* P = jsm;                          // [p][16]
     float* red = P + (size_t)p * JP;         // [16][256]
-    float* Bm = red + 16 * 256;              // [16][17]
-    float* Qm = Bm + JP * 17;                // [16][17]
-    float* cs = Qm + JP * 17;                // [8][2]
+    double* Bm = (double*)(red + 16 * 256);  // [16][17]  Gram block, fp64 from here on: the rotations that are
+    double* Qm = Bm + JP * 17;               // [16][17]  accumulated into Q must stay orthogonal to ~1e-16, or the
+    double* cs = Qm + JP * 17;               // [8][2]    column norms (= eigenvalues) drift by ~1e-6 per update
     int* role = (int*)(cs + 16);             // [16]  (pair << 1) | is_second
     int* pq = role + JP;                     // [8][2]
     __shared__ float s_off;
@@ -116,19 +116,19 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, unsign
                 }
                 __syncthreads();
                 {
-                    float s = 0.f;
+                    double s = 0.0;
 #pragma unroll
-                    for (int rg = 0; rg < 16; ++rg) s += red[rg * 256 + tid];
+                    for (int rg = 0; rg < 16; ++rg) s += (double)red[rg * 256 + tid];
                     Bm[bi * 17 + bj] = s;
-                    Qm[bi * 17 + bj] = (bi == bj) ? 1.f : 0.f;
+                    Qm[bi * 17 + bj] = (bi == bj) ? 1.0 : 0.0;
                 }
                 __syncthreads();
                 // ---- how far from orthogonal is this pair (drives the sweep loop) ----
                 {
                     float rel = 0.f;
                     if (bi < bj) {
-                        const float dii = Bm[bi * 17 + bi], djj = Bm[bj * 17 + bj];
-                        if (dii > 0.f && djj > 0.f) rel = fabsf(Bm[bi * 17 + bj]) * rsqrtf(dii * djj);
+                        const double dii = Bm[bi * 17 + bi], djj = Bm[bj * 17 + bj];
+                        if (dii > 0.0 && djj > 0.0) rel = (float)(fabs(Bm[bi * 17 + bj]) / sqrt(dii * djj));
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) rel = fmaxf(rel, __shfl_xor_sync(0xffffffffu, rel, o));
@@ -146,16 +146,17 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, unsign
                             if (tid < JB) {
                                 int a, b;
                                 tournament(st, tid, JP, a, b);
-                                const float app = Bm[a * 17 + a], aqq = Bm[b * 17 + b], apq = Bm[a * 17 + b];
-                                float c = 1.f, s = 0.f;
-                                if (app > 0.f && aqq > 0.f) {
-                                    const float rel = fabsf(apq) * rsqrtf(app * aqq);
-                                    if (rel > 1e-9f) {
-                                        const float tau = (aqq - app) / (2.f * apq);
-                                        const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-                                        c = rsqrtf(1.f + t * t);
+                                const double app = Bm[a * 17 + a], aqq = Bm[b * 17 + b], apq = Bm[a * 17 + b];
+                                double c = 1.0, s = 0.0;
+                                if (app > 0.0 && aqq > 0.0) {
+                                    const double reld = fabs(apq) / sqrt(app * aqq);
+                                    if (reld > 1e-13) {
+                                        const double tau = (aqq - app) / (2.0 * apq);
+                                        const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                                        c = 1.0 / sqrt(1.0 + t * t);
                                         s = t * c;
                                     }
+                                    const float rel = (float)reld;
                                     if (rel > s_off) atomicMax((unsigned*)&s_off, __float_as_uint(rel));
                                 }
                                 cs[2 * tid] = c;
@@ -166,13 +167,13 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, unsign
                                 role[b] = (tid << 1) | 1;
                             }
                             __syncthreads();
-                            float nb_, nq_;
+                            double nb_, nq_;
                             {
                                 const int ri = role[bi], rj = role[bj];
                                 const int ki = ri >> 1, kj = rj >> 1;
-                                const float ci = cs[2 * ki], si = cs[2 * ki + 1], cj = cs[2 * kj], sj = cs[2 * kj + 1];
+                                const double ci = cs[2 * ki], si = cs[2 * ki + 1], cj = cs[2 * kj], sj = cs[2 * kj + 1];
                                 const int ip = pq[2 * ki], iq = pq[2 * ki + 1], jp = pq[2 * kj], jq = pq[2 * kj + 1];
-                                float x_ip, x_iq;  // (B J)[ip][bj], (B J)[iq][bj]
+                                double x_ip, x_iq;  // (B J)[ip][bj], (B J)[iq][bj]
                                 if ((rj & 1) == 0) {
                                     x_ip = cj * Bm[ip * 17 + jp] - sj * Bm[ip * 17 + jq];
                                     x_iq = cj * Bm[iq * 17 + jp] - sj * Bm[iq * 17 + jq];
@@ -201,7 +202,7 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, unsign
 #pragma unroll
                     for (int k = 0; k < JP; ++k)
 #pragma unroll
-                        for (int x = 0; x < 4; ++x) q[k][x] = Qm[k * 17 + 4 * cgp + x];
+                        for (int x = 0; x < 4; ++x) q[k][x] = (float)Qm[k * 17 + 4 * cgp + x];
                     float* dst = (cgp < 2) ? (GI + cgp * 4) : (GJ + (cgp - 2) * 4);
                     for (int r = tid >> 2; r < p; r += J_THREADS / 4) {
                         const float4 v0 = *(const float4*)(P + (size_t)r * JP);
@@ -243,6 +244,80 @@ __global__ void k_jacobi_norms(const float* __restrict__ G, int p, double* __res
     if ((threadIdx.x & 31) == 0) lam[c] = sqrt(acc);
 }
 
+// Rayleigh quotients in fp64 against the ORIGINAL matrix: mu_c = (g_c^T A g_c) / (g_c^T g_c).  The fp32 sweeps leave
+// eigenvector errors of ~1e-6..1e-5; the quotient's error is their square, so eigenvalues come out at fp64-level
+// accuracy whatever the conditioning of A.  CTA = 64 rows x 64 columns of V = A G, 256 threads x (4 x 4), K loop of 16;
+// V is never stored: each CTA emits partial numerators for its 64 columns (fixed-order reduction afterwards).
+__global__ void __launch_bounds__(256) k_rayleigh_partial(const double* __restrict__ A, const float* __restrict__ G, int p,
+                                                          double* __restrict__ part /* [row_tiles][cols_pad] */, int cols_pad,
+                                                          int cols /* columns that exist in G */)
+{
+    __shared__ double As[16][64 + 1], Us[16][64 + 1];
+    __shared__ double red[16][64];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int j0 = blockIdx.x * 64, i0 = blockIdx.y * 64;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int k0 = 0; k0 < p; k0 += 16) {
+        for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
+            const int kk = idx & 15, ii = idx >> 4;          // A[i0+ii][k0+kk], 16 contiguous doubles per row
+            const int i = i0 + ii, k = k0 + kk;
+            As[kk][ii] = (i < p && k < p) ? A[(size_t)i * p + k] : 0.0;
+            const int jj = idx & 63, k2 = idx >> 6;          // G column j0+jj, row k0+k2
+            const int c = j0 + jj, kr = k0 + k2;
+            Us[k2][jj] = (kr < p && c < cols) ? (double)G[(size_t)(c / JB) * p * JB + (size_t)kr * JB + (c % JB)] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double av[4], uv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) av[a] = As[kk][ty * 4 + a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) uv[b] = Us[kk][tx * 4 + b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], uv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+    // numerator partials: sum_i G[i][c] * V[i][c] over this CTA's 64 rows
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int c = j0 + tx * 4 + b;
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = i0 + ty * 4 + a;
+            if (i < p && c < cols) s += (double)G[(size_t)(c / JB) * p * JB + (size_t)i * JB + (c % JB)] * acc[a][b];
+        }
+        red[ty][tx * 4 + b] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) s += red[r][threadIdx.x];
+        part[(size_t)blockIdx.y * cols_pad + j0 + threadIdx.x] = s;
+    }
+}
+
+// mu_c = sum_tiles(part) / lam_c^2 ; also keeps lam (the norm) for the normalisation
+__global__ void k_rayleigh_finish(const double* __restrict__ part, int row_tiles, int cols_pad, int p,
+                                  const double* __restrict__ lam, double* __restrict__ mu)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p) return;
+    double s = 0.0;
+    for (int t = 0; t < row_tiles; ++t) s += part[(size_t)t * cols_pad + c];
+    const double l = lam[c];
+    mu[c] = s / (l * l);
+}
+
 // ascending order of the eigenvalues: one CTA, bitonic sort of (lambda, index)
 __global__ void __launch_bounds__(1024, 1) k_jacobi_sort(const double* __restrict__ lam, int p, int N, int* __restrict__ order)
 {
@@ -273,14 +348,15 @@ __global__ void __launch_bounds__(1024, 1) k_jacobi_sort(const double* __restric
 }
 
 // U[:, j] = g_order[j] / lambda, column-major fp32 with leading dimension ld; mu / 1/mu in fp64
-__global__ void k_jacobi_extract(const float* __restrict__ G, const double* __restrict__ lam, const int* __restrict__ order, int p,
-                                 int m, int ld, float* __restrict__ U, double* __restrict__ mu, double* __restrict__ mu_inv)
+__global__ void k_jacobi_extract(const float* __restrict__ G, const double* __restrict__ lam, const double* __restrict__ ray,
+                                 const int* __restrict__ order, int p, int m, int ld, float* __restrict__ U,
+                                 double* __restrict__ mu, double* __restrict__ mu_inv)
 {
     const int j = blockIdx.x;
     if (j >= m) return;
     const int c = order[j];
-    const double l = lam[c];
-    const float inv = (float)(1.0 / l);
+    const float inv = (float)(1.0 / lam[c]);
+    const double l = ray[c];
     const float* col = G + (size_t)(c / JB) * p * JB + (c % JB);
     for (int r = threadIdx.x; r < ld; r += blockDim.x) U[(size_t)j * ld + r] = r < p ? col[(size_t)r * JB] * inv : 0.f;
     if (threadIdx.x == 0) {
@@ -293,13 +369,15 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
 {
     const int p = (int)L_A->rows;
     const int nb = (int)(round_up(p, JP) / JB);  // even number of panels
-    const size_t smem = sizeof(float) * ((size_t)p * JP + 16 * 256 + 2 * JP * 17 + 16) + sizeof(int) * (JP + 2 * JB);
+    const size_t smem = sizeof(float) * ((size_t)p * JP + 16 * 256) + sizeof(double) * (2 * JP * 17 + 16) + sizeof(int) * (JP + 2 * JB);
     if (smem > 227 * 1024) {
         gl_set_error("eigensolve: p = %d needs %zu bytes of shared memory per CTA (limit 227 KB)", p, smem);
         return GL_ERR_UNSUPPORTED;
     }
     GL_REQUIRE(p < (1 << 24), "eigensolve: p too large");
-    gl_buf *G = nullptr, *lam = nullptr, *order = nullptr, *ctl = nullptr;
+    gl_buf *G = nullptr, *lam = nullptr, *order = nullptr, *ctl = nullptr, *ray = nullptr, *part = nullptr;
+    const int cols_pad = nb * JB;
+    const int row_tiles = (int)ceil_div(p, 64);
     gl_mat *U = nullptr, *mu = nullptr, *mui = nullptr;
     int rc = GL_OK;
     const int max_sweeps = ctx->jacobi_max_sweeps;
@@ -307,6 +385,8 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)nb * p * JB, &G)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)p, &lam)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(int) * (size_t)p, &order)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)p, &ray)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)row_tiles * (cols_pad + 64), &part)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(unsigned) * (size_t)(max_sweeps + 4), &ctl)) != GL_OK) break;
         GL_CUDA_CHECK(cudaMemsetAsync(ctl->ptr, 0, sizeof(unsigned) * (size_t)(max_sweeps + 4), ctx->stream));
         const int64_t total = (int64_t)nb * p * JB;
@@ -334,11 +414,20 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
 
         k_jacobi_norms<<<(unsigned)ceil_div(p, 8), 256, 0, ctx->stream>>>((const float*)G->ptr, p, (double*)lam->ptr);
         GL_LAUNCH_CHECK(ctx);
+        {
+            dim3 gr((unsigned)ceil_div(cols_pad, 64), (unsigned)row_tiles);
+            k_rayleigh_partial<<<gr, 256, 0, ctx->stream>>>((const double*)L_A->buf->ptr, (const float*)G->ptr, p, (double*)part->ptr,
+                                                            cols_pad + 64, cols_pad);
+            GL_LAUNCH_CHECK(ctx);
+            k_rayleigh_finish<<<(unsigned)ceil_div(p, 128), 128, 0, ctx->stream>>>((const double*)part->ptr, row_tiles, cols_pad + 64, p,
+                                                                                   (const double*)lam->ptr, (double*)ray->ptr);
+            GL_LAUNCH_CHECK(ctx);
+        }
         int N = 2;
         while (N < p) N <<= 1;
         GL_REQUIRE(N <= 8192, "eigensolve: p too large for the single-CTA sort");
         GL_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-        k_jacobi_sort<<<1, 1024, (size_t)N * 8, ctx->stream>>>((const double*)lam->ptr, p, N, (int*)order->ptr);
+        k_jacobi_sort<<<1, 1024, (size_t)N * 8, ctx->stream>>>((const double*)ray->ptr, p, N, (int*)order->ptr);
         GL_LAUNCH_CHECK(ctx);
 
         U = gl_mat_new(ctx, GL_MAT_EIGVEC);
@@ -357,9 +446,9 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         *mui = *mu;
         mui->buf = nullptr;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m, &mui->buf)) != GL_OK) break;
-        k_jacobi_extract<<<m, 256, 0, ctx->stream>>>((const float*)G->ptr, (const double*)lam->ptr, (const int*)order->ptr, p, m,
-                                                     (int)U->ld, (float*)U->buf->ptr, (double*)mu->buf->ptr,
-                                                     (double*)mui->buf->ptr);
+        k_jacobi_extract<<<m, 256, 0, ctx->stream>>>((const float*)G->ptr, (const double*)lam->ptr, (const double*)ray->ptr,
+                                                     (const int*)order->ptr, p, m, (int)U->ld, (float*)U->buf->ptr,
+                                                     (double*)mu->buf->ptr, (double*)mui->buf->ptr);
         GL_LAUNCH_CHECK(ctx);
 
         // convergence report (one small D2H; the solve itself never synchronises with the host)
@@ -382,6 +471,8 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
     if (lam) gl_buf_release(lam);
     if (order) gl_buf_release(order);
     if (ctl) gl_buf_release(ctl);
+    if (ray) gl_buf_release(ray);
+    if (part) gl_buf_release(part);
     if (rc != GL_OK) {
         gl_mat_destroy(U);
         gl_mat_destroy(mu);

@@ -2,7 +2,7 @@
 // Replaces ComputeResultFromLaplacian (hpc/display.c:58-83) with pngbytes2OneColMat (hpc/utils.c:461-486),
 // AboveXSetY (:652-703) and OneColMat2pngbytes (:492-534).
 //
-// Two bandwidth-bound passes over Phi (bf16, [band pixels][m_pad], one 16-byte load = 8 columns):
+// Two bandwidth-bound passes over Phi (fp16, [band pixels][m_pad], one 16-byte load = 8 columns):
 //   (i)  c = Phi^T y : thread <-> (row lane, column group); 8*C fp32 accumulators per thread, rows streamed with
 //        4 loads in flight per thread; per-CTA partials, fixed-order reduction (deterministic), one small
 //        allreduce over ranks;
@@ -38,15 +38,14 @@ __device__ __forceinline__ uint4 ld_stream(const void* p)
 }
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8])
 {
-    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
-    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
-    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
-    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+    const float2 a = __half22float2(*(const __half2*)&v.x), b = __half22float2(*(const __half2*)&v.y);
+    const float2 c = __half22float2(*(const __half2*)&v.z), d = __half22float2(*(const __half2*)&v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
 // (i) partial[blockIdx][j*C + ch] = sum over this CTA's rows of Phi[row][j] * y[row][ch]
 template <int C, int NG>
-__global__ void __launch_bounds__(FL_THREADS) k_filter_project(const __nv_bfloat16* __restrict__ phi, int64_t rows, int m_pad, int G,
+__global__ void __launch_bounds__(FL_THREADS) k_filter_project(const __half* __restrict__ phi, int64_t rows, int m_pad, int G,
                                                                int TPR, int RL, const uint8_t* __restrict__ y /* band base */,
                                                                float* __restrict__ partial)
 {
@@ -143,7 +142,7 @@ __global__ void k_filter_weights(const float* __restrict__ c, const double* __re
 
 // (ii) z[row][ch] = y + sum_j Phi[row][j] * w[j][ch]; clip; optional u8
 template <int C, int NG>
-__global__ void __launch_bounds__(FL_THREADS) k_filter_apply(const __nv_bfloat16* __restrict__ phi, int64_t rows, int m_pad, int G,
+__global__ void __launch_bounds__(FL_THREADS) k_filter_apply(const __half* __restrict__ phi, int64_t rows, int m_pad, int G,
                                                              int TPR, int RL, const uint8_t* __restrict__ y,
                                                              const float* __restrict__ w, int clip_low, float* __restrict__ z,
                                                              uint8_t* __restrict__ z8)
@@ -246,7 +245,7 @@ static int run_filter(gl_ctx* ctx, gl_mat* phi, const FilterGeom& g, const doubl
     const int64_t rows = phi->local_rows;
     const int m = phi->m, m_pad = phi->m_pad;
     const uint8_t* y = (const uint8_t*)ctx->img->ptr + (size_t)phi->q0 * C;
-    const __nv_bfloat16* P = (const __nv_bfloat16*)phi->buf->ptr;
+    const __half* P = (const __half*)phi->buf->ptr;
     {
         StageTimer kt(ctx, GL_T_K_FILTER_PROJECT);
         k_filter_project<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, partial);

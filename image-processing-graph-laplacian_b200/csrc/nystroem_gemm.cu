@@ -7,7 +7,8 @@
 //   * A operand  = K_B band, [pixels x p_pad] fp16, K-major  -> M = pixels (128 per CTA tile)
 //   * B operand  = W^T, [m_pad x p_pad] fp16, K-major, scaled by one power of two so that it sits at the
 //                  top of the fp16 range (W itself is ~1e-4 and would be subnormal); unscaled in the epilogue
-//   * D          = fp32 accumulators in TMEM (2 x 256 columns, double buffered), written as bf16 Phi
+//   * D          = fp32 accumulators in TMEM (2 x 256 columns, double buffered), written as fp16 Phi (|Phi| <~ 1:
+//                  fp16's 11-bit mantissa beats bf16's 8 and the filter sums cancel heavily)
 //   * TMA (SWIZZLE_128B) feeds a 4-stage shared-memory ring; one elected thread issues tcgen05.mma;
 //     four epilogue warps drain TMEM with tcgen05.ld, convert, stage swizzled rows in shared memory and
 //     TMA-store them while the next tile's MMAs run.
@@ -76,13 +77,13 @@ __global__ void k_w_write(const float* __restrict__ U, int ld, int p, int m, int
 
 // Phi rows of the sample pixels <- Phi_A (nystroem.c:25-34); band-local
 __global__ void k_phi_sample_rows(const float* __restrict__ U, int ld, int p, int m, const uint32_t* __restrict__ samples,
-                                  int64_t q0, int64_t q1, int m_pad, __nv_bfloat16* __restrict__ phi)
+                                  int64_t q0, int64_t q1, int m_pad, __half* __restrict__ phi)
 {
     const int i = blockIdx.x;
     const int64_t q = samples[i];
     if (q < q0 || q >= q1) return;
     for (int j = threadIdx.x; j < m; j += blockDim.x)
-        phi[(size_t)(q - q0) * m_pad + j] = __float2bfloat16_rn(U[(size_t)j * ld + i]);
+        phi[(size_t)(q - q0) * m_pad + j] = __float2half_rn(U[(size_t)j * ld + i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -97,8 +98,8 @@ __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_gemm_simple(const T* __restrict__ A, const T* __restrict__ Bt, int64_t M, int N, int K,
-                                                     const float* __restrict__ scales, const __nv_bfloat16* __restrict__ addend,
-                                                     __nv_bfloat16* __restrict__ D)
+                                                     const float* __restrict__ scales, const __half* __restrict__ addend,
+                                                     __half* __restrict__ D)
 {
     __shared__ float As[32][33], Bs[32][33];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 2 x 2 outputs each
@@ -131,8 +132,8 @@ __global__ void __launch_bounds__(256) k_gemm_simple(const T* __restrict__ A, co
             const int c = n0 + tx + 16 * b;
             if (r < M && c < N) {
                 float v = acc[a][b] * sc;
-                if (addend) v += __bfloat162float(addend[(size_t)r * N + c]);
-                D[(size_t)r * N + c] = __float2bfloat16_rn(v);
+                if (addend) v += __half2float(addend[(size_t)r * N + c]);
+                D[(size_t)r * N + c] = __float2half_rn(v);
             }
         }
 }
@@ -272,10 +273,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi)
 {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    __half2 v = __floats2half2_rn(lo, hi);
     return *(uint32_t*)&v;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t w)
+{
+    return __half22float2(*(const __half2*)&w);
 }
 
 // One persistent CTA per SM.  warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator,
@@ -283,7 +288,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, int m_tiles, int n_tiles, int k_blocks, int n_total, int block_n,
-               int ab_bf16, const float* __restrict__ scales, const __nv_bfloat16* __restrict__ addend, int64_t m_rows,
+               int ab_bf16, const float* __restrict__ scales, const __half* __restrict__ addend, int64_t m_rows,
                int* __restrict__ err)
 {
     extern __shared__ uint8_t gemm_smem_raw[];
@@ -412,14 +417,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int i = 4 * i4 + j;
-                                pk[i] = pack_bf16(fmaf(__uint_as_float(v[2 * i]), sc, __uint_as_float(aw[j] << 16)),
-                                                  fmaf(__uint_as_float(v[2 * i + 1]), sc, __uint_as_float(aw[j] & 0xffff0000u)));
+                                const float2 ad = unpack_h2(aw[j]);
+                                pk[i] = pack_h2(fmaf(__uint_as_float(v[2 * i]), sc, ad.x), fmaf(__uint_as_float(v[2 * i + 1]), sc, ad.y));
                             }
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            pk[i] = pack_bf16(__uint_as_float(v[2 * i]) * sc, __uint_as_float(v[2 * i + 1]) * sc);
+                            pk[i] = pack_h2(__uint_as_float(v[2 * i]) * sc, __uint_as_float(v[2 * i + 1]) * sc);
                     }
                     // row `lane` of the slab, 16-byte chunks 4h .. 4h+3, XOR-swizzled like SWIZZLE_128B
 #pragma unroll
@@ -497,7 +502,7 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* bas
     return GL_OK;
 }
 
-// D[rows][n_pad] (bf16) = scales[1] * A[rows][k_pad] . Bt[n_pad][k_pad]^T (+ addend), A and Bt 16-bit K-major
+// D[rows][n_pad] (fp16) = scales[1] * A[rows][k_pad] . Bt[n_pad][k_pad]^T (+ addend), A and Bt 16-bit K-major
 // (ab_bf16: 0 = fp16, 1 = bf16).  k_pad % 64 == 0; n_pad is 64, 128 or a multiple of 256 (gl_m_pad).
 int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
                    const float* scales, const void* addend, void* D)
@@ -508,11 +513,11 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
         GL_REQUIRE(ceil_div(rows, 32) < 2147483647ll, "gemm(simple): band too large");
         if (ab_bf16)
             k_gemm_simple<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bt, rows, n_pad,
-                                                                         k_pad, scales, (const __nv_bfloat16*)addend,
-                                                                         (__nv_bfloat16*)D);
+                                                                         k_pad, scales, (const __half*)addend,
+                                                                         (__half*)D);
         else
             k_gemm_simple<__half><<<grid, 256, 0, ctx->stream>>>((const __half*)A, (const __half*)Bt, rows, n_pad, k_pad, scales,
-                                                                  (const __nv_bfloat16*)addend, (__nv_bfloat16*)D);
+                                                                  (const __half*)addend, (__half*)D);
         GL_LAUNCH_CHECK(ctx);
         return GL_OK;
     }
@@ -522,7 +527,7 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     CUtensorMap map_a, map_b, map_d;
     GL_CHECK(make_map_2d(&map_a, dt, A, (uint64_t)rows, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, tc::BLOCK_M));
     GL_CHECK(make_map_2d(&map_b, dt, Bt, (uint64_t)n_pad, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, (uint32_t)block_n));
-    GL_CHECK(make_map_2d(&map_d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, D, (uint64_t)rows, (uint64_t)n_pad, (uint64_t)n_pad, 64, 32));
+    GL_CHECK(make_map_2d(&map_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, (uint64_t)rows, (uint64_t)n_pad, (uint64_t)n_pad, 64, 32));
     const int m_tiles = (int)ceil_div(rows, tc::BLOCK_M);
     const int n_tiles = n_pad / block_n;
     const int k_blocks = k_pad / tc::BLOCK_K;
@@ -534,7 +539,7 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
     StageTimer kt(ctx, GL_T_K_GEMM);
     tc::k_gemm_tcgen05<<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad,
-                                                                           block_n, ab_bf16, scales, (const __nv_bfloat16*)addend,
+                                                                           block_n, ab_bf16, scales, (const __half*)addend,
                                                                            rows, (int*)err->ptr);
     gl_buf_release(err);
     GL_LAUNCH_CHECK(ctx);
@@ -564,7 +569,7 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
         phi->m = m;
         phi->m_pad = m_pad;
         phi->q0 = L_B->q0;
-        if ((rc = gl_alloc(ctx, sizeof(__nv_bfloat16) * (size_t)rows * m_pad, &phi->buf)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)rows * m_pad, &phi->buf)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)m_pad * p_pad, &Wt)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad, &colmax)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * 4, &scales)) != GL_OK) break;
@@ -583,7 +588,7 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
         if ((rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, p_pad, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
                                  phi->buf->ptr)) != GL_OK) break;
         k_phi_sample_rows<<<p, 128, 0, ctx->stream>>>(U, (int)phi_A->ld, p, m, (const uint32_t*)ctx->samples->ptr, phi->q0,
-                                                      phi->q0 + rows, m_pad, (__nv_bfloat16*)phi->buf->ptr);
+                                                      phi->q0 + rows, m_pad, (__half*)phi->buf->ptr);
         GL_LAUNCH_CHECK(ctx);
     } while (0);
     if (Wt) gl_buf_release(Wt);

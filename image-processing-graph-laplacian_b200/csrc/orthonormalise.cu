@@ -8,13 +8,13 @@
 //                           one m_pad^2 allreduce;
 //   2. R = chol(G), T = R^-1   m x m, fp64, on device (replicated, deterministic);
 //   3. Q = Phi + Phi (T - I)   tensor-core GEMM (nystroem_gemm.cu) with the identity part added in the
-//                           epilogue, so that only the small correction E = T - I is rounded to bf16.
+//                           epilogue, so that only the small correction E = T - I is rounded to fp16.
 // Phi is nearly orthonormal on entry (|Phi^T Phi - I|_F ~ 1e-3..1e-2), so G is well
-// conditioned and one CholeskyQR pass is stable; the result is orthonormal up to the bf16 storage of Q.
+// conditioned and one CholeskyQR pass is stable; the result is orthonormal up to the fp16 storage of Q.
 #include "common.cuh"
 
 // ---- 1. Gram matrix: CTA = 64 x 64 tile of G over a slab of rows; 256 threads, 4 x 4 outputs each ----------
-__global__ void __launch_bounds__(256) k_gram_tile(const __nv_bfloat16* __restrict__ phi, int64_t rows, int m_pad, int slabs,
+__global__ void __launch_bounds__(256) k_gram_tile(const __half* __restrict__ phi, int64_t rows, int m_pad, int slabs,
                                                    float* __restrict__ partial /* [slabs][m_pad][m_pad] */)
 {
     __shared__ float As[32][64 + 4], Bs[32][64 + 4];
@@ -41,10 +41,11 @@ __global__ void __launch_bounds__(256) k_gram_tile(const __nv_bfloat16* __restri
             const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                As[rr][cg * 8 + 2 * k] = __uint_as_float(wa[k] << 16);
-                As[rr][cg * 8 + 2 * k + 1] = __uint_as_float(wa[k] & 0xffff0000u);
-                Bs[rr][cg * 8 + 2 * k] = __uint_as_float(wb[k] << 16);
-                Bs[rr][cg * 8 + 2 * k + 1] = __uint_as_float(wb[k] & 0xffff0000u);
+                const float2 fa = __half22float2(*(const __half2*)&wa[k]), fb = __half22float2(*(const __half2*)&wb[k]);
+                As[rr][cg * 8 + 2 * k] = fa.x;
+                As[rr][cg * 8 + 2 * k + 1] = fa.y;
+                Bs[rr][cg * 8 + 2 * k] = fb.x;
+                Bs[rr][cg * 8 + 2 * k + 1] = fb.y;
             }
         }
         __syncthreads();
@@ -128,22 +129,26 @@ __global__ void k_upper_inverse(const double* __restrict__ R, int m, int ld, dou
     }
 }
 
-// Et[j][k] = bf16(T[k][j] - delta_kj) for k, j < m; 0 in the padding (K-major B operand of Q = Phi + Phi E)
-__global__ void k_build_et(const double* __restrict__ T, int m, int ld, int m_pad, __nv_bfloat16* __restrict__ Et,
+// Et[j][k] = fp16(2^12 * (T[k][j] - delta_kj)) for k, j < m; 0 in the padding (K-major B operand of Q = Phi + Phi E).
+// E is ~1e-3: the 2^12 keeps it in fp16's normal range; the GEMM epilogue multiplies by 2^-12.
+#define ET_SCALE_LOG2 12
+__global__ void k_build_et(const double* __restrict__ T, int m, int ld, int m_pad, __half* __restrict__ Et,
                            const double* __restrict__ R, double* __restrict__ norms)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (k >= m_pad) return;
     double v = 0.0;
     if (k < m && j < m) v = T[(size_t)k * ld + j] - (k == j ? 1.0 : 0.0);
-    Et[(size_t)j * m_pad + k] = __float2bfloat16_rn((float)v);
+    v = ldexp(v, ET_SCALE_LOG2);
+    v = fmin(fmax(v, -60000.0), 60000.0);
+    Et[(size_t)j * m_pad + k] = __float2half_rn((float)v);
     if (norms && k == j && j < m) norms[j] = R[(size_t)j * ld + j];
 }
 
-__global__ void k_unit_scales(float* s)
+__global__ void k_et_scales(float* s)
 {
-    s[0] = 1.f;
-    s[1] = 1.f;
+    s[0] = ldexpf(1.f, ET_SCALE_LOG2);
+    s[1] = ldexpf(1.f, -ET_SCALE_LOG2);
 }
 
 int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
@@ -163,15 +168,15 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)slabs * m_pad * m_pad, &partial)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m_pad * m_pad, &G)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m_pad * m_pad, &T)) != GL_OK) break;
-        if ((rc = gl_alloc(ctx, sizeof(__nv_bfloat16) * (size_t)m_pad * m_pad, &Et)) != GL_OK) break;
-        if ((rc = gl_alloc(ctx, sizeof(__nv_bfloat16) * (size_t)rows * m_pad, &Q)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)m_pad * m_pad, &Et)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)rows * m_pad, &Q)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(int) * 4, &st)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m_pad, &norms)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * 4, &sc)) != GL_OK) break;
         GL_CUDA_CHECK(cudaMemsetAsync(st->ptr, 0, sizeof(int) * 4, ctx->stream));
 
         dim3 gg((unsigned)tiles, (unsigned)tiles, (unsigned)slabs);
-        k_gram_tile<<<gg, 256, 0, ctx->stream>>>((const __nv_bfloat16*)phi->buf->ptr, rows, m_pad, slabs, (float*)partial->ptr);
+        k_gram_tile<<<gg, 256, 0, ctx->stream>>>((const __half*)phi->buf->ptr, rows, m_pad, slabs, (float*)partial->ptr);
         GL_LAUNCH_CHECK(ctx);
         dim3 gr((unsigned)ceil_div(m_pad, 128), (unsigned)m_pad);
         k_gram_reduce<<<gr, 128, 0, ctx->stream>>>((const float*)partial->ptr, slabs, m_pad, (double*)G->ptr);
@@ -183,12 +188,12 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
         k_upper_inverse<<<(unsigned)ceil_div(m, 128), 128, 0, ctx->stream>>>((const double*)G->ptr, m, m_pad, (double*)T->ptr);
         GL_LAUNCH_CHECK(ctx);
         dim3 ge((unsigned)ceil_div(m_pad, 128), (unsigned)m_pad);
-        k_build_et<<<ge, 128, 0, ctx->stream>>>((const double*)T->ptr, m, m_pad, m_pad, (__nv_bfloat16*)Et->ptr,
+        k_build_et<<<ge, 128, 0, ctx->stream>>>((const double*)T->ptr, m, m_pad, m_pad, (__half*)Et->ptr,
                                                 (const double*)G->ptr, (double*)norms->ptr);
         GL_LAUNCH_CHECK(ctx);
-        k_unit_scales<<<1, 1, 0, ctx->stream>>>((float*)sc->ptr);
+        k_et_scales<<<1, 1, 0, ctx->stream>>>((float*)sc->ptr);
         GL_LAUNCH_CHECK(ctx);
-        if ((rc = gl_gemm_kmajor(ctx, phi->buf->ptr, 1, rows, m_pad, Et->ptr, m_pad, (const float*)sc->ptr, phi->buf->ptr,
+        if ((rc = gl_gemm_kmajor(ctx, phi->buf->ptr, 0, rows, m_pad, Et->ptr, m_pad, (const float*)sc->ptr, phi->buf->ptr,
                                  Q->ptr)) != GL_OK) break;
 
         GL_CHECK(gl_ensure_pinned(ctx, sizeof(double) * (size_t)m_pad + 64));

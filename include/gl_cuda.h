@@ -64,7 +64,7 @@ enum gl_mat_kind {
                            pixels incl. samples; carries the fp64 row sums D = K_A.1 + K_B.1 */
     GL_MAT_EIGVEC = 3,  /* p x m fp32 column-major (eigenvectors of L_A in columns) */
     GL_MAT_DIAG = 4,    /* m-vector fp64 standing for a diagonal matrix */
-    GL_MAT_PHI = 5      /* this rank's pixel band x m_pad bf16 row-major, rows in raster order */
+    GL_MAT_PHI = 5      /* this rank's pixel band x m_pad fp16 row-major, rows in raster order */
 };
 
 typedef struct gl_mat_info {

@@ -175,6 +175,18 @@ static inline double kern(const orc_params* P, const uint8_t* img, uint32_t a, u
     return k;
 }
 
+/* K(samples, cols) p x ncols row-major, all host threads (used by the BLAS-backed CPU baseline
+ * oracle/cpu_pipeline.py; same kernel function as orc_pipeline). */
+ORC_API void orc_affinity_rows(const uint8_t* img, const orc_params* P, const uint32_t* s, int p,
+                               const uint32_t* cols, size_t ncols, double* K)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < p; ++i) {
+        double* row = K + (size_t)i * ncols;
+        for (size_t k = 0; k < ncols; ++k) row[k] = kern(P, img, s[i], cols[k]);
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* symmetric eigensolver: Householder tridiagonalisation + implicit-shift QL  */
 /* (the textbook EISPACK tred2/tql2 pair), fp64.  a: n x n row-major, on exit */

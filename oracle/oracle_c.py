@@ -42,6 +42,8 @@ def lib():
         L.orc_pipeline.restype = C.c_int
         L.orc_pipeline.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int, C.c_void_p,
                                    C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_affinity_rows.restype = None
+        L.orc_affinity_rows.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.orc_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -97,6 +99,19 @@ def run_pipeline(img, sample_indices, m=-1, kind="bilateral", h_loc=40.0, h_val=
         raise RuntimeError(f"orc_pipeline failed rc={rc}")
     return dict(D=D, alpha=alpha.value, mu=mu, z=z[:, :, 0] if img.ndim == 2 else z, m=mm, p=p,
                 timings=dict(zip(["affinity", "laplacian", "eigensolve", "nystroem", "gram_schmidt", "filter", "total"], t[:7])))
+
+
+def affinity_rows(img, sample_indices, cols, kind="bilateral", h_loc=40.0, h_val=30.0):
+    """K(samples, cols), p x len(cols) fp64 (OpenMP over samples)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape[:2]
+    Cn = 1 if img.ndim == 2 else img.shape[2]
+    s = np.ascontiguousarray(sample_indices, dtype=np.uint32)
+    cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    P = Params(W, H, Cn, KINDS[kind], h_loc, h_val, 3.0, 1.0, -1, 0, 0, H)
+    K = np.empty((len(s), len(cols)))
+    lib().orc_affinity_rows(img.ctypes.data, C.byref(P), s.ctypes.data, len(s), cols.ctypes.data, len(cols), K.ctypes.data)
+    return K
 
 
 def num_threads():

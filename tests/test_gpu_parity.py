@@ -110,12 +110,14 @@ def test_eigensolver(ctx, p):
     got = mu.download()
     assert got.shape == (m,)
     assert np.all(np.diff(got) >= 0)
-    assert np.max(np.abs(got - w[:m]) / w[:m]) < 2e-5
+    err_mu = float(np.max(np.abs(got - w[:m]) / w[:m]))
+    assert err_mu < 1e-8, err_mu                      # fp64 Rayleigh quotients on fp32 vectors
     assert np.allclose(mu_inv.download(), 1.0 / got, rtol=1e-12)
     Ug = U.download()
     assert Ug.shape == (p, m)
-    assert np.max(np.abs(Ug.T @ Ug - np.eye(m))) < 5e-5
-    assert np.max(np.abs(A @ Ug - Ug * got)) < 5e-5 * np.max(np.abs(w))
+    err_orth = float(np.max(np.abs(Ug.T @ Ug - np.eye(m))))
+    err_res = float(np.max(np.abs(A @ Ug - Ug * got)) / np.max(np.abs(w)))
+    assert err_orth < 2e-5 and err_res < 2e-5, (err_orth, err_res)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -140,10 +142,13 @@ def test_pipeline_matches_golden(ctx, golden, tag):
     assert r["p"] == len(g["sample_indices"]) and r["m"] == int(g["m"])
     assert np.array_equal(ctx.get_samples(), g["sample_indices"])              # bit-exact
     mu = g["mu"]
-    assert np.max(np.abs(r["mu"] - mu) / mu) <= TOL_MU
+    err_mu = float(np.max(np.abs(r["mu"] - mu) / mu))
     z = g["z"].astype(np.float64)
-    assert _rel(r["z"], z) <= TOL_Z
-    assert _rel(r["z"] - src, z - src) <= TOL_DZ
+    err_z, err_dz = _rel(r["z"], z), _rel(r["z"] - src, z - src)
+    print(f"{tag}: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_mu <= TOL_MU, err_mu
+    assert err_z <= TOL_Z, err_z
+    assert err_dz <= TOL_DZ, err_dz
     assert r["z"].max() <= 255.0
 
 
@@ -164,8 +169,10 @@ def test_gram_schmidt_stage(ctx, golden, tag):
     g = golden(tag)
     src, r = _run_case(ctx, g, gram_schmidt=1)
     z = g["z_gs"].astype(np.float64)
-    assert _rel(r["z"], z) <= TOL_Z
-    assert _rel(r["z"] - src, z - src) <= TOL_DZ
+    err_z, err_dz = _rel(r["z"], z), _rel(r["z"] - src, z - src)
+    print(f"gs {tag}: err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_z <= TOL_Z, err_z
+    assert err_dz <= TOL_DZ, err_dz
 
 
 def test_stage_by_stage_phi_properties(ctx, golden):
@@ -180,19 +187,22 @@ def test_stage_by_stage_phi_properties(ctx, golden):
     P = phi.download()
     assert P.shape == (img.size, len(s) - 1)
     Ud = U.download()
-    # sample rows of Phi are Phi_A (nystroem.c:25-34), up to bf16 storage
-    assert np.max(np.abs(P[s.astype(np.int64)] - Ud)) <= 2 ** -8 * np.max(np.abs(Ud))
+    # sample rows of Phi are Phi_A (nystroem.c:25-34), up to fp16 storage
+    assert np.max(np.abs(P[s.astype(np.int64)] - Ud)) <= 2 ** -11 * np.max(np.abs(Ud))
     G = P.T @ P
     assert np.linalg.norm(G - np.eye(G.shape[0])) < 3e-2          # nearly orthonormal before GS
     # projector parity with the oracle (eigenvector signs are arbitrary: never compare Phi entrywise)
     ref = o.run_pipeline(img, s, return_phi=True)
     y = img.reshape(-1).astype(np.float64)
-    assert _rel(P @ (P.T @ y), ref["phi"] @ (ref["phi"].T @ y)) < 2e-3
+    err_proj = _rel(P @ (P.T @ y), ref["phi"] @ (ref["phi"].T @ y))
+    assert err_proj < 2e-3, err_proj
     norms = ctx.orthonormalise(phi)
     Q = phi.download()
-    assert np.max(np.abs(Q.T @ Q - np.eye(Q.shape[1]))) < 2e-3    # orthonormal up to bf16 storage
+    err_q = float(np.max(np.abs(Q.T @ Q - np.eye(Q.shape[1]))))
+    assert err_q < 5e-4, err_q                                   # orthonormal up to fp16 storage
     _, nref = o.gram_schmidt(ref["phi"])
-    assert np.max(np.abs(norms - nref) / nref) < 5e-3
+    err_n = float(np.max(np.abs(norms - nref) / nref))
+    assert err_n < 2e-3, err_n
     z = ctx.filter(phi, mu)
     assert z.shape == img.shape and np.isfinite(z).all()
 
@@ -215,9 +225,12 @@ def test_synthetic_against_oracle(ctx, W, H, ch, p, kind, method):
     s = oc.random_sampling(W, H, p, 42) if method == "random" else oc.uniform_sampling(W, H, p)
     assert np.array_equal(ctx.get_samples(), s)
     ref = oc.run_pipeline(img, s, kind=kind)
-    assert np.max(np.abs(r["mu"] - ref["mu"]) / ref["mu"]) <= TOL_MU
-    assert _rel(r["z"], ref["z"]) <= TOL_Z
-    assert _rel(r["z"] - img, ref["z"] - img) <= TOL_DZ
+    err_mu = float(np.max(np.abs(r["mu"] - ref["mu"]) / ref["mu"]))
+    err_z, err_dz = _rel(r["z"], ref["z"]), _rel(r["z"] - img, ref["z"] - img)
+    print(f"synthetic {W}x{H}x{ch} p={p} {kind}: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_mu <= TOL_MU, err_mu
+    assert err_z <= TOL_Z, err_z
+    assert err_dz <= TOL_DZ, err_dz
 
 
 def test_filter_options(ctx, golden):
