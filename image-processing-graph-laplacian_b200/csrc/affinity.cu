@@ -1,5 +1,9 @@
 // a-2: affinity blocks K_A (p x p, fp64) and K_B (band pixels x p_pad, fp16, pixel-major) with the
-// row sums D = K_A.1 + K_B.1 taken from the fp32 kernel values before rounding.
+// row sums D = K_A.1 + K_B.1 taken from the fp32 kernel values before rounding, and the
+// image-weighted row sums T = [K_A K_B] y (one per channel) from the same fp32 values: the filter's
+// projection c = Phi^T y = U^T y_S + W^T (K_B y_B) is then a p-sized product instead of a pass over Phi,
+// and -- more important -- it is free of the fp16 rounding of W, which the heavy cancellation in Phi^T y
+// (|c| ~ 1 against |y| ~ 1e4) would amplify to a ~1e-2 error of z - y (measured).
 // Replaces ComputeAffinityMatrices / ComputeDistance / ComputeBilateralFilter,
 // hpc/affinity.c:129-262,115-122,59-113 (photometric :8-17, spatial :19-57).
 //
@@ -66,15 +70,16 @@ template <int KIND, int C>
 __global__ void __launch_bounds__(AFF_THREADS, 2)
 k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int p_pad, int width, int64_t q0, int64_t q1,
              float a2, float b2,  // -log2(e)/h_loc^2, -log2(e)/h_val^2
-             __half* __restrict__ KB, float* __restrict__ partial /* [gridDim.x][p_pad] */)
+             __half* __restrict__ KB, float* __restrict__ partial /* [gridDim.x][1 + C][p_pad] */)
 {
     extern __shared__ float aff_smem[];
-    float* cta_sum = aff_smem;                 // [p_pad]
-    float* ws = cta_sum + p_pad;               // [2][8 warps][64]
-    float* px = ws + 2 * 8 * 64;               // [(2 + C)][AFF_TP] pixel features
+    constexpr int NS = 1 + C;                  // sums per sample: D and T[ch]
+    float* cta_sum = aff_smem;                 // [NS][p_pad]
+    float* ws = cta_sum + NS * p_pad;          // [2][NS][8 warps][64]
+    float* px = ws + 2 * NS * 8 * 64;          // [(2 + C)][AFF_TP] pixel features
     const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3, lane = tid & 31, warp = tid >> 5;
     const int chunks = p_pad >> 6;
-    for (int i = tid; i < p_pad; i += AFF_THREADS) cta_sum[i] = 0.f;
+    for (int i = tid; i < NS * p_pad; i += AFF_THREADS) cta_sum[i] = 0.f;
 
     const int64_t n_band = q1 - q0;
     const int64_t tiles = (n_band + AFF_TP - 1) / AFF_TP;
@@ -106,9 +111,13 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
                 *(float4*)&sv[ch][0] = *(const float4*)&sf[(2 + ch) * p_pad + s0];
                 *(float4*)&sv[ch][4] = *(const float4*)&sf[(2 + ch) * p_pad + s0 + 4];
             }
-            float acc[8];
+            float acc[8], tacc[C][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+            for (int k = 0; k < 8; ++k) {
+                acc[k] = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) tacc[ch][k] = 0.f;
+            }
 #pragma unroll 2
             for (int i = 0; i < AFF_PPT; ++i) {
                 const int pi = ty + (i << 5);
@@ -140,7 +149,11 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
                 }
                 if (q < q1) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] += kv[k];
+                    for (int k = 0; k < 8; ++k) {
+                        acc[k] += kv[k];
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) tacc[ch][k] = fmaf(kv[k], pv[ch], tacc[ch][k]);
+                    }
                     __half2 h0 = __floats2half2_rn(kv[0], kv[1]), h1 = __floats2half2_rn(kv[2], kv[3]);
                     __half2 h2 = __floats2half2_rn(kv[4], kv[5]), h3 = __floats2half2_rn(kv[6], kv[7]);
                     uint4 pk;
@@ -153,33 +166,44 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
             for (int k = 0; k < 8; ++k) {
                 acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
                 acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    tacc[ch][k] += __shfl_xor_sync(0xffffffffu, tacc[ch][k], 8);
+                    tacc[ch][k] += __shfl_xor_sync(0xffffffffu, tacc[ch][k], 16);
+                }
             }
-            float* w = ws + flip * 512;
+            float* w = ws + flip * NS * 512;
             if (lane < 8) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w[warp * 64 + (lane << 3) + k] = acc[k];
+                for (int k = 0; k < 8; ++k) {
+                    w[warp * 64 + (lane << 3) + k] = acc[k];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) w[(1 + ch) * 512 + warp * 64 + (lane << 3) + k] = tacc[ch][k];
+                }
             }
             __syncthreads();
-            if (tid < 64) {
-                float s = 0.f;
+            for (int i = tid; i < NS * 64; i += AFF_THREADS) {
+                const int which = i >> 6, sidx = i & 63;
+                float sum = 0.f;
 #pragma unroll
-                for (int wi = 0; wi < 8; ++wi) s += w[wi * 64 + tid];
-                cta_sum[(ck << 6) + tid] += s;
+                for (int wi = 0; wi < 8; ++wi) sum += w[which * 512 + wi * 64 + sidx];
+                cta_sum[which * p_pad + (ck << 6) + sidx] += sum;
             }
             flip ^= 1;
         }
     }
     __syncthreads();
-    for (int i = tid; i < p_pad; i += AFF_THREADS) partial[(size_t)blockIdx.x * p_pad + i] = cta_sum[i];
+    for (int i = tid; i < NS * p_pad; i += AFF_THREADS) partial[(size_t)blockIdx.x * NS * p_pad + i] = cta_sum[i];
 }
 
-__global__ void k_reduce_partials(const float* __restrict__ partial, int nblocks, int p_pad, int p, double* __restrict__ D)
+// DT[which][s] = sum over CTAs (fixed order, fp64); which 0 = D, 1.. = T[ch]; padding samples get 0
+__global__ void k_reduce_partials(const float* __restrict__ partial, int nblocks, int p_pad, int ns, double* __restrict__ DT)
 {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns * p_pad) return;
     double acc = 0.0;
-    for (int b = 0; b < nblocks; ++b) acc += (double)partial[(size_t)b * p_pad + s];
-    D[s] = acc;
+    for (int b = 0; b < nblocks; ++b) acc += (double)partial[(size_t)b * ns * p_pad + i];
+    DT[i] = acc;
 }
 
 template <int KIND, int C>
@@ -191,7 +215,7 @@ static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float*
     k_affinity_A<KIND, C><<<ga, 128, 0, ctx->stream>>>((const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p,
                                                       ctx->width, 1.0 / (h_loc * h_loc), 1.0 / (h_val * h_val), KA);
     GL_LAUNCH_CHECK(ctx);
-    const size_t smem = sizeof(float) * ((size_t)p_pad + 2 * 8 * 64 + (size_t)(2 + C) * AFF_TP);
+    const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_pad + 2 * (1 + C) * 8 * 64 + (size_t)(2 + C) * AFF_TP);
     GL_CUDA_CHECK(cudaFuncSetAttribute(k_affinity_B<KIND, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const float log2e = 1.4426950408889634f;
     StageTimer kt(ctx, GL_T_K_AFFINITY_B);
@@ -227,9 +251,9 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         KB->p_pad = p_pad;
         KB->q0 = ctx->q0;
         if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)n_band * p_pad, &KB->buf)) != GL_OK) break;
-        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)p_pad, &KB->aux)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)(1 + C) * p_pad, &KB->aux)) != GL_OK) break;  // [D | T[ch]]
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_pad, &sf)) != GL_OK) break;
-        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * p_pad, &partial)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * (1 + C) * p_pad, &partial)) != GL_OK) break;
 
         k_sample_features<<<(unsigned)ceil_div(p_pad, 256), 256, 0, ctx->stream>>>(
             (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p, p_pad, ctx->width, C, (float*)sf->ptr);
@@ -244,11 +268,16 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
 #undef AFF_CASE
         if (rc != GL_OK) break;
 
-        k_reduce_partials<<<(unsigned)ceil_div(p, 128), 128, 0, ctx->stream>>>((const float*)partial->ptr, grid, p_pad, p,
-                                                                               (double*)KB->aux->ptr);
+        k_reduce_partials<<<(unsigned)ceil_div((1 + C) * p_pad, 128), 128, 0, ctx->stream>>>((const float*)partial->ptr, grid, p_pad,
+                                                                                             1 + C, (double*)KB->aux->ptr);
         GL_LAUNCH_CHECK(ctx);
-        // one p-double allreduce of the band-partial row sums
-        if ((rc = gl_allreduce_f64(ctx, (double*)KB->aux->ptr, (size_t)p)) != GL_OK) break;
+        // ONE allreduce of the band-partial sums: D (p doubles) and T (C x p doubles)
+        if ((rc = gl_allreduce_f64(ctx, (double*)KB->aux->ptr, (size_t)(1 + C) * p_pad)) != GL_OK) break;
+        KB->channels = C;
+        KB->image_epoch = ctx->image_epoch;
+        KB->aff_kind = kind;
+        KB->aff_h_loc = h_loc;
+        KB->aff_h_val = h_val;
     } while (0);
     if (sf) gl_buf_release(sf);
     if (partial) gl_buf_release(partial);

@@ -110,6 +110,10 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         int g = atoi(value);
         GL_REQUIRE(g == 1 || g == 2, "option cta_group: want 1|2");
         ctx->gemm_cta_group = g;
+    } else if (!strcmp(key, "projection")) {
+        if (!strcmp(value, "sums")) ctx->projection_mode = 0;
+        else if (!strcmp(value, "recompute")) ctx->projection_mode = 1;
+        else GL_REQUIRE(false, "option projection: want sums|recompute, got %s", value);
     } else if (!strcmp(key, "jacobi_max_sweeps")) {
         ctx->jacobi_max_sweeps = atoi(value);
     } else if (!strcmp(key, "jacobi_tol")) {
@@ -284,6 +288,7 @@ static int set_image_geometry(gl_ctx* ctx, int width, int height, int channels)
         ctx->img = nullptr;
         GL_CHECK(gl_alloc(ctx, (size_t)(n * channels), &ctx->img));
     }
+    ctx->image_epoch++;
     ctx->width = width;
     ctx->height = height;
     ctx->channels = channels;
@@ -515,6 +520,7 @@ int gl_mat_destroy(gl_mat* m)
     if (m->buf) gl_buf_release(m->buf);
     if (m->aux) gl_buf_release(m->aux);
     if (m->dscale) gl_buf_release(m->dscale);
+    if (m->proj) gl_buf_release(m->proj);
     delete m;
     return GL_OK;
 }

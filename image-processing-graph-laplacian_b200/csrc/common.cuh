@@ -85,6 +85,11 @@ struct gl_mat {
     // KB / PHI bookkeeping
     int64_t q0 = 0;              // first raster pixel of the band
     int p = 0, p_pad = 0, m = 0, m_pad = 0;
+    int channels = 0;            // KB: channels of the image-weighted sums T in aux; PHI: channels of proj
+    gl_buf* proj = nullptr;      // PHI: c = Phi^T y, fp64 [m_pad][channels], from the T sums (nystroem) -- see filter.cu
+    unsigned long long image_epoch = 0;  // image the sums / proj belong to
+    int aff_kind = 0;            // KB: the affinity that produced it (to rebuild K_A y_S in fp64)
+    double aff_h_loc = 0, aff_h_val = 0;
     float phi_scale = 1.0f;      // PHI: stored value * phi_scale = logical (always 1; scale folded in the epilogue)
 };
 
@@ -106,6 +111,9 @@ struct gl_ctx {
     int row0 = 0, row1 = 0;  // band of image rows owned by this rank
     int64_t q0 = 0, q1 = 0;  // raster range of the band
     gl_buf* img = nullptr;   // u8 [n * channels]
+
+    unsigned long long image_epoch = 0;  // bumped by every gl_set_*image
+    int projection_mode = 0;  // 0 = c from the affinity sums (default), 1 = always recompute c with a pass over Phi
 
     // samples
     unsigned p = 0;

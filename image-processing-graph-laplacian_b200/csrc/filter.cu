@@ -238,22 +238,35 @@ __global__ void __launch_bounds__(FL_THREADS) k_filter_apply(const __half* __res
     }
 }
 
+// c (fp32 [m_pad][C]) <- proj (fp64)
+__global__ void k_filter_c_from_proj(const double* __restrict__ proj, int count, float* __restrict__ c)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) c[i] = (float)proj[i];
+}
+
 template <int C, int NG>
 static int run_filter(gl_ctx* ctx, gl_mat* phi, const FilterGeom& g, const double* f, double gain, int clip_low, int grid,
-                      float* partial, float* c, float* w, float* z, uint8_t* z8)
+                      float* partial, float* c, float* w, float* z, uint8_t* z8, bool use_proj)
 {
     const int64_t rows = phi->local_rows;
     const int m = phi->m, m_pad = phi->m_pad;
     const uint8_t* y = (const uint8_t*)ctx->img->ptr + (size_t)phi->q0 * C;
     const __half* P = (const __half*)phi->buf->ptr;
-    {
-        StageTimer kt(ctx, GL_T_K_FILTER_PROJECT);
-        k_filter_project<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, partial);
+    if (use_proj) {
+        // c = Phi^T y was derived from the affinity stage's sums (nystroem_gemm.cu): no pass over Phi, no allreduce
+        k_filter_c_from_proj<<<(unsigned)ceil_div(m_pad * C, 256), 256, 0, ctx->stream>>>((const double*)phi->proj->ptr, m_pad * C, c);
+        GL_LAUNCH_CHECK(ctx);
+    } else {
+        {
+            StageTimer kt(ctx, GL_T_K_FILTER_PROJECT);
+            k_filter_project<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, partial);
+        }
+        GL_LAUNCH_CHECK(ctx);
+        k_filter_reduce<<<(unsigned)ceil_div(m_pad * C, 256), 256, 0, ctx->stream>>>(partial, grid, m_pad * C, c);
+        GL_LAUNCH_CHECK(ctx);
+        GL_CHECK(gl_allreduce_f32(ctx, c, (size_t)m_pad * C));
     }
-    GL_LAUNCH_CHECK(ctx);
-    k_filter_reduce<<<(unsigned)ceil_div(m_pad * C, 256), 256, 0, ctx->stream>>>(partial, grid, m_pad * C, c);
-    GL_LAUNCH_CHECK(ctx);
-    GL_CHECK(gl_allreduce_f32(ctx, c, (size_t)m_pad * C));
     k_filter_weights<<<(unsigned)ceil_div(m_pad * C, 256), 256, 0, ctx->stream>>>(c, f, m, m_pad, C, (float)gain, w);
     GL_LAUNCH_CHECK(ctx);
     {
@@ -278,6 +291,8 @@ int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int
 
     gl_buf *partial = nullptr, *c = nullptr, *w = nullptr, *z = nullptr, *z8 = nullptr;
     int rc = GL_OK;
+    const bool use_proj = ctx->projection_mode == 0 && phi->proj && phi->channels == C && phi->image_epoch == ctx->image_epoch;
+    if (use_proj) ctx->ev_valid[GL_T_K_FILTER_PROJECT] = false;  // that kernel does not run
     do {
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * m_pad * C, &partial)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad * C, &c)) != GL_OK) break;
@@ -291,7 +306,7 @@ int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int
             uint8_t* z8p = z8 ? (uint8_t*)z8->ptr : nullptr;
 #define FL_CASE(CC, NGG)                                                                                                      \
     if (C == CC && g.NG == NGG)                                                                                               \
-        rc = run_filter<CC, NGG>(ctx, phi, g, f, gain, clip_low, grid, (float*)partial->ptr, (float*)c->ptr, (float*)w->ptr, zp, z8p);
+        rc = run_filter<CC, NGG>(ctx, phi, g, f, gain, clip_low, grid, (float*)partial->ptr, (float*)c->ptr, (float*)w->ptr, zp, z8p, use_proj);
             FL_CASE(1, 1) else FL_CASE(1, 2) else FL_CASE(3, 1) else FL_CASE(3, 2)
 #undef FL_CASE
         }

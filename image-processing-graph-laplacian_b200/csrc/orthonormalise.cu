@@ -145,6 +145,20 @@ __global__ void k_build_et(const double* __restrict__ T, int m, int ld, int m_pa
     if (norms && k == j && j < m) norms[j] = R[(size_t)j * ld + j];
 }
 
+// Q = Phi T  =>  Q^T y = T^T (Phi^T y): out[j][ch] = sum_{k<=j} T[k][j] c[k][ch]
+__global__ void k_proj_times_t(const double* __restrict__ T, int m, int ld, int m_pad, int C, const double* __restrict__ c,
+                               double* __restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m_pad) return;
+    for (int ch = 0; ch < C; ++ch) {
+        double s = 0.0;
+        if (j < m)
+            for (int k = 0; k <= j; ++k) s += T[(size_t)k * ld + j] * c[(size_t)k * C + ch];
+        out[(size_t)j * C + ch] = s;
+    }
+}
+
 __global__ void k_et_scales(float* s)
 {
     s[0] = ldexpf(1.f, ET_SCALE_LOG2);
@@ -208,6 +222,15 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
             break;
         }
         if (norms_out) memcpy(norms_out, (char*)ctx->pinned + 64, sizeof(double) * (size_t)m);
+        if (phi->proj) {
+            gl_buf* np_ = nullptr;
+            if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m_pad * phi->channels, &np_)) != GL_OK) break;
+            k_proj_times_t<<<(unsigned)ceil_div(m_pad, 128), 128, 0, ctx->stream>>>((const double*)T->ptr, m, m_pad, m_pad, phi->channels,
+                                                                                    (const double*)phi->proj->ptr, (double*)np_->ptr);
+            ctx->launches++;
+            gl_buf_release(phi->proj);
+            phi->proj = np_;
+        }
         // Phi <- Q (swap storage; the handle keeps its identity)
         gl_buf* old = phi->buf;
         phi->buf = Q;
