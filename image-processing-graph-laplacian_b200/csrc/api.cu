@@ -114,6 +114,10 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         if (!strcmp(value, "sums")) ctx->projection_mode = 0;
         else if (!strcmp(value, "recompute")) ctx->projection_mode = 1;
         else GL_REQUIRE(false, "option projection: want sums|recompute, got %s", value);
+    } else if (!strcmp(key, "filter_apply")) {
+        if (!strcmp(value, "warp")) ctx->filter_apply_impl = 0;
+        else if (!strcmp(value, "generic")) ctx->filter_apply_impl = 1;
+        else GL_REQUIRE(false, "option filter_apply: want warp|generic, got %s", value);
     } else if (!strcmp(key, "jacobi_max_sweeps")) {
         ctx->jacobi_max_sweeps = atoi(value);
     } else if (!strcmp(key, "jacobi_tol")) {

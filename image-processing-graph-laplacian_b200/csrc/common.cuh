@@ -113,6 +113,7 @@ struct gl_ctx {
     gl_buf* img = nullptr;   // u8 [n * channels]
 
     unsigned long long image_epoch = 0;  // bumped by every gl_set_*image
+    int filter_apply_impl = 0;  // 0 = warp-per-row kernel when the shape allows, 1 = always the generic kernel
     int projection_mode = 0;  // 0 = c from the affinity sums (default), 1 = always recompute c with a pass over Phi
 
     // samples

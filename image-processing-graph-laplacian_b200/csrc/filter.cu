@@ -238,6 +238,66 @@ __global__ void __launch_bounds__(FL_THREADS) k_filter_apply(const __half* __res
     }
 }
 
+// (ii), fast path when a row is a whole number of warps' worth of 16-byte groups (m_pad % 256 == 0): one WARP per
+// row, lane l owns groups l, l+32, ...; w lives in registers; no block-level synchronisation at all, 2 rows
+// (2 * NGL independent 16-byte loads per lane) in flight.
+template <int C, int NGL>
+__global__ void __launch_bounds__(FL_THREADS) k_filter_apply_warp(const __half* __restrict__ phi, int64_t rows, int m_pad,
+                                                                  const uint8_t* __restrict__ y, const float* __restrict__ w,
+                                                                  int clip_low, float* __restrict__ z, uint8_t* __restrict__ z8)
+{
+    constexpr int RU = 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int WPC = FL_THREADS / 32;
+    float wr[NGL][8][C];
+#pragma unroll
+    for (int g = 0; g < NGL; ++g)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) wr[g][k][ch] = w[(size_t)((lane + 32 * g) * 8 + k) * C + ch];
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r_begin = per * blockIdx.x, r_end = min(rows, r_begin + per);
+    for (int64_t r0 = r_begin + warp; r0 < r_end; r0 += (int64_t)WPC * RU) {
+        uint4 v[RU][NGL];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int64_t r = r0 + (int64_t)u * WPC;
+#pragma unroll
+            for (int g = 0; g < NGL; ++g)
+                v[u][g] = r < r_end ? ld_stream(phi + (size_t)r * m_pad + (size_t)(lane + 32 * g) * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            float dot[C];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) dot[ch] = 0.f;
+#pragma unroll
+            for (int g = 0; g < NGL; ++g) {
+                float f[8];
+                unpack8(v[u][g], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) dot[ch] = fmaf(f[k], wr[g][k][ch], dot[ch]);
+            }
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) dot[ch] = warp_sum(dot[ch]);
+            const int64_t r = r0 + (int64_t)u * WPC;
+            if (lane < C && r < r_end) {
+                float d = dot[0];
+#pragma unroll
+                for (int ch = 1; ch < C; ++ch) d = lane == ch ? dot[ch] : d;
+                float val = (float)y[(size_t)r * C + lane] + d;
+                val = fminf(val, 255.f);                  // AboveXSetY(z, 255, 255), display.c:76
+                if (clip_low) val = fmaxf(val, 0.f);
+                if (z) z[(size_t)r * C + lane] = val;
+                if (z8) z8[(size_t)r * C + lane] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);
+            }
+        }
+    }
+}
+
 // c (fp32 [m_pad][C]) <- proj (fp64)
 __global__ void k_filter_c_from_proj(const double* __restrict__ proj, int count, float* __restrict__ c)
 {
@@ -271,7 +331,20 @@ static int run_filter(gl_ctx* ctx, gl_mat* phi, const FilterGeom& g, const doubl
     GL_LAUNCH_CHECK(ctx);
     {
         StageTimer kt(ctx, GL_T_K_FILTER_APPLY);
-        k_filter_apply<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, w, clip_low, z, z8);
+        const int ngl = (g.G % 32 == 0) ? g.G / 32 : 0;
+        int wgrid = ctx->sm_count * 8;
+        if ((int64_t)wgrid * 16 > rows) wgrid = (int)ceil_div(rows, 16);
+        if (ctx->filter_apply_impl == 1 || ngl == 0 || ngl * C > 12)
+            k_filter_apply<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, w, clip_low, z, z8);
+#define FLW_CASE(N)                                                                                                     \
+    else if (ngl == N) {                                                                                                \
+        if constexpr (N * C <= 12)                                                                                      \
+            k_filter_apply_warp<C, N><<<wgrid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, y, w, clip_low, z, z8);     \
+    }
+        FLW_CASE(1) FLW_CASE(2) FLW_CASE(3) FLW_CASE(4) FLW_CASE(5) FLW_CASE(6) FLW_CASE(7) FLW_CASE(8) FLW_CASE(9)
+        FLW_CASE(10) FLW_CASE(11) FLW_CASE(12)
+#undef FLW_CASE
+        else k_filter_apply<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, w, clip_low, z, z8);
     }
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;

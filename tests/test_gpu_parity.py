@@ -13,7 +13,7 @@ from oracle import oracle_np as o
 
 pytestmark = pytest.mark.gpu
 
-TOL_MU, TOL_Z, TOL_DZ = 1e-4, 1e-3, 2e-2
+TOL_MU, TOL_Z, TOL_DZ = 1e-4, 1e-3, 5e-3
 
 
 @pytest.fixture(scope="module")
@@ -195,7 +195,7 @@ def test_stage_by_stage_phi_properties(ctx, golden):
     ref = o.run_pipeline(img, s, return_phi=True)
     y = img.reshape(-1).astype(np.float64)
     err_proj = _rel(P @ (P.T @ y), ref["phi"] @ (ref["phi"].T @ y))
-    assert err_proj < 2e-3, err_proj
+    assert err_proj < 2e-2, err_proj     # Phi^T y cancels ~1e4-fold, so fp16 W shows here (the product path avoids it)
     norms = ctx.orthonormalise(phi)
     Q = phi.download()
     err_q = float(np.max(np.abs(Q.T @ Q - np.eye(Q.shape[1]))))
@@ -231,6 +231,27 @@ def test_synthetic_against_oracle(ctx, W, H, ch, p, kind, method):
     assert err_mu <= TOL_MU, err_mu
     assert err_z <= TOL_Z, err_z
     assert err_dz <= TOL_DZ, err_dz
+
+
+def test_projection_and_apply_variants_agree(ctx, golden):
+    """c = Phi^T y from the affinity sums (default) vs the stand-alone pass over Phi; warp-per-row vs generic apply."""
+    for tag in ("barbara_uniform256", "lion_rgb_photometric500", "test_uniform100"):
+        g = golden(tag)
+        src, a = _run_case(ctx, g)
+        z = g["z"].astype(np.float64)
+        res = {}
+        for proj, app in (("recompute", "warp"), ("sums", "generic"), ("recompute", "generic")):
+            ctx.set_option("projection", proj)
+            ctx.set_option("filter_apply", app)
+            try:
+                _, b = _run_case(ctx, g)
+            finally:
+                ctx.set_option("projection", "sums")
+                ctx.set_option("filter_apply", "warp")
+            res[(proj, app)] = (_rel(b["z"], z), _rel(b["z"] - src, z - src))
+            assert res[(proj, app)][0] <= TOL_Z
+            assert _rel(b["z"], a["z"].astype(np.float64)) < 2e-4
+        print(f"variants {tag}: default dz={_rel(a['z'] - src, z - src):.2e} " + " ".join(f"{k}:dz={v[1]:.2e}" for k, v in res.items()))
 
 
 def test_filter_options(ctx, golden):
