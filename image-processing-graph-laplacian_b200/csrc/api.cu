@@ -118,6 +118,8 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         if (!strcmp(value, "warp")) ctx->filter_apply_impl = 0;
         else if (!strcmp(value, "generic")) ctx->filter_apply_impl = 1;
         else GL_REQUIRE(false, "option filter_apply: want warp|generic, got %s", value);
+    } else if (!strcmp(key, "eig_largest")) {
+        ctx->eig_largest = atoi(value) != 0;   // EigendecompositionLargest (hpc/eigendecomposition.c:116-119)
     } else if (!strcmp(key, "jacobi_max_sweeps")) {
         ctx->jacobi_max_sweeps = atoi(value);
     } else if (!strcmp(key, "jacobi_tol")) {

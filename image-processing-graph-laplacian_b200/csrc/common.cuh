@@ -139,6 +139,7 @@ struct gl_ctx {
     // options
     int gemm_impl = 0;        // 0 = tcgen05 (default), 1 = simple CUDA-core checker kernel
     int gemm_cta_group = 1;   // 1 or 2
+    int eig_largest = 0;      // 1: keep the m LARGEST eigenpairs (descending) instead of the smallest (ascending)
     int jacobi_max_sweeps = 40;
     float jacobi_tol = 2e-6f;
     int verbose = 0;

@@ -349,12 +349,12 @@ __global__ void __launch_bounds__(1024, 1) k_jacobi_sort(const double* __restric
 
 // U[:, j] = g_order[j] / lambda, column-major fp32 with leading dimension ld; mu / 1/mu in fp64
 __global__ void k_jacobi_extract(const float* __restrict__ G, const double* __restrict__ lam, const double* __restrict__ ray,
-                                 const int* __restrict__ order, int p, int m, int ld, float* __restrict__ U,
+                                 const int* __restrict__ order, int p, int m, int ld, int largest, float* __restrict__ U,
                                  double* __restrict__ mu, double* __restrict__ mu_inv)
 {
     const int j = blockIdx.x;
     if (j >= m) return;
-    const int c = order[j];
+    const int c = order[largest ? p - 1 - j : j];
     const float inv = (float)(1.0 / lam[c]);
     const double l = ray[c];
     const float* col = G + (size_t)(c / JB) * p * JB + (c % JB);
@@ -447,7 +447,7 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         mui->buf = nullptr;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m, &mui->buf)) != GL_OK) break;
         k_jacobi_extract<<<m, 256, 0, ctx->stream>>>((const float*)G->ptr, (const double*)lam->ptr, (const double*)ray->ptr,
-                                                     (const int*)order->ptr, p, m, (int)U->ld, (float*)U->buf->ptr,
+                                                     (const int*)order->ptr, p, m, (int)U->ld, ctx->eig_largest, (float*)U->buf->ptr,
                                                      (double*)mu->buf->ptr, (double*)mui->buf->ptr);
         GL_LAUNCH_CHECK(ctx);
 
