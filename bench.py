@@ -163,9 +163,9 @@ def main():
     width, height, channels, p_req, sampling, affinity = wl
     n = width * height
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import ipgl_b200 as gl
+    from ipgl_b200 import dist as gd
+    rank, world, local_rank = gd.env_rank_world()
     if world != args.gpus and world > 1:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
     import torch
@@ -176,14 +176,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    import ipgl_b200 as gl
     ctx = gl.Context(local_rank, rank, world)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.tensor(list(gl.Context.unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        ctx.init_comm(bytes(uid.cpu().tolist()))
+        gd.init_comm(ctx, dist, device="cuda")
 
     prm = gl.default_params(affinity=affinity, sampling=sampling, sample_size=p_req, seed=SEED_SAMPLES,
                             gram_schmidt=args.gram_schmidt)
@@ -249,10 +244,7 @@ def main():
     r0, r1 = ctx.band()
     band_px = (r1 - r0) * width
 
-    if dist is not None:
-        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    t_dev, t_e2e = gd.max_over_ranks([t_dev, t_e2e], dist, device="cuda")
 
     p, m = info["p"], info["m"]
     ms_step = t_dev / args.steps

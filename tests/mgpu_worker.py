@@ -1,0 +1,43 @@
+"""One rank of the multi-GPU parity test (launched by tests/test_multi_gpu.py under torchrun, one process per GPU):
+runs the whole path through the C ABI on this rank's band of image rows and saves the band's z, the eigenvalues
+and the sample indices for the parent test to compare with the oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    out_dir, W, H, ch, p_req, sampling, gs = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6], int(sys.argv[7])
+    import torch
+    import torch.distributed as dist
+
+    import ipgl_b200 as gl
+    from ipgl_b200 import dist as gd
+
+    rank, world, local = gd.env_rank_world()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = gl.Context(local, rank, world)
+    gd.init_comm(ctx, dist, device="cuda")
+    ctx.set_synthetic_image(W, H, ch, 77)
+    img = ctx.get_image()
+    prm = gl.default_params(sampling=sampling, sample_size=p_req, seed=3, gram_schmidt=gs)
+    z = np.zeros(img.shape, dtype=np.float32)
+    r = ctx.run(img, prm, z_out=z)
+    r2 = ctx.run(img, prm, z_out=np.zeros_like(z))           # run twice: the comm must survive reuse
+    assert np.array_equal(r["mu"], r2["mu"])
+    r0, r1 = ctx.band()
+    assert (r0, r1) == gd.band(H, rank, world)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), z=z[r0:r1], mu=r["mu"], s=ctx.get_samples(), band=np.array([r0, r1]),
+             outside=np.array([float(np.abs(z[:r0]).sum() + np.abs(z[r1:]).sum())]))
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
