@@ -193,6 +193,12 @@ def main():
     info = None
     for _ in range(max(args.warmup, 3)):
         info = ctx.run_resident(prm)
+    # one staged pass to read how many [512 x 64] blocks of K_B the spatial cutoff keeps (executed vs dense flops)
+    ctx.sampling(sampling, p_req, SEED_SAMPLES)
+    K_A_, K_B_ = ctx.affinity(affinity)
+    kb_info = K_B_.info
+    stored_blocks = int(kb_info.stored_blocks)
+    K_A_.destroy(); K_B_.destroy()
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -255,8 +261,15 @@ def main():
     # algorithmic work per launch on THIS rank: extrapolation 2*p*m*rows flop; filter bytes
     f_ext = 2.0 * p * m * band_px
     f_aff = 2.0 * (2 + channels) * p * band_px
-    gemm_tf = f_ext / (med["k_gemm"] * 1e-3) / 1e12 if med["k_gemm"] > 0 else 0.0
     m_pad = 64 if m <= 64 else (128 if m <= 128 else (m + 255) // 256 * 256)
+    p_pad = (p + 63) // 64 * 64
+    dense_blocks = -(-band_px // 512) * (p_pad // 64)
+    f_ext_exec = 2.0 * stored_blocks * 512 * 64 * m_pad          # MMA work actually issued (padding included)
+    kb_bytes = stored_blocks * 512 * 64 * 2.0
+    gemm_bytes = kb_bytes + band_px * m_pad * 2.0                # K_B blocks read once + Phi written once
+    gemm_tf = f_ext / (med["k_gemm"] * 1e-3) / 1e12 if med["k_gemm"] > 0 else 0.0
+    gemm_tf_exec = f_ext_exec / (med["k_gemm"] * 1e-3) / 1e12 if med["k_gemm"] > 0 else 0.0
+    gemm_gbs = gemm_bytes / (med["k_gemm"] * 1e-3) / 1e9 if med["k_gemm"] > 0 else 0.0
     b_proj = band_px * m_pad * 2.0 + band_px * channels
     b_apply = band_px * m_pad * 2.0 + band_px * channels * (1 + 4)
     pair_ms = {k: float(np.median(v)) for k, v in pair.items()}
@@ -285,6 +298,11 @@ def main():
                                     in_pipeline="projection taken from the affinity sums: only k_filter_apply runs, %.0f GB/s (%.2f of peak)"
                                                 % (apply_gbs, apply_gbs / peaks["hbm"])),
                affinity_plus_extrapolation_tflops=aff_ext_tf,
+               kb_cutoff=dict(stored_blocks=stored_blocks, dense_blocks=int(dense_blocks), kept=stored_blocks / max(1, dense_blocks),
+                              note="sample blocks whose K_B entries fp16 flushes to zero (|drow| > h_loc*sqrt(25 ln 2)) are neither "
+                                   "computed, stored nor multiplied"),
+               gemm=dict(ms=med["k_gemm"], flop_dense_equivalent=f_ext, flop_executed=f_ext_exec, tflops_dense_equivalent=gemm_tf,
+                         tflops_executed=gemm_tf_exec, bytes=gemm_bytes, gbs=gemm_gbs),
                stage_ms={k: round(v, 4) for k, v in stage.items()},
                kernel_ms_median={k: round(v, 4) for k, v in med.items()})
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -16,6 +16,17 @@
 //   * coordinates and grey values are integers: differences are exact in fp32, the two bandwidth
 //     factors are applied to the exact squared distances, one ex2 per pair (the reference takes two exps
 //     and multiplies, hpc/affinity.c:99,107,110 -- equal up to rounding).
+//   * K_B is stored in BLOCKS of [512 pixels][64 samples] fp16 (a pixel row of a block = 128 contiguous bytes), and only
+//     the blocks that can hold a non-zero are stored: the samples are in ascending raster order, hence sorted by image
+//     row, so for a 512-pixel tile covering rows [ra, rb] the samples within R rows form a contiguous range, and
+//     everything outside it has exp(-dr^2/h_loc^2) < 2^-25, which fp16 storage flushes to zero anyway
+//     (R = floor(h_loc sqrt(25 ln 2)) + 1).  The tile table {first block, block count, block offset} is
+//     built on the host from the sample indices and cached.  Photometric affinity has no cutoff: every block is stored
+//     and the layout degenerates to a dense blocked matrix.  At 4K / p=1000 / h_loc=40 this keeps ~21 % of the blocks:
+//     the kernel evaluations, the K_B bytes and the extrapolation GEMM's K loop all shrink by that factor.
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 
 #define AFF_THREADS 256
@@ -70,7 +81,8 @@ template <int KIND, int C>
 __global__ void __launch_bounds__(AFF_THREADS, 2)
 k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int p_pad, int width, int64_t q0, int64_t q1,
              float a2, float b2,  // -log2(e)/h_loc^2, -log2(e)/h_val^2
-             __half* __restrict__ KB, float* __restrict__ partial /* [gridDim.x][1 + C][p_pad] */)
+             const int4* __restrict__ tab /* per tile: first block, block count, block offset */,
+             __half* __restrict__ KB /* [block][512][64] */, float* __restrict__ partial /* [gridDim.x][1 + C][p_pad] */)
 {
     extern __shared__ float aff_smem[];
     constexpr int NS = 1 + C;                  // sums per sample: D and T[ch]
@@ -78,7 +90,6 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
     float* ws = cta_sum + NS * p_pad;          // [2][NS][8 warps][64]
     float* px = ws + 2 * NS * 8 * 64;          // [(2 + C)][AFF_TP] pixel features
     const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3, lane = tid & 31, warp = tid >> 5;
-    const int chunks = p_pad >> 6;
     for (int i = tid; i < NS * p_pad; i += AFF_THREADS) cta_sum[i] = 0.f;
 
     const int64_t n_band = q1 - q0;
@@ -97,8 +108,11 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
             for (int ch = 0; ch < C; ++ch) px[(2 + ch) * AFF_TP + i] = (float)img[(size_t)qq * C + ch];
         }
         __syncthreads();
-        for (int ck = 0; ck < chunks; ++ck) {
+        const int4 tl = tab[tile];
+        for (int ci = 0; ci < tl.y; ++ci) {
+            const int ck = tl.x + ci;
             const int s0 = (ck << 6) + (tx << 3);
+            __half* kb_blk = KB + ((size_t)(tl.z + ci) * AFF_TP) * 64 + (tx << 3);
             float sr[8], sc[8], sv[C][8];
             if (KIND != GL_PHOTOMETRIC) {
                 *(float4*)&sr[0] = *(const float4*)&sf[s0];
@@ -158,7 +172,7 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
                     __half2 h2 = __floats2half2_rn(kv[4], kv[5]), h3 = __floats2half2_rn(kv[6], kv[7]);
                     uint4 pk;
                     pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
-                    *(uint4*)&KB[(size_t)(q - q0) * p_pad + s0] = pk;
+                    *(uint4*)&kb_blk[(size_t)pi * 64] = pk;
                 }
             }
             // row sums: fixed-order reduction (deterministic): lanes sharing tx, then the 8 warps
@@ -206,9 +220,63 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int nblocks
     DT[i] = acc;
 }
 
+// Tile table of K_B (see the header): one int4 {first 64-sample block, block count, block offset, 0} per 512-pixel tile
+// of this rank's band.  Built on the host (tiles x 2 binary searches over the sorted sample rows), uploaded only when
+// it differs from the cached one.
+static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
+{
+    const int p = (int)ctx->p, nblk = ctx->p_pad >> 6, W = ctx->width;
+    const int64_t n_band = ctx->q1 - ctx->q0;
+    const int64_t tiles = (n_band + AFF_TP - 1) / AFF_TP;
+    if (!ctx->h_samples_valid) {
+        ctx->h_samples.resize(p);
+        GL_CUDA_CHECK(cudaMemcpyAsync(ctx->h_samples.data(), ctx->samples->ptr, sizeof(uint32_t) * p, cudaMemcpyDeviceToHost, ctx->stream));
+        GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->h_samples_valid = true;
+    }
+    const bool cut = ctx->kb_cutoff && kind != GL_PHOTOMETRIC;
+    // |dr| > h_loc sqrt(25 ln 2)  =>  exp(-dr^2/h_loc^2) < 2^-25  =>  the fp16 value is 0; one more row for rounding slack
+    const double rr = std::floor(h_loc * std::sqrt(25.0 * 0.6931471805599453)) + 1.0;
+    const int64_t R = rr < 1e9 ? (int64_t)rr : (int64_t)1e9;
+    std::vector<int> srow(p);
+    for (int i = 0; i < p; ++i) srow[i] = (int)(ctx->h_samples[i] / (uint32_t)W);
+    std::vector<int4> tab((size_t)tiles);
+    int64_t off = 0;
+    for (int64_t t = 0; t < tiles; ++t) {
+        int lo = 0, cnt = nblk;
+        if (cut) {
+            const int64_t qa = ctx->q0 + t * AFF_TP, qb = std::min(ctx->q1, qa + AFF_TP) - 1;
+            const int64_t ra = qa / W - R, rb = qb / W + R;
+            const int s_lo = (int)(std::lower_bound(srow.begin(), srow.end(), (int)std::max<int64_t>(ra, -1)) - srow.begin());
+            const int s_hi = (int)(std::upper_bound(srow.begin(), srow.end(), (int)std::min<int64_t>(rb, 0x7fffffff)) - srow.begin());
+            lo = s_lo >> 6;
+            cnt = ((s_hi + 63) >> 6) - lo;
+            if (cnt < 1) { lo = std::min(lo, nblk - 1); cnt = 1; }   // keep one block so that the GEMM writes zeros
+        }
+        tab[(size_t)t] = make_int4(lo, cnt, (int)off, 0);
+        off += cnt;
+        GL_REQUIRE(off < 0x7fffffff / 512, "affinity: K_B has too many blocks for 32-bit tile coordinates");
+    }
+    const bool same = ctx->tile_tab && ctx->h_tile_tab.size() == tab.size() &&
+                      !memcmp(ctx->h_tile_tab.data(), tab.data(), sizeof(int4) * tab.size());
+    if (!same) {
+        const size_t bytes = sizeof(int4) * tab.size();
+        if (ctx->tile_tab) gl_buf_release(ctx->tile_tab);
+        ctx->tile_tab = nullptr;
+        GL_CHECK(gl_alloc(ctx, bytes, &ctx->tile_tab));
+        GL_CHECK(gl_ensure_pinned(ctx, bytes));
+        GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the pinned block may still feed an earlier copy
+        memcpy(ctx->pinned, tab.data(), bytes);
+        GL_CUDA_CHECK(cudaMemcpyAsync(ctx->tile_tab->ptr, ctx->pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h_tile_tab.swap(tab);
+        ctx->tile_total_blocks = off;
+    }
+    return GL_OK;
+}
+
 template <int KIND, int C>
-static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float* sf, double* KA, __half* KB, float* partial,
-                           int grid)
+static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float* sf, double* KA, const int4* tab, __half* KB,
+                           float* partial, int grid)
 {
     const int p = (int)ctx->p, p_pad = ctx->p_pad;
     dim3 ga((unsigned)ceil_div(p, 128), (unsigned)p);
@@ -221,7 +289,7 @@ static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float*
     StageTimer kt(ctx, GL_T_K_AFFINITY_B);
     k_affinity_B<KIND, C><<<grid, AFF_THREADS, smem, ctx->stream>>>(
         (const uint8_t*)ctx->img->ptr, sf, p_pad, ctx->width, ctx->q0, ctx->q1, (float)(-log2e / (h_loc * h_loc)),
-        (float)(-log2e / (h_val * h_val)), KB, partial);
+        (float)(-log2e / (h_val * h_val)), tab, KB, partial);
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;
 }
@@ -245,12 +313,16 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         KB->rows = p;                   // logical K_B: p x (n - p); stored transposed for the whole band
         KB->cols = ctx->n - p;
         KB->local_rows = n_band;
-        KB->ld = p_pad;
+        KB->ld = 64;                    // blocked storage: a pixel row of a block is 64 samples
         KB->elem_bytes = 2;
         KB->p = p;
         KB->p_pad = p_pad;
         KB->q0 = ctx->q0;
-        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)n_band * p_pad, &KB->buf)) != GL_OK) break;
+        if ((rc = build_tile_table(ctx, kind, h_loc)) != GL_OK) break;
+        KB->tiles = ctx->tile_tab;      // shared with the context's cache (a new table is a new buffer)
+        KB->tiles->refs++;
+        KB->total_blocks = ctx->tile_total_blocks;
+        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)KB->total_blocks * AFF_TP * 64, &KB->buf)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)(1 + C) * p_pad, &KB->aux)) != GL_OK) break;  // [D | T[ch]]
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_pad, &sf)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * (1 + C) * p_pad, &partial)) != GL_OK) break;
@@ -261,8 +333,8 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
 
 #define AFF_CASE(K, CC)                                                                                              \
     if (kind == K && C == CC)                                                                                        \
-        rc = launch_affinity<K, CC>(ctx, h_loc, h_val, (const float*)sf->ptr, (double*)KA->buf->ptr, (__half*)KB->buf->ptr, \
-                                    (float*)partial->ptr, grid);
+        rc = launch_affinity<K, CC>(ctx, h_loc, h_val, (const float*)sf->ptr, (double*)KA->buf->ptr, (const int4*)KB->tiles->ptr, \
+                                    (__half*)KB->buf->ptr, (float*)partial->ptr, grid);
         AFF_CASE(GL_BILATERAL, 1) else AFF_CASE(GL_BILATERAL, 3) else AFF_CASE(GL_PHOTOMETRIC, 1)
         else AFF_CASE(GL_PHOTOMETRIC, 3) else AFF_CASE(GL_SPATIAL, 1) else AFF_CASE(GL_SPATIAL, 3)
 #undef AFF_CASE

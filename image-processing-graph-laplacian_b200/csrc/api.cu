@@ -118,6 +118,8 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         if (!strcmp(value, "warp")) ctx->filter_apply_impl = 0;
         else if (!strcmp(value, "generic")) ctx->filter_apply_impl = 1;
         else GL_REQUIRE(false, "option filter_apply: want warp|generic, got %s", value);
+    } else if (!strcmp(key, "kb_cutoff")) {
+        ctx->kb_cutoff = atoi(value) != 0;
     } else if (!strcmp(key, "eig_largest")) {
         ctx->eig_largest = atoi(value) != 0;   // EigendecompositionLargest (hpc/eigendecomposition.c:116-119)
     } else if (!strcmp(key, "jacobi_max_sweeps")) {
@@ -148,6 +150,7 @@ int gl_ctx_destroy(gl_ctx* ctx)
     gl_comm_destroy(ctx);
     if (ctx->img) gl_buf_release(ctx->img);
     if (ctx->samples) gl_buf_release(ctx->samples);
+    if (ctx->tile_tab) gl_buf_release(ctx->tile_tab);
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
     ctx->free_blocks.clear();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -397,6 +400,8 @@ int gl_set_samples(gl_ctx* ctx, const uint32_t* indices, unsigned count)
     GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->p = count;
     ctx->p_pad = p_pad;
+    ctx->h_samples.assign(indices, indices + count);
+    ctx->h_samples_valid = true;
     return GL_OK;
 }
 
@@ -509,6 +514,7 @@ int gl_mat_info_get(const gl_mat* m, gl_mat_info* info)
         mm->scale_on_host = true;
     }
     info->scale = m->scale;
+    info->stored_blocks = m->total_blocks;
     return GL_OK;
 }
 
@@ -525,6 +531,7 @@ int gl_mat_destroy(gl_mat* m)
     if (--m->refs > 0) return GL_OK;
     if (m->buf) gl_buf_release(m->buf);
     if (m->aux) gl_buf_release(m->aux);
+    if (m->tiles) gl_buf_release(m->tiles);
     if (m->dscale) gl_buf_release(m->dscale);
     if (m->proj) gl_buf_release(m->proj);
     delete m;
@@ -541,6 +548,21 @@ __global__ void k_half_to_f64(const __half* __restrict__ src, int64_t ld, int64_
     if (i >= rows * cols) return;
     int64_t r = i / cols, c = i % cols;
     dst[i] = scale * (double)__half2float(src[r * ld + c]);
+}
+// K_B from its blocked storage ([block][512 pixels][64 samples], affinity.cu) to dense fp64 rows x cols; blocks that
+// were never stored (all entries below the fp16 flush-to-zero cutoff) read as 0
+__global__ void k_kb_blocked_to_f64(const __half* __restrict__ src, const int4* __restrict__ tab, int64_t rows, int64_t cols,
+                                    double scale, double* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols;
+    const int c = (int)(i % cols);
+    const int4 tl = tab[r >> 9];
+    const int blk = (c >> 6) - tl.x;
+    double v = 0.0;
+    if (blk >= 0 && blk < tl.y) v = (double)__half2float(src[(((size_t)tl.z + blk) * 512 + (size_t)(r & 511)) * 64 + (c & 63)]);
+    dst[i] = scale * v;
 }
 __global__ void k_colmajor_f32_to_f64(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols,
                                       double* __restrict__ dst)
@@ -591,7 +613,8 @@ int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap)
         k_scale_f64<<<blocks, T, 0, ctx->stream>>>((const double*)m->buf->ptr, count, m->scale, d);
         break;
     case GL_MAT_KB:
-        k_half_to_f64<<<blocks, T, 0, ctx->stream>>>((const __half*)m->buf->ptr, m->ld, rows, cols, m->scale, d);
+        k_kb_blocked_to_f64<<<blocks, T, 0, ctx->stream>>>((const __half*)m->buf->ptr, (const int4*)m->tiles->ptr, rows, cols,
+                                                           m->scale, d);
         break;
     case GL_MAT_PHI:
         k_half_to_f64<<<blocks, T, 0, ctx->stream>>>((const __half*)m->buf->ptr, m->ld, rows, cols, m->scale, d);

@@ -78,6 +78,8 @@ struct gl_mat {
     double scale = 1.0;
     gl_buf* buf = nullptr;       // main storage
     gl_buf* aux = nullptr;       // KB: fp64 row sums D[p] (summed over ranks)
+    gl_buf* tiles = nullptr;     // KB: int4 per 512-pixel tile {first 64-sample block, block count, block offset, 0}
+    int64_t total_blocks = 0;    // KB: stored [512 x 64] blocks (see affinity.cu)
     gl_buf* dscale = nullptr;    // optional device double holding `scale` (L_B: -alpha), so no host sync is needed
     bool scale_on_host = true;   // false until the device value has been fetched
     int refs = 1;
@@ -120,6 +122,14 @@ struct gl_ctx {
     unsigned p = 0;
     int p_pad = 0;
     gl_buf* samples = nullptr;  // u32 [p_pad] (padding = 0xffffffff)
+    std::vector<uint32_t> h_samples;  // host mirror of the sample indices (tile-table construction, affinity.cu)
+    bool h_samples_valid = false;
+
+    // cached K_B tile table (affinity.cu): rebuilt only when the geometry, the samples or the cutoff change
+    gl_buf* tile_tab = nullptr;
+    std::vector<int4> h_tile_tab;
+    int64_t tile_total_blocks = 0;
+    int kb_cutoff = 1;        // option kb_cutoff: 1 = skip sample blocks whose K_B entries fp16 flushes to zero, 0 = dense
 
     // size-keyed cache of freed device blocks (no cudaMalloc in steady state)
     std::multimap<size_t, void*> free_blocks;
@@ -176,8 +186,9 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
 int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out);
 int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip_low, float* z_f32, uint8_t* z_u8);
 int gl_impl_diag_map(gl_ctx* ctx, gl_mat* d, int op, double arg, gl_mat** out);
+// A is either a dense [rows][k_pad] K-major matrix (a_tab == nullptr) or K_B's blocked storage with its tile table
 int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
-                   const float* scales, const void* addend, void* D);
+                   const float* scales, const void* addend, void* D, const int4* a_tab = nullptr, int64_t a_total_blocks = 0);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -63,6 +63,7 @@ int gl_impl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A_out, g
     LB->refs = 1;
     LB->buf->refs++;         // ... sharing the storage
     if (LB->aux) LB->aux->refs++;
+    if (LB->tiles) LB->tiles->refs++;
     LB->proj = nullptr;
     LB->dscale = al;         // scale = -alpha, device resident
     LB->scale_on_host = false;

@@ -208,6 +208,52 @@ __global__ void __launch_bounds__(256) k_gemm_simple(const T* __restrict__ A, co
         }
 }
 
+// element (r, k) of K_B in its blocked storage; blocks outside the tile's range are zero
+__device__ __forceinline__ float kb_blocked_at(const __half* __restrict__ A, const int4* __restrict__ tab, int64_t r, int k)
+{
+    const int4 tl = tab[r >> 9];
+    const int blk = (k >> 6) - tl.x;
+    if (blk < 0 || blk >= tl.y) return 0.f;
+    return __half2float(A[(((size_t)tl.z + blk) * 512 + (size_t)(r & 511)) * 64 + (k & 63)]);
+}
+
+__global__ void __launch_bounds__(256) k_gemm_simple_blocked(const __half* __restrict__ A, const int4* __restrict__ tab,
+                                                             const __half* __restrict__ Bt, int64_t M, int N, int K,
+                                                             const float* __restrict__ scales, __half* __restrict__ D)
+{
+    __shared__ float As[32][33], Bs[32][33];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t m0 = (int64_t)blockIdx.y * 32;
+    const int n0 = blockIdx.x * 32;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+            const int r = i >> 5, c = i & 31;
+            As[r][c] = (m0 + r < M) ? kb_blocked_at(A, tab, m0 + r, k0 + c) : 0.f;
+            Bs[r][c] = (n0 + r < N) ? __half2float(Bt[(size_t)(n0 + r) * K + k0 + c]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float a0 = As[ty][k], a1 = As[ty + 16][k], b0 = Bs[tx][k], b1 = Bs[tx + 16][k];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]);
+            acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]);
+            acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+    const float sc = scales[1];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int64_t r = m0 + ty + 16 * a;
+            const int c = n0 + tx + 16 * b;
+            if (r < M && c < N) D[(size_t)r * N + c] = __float2half_rn(acc[a][b] * sc);
+        }
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 GEMM
 // ---------------------------------------------------------------------------------------------
@@ -359,7 +405,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, int m_tiles, int n_tiles, int k_blocks, int n_total, int block_n,
                int ab_bf16, const float* __restrict__ scales, const __half* __restrict__ addend, int64_t m_rows,
-               int* __restrict__ err)
+               const int4* __restrict__ a_tab /* K_B tile table, or null for a dense A */, int* __restrict__ err)
 {
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -409,11 +455,24 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / n_tiles, nt = tile % n_tiles;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                // dense A: K block kb of rows mt*128..; blocked A (K_B): block (offset + kb) of the 512-pixel tile, rows
+                // (mt % 4) * 128.. inside it, multiplying rows (first block + kb) * 64.. of W
+                int kb_first = 0, kb_count = k_blocks, a_row = mt * BLOCK_M, a_row_step = 0, a_col_step = BLOCK_K;
+                if (a_tab) {
+                    const int4 tl = a_tab[mt >> 2];
+                    kb_first = tl.x;
+                    kb_count = tl.y;
+                    a_row = tl.z * 512 + (mt & 3) * BLOCK_M;
+                    a_row_step = 512;
+                    a_col_step = 0;
+                }
+                for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1, err, 1);
                     mbar_expect_tx(bar_full + 8 * stage, stage_tx);
-                    tma_load_2d(smem_u32(smem_a + stage * A_STAGE_BYTES), &map_a, bar_full + 8 * stage, kb * BLOCK_K, mt * BLOCK_M);
-                    tma_load_2d(smem_u32(smem_b + stage * B_STAGE_BYTES), &map_b, bar_full + 8 * stage, kb * BLOCK_K, nt * block_n);
+                    tma_load_2d(smem_u32(smem_a + stage * A_STAGE_BYTES), &map_a, bar_full + 8 * stage, kb * a_col_step,
+                                a_row + kb * a_row_step);
+                    tma_load_2d(smem_u32(smem_b + stage * B_STAGE_BYTES), &map_b, bar_full + 8 * stage, (kb_first + kb) * BLOCK_K,
+                                nt * block_n);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -426,6 +485,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int nt = tile % n_tiles;
+                const int kb_count = a_tab ? a_tab[(tile / n_tiles) >> 2].y : k_blocks;
                 const int n_size = min(block_n, n_total - nt * block_n);
                 const uint32_t idesc = make_idesc(BLOCK_M, n_size, (uint32_t)ab_bf16);
                 const int acc = it & 1;
@@ -433,7 +493,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, err, 2);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_BLOCK_N);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase, err, 3);
                     tcgen05_fence_after();
                     const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
@@ -575,13 +635,17 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* bas
 // D[rows][n_pad] (fp16) = scales[1] * A[rows][k_pad] . Bt[n_pad][k_pad]^T (+ addend), A and Bt 16-bit K-major
 // (ab_bf16: 0 = fp16, 1 = bf16).  k_pad % 64 == 0; n_pad is 64, 128 or a multiple of 256 (gl_m_pad).
 int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
-                   const float* scales, const void* addend, void* D)
+                   const float* scales, const void* addend, void* D, const int4* a_tab, int64_t a_total_blocks)
 {
     GL_REQUIRE(k_pad % 64 == 0 && n_pad % 64 == 0, "gemm: k_pad %d / n_pad %d must be multiples of 64", k_pad, n_pad);
     if (ctx->gemm_impl == 1) {
         dim3 grid((unsigned)ceil_div(n_pad, 32), (unsigned)ceil_div(rows, 32));
         GL_REQUIRE(ceil_div(rows, 32) < 2147483647ll, "gemm(simple): band too large");
-        if (ab_bf16)
+        if (a_tab) {
+            GL_REQUIRE(!ab_bf16 && !addend, "gemm(simple): the blocked operand is fp16 K_B without addend");
+            k_gemm_simple_blocked<<<grid, 256, 0, ctx->stream>>>((const __half*)A, a_tab, (const __half*)Bt, rows, n_pad, k_pad, scales,
+                                                                 (__half*)D);
+        } else if (ab_bf16)
             k_gemm_simple<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bt, rows, n_pad,
                                                                          k_pad, scales, (const __half*)addend,
                                                                          (__half*)D);
@@ -595,7 +659,10 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     GL_REQUIRE(n_pad % block_n == 0, "gemm: n_pad %d is not a multiple of the N tile %d", n_pad, block_n);
     const CUtensorMapDataType dt = ab_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap map_a, map_b, map_d;
-    GL_CHECK(make_map_2d(&map_a, dt, A, (uint64_t)rows, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, tc::BLOCK_M));
+    if (a_tab)  // K_B's blocked storage seen as one tall [blocks * 512][64] matrix
+        GL_CHECK(make_map_2d(&map_a, dt, A, (uint64_t)a_total_blocks * 512, 64, 64, tc::BLOCK_K, tc::BLOCK_M));
+    else
+        GL_CHECK(make_map_2d(&map_a, dt, A, (uint64_t)rows, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, tc::BLOCK_M));
     GL_CHECK(make_map_2d(&map_b, dt, Bt, (uint64_t)n_pad, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, (uint32_t)block_n));
     GL_CHECK(make_map_2d(&map_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, (uint64_t)rows, (uint64_t)n_pad, (uint64_t)n_pad, 64, 32));
     const int m_tiles = (int)ceil_div(rows, tc::BLOCK_M);
@@ -610,7 +677,7 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     StageTimer kt(ctx, GL_T_K_GEMM);
     tc::k_gemm_tcgen05<<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad,
                                                                            block_n, ab_bf16, scales, (const __half*)addend,
-                                                                           rows, (int*)err->ptr);
+                                                                           rows, a_tab, (int*)err->ptr);
     gl_buf_release(err);
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;
@@ -655,8 +722,9 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
                                                   (const float*)scales->ptr, (__half*)Wt->ptr);
         GL_LAUNCH_CHECK(ctx);
 
+        GL_REQUIRE(L_B->tiles, "nystroem: K_B handle without a tile table");
         if ((rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, p_pad, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
-                                 phi->buf->ptr)) != GL_OK) break;
+                                 phi->buf->ptr, (const int4*)L_B->tiles->ptr, L_B->total_blocks)) != GL_OK) break;
         // projection c = Phi^T y from the affinity sums (valid while the image and the samples are unchanged)
         if (L_B->aux && L_B->channels == ctx->channels && L_B->image_epoch == ctx->image_epoch) {
             const int C = ctx->channels;

@@ -32,6 +32,7 @@ static int set_sample_buffer(gl_ctx* ctx, unsigned count)
     GL_CHECK(gl_alloc(ctx, sizeof(uint32_t) * p_pad, &ctx->samples));
     ctx->p = count;
     ctx->p_pad = p_pad;
+    ctx->h_samples_valid = false;
     return GL_OK;
 }
 
@@ -52,6 +53,10 @@ int gl_impl_sampling_uniform(gl_ctx* ctx, unsigned requested, unsigned* actual)
                                                                                  (unsigned)ctx->p_pad, cols, xy0, dist,
                                                                                  (unsigned)width);
     GL_LAUNCH_CHECK(ctx);
+    // host mirror (same formula; needed by the K_B tile table, affinity.cu)
+    ctx->h_samples.resize(count);
+    for (unsigned c = 0; c < count; ++c) ctx->h_samples[c] = (unsigned)width * (xy0 + (c / cols) * dist) + xy0 + (c % cols) * dist;
+    ctx->h_samples_valid = true;
     if (actual) *actual = count;
     return GL_OK;
 }
@@ -252,11 +257,20 @@ int gl_impl_sampling_random(gl_ctx* ctx, unsigned requested, uint32_t seed, unsi
     k_random_sampling<<<1, RS_THREADS, smem, ctx->stream>>>(seed, (uint32_t)ctx->n, requested, (uint32_t)ctx->p_pad,
                                                            (uint32_t*)ctx->samples->ptr, (int*)st->ptr);
     GL_LAUNCH_CHECK(ctx);
-    GL_CHECK(gl_ensure_pinned(ctx, 64));
+    // the status word and the indices come back in the same synchronisation (host mirror for the K_B tile table)
+    GL_CHECK(gl_ensure_pinned(ctx, 64 + sizeof(uint32_t) * requested));
     GL_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, st->ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA_CHECK(cudaMemcpyAsync((char*)ctx->pinned + 64, ctx->samples->ptr, sizeof(uint32_t) * requested, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
     GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     gl_buf_release(st);
     const int status = *(int*)ctx->pinned;
+    ctx->h_samples_valid = false;
+    if (status == 0) {
+        const uint32_t* hs = (const uint32_t*)((char*)ctx->pinned + 64);
+        ctx->h_samples.assign(hs, hs + requested);
+        ctx->h_samples_valid = true;
+    }
     if (status != 0) {
         gl_set_error("random sampling kernel failed (status %d)", status);
         return status == 1 ? GL_ERR_UNSUPPORTED : GL_ERR_CUDA;

@@ -60,8 +60,10 @@ enum gl_affinity_kind { /* hpc/affinity.c:115-122 picks bilateral; the two other
 
 enum gl_mat_kind {
     GL_MAT_KA = 1,      /* p x p fp64 row-major (K_A or L_A) */
-    GL_MAT_KB = 2,      /* this rank's pixel band x p_pad fp16: K_B stored pixel-major (transposed), all band
-                           pixels incl. samples; carries the fp64 row sums D = K_A.1 + K_B.1 */
+    GL_MAT_KB = 2,      /* this rank's pixel band x p fp16: K_B stored pixel-major (transposed) in blocks of
+                           [512 pixels][64 samples], all band pixels incl. samples; sample blocks whose entries
+                           fp16 flushes to zero (spatial distance) are not stored; carries the fp64 row sums
+                           D = K_A.1 + K_B.1 */
     GL_MAT_EIGVEC = 3,  /* p x m fp32 column-major (eigenvectors of L_A in columns) */
     GL_MAT_DIAG = 4,    /* m-vector fp64 standing for a diagonal matrix */
     GL_MAT_PHI = 5      /* this rank's pixel band x m_pad fp16 row-major, rows in raster order */
@@ -74,6 +76,7 @@ typedef struct gl_mat_info {
     int64_t ld;          /* leading dimension in elements of the stored layout */
     int elem_bytes;
     double scale;        /* logical value = scale * stored value (L_B = -alpha K_B shares K_B's buffer) */
+    int64_t stored_blocks; /* KB: [512 x 64] blocks held (of ceil(local_rows/512) * ceil(p/64) dense ones); else 0 */
 } gl_mat_info;
 
 /* Stage indices for gl_ctx_stage_ms (same vocabulary as the reference's stdout timers,

@@ -254,6 +254,46 @@ def test_projection_and_apply_variants_agree(ctx, golden):
         print(f"variants {tag}: default dz={_rel(a['z'] - src, z - src):.2e} " + " ".join(f"{k}:dz={v[1]:.2e}" for k, v in res.items()))
 
 
+def test_kb_cutoff_blocks(ctx):
+    """K_B's spatial cutoff (sample blocks whose entries fp16 flushes to zero are not stored, affinity.cu): the
+    stored blocks shrink, the skipped entries really are < 2^-25 in the oracle, and the result equals the dense run."""
+    W, H, p_req, h_loc = 200, 1500, 700, 12.0
+    img = o.synthetic_image(W, H, 1, seed=3)
+    s = oc.uniform_sampling(W, H, p_req)
+    out = {}
+    for cut in (1, 0):
+        ctx.set_option("kb_cutoff", cut)
+        try:
+            ctx.set_image(img)
+            ctx.set_samples(s)
+            K_A, K_B = ctx.affinity(gl.BILATERAL, h_loc, 30.0)
+            info = K_B.info
+            dense_blocks = -(-img.size // 512) * -(-len(s) // 64)
+            D = K_B.rowsums()
+            L_A, L_B = ctx.laplacian(K_A, K_B)
+            U, mu, mu_inv = ctx.eigensolve(L_A, -1)
+            phi = ctx.nystroem(L_B, U, mu_inv)
+            z = ctx.filter(phi, mu)
+            KB = K_B.download()
+            out[cut] = dict(blocks=info.stored_blocks, dense=dense_blocks, D=D, z=z.astype(np.float64), KB=KB, mu=mu.download())
+        finally:
+            ctx.set_option("kb_cutoff", 1)
+    assert out[0]["blocks"] == out[0]["dense"]
+    assert out[1]["blocks"] < 0.25 * out[1]["dense"], (out[1]["blocks"], out[1]["dense"])
+    # every entry the cutoff dropped is below fp16's flush-to-zero threshold in the fp64 oracle
+    cols = np.arange(0, img.size, 97)
+    ref = o.affinity_rows(img, s, cols, "bilateral", h_loc, 30.0).T
+    dropped = (out[1]["KB"][cols] == 0) & (out[0]["KB"][cols] != 0)
+    assert not dropped.any() or ref[dropped].max() < 2.0 ** -24
+    assert np.max(np.abs(out[1]["KB"][cols] - ref)) < 6e-4
+    assert np.max(np.abs(out[1]["D"] - out[0]["D"]) / out[0]["D"]) < 1e-6
+    assert np.max(np.abs(out[1]["mu"] - out[0]["mu"]) / out[0]["mu"]) < 1e-6
+    assert _rel(out[1]["z"], out[0]["z"]) < 1e-6
+    refp = oc.run_pipeline(img, s, h_loc=h_loc)
+    assert np.max(np.abs(out[1]["mu"] - refp["mu"]) / refp["mu"]) <= TOL_MU
+    assert _rel(out[1]["z"], refp["z"]) <= TOL_Z and _rel(out[1]["z"] - img, refp["z"] - img) <= TOL_DZ
+
+
 def test_filter_options(ctx, golden):
     g = golden("test_uniform100")
     img, s = g["image"], g["sample_indices"]
