@@ -238,6 +238,10 @@ static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
     // |dr| > h_loc sqrt(25 ln 2)  =>  exp(-dr^2/h_loc^2) < 2^-25  =>  the fp16 value is 0; one more row for rounding slack
     const double rr = std::floor(h_loc * std::sqrt(25.0 * 0.6931471805599453)) + 1.0;
     const int64_t R = rr < 1e9 ? (int64_t)rr : (int64_t)1e9;
+    const int64_t key[6] = {W, ctx->q0, ctx->q1, p, R, cut ? 1 : 0};
+    if (ctx->tile_tab && !memcmp(key, ctx->tab_key, sizeof(key)) && ctx->tab_samples.size() == (size_t)p &&
+        !memcmp(ctx->tab_samples.data(), ctx->h_samples.data(), sizeof(uint32_t) * p))
+        return GL_OK;  // same geometry, samples and cutoff as last time: the cached table stands
     std::vector<int> srow(p);
     for (int i = 0; i < p; ++i) srow[i] = (int)(ctx->h_samples[i] / (uint32_t)W);
     std::vector<int4> tab((size_t)tiles);
@@ -271,6 +275,8 @@ static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
         ctx->h_tile_tab.swap(tab);
         ctx->tile_total_blocks = off;
     }
+    memcpy(ctx->tab_key, key, sizeof(key));
+    ctx->tab_samples = ctx->h_samples;
     return GL_OK;
 }
 

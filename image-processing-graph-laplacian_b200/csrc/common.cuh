@@ -128,6 +128,8 @@ struct gl_ctx {
     // cached K_B tile table (affinity.cu): rebuilt only when the geometry, the samples or the cutoff change
     gl_buf* tile_tab = nullptr;
     std::vector<int4> h_tile_tab;
+    std::vector<uint32_t> tab_samples;  // the samples and parameters the cached table was built from
+    int64_t tab_key[6] = {-1, -1, -1, -1, -1, -1};
     int64_t tile_total_blocks = 0;
     int kb_cutoff = 1;        // option kb_cutoff: 1 = skip sample blocks whose K_B entries fp16 flushes to zero, 0 = dense
 

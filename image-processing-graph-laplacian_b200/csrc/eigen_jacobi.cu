@@ -17,6 +17,8 @@
 //     every GPU of a multi-GPU run can solve redundantly and hold identical eigenvectors.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -54,9 +56,166 @@ __device__ __forceinline__ void tournament(int step, int pair, int nb, int& a, i
     if (a > b) { int t = a; a = b; b = t; }
 }
 
+// One panel pair (I, J): load the two panels, form the 16 x 16 Gram block, diagonalise it, rotate the panels.
+__device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I, int J, float tol, float* P, float* red, double* Bm,
+                                            double* Qm, double* cs, int* role, int* pq, float* s_off, unsigned* s_cta_off)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int bi = tid >> 4, bj = tid & 15;  // this thread's element of the 16 x 16 block
+    float* GI = G + (size_t)I * p * JB;
+    float* GJ = G + (size_t)J * p * JB;
+    // ---- load the panel pair (L2 loads: the data was written by other SMs) ----
+    for (int idx = tid; idx < 2 * p; idx += J_THREADS) {
+        const int r = idx >> 1, h = idx & 1;
+        float4 a = __ldcg((const float4*)(GI + (size_t)r * JB + h * 4));
+        float4 b = __ldcg((const float4*)(GJ + (size_t)r * JB + h * 4));
+        *(float4*)(P + (size_t)r * JP + h * 4) = a;
+        *(float4*)(P + (size_t)r * JP + JB + h * 4) = b;
+    }
+    if (tid == 0) *s_cta_off = 0u;
+    __syncthreads();
+    // ---- Gram block: 16 row groups x (4 x 4 register tiles) ----
+    {
+        const int rg = tid >> 4, ti = (tid >> 2) & 3, tj = tid & 3;
+        float acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+        for (int r = rg; r < p; r += 16) {
+            const float4 a = *(const float4*)(P + (size_t)r * JP + 4 * ti);
+            const float4 b = *(const float4*)(P + (size_t)r * JP + 4 * tj);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) red[rg * 256 + (4 * ti + x) * 16 + 4 * tj + y] = acc[x][y];
+    }
+    __syncthreads();
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int rg = 0; rg < 16; ++rg) s += (double)red[rg * 256 + tid];
+        Bm[bi * 17 + bj] = s;
+        Qm[bi * 17 + bj] = (bi == bj) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    // ---- how far from orthogonal is this pair now (rotations made earlier in the sweep may have changed it) ----
+    {
+        float rel = 0.f;
+        if (bi < bj) {
+            const double dii = Bm[bi * 17 + bi], djj = Bm[bj * 17 + bj];
+            if (dii > 0.0 && djj > 0.0) rel = (float)(fabs(Bm[bi * 17 + bj]) / sqrt(dii * djj));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rel = fmaxf(rel, __shfl_xor_sync(0xffffffffu, rel, o));
+        if (lane == 0) atomicMax(s_cta_off, __float_as_uint(rel));
+    }
+    __syncthreads();
+    const float pair_off = __uint_as_float(*s_cta_off);
+    // ---- diagonalise the 16 x 16 block: cyclic two-sided Jacobi, Q accumulates the rotations ----
+    if (pair_off > 0.25f * tol) {
+        if (tid == 0) *s_off = 0.f;
+        __syncthreads();
+        for (int isw = 0; isw < J_INNER_MAX; ++isw) {
+            for (int st = 0; st < JP - 1; ++st) {
+                if (tid < JB) {
+                    int a, b;
+                    tournament(st, tid, JP, a, b);
+                    const double app = Bm[a * 17 + a], aqq = Bm[b * 17 + b], apq = Bm[a * 17 + b];
+                    double c = 1.0, s = 0.0;
+                    if (app > 0.0 && aqq > 0.0) {
+                        const double reld = fabs(apq) / sqrt(app * aqq);
+                        if (reld > 1e-13) {
+                            const double tau = (aqq - app) / (2.0 * apq);
+                            const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                            c = 1.0 / sqrt(1.0 + t * t);
+                            s = t * c;
+                        }
+                        const float rel = (float)reld;
+                        if (rel > *s_off) atomicMax((unsigned*)s_off, __float_as_uint(rel));
+                    }
+                    cs[2 * tid] = c;
+                    cs[2 * tid + 1] = s;
+                    pq[2 * tid] = a;
+                    pq[2 * tid + 1] = b;
+                    role[a] = tid << 1;
+                    role[b] = (tid << 1) | 1;
+                }
+                __syncthreads();
+                double nb_, nq_;
+                {
+                    const int ri = role[bi], rj = role[bj];
+                    const int ki = ri >> 1, kj = rj >> 1;
+                    const double ci = cs[2 * ki], si = cs[2 * ki + 1], cj = cs[2 * kj], sj = cs[2 * kj + 1];
+                    const int ip = pq[2 * ki], iq = pq[2 * ki + 1], jp = pq[2 * kj], jq = pq[2 * kj + 1];
+                    double x_ip, x_iq;  // (B J)[ip][bj], (B J)[iq][bj]
+                    if ((rj & 1) == 0) {
+                        x_ip = cj * Bm[ip * 17 + jp] - sj * Bm[ip * 17 + jq];
+                        x_iq = cj * Bm[iq * 17 + jp] - sj * Bm[iq * 17 + jq];
+                        nq_ = cj * Qm[bi * 17 + jp] - sj * Qm[bi * 17 + jq];
+                    } else {
+                        x_ip = sj * Bm[ip * 17 + jp] + cj * Bm[ip * 17 + jq];
+                        x_iq = sj * Bm[iq * 17 + jp] + cj * Bm[iq * 17 + jq];
+                        nq_ = sj * Qm[bi * 17 + jp] + cj * Qm[bi * 17 + jq];
+                    }
+                    nb_ = ((ri & 1) == 0) ? (ci * x_ip - si * x_iq) : (si * x_ip + ci * x_iq);
+                }
+                __syncthreads();
+                Bm[bi * 17 + bj] = nb_;
+                Qm[bi * 17 + bj] = nq_;
+                __syncthreads();
+            }
+            const float inner_off = *s_off;
+            __syncthreads();
+            if (tid == 0) *s_off = 0.f;
+            __syncthreads();
+            if (inner_off <= 0.1f * tol) break;
+        }
+        // ---- apply: [G_I G_J] <- [G_I G_J] Q, streamed straight back to global ----
+        const int cgp = tid & 3;
+        float q[JP][4];
+#pragma unroll
+        for (int k = 0; k < JP; ++k)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) q[k][x] = (float)Qm[k * 17 + 4 * cgp + x];
+        float* dst = (cgp < 2) ? (GI + cgp * 4) : (GJ + (cgp - 2) * 4);
+        for (int r = tid >> 2; r < p; r += J_THREADS / 4) {
+            const float4 v0 = *(const float4*)(P + (size_t)r * JP);
+            const float4 v1 = *(const float4*)(P + (size_t)r * JP + 4);
+            const float4 v2 = *(const float4*)(P + (size_t)r * JP + 8);
+            const float4 v3 = *(const float4*)(P + (size_t)r * JP + 12);
+            const float pv[JP] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w,
+                                  v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < JP; ++k)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) o[x] = fmaf(pv[k], q[k][x], o[x]);
+            __stcg((float4*)(dst + (size_t)r * JB), make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+    __syncthreads();
+}
+
+// The whole solve in ONE cooperative launch.  Per sweep:
+//   A. screen: C = G^T G (fp32, 64 x 64 tiles over all CTAs);
+//   B. per panel pair the largest relative off-diagonal of its 8 x 8 block of C (the pair (2k, 2k+1) also carries the
+//      within-panel blocks of its two panels); global maximum = the convergence measure; pairs above 0.2 tol are ACTIVE;
+//   C. rotations over the active pairs only.  L_A of this pipeline is nearly diagonal with couplings between spatially
+//      close samples only (at 4K / p = 1000: 600 of 7875 panel pairs, all with |I - J| <= 8), so the pairs are visited
+//      by distance class: step (d, par) = all pairs (I, I + d) with floor(I / d) of parity par -- mutually disjoint,
+//      and steps without an active pair cost nothing (no barrier).  When more than half of the pairs are active
+//      (photometric affinity) the round-robin tournament is used instead: (panels - 1) steps of panels / 2 pairs.
 __global__ void __launch_bounds__(J_THREADS, 1)
-k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, unsigned* __restrict__ sweep_off,
-         int* __restrict__ sweeps_done)
+k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, float* __restrict__ C /* [cp][cp], cp = nb * 8 */,
+         float* __restrict__ pair_rel /* [nb][nb] */, int* __restrict__ step_cnt /* [max_sweeps][2 * nb] */,
+         unsigned* __restrict__ sweep_off, int* __restrict__ sweeps_done)
 {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) float jsm[];
@@ -70,161 +229,142 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, unsign
     __shared__ float s_off;
     __shared__ unsigned s_cta_off;
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int bi = tid >> 4, bj = tid & 15;  // this thread's element of the 16 x 16 block
-    const int npairs = nb >> 1;
+    const int tid = threadIdx.x;
+    const int cp = nb * JB;
+    const int T = (cp + 63) >> 6;            // 64-column tiles of C
+    const int ntile = T * (T + 1) / 2;
+    const int npairs_all = nb * (nb - 1) / 2;
 
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
-        for (int step = 0; step < nb - 1; ++step) {
-            for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-                int I, J;
-                tournament(step, pair, nb, I, J);
-                float* GI = G + (size_t)I * p * JB;
-                float* GJ = G + (size_t)J * p * JB;
-                // ---- load the panel pair (L2 loads: the data was written by other SMs) ----
-                for (int idx = tid; idx < 2 * p; idx += J_THREADS) {
-                    const int r = idx >> 1, h = idx & 1;
-                    float4 a = __ldcg((const float4*)(GI + (size_t)r * JB + h * 4));
-                    float4 b = __ldcg((const float4*)(GJ + (size_t)r * JB + h * 4));
-                    *(float4*)(P + (size_t)r * JP + h * 4) = a;
-                    *(float4*)(P + (size_t)r * JP + JB + h * 4) = b;
-                }
-                if (tid == 0) s_cta_off = 0u;
-                __syncthreads();
-                // ---- Gram block: 16 row groups x (4 x 4 register tiles) ----
-                {
-                    const int rg = tid >> 4, ti = (tid >> 2) & 3, tj = tid & 3;
-                    float acc[4][4];
+        int* cnt = step_cnt + (size_t)sweep * 2 * nb;   // [0] = active pairs in total, [2 d + par] = per step
+        // ---- A. C = G^T G, upper tiles ----
+        {
+            float* As = jsm;                 // [32][68]
+            float* Bs = jsm + 32 * 68;       // [32][68]
+            const int tx = tid & 15, ty = tid >> 4;
+            for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+                int ti = 0, rem = tile;
+                while (rem >= T - ti) { rem -= T - ti; ++ti; }
+                const int tj = ti + rem;
+                float acc[4][4];
 #pragma unroll
-                    for (int x = 0; x < 4; ++x)
+                for (int x = 0; x < 4; ++x)
 #pragma unroll
-                        for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-                    for (int r = rg; r < p; r += 16) {
-                        const float4 a = *(const float4*)(P + (size_t)r * JP + 4 * ti);
-                        const float4 b = *(const float4*)(P + (size_t)r * JP + 4 * tj);
+                    for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+                const int lp = tid >> 5, lr = tid & 31;          // panel within the tile, row within the chunk
+                const int pa = ti * 8 + lp, pb = tj * 8 + lp;
+                for (int r0 = 0; r0 < p; r0 += 32) {
+                    const int r = r0 + lr;
+                    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+                    if (r < p) {
+                        if (pa < nb) {
+                            a0 = __ldcg((const float4*)(G + ((size_t)pa * p + r) * JB));
+                            a1 = __ldcg((const float4*)(G + ((size_t)pa * p + r) * JB + 4));
+                        }
+                        if (pb < nb) {
+                            b0 = __ldcg((const float4*)(G + ((size_t)pb * p + r) * JB));
+                            b1 = __ldcg((const float4*)(G + ((size_t)pb * p + r) * JB + 4));
+                        }
+                    }
+                    __syncthreads();
+                    *(float4*)&As[lr * 68 + lp * 8] = a0;
+                    *(float4*)&As[lr * 68 + lp * 8 + 4] = a1;
+                    *(float4*)&Bs[lr * 68 + lp * 8] = b0;
+                    *(float4*)&Bs[lr * 68 + lp * 8 + 4] = b1;
+                    __syncthreads();
+#pragma unroll 8
+                    for (int k = 0; k < 32; ++k) {
+                        const float4 a = *(const float4*)&As[k * 68 + ty * 4];
+                        const float4 b = *(const float4*)&Bs[k * 68 + tx * 4];
                         const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
 #pragma unroll
                             for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
                     }
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) red[rg * 256 + (4 * ti + x) * 16 + 4 * tj + y] = acc[x][y];
                 }
-                __syncthreads();
-                {
-                    double s = 0.0;
 #pragma unroll
-                    for (int rg = 0; rg < 16; ++rg) s += (double)red[rg * 256 + tid];
-                    Bm[bi * 17 + bj] = s;
-                    Qm[bi * 17 + bj] = (bi == bj) ? 1.0 : 0.0;
-                }
-                __syncthreads();
-                // ---- how far from orthogonal is this pair (drives the sweep loop) ----
-                {
-                    float rel = 0.f;
-                    if (bi < bj) {
-                        const double dii = Bm[bi * 17 + bi], djj = Bm[bj * 17 + bj];
-                        if (dii > 0.0 && djj > 0.0) rel = (float)(fabs(Bm[bi * 17 + bj]) / sqrt(dii * djj));
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) rel = fmaxf(rel, __shfl_xor_sync(0xffffffffu, rel, o));
-                    if (lane == 0) atomicMax(&s_cta_off, __float_as_uint(rel));
-                }
-                __syncthreads();
-                const float pair_off = __uint_as_float(s_cta_off);
-                if (tid == 0) atomicMax(&sweep_off[sweep], s_cta_off);
-                // ---- diagonalise the 16 x 16 block: cyclic two-sided Jacobi, Q accumulates the rotations ----
-                if (pair_off > 0.25f * tol) {
-                    if (tid == 0) s_off = 0.f;
-                    __syncthreads();
-                    for (int isw = 0; isw < J_INNER_MAX; ++isw) {
-                        for (int st = 0; st < JP - 1; ++st) {
-                            if (tid < JB) {
-                                int a, b;
-                                tournament(st, tid, JP, a, b);
-                                const double app = Bm[a * 17 + a], aqq = Bm[b * 17 + b], apq = Bm[a * 17 + b];
-                                double c = 1.0, s = 0.0;
-                                if (app > 0.0 && aqq > 0.0) {
-                                    const double reld = fabs(apq) / sqrt(app * aqq);
-                                    if (reld > 1e-13) {
-                                        const double tau = (aqq - app) / (2.0 * apq);
-                                        const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                                        c = 1.0 / sqrt(1.0 + t * t);
-                                        s = t * c;
-                                    }
-                                    const float rel = (float)reld;
-                                    if (rel > s_off) atomicMax((unsigned*)&s_off, __float_as_uint(rel));
-                                }
-                                cs[2 * tid] = c;
-                                cs[2 * tid + 1] = s;
-                                pq[2 * tid] = a;
-                                pq[2 * tid + 1] = b;
-                                role[a] = tid << 1;
-                                role[b] = (tid << 1) | 1;
-                            }
-                            __syncthreads();
-                            double nb_, nq_;
-                            {
-                                const int ri = role[bi], rj = role[bj];
-                                const int ki = ri >> 1, kj = rj >> 1;
-                                const double ci = cs[2 * ki], si = cs[2 * ki + 1], cj = cs[2 * kj], sj = cs[2 * kj + 1];
-                                const int ip = pq[2 * ki], iq = pq[2 * ki + 1], jp = pq[2 * kj], jq = pq[2 * kj + 1];
-                                double x_ip, x_iq;  // (B J)[ip][bj], (B J)[iq][bj]
-                                if ((rj & 1) == 0) {
-                                    x_ip = cj * Bm[ip * 17 + jp] - sj * Bm[ip * 17 + jq];
-                                    x_iq = cj * Bm[iq * 17 + jp] - sj * Bm[iq * 17 + jq];
-                                    nq_ = cj * Qm[bi * 17 + jp] - sj * Qm[bi * 17 + jq];
-                                } else {
-                                    x_ip = sj * Bm[ip * 17 + jp] + cj * Bm[ip * 17 + jq];
-                                    x_iq = sj * Bm[iq * 17 + jp] + cj * Bm[iq * 17 + jq];
-                                    nq_ = sj * Qm[bi * 17 + jp] + cj * Qm[bi * 17 + jq];
-                                }
-                                nb_ = ((ri & 1) == 0) ? (ci * x_ip - si * x_iq) : (si * x_ip + ci * x_iq);
-                            }
-                            __syncthreads();
-                            Bm[bi * 17 + bj] = nb_;
-                            Qm[bi * 17 + bj] = nq_;
-                            __syncthreads();
-                        }
-                        const float inner_off = s_off;
-                        __syncthreads();
-                        if (tid == 0) s_off = 0.f;
-                        __syncthreads();
-                        if (inner_off <= 0.1f * tol) break;
-                    }
-                    // ---- apply: [G_I G_J] <- [G_I G_J] Q, streamed straight back to global ----
-                    const int cgp = tid & 3;
-                    float q[JP][4];
-#pragma unroll
-                    for (int k = 0; k < JP; ++k)
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) q[k][x] = (float)Qm[k * 17 + 4 * cgp + x];
-                    float* dst = (cgp < 2) ? (GI + cgp * 4) : (GJ + (cgp - 2) * 4);
-                    for (int r = tid >> 2; r < p; r += J_THREADS / 4) {
-                        const float4 v0 = *(const float4*)(P + (size_t)r * JP);
-                        const float4 v1 = *(const float4*)(P + (size_t)r * JP + 4);
-                        const float4 v2 = *(const float4*)(P + (size_t)r * JP + 8);
-                        const float4 v3 = *(const float4*)(P + (size_t)r * JP + 12);
-                        const float pv[JP] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w,
-                                              v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-                        float o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int k = 0; k < JP; ++k)
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) o[x] = fmaf(pv[k], q[k][x], o[x]);
-                        __stcg((float4*)(dst + (size_t)r * JB), make_float4(o[0], o[1], o[2], o[3]));
-                    }
+                for (int x = 0; x < 4; ++x) {
+                    const int row = ti * 64 + ty * 4 + x, col = tj * 64 + tx * 4;
+                    if (row < cp && col < cp) __stcg((float4*)(C + (size_t)row * cp + col), make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]));
                 }
                 __syncthreads();
             }
-            grid.sync();
         }
+        grid.sync();
+        // ---- B. panel-pair screen ----
+        {
+            float cta_max = 0.f;
+            for (int idx = blockIdx.x * J_THREADS + tid; idx < nb * nb; idx += gridDim.x * J_THREADS) {
+                const int I = idx / nb, J = idx - I * nb;
+                if (J <= I) continue;
+                float rel = 0.f;
+                float di[JB], dj[JB];
+#pragma unroll
+                for (int a = 0; a < JB; ++a) {
+                    di[a] = __ldcg(C + (size_t)(I * JB + a) * cp + I * JB + a);
+                    dj[a] = __ldcg(C + (size_t)(J * JB + a) * cp + J * JB + a);
+                }
+#pragma unroll
+                for (int a = 0; a < JB; ++a)
+#pragma unroll
+                    for (int b = 0; b < JB; ++b) {
+                        const float c = fabsf(__ldcg(C + (size_t)(I * JB + a) * cp + J * JB + b));
+                        const float d = di[a] * dj[b];
+                        if (d > 0.f) rel = fmaxf(rel, c * rsqrtf(d));
+                    }
+                if (J == (I ^ 1)) {  // this pair also answers for the blocks inside its two panels
+#pragma unroll
+                    for (int a = 0; a < JB; ++a)
+#pragma unroll
+                        for (int b = a + 1; b < JB; ++b) {
+                            const float c1 = fabsf(__ldcg(C + (size_t)(I * JB + a) * cp + I * JB + b)), d1 = di[a] * di[b];
+                            const float c2 = fabsf(__ldcg(C + (size_t)(J * JB + a) * cp + J * JB + b)), d2 = dj[a] * dj[b];
+                            if (d1 > 0.f) rel = fmaxf(rel, c1 * rsqrtf(d1));
+                            if (d2 > 0.f) rel = fmaxf(rel, c2 * rsqrtf(d2));
+                        }
+                }
+                pair_rel[idx] = rel;
+                cta_max = fmaxf(cta_max, rel);
+                if (rel > 0.2f * tol) {
+                    const int d = J - I, par = (I / d) & 1;
+                    atomicAdd(&cnt[2 * d + par], 1);
+                    atomicAdd(&cnt[0], 1);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cta_max = fmaxf(cta_max, __shfl_xor_sync(0xffffffffu, cta_max, o));
+            if ((tid & 31) == 0 && cta_max > 0.f) atomicMax(&sweep_off[sweep], __float_as_uint(cta_max));
+        }
+        grid.sync();
         const float off = __uint_as_float(__ldcg(&sweep_off[sweep]));
-        if (off <= tol) { ++sweep; break; }
+        if (off <= tol) break;
+        // ---- C. rotations ----
+        const int active = __ldcg(&cnt[0]);
+        if (2 * active > npairs_all) {
+            for (int step = 0; step < nb - 1; ++step) {
+                for (int pair = blockIdx.x; pair < (nb >> 1); pair += gridDim.x) {
+                    int I, J;
+                    tournament(step, pair, nb, I, J);
+                    if (__ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
+                        jacobi_pair(G, p, I, J, tol, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
+                }
+                grid.sync();
+            }
+        } else {
+            for (int d = 1; d < nb; ++d)
+                for (int par = 0; par < 2; ++par) {
+                    if (__ldcg(&cnt[2 * d + par]) == 0) continue;   // uniform over the grid: no barrier needed
+                    const int ncand = ((nb + 2 * d - 1) / (2 * d)) * d;
+                    for (int c = blockIdx.x; c < ncand; c += gridDim.x) {
+                        const int I = (c / d) * 2 * d + par * d + (c % d), J = I + d;
+                        if (J < nb && __ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
+                            jacobi_pair(G, p, I, J, tol, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
+                    }
+                    grid.sync();
+                }
+        }
     }
     if (blockIdx.x == 0 && tid == 0) *sweeps_done = sweep;
 }
@@ -376,6 +516,7 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
     }
     GL_REQUIRE(p < (1 << 24), "eigensolve: p too large");
     gl_buf *G = nullptr, *lam = nullptr, *order = nullptr, *ctl = nullptr, *ray = nullptr, *part = nullptr;
+    gl_buf *Cg = nullptr, *prel = nullptr, *scnt = nullptr;
     const int cols_pad = nb * JB;
     const int row_tiles = (int)ceil_div(p, 64);
     gl_mat *U = nullptr, *mu = nullptr, *mui = nullptr;
@@ -389,6 +530,10 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)row_tiles * (cols_pad + 64), &part)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(unsigned) * (size_t)(max_sweeps + 4), &ctl)) != GL_OK) break;
         GL_CUDA_CHECK(cudaMemsetAsync(ctl->ptr, 0, sizeof(unsigned) * (size_t)(max_sweeps + 4), ctx->stream));
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)cols_pad * cols_pad, &Cg)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)nb * nb, &prel)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(int) * (size_t)max_sweeps * 2 * nb, &scnt)) != GL_OK) break;
+        GL_CUDA_CHECK(cudaMemsetAsync(scnt->ptr, 0, sizeof(int) * (size_t)max_sweeps * 2 * nb, ctx->stream));
         const int64_t total = (int64_t)nb * p * JB;
         k_jacobi_init<<<(unsigned)ceil_div(total, 256), 256, 0, ctx->stream>>>((const double*)L_A->buf->ptr, p, nb,
                                                                                (float*)G->ptr);
@@ -398,14 +543,19 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         int per_sm = 0;
         GL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi, J_THREADS, smem));
         GL_REQUIRE(per_sm >= 1, "eigensolve: kernel does not fit on an SM");
-        int grid = nb / 2;
+        const int ctiles = (int)ceil_div(cols_pad, 64);
+        int grid = std::max(nb / 2, ctiles * (ctiles + 1) / 2);   // rotation pairs per step / tiles of the Gram screen
+        if (grid > ctx->sm_count) grid = ctx->sm_count;
         if (grid > per_sm * ctx->sm_count) grid = per_sm * ctx->sm_count;
         float* Gp = (float*)G->ptr;
         int p_ = p, nb_ = nb, ms = max_sweeps;
         float tol = ctx->jacobi_tol;
-        unsigned* off = (unsigned*)ctl->ptr;
-        int* done = (int*)((unsigned*)ctl->ptr + max_sweeps);
-        void* args[] = {&Gp, &p_, &nb_, &ms, &tol, &off, &done};
+        unsigned* off = (unsigned*)ctl->ptr;                       // [max_sweeps + 1] screen results, then the sweep count
+        int* done = (int*)((unsigned*)ctl->ptr + max_sweeps + 1);
+        float* Cp = (float*)Cg->ptr;
+        float* prp = (float*)prel->ptr;
+        int* scp = (int*)scnt->ptr;
+        void* args[] = {&Gp, &p_, &nb_, &ms, &tol, &Cp, &prp, &scp, &off, &done};
         {
             StageTimer kt(ctx, GL_T_K_JACOBI);
             GL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));
@@ -457,11 +607,12 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
                                       ctx->stream));
         GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         const unsigned* h = (const unsigned*)ctx->pinned;
-        const int sweeps = (int)h[max_sweeps];
-        float last;
-        memcpy(&last, &h[sweeps > 0 ? sweeps - 1 : 0], sizeof(float));
+        const int sweeps = (int)h[max_sweeps + 1];   // rotation sweeps done; screen number `sweeps` ended the loop
+        float last = 1.f;
+        if (sweeps < max_sweeps) memcpy(&last, &h[sweeps], sizeof(float));
+        else memcpy(&last, &h[max_sweeps - 1], sizeof(float));
         if (ctx->verbose) fprintf(stderr, "[libglcuda] jacobi: p=%d panels=%d grid=%d sweeps=%d last off=%.3g\n", p, nb, grid, sweeps, last);
-        if (last > ctx->jacobi_tol) {
+        if (sweeps >= max_sweeps || last > ctx->jacobi_tol) {
             gl_set_error("eigensolve: not converged after %d sweeps (off-orthogonality %.3g > %.3g)", sweeps, last, ctx->jacobi_tol);
             rc = GL_ERR_NOTCONVERGED;
             break;
@@ -471,6 +622,9 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
     if (lam) gl_buf_release(lam);
     if (order) gl_buf_release(order);
     if (ctl) gl_buf_release(ctl);
+    if (Cg) gl_buf_release(Cg);
+    if (prel) gl_buf_release(prel);
+    if (scnt) gl_buf_release(scnt);
     if (ray) gl_buf_release(ray);
     if (part) gl_buf_release(part);
     if (rc != GL_OK) {
