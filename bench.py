@@ -232,6 +232,20 @@ def main():
         for k in pair:
             pair[k].append(s_[k])
     ctx.set_option("projection", "sums")
+    # the extrapolation GEMM with every K_B block stored and multiplied (option kb_cutoff=0): the tensor-pipe number
+    dense_gemm_ms = None
+    try:
+        ctx.set_option("kb_cutoff", 0)
+        dg = []
+        for _ in range(3):
+            ctx.run_resident(prm)
+            dg.append(ctx.stage_ms()["k_gemm"])
+        dense_gemm_ms = float(np.median(dg[1:]))
+    except gl.GLError as e:       # dense K_B may not fit (C5 on few GPUs)
+        print(f"dense GEMM leg skipped: {e}", file=sys.stderr)
+    finally:
+        ctx.set_option("kb_cutoff", 1)
+        ctx.run_resident(prm)
     clk = clocks.stop() if rank == 0 else None
 
     # ---------------- end-to-end leg (e2e): pinned host image -> pinned host z ----------------
@@ -277,6 +291,30 @@ def main():
     apply_gbs = b_apply / (med["k_filter_apply"] * 1e-3) / 1e9
     aff_ext_tf = (f_aff + f_ext) / ((med["k_affinity_b"] + med["k_gemm"]) * 1e-3) / 1e12
 
+    # ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
+    NCU_TRAFFIC = {("c4", 1, "cutoff"): (20.40e9, "profiles/r01_ncu_full_c4_v3.txt"),
+                   ("c4", 1, "dense"): (33.9e9, "profiles/r01_ncu_full_c4.txt")}
+    kept = stored_blocks / max(1, dense_blocks)
+    if kept < 0.5:
+        # with the spatial cutoff the GEMM's K loop is short and the kernel is bound by the bytes it moves: the stored K_B
+        # blocks read once and Phi written once
+        tr = NCU_TRAFFIC.get((args.workload, world, "cutoff"))
+        roof = dict(kernel="k_gemm_tcgen05 (Nystroem extrapolation over the stored K_B blocks)", bound="hbm", achieved=gemm_gbs,
+                    peak=peaks["hbm"], unit="GB/s", frac=gemm_gbs / peaks["hbm"], traffic=tr[0] if tr else None,
+                    traffic_source=tr[1] if tr else None, peak_source=peaks["source"] + " copy bandwidth", ms=med["k_gemm"],
+                    bytes=gemm_bytes, note="83 %% of these bytes are WRITES (Phi); a pure 17 GB write (torch fill) runs at 3.94 TB/s on "
+                    "this part, the kernel writes at %.2f TB/s" % (band_px * m_pad * 2.0 / (med["k_gemm"] * 1e-3) / 1e12))
+    else:
+        tr = NCU_TRAFFIC.get((args.workload, world, "dense"))
+        roof = dict(kernel="k_gemm_tcgen05 (Nystroem extrapolation)", bound="tensor", achieved=gemm_tf, peak=peaks["tf_sustained"],
+                    unit="TFLOP/s", frac=gemm_tf / peaks["tf_sustained"], traffic=tr[0] if tr else None,
+                    traffic_source=tr[1] if tr else None, peak_source=peaks["source"] + " bf16 sustained", ms=med["k_gemm"], flop=f_ext)
+    roof_dense = None
+    if dense_gemm_ms:
+        tfd = f_ext / (dense_gemm_ms * 1e-3) / 1e12
+        roof_dense = dict(kernel="k_gemm_tcgen05 with option kb_cutoff=0 (all K_B blocks stored and multiplied)", bound="tensor",
+                          achieved=tfd, peak=peaks["tf_sustained"], unit="TFLOP/s", frac=tfd / peaks["tf_sustained"],
+                          peak_source=peaks["source"] + " bf16 sustained", ms=dense_gemm_ms, flop=f_ext)
     out = dict(metric="Mpixels/s filtered end-to-end", value=value, unit="Mpixel/s", n_gpus=world, steps=args.steps,
                warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
                dtype="f16 operands and Phi / f32 accumulate (K_A, D, L_A, eigenvalues, projection f64; eigenvectors f32)", data="synthetic",
@@ -288,9 +326,8 @@ def main():
                         ms_per_step=t_e2e / args.steps),
                gpu_launches=int(launches),
                clocks=clk,
-               roofline=dict(kernel="k_gemm_tcgen05 (Nystroem extrapolation)", bound="tensor", achieved=gemm_tf,
-                             peak=peaks["tf_sustained"], unit="TFLOP/s", frac=gemm_tf / peaks["tf_sustained"], traffic=None,
-                             peak_source=peaks["source"] + " bf16 sustained", ms=med["k_gemm"], flop=f_ext),
+               roofline=roof,
+               roofline_gemm_dense=roof_dense,
                roofline_filter=dict(kernel="k_filter_project + k_filter_apply (stand-alone GEMV pair, option projection=recompute)",
                                     bound="hbm", achieved=filt_gbs, peak=peaks["hbm"], unit="GB/s", frac=filt_gbs / peaks["hbm"],
                                     ms=pair_ms["k_filter_project"] + pair_ms["k_filter_apply"], ms_project=pair_ms["k_filter_project"],

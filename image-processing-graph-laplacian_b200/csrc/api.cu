@@ -118,6 +118,12 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         if (!strcmp(value, "warp")) ctx->filter_apply_impl = 0;
         else if (!strcmp(value, "generic")) ctx->filter_apply_impl = 1;
         else GL_REQUIRE(false, "option filter_apply: want warp|generic, got %s", value);
+    } else if (!strcmp(key, "gemm_stages")) {
+        ctx->gemm_stages = atoi(value);
+        GL_REQUIRE(ctx->gemm_stages == 0 || ctx->gemm_stages == 3 || ctx->gemm_stages == 4, "option gemm_stages: want 0|3|4");
+    } else if (!strcmp(key, "gemm_prefetch")) {
+        ctx->gemm_prefetch = atoi(value);
+        GL_REQUIRE(ctx->gemm_prefetch >= 0 && ctx->gemm_prefetch <= 16, "option gemm_prefetch: want 0..16");
     } else if (!strcmp(key, "kb_cutoff")) {
         ctx->kb_cutoff = atoi(value) != 0;
     } else if (!strcmp(key, "eig_largest")) {

@@ -151,6 +151,8 @@ struct gl_ctx {
     // options
     int gemm_impl = 0;        // 0 = tcgen05 (default), 1 = simple CUDA-core checker kernel
     int gemm_cta_group = 1;   // 1 or 2
+    int gemm_stages = 0;      // 0 = automatic, 3 | 4 = force that ring depth (tuning)
+    int gemm_prefetch = 2;    // blocked A: L2-prefetch the A blocks of the tile this many iterations ahead (0 = off)
     int eig_largest = 0;      // 1: keep the m LARGEST eigenpairs (descending) instead of the smallest (ascending)
     int jacobi_max_sweeps = 40;
     float jacobi_tol = 2e-6f;

@@ -262,14 +262,20 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;       // 64 fp16 = 128 bytes = one SWIZZLE_128B row
 constexpr int MAX_BLOCK_N = 256;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int UMMA_K = 16;
-constexpr int THREADS = 256;
+constexpr int MAX_THREADS = 384;   // warps 0-3: producer, MMA issuer, TMEM allocator, idle; then 4 or 8 epilogue warps
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int C_SLAB_BYTES = 32 * 128;                     // 32 rows x 64 bf16
-constexpr int C_BYTES = 4 * 2 * C_SLAB_BYTES;              // 4 epilogue warps x 2 buffers
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + C_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
+// two shapes of the shared-memory budget (227 KB): a deep operand ring for long K loops (dense A, the epilogue has
+// slack: one store slab per epilogue warp), or a shorter ring with double-buffered store slabs for the short K loops of
+// the blocked K_B, where the epilogue is the critical path
+template <int STAGES, int CBUFS, int EPI_WARPS>
+constexpr int smem_bytes()
+{
+    return STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_WARPS * CBUFS * C_SLAB_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -317,6 +323,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+// L2 prefetch of a tile (no shared-memory destination): used to pull the A blocks of tiles a few iterations ahead out
+// of HBM early, which buys prefetch depth the shared-memory ring cannot hold
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
 {
@@ -400,19 +412,22 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t w)
 }
 
 // One persistent CTA per SM.  warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator,
-// warps 4-7: epilogue (warp w drains TMEM lanes 32*(w%4) .. +31).
-__global__ void __launch_bounds__(THREADS, 1)
+// warps 4..: epilogue, EPI_WARPS / 4 per TMEM lane quarter (warp w drains lanes 32*(w%4) .. +31 and its share of the
+// accumulator's columns).
+template <int STAGES, int CBUFS, int EPI_WARPS>
+__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, int m_tiles, int n_tiles, int k_blocks, int n_total, int block_n,
                int ab_bf16, const float* __restrict__ scales, const __half* __restrict__ addend, int64_t m_rows,
-               const int4* __restrict__ a_tab /* K_B tile table, or null for a dense A */, int* __restrict__ err)
+               const int4* __restrict__ a_tab /* K_B tile table, or null for a dense A */, int prefetch_tiles,
+               int* __restrict__ err)
 {
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + STAGES * A_STAGE_BYTES;
     uint8_t* smem_c = smem_b + STAGES * B_STAGE_BYTES;
-    uint64_t* bars = (uint64_t*)(smem_c + C_BYTES);
+    uint64_t* bars = (uint64_t*)(smem_c + EPI_WARPS * CBUFS * C_SLAB_BYTES);
     // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then the TMEM base address
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
@@ -433,7 +448,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 4);  // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8 * a, EPI_WARPS);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -465,6 +480,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     a_row = tl.z * 512 + (mt & 3) * BLOCK_M;
                     a_row_step = 512;
                     a_col_step = 0;
+                }
+                if (a_tab && prefetch_tiles > 0) {
+                    const int ft = tile + prefetch_tiles * (int)gridDim.x;
+                    if (ft < total_tiles) {
+                        const int fmt = ft / n_tiles;
+                        const int4 fl = a_tab[fmt >> 2];
+                        for (int kb = 0; kb < fl.y; ++kb) tma_prefetch_2d(&map_a, 0, fl.z * 512 + (fmt & 3) * BLOCK_M + kb * 512);
+                    }
                 }
                 for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1, err, 1);
@@ -511,29 +534,37 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ===== epilogue =====
-        const int wq = warp & 3;  // TMEM lane quarter
-        uint8_t* slab0 = smem_c + wq * 2 * C_SLAB_BYTES;
+        const int wq = warp & 3;          // TMEM lane quarter
+        const int ch = (warp - 4) >> 2;   // which share of the accumulator's columns
+        constexpr int SHARES = EPI_WARPS / 4;
+        uint8_t* slab0 = smem_c + (warp - 4) * CBUFS * C_SLAB_BYTES;
         const float sc = scales[1];
         int it = 0;
         int buf = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile / n_tiles, nt = tile % n_tiles;
             const int n_size = min(block_n, n_total - nt * block_n);
+            // n_size is a multiple of 128, or 64 (then only share 0 works)
+            const int c_lo = ch * (n_size / SHARES), c_hi = c_lo + n_size / SHARES;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
             mbar_wait(bar_tfull + 8 * acc, acc_phase, err, 4);
             tcgen05_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * MAX_BLOCK_N);
-            for (int c0 = 0; c0 < n_size; c0 += 64) {
+            const bool split = n_size >= 64 * SHARES;
+            const int c_end = split ? c_hi : (ch == 0 ? n_size : 0);
+            for (int c0 = (split ? c_lo : 0); c0 < c_end; c0 += 64) {
                 uint8_t* slab = slab0 + buf * C_SLAB_BYTES;
+                // both halves of the 64-column group in flight before the wait
+                uint32_t v[2][32];
+                tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v[0]);
+                tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v[1]);
                 // the TMA store that last read this slab must be done with it
-                if (lane == 0) tma_store_wait_read<1>();
+                if (lane == 0) tma_store_wait_read<CBUFS - 1>();
+                tmem_ld_wait();
                 __syncwarp();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32 * h), v);
-                    tmem_ld_wait();
                     uint32_t pk[16];
                     if (addend != nullptr) {
                         // D = addend + scale * acc (orthonormalise.cu: Phi + Phi E); one 64-byte run of this thread's row
@@ -548,13 +579,13 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (int j = 0; j < 4; ++j) {
                                 const int i = 4 * i4 + j;
                                 const float2 ad = unpack_h2(aw[j]);
-                                pk[i] = pack_h2(fmaf(__uint_as_float(v[2 * i]), sc, ad.x), fmaf(__uint_as_float(v[2 * i + 1]), sc, ad.y));
+                                pk[i] = pack_h2(fmaf(__uint_as_float(v[h][2 * i]), sc, ad.x), fmaf(__uint_as_float(v[h][2 * i + 1]), sc, ad.y));
                             }
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            pk[i] = pack_h2(__uint_as_float(v[2 * i]) * sc, __uint_as_float(v[2 * i + 1]) * sc);
+                            pk[i] = pack_h2(__uint_as_float(v[h][2 * i]) * sc, __uint_as_float(v[h][2 * i + 1]) * sc);
                     }
                     // row `lane` of the slab, 16-byte chunks 4h .. 4h+3, XOR-swizzled like SWIZZLE_128B
 #pragma unroll
@@ -569,7 +600,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tma_store_2d(&map_d, smem_u32(slab), nt * block_n + c0, mt * BLOCK_M + wq * 32);
                     tma_store_commit();
                 }
-                buf ^= 1;
+                if (CBUFS > 1) buf ^= 1;
             }
             // all tcgen05.ld of this accumulator have completed (wait::ld above): hand it back to the MMA warp
             tcgen05_fence_before();
@@ -671,13 +702,25 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     gl_buf* err = nullptr;
     GL_CHECK(gl_alloc(ctx, sizeof(int) * 4, &err));
     cudaMemsetAsync(err->ptr, 0, sizeof(int) * 4, ctx->stream);
-    GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     int grid = ctx->sm_count;
     if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
+    // short K loops (blocked K_B with few blocks per tile): the epilogue is the critical path
+    const bool short_k = a_tab != nullptr && a_total_blocks * 4 < (int64_t)m_tiles * 8;   // fewer than 8 K blocks per M tile on average
     StageTimer kt(ctx, GL_T_K_GEMM);
-    tc::k_gemm_tcgen05<<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad,
-                                                                           block_n, ab_bf16, scales, (const __half*)addend,
-                                                                           rows, a_tab, (int*)err->ptr);
+    const int pf = short_k ? ctx->gemm_prefetch : 0;   // with long K loops the ring already covers the latency; prefetch only adds L2 churn
+    if (ctx->gemm_stages == 3 || (ctx->gemm_stages == 0 && short_k)) {
+        constexpr int SM = tc::smem_bytes<3, 2, 8>();
+        GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<3, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+        tc::k_gemm_tcgen05<3, 2, 8><<<grid, 128 + 32 * 8, SM, ctx->stream>>>(map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad, block_n,
+                                                                         ab_bf16, scales, (const __half*)addend, rows, a_tab, pf,
+                                                                         (int*)err->ptr);
+    } else {
+        constexpr int SM = tc::smem_bytes<4, 2, 4>();
+        GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<4, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+        tc::k_gemm_tcgen05<4, 2, 4><<<grid, 128 + 32 * 4, SM, ctx->stream>>>(map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad, block_n,
+                                                                         ab_bf16, scales, (const __half*)addend, rows, a_tab, pf,
+                                                                         (int*)err->ptr);
+    }
     gl_buf_release(err);
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;
