@@ -215,39 +215,13 @@ def main():
     stage = ctx.stage_ms()          # last step's per-stage / per-kernel CUDA-event times
     # a second pass that reads the per-stage timers every step (the read synchronises, so it is kept out of the
     # headline region)
-    kern = ("k_gemm", "k_affinity_b", "k_filter_project", "k_filter_apply", "k_jacobi")
+    kern = ("k_gemm", "k_affinity_b", "k_jacobi")
     per_kernel = {k: [] for k in kern}
     for _ in range(args.steps):
         ctx.run_resident(prm)
         s_ = ctx.stage_ms()
         for k in kern:
             per_kernel[k].append(s_[k])
-    # the filter as the stand-alone GEMV pair (c = Phi^T y recomputed by a pass over Phi instead of taken from the
-    # affinity sums): the numbers behind roofline_filter
-    ctx.set_option("projection", "recompute")
-    pair = {"k_filter_project": [], "k_filter_apply": []}
-    for _ in range(max(2, args.steps)):
-        ctx.run_resident(prm)
-        s_ = ctx.stage_ms()
-        for k in pair:
-            pair[k].append(s_[k])
-    ctx.set_option("projection", "sums")
-    # the extrapolation GEMM with every K_B block stored and multiplied (option kb_cutoff=0): the tensor-pipe number
-    dense_gemm_ms = None
-    try:
-        ctx.set_option("kb_cutoff", 0)
-        dg = []
-        for _ in range(3):
-            ctx.run_resident(prm)
-            dg.append(ctx.stage_ms()["k_gemm"])
-        dense_gemm_ms = float(np.median(dg[1:]))
-    except gl.GLError as e:       # dense K_B may not fit (C5 on few GPUs)
-        print(f"dense GEMM leg skipped: {e}", file=sys.stderr)
-    finally:
-        ctx.set_option("kb_cutoff", 1)
-        ctx.run_resident(prm)
-    clk = clocks.stop() if rank == 0 else None
-
     # ---------------- end-to-end leg (e2e): pinned host image -> pinned host z ----------------
     img_pin = gl.PinnedArray((height, width) if channels == 1 else (height, width, channels), np.uint8)
     z_pin = gl.PinnedArray((height, width) if channels == 1 else (height, width, channels), np.float32)
@@ -261,6 +235,38 @@ def main():
     ctx.mark(3)
     barrier()
     t_e2e = ctx.elapsed_ms(2, 3)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---------------- side legs (diagnostics, outside the headline regions) ----------------
+    def leg(n, keys):
+        acc = {k: [] for k in keys}
+        for _ in range(n):
+            ctx.run_resident(prm)
+            s__ = ctx.stage_ms()
+            for k in keys:
+                acc[k].append(s__[k])
+        return {k: float(np.median(v[1:] if len(v) > 1 else v)) for k, v in acc.items()}
+    # (1) the stages run apart, as the reference sequences them: Nystroem, then the filter reading Phi back
+    ctx.set_option("fuse_filter", 0)
+    staged = leg(3, ("nystroem", "filter", "k_gemm", "k_filter_apply", "total"))
+    # (2) the filter as the stand-alone GEMV pair (c = Phi^T y recomputed by a pass over Phi instead of taken from the
+    # affinity sums): the numbers behind roofline_filter
+    ctx.set_option("projection", "recompute")
+    pair_ms = leg(max(3, args.steps), ("k_filter_project", "k_filter_apply"))
+    ctx.set_option("projection", "sums")
+    ctx.set_option("fuse_filter", 1)
+    # (3) the extrapolation GEMM with every K_B block stored and multiplied (option kb_cutoff=0): the tensor-pipe number
+    dense_gemm_ms = None
+    try:
+        ctx.set_option("kb_cutoff", 0)
+        ctx.set_option("fuse_filter", 0)
+        dense_gemm_ms = leg(3, ("k_gemm",))["k_gemm"]
+    except gl.GLError as e:       # dense K_B may not fit (C5 on few GPUs)
+        print(f"dense GEMM leg skipped: {e}", file=sys.stderr)
+    finally:
+        ctx.set_option("kb_cutoff", 1)
+        ctx.set_option("fuse_filter", 1)
+        ctx.run_resident(prm)
     r0, r1 = ctx.band()
     band_px = (r1 - r0) * width
 
@@ -286,9 +292,8 @@ def main():
     gemm_gbs = gemm_bytes / (med["k_gemm"] * 1e-3) / 1e9 if med["k_gemm"] > 0 else 0.0
     b_proj = band_px * m_pad * 2.0 + band_px * channels
     b_apply = band_px * m_pad * 2.0 + band_px * channels * (1 + 4)
-    pair_ms = {k: float(np.median(v)) for k, v in pair.items()}
     filt_gbs = (b_proj + b_apply) / ((pair_ms["k_filter_project"] + pair_ms["k_filter_apply"]) * 1e-3) / 1e9
-    apply_gbs = b_apply / (med["k_filter_apply"] * 1e-3) / 1e9
+    apply_gbs = b_apply / (staged["k_filter_apply"] * 1e-3) / 1e9 if staged["k_filter_apply"] > 0 else 0.0
     aff_ext_tf = (f_aff + f_ext) / ((med["k_affinity_b"] + med["k_gemm"]) * 1e-3) / 1e12
 
     # ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
@@ -332,8 +337,11 @@ def main():
                                     bound="hbm", achieved=filt_gbs, peak=peaks["hbm"], unit="GB/s", frac=filt_gbs / peaks["hbm"],
                                     ms=pair_ms["k_filter_project"] + pair_ms["k_filter_apply"], ms_project=pair_ms["k_filter_project"],
                                     ms_apply=pair_ms["k_filter_apply"], bytes=b_proj + b_apply, phi_elem_bytes=2,
-                                    in_pipeline="projection taken from the affinity sums: only k_filter_apply runs, %.0f GB/s (%.2f of peak)"
-                                                % (apply_gbs, apply_gbs / peaks["hbm"])),
+                                    in_pipeline="default: the apply rides on the extrapolation GEMM's epilogue (gl_nystroem_filter) and c comes "
+                                                "from the affinity sums, so neither kernel runs; with option fuse_filter=0 only "
+                                                "k_filter_apply runs: %.3f ms = %.0f GB/s (%.2f of peak)"
+                                                % (staged["k_filter_apply"], apply_gbs, apply_gbs / peaks["hbm"])),
+               staged_ms=dict(staged, note="option fuse_filter=0: Nystroem and the filter as two passes over Phi"),
                affinity_plus_extrapolation_tflops=aff_ext_tf,
                kb_cutoff=dict(stored_blocks=stored_blocks, dense_blocks=int(dense_blocks), kept=stored_blocks / max(1, dense_blocks),
                               note="sample blocks whose K_B entries fp16 flushes to zero (|drow| > h_loc*sqrt(25 ln 2)) are neither "

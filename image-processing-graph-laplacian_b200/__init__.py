@@ -37,7 +37,7 @@ EXPORTS = [
     "gl_comm_unique_id", "gl_comm_init",
     "gl_set_image", "gl_set_image_rows", "gl_set_synthetic_image", "gl_get_image", "gl_get_band",
     "gl_sampling_uniform", "gl_sampling_random", "gl_set_samples", "gl_get_samples",
-    "gl_affinity", "gl_laplacian", "gl_eigensolve", "gl_nystroem", "gl_orthonormalise", "gl_filter",
+    "gl_affinity", "gl_laplacian", "gl_eigensolve", "gl_nystroem", "gl_nystroem_filter", "gl_orthonormalise", "gl_filter",
     "gl_diag_inverse", "gl_diag_pow", "gl_run", "gl_run_resident",
     "gl_mat_info_get", "gl_mat_retain", "gl_mat_destroy", "gl_mat_download", "gl_mat_rowsums", "gl_mat_upload",
     "gl_host_alloc", "gl_host_free",
@@ -101,6 +101,7 @@ def lib():
         L.gl_laplacian.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp)]
         L.gl_eigensolve.argtypes = [vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         L.gl_nystroem.argtypes = [vp, vp, vp, vp, C.POINTER(vp)]
+        L.gl_nystroem_filter.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_int, C.POINTER(vp), vp, vp]
         L.gl_orthonormalise.argtypes = [vp, vp, vp]
         L.gl_filter.argtypes = [vp, vp, vp, C.c_double, C.c_int, vp, vp]
         L.gl_diag_inverse.argtypes = [vp, vp, C.POINTER(vp)]
@@ -329,6 +330,15 @@ class Context:
         p = C.c_void_p()
         _check(lib().gl_nystroem(self.h, L_B.h, phi_A.h, eigvals_inv.h, C.byref(p)))
         return Mat(self, p)
+
+    def nystroem_filter(self, L_B: Mat, phi_A: Mat, eigvals_inv: Mat, f_eigvals: Mat, gain=3.0, clip_low=False):
+        """Nystroem + ComputeResultFromLaplacian in one pass over Phi; returns (phi, z)."""
+        H, W, ch = self.shape
+        z = np.zeros((H, W, ch), dtype=np.float32)
+        p = C.c_void_p()
+        _check(lib().gl_nystroem_filter(self.h, L_B.h, phi_A.h, eigvals_inv.h, f_eigvals.h, gain, int(clip_low), C.byref(p),
+                                        z.ctypes.data, None))
+        return Mat(self, p), (z[:, :, 0] if ch == 1 else z)
 
     def orthonormalise(self, phi: Mat) -> np.ndarray:
         norms = np.empty(phi.info.cols, dtype=np.float64)

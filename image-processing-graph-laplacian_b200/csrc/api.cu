@@ -114,6 +114,8 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         if (!strcmp(value, "sums")) ctx->projection_mode = 0;
         else if (!strcmp(value, "recompute")) ctx->projection_mode = 1;
         else GL_REQUIRE(false, "option projection: want sums|recompute, got %s", value);
+    } else if (!strcmp(key, "fuse_filter")) {
+        ctx->fuse_filter = atoi(value) != 0;
     } else if (!strcmp(key, "filter_apply")) {
         if (!strcmp(value, "warp")) ctx->filter_apply_impl = 0;
         else if (!strcmp(value, "generic")) ctx->filter_apply_impl = 1;
@@ -468,6 +470,27 @@ int gl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl
     return gl_impl_nystroem(ctx, L_B, phi_A, eigvals_inv, phi);
 }
 
+int gl_nystroem_filter(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat* f_eigvals, double gain, int clip_low,
+                       gl_mat** phi, float* z_f32, uint8_t* z_u8)
+{
+    GL_REQUIRE(ctx && L_B && phi_A && eigvals_inv && f_eigvals && phi, "gl_nystroem_filter: null");
+    GL_REQUIRE(L_B->kind == GL_MAT_KB && phi_A->kind == GL_MAT_EIGVEC && eigvals_inv->kind == GL_MAT_DIAG && f_eigvals->kind == GL_MAT_DIAG,
+               "gl_nystroem_filter: wrong handle kinds");
+    GL_REQUIRE(phi_A->rows == L_B->p && eigvals_inv->rows == phi_A->cols && f_eigvals->rows == phi_A->cols,
+               "gl_nystroem_filter: shape mismatch");
+    GL_REQUIRE(L_B->q0 == ctx->q0 && L_B->local_rows == ctx->q1 - ctx->q0 && L_B->image_epoch == ctx->image_epoch,
+               "gl_nystroem_filter: L_B does not belong to the current image");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    gl_fused_filter ff;
+    ff.f_eigvals = f_eigvals;
+    ff.gain = gain;
+    ff.clip_low = clip_low;
+    ff.z_f32 = z_f32;
+    ff.z_u8 = z_u8;
+    StageTimer t(ctx, GL_T_NYSTROEM);
+    return gl_impl_nystroem(ctx, L_B, phi_A, eigvals_inv, phi, &ff);
+}
+
 int gl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
 {
     GL_REQUIRE(ctx && phi && phi->kind == GL_MAT_PHI, "gl_orthonormalise: want a Phi handle");
@@ -719,13 +742,21 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
         gl_mat_destroy(K_B); K_B = nullptr;
         if ((rc = gl_eigensolve(ctx, L_A, prm->num_eigvals, &U, &mu, &mu_inv)) != GL_OK) break;
         gl_mat_destroy(L_A); L_A = nullptr;
-        if ((rc = gl_nystroem(ctx, L_B, U, mu_inv, &phi)) != GL_OK) break;
+        if ((rc = gl_diag_pow(ctx, mu, prm->power, &f_mu)) != GL_OK) break;  // MatPow(eigvals, .) as intended
+        // without an orthonormalisation in between, the filter can ride on the extrapolation GEMM's epilogue: Phi is
+        // still written, but never read back (option fuse_filter=0 runs the two stages apart, as the reference does)
+        const bool fused = ctx->fuse_filter && !prm->gram_schmidt && ctx->projection_mode == 0 && ctx->gemm_impl == 0;
+        if (fused) {
+            ctx->ev_valid[GL_T_FILTER] = false;
+            if ((rc = gl_nystroem_filter(ctx, L_B, U, mu_inv, f_mu, prm->gain, prm->clip_low, &phi, z_f32, z_u8)) != GL_OK) break;
+        } else if ((rc = gl_nystroem(ctx, L_B, U, mu_inv, &phi)) != GL_OK) break;
         gl_mat_destroy(L_B); L_B = nullptr;
         gl_mat_destroy(U); U = nullptr;
         gl_mat_destroy(mu_inv); mu_inv = nullptr;
-        if (prm->gram_schmidt && (rc = gl_orthonormalise(ctx, phi, nullptr)) != GL_OK) break;
-        if ((rc = gl_diag_pow(ctx, mu, prm->power, &f_mu)) != GL_OK) break;  // MatPow(eigvals, .) as intended
-        if ((rc = gl_filter(ctx, phi, f_mu, prm->gain, prm->clip_low, z_f32, z_u8)) != GL_OK) break;
+        if (!fused) {
+            if (prm->gram_schmidt && (rc = gl_orthonormalise(ctx, phi, nullptr)) != GL_OK) break;
+            if ((rc = gl_filter(ctx, phi, f_mu, prm->gain, prm->clip_low, z_f32, z_u8)) != GL_OK) break;
+        }
         if (p_out) *p_out = p;
         if (m_out) *m_out = (int)mu->rows;
         if (eigvals_out) rc = gl_mat_download(ctx, mu, eigvals_out, (size_t)mu->rows);

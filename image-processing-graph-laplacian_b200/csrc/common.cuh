@@ -117,6 +117,7 @@ struct gl_ctx {
     unsigned long long image_epoch = 0;  // bumped by every gl_set_*image
     int filter_apply_impl = 0;  // 0 = warp-per-row kernel when the shape allows, 1 = always the generic kernel
     int projection_mode = 0;  // 0 = c from the affinity sums (default), 1 = always recompute c with a pass over Phi
+    int fuse_filter = 1;      // gl_run: apply the filter inside the extrapolation GEMM's epilogue when possible
 
     // samples
     unsigned p = 0;
@@ -186,13 +187,32 @@ int gl_impl_synthetic(gl_ctx* ctx, uint32_t seed);
 int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A, gl_mat** K_B);
 int gl_impl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A, gl_mat** L_B);
 int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv);
-int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi);
+// request to apply the filter inside the extrapolation GEMM (gl_nystroem_filter)
+struct gl_fused_filter {
+    gl_mat* f_eigvals = nullptr;
+    double gain = 0.0;
+    int clip_low = 0;
+    float* z_f32 = nullptr;   // host destinations as in gl_filter (may be null)
+    uint8_t* z_u8 = nullptr;
+};
+int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi, const gl_fused_filter* ff = nullptr);
+int gl_filter_weights_from_proj(gl_ctx* ctx, const double* proj, const double* f, double gain, int m, int m_pad, int C, float* w);
+int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int parts, const float* w, const float* U, int ldU,
+                           int clip_low, float* z_f32, uint8_t* z_u8);
 int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out);
 int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip_low, float* z_f32, uint8_t* z_u8);
 int gl_impl_diag_map(gl_ctx* ctx, gl_mat* d, int op, double arg, gl_mat** out);
+// optional fusion of the filter application into the GEMM epilogue (nystroem_gemm.cu / filter.cu)
+struct gl_gemm_fuse {
+    const float* w = nullptr;   // [n_pad][C] filter weights gain * f(lambda) o c
+    float* zpart = nullptr;     // [parts][rows][C] partial row dots, to be summed in the order of `parts`
+    int C = 0;
+    int parts = 0;              // out: number of partials per row the kernel writes
+};
 // A is either a dense [rows][k_pad] K-major matrix (a_tab == nullptr) or K_B's blocked storage with its tile table
 int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
-                   const float* scales, const void* addend, void* D, const int4* a_tab = nullptr, int64_t a_total_blocks = 0);
+                   const float* scales, const void* addend, void* D, const int4* a_tab = nullptr, int64_t a_total_blocks = 0,
+                   gl_gemm_fuse* fuse = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

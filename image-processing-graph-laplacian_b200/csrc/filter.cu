@@ -305,6 +305,105 @@ __global__ void k_filter_c_from_proj(const double* __restrict__ proj, int count,
     if (i < count) c[i] = (float)proj[i];
 }
 
+// ---- filter applied inside the extrapolation GEMM (nystroem_gemm.cu, FC > 0): weights first, partial sums afterwards ----
+__global__ void k_filter_weights_from_proj(const double* __restrict__ proj, const double* __restrict__ f, int m, int m_pad, int C,
+                                           double gain, float* __restrict__ w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m_pad * C) return;
+    const int j = i / C;
+    w[i] = j < m ? (float)(gain * f[j] * (double)(float)proj[i]) : 0.f;   // c is rounded to fp32 exactly as in the staged path
+}
+
+int gl_filter_weights_from_proj(gl_ctx* ctx, const double* proj, const double* f, double gain, int m, int m_pad, int C, float* w)
+{
+    k_filter_weights_from_proj<<<(unsigned)ceil_div(m_pad * C, 256), 256, 0, ctx->stream>>>(proj, f, m, m_pad, C, gain, w);
+    GL_LAUNCH_CHECK(ctx);
+    return GL_OK;
+}
+
+// z[row][ch] = y + sum over parts (fixed order); clip; optional u8
+__global__ void k_filter_sum_parts(const float* __restrict__ zpart, int parts, int64_t rows, int C, const uint8_t* __restrict__ y,
+                                   int clip_low, float* __restrict__ z, uint8_t* __restrict__ z8)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * C) return;
+    float s = 0.f;
+    for (int k = 0; k < parts; ++k) s += zpart[(size_t)k * rows * C + i];
+    float val = fminf((float)y[i] + s, 255.f);        // AboveXSetY(z, 255, 255), display.c:76
+    if (clip_low) val = fmaxf(val, 0.f);
+    z[i] = val;
+    if (z8) z8[i] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);
+}
+
+// the sample pixels' rows of Phi are Phi_A, not the extrapolation (nystroem.c:25-34): z[s_i] = y + U[i, :] . w
+__global__ void k_filter_sample_rows(const float* __restrict__ U, int ldU, int p, int m, const uint32_t* __restrict__ samples,
+                                     int64_t q0, int64_t q1, int C, const float* __restrict__ w, const uint8_t* __restrict__ img,
+                                     int clip_low, float* __restrict__ z, uint8_t* __restrict__ z8)
+{
+    const int i = blockIdx.x;
+    const int64_t q = samples[i];
+    if (q < q0 || q >= q1) return;
+    __shared__ float red[3][32];
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const float u = __half2float(__float2half_rn(U[(size_t)j * ldU + i]));   // the value stored in Phi
+        for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(u, w[(size_t)j * C + ch], acc[ch]);
+    }
+    for (int ch = 0; ch < C; ++ch) {
+        const float v = warp_sum(acc[ch]);
+        if ((threadIdx.x & 31) == 0) red[ch][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+        float s = 0.f;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += red[threadIdx.x][k];
+        const size_t o = (size_t)(q - q0) * C + threadIdx.x;
+        float val = fminf((float)img[(size_t)q * C + threadIdx.x] + s, 255.f);
+        if (clip_low) val = fmaxf(val, 0.f);
+        z[o] = val;
+        if (z8) z8[o] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);
+    }
+}
+
+int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int parts, const float* w, const float* U, int ldU,
+                           int clip_low, float* z_f32, uint8_t* z_u8)
+{
+    const int C = ctx->channels;
+    const int64_t rows = phi->local_rows;
+    gl_buf *z = nullptr, *z8 = nullptr;
+    int rc = GL_OK;
+    do {
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)rows * C, &z)) != GL_OK) break;
+        if (z_u8 && (rc = gl_alloc(ctx, (size_t)rows * C, &z8)) != GL_OK) break;
+        {
+            StageTimer t(ctx, GL_T_FILTER);
+            const uint8_t* y = (const uint8_t*)ctx->img->ptr + (size_t)phi->q0 * C;
+            k_filter_sum_parts<<<(unsigned)ceil_div(rows * C, 256), 256, 0, ctx->stream>>>(zpart, parts, rows, C, y, clip_low, (float*)z->ptr,
+                                                                                          z8 ? (uint8_t*)z8->ptr : nullptr);
+            GL_LAUNCH_CHECK(ctx);
+            k_filter_sample_rows<<<phi->p, 128, 0, ctx->stream>>>(U, ldU, phi->p, phi->m, (const uint32_t*)ctx->samples->ptr, phi->q0,
+                                                                 phi->q0 + rows, C, w, (const uint8_t*)ctx->img->ptr, clip_low,
+                                                                 (float*)z->ptr, z8 ? (uint8_t*)z8->ptr : nullptr);
+            GL_LAUNCH_CHECK(ctx);
+        }
+        ctx->ev_valid[GL_T_K_FILTER_PROJECT] = false;
+        ctx->ev_valid[GL_T_K_FILTER_APPLY] = false;
+        {
+            StageTimer t(ctx, GL_T_D2H);
+            if (z_f32)
+                GL_CUDA_CHECK(cudaMemcpyAsync(z_f32 + (size_t)phi->q0 * C, z->ptr, sizeof(float) * (size_t)rows * C, cudaMemcpyDeviceToHost,
+                                              ctx->stream));
+            if (z_u8)
+                GL_CUDA_CHECK(cudaMemcpyAsync(z_u8 + (size_t)phi->q0 * C, z8->ptr, (size_t)rows * C, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (z_f32 || z_u8) GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } while (0);
+    if (z) gl_buf_release(z);
+    if (z8) gl_buf_release(z8);
+    return rc;
+}
+
 template <int C, int NG>
 static int run_filter(gl_ctx* ctx, gl_mat* phi, const FilterGeom& g, const double* f, double gain, int clip_low, int grid,
                       float* partial, float* c, float* w, float* z, uint8_t* z8, bool use_proj)

@@ -276,6 +276,7 @@ constexpr int smem_bytes()
 {
     return STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_WARPS * CBUFS * C_SLAB_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
 }
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -414,12 +415,16 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t w)
 // One persistent CTA per SM.  warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator,
 // warps 4..: epilogue, EPI_WARPS / 4 per TMEM lane quarter (warp w drains lanes 32*(w%4) .. +31 and its share of the
 // accumulator's columns).
-template <int STAGES, int CBUFS, int EPI_WARPS>
+// FC > 0 fuses the filter application into the epilogue (FC = image channels): besides storing the fp16 tile, every
+// epilogue thread accumulates dot(row of D, w[:, ch]) over its columns from the fp32 accumulators and writes one partial
+// per (N tile, column share) to zpart[part][row][ch]; filter.cu sums the partials in fixed order (deterministic).
+template <int STAGES, int CBUFS, int EPI_WARPS, int FC>
 __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, int m_tiles, int n_tiles, int k_blocks, int n_total, int block_n,
                int ab_bf16, const float* __restrict__ scales, const __half* __restrict__ addend, int64_t m_rows,
                const int4* __restrict__ a_tab /* K_B tile table, or null for a dense A */, int prefetch_tiles,
+               const float* __restrict__ fuse_w /* [n_total][FC] */, float* __restrict__ zpart /* [parts][m_rows][FC] */,
                int* __restrict__ err)
 {
     extern __shared__ uint8_t gemm_smem_raw[];
@@ -432,9 +437,12 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+    float* w_s = (float*)(bars + 32);   // after the 256-byte barrier block: the filter weights (FC > 0 only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = m_tiles * n_tiles;
+    if (FC > 0)
+        for (int i = threadIdx.x; i < n_total * FC; i += blockDim.x) w_s[i] = fuse_w[i];
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -551,6 +559,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(bar_tfull + 8 * acc, acc_phase, err, 4);
             tcgen05_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * MAX_BLOCK_N);
+            float dot[FC > 0 ? FC : 1];
+#pragma unroll
+            for (int q = 0; q < (FC > 0 ? FC : 1); ++q) dot[q] = 0.f;
             const bool split = n_size >= 64 * SHARES;
             const int c_end = split ? c_hi : (ch == 0 ? n_size : 0);
             for (int c0 = (split ? c_lo : 0); c0 < c_end; c0 += 64) {
@@ -586,6 +597,22 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             pk[i] = pack_h2(__uint_as_float(v[h][2 * i]) * sc, __uint_as_float(v[h][2 * i + 1]) * sc);
+                        if (FC > 0) {
+                            // 32 columns starting at nt * block_n + c0 + 32 h; weights read as broadcast float4s
+                            const float4* wv = (const float4*)(w_s + (size_t)(nt * block_n + c0 + 32 * h) * FC);
+#pragma unroll
+                            for (int g8 = 0; g8 < 4; ++g8) {   // 8 columns = 8 * FC floats = 2 * FC float4
+                                float wr[8 * (FC > 0 ? FC : 1)];
+#pragma unroll
+                                for (int q = 0; q < 2 * FC; ++q) *(float4*)&wr[4 * q] = wv[g8 * 2 * FC + q];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float val = __uint_as_float(v[h][8 * g8 + i]) * sc;
+#pragma unroll
+                                    for (int q = 0; q < FC; ++q) dot[q] = fmaf(val, wr[i * FC + q], dot[q]);
+                                }
+                            }
+                        }
                     }
                     // row `lane` of the slab, 16-byte chunks 4h .. 4h+3, XOR-swizzled like SWIZZLE_128B
 #pragma unroll
@@ -606,6 +633,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (FC > 0) {
+                const int64_t row = (int64_t)mt * BLOCK_M + wq * 32 + lane;
+                if (row < m_rows) {   // a share that had no columns (narrow N tile) writes its zero
+                    const int part = nt * SHARES + ch;
+#pragma unroll
+                    for (int q = 0; q < FC; ++q) zpart[((size_t)part * m_rows + row) * FC + q] = dot[q];
+                }
+            }
         }
         if (lane == 0) tma_store_wait_all<0>();
     }
@@ -666,9 +701,10 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* bas
 // D[rows][n_pad] (fp16) = scales[1] * A[rows][k_pad] . Bt[n_pad][k_pad]^T (+ addend), A and Bt 16-bit K-major
 // (ab_bf16: 0 = fp16, 1 = bf16).  k_pad % 64 == 0; n_pad is 64, 128 or a multiple of 256 (gl_m_pad).
 int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
-                   const float* scales, const void* addend, void* D, const int4* a_tab, int64_t a_total_blocks)
+                   const float* scales, const void* addend, void* D, const int4* a_tab, int64_t a_total_blocks, gl_gemm_fuse* fuse)
 {
     GL_REQUIRE(k_pad % 64 == 0 && n_pad % 64 == 0, "gemm: k_pad %d / n_pad %d must be multiples of 64", k_pad, n_pad);
+    GL_REQUIRE(!(fuse && ctx->gemm_impl == 1), "gemm: the CUDA-core checker has no fused filter");
     if (ctx->gemm_impl == 1) {
         dim3 grid((unsigned)ceil_div(n_pad, 32), (unsigned)ceil_div(rows, 32));
         GL_REQUIRE(ceil_div(rows, 32) < 2147483647ll, "gemm(simple): band too large");
@@ -706,27 +742,45 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
     // short K loops (blocked K_B with few blocks per tile): the epilogue is the critical path
     const bool short_k = a_tab != nullptr && a_total_blocks * 4 < (int64_t)m_tiles * 8;   // fewer than 8 K blocks per M tile on average
-    StageTimer kt(ctx, GL_T_K_GEMM);
     const int pf = short_k ? ctx->gemm_prefetch : 0;   // with long K loops the ring already covers the latency; prefetch only adds L2 churn
-    if (ctx->gemm_stages == 3 || (ctx->gemm_stages == 0 && short_k)) {
-        constexpr int SM = tc::smem_bytes<3, 2, 8>();
-        GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<3, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
-        tc::k_gemm_tcgen05<3, 2, 8><<<grid, 128 + 32 * 8, SM, ctx->stream>>>(map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad, block_n,
-                                                                         ab_bf16, scales, (const __half*)addend, rows, a_tab, pf,
-                                                                         (int*)err->ptr);
-    } else {
-        constexpr int SM = tc::smem_bytes<4, 2, 4>();
-        GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<4, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
-        tc::k_gemm_tcgen05<4, 2, 4><<<grid, 128 + 32 * 4, SM, ctx->stream>>>(map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad, block_n,
-                                                                         ab_bf16, scales, (const __half*)addend, rows, a_tab, pf,
-                                                                         (int*)err->ptr);
+    const bool deep = !(ctx->gemm_stages == 3 || (ctx->gemm_stages == 0 && short_k));
+    const int FCH = fuse ? fuse->C : 0;
+    const int w_bytes = FCH * n_pad * (int)sizeof(float);
+    if (fuse) {
+        GL_REQUIRE(!addend && (FCH == 1 || FCH == 3), "gemm: fused filter wants 1 or 3 channels and no addend");
+        GL_REQUIRE(ctx->gemm_impl == 0, "gemm: the CUDA-core checker has no fused filter");
+        GL_REQUIRE((deep ? tc::smem_bytes<4, 1, 4>() : tc::smem_bytes<3, 2, 8>()) + w_bytes <= tc::SMEM_LIMIT,
+                   "gemm: no shared memory left for %d filter weights", FCH * n_pad);
+        fuse->parts = n_tiles * (deep ? 1 : 2);
     }
+    const float* fw = fuse ? fuse->w : nullptr;
+    float* zp = fuse ? fuse->zpart : nullptr;
+    StageTimer kt(ctx, GL_T_K_GEMM);
+#define GEMM_LAUNCH(S, CB, EW, FC)                                                                                           \
+    do {                                                                                                                       \
+        const int SM = tc::smem_bytes<S, CB, EW>() + w_bytes;                                                                  \
+        GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<S, CB, EW, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
+        tc::k_gemm_tcgen05<S, CB, EW, FC><<<grid, 128 + 32 * EW, SM, ctx->stream>>>(                                            \
+            map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad, block_n, ab_bf16, scales, (const __half*)addend, rows, a_tab, \
+            pf, fw, zp, (int*)err->ptr);                                                                                        \
+    } while (0)
+    if (!deep) {
+        if (FCH == 1) GEMM_LAUNCH(3, 2, 8, 1);
+        else if (FCH == 3) GEMM_LAUNCH(3, 2, 8, 3);
+        else GEMM_LAUNCH(3, 2, 8, 0);
+    } else {
+        // the deep ring leaves room for the weights only with single store slabs (the epilogue has slack here)
+        if (FCH == 1) GEMM_LAUNCH(4, 1, 4, 1);
+        else if (FCH == 3) GEMM_LAUNCH(4, 1, 4, 3);
+        else GEMM_LAUNCH(4, 2, 4, 0);
+    }
+#undef GEMM_LAUNCH
     gl_buf_release(err);
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;
 }
 
-int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi_out)
+int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi_out, const gl_fused_filter* ff)
 {
     const int p = L_B->p, p_pad = L_B->p_pad;
     const int m = (int)phi_A->cols;
@@ -765,9 +819,6 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
                                                   (const float*)scales->ptr, (__half*)Wt->ptr);
         GL_LAUNCH_CHECK(ctx);
 
-        GL_REQUIRE(L_B->tiles, "nystroem: K_B handle without a tile table");
-        if ((rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, p_pad, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
-                                 phi->buf->ptr, (const int4*)L_B->tiles->ptr, L_B->total_blocks)) != GL_OK) break;
         // projection c = Phi^T y from the affinity sums (valid while the image and the samples are unchanged)
         if (L_B->aux && L_B->channels == ctx->channels && L_B->image_epoch == ctx->image_epoch) {
             const int C = ctx->channels;
@@ -787,6 +838,32 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
             phi->channels = C;
             phi->image_epoch = ctx->image_epoch;
         }
+        GL_REQUIRE(L_B->tiles, "nystroem: K_B handle without a tile table");
+        gl_gemm_fuse fuse;
+        gl_buf *wbuf = nullptr, *zpart = nullptr;
+        const bool do_fuse = ff != nullptr;
+        if (do_fuse) {
+            // filter weights before the GEMM: w = gain * f(lambda) o c with c from the affinity sums
+            const int C = ctx->channels;
+            if (!phi->proj) { gl_set_error("nystroem: fused filter needs the affinity sums of the current image"); rc = GL_ERR_ARG; break; }
+            if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad * C, &wbuf)) != GL_OK) break;
+            const int parts_max = 2 * (m_pad / (m_pad < 256 ? m_pad : 256));
+            if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)parts_max * rows * C, &zpart)) != GL_OK) { gl_buf_release(wbuf); break; }
+            if ((rc = gl_filter_weights_from_proj(ctx, (const double*)phi->proj->ptr, (const double*)ff->f_eigvals->buf->ptr, ff->gain, m, m_pad,
+                                                  C, (float*)wbuf->ptr)) != GL_OK) { gl_buf_release(wbuf); gl_buf_release(zpart); break; }
+            fuse.w = (const float*)wbuf->ptr;
+            fuse.zpart = (float*)zpart->ptr;
+            fuse.C = C;
+        }
+        rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, p_pad, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr, phi->buf->ptr,
+                            (const int4*)L_B->tiles->ptr, L_B->total_blocks, do_fuse ? &fuse : nullptr);
+        if (rc == GL_OK && do_fuse)
+            rc = gl_filter_fused_finish(ctx, phi, (const float*)zpart->ptr, fuse.parts, (const float*)wbuf->ptr, U, (int)phi_A->ld,
+                                        ff->clip_low, ff->z_f32, ff->z_u8);
+        if (wbuf) gl_buf_release(wbuf);
+        if (zpart) gl_buf_release(zpart);
+        if (rc != GL_OK) break;
+
         k_phi_sample_rows<<<p, 128, 0, ctx->stream>>>(U, (int)phi_A->ld, p, m, (const uint32_t*)ctx->samples->ptr, phi->q0,
                                                       phi->q0 + rows, m_pad, (__half*)phi->buf->ptr);
         GL_LAUNCH_CHECK(ctx);

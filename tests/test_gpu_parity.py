@@ -254,6 +254,36 @@ def test_projection_and_apply_variants_agree(ctx, golden):
         print(f"variants {tag}: default dz={_rel(a['z'] - src, z - src):.2e} " + " ".join(f"{k}:dz={v[1]:.2e}" for k, v in res.items()))
 
 
+@pytest.mark.parametrize("tag", ["barbara_uniform256", "lion_rgb_photometric500", "cat_small_uniform_m20"])
+def test_fused_filter_matches_staged(ctx, golden, tag):
+    """gl_run applies the filter inside the extrapolation GEMM's epilogue (gl_nystroem_filter); option fuse_filter=0
+    runs Nystroem and the filter apart like the reference.  Same answer, and Phi is still produced."""
+    g = golden(tag)
+    src, a = _run_case(ctx, g)                         # fused (default)
+    ctx.set_option("fuse_filter", 0)
+    try:
+        _, b = _run_case(ctx, g)
+    finally:
+        ctx.set_option("fuse_filter", 1)
+    z = g["z"].astype(np.float64)
+    for r in (a, b):
+        assert _rel(r["z"], z) <= TOL_Z and _rel(r["z"] - src, z - src) <= TOL_DZ
+    assert _rel(a["z"], b["z"].astype(np.float64)) < 2e-5
+    # stage-level call: Phi comes back and equals the staged Phi
+    img, s = src, g["sample_indices"]
+    ctx.set_image(img)
+    ctx.set_samples(s)
+    K_A, K_B = ctx.affinity(str(g["kind"]), float(g["h_loc"]), float(g["h_val"]))
+    L_A, L_B = ctx.laplacian(K_A, K_B)
+    U, mu, mu_inv = ctx.eigensolve(L_A, int(g["m"]))
+    phi_f, z_f = ctx.nystroem_filter(L_B, U, mu_inv, mu)
+    phi_s = ctx.nystroem(L_B, U, mu_inv)
+    assert np.array_equal(phi_f.download(), phi_s.download())
+    z_s = ctx.filter(phi_s, mu)
+    assert _rel(z_f, z_s.astype(np.float64)) < 2e-5
+    assert _rel(z_f, z) <= TOL_Z
+
+
 def test_kb_cutoff_blocks(ctx):
     """K_B's spatial cutoff (sample blocks whose entries fp16 flushes to zero are not stored, affinity.cu): the
     stored blocks shrink, the skipped entries really are < 2^-25 in the oracle, and the result equals the dense run."""
