@@ -26,7 +26,7 @@ AFFINITY_KINDS = {BILATERAL: 0, PHOTOMETRIC: 1, SPATIAL: 2}
 # sampling -- names follow python/sampling/__init__.py:4
 RANDOM, SPATIALLY_UNIFORM = "random", "spatially_uniform"
 # gl_mat_kind
-MAT_KA, MAT_KB, MAT_EIGVEC, MAT_DIAG, MAT_PHI = 1, 2, 3, 4, 5
+MAT_KA, MAT_KB, MAT_EIGVEC, MAT_DIAG, MAT_PHI, MAT_FULL = 1, 2, 3, 4, 5, 6
 STAGES = ["h2d", "sampling", "affinity", "laplacian", "eigen", "nystroem", "gram_schmidt", "filter", "d2h", "total",
           "k_affinity_b", "k_gemm", "k_filter_project", "k_filter_apply", "k_jacobi"]
 
@@ -38,7 +38,7 @@ EXPORTS = [
     "gl_set_image", "gl_set_image_rows", "gl_set_synthetic_image", "gl_get_image", "gl_get_band",
     "gl_sampling_uniform", "gl_sampling_random", "gl_set_samples", "gl_get_samples",
     "gl_affinity", "gl_laplacian", "gl_eigensolve", "gl_nystroem", "gl_nystroem_filter", "gl_orthonormalise", "gl_filter",
-    "gl_diag_inverse", "gl_diag_pow", "gl_run", "gl_run_resident",
+    "gl_diag_inverse", "gl_diag_pow", "gl_full_affinity", "gl_full_laplacian", "gl_full_result", "gl_run", "gl_run_resident",
     "gl_mat_info_get", "gl_mat_retain", "gl_mat_destroy", "gl_mat_download", "gl_mat_rowsums", "gl_mat_upload",
     "gl_host_alloc", "gl_host_free",
 ]
@@ -104,6 +104,9 @@ def lib():
         L.gl_nystroem_filter.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_int, C.POINTER(vp), vp, vp]
         L.gl_orthonormalise.argtypes = [vp, vp, vp]
         L.gl_filter.argtypes = [vp, vp, vp, C.c_double, C.c_int, vp, vp]
+        L.gl_full_affinity.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
+        L.gl_full_laplacian.argtypes = [vp, vp, C.POINTER(vp)]
+        L.gl_full_result.argtypes = [vp, vp, vp, vp]
         L.gl_diag_inverse.argtypes = [vp, vp, C.POINTER(vp)]
         L.gl_diag_pow.argtypes = [vp, vp, C.c_double, C.POINTER(vp)]
         L.gl_run.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(Params), vp, vp, C.POINTER(C.c_uint), ip, vp]
@@ -355,6 +358,25 @@ class Context:
         _check(lib().gl_diag_inverse(self.h, d.h, C.byref(o)))
         return Mat(self, o)
 
+    # ---- the reference's -no_approx mode (matrix-free) -----------------------------------------------
+    def full_affinity(self, kind=BILATERAL, h_loc=40.0, h_val=30.0) -> Mat:
+        k = C.c_void_p()
+        _check(lib().gl_full_affinity(self.h, AFFINITY_KINDS[kind], h_loc, h_val, C.byref(k)))
+        return Mat(self, k)
+
+    def full_laplacian(self, K: Mat) -> Mat:
+        o = C.c_void_p()
+        _check(lib().gl_full_laplacian(self.h, K.h, C.byref(o)))
+        return Mat(self, o)
+
+    def full_result(self, L: Mat, want_u8=False):
+        H, W, ch = self.shape
+        z = np.zeros((H, W, ch), dtype=np.float32)
+        z8 = np.zeros((H, W, ch), dtype=np.uint8) if want_u8 else None
+        _check(lib().gl_full_result(self.h, L.h, z.ctypes.data, z8.ctypes.data if want_u8 else None))
+        z = z[:, :, 0] if ch == 1 else z
+        return (z, z8[:, :, 0] if ch == 1 else z8) if want_u8 else z
+
     def upload(self, kind, a) -> Mat:
         a = np.ascontiguousarray(a, dtype=np.float64)
         rows, cols = (a.shape[0], 1) if a.ndim == 1 else a.shape
@@ -382,10 +404,12 @@ class Context:
         self.shape = (H, W, ch)
         if z_out is None:
             z_out = np.zeros(img.shape, dtype=np.float32)
+        elif z_out is False:        # no fp32 result wanted (u8 only)
+            z_out = None
         p, m = C.c_uint(), C.c_int()
         cap = params.sample_size if params.sample_size else int(H * W * 0.01)
         mu = np.zeros(max(cap * 2 + 64, 64), dtype=np.float64) if want_eigvals else None
-        _check(lib().gl_run(self.h, img.ctypes.data, W, H, ch, C.byref(params), z_out.ctypes.data,
+        _check(lib().gl_run(self.h, img.ctypes.data, W, H, ch, C.byref(params), z_out.ctypes.data if z_out is not None else None,
                             z8_out.ctypes.data if z8_out is not None else None, C.byref(p), C.byref(m),
                             mu.ctypes.data if want_eigvals else None))
         return dict(z=z_out, p=p.value, m=m.value, mu=mu[:m.value] if want_eigvals else None)

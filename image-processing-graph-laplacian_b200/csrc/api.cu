@@ -132,6 +132,8 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         ctx->eig_largest = atoi(value) != 0;   // EigendecompositionLargest (hpc/eigendecomposition.c:116-119)
     } else if (!strcmp(key, "jacobi_max_sweeps")) {
         ctx->jacobi_max_sweeps = atoi(value);
+    } else if (!strcmp(key, "jacobi_inner")) {
+        ctx->jacobi_inner = atoi(value);
     } else if (!strcmp(key, "jacobi_tol")) {
         ctx->jacobi_tol = (float)atof(value);
     } else if (!strcmp(key, "verbose")) {
@@ -507,6 +509,34 @@ int gl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip
     GL_REQUIRE(phi->q0 == ctx->q0 && phi->local_rows == ctx->q1 - ctx->q0, "gl_filter: Phi does not belong to the current image");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
     return gl_impl_filter(ctx, phi, f_eigvals, gain, clip_low, z_f32, z_u8);
+}
+
+int gl_full_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K)
+{
+    GL_REQUIRE(ctx && K, "gl_full_affinity: null");
+    GL_REQUIRE(ctx->n > 0, "gl_full_affinity: set an image first");
+    GL_REQUIRE(kind >= GL_BILATERAL && kind <= GL_SPATIAL, "gl_full_affinity: bad kind %d", kind);
+    GL_REQUIRE(h_loc > 0 && h_val > 0, "gl_full_affinity: bandwidths must be positive");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_AFFINITY);
+    return gl_impl_full_affinity(ctx, kind, h_loc, h_val, K);
+}
+
+int gl_full_laplacian(gl_ctx* ctx, gl_mat* K, gl_mat** L)
+{
+    GL_REQUIRE(ctx && K && L && K->kind == GL_MAT_FULL && !K->dscale, "gl_full_laplacian: want the handle gl_full_affinity returned");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_LAPLACIAN);
+    return gl_impl_full_laplacian(ctx, K, L);
+}
+
+int gl_full_result(gl_ctx* ctx, gl_mat* L, float* z_f32, uint8_t* z_u8)
+{
+    GL_REQUIRE(ctx && L && L->kind == GL_MAT_FULL && L->dscale, "gl_full_result: want the handle gl_full_laplacian returned");
+    GL_REQUIRE(L->image_epoch == ctx->image_epoch && L->q0 == ctx->q0, "gl_full_result: the matrix does not belong to the current image");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_FILTER);
+    return gl_impl_full_result(ctx, L, z_f32, z_u8);
 }
 
 int gl_diag_inverse(gl_ctx* ctx, gl_mat* d, gl_mat** out)

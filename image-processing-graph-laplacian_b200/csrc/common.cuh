@@ -156,7 +156,8 @@ struct gl_ctx {
     int gemm_prefetch = 2;    // blocked A: L2-prefetch the A blocks of the tile this many iterations ahead (0 = off)
     int eig_largest = 0;      // 1: keep the m LARGEST eigenpairs (descending) instead of the smallest (ascending)
     int jacobi_max_sweeps = 40;
-    float jacobi_tol = 2e-6f;
+    int jacobi_inner = 1;     // inner 16 x 16 Jacobi sweeps per pair visit (0 = until converged, at most 12); 1 is enough: the outer sweeps repeat
+    float jacobi_tol = 1e-5f;  // largest relative off-diagonal of G^T G at convergence (eigenvalues are refined by fp64 Rayleigh quotients)
     int verbose = 0;
 };
 
@@ -202,6 +203,9 @@ int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int par
 int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out);
 int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip_low, float* z_f32, uint8_t* z_u8);
 int gl_impl_diag_map(gl_ctx* ctx, gl_mat* d, int op, double arg, gl_mat** out);
+int gl_impl_full_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K);
+int gl_impl_full_laplacian(gl_ctx* ctx, gl_mat* K, gl_mat** L);
+int gl_impl_full_result(gl_ctx* ctx, gl_mat* L, float* z_f32, uint8_t* z_u8);
 // optional fusion of the filter application into the GEMM epilogue (nystroem_gemm.cu / filter.cu)
 struct gl_gemm_fuse {
     const float* w = nullptr;   // [n_pad][C] filter weights gain * f(lambda) o c

@@ -57,7 +57,7 @@ __device__ __forceinline__ void tournament(int step, int pair, int nb, int& a, i
 }
 
 // One panel pair (I, J): load the two panels, form the 16 x 16 Gram block, diagonalise it, rotate the panels.
-__device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I, int J, float tol, float* P, float* red, double* Bm,
+__device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I, int J, float tol, int inner_max, float* P, float* red, double* Bm,
                                             double* Qm, double* cs, int* role, int* pq, float* s_off, unsigned* s_cta_off)
 {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I,
     if (pair_off > 0.25f * tol) {
         if (tid == 0) *s_off = 0.f;
         __syncthreads();
-        for (int isw = 0; isw < J_INNER_MAX; ++isw) {
+        for (int isw = 0; isw < inner_max; ++isw) {
             for (int st = 0; st < JP - 1; ++st) {
                 if (tid < JB) {
                     int a, b;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I,
 //      and steps without an active pair cost nothing (no barrier).  When more than half of the pairs are active
 //      (photometric affinity) the round-robin tournament is used instead: (panels - 1) steps of panels / 2 pairs.
 __global__ void __launch_bounds__(J_THREADS, 1)
-k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, float* __restrict__ C /* [cp][cp], cp = nb * 8 */,
+k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, int inner_max, float* __restrict__ C /* [cp][cp], cp = nb * 8 */,
          float* __restrict__ pair_rel /* [nb][nb] */, int* __restrict__ step_cnt /* [max_sweeps][2 * nb] */,
          unsigned* __restrict__ sweep_off, int* __restrict__ sweeps_done)
 {
@@ -348,7 +348,7 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, float*
                     int I, J;
                     tournament(step, pair, nb, I, J);
                     if (__ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
-                        jacobi_pair(G, p, I, J, tol, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
+                        jacobi_pair(G, p, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
                 }
                 grid.sync();
             }
@@ -360,7 +360,7 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, float*
                     for (int c = blockIdx.x; c < ncand; c += gridDim.x) {
                         const int I = (c / d) * 2 * d + par * d + (c % d), J = I + d;
                         if (J < nb && __ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
-                            jacobi_pair(G, p, I, J, tol, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
+                            jacobi_pair(G, p, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
                     }
                     grid.sync();
                 }
@@ -555,7 +555,8 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         float* Cp = (float*)Cg->ptr;
         float* prp = (float*)prel->ptr;
         int* scp = (int*)scnt->ptr;
-        void* args[] = {&Gp, &p_, &nb_, &ms, &tol, &Cp, &prp, &scp, &off, &done};
+        int inner = ctx->jacobi_inner > 0 ? ctx->jacobi_inner : J_INNER_MAX;
+        void* args[] = {&Gp, &p_, &nb_, &ms, &tol, &inner, &Cp, &prp, &scp, &off, &done};
         {
             StageTimer kt(ctx, GL_T_K_JACOBI);
             GL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));

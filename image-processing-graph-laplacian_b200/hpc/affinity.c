@@ -26,11 +26,19 @@ void ComputeAffinityMatrices(Mat* K_A, Mat* K_B, const png_bytep* const img_byte
     if (gl_affinity(ctx, g_opt.affinity_kind, g_opt.h_loc, g_opt.h_val, K_A, K_B) != GL_OK) GLHostFatal("ComputeAffinityMatrices");
 }
 
-/* Reference: hpc/affinity.c:264-336 (-no_approx).  The N x N matrix is O(N^2) memory ("very memory consuming",
- * hpc/README.md:19) and outside the accelerated path. */
+/* Reference: hpc/affinity.c:264-336 (-no_approx).  The N x N matrix is never formed: the handle stands for K through
+ * the per-pixel sums the later stages need (csrc/full_filter.cu). */
 void ComputeEntireAffinityMatrix(Mat* K, const png_bytep* const img_bytes, const int width, const int height)
 {
-    (void)img_bytes; (void)width; (void)height;
+    gl_ctx* ctx = GLHostContext();
     *K = NULL;
-    fprintf(stderr, "ComputeEntireAffinityMatrix: the -no_approx path is not part of this build\n");
+    if (g_opt.color) {
+        uint8_t* flat = (uint8_t*)malloc((size_t)width * height * 3);
+        for (int r = 0; r < height; ++r) memcpy(flat + (size_t)r * width * 3, img_bytes[r], (size_t)width * 3);
+        int rc = gl_set_image(ctx, flat, width, height, 3);
+        if (rc == GL_OK) rc = gl_ctx_sync(ctx);
+        free(flat);
+        if (rc != GL_OK) GLHostFatal("ComputeEntireAffinityMatrix");
+    } else if (gl_set_image_rows(ctx, (const uint8_t* const*)img_bytes, width, height) != GL_OK) GLHostFatal("ComputeEntireAffinityMatrix");
+    if (gl_full_affinity(ctx, g_opt.affinity_kind, g_opt.h_loc, g_opt.h_val, K) != GL_OK) GLHostFatal("ComputeEntireAffinityMatrix");
 }

@@ -53,9 +53,23 @@ png_bytep* ComputeResultFromLaplacian(const png_bytep* const img_bytes, Mat phi,
     return out;
 }
 
+/* hpc/display.c:128-149: z = y - L y, clipped to [0, 255] on both sides. */
 png_bytep* ComputeResultFromEntireLaplacian(const png_bytep* const img_bytes, Mat Lapl, const unsigned int width, const unsigned int height)
 {
-    (void)img_bytes; (void)Lapl; (void)width; (void)height;
-    fprintf(stderr, "ComputeResultFromEntireLaplacian: the -no_approx path is not part of this build\n");
-    return NULL;
+    (void)img_bytes;
+    const unsigned int row_bytes = width * (g_opt.color ? 3u : 1u);
+    png_bytep* shared = GLHostSharedImage(row_bytes, height);
+    if (!shared) {
+        fprintf(stderr, "ComputeResultFromEntireLaplacian: image too large for the shared output buffer\n");
+        exit(1);
+    }
+    if (gl_full_result(GLHostContext(), Lapl, NULL, shared[0]) != GL_OK) GLHostFatal("ComputeResultFromEntireLaplacian");
+    if (GLHostRank() != 0) return NULL;
+    GLHostBarrierAtExit();
+    png_bytep* out = (png_bytep*)malloc(sizeof(png_bytep) * height);
+    for (unsigned int i = 0; i < height; ++i) {
+        out[i] = (png_bytep)malloc(row_bytes);
+        memcpy(out[i], shared[i], row_bytes);
+    }
+    return out;
 }

@@ -98,21 +98,23 @@ static PetscScalar GetInverseIterationEpsilon(void)
     return epsilon;
 }
 
-/* -no_approx (hpc/image_processing.c:155-181): N x N matrices, outside the accelerated path of this build */
+/* -no_approx (hpc/image_processing.c:155-181), same three stages and stdout lines; the N x N matrices are matrix-free */
 static png_bytep* EntireComputation(const png_bytep* const img_bytes, const unsigned int width, const unsigned int height)
 {
     Mat K = NULL, Lapl = NULL;
+    double t0 = StageClock();
     GLHostPrintf("Computing entire affinity matrix... ");
     ComputeEntireAffinityMatrix(&K, img_bytes, width, height);
-    if (!K) {
-        GLHostPrintf("unsupported\n");
-        return NULL;
-    }
+    GLHostPrintf("%fs\n", StageClock() - t0);
+    t0 = StageClock();
     GLHostPrintf("Computing entire Laplacian matrix... ");
     ComputeEntireLaplacianMatrix(&Lapl, K);
+    GLHostPrintf("%fs\n", StageClock() - t0);
     MatDestroy(&K);
+    t0 = StageClock();
     GLHostPrintf("Computing output image... ");
     png_bytep* out = ComputeResultFromEntireLaplacian(img_bytes, Lapl, width, height);
+    GLHostPrintf("%fs\n", GLHostWtime() - t0);
     MatDestroy(&Lapl);
     return out;
 }
@@ -226,7 +228,7 @@ int main(int argc, char** argv)
 
     const double total = GLHostWtime() - start_time;
     GLHostPrintf("Total computation time: %fs\n", total);
-    if (rank == 0 && output_img) {
+    if (rank == 0 && output_img && !OptionsHasName("-no_approx")) {
         float ms[GL_T_COUNT];
         if (gl_ctx_stage_ms(GLHostContext(), ms) == GL_OK) {
             const float dev = ms[GL_T_SAMPLING] + ms[GL_T_AFFINITY] + ms[GL_T_LAPLACIAN] + ms[GL_T_EIGEN] + ms[GL_T_NYSTROEM] +

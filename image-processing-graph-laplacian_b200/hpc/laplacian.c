@@ -10,9 +10,8 @@ void ComputeLaplacianMatrix(Mat* L_A, Mat* L_B, Mat K_A, Mat K_B)
     if (gl_laplacian(GLHostContext(), K_A, K_B, L_A, L_B) != GL_OK) GLHostFatal("ComputeLaplacianMatrix");
 }
 
+/* Reference: hpc/laplacian.c:44-65: alpha = 1 / mean(rowsum K), L = alpha (D - K); matrix-free here. */
 void ComputeEntireLaplacianMatrix(Mat* Lapl, Mat K)
 {
-    (void)K;
-    *Lapl = NULL;
-    fprintf(stderr, "ComputeEntireLaplacianMatrix: the -no_approx path is not part of this build\n");
+    if (gl_full_laplacian(GLHostContext(), K, Lapl) != GL_OK) GLHostFatal("ComputeEntireLaplacianMatrix");
 }

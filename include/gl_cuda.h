@@ -66,7 +66,9 @@ enum gl_mat_kind {
                            D = K_A.1 + K_B.1 */
     GL_MAT_EIGVEC = 3,  /* p x m fp32 column-major (eigenvectors of L_A in columns) */
     GL_MAT_DIAG = 4,    /* m-vector fp64 standing for a diagonal matrix */
-    GL_MAT_PHI = 5      /* this rank's pixel band x m_pad fp16 row-major, rows in raster order */
+    GL_MAT_PHI = 5,     /* this rank's pixel band x m_pad fp16 row-major, rows in raster order */
+    GL_MAT_FULL = 6     /* -no_approx: the n x n K (or L = alpha (D - K)) held matrix-free as the per-pixel vectors
+                           D = K.1 and Q = sum_j K_ij (y_i - y_j) of this rank's band (+ alpha for L) */
 };
 
 typedef struct gl_mat_info {
@@ -160,6 +162,14 @@ GL_API int gl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, i
 /* diag helpers: InverseDiagMat (hpc/utils.c:559-586) and MatPow (hpc/utils.c:705-729, as intended: x^power) */
 GL_API int gl_diag_inverse(gl_ctx* ctx, gl_mat* d, gl_mat** out);
 GL_API int gl_diag_pow(gl_ctx* ctx, gl_mat* d, double power, gl_mat** out);
+
+/* ---- the reference's -no_approx mode, matrix-free (csrc/full_filter.cu) ----------------------------------
+ *   gl_full_affinity  <- ComputeEntireAffinityMatrix       hpc/affinity.c:264-336
+ *   gl_full_laplacian <- ComputeEntireLaplacianMatrix      hpc/laplacian.c:44-65
+ *   gl_full_result    <- ComputeResultFromEntireLaplacian  hpc/display.c:128-149:  z = clip(y - L y, 0, 255) */
+GL_API int gl_full_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K);
+GL_API int gl_full_laplacian(gl_ctx* ctx, gl_mat* K, gl_mat** L);
+GL_API int gl_full_result(gl_ctx* ctx, gl_mat* L, float* z_f32, uint8_t* z_u8);
 
 /* ---- whole path in one call (what hpc/image_processing.c:183-277 sequences) ------------------- */
 GL_API int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, const gl_params* prm,

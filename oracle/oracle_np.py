@@ -325,6 +325,27 @@ def run_pipeline(img, sample_indices, m=None, kind=BILATERAL, h_loc=40.0, h_val=
     return out
 
 
+def run_full(img, kind=BILATERAL, h_loc=40.0, h_val=30.0, chunk=2048):
+    """The reference's -no_approx mode in fp64: K is the n x n affinity of ALL pixels (hpc/affinity.c:264-336),
+    D = K.1, alpha = 1/mean(D), L = alpha (diag D - K) (hpc/laplacian.c:44-65), z = y - L y clipped to [0, 255]
+    (hpc/display.c:128-149).  Rows of K are formed in chunks; O(n^2) time, small images only."""
+    imgc = _as_hwc(img)
+    H, W, C = imgc.shape
+    n = H * W
+    y = imgc.reshape(n, C).astype(np.float64)
+    allpx = np.arange(n)
+    D = np.empty(n)
+    Ky = np.empty((n, C))
+    for a in range(0, n, chunk):
+        K = affinity_rows(imgc, allpx[a:a + chunk], allpx, kind, h_loc, h_val)
+        D[a:a + chunk] = K.sum(axis=1)
+        Ky[a:a + chunk] = K @ y
+    alpha = 1.0 / D.mean()
+    z = y - alpha * (D[:, None] * y - Ky)
+    z = np.clip(z, 0.0, 255.0).reshape(H, W, C)
+    return dict(D=D, alpha=alpha, z=z[:, :, 0] if np.asarray(img).ndim == 2 else z)
+
+
 def quantise(z):
     """OneColMat2pngbytes (hpc/utils.c:492-534) casts double -> png_byte; negative
     inputs are UB there, so the build clamps to [0,255] then truncates

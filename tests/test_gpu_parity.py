@@ -111,7 +111,7 @@ def test_eigensolver(ctx, p):
     assert got.shape == (m,)
     assert np.all(np.diff(got) >= 0)
     err_mu = float(np.max(np.abs(got - w[:m]) / w[:m]))
-    assert err_mu < 1e-8, err_mu                      # fp64 Rayleigh quotients on fp32 vectors
+    assert err_mu < 1e-7, err_mu                      # fp64 Rayleigh quotients on fp32 vectors (north_star asks for 1e-4)
     assert np.allclose(mu_inv.download(), 1.0 / got, rtol=1e-12)
     Ug = U.download()
     assert Ug.shape == (p, m)
@@ -322,6 +322,31 @@ def test_kb_cutoff_blocks(ctx):
     refp = oc.run_pipeline(img, s, h_loc=h_loc)
     assert np.max(np.abs(out[1]["mu"] - refp["mu"]) / refp["mu"]) <= TOL_MU
     assert _rel(out[1]["z"], refp["z"]) <= TOL_Z and _rel(out[1]["z"] - img, refp["z"] - img) <= TOL_DZ
+
+
+@pytest.mark.parametrize("W,H,ch,kind,h_loc,h_val", [
+    (96, 64, 1, "bilateral", 6.0, 30.0),        # window (r_c = 28) smaller than the image: the cutoff is exercised
+    (61, 47, 1, "bilateral", 40.0, 30.0),       # reference constants: window covers the whole image
+    (50, 40, 3, "bilateral", 5.0, 25.0),
+    (64, 48, 1, "photometric", 40.0, 10.0),     # no spatial term: O(n^2)
+    (40, 33, 1, "spatial", 4.0, 30.0),
+])
+def test_full_no_approx_path(ctx, W, H, ch, kind, h_loc, h_val):
+    """-no_approx (hpc/affinity.c:264-336, laplacian.c:44-65, display.c:128-149), matrix-free on the device, against
+    the dense fp64 oracle."""
+    img = o.synthetic_image(W, H, ch, seed=W * H)
+    ctx.set_image(img)
+    K = ctx.full_affinity(kind, h_loc, h_val)
+    L = ctx.full_laplacian(K)
+    alpha = L.info.scale
+    z, z8 = ctx.full_result(L, want_u8=True)
+    ref = o.run_full(img, kind, h_loc, h_val)
+    assert abs(alpha - ref["alpha"]) <= 2e-6 * ref["alpha"]
+    err_z, err_dz = _rel(z, ref["z"]), _rel(z - img, ref["z"] - img)
+    print(f"full {W}x{H}x{ch} {kind}: err_alpha={abs(alpha - ref['alpha']) / ref['alpha']:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_z <= TOL_Z and err_dz <= TOL_DZ
+    assert z.min() >= 0.0 and z.max() <= 255.0
+    assert np.array_equal(z8, z.astype(np.uint8))
 
 
 def test_filter_options(ctx, golden):

@@ -218,6 +218,12 @@ def test_binary_options(golden, tmp_path):
     # missing -f: message and exit(1) (hpc/image_processing.c:88-92)
     r = subprocess.run([BIN], capture_output=True, text=True, cwd=str(tmp_path))
     assert r.returncode == 1 and "No filename found (option -f)" in r.stderr
-    # -no_approx is declared out of scope: it says so and still exits cleanly without an output image
-    r = _run_bin(tmp_path, ["-f", src, "-no_approx"])
-    assert "not part of this build" in r.stderr
+    # -no_approx (hpc/image_processing.c:155-181): the full-matrix mode, matrix-free here; small image, narrow kernel
+    small = o.synthetic_image(72, 56, 1, seed=9)
+    PIL.fromarray(small).save(src)
+    r = _run_bin(tmp_path, ["-f", src, "-no_approx", "-h_loc", "5", "-o", out])
+    for line in ("Computing entire affinity matrix... ", "Computing entire Laplacian matrix... ", "Computing output image... "):
+        assert line in r.stdout
+    ref = o.run_full(small, "bilateral", 5.0, 30.0)
+    z8 = np.asarray(PIL.open(out)).astype(np.int32)
+    assert np.max(np.abs(z8 - ref["z"].astype(np.uint8).astype(np.int32))) <= 1

@@ -120,3 +120,22 @@ def test_band_sample_is_a_restriction(golden):
     z = r["z"]
     assert np.array_equal(z[:20], img[:20].astype(np.float64)) and np.array_equal(z[60:], img[60:].astype(np.float64))
     assert not np.array_equal(z[20:60], img[20:60].astype(np.float64))
+
+
+def test_full_path_oracle_identities():
+    """run_full (the -no_approx restatement): rows of L = alpha (D - K) sum to zero, so a constant image is a fixed point;
+    and the streamed form y - alpha (D y - K y) equals the explicit y - L y."""
+    from oracle import oracle_np as o
+    img = o.synthetic_image(24, 18, 1, seed=2)
+    r = o.run_full(img, "bilateral", 6.0, 30.0)
+    n = img.size
+    K = o.affinity_rows(img, np.arange(n), np.arange(n), "bilateral", 6.0, 30.0)
+    D = K.sum(axis=1)
+    alpha = 1.0 / D.mean()
+    L = alpha * (np.diag(D) - K)
+    assert np.allclose(L.sum(axis=1), 0.0, atol=1e-12)
+    y = img.reshape(-1).astype(np.float64)
+    assert np.allclose(np.clip(y - L @ y, 0, 255).reshape(img.shape), r["z"], rtol=0, atol=1e-9)
+    assert abs(r["alpha"] - alpha) < 1e-15
+    flat = np.full((10, 12), 77, dtype=np.uint8)
+    assert np.allclose(o.run_full(flat)["z"], 77.0)
