@@ -437,12 +437,11 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
-    float* w_s = (float*)(bars + 32);   // after the 256-byte barrier block: the filter weights (FC > 0 only)
+    float* w_s = (float*)(bars + 32);   // after the 256-byte barrier block (FC > 0 only): per epilogue warp, the filter
+                                        // weights of the columns it drains in the current tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = m_tiles * n_tiles;
-    if (FC > 0)
-        for (int i = threadIdx.x; i < n_total * FC; i += blockDim.x) w_s[i] = fuse_w[i];
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -556,13 +555,22 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int c_lo = ch * (n_size / SHARES), c_hi = c_lo + n_size / SHARES;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+            const bool split = n_size >= 64 * SHARES;
+            const int c_base = split ? c_lo : 0;
+            float* w_mine = w_s + (size_t)(warp - 4) * (MAX_BLOCK_N / SHARES) * (FC > 0 ? FC : 1);
+            if (FC > 0) {
+                // this warp's slice of the weights for this tile, fetched while the MMAs of the tile are still running
+                const int ncols = split ? n_size / SHARES : (ch == 0 ? n_size : 0);
+                const float* src = fuse_w + (size_t)(nt * block_n + c_base) * FC;
+                for (int i = lane; i < ncols * FC; i += 32) w_mine[i] = __ldg(src + i);
+                __syncwarp();
+            }
             mbar_wait(bar_tfull + 8 * acc, acc_phase, err, 4);
             tcgen05_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * MAX_BLOCK_N);
             float dot[FC > 0 ? FC : 1];
 #pragma unroll
             for (int q = 0; q < (FC > 0 ? FC : 1); ++q) dot[q] = 0.f;
-            const bool split = n_size >= 64 * SHARES;
             const int c_end = split ? c_hi : (ch == 0 ? n_size : 0);
             for (int c0 = (split ? c_lo : 0); c0 < c_end; c0 += 64) {
                 uint8_t* slab = slab0 + buf * C_SLAB_BYTES;
@@ -599,7 +607,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             pk[i] = pack_h2(__uint_as_float(v[h][2 * i]) * sc, __uint_as_float(v[h][2 * i + 1]) * sc);
                         if (FC > 0) {
                             // 32 columns starting at nt * block_n + c0 + 32 h; weights read as broadcast float4s
-                            const float4* wv = (const float4*)(w_s + (size_t)(nt * block_n + c0 + 32 * h) * FC);
+                            const float4* wv = (const float4*)(w_mine + (size_t)(c0 - c_base + 32 * h) * FC);
 #pragma unroll
                             for (int g8 = 0; g8 < 4; ++g8) {   // 8 columns = 8 * FC floats = 2 * FC float4
                                 float wr[8 * (FC > 0 ? FC : 1)];
@@ -745,12 +753,12 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     const int pf = short_k ? ctx->gemm_prefetch : 0;   // with long K loops the ring already covers the latency; prefetch only adds L2 churn
     const bool deep = !(ctx->gemm_stages == 3 || (ctx->gemm_stages == 0 && short_k));
     const int FCH = fuse ? fuse->C : 0;
-    const int w_bytes = FCH * n_pad * (int)sizeof(float);
+    const int w_bytes = FCH * 4 * tc::MAX_BLOCK_N * (int)sizeof(float);   // per epilogue warp: its columns of one tile
     if (fuse) {
         GL_REQUIRE(!addend && (FCH == 1 || FCH == 3), "gemm: fused filter wants 1 or 3 channels and no addend");
         GL_REQUIRE(ctx->gemm_impl == 0, "gemm: the CUDA-core checker has no fused filter");
         GL_REQUIRE((deep ? tc::smem_bytes<4, 1, 4>() : tc::smem_bytes<3, 2, 8>()) + w_bytes <= tc::SMEM_LIMIT,
-                   "gemm: no shared memory left for %d filter weights", FCH * n_pad);
+                   "gemm: no shared memory left for the filter weights");
         fuse->parts = n_tiles * (deep ? 1 : 2);
     }
     const float* fw = fuse ? fuse->w : nullptr;
