@@ -128,7 +128,7 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    band_rows = max(4, min(height, int(round(16 * (3840.0 * 1000 * 1000) / (width * p_req * p_req)))))
+    band_rows = max(4, min(height, int(round(64 * (3840.0 * 1000 * 1000) / (width * p_req * p_req)))))
     vals, last = [], None
     for i in range(args.warmup + args.steps):
         cb, _ = cpu_sample(width, height, channels, p_req, sampling, affinity, band_rows)
@@ -306,7 +306,7 @@ def main():
     aff_ext_tf = (f_aff + f_ext) / ((med["k_affinity_b"] + med["k_gemm"]) * 1e-3) / 1e12
 
     # ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
-    NCU_TRAFFIC = {("c4", 1, "cutoff"): (20.40e9, "profiles/r01_ncu_full_c4_v3.txt"),
+    NCU_TRAFFIC = {("c4", 1, "cutoff"): (20.74e9, "profiles/r01_ncu_full_c4_v4.txt"),
                    ("c4", 1, "dense"): (33.9e9, "profiles/r01_ncu_full_c4.txt")}
     kept = stored_blocks / max(1, dense_blocks)
     if kept < 0.5:
@@ -362,7 +362,7 @@ def main():
                stage_ms={k: round(v, 4) for k, v in stage.items()},
                kernel_ms_median={k: round(v, 4) for k, v in med.items()})
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        band_rows = max(4, min(height, int(round(16 * (3840.0 * 1000 * 1000) / (width * p_req * p_req)))))
+        band_rows = max(4, min(height, int(round(64 * (3840.0 * 1000 * 1000) / (width * p_req * p_req)))))
         cb, _ = cpu_sample(width, height, channels, p_req, sampling, affinity, band_rows)
         out["cpu_baseline"] = cb
     ctx.close()
