@@ -1,7 +1,2 @@
-/* Same entry points as the reference's hpc/eigendecomposition.h:3-4. */
-#ifndef GLB200_EIGENDECOMPOSITION_H
-#define GLB200_EIGENDECOMPOSITION_H
-#include "petsc_compat.h"
-void EigendecompositionLargest(Mat A, const PetscInt num_eigenpairs, Mat* eigenvectors, Mat* eigenvalues, Mat* eigenvalues_inv);
-void EigendecompositionSmallest(Mat A, const PetscInt num_eigenpairs, Mat* eigenvectors, Mat* eigenvalues, Mat* eigenvalues_inv);
-#endif
+/* Compatibility header: code written against the reference includes "eigendecomposition.h"; the declarations live in hpc_api.h. */
+#include "hpc_api.h"

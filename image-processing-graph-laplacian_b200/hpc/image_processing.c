@@ -35,22 +35,50 @@ static double StageClock(void)
     return GLHostWtime();
 }
 
-static void GetFilePath(char* const filename)
+/* Everything the reference reads from the PETSc options database while it runs (hpc/image_processing.c:82-153),
+ * parsed once up front.  Same defaults and the same stderr notes. */
+typedef struct RunOptions {
+    char input[PETSC_MAX_PATH_LEN];   /* -f (or "synthetic WxH") */
+    char output[PETSC_MAX_PATH_LEN];  /* -o, default results/output.png */
+    int num_eigvals;                  /* -num_eigvals, -1 when absent: resolved against the sample count later */
+    int no_approx, use_slepc;         /* -no_approx, -use_slepc */
+    int opti_gs;                      /* -opti_gs, values < 1 become 1 (:134-138) */
+    double inv_it_epsilon;            /* -inv_it_epsilon, default 0.1 (:148-152) */
+} RunOptions;
+
+static void ParseRunOptions(RunOptions* o)
 {
+    memset(o, 0, sizeof *o);
     if (g_opt.synthetic_w > 0 && g_opt.synthetic_h > 0) {
-        snprintf(filename, PETSC_MAX_PATH_LEN, "synthetic %dx%d", g_opt.synthetic_w, g_opt.synthetic_h);
-        return;
-    }
-    if (!OptionsGetString("-f", filename, PETSC_MAX_PATH_LEN)) {
-        if (GLHostRank() == 0) fprintf(stderr, "No filename found (option -f)\n");
+        snprintf(o->input, sizeof o->input, "synthetic %dx%d", g_opt.synthetic_w, g_opt.synthetic_h);
+    } else if (!OptionsGetString("-f", o->input, sizeof o->input)) {
+        if (GLHostRank() == 0) fprintf(stderr, "No filename found (option -f)\n");   /* :88-92 */
         GLHostFinalize();
         exit(1);
     }
+    if (!OptionsGetString("-o", o->output, sizeof o->output)) strcpy(o->output, "results/output.png");
+    if (!OptionsGetInt("-num_eigvals", &o->num_eigvals)) o->num_eigvals = -1;
+    o->no_approx = OptionsHasName("-no_approx");
+    o->use_slepc = OptionsHasName("-use_slepc");
+    if (!OptionsGetInt("-opti_gs", &o->opti_gs) || o->opti_gs < 1) o->opti_gs = 1;
+    if (!OptionsGetScalar("-inv_it_epsilon", &o->inv_it_epsilon)) o->inv_it_epsilon = 0.1;
+}
+
+/* m = -num_eigvals, or sample_size - 1 with the reference's note on stderr when absent or out of range (:96-108) */
+static PetscInt ResolveEigenpairCount(const RunOptions* o, const unsigned int sample_size)
+{
+    int m = o->num_eigvals;
+    if (m < 0 || m >= (int)sample_size) {
+        m = (int)sample_size - 1;
+        if (GLHostRank() == 0)
+            fprintf(stderr, "Invalid or invalid number of eigenvalues found (option -num_eigvals), so using %d\n", m);
+    }
+    return m;
 }
 
 /* Every rank ends up with the whole image, as after the reference's ReadAndBcastImage (:45-76).  The ranks are
  * processes of one box, so each decodes the file itself instead of receiving `height` broadcasts. */
-static int ReadImageOnEveryRank(const char* const filename, png_bytep** const img_bytes, int* const width, int* const height)
+static int LoadImageOnEveryRank(const RunOptions* o, png_bytep** const img_bytes, int* const width, int* const height)
 {
     if (g_opt.synthetic_w > 0 && g_opt.synthetic_h > 0) {
         const int w = g_opt.synthetic_w, h = g_opt.synthetic_h, ch = g_opt.color ? 3 : 1;
@@ -68,34 +96,8 @@ static int ReadImageOnEveryRank(const char* const filename, png_bytep** const im
         *height = h;
         return 0;
     }
-    if (g_opt.color) return read_png_rgb(filename, img_bytes, width, height, NULL);
-    return read_png(filename, img_bytes, width, height);
-}
-
-static PetscInt GetNumberEigenvalues(const unsigned int sample_size)
-{
-    int num_eigvals = 0;
-    const int found = OptionsGetInt("-num_eigvals", &num_eigvals);
-    if (!found || num_eigvals < 0 || num_eigvals >= (int)sample_size) {
-        num_eigvals = (int)sample_size - 1;
-        if (GLHostRank() == 0)
-            fprintf(stderr, "Invalid or invalid number of eigenvalues found (option -num_eigvals), so using %d\n", num_eigvals);
-    }
-    return num_eigvals;
-}
-
-static PetscInt GetOptiGramSchmidt(void)
-{
-    int value = 1;
-    if (!OptionsGetInt("-opti_gs", &value) || value < 1) value = 1;
-    return value;
-}
-
-static PetscScalar GetInverseIterationEpsilon(void)
-{
-    double epsilon = 0.1;
-    if (!OptionsGetScalar("-inv_it_epsilon", &epsilon)) epsilon = 0.1;
-    return epsilon;
+    if (g_opt.color) return read_png_rgb(o->input, img_bytes, width, height, NULL);
+    return read_png(o->input, img_bytes, width, height);
 }
 
 /* -no_approx (hpc/image_processing.c:155-181), same three stages and stdout lines; the N x N matrices are matrix-free */
@@ -119,14 +121,14 @@ static png_bytep* EntireComputation(const png_bytep* const img_bytes, const unsi
     return out;
 }
 
-static png_bytep* ApproximationComputation(png_bytep* img_bytes, const unsigned int width, const unsigned int height)
+static png_bytep* ApproximationComputation(const RunOptions* o, png_bytep* img_bytes, const unsigned int width, const unsigned int height)
 {
     unsigned int p = g_opt.sample_size ? g_opt.sample_size : (unsigned int)(width * height * 0.01); /* 1 %, :187 */
     unsigned int* sample_indices = NULL; /* ascending */
     Sampling(width, height, &p, &sample_indices);
     GLHostPrintf("Sample size: %d\n", p);
 
-    const PetscInt m = GetNumberEigenvalues(p);
+    const PetscInt m = ResolveEigenpairCount(o, p);
 
     double t0 = StageClock();
     GLHostPrintf("Computing affinity matrices... ");
@@ -145,12 +147,11 @@ static png_bytep* ApproximationComputation(png_bytep* img_bytes, const unsigned 
     t0 = StageClock();
     Mat eigvals, eigvecs_A;
     GLHostPrintf("Computing %d smallest eigenvalues... ", m);
-    if (OptionsHasName("-use_slepc")) {
+    if (o->use_slepc) {
         EigendecompositionSmallest(L_A, m, &eigvecs_A, &eigvals, NULL);
     } else {
-        const PetscScalar epsilon = GetInverseIterationEpsilon();
-        GLHostPrintf("(epsilon: %g) ", epsilon);
-        InversePowerIteration(L_A, m, &eigvecs_A, &eigvals, GetOptiGramSchmidt(), epsilon);
+        GLHostPrintf("(epsilon: %g) ", o->inv_it_epsilon);
+        InversePowerIteration(L_A, m, &eigvecs_A, &eigvals, o->opti_gs, o->inv_it_epsilon);
     }
     GLHostPrintf("%fs\n", StageClock() - t0);
     WriteDiagMat(eigvals, "results/eigenvalues_laplacian.txt");
@@ -192,8 +193,7 @@ static png_bytep* ApproximationComputation(png_bytep* img_bytes, const unsigned 
 
 int main(int argc, char** argv)
 {
-    char filename[PETSC_MAX_PATH_LEN];
-    char outname[PETSC_MAX_PATH_LEN];
+    RunOptions opt;
     PetscMPIInt rank, size;
 
     if (GLHostInit(argc, argv, &rank, &size)) {
@@ -203,32 +203,30 @@ int main(int argc, char** argv)
     const double start_time = GLHostWtime();
     if (rank == 0) mkdir("results", 0777); /* the reference expects results/ to exist (it ships a .gitkeep there) */
     GLHostPrintf("Running with %d processes\n", size);
-    GetFilePath(filename);
-    if (!OptionsGetString("-o", outname, sizeof outname)) strcpy(outname, "results/output.png");
+    ParseRunOptions(&opt);
 
     int width = 0, height = 0;
     png_bytep *img_bytes = NULL, *output_img = NULL;
-    if (ReadImageOnEveryRank(filename, &img_bytes, &width, &height)) {
+    if (LoadImageOnEveryRank(&opt, &img_bytes, &width, &height)) {
         GLHostFinalize();
         return 1;
     }
-    GLHostPrintf("Read image %s of size %dx%d => %d pixels\n", filename, width, height, width * height);
+    GLHostPrintf("Read image %s of size %dx%d => %d pixels\n", opt.input, width, height, width * height);
 
-    if (OptionsHasName("-no_approx")) output_img = EntireComputation(img_bytes, width, height);
-    else output_img = ApproximationComputation(img_bytes, width, height);
+    output_img = opt.no_approx ? EntireComputation(img_bytes, width, height) : ApproximationComputation(&opt, img_bytes, width, height);
 
     if (rank == 0) {
         if (g_opt.color) write_png_rgb("results/input.png", img_bytes, width, height);
         else write_png("results/input.png", img_bytes, width, height);
         if (output_img) {
-            if (g_opt.color) write_png_rgb(outname, output_img, width, height);
-            else write_png(outname, output_img, width, height);
+            if (g_opt.color) write_png_rgb(opt.output, output_img, width, height);
+            else write_png(opt.output, output_img, width, height);
         }
     }
 
     const double total = GLHostWtime() - start_time;
     GLHostPrintf("Total computation time: %fs\n", total);
-    if (rank == 0 && output_img && !OptionsHasName("-no_approx")) {
+    if (rank == 0 && output_img && !opt.no_approx) {
         float ms[GL_T_COUNT];
         if (gl_ctx_stage_ms(GLHostContext(), ms) == GL_OK) {
             const float dev = ms[GL_T_SAMPLING] + ms[GL_T_AFFINITY] + ms[GL_T_LAPLACIAN] + ms[GL_T_EIGEN] + ms[GL_T_NYSTROEM] +

@@ -1,7 +1,2 @@
-/* Same entry point as the reference's hpc/inverse_power_it.h:3. */
-#ifndef GLB200_INVERSE_POWER_IT_H
-#define GLB200_INVERSE_POWER_IT_H
-#include "petsc_compat.h"
-void InversePowerIteration(const Mat A, const unsigned int p, Mat* eigenvectors, Mat* eigenvalues, PetscBool optiGramSchmidt,
-                           PetscScalar epsilon);
-#endif
+/* Compatibility header: code written against the reference includes "inverse_power_it.h"; the declarations live in hpc_api.h. */
+#include "hpc_api.h"
