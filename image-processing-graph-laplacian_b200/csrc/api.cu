@@ -120,6 +120,12 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         if (!strcmp(value, "warp")) ctx->filter_apply_impl = 0;
         else if (!strcmp(value, "generic")) ctx->filter_apply_impl = 1;
         else GL_REQUIRE(false, "option filter_apply: want warp|generic, got %s", value);
+    } else if (!strcmp(key, "gram")) {
+        if (!strcmp(value, "tcgen05")) ctx->gram_impl = 0;
+        else if (!strcmp(value, "simple")) ctx->gram_impl = 1;
+        else GL_REQUIRE(false, "option gram: want tcgen05|simple, got %s", value);
+    } else if (!strcmp(key, "gram_lbo")) {
+        ctx->gram_lbo = atoi(value);
     } else if (!strcmp(key, "gemm_stages")) {
         ctx->gemm_stages = atoi(value);
         GL_REQUIRE(ctx->gemm_stages == 0 || ctx->gemm_stages == 3 || ctx->gemm_stages == 4, "option gemm_stages: want 0|3|4");

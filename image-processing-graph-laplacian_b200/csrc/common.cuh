@@ -152,6 +152,8 @@ struct gl_ctx {
     // options
     int gemm_impl = 0;        // 0 = tcgen05 (default), 1 = simple CUDA-core checker kernel
     int gemm_cta_group = 1;   // 1 or 2
+    int gram_impl = 0;        // orthonormalise: 0 = tcgen05 Gram when m_pad % 256 == 0, 1 = always the CUDA-core tiles
+    int gram_lbo = 8192;      // leading byte offset of the MN-major operand descriptors (tuning/debug)
     int gemm_stages = 0;      // 0 = automatic, 3 | 4 = force that ring depth (tuning)
     int gemm_prefetch = 2;    // blocked A: L2-prefetch the A blocks of the tile this many iterations ahead (0 = off)
     int eig_largest = 0;      // 1: keep the m LARGEST eigenpairs (descending) instead of the smallest (ascending)

@@ -15,9 +15,7 @@
 //   * every pixel's row is written at its raster position, so there is no permutation pass; the p sample
 //     rows are then overwritten with Phi_A (nystroem.c:25-34).
 // A plain CUDA-core kernel (option gemm=simple) computes the same thing for cross-checking in tests.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // W^T build
@@ -259,14 +257,8 @@ __global__ void __launch_bounds__(256) k_gemm_simple_blocked(const __half* __res
 // ---------------------------------------------------------------------------------------------
 namespace tc {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;       // 64 fp16 = 128 bytes = one SWIZZLE_128B row
-constexpr int MAX_BLOCK_N = 256;
 constexpr int MAX_STAGES = 4;
-constexpr int UMMA_K = 16;
 constexpr int MAX_THREADS = 384;   // warps 0-3: producer, MMA issuer, TMEM allocator, idle; then 4 or 8 epilogue warps
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KB
-constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int C_SLAB_BYTES = 32 * 128;                     // 32 rows x 64 bf16
 // two shapes of the shared-memory budget (227 KB): a deep operand ring for long K loops (dense A, the epilogue has
 // slack: one store slab per epilogue warp), or a shorter ring with double-buffered store slabs for the short K loops of
@@ -275,141 +267,6 @@ template <int STAGES, int CBUFS, int EPI_WARPS>
 constexpr int smem_bytes()
 {
     return STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_WARPS * CBUFS * C_SLAB_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
-}
-constexpr int SMEM_LIMIT = 227 * 1024;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a pipeline bug must end in a trap (a CUDA error the host reports), never in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code)
-{
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {  // ~2 s
-            if (err) atomicExch(err, code);
-            __threadfence_system();
-            asm volatile("trap;");
-        }
-    }
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-// L2 prefetch of a tile (no shared-memory destination): used to pull the A blocks of tiles a few iterations ahead out
-// of HBM early, which buys prefetch depth the shared-memory ring cannot hold
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
-                 "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read()
-{
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void tma_store_wait_all()
-{
-    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);  // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell), bits [46,48)
-    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B, bits [61,64)
-    return d;
-}
-// kind::f16 instruction descriptor: (fp16 x fp16 | bf16 x bf16) -> fp32, both operands K-major
-__device__ __forceinline__ uint32_t make_idesc(int M, int N, uint32_t ab_format /* 0 = f16, 1 = bf16 */)
-{
-    uint32_t d = 0;
-    d |= 1u << 4;                     // D format: f32
-    d |= ab_format << 7;              // A format
-    d |= ab_format << 10;             // B format
-    d |= (uint32_t)(N >> 3) << 17;    // N / 8
-    d |= (uint32_t)(M >> 4) << 24;    // M / 16
-    return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t pack_h2(float lo, float hi)
-{
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *(uint32_t*)&v;
-}
-__device__ __forceinline__ float2 unpack_h2(uint32_t w)
-{
-    return __half22float2(*(const __half2*)&w);
 }
 
 // One persistent CTA per SM.  warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator,
@@ -666,46 +523,6 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode()
-{
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
-    return fn;
-}
-
-// 2-D row-major 16-bit tensor [rows][cols] (cols contiguous), box = box_cols x box_rows, SWIZZLE_128B
-static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                       uint32_t box_cols, uint32_t box_rows)
-{
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) {
-        gl_set_error("cuTensorMapEncodeTiled is not available from the driver");
-        return GL_ERR_CUDA;
-    }
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld_elems * 2};
-    cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        gl_set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r, (unsigned long long)rows,
-                     (unsigned long long)cols, (unsigned long long)ld_elems, box_cols, box_rows);
-        return GL_ERR_CUDA;
-    }
-    return GL_OK;
-}
-
 // D[rows][n_pad] (fp16) = scales[1] * A[rows][k_pad] . Bt[n_pad][k_pad]^T (+ addend), A and Bt 16-bit K-major
 // (ab_bf16: 0 = fp16, 1 = bf16).  k_pad % 64 == 0; n_pad is 64, 128 or a multiple of 256 (gl_m_pad).
 int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,

@@ -175,6 +175,37 @@ def test_gram_schmidt_stage(ctx, golden, tag):
     assert err_dz <= TOL_DZ, err_dz
 
 
+@pytest.mark.parametrize("gram", ["tcgen05", "simple"])
+def test_gram_schmidt_wide_phi(ctx, gram):
+    """m_pad = 256: the Gram matrix comes from the tcgen05 kernel with MN-major operands (option gram=simple: the
+    CUDA-core tiles); blocked Cholesky + triangular inverse; against the oracle's column-by-column Gram-Schmidt."""
+    W, H, p = 320, 200, 200
+    img = o.synthetic_image(W, H, 1, seed=11)
+    s = oc.random_sampling(W, H, p, 4)
+    ref = o.run_pipeline(img, s, orthonormalise=True, return_phi=True)
+    _, nref = o.gram_schmidt(o.run_pipeline(img, s, return_phi=True)["phi"])
+    ctx.set_option("gram", gram)
+    try:
+        ctx.set_image(img)
+        ctx.set_samples(s)
+        K_A, K_B = ctx.affinity()
+        L_A, L_B = ctx.laplacian(K_A, K_B)
+        U, mu, mu_inv = ctx.eigensolve(L_A, -1)
+        phi = ctx.nystroem(L_B, U, mu_inv)
+        assert phi.info.ld == 256
+        norms = ctx.orthonormalise(phi)
+        Q = phi.download()
+        z = ctx.filter(phi, mu)
+    finally:
+        ctx.set_option("gram", "tcgen05")
+    err_q = float(np.max(np.abs(Q.T @ Q - np.eye(Q.shape[1]))))
+    err_n = float(np.max(np.abs(norms - nref) / nref))
+    err_z, err_dz = _rel(z, ref["z"]), _rel(z - img, ref["z"] - img)
+    print(f"gs wide ({gram}): orth={err_q:.2e} norms={err_n:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_q < 1e-3 and err_n < 2e-3
+    assert err_z <= TOL_Z and err_dz <= TOL_DZ
+
+
 def test_stage_by_stage_phi_properties(ctx, golden):
     g = golden("cat_small_random50")
     img, s = g["image"], g["sample_indices"]
