@@ -43,8 +43,9 @@ png_bytep* ComputeResultFromLaplacian(const png_bytep* const img_bytes, Mat phi,
         exit(1);
     }
     if (gl_filter(GLHostContext(), phi, Pi, g_opt.filter_gain, 0, NULL, shared[0]) != GL_OK) GLHostFatal("ComputeResultFromLaplacian");
+    GLHostBandDone();
     if (GLHostRank() != 0) return NULL;
-    GLHostBarrierAtExit();  /* the other ranks have written their bands once they exit */
+    GLHostWaitBands();
     png_bytep* out = (png_bytep*)malloc(sizeof(png_bytep) * height);
     for (unsigned int i = 0; i < height; ++i) {
         out[i] = (png_bytep)malloc(row_bytes);
@@ -64,8 +65,9 @@ png_bytep* ComputeResultFromEntireLaplacian(const png_bytep* const img_bytes, Ma
         exit(1);
     }
     if (gl_full_result(GLHostContext(), Lapl, NULL, shared[0]) != GL_OK) GLHostFatal("ComputeResultFromEntireLaplacian");
+    GLHostBandDone();
     if (GLHostRank() != 0) return NULL;
-    GLHostBarrierAtExit();
+    GLHostWaitBands();
     png_bytep* out = (png_bytep*)malloc(sizeof(png_bytep) * height);
     for (unsigned int i = 0; i < height; ++i) {
         out[i] = (png_bytep)malloc(row_bytes);

@@ -16,6 +16,7 @@ static char** g_argv;
 static gl_ctx* g_ctx = NULL;
 static int g_rank = 0, g_size = 1;
 static pid_t g_children[64];
+static volatile int* g_bands_done = NULL;   /* shared counter: ranks that have written their band of the output image */
 static unsigned char* g_shared = NULL;
 static size_t g_shared_bytes = 0;
 static png_bytep* g_shared_rows = NULL;
@@ -126,6 +127,7 @@ int GLHostInit(int argc, char** argv, int* rank, int* size)
     unsigned char* id = (unsigned char*)mmap(NULL, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     if (id == MAP_FAILED) return 1;
     volatile int* id_ready = (volatile int*)(id + 256);
+    g_bands_done = (volatile int*)(id + 512);
     g_shared_bytes = (size_t)1 << 31;  /* reserve 2 GiB of address space; pages are touched on demand */
     g_shared = (unsigned char*)mmap(NULL, g_shared_bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (g_shared == MAP_FAILED) return 1;
@@ -161,21 +163,41 @@ png_bytep* GLHostSharedImage(unsigned int width, unsigned int height)
     return g_shared_rows;
 }
 
-void GLHostBarrierAtExit(void)
+/* Every rank calls this once its band of the shared output image is written; rank 0 then waits for all of them.
+ * (Not a waitpid: the ranks still have to tear their NCCL communicator down together in GLHostFinalize.) */
+void GLHostBandDone(void)
+{
+    __sync_synchronize();
+    __sync_fetch_and_add((int*)g_bands_done, 1);
+}
+
+void GLHostWaitBands(void)
 {
     if (g_rank != 0) return;
-    for (int r = 1; r < g_size; ++r) {
-        int st = 0;
-        waitpid(g_children[r], &st, 0);
-        if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) fprintf(stderr, "rank %d ended abnormally\n", r);
+    while (*g_bands_done < g_size) {
+        for (int r = 1; r < g_size; ++r) {   /* a rank that died will never report: do not wait for ever */
+            int st = 0;
+            if (waitpid(g_children[r], &st, WNOHANG) == g_children[r]) {
+                fprintf(stderr, "rank %d ended before writing its band\n", r);
+                exit(1);
+            }
+        }
+        usleep(200);
     }
+    __sync_synchronize();
+    *g_bands_done = 0;
 }
 
 void GLHostFinalize(void)
 {
-    if (g_ctx) gl_ctx_destroy(g_ctx);
+    if (g_ctx) gl_ctx_destroy(g_ctx);   /* collective over the ranks of one box (ncclCommDestroy) */
     g_ctx = NULL;
     if (g_rank != 0) _exit(0);
+    for (int r = 1; r < g_size; ++r) {
+        int st = 0;
+        if (g_children[r] > 0 && waitpid(g_children[r], &st, 0) == g_children[r] && (!WIFEXITED(st) || WEXITSTATUS(st) != 0))
+            fprintf(stderr, "rank %d ended abnormally\n", r);
+    }
 }
 
 PetscErrorCode MatDestroy(Mat* m)

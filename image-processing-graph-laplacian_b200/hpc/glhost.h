@@ -34,7 +34,8 @@ int GLHostInit(int argc, char** argv, int* rank, int* size);
 void GLHostFinalize(void);
 /* output image rows shared by all ranks (anonymous shared mapping made before the fork) */
 png_bytep* GLHostSharedImage(unsigned int width, unsigned int height);
-void GLHostBarrierAtExit(void);   /* rank 0: wait for the other ranks */
+void GLHostBandDone(void);        /* every rank: my band of the shared output image is written */
+void GLHostWaitBands(void);       /* rank 0: wait until every rank has reported */
 double GLHostWtime(void);
 void GLHostPrintf(const char* fmt, ...);          /* rank-0 stdout, like PetscPrintf(PETSC_COMM_WORLD, ...) */
 #endif

@@ -151,7 +151,7 @@ def test_host_binary_fails_loudly_without_gpu(tmp_path):
 # the binary on a GPU
 # ---------------------------------------------------------------------------------------------------------------
 def _run_bin(tmp_path, args):
-    r = subprocess.run([BIN] + args, capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    r = subprocess.run([BIN] + args, capture_output=True, text=True, cwd=str(tmp_path), timeout=120)
     assert r.returncode == 0, r.stderr + r.stdout
     return r
 
@@ -227,3 +227,23 @@ def test_binary_options(golden, tmp_path):
     ref = o.run_full(small, "bilateral", 5.0, 30.0)
     z8 = np.asarray(PIL.open(out)).astype(np.int32)
     assert np.max(np.abs(z8 - ref["z"].astype(np.uint8).astype(np.int32))) <= 1
+
+
+@pytest.mark.gpu
+def test_binary_two_ranks(golden, tmp_path):
+    """-ngpus 2: one forked process per GPU (the reference's `mpiexec -n 2`), bands of rows, NCCL id through shared
+    memory, both ranks writing their band into the shared output image."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import oracle_np as o
+    g = golden("barbara_uniform256")
+    src, out = str(tmp_path / "in.png"), str(tmp_path / "o.png")
+    PIL.fromarray(g["image"]).save(src)
+    r = _run_bin(tmp_path, ["-f", src, "-sample_size", "256", "-ngpus", "2", "-o", out])
+    assert "Running with 2 processes" in r.stdout
+    z8 = np.asarray(PIL.open(out)).astype(np.int32)
+    assert np.max(np.abs(z8 - o.quantise(g["z"]).astype(np.int32))) <= 1
+    r = _run_bin(tmp_path, ["-f", src, "-sample_size", "256", "-ngpus", "2", "-gram_schmidt", "-o", out])
+    z8 = np.asarray(PIL.open(out)).astype(np.int32)
+    assert np.max(np.abs(z8 - o.quantise(g["z_gs"]).astype(np.int32))) <= 1
