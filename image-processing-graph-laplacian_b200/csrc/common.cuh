@@ -159,7 +159,7 @@ struct gl_ctx {
     int eig_largest = 0;      // 1: keep the m LARGEST eigenpairs (descending) instead of the smallest (ascending)
     int jacobi_max_sweeps = 40;
     int jacobi_inner = 1;     // inner 16 x 16 Jacobi sweeps per pair visit (0 = until converged, at most 12); 1 is enough: the outer sweeps repeat
-    float jacobi_tol = 1e-5f;  // largest relative off-diagonal of G^T G at convergence (eigenvalues are refined by fp64 Rayleigh quotients)
+    float jacobi_tol = 2e-5f;  // largest relative off-diagonal of G^T G at convergence (eigenvalues are refined by fp64 Rayleigh quotients)
     int verbose = 0;
 };
 

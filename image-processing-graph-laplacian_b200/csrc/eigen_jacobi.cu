@@ -390,7 +390,8 @@ __global__ void k_jacobi_norms(const float* __restrict__ G, int p, double* __res
 // V is never stored: each CTA emits partial numerators for its 64 columns (fixed-order reduction afterwards).
 __global__ void __launch_bounds__(256) k_rayleigh_partial(const double* __restrict__ A, const float* __restrict__ G, int p,
                                                           double* __restrict__ part /* [row_tiles][cols_pad] */, int cols_pad,
-                                                          int cols /* columns that exist in G */)
+                                                          int cols /* columns that exist in G */,
+                                                          const unsigned char* __restrict__ nz /* [row_tiles][ceil(p/16)] or null */)
 {
     __shared__ double As[16][64 + 1], Us[16][64 + 1];
     __shared__ double red[16][64];
@@ -401,7 +402,9 @@ __global__ void __launch_bounds__(256) k_rayleigh_partial(const double* __restri
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const int nz_ld = (p + 15) >> 4;
     for (int k0 = 0; k0 < p; k0 += 16) {
+        if (nz && !nz[(size_t)blockIdx.y * nz_ld + (k0 >> 4)]) continue;   // this chunk of A is all zeros (block-uniform)
         for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
             const int kk = idx & 15, ii = idx >> 4;          // A[i0+ii][k0+kk], 16 contiguous doubles per row
             const int i = i0 + ii, k = k0 + kk;
@@ -568,7 +571,8 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         {
             dim3 gr((unsigned)ceil_div(cols_pad, 64), (unsigned)row_tiles);
             k_rayleigh_partial<<<gr, 256, 0, ctx->stream>>>((const double*)L_A->buf->ptr, (const float*)G->ptr, p, (double*)part->ptr,
-                                                            cols_pad + 64, cols_pad);
+                                                            cols_pad + 64, cols_pad,
+                                                            L_A->aux ? (const unsigned char*)L_A->aux->ptr : nullptr);
             GL_LAUNCH_CHECK(ctx);
             k_rayleigh_finish<<<(unsigned)ceil_div(p, 128), 128, 0, ctx->stream>>>((const double*)part->ptr, row_tiles, cols_pad + 64, p,
                                                                                    (const double*)lam->ptr, (double*)ray->ptr);

@@ -27,13 +27,17 @@ __global__ void k_alpha(const double* __restrict__ D, int p, double* __restrict_
     }
 }
 
+// also marks which [64 rows x 16 columns] chunks of L_A hold anything but (numerical) zeros: K_A between samples further
+// apart than a few h_loc is < 1e-25, and the eigensolver's fp64 Rayleigh pass skips those chunks (eigen_jacobi.cu)
 __global__ void k_laplacian_A(const double* __restrict__ KA, const double* __restrict__ D, const double* __restrict__ al, int p,
-                              double* __restrict__ LA)
+                              double* __restrict__ LA, unsigned char* __restrict__ nz, int nz_ld)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= p) return;
     const double alpha = al[1];
-    LA[(size_t)i * p + j] = alpha * ((i == j ? D[i] : 0.0) - KA[(size_t)i * p + j]);
+    const double v = alpha * ((i == j ? D[i] : 0.0) - KA[(size_t)i * p + j]);
+    LA[(size_t)i * p + j] = v;
+    if (fabs(v) > 1e-25) nz[(size_t)(i >> 6) * nz_ld + (j >> 4)] = 1;
 }
 
 int gl_impl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A_out, gl_mat** L_B_out)
@@ -45,17 +49,20 @@ int gl_impl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A_out, g
     LA->ld = p;
     LA->elem_bytes = 8;
     gl_buf* al = nullptr;
+    const int nz_ld = (int)ceil_div(p, 16), nz_rows = (int)ceil_div(p, 64);
     int rc = gl_alloc(ctx, sizeof(double) * (size_t)p * p, &LA->buf);
     if (rc == GL_OK) rc = gl_alloc(ctx, 2 * sizeof(double), &al);
+    if (rc == GL_OK) rc = gl_alloc(ctx, (size_t)nz_ld * nz_rows, &LA->aux);   // chunk occupancy map of L_A
     if (rc != GL_OK) {
         gl_mat_destroy(LA);
         return rc;
     }
     k_alpha<<<1, 1024, 0, ctx->stream>>>((const double*)K_B->aux->ptr, p, (double*)al->ptr);
     GL_LAUNCH_CHECK(ctx);
+    GL_CUDA_CHECK(cudaMemsetAsync(LA->aux->ptr, 0, (size_t)nz_ld * nz_rows, ctx->stream));
     dim3 g((unsigned)ceil_div(p, 128), (unsigned)p);
     k_laplacian_A<<<g, 128, 0, ctx->stream>>>((const double*)K_A->buf->ptr, (const double*)K_B->aux->ptr,
-                                             (const double*)al->ptr, p, (double*)LA->buf->ptr);
+                                             (const double*)al->ptr, p, (double*)LA->buf->ptr, (unsigned char*)LA->aux->ptr, nz_ld);
     GL_LAUNCH_CHECK(ctx);
 
     gl_mat* LB = gl_mat_new(ctx, GL_MAT_KB);
