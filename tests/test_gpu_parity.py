@@ -264,6 +264,24 @@ def test_synthetic_against_oracle(ctx, W, H, ch, p, kind, method):
     assert err_dz <= TOL_DZ, err_dz
 
 
+def test_config5_shape_colour_p2000(ctx):
+    """BASELINE config 5's shape on a small image: colour (5-dimensional features), p = 2000 random samples, m = 1999
+    (m_pad = 2048: eight N tiles, three-channel fused filter, 250-panel eigensolve), against the fp64 CPU pipeline
+    (OpenMP kernel rows + LAPACK eigh + BLAS)."""
+    from oracle import cpu_pipeline as cp
+    W, H, p = 480, 320, 2000
+    img = o.synthetic_image(W, H, 3, seed=5)
+    prm = gl.default_params(sampling=gl.RANDOM, sample_size=p, seed=9)
+    r = ctx.run(img, prm)
+    s = oc.random_sampling(W, H, p, 9)
+    assert np.array_equal(ctx.get_samples(), s) and r["m"] == p - 1
+    ref = cp.run(img, s)
+    err_mu = float(np.max(np.abs(r["mu"] - ref["mu"]) / ref["mu"]))
+    err_z, err_dz = _rel(r["z"], ref["z"]), _rel(r["z"] - img, ref["z"] - img)
+    print(f"config-5 shape {W}x{H}x3 p={p}: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_mu <= TOL_MU and err_z <= TOL_Z and err_dz <= TOL_DZ
+
+
 def test_projection_and_apply_variants_agree(ctx, golden):
     """c = Phi^T y from the affinity sums (default) vs the stand-alone pass over Phi; warp-per-row vs generic apply."""
     for tag in ("barbara_uniform256", "lion_rgb_photometric500", "test_uniform100"):
