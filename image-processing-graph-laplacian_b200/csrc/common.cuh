@@ -43,6 +43,23 @@ void gl_set_error(const char* fmt, ...);
         }                                \
     } while (0)
 
+// the same checks for use inside a `do { ... } while (0)` block that owns buffers: record the status and leave the block,
+// so that the clean-up after it runs
+#define GL_CUDA_BREAK(rc, expr)                                                                         \
+    {                                                                                                   \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            gl_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+            (rc) = GL_ERR_CUDA;                                                                         \
+            break;                                                                                      \
+        }                                                                                               \
+    }
+#define GL_BREAK(rc, expr)               \
+    {                                    \
+        (rc) = (expr);                   \
+        if ((rc) != GL_OK) break;        \
+    }
+
 #define GL_LAUNCH_CHECK(ctx)                                                                            \
     do {                                                                                                \
         (ctx)->launches++;                                                                              \

@@ -532,19 +532,19 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)p, &ray)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)row_tiles * (cols_pad + 64), &part)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(unsigned) * (size_t)(max_sweeps + 4), &ctl)) != GL_OK) break;
-        GL_CUDA_CHECK(cudaMemsetAsync(ctl->ptr, 0, sizeof(unsigned) * (size_t)(max_sweeps + 4), ctx->stream));
+        GL_CUDA_BREAK(rc, cudaMemsetAsync(ctl->ptr, 0, sizeof(unsigned) * (size_t)(max_sweeps + 4), ctx->stream));
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)cols_pad * cols_pad, &Cg)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)nb * nb, &prel)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(int) * (size_t)max_sweeps * 2 * nb, &scnt)) != GL_OK) break;
-        GL_CUDA_CHECK(cudaMemsetAsync(scnt->ptr, 0, sizeof(int) * (size_t)max_sweeps * 2 * nb, ctx->stream));
+        GL_CUDA_BREAK(rc, cudaMemsetAsync(scnt->ptr, 0, sizeof(int) * (size_t)max_sweeps * 2 * nb, ctx->stream));
         const int64_t total = (int64_t)nb * p * JB;
         k_jacobi_init<<<(unsigned)ceil_div(total, 256), 256, 0, ctx->stream>>>((const double*)L_A->buf->ptr, p, nb,
                                                                                (float*)G->ptr);
         GL_LAUNCH_CHECK(ctx);
 
-        GL_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GL_CUDA_BREAK(rc, cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        GL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi, J_THREADS, smem));
+        GL_CUDA_BREAK(rc, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi, J_THREADS, smem));
         GL_REQUIRE(per_sm >= 1, "eigensolve: kernel does not fit on an SM");
         const int ctiles = (int)ceil_div(cols_pad, 64);
         int grid = std::max(nb / 2, ctiles * (ctiles + 1) / 2);   // rotation pairs per step / tiles of the Gram screen
@@ -562,7 +562,7 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         void* args[] = {&Gp, &p_, &nb_, &ms, &tol, &inner, &Cp, &prp, &scp, &off, &done};
         {
             StageTimer kt(ctx, GL_T_K_JACOBI);
-            GL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));
+            GL_CUDA_BREAK(rc, cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));
         }
         ctx->launches++;
 
@@ -581,7 +581,7 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         int N = 2;
         while (N < p) N <<= 1;
         GL_REQUIRE(N <= 8192, "eigensolve: p too large for the single-CTA sort");
-        GL_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        GL_CUDA_BREAK(rc, cudaFuncSetAttribute(k_jacobi_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
         k_jacobi_sort<<<1, 1024, (size_t)N * 8, ctx->stream>>>((const double*)ray->ptr, p, N, (int*)order->ptr);
         GL_LAUNCH_CHECK(ctx);
 
@@ -607,10 +607,10 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         GL_LAUNCH_CHECK(ctx);
 
         // convergence report (one small D2H; the solve itself never synchronises with the host)
-        GL_CHECK(gl_ensure_pinned(ctx, sizeof(unsigned) * (size_t)(max_sweeps + 4)));
-        GL_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, ctl->ptr, sizeof(unsigned) * (size_t)(max_sweeps + 4), cudaMemcpyDeviceToHost,
+        GL_BREAK(rc, gl_ensure_pinned(ctx, sizeof(unsigned) * (size_t)(max_sweeps + 4)));
+        GL_CUDA_BREAK(rc, cudaMemcpyAsync(ctx->pinned, ctl->ptr, sizeof(unsigned) * (size_t)(max_sweeps + 4), cudaMemcpyDeviceToHost,
                                       ctx->stream));
-        GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        GL_CUDA_BREAK(rc, cudaStreamSynchronize(ctx->stream));
         const unsigned* h = (const unsigned*)ctx->pinned;
         const int sweeps = (int)h[max_sweeps + 1];   // rotation sweeps done; screen number `sweeps` ended the loop
         float last = 1.f;

@@ -392,12 +392,12 @@ int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int par
         {
             StageTimer t(ctx, GL_T_D2H);
             if (z_f32)
-                GL_CUDA_CHECK(cudaMemcpyAsync(z_f32 + (size_t)phi->q0 * C, z->ptr, sizeof(float) * (size_t)rows * C, cudaMemcpyDeviceToHost,
+                GL_CUDA_BREAK(rc, cudaMemcpyAsync(z_f32 + (size_t)phi->q0 * C, z->ptr, sizeof(float) * (size_t)rows * C, cudaMemcpyDeviceToHost,
                                               ctx->stream));
             if (z_u8)
-                GL_CUDA_CHECK(cudaMemcpyAsync(z_u8 + (size_t)phi->q0 * C, z8->ptr, (size_t)rows * C, cudaMemcpyDeviceToHost, ctx->stream));
+                GL_CUDA_BREAK(rc, cudaMemcpyAsync(z_u8 + (size_t)phi->q0 * C, z8->ptr, (size_t)rows * C, cudaMemcpyDeviceToHost, ctx->stream));
         }
-        if (z_f32 || z_u8) GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (z_f32 || z_u8) GL_CUDA_BREAK(rc, cudaStreamSynchronize(ctx->stream));
     } while (0);
     if (z) gl_buf_release(z);
     if (z8) gl_buf_release(z8);
@@ -486,13 +486,13 @@ int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int
         {
             StageTimer t(ctx, GL_T_D2H);
             if (z_f32)
-                GL_CUDA_CHECK(cudaMemcpyAsync(z_f32 + (size_t)phi->q0 * C, z->ptr, sizeof(float) * (size_t)rows * C,
+                GL_CUDA_BREAK(rc, cudaMemcpyAsync(z_f32 + (size_t)phi->q0 * C, z->ptr, sizeof(float) * (size_t)rows * C,
                                               cudaMemcpyDeviceToHost, ctx->stream));
             if (z_u8)
-                GL_CUDA_CHECK(cudaMemcpyAsync(z_u8 + (size_t)phi->q0 * C, z8->ptr, (size_t)rows * C, cudaMemcpyDeviceToHost,
+                GL_CUDA_BREAK(rc, cudaMemcpyAsync(z_u8 + (size_t)phi->q0 * C, z8->ptr, (size_t)rows * C, cudaMemcpyDeviceToHost,
                                               ctx->stream));
         }
-        if (z_f32 || z_u8) GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (z_f32 || z_u8) GL_CUDA_BREAK(rc, cudaStreamSynchronize(ctx->stream));
     } while (0);
     if (partial) gl_buf_release(partial);
     if (c) gl_buf_release(c);

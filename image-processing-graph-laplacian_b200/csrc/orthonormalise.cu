@@ -411,7 +411,7 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
         if ((rc = gl_alloc(ctx, sizeof(int) * 4, &st)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m_pad, &norms)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * 4, &sc)) != GL_OK) break;
-        GL_CUDA_CHECK(cudaMemsetAsync(st->ptr, 0, sizeof(int) * 4, ctx->stream));
+        GL_CUDA_BREAK(rc, cudaMemsetAsync(st->ptr, 0, sizeof(int) * 4, ctx->stream));
 
         if (tc_gram) {
             CUtensorMap map_phi;
@@ -420,7 +420,7 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
             gl_buf* gerr = nullptr;
             if ((rc = gl_alloc(ctx, sizeof(int) * 4, &gerr)) != GL_OK) break;
             cudaMemsetAsync(gerr->ptr, 0, sizeof(int) * 4, ctx->stream);
-            GL_CUDA_CHECK(cudaFuncSetAttribute(gram::k_gram_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, gram::SMEM_BYTES));
+            GL_CUDA_BREAK(rc, cudaFuncSetAttribute(gram::k_gram_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, gram::SMEM_BYTES));
             int ntiles = 0;
             for (int ti = 0; ti < m_pad / 128; ++ti) ntiles += m_pad / 256 - ti / 2;
             int grid = ctx->sm_count;
@@ -452,7 +452,7 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
                     ctx->launches += 2;
                 }
             }
-            GL_CUDA_CHECK(cudaMemsetAsync(T->ptr, 0, sizeof(double) * (size_t)m_pad * m_pad, ctx->stream));
+            GL_CUDA_BREAK(rc, cudaMemsetAsync(T->ptr, 0, sizeof(double) * (size_t)m_pad * m_pad, ctx->stream));
             k_upper_inverse_blocked<<<nblk, CB * CB, 0, ctx->stream>>>((const double*)G->ptr, m, m_pad, (const double*)Tdiag->ptr,
                                                                        (double*)T->ptr);
             GL_LAUNCH_CHECK(ctx);
@@ -466,11 +466,11 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
         if ((rc = gl_gemm_kmajor(ctx, phi->buf->ptr, 0, rows, m_pad, Et->ptr, m_pad, (const float*)sc->ptr, phi->buf->ptr,
                                  Q->ptr)) != GL_OK) break;
 
-        GL_CHECK(gl_ensure_pinned(ctx, sizeof(double) * (size_t)m_pad + 64));
-        GL_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, st->ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        GL_CUDA_CHECK(cudaMemcpyAsync((char*)ctx->pinned + 64, norms->ptr, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost,
+        GL_BREAK(rc, gl_ensure_pinned(ctx, sizeof(double) * (size_t)m_pad + 64));
+        GL_CUDA_BREAK(rc, cudaMemcpyAsync(ctx->pinned, st->ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GL_CUDA_BREAK(rc, cudaMemcpyAsync((char*)ctx->pinned + 64, norms->ptr, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost,
                                       ctx->stream));
-        GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        GL_CUDA_BREAK(rc, cudaStreamSynchronize(ctx->stream));
         const int status = *(int*)ctx->pinned;
         if (status != 0) {
             gl_set_error("orthonormalise: Gram matrix not positive definite at column %d (Phi rank deficient)", status - 1);

@@ -1,5 +1,6 @@
 #include "glhost.h"
 
+#include <signal.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -16,6 +17,7 @@ static char** g_argv;
 static gl_ctx* g_ctx = NULL;
 static int g_rank = 0, g_size = 1;
 static pid_t g_children[64];
+static pid_t g_parent = 0;   /* rank 0's pid, as seen by the forked ranks */
 static volatile int* g_bands_done = NULL;   /* shared counter: ranks that have written their band of the output image */
 static unsigned char* g_shared = NULL;
 static size_t g_shared_bytes = 0;
@@ -98,6 +100,15 @@ int GLHostSize(void) { return g_size; }
 void GLHostFatal(const char* where)
 {
     fprintf(stderr, "[rank %d] %s: %s\n", g_rank, where, gl_last_error());
+    /* the other ranks may be waiting for this one inside a collective: take them down too (MPI_Abort semantics) */
+    if (g_size > 1) {
+        if (g_rank == 0) {
+            for (int r = 1; r < g_size; ++r)
+                if (g_children[r] > 0) kill(g_children[r], SIGTERM);
+        } else if (g_parent > 1) {
+            kill(g_parent, SIGTERM);
+        }
+    }
     exit(1);
 }
 
@@ -132,6 +143,7 @@ int GLHostInit(int argc, char** argv, int* rank, int* size)
     g_shared = (unsigned char*)mmap(NULL, g_shared_bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (g_shared == MAP_FAILED) return 1;
     /* fork BEFORE any CUDA call: one process per GPU, SPMD like the reference's MPI ranks */
+    g_parent = getpid();
     for (int r = 1; r < g_size; ++r) {
         pid_t pid = fork();
         if (pid < 0) return 1;
