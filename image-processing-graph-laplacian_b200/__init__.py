@@ -448,5 +448,34 @@ def image_processing(y, cr=None, cb=None, ctx: Context | None = None, **kwargs):
             ctx.close()
 
 
+# python/utils.py:33-44 (rgb2ycc / ycc2rgb: the YUV matrices of scikit-image)
+YUV_FROM_RGB = np.array([[0.299, 0.587, 0.114],
+                         [-0.14714119, -0.28886916, 0.43601035],
+                         [0.61497538, -0.51496512, -0.10001026]])
+RGB_FROM_YUV = np.linalg.inv(YUV_FROM_RGB)
+
+
+def rgb2ycc(im):
+    return np.dot(im, YUV_FROM_RGB.T)
+
+
+def ycc2rgb(im):
+    return np.dot(im, RGB_FROM_YUV.T)
+
+
+def image_processing_rgb(rgb, ctx: Context | None = None, **kwargs):
+    """The colour branch of the prototype's main (python/image_processing.py:411-424): RGB -> YCC, filter the luma plane
+    only, pass Cr/Cb through, back to RGB.  The device path works on 8-bit samples, so the luma is rounded to u8 before
+    filtering (the prototype filters the float luma); boundary plumbing on the host, the filter itself on the GPU.
+    Returns float64 [H, W, 3] (not clipped, like the prototype before its uint8 cast)."""
+    rgb = np.asarray(rgb)
+    ycc = rgb2ycc(rgb.astype(np.float64))
+    y8 = np.clip(np.rint(ycc[:, :, 0]), 0, 255).astype(np.uint8)
+    z_y, _, _ = image_processing(y8, ycc[:, :, 1], ycc[:, :, 2], ctx=ctx, **kwargs)
+    out = ycc.copy()
+    out[:, :, 0] = ycc[:, :, 0] + (z_y.astype(np.float64) - y8)     # the filter's change, applied to the unrounded luma
+    return ycc2rgb(out)
+
+
 sampling_methods = {RANDOM: RANDOM, SPATIALLY_UNIFORM: SPATIALLY_UNIFORM}
 affinity_methods = {SPATIAL: SPATIAL, PHOTOMETRIC: PHOTOMETRIC, BILATERAL: BILATERAL}

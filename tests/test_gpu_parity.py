@@ -415,6 +415,24 @@ def test_filter_options(ctx, golden):
     assert np.array_equal(z8, o.quantise(r["z"]))
 
 
+def test_python_interface_and_colour_branch(ctx):
+    """image_processing(y, cr, cb, **kwargs) as the prototype exposes it (python/image_processing.py:244) and the colour
+    branch of its main (:411-424): luma filtered, chroma untouched."""
+    rgb = o.synthetic_image(160, 120, 3, seed=21)
+    ycc = gl.rgb2ycc(rgb.astype(np.float64))
+    assert np.allclose(gl.ycc2rgb(ycc), rgb, atol=1e-9)
+    y8 = np.clip(np.rint(ycc[:, :, 0]), 0, 255).astype(np.uint8)
+    ycr, ycb = ycc[:, :, 1], ycc[:, :, 2]
+    z, cr, cb = gl.image_processing(y8, ycr, ycb, ctx=ctx, sampling="spatially_uniform", affinity="bilateral", sample_size=80)
+    assert cr is ycr and cb is ycb                                                                  # passed through untouched
+    ref = oc.run_pipeline(y8, oc.uniform_sampling(160, 120, 80))
+    assert _rel(z, ref["z"]) <= TOL_Z and _rel(z - y8, ref["z"] - y8) <= TOL_DZ
+    out = gl.image_processing_rgb(rgb, ctx=ctx, sample_size=80)
+    back = gl.rgb2ycc(out)
+    assert np.allclose(back[:, :, 1:], ycc[:, :, 1:], atol=1e-9)                                    # chroma unchanged
+    assert _rel(back[:, :, 0] - ycc[:, :, 0], ref["z"] - y8) <= TOL_DZ                               # luma changed by the filter
+
+
 def test_errors(ctx):
     with pytest.raises(gl.GLError):
         ctx.set_image(np.zeros((1, 1), dtype=np.uint8))
