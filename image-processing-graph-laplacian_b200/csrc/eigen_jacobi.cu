@@ -130,14 +130,21 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I,
                     const double app = Bm[a * 17 + a], aqq = Bm[b * 17 + b], apq = Bm[a * 17 + b];
                     double c = 1.0, s = 0.0;
                     if (app > 0.0 && aqq > 0.0) {
-                        const double reld = fabs(apq) / sqrt(app * aqq);
-                        if (reld > 1e-13) {
-                            const double tau = (aqq - app) / (2.0 * apq);
-                            const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                            c = 1.0 / sqrt(1.0 + t * t);
-                            s = t * c;
+                        // The rotation ANGLE only has to be about right (fp32: fast rsqrt / divide instead of chains of
+                        // fp64 sqrt and divide, which dominated the step); the rotation itself must be orthogonal to fp64
+                        // accuracy, so c = (1 + t^2)^-1/2 is polished with two Newton steps in fp64 and s = t c.
+                        const float rel = fabsf((float)apq) * rsqrtf((float)app * (float)aqq);
+                        if (rel > 1e-12f) {
+                            const float tau = __fdividef((float)(aqq - app), 2.f * (float)apq);
+                            const float tf = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(fmaf(tau, tau, 1.f)));
+                            const double t = isfinite(tf) ? (double)tf : 0.0;
+                            const double x = fma(t, t, 1.0);
+                            double y = (double)rsqrtf((float)x);
+                            y = y * fma(-0.5 * x, y * y, 1.5);
+                            y = y * fma(-0.5 * x, y * y, 1.5);
+                            c = y;
+                            s = t * y;
                         }
-                        const float rel = (float)reld;
                         if (rel > *s_off) atomicMax((unsigned*)s_off, __float_as_uint(rel));
                     }
                     cs[2 * tid] = c;
