@@ -95,6 +95,7 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
     ctx->verbose = v ? atoi(v) : 0;
     if (const char* g = getenv("GLB200_GEMM")) gl_ctx_set_option(ctx, "gemm", g);
     if (const char* g = getenv("GLB200_CTA_GROUP")) gl_ctx_set_option(ctx, "cta_group", g);
+    if (const char* g = getenv("GLB200_JACOBI_TOL")) gl_ctx_set_option(ctx, "jacobi_tol", g);
     *out = ctx;
     return GL_OK;
 }

@@ -117,7 +117,7 @@ def test_eigensolver(ctx, p):
     assert Ug.shape == (p, m)
     err_orth = float(np.max(np.abs(Ug.T @ Ug - np.eye(m))))
     err_res = float(np.max(np.abs(A @ Ug - Ug * got)) / np.max(np.abs(w)))
-    assert err_orth < 5e-5 and err_res < 5e-5, (err_orth, err_res)   # the solver stops at a relative off-diagonal of 2e-5
+    assert err_orth < 1e-4 and err_res < 1e-4, (err_orth, err_res)   # the solver stops at a relative off-diagonal of 5e-5
 
 
 # ---------------------------------------------------------------------------------------------
