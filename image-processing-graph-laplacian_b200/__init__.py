@@ -334,14 +334,15 @@ class Context:
         _check(lib().gl_nystroem(self.h, L_B.h, phi_A.h, eigvals_inv.h, C.byref(p)))
         return Mat(self, p)
 
-    def nystroem_filter(self, L_B: Mat, phi_A: Mat, eigvals_inv: Mat, f_eigvals: Mat, gain=3.0, clip_low=False):
-        """Nystroem + ComputeResultFromLaplacian in one pass over Phi; returns (phi, z)."""
+    def nystroem_filter(self, L_B: Mat, phi_A: Mat, eigvals_inv: Mat, f_eigvals: Mat, gain=3.0, clip_low=False, keep_phi=True):
+        """Nystroem + ComputeResultFromLaplacian in one pass over Phi; returns (phi, z) -- phi is None with keep_phi=False
+        (Phi is then never written to memory)."""
         H, W, ch = self.shape
         z = np.zeros((H, W, ch), dtype=np.float32)
         p = C.c_void_p()
-        _check(lib().gl_nystroem_filter(self.h, L_B.h, phi_A.h, eigvals_inv.h, f_eigvals.h, gain, int(clip_low), C.byref(p),
-                                        z.ctypes.data, None))
-        return Mat(self, p), (z[:, :, 0] if ch == 1 else z)
+        _check(lib().gl_nystroem_filter(self.h, L_B.h, phi_A.h, eigvals_inv.h, f_eigvals.h, gain, int(clip_low),
+                                        C.byref(p) if keep_phi else None, z.ctypes.data, None))
+        return (Mat(self, p) if keep_phi else None), (z[:, :, 0] if ch == 1 else z)
 
     def orthonormalise(self, phi: Mat) -> np.ndarray:
         norms = np.empty(phi.info.cols, dtype=np.float64)

@@ -117,6 +117,8 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         else GL_REQUIRE(false, "option projection: want sums|recompute, got %s", value);
     } else if (!strcmp(key, "fuse_filter")) {
         ctx->fuse_filter = atoi(value) != 0;
+    } else if (!strcmp(key, "keep_phi")) {
+        ctx->keep_phi = atoi(value) != 0;
     } else if (!strcmp(key, "filter_apply")) {
         if (!strcmp(value, "warp")) ctx->filter_apply_impl = 0;
         else if (!strcmp(value, "generic")) ctx->filter_apply_impl = 1;
@@ -482,7 +484,7 @@ int gl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl
 int gl_nystroem_filter(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat* f_eigvals, double gain, int clip_low,
                        gl_mat** phi, float* z_f32, uint8_t* z_u8)
 {
-    GL_REQUIRE(ctx && L_B && phi_A && eigvals_inv && f_eigvals && phi, "gl_nystroem_filter: null");
+    GL_REQUIRE(ctx && L_B && phi_A && eigvals_inv && f_eigvals, "gl_nystroem_filter: null");
     GL_REQUIRE(L_B->kind == GL_MAT_KB && phi_A->kind == GL_MAT_EIGVEC && eigvals_inv->kind == GL_MAT_DIAG && f_eigvals->kind == GL_MAT_DIAG,
                "gl_nystroem_filter: wrong handle kinds");
     GL_REQUIRE(phi_A->rows == L_B->p && eigvals_inv->rows == phi_A->cols && f_eigvals->rows == phi_A->cols,
@@ -785,7 +787,10 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
         const bool fused = ctx->fuse_filter && !prm->gram_schmidt && ctx->projection_mode == 0 && ctx->gemm_impl == 0;
         if (fused) {
             ctx->ev_valid[GL_T_FILTER] = false;
-            if ((rc = gl_nystroem_filter(ctx, L_B, U, mu_inv, f_mu, prm->gain, prm->clip_low, &phi, z_f32, z_u8)) != GL_OK) break;
+            // option keep_phi=0: Phi is only a temporary of this one-call path, so its tiles can be consumed in the epilogue
+            // and never written to HBM at all
+            if ((rc = gl_nystroem_filter(ctx, L_B, U, mu_inv, f_mu, prm->gain, prm->clip_low, ctx->keep_phi ? &phi : nullptr, z_f32,
+                                         z_u8)) != GL_OK) break;
         } else if ((rc = gl_nystroem(ctx, L_B, U, mu_inv, &phi)) != GL_OK) break;
         gl_mat_destroy(L_B); L_B = nullptr;
         gl_mat_destroy(U); U = nullptr;

@@ -135,6 +135,7 @@ struct gl_ctx {
     int filter_apply_impl = 0;  // 0 = warp-per-row kernel when the shape allows, 1 = always the generic kernel
     int projection_mode = 0;  // 0 = c from the affinity sums (default), 1 = always recompute c with a pass over Phi
     int fuse_filter = 1;      // gl_run: apply the filter inside the extrapolation GEMM's epilogue when possible
+    int keep_phi = 1;         // gl_run with the fused filter: 1 = still write Phi to HBM (the reference's data flow), 0 = never store it
 
     // samples
     unsigned p = 0;

@@ -282,7 +282,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                int ab_bf16, const float* __restrict__ scales, const __half* __restrict__ addend, int64_t m_rows,
                const int4* __restrict__ a_tab /* K_B tile table, or null for a dense A */, int prefetch_tiles,
                const float* __restrict__ fuse_w /* [n_total][FC] */, float* __restrict__ zpart /* [parts][m_rows][FC] */,
-               int* __restrict__ err)
+               int store_d /* 0: D is consumed by the fused filter only and never written */, int* __restrict__ err)
 {
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -436,7 +436,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v[0]);
                 tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v[1]);
                 // the TMA store that last read this slab must be done with it
-                if (lane == 0) tma_store_wait_read<CBUFS - 1>();
+                if (store_d && lane == 0) tma_store_wait_read<CBUFS - 1>();
                 tmem_ld_wait();
                 __syncwarp();
 #pragma unroll
@@ -459,9 +459,11 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                         }
                     } else {
+                        if (store_d) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            pk[i] = pack_h2(__uint_as_float(v[h][2 * i]) * sc, __uint_as_float(v[h][2 * i + 1]) * sc);
+                            for (int i = 0; i < 16; ++i)
+                                pk[i] = pack_h2(__uint_as_float(v[h][2 * i]) * sc, __uint_as_float(v[h][2 * i + 1]) * sc);
+                        }
                         if (FC > 0) {
                             // 32 columns starting at nt * block_n + c0 + 32 h; weights read as broadcast float4s
                             const float4* wv = (const float4*)(w_mine + (size_t)(c0 - c_base + 32 * h) * FC);
@@ -480,19 +482,23 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     }
                     // row `lane` of the slab, 16-byte chunks 4h .. 4h+3, XOR-swizzled like SWIZZLE_128B
+                    if (store_d) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int chunk = (4 * h + c) ^ (lane & 7);
-                        *(uint4*)(slab + lane * 128 + chunk * 16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                        for (int c = 0; c < 4; ++c) {
+                            const int chunk = (4 * h + c) ^ (lane & 7);
+                            *(uint4*)(slab + lane * 128 + chunk * 16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                        }
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&map_d, smem_u32(slab), nt * block_n + c0, mt * BLOCK_M + wq * 32);
-                    tma_store_commit();
+                if (store_d) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_d, smem_u32(slab), nt * block_n + c0, mt * BLOCK_M + wq * 32);
+                        tma_store_commit();
+                    }
+                    if (CBUFS > 1) buf ^= 1;
                 }
-                if (CBUFS > 1) buf ^= 1;
             }
             // all tcgen05.ld of this accumulator have completed (wait::ld above): hand it back to the MMA warp
             tcgen05_fence_before();
@@ -556,7 +562,9 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     else
         GL_CHECK(make_map_2d(&map_a, dt, A, (uint64_t)rows, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, tc::BLOCK_M));
     GL_CHECK(make_map_2d(&map_b, dt, Bt, (uint64_t)n_pad, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, (uint32_t)block_n));
-    GL_CHECK(make_map_2d(&map_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, (uint64_t)rows, (uint64_t)n_pad, (uint64_t)n_pad, 64, 32));
+    // (no D: the store map is never used; it is encoded over A's storage only to have a valid descriptor)
+    GL_CHECK(make_map_2d(&map_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D ? D : A, (uint64_t)(D ? rows : 32), (uint64_t)(D ? n_pad : 64),
+                         (uint64_t)(D ? n_pad : 64), 64, 32));
     const int m_tiles = (int)ceil_div(rows, tc::BLOCK_M);
     const int n_tiles = n_pad / block_n;
     const int k_blocks = k_pad / tc::BLOCK_K;
@@ -580,6 +588,8 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     }
     const float* fw = fuse ? fuse->w : nullptr;
     float* zp = fuse ? fuse->zpart : nullptr;
+    const int store_d = D != nullptr;
+    GL_REQUIRE(store_d || fuse, "gemm: no output requested");
     StageTimer kt(ctx, GL_T_K_GEMM);
 #define GEMM_LAUNCH(S, CB, EW, FC)                                                                                           \
     do {                                                                                                                       \
@@ -587,7 +597,7 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
         GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<S, CB, EW, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
         tc::k_gemm_tcgen05<S, CB, EW, FC><<<grid, 128 + 32 * EW, SM, ctx->stream>>>(                                            \
             map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad, block_n, ab_bf16, scales, (const __half*)addend, rows, a_tab, \
-            pf, fw, zp, (int*)err->ptr);                                                                                        \
+            pf, fw, zp, store_d, (int*)err->ptr);                                                                                        \
     } while (0)
     if (!deep) {
         if (FCH == 1) GEMM_LAUNCH(3, 2, 8, 1);
@@ -613,6 +623,7 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
     const int64_t rows = L_B->local_rows;
     GL_REQUIRE(L_B->dscale, "nystroem: expected L_B (from gl_laplacian), got a bare K_B");
     GL_REQUIRE(rows > 0, "nystroem: empty band");
+    GL_REQUIRE(phi_out || ff, "nystroem: nothing to return");
 
     gl_mat* phi = gl_mat_new(ctx, GL_MAT_PHI);
     gl_buf *Wt = nullptr, *colmax = nullptr, *scales = nullptr;
@@ -628,7 +639,8 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
         phi->m = m;
         phi->m_pad = m_pad;
         phi->q0 = L_B->q0;
-        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)rows * m_pad, &phi->buf)) != GL_OK) break;
+        const bool keep_phi = phi_out != nullptr;   // gl_nystroem_filter may be asked for z only: Phi then never leaves the chip
+        if (keep_phi && (rc = gl_alloc(ctx, sizeof(__half) * (size_t)rows * m_pad, &phi->buf)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)m_pad * p_pad, &Wt)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad, &colmax)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * 4, &scales)) != GL_OK) break;
@@ -680,8 +692,8 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
             fuse.zpart = (float*)zpart->ptr;
             fuse.C = C;
         }
-        rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, p_pad, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr, phi->buf->ptr,
-                            (const int4*)L_B->tiles->ptr, L_B->total_blocks, do_fuse ? &fuse : nullptr);
+        rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, p_pad, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
+                            keep_phi ? phi->buf->ptr : nullptr, (const int4*)L_B->tiles->ptr, L_B->total_blocks, do_fuse ? &fuse : nullptr);
         if (rc == GL_OK && do_fuse)
             rc = gl_filter_fused_finish(ctx, phi, (const float*)zpart->ptr, fuse.parts, (const float*)wbuf->ptr, U, (int)phi_A->ld,
                                         ff->clip_low, ff->z_f32, ff->z_u8);
@@ -689,14 +701,16 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
         if (zpart) gl_buf_release(zpart);
         if (rc != GL_OK) break;
 
-        k_phi_sample_rows<<<p, 128, 0, ctx->stream>>>(U, (int)phi_A->ld, p, m, (const uint32_t*)ctx->samples->ptr, phi->q0,
-                                                      phi->q0 + rows, m_pad, (__half*)phi->buf->ptr);
-        GL_LAUNCH_CHECK(ctx);
+        if (keep_phi) {
+            k_phi_sample_rows<<<p, 128, 0, ctx->stream>>>(U, (int)phi_A->ld, p, m, (const uint32_t*)ctx->samples->ptr, phi->q0,
+                                                          phi->q0 + rows, m_pad, (__half*)phi->buf->ptr);
+            GL_LAUNCH_CHECK(ctx);
+        }
     } while (0);
     if (Wt) gl_buf_release(Wt);
     if (colmax) gl_buf_release(colmax);
     if (scales) gl_buf_release(scales);
-    if (rc != GL_OK) {
+    if (rc != GL_OK || !phi_out) {
         gl_mat_destroy(phi);
         return rc;
     }

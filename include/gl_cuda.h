@@ -152,7 +152,8 @@ GL_API int gl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_m
 GL_API int gl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi);
 /* gl_nystroem and gl_filter in ONE pass over Phi: the filter weights gain * f o (Phi^T y) are formed first (Phi^T y
  * from the affinity stage's sums), the extrapolation GEMM writes Phi and accumulates each row's product with the weights
- * in its epilogue, so Phi is never read back.  Needs L_B of the CURRENT image; same outputs as the two calls. */
+ * in its epilogue, so Phi is never read back.  Needs L_B of the CURRENT image; same outputs as the two calls.  `phi` may be
+ * NULL: Phi is then not written to memory at all (its tiles only ever exist in tensor memory). */
 GL_API int gl_nystroem_filter(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat* f_eigvals, double gain,
                               int clip_low, gl_mat** phi, float* z_f32, uint8_t* z_u8);
 GL_API int gl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out /* m, may be NULL */);

@@ -326,6 +326,8 @@ def test_fused_filter_matches_staged(ctx, golden, tag):
     L_A, L_B = ctx.laplacian(K_A, K_B)
     U, mu, mu_inv = ctx.eigensolve(L_A, int(g["m"]))
     phi_f, z_f = ctx.nystroem_filter(L_B, U, mu_inv, mu)
+    none, z_n = ctx.nystroem_filter(L_B, U, mu_inv, mu, keep_phi=False)     # Phi never written: same z, bit for bit
+    assert none is None and np.array_equal(z_n, z_f)
     phi_s = ctx.nystroem(L_B, U, mu_inv)
     assert np.array_equal(phi_f.download(), phi_s.download())
     z_s = ctx.filter(phi_s, mu)
