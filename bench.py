@@ -362,8 +362,9 @@ def main():
                                          "HBM (same z bit for bit); NOT the headline, which keeps the reference's data flow and stores Phi"),
                affinity_plus_extrapolation_tflops=aff_ext_tf,
                kb_cutoff=dict(stored_blocks=stored_blocks, dense_blocks=int(dense_blocks), kept=stored_blocks / max(1, dense_blocks),
-                              note="sample blocks whose K_B entries fp16 flushes to zero (|drow| > h_loc*sqrt(25 ln 2)) are neither "
-                                   "computed, stored nor multiplied"),
+                              note="64-sample blocks of K_B whose entries fp16 flushes to zero (sample further than h_loc*sqrt(25 ln 2) "
+                                   "from the 512-pixel tile in rows or columns; samples ordered by column strip, then row) are "
+                                   "neither computed, stored nor multiplied"),
                gemm=dict(ms=med["k_gemm"], flop_dense_equivalent=f_ext, flop_executed=f_ext_exec, tflops_dense_equivalent=gemm_tf,
                          tflops_executed=gemm_tf_exec, bytes=gemm_bytes, gbs=gemm_gbs),
                stage_ms={k: round(v, 4) for k, v in stage.items()},

@@ -33,19 +33,21 @@
 #define AFF_TP 512               // pixels per tile
 #define AFF_PPT (AFF_TP / 32)    // pixels per thread per 64-sample chunk
 
-// sample features, SoA: [0] row, [1] col, [2..2+C) values; padded samples carry 1e18 so that K == 0
-__global__ void k_sample_features(const uint8_t* __restrict__ img, const uint32_t* __restrict__ samples, int p, int p_pad,
-                                  int width, int channels, float* __restrict__ sf)
+// sample features in INTERNAL sample order (perm[i] = index of the i-th internal sample in the caller's ascending list),
+// SoA with stride p_int: [0] row, [1] col, [2..2+C) values; slots without a sample carry 1e18 so that K == 0
+__global__ void k_sample_features(const uint8_t* __restrict__ img, const uint32_t* __restrict__ samples, const uint32_t* __restrict__ perm,
+                                  int p_int, int width, int channels, float* __restrict__ sf)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p_pad) return;
-    if (i < p) {
-        uint32_t q = samples[i];
+    if (i >= p_int) return;
+    const uint32_t j = perm[i];
+    if (j != 0xffffffffu) {
+        uint32_t q = samples[j];
         sf[i] = (float)(q / width);
-        sf[p_pad + i] = (float)(q % width);
-        for (int ch = 0; ch < channels; ++ch) sf[(2 + ch) * p_pad + i] = (float)img[(size_t)q * channels + ch];
+        sf[p_int + i] = (float)(q % width);
+        for (int ch = 0; ch < channels; ++ch) sf[(2 + ch) * p_int + i] = (float)img[(size_t)q * channels + ch];
     } else {
-        for (int k = 0; k < 2 + channels; ++k) sf[k * p_pad + i] = 1e18f;
+        for (int k = 0; k < 2 + channels; ++k) sf[k * p_int + i] = 1e18f;
     }
 }
 
@@ -79,10 +81,11 @@ __global__ void k_affinity_A(const uint8_t* __restrict__ img, const uint32_t* __
 // chunk x pixels ty, ty+32, ... of the tile.  A warp stores 4 pixel rows x 128 contiguous bytes.
 template <int KIND, int C>
 __global__ void __launch_bounds__(AFF_THREADS, 2)
-k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int p_pad, int width, int64_t q0, int64_t q1,
-             float a2, float b2,  // -log2(e)/h_loc^2, -log2(e)/h_val^2
-             const int4* __restrict__ tab /* per tile: first block, block count, block offset */,
-             __half* __restrict__ KB /* [block][512][64] */, float* __restrict__ partial /* [gridDim.x][1 + C][p_pad] */)
+k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int p_pad /* = p_int: internal sample slots */, int width,
+             int64_t q0, int64_t q1, float a2, float b2,  // -log2(e)/h_loc^2, -log2(e)/h_val^2
+             const int4* __restrict__ tab /* per tile: first entry of its block list, block count, storage offset */,
+             const int* __restrict__ starts /* first internal sample of every stored block */,
+             __half* __restrict__ KB /* [block][512][64] */, float* __restrict__ partial /* [gridDim.x][1 + C][p_int] */)
 {
     extern __shared__ float aff_smem[];
     constexpr int NS = 1 + C;                  // sums per sample: D and T[ch]
@@ -110,8 +113,8 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
         __syncthreads();
         const int4 tl = tab[tile];
         for (int ci = 0; ci < tl.y; ++ci) {
-            const int ck = tl.x + ci;
-            const int s0 = (ck << 6) + (tx << 3);
+            const int sb = starts[tl.x + ci];          // multiple of 8: the float4 loads below stay aligned
+            const int s0 = sb + (tx << 3);
             __half* kb_blk = KB + ((size_t)(tl.z + ci) * AFF_TP) * 64 + (tx << 3);
             float sr[8], sc[8], sv[C][8];
             if (KIND != GL_PHOTOMETRIC) {
@@ -201,7 +204,7 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
                 float sum = 0.f;
 #pragma unroll
                 for (int wi = 0; wi < 8; ++wi) sum += w[which * 512 + wi * 64 + sidx];
-                cta_sum[which * p_pad + (ck << 6) + sidx] += sum;
+                cta_sum[which * p_pad + sb + sidx] += sum;
             }
             flip ^= 1;
         }
@@ -210,24 +213,113 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
     for (int i = tid; i < NS * p_pad; i += AFF_THREADS) partial[(size_t)blockIdx.x * NS * p_pad + i] = cta_sum[i];
 }
 
-// DT[which][s] = sum over CTAs (fixed order, fp64); which 0 = D, 1.. = T[ch]; padding samples get 0
-__global__ void k_reduce_partials(const float* __restrict__ partial, int nblocks, int p_pad, int ns, double* __restrict__ DT)
+// DT[which][j] = sum over CTAs (fixed order, fp64) for the sample j = perm[i] of internal slot i; which 0 = D, 1.. = T[ch].
+// DT is in the caller's sample order (stride p_pad) and must be zeroed beforehand (its padding stays 0).
+__global__ void k_reduce_partials(const float* __restrict__ partial, int nblocks, int p_int, int ns, const uint32_t* __restrict__ perm,
+                                  int p_pad, double* __restrict__ DT)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ns * p_pad) return;
+    if (i >= ns * p_int) return;
+    const int which = i / p_int, slot = i - which * p_int;
+    const uint32_t j = perm[slot];
+    if (j == 0xffffffffu) return;
     double acc = 0.0;
-    for (int b = 0; b < nblocks; ++b) acc += (double)partial[(size_t)b * ns * p_pad + i];
-    DT[i] = acc;
+    for (int b = 0; b < nblocks; ++b) acc += (double)partial[(size_t)b * ns * p_int + i];
+    DT[(size_t)which * p_pad + j] = acc;
 }
 
-// Tile table of K_B (see the header): one int4 {first 64-sample block, block count, block offset, 0} per 512-pixel tile
-// of this rank's band.  Built on the host (tiles x 2 binary searches over the sorted sample rows), uploaded only when
-// it differs from the cached one.
-static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
+// Layout of the stored K_B blocks (see the header).  Samples get an INTERNAL order: by column strip (S strips of equal
+// width), then by raster index, so that inside a strip they are sorted by image row.  For a 512-pixel tile the samples that
+// can matter are, per strip within R columns of the tile, a contiguous run of that strip's rows within R rows of the tile;
+// each run is covered by 64-sample blocks starting at a multiple of 8 (unaligned to 64 on purpose: a run of <= 57 samples
+// is one block).  Blocks of a tile are ascending and never overlap, so no (pixel, sample) pair is stored twice.
+//   tile table : int4 {first entry in `starts`, block count, storage offset in blocks, 0} per tile
+//   starts     : first internal sample slot of every stored block
+//   perm       : internal slot -> index in the caller's ascending sample list (0xffffffff: empty slot), p_int = p_pad + 64
+// S is chosen on the host as the candidate with the fewest stored blocks; S = 1 with the row cutoff alone when the image is
+// narrow, and every block (aligned, S = 1) when there is no spatial term.  Built from the host mirror of the indices and
+// cached on (geometry, samples, R).
+struct KbLayout {
+    std::vector<int4> tab;
+    std::vector<int> starts;
+    std::vector<uint32_t> perm;
+    int64_t total = 0;
+};
+
+static void kb_layout_for(const gl_ctx* ctx, const std::vector<uint32_t>& samples, bool cut, int64_t R, int S, bool count_only, KbLayout* out,
+                          int64_t tile_stride = 1 /* count_only: visit every tile_stride-th tile */)
 {
-    const int p = (int)ctx->p, nblk = ctx->p_pad >> 6, W = ctx->width;
+    const int p = (int)samples.size(), W = ctx->width, p_pad = ctx->p_pad, p_int = p_pad + 64;
     const int64_t n_band = ctx->q1 - ctx->q0;
     const int64_t tiles = (n_band + AFF_TP - 1) / AFF_TP;
+    // internal order: (strip, raster index); the input is ascending, so a stable bucket pass does it
+    std::vector<int> strip_of(p), strip_begin(S + 1, 0);
+    for (int i = 0; i < p; ++i) {
+        strip_of[i] = (int)((int64_t)(samples[i] % (uint32_t)W) * S / W);
+        strip_begin[strip_of[i] + 1]++;
+    }
+    for (int s = 0; s < S; ++s) strip_begin[s + 1] += strip_begin[s];
+    std::vector<int> row_int(p);        // image row of the sample in internal slot i
+    std::vector<uint32_t> perm(p_int, 0xffffffffu);
+    {
+        std::vector<int> fill(strip_begin.begin(), strip_begin.end() - 1);
+        for (int i = 0; i < p; ++i) {
+            const int slot = fill[strip_of[i]]++;
+            perm[slot] = (uint32_t)i;
+            row_int[slot] = (int)(samples[i] / (uint32_t)W);
+        }
+    }
+    out->total = 0;
+    if (!count_only) {
+        out->tab.assign((size_t)tiles, make_int4(0, 0, 0, 0));
+        out->starts.clear();
+        out->perm = perm;
+    }
+    for (int64_t t = 0; t < tiles; t += tile_stride) {
+        const int64_t first_entry = out->total;
+        int64_t prev_end = 0;
+        int cnt = 0;
+        auto emit = [&](int64_t lo, int64_t hi) {   // cover internal slots [lo, hi) with blocks
+            int64_t start = std::max<int64_t>(lo & ~(int64_t)7, prev_end);
+            while (start < hi) {
+                if (!count_only) out->starts.push_back((int)start);
+                ++cnt;
+                start += 64;
+                prev_end = start;
+            }
+        };
+        if (!cut) {
+            emit(0, p_pad);
+        } else {
+            const int64_t qa = ctx->q0 + t * AFF_TP, qb = std::min(ctx->q1, qa + AFF_TP) - 1;
+            const int64_t ra = qa / W, rb = qb / W;
+            // column intervals the tile's pixels occupy: one or two row segments, or whole rows
+            int64_t seg[2][2];
+            int nseg = 1;
+            if (ra == rb) { seg[0][0] = qa % W; seg[0][1] = qb % W; }
+            else if (rb == ra + 1 && qb % W < qa % W) { seg[0][0] = qa % W; seg[0][1] = W - 1; seg[1][0] = 0; seg[1][1] = qb % W; nseg = 2; }
+            else { seg[0][0] = 0; seg[0][1] = W - 1; }
+            for (int s = 0; s < S; ++s) {
+                const int64_t c_lo = (int64_t)s * W / S, c_hi = (int64_t)(s + 1) * W / S - 1;   // columns of this strip (approx. bounds)
+                bool need = false;
+                for (int g = 0; g < nseg; ++g) need = need || (seg[g][0] - R <= c_hi + 1 && seg[g][1] + R >= c_lo - 1);
+                if (!need) continue;
+                const int* rb_ = row_int.data() + strip_begin[s];
+                const int* re_ = row_int.data() + strip_begin[s + 1];
+                const int64_t lo = strip_begin[s] + (std::lower_bound(rb_, re_, (int)std::max<int64_t>(ra - R, -1)) - rb_);
+                const int64_t hi = strip_begin[s] + (std::upper_bound(rb_, re_, (int)std::min<int64_t>(rb + R, 0x7fffffff)) - rb_);
+                if (hi > lo) emit(lo, hi);
+            }
+            if (cnt == 0) emit(0, 1);   // keep one block so that the GEMM writes zeros
+        }
+        if (!count_only) out->tab[(size_t)t] = make_int4((int)first_entry, cnt, (int)first_entry, 0);
+        out->total += cnt;
+    }
+}
+
+static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
+{
+    const int p = (int)ctx->p, W = ctx->width;
     if (!ctx->h_samples_valid) {
         ctx->h_samples.resize(p);
         GL_CUDA_CHECK(cudaMemcpyAsync(ctx->h_samples.data(), ctx->samples->ptr, sizeof(uint32_t) * p, cudaMemcpyDeviceToHost, ctx->stream));
@@ -235,56 +327,56 @@ static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
         ctx->h_samples_valid = true;
     }
     const bool cut = ctx->kb_cutoff && kind != GL_PHOTOMETRIC;
-    // |dr| > h_loc sqrt(25 ln 2)  =>  exp(-dr^2/h_loc^2) < 2^-25  =>  the fp16 value is 0; one more row for rounding slack
+    // |d| > h_loc sqrt(25 ln 2)  =>  exp(-d^2/h_loc^2) < 2^-25  =>  the fp16 value is 0; one more pixel for rounding slack
     const double rr = std::floor(h_loc * std::sqrt(25.0 * 0.6931471805599453)) + 1.0;
     const int64_t R = rr < 1e9 ? (int64_t)rr : (int64_t)1e9;
-    const int64_t key[6] = {W, ctx->q0, ctx->q1, p, R, cut ? 1 : 0};
+    const int64_t key[6] = {W, ctx->q0, ctx->q1, p, R, (cut ? 1 : 0) + 2 * ctx->kb_strips};
     if (ctx->tile_tab && !memcmp(key, ctx->tab_key, sizeof(key)) && ctx->tab_samples.size() == (size_t)p &&
         !memcmp(ctx->tab_samples.data(), ctx->h_samples.data(), sizeof(uint32_t) * p))
-        return GL_OK;  // same geometry, samples and cutoff as last time: the cached table stands
-    std::vector<int> srow(p);
-    for (int i = 0; i < p; ++i) srow[i] = (int)(ctx->h_samples[i] / (uint32_t)W);
-    std::vector<int4> tab((size_t)tiles);
-    int64_t off = 0;
-    for (int64_t t = 0; t < tiles; ++t) {
-        int lo = 0, cnt = nblk;
-        if (cut) {
-            const int64_t qa = ctx->q0 + t * AFF_TP, qb = std::min(ctx->q1, qa + AFF_TP) - 1;
-            const int64_t ra = qa / W - R, rb = qb / W + R;
-            const int s_lo = (int)(std::lower_bound(srow.begin(), srow.end(), (int)std::max<int64_t>(ra, -1)) - srow.begin());
-            const int s_hi = (int)(std::upper_bound(srow.begin(), srow.end(), (int)std::min<int64_t>(rb, 0x7fffffff)) - srow.begin());
-            lo = s_lo >> 6;
-            cnt = ((s_hi + 63) >> 6) - lo;
-            if (cnt < 1) { lo = std::min(lo, nblk - 1); cnt = 1; }   // keep one block so that the GEMM writes zeros
+        return GL_OK;  // same geometry, samples and cutoff as last time: the cached layout stands
+    KbLayout lay;
+    int best_S = 1;
+    if (cut) {
+        if (ctx->kb_strips > 0) {
+            best_S = ctx->kb_strips;
+        } else {
+            int64_t best = -1;
+            for (int S : {1, 2, 3, 4, 5, 6, 8, 10, 12, 16}) {
+                if (S > 1 && (W / S < 64 || 2 * R * S > 4 * (int64_t)W)) continue;   // strips much narrower than the reach cannot help
+                kb_layout_for(ctx, ctx->h_samples, true, R, S, true, &lay, 7);   // a sample of the tiles is enough to rank the candidates
+                if (best < 0 || lay.total < best) { best = lay.total; best_S = S; }
+            }
         }
-        tab[(size_t)t] = make_int4(lo, cnt, (int)off, 0);
-        off += cnt;
-        GL_REQUIRE(off < 0x7fffffff / 512, "affinity: K_B has too many blocks for 32-bit tile coordinates");
     }
-    const bool same = ctx->tile_tab && ctx->h_tile_tab.size() == tab.size() &&
-                      !memcmp(ctx->h_tile_tab.data(), tab.data(), sizeof(int4) * tab.size());
-    if (!same) {
-        const size_t bytes = sizeof(int4) * tab.size();
-        if (ctx->tile_tab) gl_buf_release(ctx->tile_tab);
-        ctx->tile_tab = nullptr;
-        GL_CHECK(gl_alloc(ctx, bytes, &ctx->tile_tab));
-        GL_CHECK(gl_ensure_pinned(ctx, bytes));
-        GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the pinned block may still feed an earlier copy
-        memcpy(ctx->pinned, tab.data(), bytes);
-        GL_CUDA_CHECK(cudaMemcpyAsync(ctx->tile_tab->ptr, ctx->pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->h_tile_tab.swap(tab);
-        ctx->tile_total_blocks = off;
+    kb_layout_for(ctx, ctx->h_samples, cut, R, best_S, false, &lay);
+    GL_REQUIRE(lay.total < 0x7fffffff / 512, "affinity: K_B has too many blocks for 32-bit tile coordinates");
+    // upload: table, block starts, permutation (one staging pass through the pinned block each)
+    gl_buf** dst[3] = {&ctx->tile_tab, &ctx->tile_starts, &ctx->tile_perm};
+    const void* src[3] = {lay.tab.data(), lay.starts.data(), lay.perm.data()};
+    const size_t bytes[3] = {sizeof(int4) * lay.tab.size(), sizeof(int) * lay.starts.size(), sizeof(uint32_t) * lay.perm.size()};
+    GL_CHECK(gl_ensure_pinned(ctx, bytes[0] + bytes[1] + bytes[2] + 64));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the pinned block may still feed an earlier copy
+    size_t off = 0;
+    for (int k = 0; k < 3; ++k) {
+        if (*dst[k]) gl_buf_release(*dst[k]);
+        *dst[k] = nullptr;
+        GL_CHECK(gl_alloc(ctx, bytes[k], dst[k]));
+        memcpy((char*)ctx->pinned + off, src[k], bytes[k]);
+        GL_CUDA_CHECK(cudaMemcpyAsync((*dst[k])->ptr, (char*)ctx->pinned + off, bytes[k], cudaMemcpyHostToDevice, ctx->stream));
+        off += (bytes[k] + 15) & ~(size_t)15;
     }
+    ctx->tile_total_blocks = lay.total;
+    ctx->tile_strips = best_S;
     memcpy(ctx->tab_key, key, sizeof(key));
     ctx->tab_samples = ctx->h_samples;
     return GL_OK;
 }
 
 template <int KIND, int C>
-static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float* sf, double* KA, const int4* tab, __half* KB,
-                           float* partial, int grid)
+static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float* sf, double* KA, const int4* tab, const int* starts,
+                           __half* KB, float* partial, int grid)
 {
-    const int p = (int)ctx->p, p_pad = ctx->p_pad;
+    const int p = (int)ctx->p, p_pad = ctx->p_pad + 64;   // the K_B kernel works on the internal sample slots (p_int)
     dim3 ga((unsigned)ceil_div(p, 128), (unsigned)p);
     k_affinity_A<KIND, C><<<ga, 128, 0, ctx->stream>>>((const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p,
                                                       ctx->width, 1.0 / (h_loc * h_loc), 1.0 / (h_val * h_val), KA);
@@ -295,7 +387,7 @@ static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float*
     StageTimer kt(ctx, GL_T_K_AFFINITY_B);
     k_affinity_B<KIND, C><<<grid, AFF_THREADS, smem, ctx->stream>>>(
         (const uint8_t*)ctx->img->ptr, sf, p_pad, ctx->width, ctx->q0, ctx->q1, (float)(-log2e / (h_loc * h_loc)),
-        (float)(-log2e / (h_val * h_val)), tab, KB, partial);
+        (float)(-log2e / (h_val * h_val)), tab, starts, KB, partial);
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;
 }
@@ -303,8 +395,15 @@ static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float*
 int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A_out, gl_mat** K_B_out)
 {
     const int p = (int)ctx->p, p_pad = ctx->p_pad, C = ctx->channels;
+    const int p_int = p_pad + 64;   // internal sample slots (a block may start at any multiple of 8 below p)
     const int64_t n_band = ctx->q1 - ctx->q0;
-    GL_REQUIRE(p_pad <= 16384, "affinity: p = %d too large", p);
+    {
+        const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_int + 2 * (1 + C) * 8 * 64 + (size_t)(2 + C) * AFF_TP);
+        if (smem > 227 * 1024) {
+            gl_set_error("affinity: p = %d samples need %zu bytes of shared memory per CTA (limit 227 KB)", p, smem);
+            return GL_ERR_UNSUPPORTED;
+        }
+    }
 
     gl_mat* KA = gl_mat_new(ctx, GL_MAT_KA);
     gl_mat* KB = gl_mat_new(ctx, GL_MAT_KB);
@@ -325,29 +424,35 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         KB->p_pad = p_pad;
         KB->q0 = ctx->q0;
         if ((rc = build_tile_table(ctx, kind, h_loc)) != GL_OK) break;
-        KB->tiles = ctx->tile_tab;      // shared with the context's cache (a new table is a new buffer)
+        KB->tiles = ctx->tile_tab;      // shared with the context's cache (a new layout is a new set of buffers)
         KB->tiles->refs++;
+        KB->starts = ctx->tile_starts;
+        KB->starts->refs++;
+        KB->perm = ctx->tile_perm;
+        KB->perm->refs++;
         KB->total_blocks = ctx->tile_total_blocks;
         if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)KB->total_blocks * AFF_TP * 64, &KB->buf)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)(1 + C) * p_pad, &KB->aux)) != GL_OK) break;  // [D | T[ch]]
-        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_pad, &sf)) != GL_OK) break;
-        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * (1 + C) * p_pad, &partial)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_int, &sf)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * (1 + C) * p_int, &partial)) != GL_OK) break;
 
-        k_sample_features<<<(unsigned)ceil_div(p_pad, 256), 256, 0, ctx->stream>>>(
-            (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p, p_pad, ctx->width, C, (float*)sf->ptr);
+        k_sample_features<<<(unsigned)ceil_div(p_int, 256), 256, 0, ctx->stream>>>(
+            (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, (const uint32_t*)KB->perm->ptr, p_int, ctx->width, C,
+            (float*)sf->ptr);
         ctx->launches++;
 
 #define AFF_CASE(K, CC)                                                                                              \
     if (kind == K && C == CC)                                                                                        \
         rc = launch_affinity<K, CC>(ctx, h_loc, h_val, (const float*)sf->ptr, (double*)KA->buf->ptr, (const int4*)KB->tiles->ptr, \
-                                    (__half*)KB->buf->ptr, (float*)partial->ptr, grid);
+                                    (const int*)KB->starts->ptr, (__half*)KB->buf->ptr, (float*)partial->ptr, grid);
         AFF_CASE(GL_BILATERAL, 1) else AFF_CASE(GL_BILATERAL, 3) else AFF_CASE(GL_PHOTOMETRIC, 1)
         else AFF_CASE(GL_PHOTOMETRIC, 3) else AFF_CASE(GL_SPATIAL, 1) else AFF_CASE(GL_SPATIAL, 3)
 #undef AFF_CASE
         if (rc != GL_OK) break;
 
-        k_reduce_partials<<<(unsigned)ceil_div((1 + C) * p_pad, 128), 128, 0, ctx->stream>>>((const float*)partial->ptr, grid, p_pad,
-                                                                                             1 + C, (double*)KB->aux->ptr);
+        GL_CUDA_BREAK(rc, cudaMemsetAsync(KB->aux->ptr, 0, sizeof(double) * (size_t)(1 + C) * p_pad, ctx->stream));
+        k_reduce_partials<<<(unsigned)ceil_div((1 + C) * p_int, 128), 128, 0, ctx->stream>>>(
+            (const float*)partial->ptr, grid, p_int, 1 + C, (const uint32_t*)KB->perm->ptr, p_pad, (double*)KB->aux->ptr);
         GL_LAUNCH_CHECK(ctx);
         // ONE allreduce of the band-partial sums: D (p doubles) and T (C x p doubles)
         if ((rc = gl_allreduce_f64(ctx, (double*)KB->aux->ptr, (size_t)(1 + C) * p_pad)) != GL_OK) break;

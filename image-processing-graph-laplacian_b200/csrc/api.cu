@@ -137,6 +137,9 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         GL_REQUIRE(ctx->gemm_prefetch >= 0 && ctx->gemm_prefetch <= 16, "option gemm_prefetch: want 0..16");
     } else if (!strcmp(key, "kb_cutoff")) {
         ctx->kb_cutoff = atoi(value) != 0;
+    } else if (!strcmp(key, "kb_strips")) {
+        ctx->kb_strips = atoi(value);
+        GL_REQUIRE(ctx->kb_strips >= 0 && ctx->kb_strips <= 64, "option kb_strips: want 0..64");
     } else if (!strcmp(key, "eig_largest")) {
         ctx->eig_largest = atoi(value) != 0;   // EigendecompositionLargest (hpc/eigendecomposition.c:116-119)
     } else if (!strcmp(key, "jacobi_max_sweeps")) {
@@ -170,6 +173,8 @@ int gl_ctx_destroy(gl_ctx* ctx)
     if (ctx->img) gl_buf_release(ctx->img);
     if (ctx->samples) gl_buf_release(ctx->samples);
     if (ctx->tile_tab) gl_buf_release(ctx->tile_tab);
+    if (ctx->tile_starts) gl_buf_release(ctx->tile_starts);
+    if (ctx->tile_perm) gl_buf_release(ctx->tile_perm);
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
     ctx->free_blocks.clear();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -600,6 +605,8 @@ int gl_mat_destroy(gl_mat* m)
     if (m->buf) gl_buf_release(m->buf);
     if (m->aux) gl_buf_release(m->aux);
     if (m->tiles) gl_buf_release(m->tiles);
+    if (m->starts) gl_buf_release(m->starts);
+    if (m->perm) gl_buf_release(m->perm);
     if (m->dscale) gl_buf_release(m->dscale);
     if (m->proj) gl_buf_release(m->proj);
     delete m;
@@ -617,20 +624,29 @@ __global__ void k_half_to_f64(const __half* __restrict__ src, int64_t ld, int64_
     int64_t r = i / cols, c = i % cols;
     dst[i] = scale * (double)__half2float(src[r * ld + c]);
 }
-// K_B from its blocked storage ([block][512 pixels][64 samples], affinity.cu) to dense fp64 rows x cols; blocks that
-// were never stored (all entries below the fp16 flush-to-zero cutoff) read as 0
-__global__ void k_kb_blocked_to_f64(const __half* __restrict__ src, const int4* __restrict__ tab, int64_t rows, int64_t cols,
-                                    double scale, double* __restrict__ dst)
+// K_B from its blocked storage ([block][512 pixels][64 sample slots], affinity.cu) to dense fp64 rows x cols in the caller's
+// sample order; sample slots that no stored block of the tile covers (entries below the fp16 flush-to-zero cutoff) read as 0
+__global__ void k_kb_blocked_to_f64(const __half* __restrict__ src, const int4* __restrict__ tab, const int* __restrict__ starts,
+                                    const uint32_t* __restrict__ perm, int p_int, int64_t rows, int64_t cols, double scale,
+                                    double* __restrict__ dst)
 {
+    // one thread per (pixel row, internal slot): the slot's sample decides the output column
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * cols) return;
-    const int64_t r = i / cols;
-    const int c = (int)(i % cols);
+    if (i >= rows * p_int) return;
+    const int64_t r = i / p_int;
+    const int slot = (int)(i % p_int);
+    const uint32_t c = perm[slot];
+    if (c == 0xffffffffu || (int64_t)c >= cols) return;
     const int4 tl = tab[r >> 9];
-    const int blk = (c >> 6) - tl.x;
     double v = 0.0;
-    if (blk >= 0 && blk < tl.y) v = (double)__half2float(src[(((size_t)tl.z + blk) * 512 + (size_t)(r & 511)) * 64 + (c & 63)]);
-    dst[i] = scale * v;
+    for (int k = 0; k < tl.y; ++k) {
+        const int sb = starts[tl.x + k];
+        if (slot >= sb && slot < sb + 64) {
+            v = (double)__half2float(src[(((size_t)tl.z + k) * 512 + (size_t)(r & 511)) * 64 + (slot - sb)]);
+            break;
+        }
+    }
+    dst[r * cols + c] = scale * v;
 }
 __global__ void k_colmajor_f32_to_f64(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols,
                                       double* __restrict__ dst)
@@ -680,10 +696,13 @@ int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap)
     case GL_MAT_DIAG:
         k_scale_f64<<<blocks, T, 0, ctx->stream>>>((const double*)m->buf->ptr, count, m->scale, d);
         break;
-    case GL_MAT_KB:
-        k_kb_blocked_to_f64<<<blocks, T, 0, ctx->stream>>>((const __half*)m->buf->ptr, (const int4*)m->tiles->ptr, rows, cols,
-                                                           m->scale, d);
+    case GL_MAT_KB: {
+        const int p_int = m->p_pad + 64;
+        k_kb_blocked_to_f64<<<(unsigned)ceil_div(rows * p_int, T), T, 0, ctx->stream>>>(
+            (const __half*)m->buf->ptr, (const int4*)m->tiles->ptr, (const int*)m->starts->ptr, (const uint32_t*)m->perm->ptr, p_int, rows,
+            cols, m->scale, d);
         break;
+    }
     case GL_MAT_PHI:
         k_half_to_f64<<<blocks, T, 0, ctx->stream>>>((const __half*)m->buf->ptr, m->ld, rows, cols, m->scale, d);
         break;

@@ -71,6 +71,8 @@ int gl_impl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A_out, g
     LB->buf->refs++;         // ... sharing the storage
     if (LB->aux) LB->aux->refs++;
     if (LB->tiles) LB->tiles->refs++;
+    if (LB->starts) LB->starts->refs++;
+    if (LB->perm) LB->perm->refs++;
     LB->proj = nullptr;
     LB->dscale = al;         // scale = -alpha, device resident
     LB->scale_on_host = false;

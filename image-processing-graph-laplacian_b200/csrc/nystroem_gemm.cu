@@ -61,15 +61,17 @@ __global__ void k_w_scale(const float* __restrict__ colmax, int m, float* __rest
     }
 }
 
-__global__ void k_w_write(const float* __restrict__ U, int ld, int p, int m, int p_pad, int m_pad,
+// W^T in K_B's INTERNAL sample order: column `slot` of row j holds W[perm[slot]][j] (0 for empty slots); k_dim = p_pad + 64
+__global__ void k_w_write(const float* __restrict__ U, int ld, int m, int k_dim, const uint32_t* __restrict__ perm,
                           const double* __restrict__ mu_inv, const double* __restrict__ neg_alpha,
                           const float* __restrict__ scales, __half* __restrict__ Wt)
 {
     const int j = blockIdx.x;  // row of W^T
     const float f = j < m ? (float)(neg_alpha[0] * mu_inv[j]) * scales[0] : 0.f;
-    for (int s = threadIdx.x; s < p_pad; s += blockDim.x) {
-        float v = (j < m && s < p) ? U[(size_t)j * ld + s] * f : 0.f;
-        Wt[(size_t)j * p_pad + s] = __float2half_rn(v);
+    for (int s = threadIdx.x; s < k_dim; s += blockDim.x) {
+        const uint32_t i = perm[s];
+        float v = (j < m && i != 0xffffffffu) ? U[(size_t)j * ld + i] * f : 0.f;
+        Wt[(size_t)j * k_dim + s] = __float2half_rn(v);
     }
 }
 
@@ -206,17 +208,21 @@ __global__ void __launch_bounds__(256) k_gemm_simple(const T* __restrict__ A, co
         }
 }
 
-// element (r, k) of K_B in its blocked storage; blocks outside the tile's range are zero
-__device__ __forceinline__ float kb_blocked_at(const __half* __restrict__ A, const int4* __restrict__ tab, int64_t r, int k)
+// element (pixel row r, internal sample slot k) of K_B in its blocked storage; slots no stored block of the tile covers are zero
+__device__ __forceinline__ float kb_blocked_at(const __half* __restrict__ A, const int4* __restrict__ tab, const int* __restrict__ starts,
+                                               int64_t r, int k)
 {
     const int4 tl = tab[r >> 9];
-    const int blk = (k >> 6) - tl.x;
-    if (blk < 0 || blk >= tl.y) return 0.f;
-    return __half2float(A[(((size_t)tl.z + blk) * 512 + (size_t)(r & 511)) * 64 + (k & 63)]);
+    for (int b = 0; b < tl.y; ++b) {
+        const int sb = starts[tl.x + b];
+        if (k >= sb && k < sb + 64) return __half2float(A[(((size_t)tl.z + b) * 512 + (size_t)(r & 511)) * 64 + (k - sb)]);
+    }
+    return 0.f;
 }
 
 __global__ void __launch_bounds__(256) k_gemm_simple_blocked(const __half* __restrict__ A, const int4* __restrict__ tab,
-                                                             const __half* __restrict__ Bt, int64_t M, int N, int K,
+                                                             const int* __restrict__ starts, const __half* __restrict__ Bt, int64_t M,
+                                                             int N, int K,
                                                              const float* __restrict__ scales, __half* __restrict__ D)
 {
     __shared__ float As[32][33], Bs[32][33];
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(256) k_gemm_simple_blocked(const __half* __res
     for (int k0 = 0; k0 < K; k0 += 32) {
         for (int i = threadIdx.x; i < 32 * 32; i += 256) {
             const int r = i >> 5, c = i & 31;
-            As[r][c] = (m0 + r < M) ? kb_blocked_at(A, tab, m0 + r, k0 + c) : 0.f;
+            As[r][c] = (m0 + r < M) ? kb_blocked_at(A, tab, starts, m0 + r, k0 + c) : 0.f;
             Bs[r][c] = (n0 + r < N) ? __half2float(Bt[(size_t)(n0 + r) * K + k0 + c]) : 0.f;
         }
         __syncthreads();
@@ -280,7 +286,8 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, int m_tiles, int n_tiles, int k_blocks, int n_total, int block_n,
                int ab_bf16, const float* __restrict__ scales, const __half* __restrict__ addend, int64_t m_rows,
-               const int4* __restrict__ a_tab /* K_B tile table, or null for a dense A */, int prefetch_tiles,
+               const int4* __restrict__ a_tab /* K_B tile table, or null for a dense A */,
+               const int* __restrict__ a_starts /* K_B: first W row (sample slot) of every stored block */, int prefetch_tiles,
                const float* __restrict__ fuse_w /* [n_total][FC] */, float* __restrict__ zpart /* [parts][m_rows][FC] */,
                int store_d /* 0: D is consumed by the fused filter only and never written */, int* __restrict__ err)
 {
@@ -334,12 +341,13 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / n_tiles, nt = tile % n_tiles;
-                // dense A: K block kb of rows mt*128..; blocked A (K_B): block (offset + kb) of the 512-pixel tile, rows
-                // (mt % 4) * 128.. inside it, multiplying rows (first block + kb) * 64.. of W
-                int kb_first = 0, kb_count = k_blocks, a_row = mt * BLOCK_M, a_row_step = 0, a_col_step = BLOCK_K;
+                // dense A: K block kb of rows mt*128..; blocked A (K_B): stored block (offset + kb) of the 512-pixel tile, rows
+                // (mt % 4) * 128.. inside it, multiplying the 64 rows of W that start at the block's first sample slot
+                int kb_count = k_blocks, a_row = mt * BLOCK_M, a_row_step = 0, a_col_step = BLOCK_K;
+                const int* my_starts = nullptr;
                 if (a_tab) {
                     const int4 tl = a_tab[mt >> 2];
-                    kb_first = tl.x;
+                    my_starts = a_starts + tl.x;
                     kb_count = tl.y;
                     a_row = tl.z * 512 + (mt & 3) * BLOCK_M;
                     a_row_step = 512;
@@ -358,8 +366,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_expect_tx(bar_full + 8 * stage, stage_tx);
                     tma_load_2d(smem_u32(smem_a + stage * A_STAGE_BYTES), &map_a, bar_full + 8 * stage, kb * a_col_step,
                                 a_row + kb * a_row_step);
-                    tma_load_2d(smem_u32(smem_b + stage * B_STAGE_BYTES), &map_b, bar_full + 8 * stage, (kb_first + kb) * BLOCK_K,
-                                nt * block_n);
+                    tma_load_2d(smem_u32(smem_b + stage * B_STAGE_BYTES), &map_b, bar_full + 8 * stage,
+                                my_starts ? my_starts[kb] : kb * BLOCK_K, nt * block_n);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -532,8 +540,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // D[rows][n_pad] (fp16) = scales[1] * A[rows][k_pad] . Bt[n_pad][k_pad]^T (+ addend), A and Bt 16-bit K-major
 // (ab_bf16: 0 = fp16, 1 = bf16).  k_pad % 64 == 0; n_pad is 64, 128 or a multiple of 256 (gl_m_pad).
 int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
-                   const float* scales, const void* addend, void* D, const int4* a_tab, int64_t a_total_blocks, gl_gemm_fuse* fuse)
+                   const float* scales, const void* addend, void* D, const int4* a_tab, int64_t a_total_blocks, gl_gemm_fuse* fuse,
+                   const int* a_starts)
 {
+    GL_REQUIRE(!a_tab == !a_starts, "gemm: the blocked operand needs both its tile table and its block starts");
     GL_REQUIRE(k_pad % 64 == 0 && n_pad % 64 == 0, "gemm: k_pad %d / n_pad %d must be multiples of 64", k_pad, n_pad);
     GL_REQUIRE(!(fuse && ctx->gemm_impl == 1), "gemm: the CUDA-core checker has no fused filter");
     if (ctx->gemm_impl == 1) {
@@ -541,8 +551,8 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
         GL_REQUIRE(ceil_div(rows, 32) < 2147483647ll, "gemm(simple): band too large");
         if (a_tab) {
             GL_REQUIRE(!ab_bf16 && !addend, "gemm(simple): the blocked operand is fp16 K_B without addend");
-            k_gemm_simple_blocked<<<grid, 256, 0, ctx->stream>>>((const __half*)A, a_tab, (const __half*)Bt, rows, n_pad, k_pad, scales,
-                                                                 (__half*)D);
+            k_gemm_simple_blocked<<<grid, 256, 0, ctx->stream>>>((const __half*)A, a_tab, a_starts, (const __half*)Bt, rows, n_pad, k_pad,
+                                                                 scales, (__half*)D);
         } else if (ab_bf16)
             k_gemm_simple<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bt, rows, n_pad,
                                                                          k_pad, scales, (const __half*)addend,
@@ -597,7 +607,7 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
         GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<S, CB, EW, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
         tc::k_gemm_tcgen05<S, CB, EW, FC><<<grid, 128 + 32 * EW, SM, ctx->stream>>>(                                            \
             map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad, block_n, ab_bf16, scales, (const __half*)addend, rows, a_tab, \
-            pf, fw, zp, store_d, (int*)err->ptr);                                                                                        \
+            a_starts, pf, fw, zp, store_d, (int*)err->ptr);                                                                                        \
     } while (0)
     if (!deep) {
         if (FCH == 1) GEMM_LAUNCH(3, 2, 8, 1);
@@ -641,7 +651,9 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
         phi->q0 = L_B->q0;
         const bool keep_phi = phi_out != nullptr;   // gl_nystroem_filter may be asked for z only: Phi then never leaves the chip
         if (keep_phi && (rc = gl_alloc(ctx, sizeof(__half) * (size_t)rows * m_pad, &phi->buf)) != GL_OK) break;
-        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)m_pad * p_pad, &Wt)) != GL_OK) break;
+        const int k_dim = p_pad + 64;   // K_B's internal sample slots
+        GL_REQUIRE(L_B->tiles && L_B->starts && L_B->perm, "nystroem: K_B handle without its block layout");
+        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)m_pad * k_dim, &Wt)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad, &colmax)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * 4, &scales)) != GL_OK) break;
 
@@ -652,7 +664,7 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
         GL_LAUNCH_CHECK(ctx);
         k_w_scale<<<1, 1024, 0, ctx->stream>>>((const float*)colmax->ptr, m, (float*)scales->ptr);
         GL_LAUNCH_CHECK(ctx);
-        k_w_write<<<m_pad, 256, 0, ctx->stream>>>(U, (int)phi_A->ld, p, m, p_pad, m_pad, mu_inv, neg_alpha,
+        k_w_write<<<m_pad, 256, 0, ctx->stream>>>(U, (int)phi_A->ld, m, k_dim, (const uint32_t*)L_B->perm->ptr, mu_inv, neg_alpha,
                                                   (const float*)scales->ptr, (__half*)Wt->ptr);
         GL_LAUNCH_CHECK(ctx);
 
@@ -675,7 +687,6 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
             phi->channels = C;
             phi->image_epoch = ctx->image_epoch;
         }
-        GL_REQUIRE(L_B->tiles, "nystroem: K_B handle without a tile table");
         gl_gemm_fuse fuse;
         gl_buf *wbuf = nullptr, *zpart = nullptr;
         const bool do_fuse = ff != nullptr;
@@ -692,8 +703,9 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
             fuse.zpart = (float*)zpart->ptr;
             fuse.C = C;
         }
-        rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, p_pad, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
-                            keep_phi ? phi->buf->ptr : nullptr, (const int4*)L_B->tiles->ptr, L_B->total_blocks, do_fuse ? &fuse : nullptr);
+        rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, k_dim, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
+                            keep_phi ? phi->buf->ptr : nullptr, (const int4*)L_B->tiles->ptr, L_B->total_blocks, do_fuse ? &fuse : nullptr,
+                            (const int*)L_B->starts->ptr);
         if (rc == GL_OK && do_fuse)
             rc = gl_filter_fused_finish(ctx, phi, (const float*)zpart->ptr, fuse.parts, (const float*)wbuf->ptr, U, (int)phi_A->ld,
                                         ff->clip_low, ff->z_f32, ff->z_u8);
