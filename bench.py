@@ -340,7 +340,9 @@ def main():
                            cache="working set (K_B + Phi = %.1f GB per GPU) far larger than the 126 MB L2; no flush needed"
                                  % (2 * band_px * (m_pad + (p + 63) // 64 * 64) / 1e9),
                            parallelism=f"pixel-row bands x{world}"),
-               e2e=dict(value=e2e_val, unit="Mpixel/s", h2d_bytes_per_step=n * channels, d2h_bytes_per_step=band_px * channels,
+               e2e=dict(value=e2e_val, unit="Mpixel/s",
+                        h2d_bytes_per_step=(n * channels if world == 1 else (band_px + p) * channels),   # N > 1: a rank uploads its band + the sample pixels
+                        d2h_bytes_per_step=band_px * channels,
                         ms_per_step=t_e2e / args.steps, result="filtered image as u8 (the reference's png bytes), per-rank band",
                         with_fp32_result=dict(value=n / (t_e2e_f32 / args.steps * 1e-3) / 1e6, ms_per_step=t_e2e_f32 / args.steps,
                                               d2h_bytes_per_step=band_px * channels * 4)),

@@ -776,6 +776,45 @@ int gl_mat_upload(gl_ctx* ctx, int kind, const double* data, int64_t rows, int64
 // -------------------------------------------------------------------------------------------
 // whole path: the stage order of hpc/image_processing.c:183-275 (restored block)
 // -------------------------------------------------------------------------------------------
+}  // extern "C"
+
+__global__ void k_scatter_sample_pixels(uint8_t* __restrict__ img, const uint32_t* __restrict__ samples, const uint8_t* __restrict__ vals,
+                                        int p, int C)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p * C) return;
+    img[(size_t)samples[i / C] * C + (i % C)] = vals[i];
+}
+
+// multi-GPU gl_run: the values of the p sampled pixels, gathered from the caller's host image, placed into ctx->img
+static int upload_sample_pixels(gl_ctx* ctx)
+{
+    const int p = (int)ctx->p, C = ctx->channels;
+    GL_REQUIRE(ctx->h_samples_valid && (int)ctx->h_samples.size() == p, "gl_run: no host copy of the sample indices");
+    gl_buf* vals = nullptr;
+    GL_CHECK(gl_alloc(ctx, (size_t)p * C, &vals));
+    int rc = gl_ensure_pinned(ctx, (size_t)p * C);
+    if (rc == GL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GL_ERR_CUDA;   // the pinned block may be in flight
+    if (rc == GL_OK) {
+        uint8_t* h = (uint8_t*)ctx->pinned;
+        for (int i = 0; i < p; ++i)
+            for (int ch = 0; ch < C; ++ch) h[(size_t)i * C + ch] = ctx->host_pixels[(size_t)ctx->h_samples[i] * C + ch];
+        StageTimer t(ctx, GL_T_H2D);
+        if (cudaMemcpyAsync(vals->ptr, h, (size_t)p * C, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = GL_ERR_CUDA;
+    }
+    if (rc == GL_OK) {
+        k_scatter_sample_pixels<<<(unsigned)ceil_div(p * C, 256), 256, 0, ctx->stream>>>((uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr,
+                                                                                         (const uint8_t*)vals->ptr, p, C);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = GL_ERR_CUDA;
+    }
+    if (rc == GL_ERR_CUDA) gl_set_error("gl_run: uploading the sample pixels failed");
+    gl_buf_release(vals);
+    return rc;
+}
+
+extern "C" {
+
 int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out,
                     double* eigvals_out)
 {
@@ -789,6 +828,7 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
     unsigned p = 0;
     if (prm->sampling_random) GL_CHECK(gl_sampling_random(ctx, requested, prm->seed, &p));
     else GL_CHECK(gl_sampling_uniform(ctx, requested, &p));
+    if (ctx->host_pixels) GL_CHECK(upload_sample_pixels(ctx));
 
     gl_mat *K_A = nullptr, *K_B = nullptr, *L_A = nullptr, *L_B = nullptr;
     gl_mat *U = nullptr, *mu = nullptr, *mu_inv = nullptr, *phi = nullptr, *f_mu = nullptr;
@@ -833,12 +873,24 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
 int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, const gl_params* prm, float* z_f32,
            uint8_t* z_u8, unsigned* p_out, int* m_out, double* eigvals_out)
 {
-    GL_REQUIRE(ctx, "gl_run: null");
+    GL_REQUIRE(ctx && pixels, "gl_run: null");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaEventRecord(ctx->ev_begin[GL_T_TOTAL], ctx->stream);
-    GL_CHECK(gl_set_image(ctx, pixels, width, height, channels));
+    if (ctx->world == 1) {
+        GL_CHECK(gl_set_image(ctx, pixels, width, height, channels));
+    } else {
+        // a rank of a multi-GPU run needs its own band of rows and the sampled pixels, nothing else: upload the band now, the
+        // p sample values right after the sampling stage (gl_run_resident); the rest of ctx->img is not meaningful
+        GL_CHECK(set_image_geometry(ctx, width, height, channels));
+        StageTimer t(ctx, GL_T_H2D);
+        GL_CUDA_CHECK(cudaMemcpyAsync((uint8_t*)ctx->img->ptr + (size_t)ctx->q0 * channels, pixels + (size_t)ctx->q0 * channels,
+                                      (size_t)(ctx->q1 - ctx->q0) * channels, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->host_pixels = pixels;
+    }
     ctx->total_started = true;
-    return gl_run_resident(ctx, prm, z_f32, z_u8, p_out, m_out, eigvals_out);
+    const int rc = gl_run_resident(ctx, prm, z_f32, z_u8, p_out, m_out, eigvals_out);
+    ctx->host_pixels = nullptr;
+    return rc;
 }
 
 }  // extern "C"

@@ -132,6 +132,7 @@ struct gl_ctx {
     int row0 = 0, row1 = 0;  // band of image rows owned by this rank
     int64_t q0 = 0, q1 = 0;  // raster range of the band
     gl_buf* img = nullptr;   // u8 [n * channels]
+    const uint8_t* host_pixels = nullptr;  // during a multi-GPU gl_run: the caller's host image (band + sample pixels are uploaded)
 
     unsigned long long image_epoch = 0;  // bumped by every gl_set_*image
     int filter_apply_impl = 0;  // 0 = warp-per-row kernel when the shape allows, 1 = always the generic kernel

@@ -173,6 +173,7 @@ GL_API int gl_full_laplacian(gl_ctx* ctx, gl_mat* K, gl_mat** L);
 GL_API int gl_full_result(gl_ctx* ctx, gl_mat* L, float* z_f32, uint8_t* z_u8);
 
 /* ---- whole path in one call (what hpc/image_processing.c:183-277 sequences) ------------------- */
+/* (world > 1: every rank passes the WHOLE host image; a rank copies only its band of rows and the sampled pixels to its GPU.) */
 GL_API int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, const gl_params* prm,
                   float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out, double* eigvals_out /* m, may be NULL */);
 /* Same, image already on the device (gl_set_image / gl_set_synthetic_image); no host copies unless z_* given. */
