@@ -310,7 +310,7 @@ def main():
     aff_ext_tf = (f_aff + f_ext) / ((med["k_affinity_b"] + med["k_gemm"]) * 1e-3) / 1e12
 
     # ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
-    NCU_TRAFFIC = {("c4", 1, "cutoff"): (20.74e9, "profiles/r01_ncu_full_c4_v4.txt"),
+    NCU_TRAFFIC = {("c4", 1, "cutoff"): (19.14e9, "profiles/r01_ncu_full_c4_v5.txt"),
                    ("c4", 1, "dense"): (33.9e9, "profiles/r01_ncu_full_c4.txt")}
     kept = stored_blocks / max(1, dense_blocks)
     if kept < 0.5:
@@ -320,7 +320,7 @@ def main():
         roof = dict(kernel="k_gemm_tcgen05 (Nystroem extrapolation over the stored K_B blocks)", bound="hbm", achieved=gemm_gbs,
                     peak=peaks["hbm"], unit="GB/s", frac=gemm_gbs / peaks["hbm"], traffic=tr[0] if tr else None,
                     traffic_source=tr[1] if tr else None, peak_source=peaks["source"] + " copy bandwidth", ms=med["k_gemm"],
-                    bytes=gemm_bytes, note="83 %% of these bytes are WRITES (Phi); a pure 17 GB write (torch fill) runs at 3.94 TB/s on "
+                    bytes=gemm_bytes, note="91 %% of these bytes are WRITES (Phi); a pure 17 GB write (torch fill) runs at 3.94 TB/s on "
                     "this part, the kernel writes at %.2f TB/s" % (band_px * m_pad * 2.0 / (med["k_gemm"] * 1e-3) / 1e12))
     else:
         tr = NCU_TRAFFIC.get((args.workload, world, "dense"))

@@ -218,14 +218,16 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
 __global__ void k_reduce_partials(const float* __restrict__ partial, int nblocks, int p_int, int ns, const uint32_t* __restrict__ perm,
                                   int p_pad, double* __restrict__ DT)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per output: lane l adds the CTA partials l, l + 32, ... in order, then a fixed shuffle tree (deterministic)
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= ns * p_int) return;
     const int which = i / p_int, slot = i - which * p_int;
     const uint32_t j = perm[slot];
     if (j == 0xffffffffu) return;
     double acc = 0.0;
-    for (int b = 0; b < nblocks; ++b) acc += (double)partial[(size_t)b * ns * p_int + i];
-    DT[(size_t)which * p_pad + j] = acc;
+    for (int b = lane; b < nblocks; b += 32) acc += (double)partial[(size_t)b * ns * p_int + i];
+    acc = warp_sum(acc);
+    if (lane == 0) DT[(size_t)which * p_pad + j] = acc;
 }
 
 // Layout of the stored K_B blocks (see the header).  Samples get an INTERNAL order: by column strip (S strips of equal
@@ -451,7 +453,7 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         if (rc != GL_OK) break;
 
         GL_CUDA_BREAK(rc, cudaMemsetAsync(KB->aux->ptr, 0, sizeof(double) * (size_t)(1 + C) * p_pad, ctx->stream));
-        k_reduce_partials<<<(unsigned)ceil_div((1 + C) * p_int, 128), 128, 0, ctx->stream>>>(
+        k_reduce_partials<<<(unsigned)ceil_div((1 + C) * p_int, 8), 256, 0, ctx->stream>>>(
             (const float*)partial->ptr, grid, p_int, 1 + C, (const uint32_t*)KB->perm->ptr, p_pad, (double*)KB->aux->ptr);
         GL_LAUNCH_CHECK(ctx);
         // ONE allreduce of the band-partial sums: D (p doubles) and T (C x p doubles)
