@@ -36,12 +36,14 @@ WORKLOADS = {
     "c2": (512, 512, 1, 256, "spatially_uniform", "bilateral"),
     "c5": (8192, 8192, 3, 2000, "random", "bilateral"),
     "hd": (1920, 1080, 1, 500, "random", "bilateral"),
+    "c5s": (8192, 1024, 3, 2000, "random", "bilateral"),   # one eighth of c5: what one rank of the 8-GPU run holds
 }
 DESCR = {
     "c4": "synthetic 3840x2160 (8.3 MP) grey, p=1000 random samples (seed 0), m=999, bilateral h_loc=40 h_val=30",
     "c2": "synthetic 512x512 grey, p=256 uniform, m=255",
     "c5": "synthetic 8192x8192 (67 MP) colour, p=2000 random, m=1999",
     "hd": "synthetic 1920x1080 grey, p=500 random, m=499",
+    "c5s": "synthetic 8192x1024 colour (one eighth of config 5), p=2000 random, m=1999",
 }
 SEED_IMG, SEED_SAMPLES = 1234, 0
 

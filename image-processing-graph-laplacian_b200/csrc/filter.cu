@@ -241,11 +241,16 @@ __global__ void __launch_bounds__(FL_THREADS) k_filter_apply(const __half* __res
 // (ii), fast path when a row is a whole number of warps' worth of 16-byte groups (m_pad % 256 == 0): one WARP per
 // row, lane l owns groups l, l+32, ...; w lives in registers; no block-level synchronisation at all, 2 rows
 // (2 * NGL independent 16-byte loads per lane) in flight.
+// A wide Phi (more than 12 / C groups per lane) is processed in column chunks of NGL * 256 columns, one launch each: the
+// first chunks leave the partial dot in z (`first` = start from 0, `last` = add y, clip, write the result).
 template <int C, int NGL>
 __global__ void __launch_bounds__(FL_THREADS) k_filter_apply_warp(const __half* __restrict__ phi, int64_t rows, int m_pad,
                                                                   const uint8_t* __restrict__ y, const float* __restrict__ w,
-                                                                  int clip_low, float* __restrict__ z, uint8_t* __restrict__ z8)
+                                                                  int clip_low, float* __restrict__ z, uint8_t* __restrict__ z8,
+                                                                  int col0 = 0, int first = 1, int last = 1)
 {
+    phi += col0;
+    w += (size_t)col0 * C;
     constexpr int RU = 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int WPC = FL_THREADS / 32;
@@ -288,11 +293,16 @@ __global__ void __launch_bounds__(FL_THREADS) k_filter_apply_warp(const __half* 
                 float d = dot[0];
 #pragma unroll
                 for (int ch = 1; ch < C; ++ch) d = lane == ch ? dot[ch] : d;
-                float val = (float)y[(size_t)r * C + lane] + d;
-                val = fminf(val, 255.f);                  // AboveXSetY(z, 255, 255), display.c:76
-                if (clip_low) val = fmaxf(val, 0.f);
-                if (z) z[(size_t)r * C + lane] = val;
-                if (z8) z8[(size_t)r * C + lane] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);
+                if (!first) d += z[(size_t)r * C + lane];
+                if (!last) {
+                    z[(size_t)r * C + lane] = d;          // partial dot of the column chunks so far
+                } else {
+                    float val = (float)y[(size_t)r * C + lane] + d;
+                    val = fminf(val, 255.f);                  // AboveXSetY(z, 255, 255), display.c:76
+                    if (clip_low) val = fmaxf(val, 0.f);
+                    if (z) z[(size_t)r * C + lane] = val;
+                    if (z8) z8[(size_t)r * C + lane] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);
+                }
             }
         }
     }
@@ -430,20 +440,28 @@ static int run_filter(gl_ctx* ctx, gl_mat* phi, const FilterGeom& g, const doubl
     GL_LAUNCH_CHECK(ctx);
     {
         StageTimer kt(ctx, GL_T_K_FILTER_APPLY);
-        const int ngl = (g.G % 32 == 0) ? g.G / 32 : 0;
+        const int ngl = (g.G % 32 == 0) ? g.G / 32 : 0;   // 16-byte groups per lane when a warp owns a row
         int wgrid = ctx->sm_count * 8;
         if ((int64_t)wgrid * 16 > rows) wgrid = (int)ceil_div(rows, 16);
-        if (ctx->filter_apply_impl == 1 || ngl == 0 || ngl * C > 12)
+        constexpr int MAXG = 12 / C;   // groups per lane whose weights fit in registers
+        if (ctx->filter_apply_impl == 1 || ngl == 0) {
             k_filter_apply<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, w, clip_low, z, z8);
-#define FLW_CASE(N)                                                                                                     \
-    else if (ngl == N) {                                                                                                \
-        if constexpr (N * C <= 12)                                                                                      \
-            k_filter_apply_warp<C, N><<<wgrid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, y, w, clip_low, z, z8);     \
+        } else {
+            // column chunks of at most MAXG groups per lane (one chunk unless Phi is very wide or has three channels)
+            for (int g0 = 0; g0 < ngl; g0 += MAXG) {
+                const int n = ngl - g0 < MAXG ? ngl - g0 : MAXG;
+                const int col0 = g0 * 256, first = g0 == 0, last = g0 + n >= ngl;
+#define FLW_CASE(N)                                                                                                                  \
+    if (n == N) {                                                                                                                      \
+        if constexpr (N <= MAXG)                                                                                                       \
+            k_filter_apply_warp<C, N><<<wgrid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, y, w, clip_low, z, z8, col0, first, last); \
     }
-        FLW_CASE(1) FLW_CASE(2) FLW_CASE(3) FLW_CASE(4) FLW_CASE(5) FLW_CASE(6) FLW_CASE(7) FLW_CASE(8) FLW_CASE(9)
-        FLW_CASE(10) FLW_CASE(11) FLW_CASE(12)
+                FLW_CASE(1) FLW_CASE(2) FLW_CASE(3) FLW_CASE(4) FLW_CASE(5) FLW_CASE(6) FLW_CASE(7) FLW_CASE(8) FLW_CASE(9)
+                FLW_CASE(10) FLW_CASE(11) FLW_CASE(12)
 #undef FLW_CASE
-        else k_filter_apply<C, NG><<<grid, FL_THREADS, 0, ctx->stream>>>(P, rows, m_pad, g.G, g.TPR, g.RL, y, w, clip_low, z, z8);
+                if (!last) ctx->launches++;
+            }
+        }
     }
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;

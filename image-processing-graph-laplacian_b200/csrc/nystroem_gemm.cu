@@ -433,9 +433,11 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(bar_tfull + 8 * acc, acc_phase, err, 4);
             tcgen05_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * MAX_BLOCK_N);
-            float dot[FC > 0 ? FC : 1];
+            float dot[FC > 0 ? FC : 1][4];   // four independent accumulation chains per channel (column mod 4): the FMAs pipeline
 #pragma unroll
-            for (int q = 0; q < (FC > 0 ? FC : 1); ++q) dot[q] = 0.f;
+            for (int q = 0; q < (FC > 0 ? FC : 1); ++q)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dot[q][u] = 0.f;
             const int c_end = split ? c_hi : (ch == 0 ? n_size : 0);
             for (int c0 = (split ? c_lo : 0); c0 < c_end; c0 += 64) {
                 uint8_t* slab = slab0 + buf * C_SLAB_BYTES;
@@ -484,7 +486,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 for (int i = 0; i < 8; ++i) {
                                     const float val = __uint_as_float(v[h][8 * g8 + i]) * sc;
 #pragma unroll
-                                    for (int q = 0; q < FC; ++q) dot[q] = fmaf(val, wr[i * FC + q], dot[q]);
+                                    for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
                                 }
                             }
                         }
@@ -517,7 +519,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (row < m_rows) {   // a share that had no columns (narrow N tile) writes its zero
                     const int part = nt * SHARES + ch;
 #pragma unroll
-                    for (int q = 0; q < FC; ++q) zpart[((size_t)part * m_rows + row) * FC + q] = dot[q];
+                    for (int q = 0; q < FC; ++q)
+                        zpart[((size_t)part * m_rows + row) * FC + q] = (dot[q][0] + dot[q][1]) + (dot[q][2] + dot[q][3]);
                 }
             }
         }

@@ -280,6 +280,17 @@ def test_config5_shape_colour_p2000(ctx):
     err_z, err_dz = _rel(r["z"], ref["z"]), _rel(r["z"] - img, ref["z"] - img)
     print(f"config-5 shape {W}x{H}x3 p={p}: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
     assert err_mu <= TOL_MU and err_z <= TOL_Z and err_dz <= TOL_DZ
+    # the stages apart: the wide three-channel Phi goes through the column-chunked warp apply (and the generic kernel)
+    for impl in ("warp", "generic"):
+        ctx.set_option("fuse_filter", 0)
+        ctx.set_option("filter_apply", impl)
+        try:
+            r2 = ctx.run(img, prm)
+        finally:
+            ctx.set_option("fuse_filter", 1)
+            ctx.set_option("filter_apply", "warp")
+        assert _rel(r2["z"], ref["z"]) <= TOL_Z and _rel(r2["z"] - img, ref["z"] - img) <= TOL_DZ, impl
+        assert _rel(r2["z"], r["z"].astype(np.float64)) < 5e-5, impl
 
 
 def test_projection_and_apply_variants_agree(ctx, golden):
