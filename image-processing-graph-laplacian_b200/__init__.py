@@ -40,7 +40,7 @@ EXPORTS = [
     "gl_affinity", "gl_laplacian", "gl_eigensolve", "gl_nystroem", "gl_nystroem_filter", "gl_orthonormalise", "gl_filter",
     "gl_diag_inverse", "gl_diag_pow", "gl_full_affinity", "gl_full_laplacian", "gl_full_result", "gl_run", "gl_run_resident",
     "gl_mat_info_get", "gl_mat_retain", "gl_mat_destroy", "gl_mat_download", "gl_mat_rowsums", "gl_mat_upload",
-    "gl_host_alloc", "gl_host_free",
+    "gl_host_alloc", "gl_host_free", "gl_kb_layout_host",
 ]
 
 
@@ -117,6 +117,8 @@ def lib():
         L.gl_mat_download.argtypes = [vp, vp, vp, C.c_size_t]
         L.gl_mat_rowsums.argtypes = [vp, vp, vp, C.c_size_t]
         L.gl_mat_upload.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(vp)]
+        L.gl_kb_layout_host.argtypes = [C.c_int, C.c_int64, C.c_int64, vp, C.c_uint, C.c_double, C.c_int, C.c_int, ip,
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, vp, vp, vp]
         L.gl_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.gl_host_free.argtypes = [vp]
         L.gl_default_params.argtypes = [C.POINTER(Params)]
@@ -143,6 +145,21 @@ def default_params(**kw) -> Params:
                 raise TypeError(f"unknown parameter {k}")
             setattr(p, k, v)
     return p
+
+
+def kb_layout(width, q0, q1, samples, h_loc=40.0, cutoff=True, strips=0):
+    """Host-only: the block layout gl_affinity gives K_B (gl_kb_layout_host).  Returns a dict with strips, tile_first,
+    tile_count, starts, perm."""
+    s = np.ascontiguousarray(samples, dtype=np.uint32)
+    S, nt, nb = C.c_int(), C.c_int64(), C.c_int64()
+    _check(lib().gl_kb_layout_host(width, q0, q1, s.ctypes.data, len(s), h_loc, int(cutoff), strips, C.byref(S), C.byref(nt),
+                                   C.byref(nb), None, None, None, None))
+    first, count = np.empty(nt.value, np.int32), np.empty(nt.value, np.int32)
+    starts = np.empty(nb.value, np.int32)
+    perm = np.empty((len(s) + 63) // 64 * 64 + 64, np.uint32)
+    _check(lib().gl_kb_layout_host(width, q0, q1, s.ctypes.data, len(s), h_loc, int(cutoff), strips, C.byref(S), C.byref(nt),
+                                   C.byref(nb), first.ctypes.data, count.ctypes.data, starts.ctypes.data, perm.ctypes.data))
+    return dict(strips=S.value, tile_first=first, tile_count=count, starts=starts, perm=perm, n_blocks=nb.value)
 
 
 def device_count() -> int:

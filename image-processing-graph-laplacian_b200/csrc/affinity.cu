@@ -248,11 +248,17 @@ struct KbLayout {
     int64_t total = 0;
 };
 
-static void kb_layout_for(const gl_ctx* ctx, const std::vector<uint32_t>& samples, bool cut, int64_t R, int S, bool count_only, KbLayout* out,
+struct KbGeom {
+    int W;            // image width
+    int64_t q0, q1;   // raster range of the band
+    int p_pad;        // sample count rounded up to 64
+};
+
+static void kb_layout_for(const KbGeom& geo, const std::vector<uint32_t>& samples, bool cut, int64_t R, int S, bool count_only, KbLayout* out,
                           int64_t tile_stride = 1 /* count_only: visit every tile_stride-th tile */)
 {
-    const int p = (int)samples.size(), W = ctx->width, p_pad = ctx->p_pad, p_int = p_pad + 64;
-    const int64_t n_band = ctx->q1 - ctx->q0;
+    const int p = (int)samples.size(), W = geo.W, p_pad = geo.p_pad, p_int = p_pad + 64;
+    const int64_t n_band = geo.q1 - geo.q0;
     const int64_t tiles = (n_band + AFF_TP - 1) / AFF_TP;
     // internal order: (strip, raster index); the input is ascending, so a stable bucket pass does it
     std::vector<int> strip_of(p), strip_begin(S + 1, 0);
@@ -293,7 +299,7 @@ static void kb_layout_for(const gl_ctx* ctx, const std::vector<uint32_t>& sample
         if (!cut) {
             emit(0, p_pad);
         } else {
-            const int64_t qa = ctx->q0 + t * AFF_TP, qb = std::min(ctx->q1, qa + AFF_TP) - 1;
+            const int64_t qa = geo.q0 + t * AFF_TP, qb = std::min(geo.q1, qa + AFF_TP) - 1;
             const int64_t ra = qa / W, rb = qb / W;
             // column intervals the tile's pixels occupy: one or two row segments, or whole rows
             int64_t seg[2][2];
@@ -319,6 +325,55 @@ static void kb_layout_for(const gl_ctx* ctx, const std::vector<uint32_t>& sample
     }
 }
 
+// reach of the spatial term in pixels: |d| > h_loc sqrt(25 ln 2)  =>  exp(-d^2/h_loc^2) < 2^-25  =>  the fp16 value is 0;
+// one more pixel for rounding slack
+static int64_t kb_reach(double h_loc)
+{
+    const double rr = std::floor(h_loc * std::sqrt(25.0 * 0.6931471805599453)) + 1.0;
+    return rr < 1e9 ? (int64_t)rr : (int64_t)1e9;
+}
+
+// picks the strip count (forced_S > 0: that one) and builds the layout; returns the strip count
+static int kb_choose_and_build(const KbGeom& geo, const std::vector<uint32_t>& samples, bool cut, int64_t R, int forced_S, KbLayout* lay)
+{
+    int best_S = 1;
+    if (cut) {
+        if (forced_S > 0) {
+            best_S = forced_S;
+        } else {
+            int64_t best = -1;
+            for (int S : {1, 2, 3, 4, 5, 6, 8, 10, 12, 16}) {
+                if (S > 1 && (geo.W / S < 64 || 2 * R * S > 4 * (int64_t)geo.W)) continue;   // strips much narrower than the reach cannot help
+                kb_layout_for(geo, samples, true, R, S, true, lay, 7);   // a sample of the tiles is enough to rank the candidates
+                if (best < 0 || lay->total < best) { best = lay->total; best_S = S; }
+            }
+        }
+    }
+    kb_layout_for(geo, samples, cut, R, best_S, false, lay);
+    return best_S;
+}
+
+// Host-only view of the layout (no GPU, no context): what gl_affinity would store for these samples.  Used by the CPU tests.
+extern "C" int gl_kb_layout_host(int width, int64_t q0, int64_t q1, const uint32_t* samples, unsigned p, double h_loc, int cutoff,
+                                 int strips, int* strips_out, int64_t* n_tiles, int64_t* n_blocks, int32_t* tile_first,
+                                 int32_t* tile_count, int32_t* starts, uint32_t* perm)
+{
+    GL_REQUIRE(samples && p >= 1 && width > 0 && q1 > q0 && h_loc > 0, "gl_kb_layout_host: bad arguments");
+    for (unsigned i = 1; i < p; ++i) GL_REQUIRE(samples[i] > samples[i - 1], "gl_kb_layout_host: samples must be strictly ascending");
+    const KbGeom geo = {width, q0, q1, (int)round_up(p, 64)};
+    std::vector<uint32_t> sv(samples, samples + p);
+    KbLayout lay;
+    const int S = kb_choose_and_build(geo, sv, cutoff != 0, kb_reach(h_loc), strips, &lay);
+    if (strips_out) *strips_out = S;
+    if (n_tiles) *n_tiles = (int64_t)lay.tab.size();
+    if (n_blocks) *n_blocks = lay.total;
+    if (tile_first && tile_count)
+        for (size_t t = 0; t < lay.tab.size(); ++t) { tile_first[t] = lay.tab[t].x; tile_count[t] = lay.tab[t].y; }
+    if (starts) memcpy(starts, lay.starts.data(), sizeof(int) * lay.starts.size());
+    if (perm) memcpy(perm, lay.perm.data(), sizeof(uint32_t) * lay.perm.size());
+    return GL_OK;
+}
+
 static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
 {
     const int p = (int)ctx->p, W = ctx->width;
@@ -329,28 +384,14 @@ static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
         ctx->h_samples_valid = true;
     }
     const bool cut = ctx->kb_cutoff && kind != GL_PHOTOMETRIC;
-    // |d| > h_loc sqrt(25 ln 2)  =>  exp(-d^2/h_loc^2) < 2^-25  =>  the fp16 value is 0; one more pixel for rounding slack
-    const double rr = std::floor(h_loc * std::sqrt(25.0 * 0.6931471805599453)) + 1.0;
-    const int64_t R = rr < 1e9 ? (int64_t)rr : (int64_t)1e9;
+    const int64_t R = kb_reach(h_loc);
     const int64_t key[6] = {W, ctx->q0, ctx->q1, p, R, (cut ? 1 : 0) + 2 * ctx->kb_strips};
     if (ctx->tile_tab && !memcmp(key, ctx->tab_key, sizeof(key)) && ctx->tab_samples.size() == (size_t)p &&
         !memcmp(ctx->tab_samples.data(), ctx->h_samples.data(), sizeof(uint32_t) * p))
         return GL_OK;  // same geometry, samples and cutoff as last time: the cached layout stands
     KbLayout lay;
-    int best_S = 1;
-    if (cut) {
-        if (ctx->kb_strips > 0) {
-            best_S = ctx->kb_strips;
-        } else {
-            int64_t best = -1;
-            for (int S : {1, 2, 3, 4, 5, 6, 8, 10, 12, 16}) {
-                if (S > 1 && (W / S < 64 || 2 * R * S > 4 * (int64_t)W)) continue;   // strips much narrower than the reach cannot help
-                kb_layout_for(ctx, ctx->h_samples, true, R, S, true, &lay, 7);   // a sample of the tiles is enough to rank the candidates
-                if (best < 0 || lay.total < best) { best = lay.total; best_S = S; }
-            }
-        }
-    }
-    kb_layout_for(ctx, ctx->h_samples, cut, R, best_S, false, &lay);
+    const KbGeom geo = {W, ctx->q0, ctx->q1, ctx->p_pad};
+    const int best_S = kb_choose_and_build(geo, ctx->h_samples, cut, R, ctx->kb_strips, &lay);
     GL_REQUIRE(lay.total < 0x7fffffff / 512, "affinity: K_B has too many blocks for 32-bit tile coordinates");
     // upload: table, block starts, permutation (one staging pass through the pinned block each)
     gl_buf** dst[3] = {&ctx->tile_tab, &ctx->tile_starts, &ctx->tile_perm};

@@ -192,6 +192,15 @@ GL_API int gl_mat_rowsums(gl_ctx* ctx, const gl_mat* K_B, double* out, size_t ca
 /* Upload a host fp64 row-major matrix as GL_MAT_KA / GL_MAT_EIGVEC / GL_MAT_DIAG (tests, host-built inputs). */
 GL_API int gl_mat_upload(gl_ctx* ctx, int kind, const double* data, int64_t rows, int64_t cols, gl_mat** out);
 
+/* ---- inspection (host only, no GPU needed) ------------------------------------------------------------------------
+ * The storage layout gl_affinity gives K_B for these (strictly ascending) samples over the raster range [q0, q1): per
+ * 512-pixel tile `tile_count` blocks of 64 sample slots whose first slots are starts[tile_first ...]; perm[slot] = index
+ * of the sample in `samples` (0xffffffff: empty), p_pad + 64 slots with p_pad = p rounded up to 64.  Call once with the
+ * arrays NULL to learn n_tiles / n_blocks.  strips = 0 lets the library choose the number of column strips. */
+GL_API int gl_kb_layout_host(int width, int64_t q0, int64_t q1, const uint32_t* samples, unsigned p, double h_loc, int cutoff,
+                             int strips, int* strips_out, int64_t* n_tiles, int64_t* n_blocks, int32_t* tile_first,
+                             int32_t* tile_count, int32_t* starts, uint32_t* perm);
+
 /* ---- pinned host memory for callers that want async copies ------------------------------------ */
 GL_API int gl_host_alloc(void** p, size_t bytes);
 GL_API int gl_host_free(void* p);

@@ -1,0 +1,88 @@
+"""CPU tests of the K_B storage layout (gl_kb_layout_host: the host logic behind gl_affinity's spatial cutoff, no GPU
+needed).  Properties checked with numpy:
+  * perm is a bijection from the occupied internal slots onto the samples; samples are ordered by column strip, then raster;
+  * the blocks of a tile are ascending, start at multiples of 8, never overlap and stay inside the slot range;
+  * COVERAGE: every (tile, sample) pair whose kernel value can exceed the fp16 flush-to-zero threshold 2^-25 -- i.e. whose
+    sample lies within h_loc*sqrt(25 ln 2) of some pixel of the tile -- is covered by exactly one block of that tile;
+  * without a cutoff every block is stored, aligned."""
+import numpy as np
+import pytest
+
+import ipgl_b200 as gl
+from oracle import oracle_np as o
+
+TP = 512
+
+
+def _covered(lay, t):
+    """internal slots covered by tile t's blocks (each at most once)"""
+    st = lay["starts"][lay["tile_first"][t]: lay["tile_first"][t] + lay["tile_count"][t]]
+    assert np.all(st % 8 == 0) and np.all(np.diff(st) >= 64), "blocks must be ascending, aligned to 8 and disjoint"
+    return st, np.concatenate([np.arange(s, s + 64) for s in st])
+
+
+@pytest.mark.parametrize("W,H,p,h_loc,method,band", [
+    (3840, 400, 300, 40.0, "random", None),        # wide image: several column strips pay off
+    (640, 480, 400, 12.0, "uniform", None),
+    (301, 203, 77, 9.0, "random", (50, 140)),      # ragged sizes, a band of rows (one rank of a multi-GPU run)
+    (97, 61, 40, 40.0, "uniform", None),           # reach larger than the image: everything must be covered
+    (200, 2000, 600, 10.0, "random", (1000, 2000)),
+])
+def test_layout_covers_every_pair_within_reach_exactly_once(W, H, p, h_loc, method, band):
+    s = o.random_sampling(W, H, p, 3) if method == "random" else o.uniform_sampling(W, H, p)
+    p = len(s)
+    r0, r1 = band if band else (0, H)
+    q0, q1 = r0 * W, r1 * W
+    lay = gl.kb_layout(W, q0, q1, s, h_loc=h_loc)
+    p_pad = (p + 63) // 64 * 64
+    perm = lay["perm"]
+    assert perm.shape == (p_pad + 64,)
+    occ = perm != 0xFFFFFFFF
+    assert occ.sum() == p and np.array_equal(np.sort(perm[occ]), np.arange(p))
+    assert np.all(occ[:p]) and not np.any(occ[p:])                     # occupied slots are the first p
+    # internal order: by strip, then raster (strip = col * S // W)
+    S = lay["strips"]
+    col = (s % W).astype(np.int64)
+    key = (col * S // W) * (W * H) + s.astype(np.int64)
+    assert np.all(np.diff(key[perm[:p]]) > 0)
+    slot_of = np.empty(p, np.int64)
+    slot_of[perm[:p]] = np.arange(p)
+    cut2 = (h_loc ** 2) * 25.0 * np.log(2.0)
+    sr, sc = (s // W).astype(np.int64), col
+    n_tiles = (q1 - q0 + TP - 1) // TP
+    assert len(lay["tile_first"]) == n_tiles and lay["tile_count"].min() >= 1
+    assert lay["tile_first"][0] == 0 and np.array_equal(lay["tile_first"][1:], np.cumsum(lay["tile_count"])[:-1])
+    stored = 0
+    for t in range(n_tiles):
+        st, slots = _covered(lay, t)
+        assert slots.max() < p_pad + 64
+        stored += len(st)
+        q = np.arange(q0 + t * TP, min(q1, q0 + (t + 1) * TP))
+        pr, pc = q // W, q % W
+        # distance of every sample to the nearest pixel of the tile
+        d2 = ((sr[:, None] - pr[None, :]) ** 2 + (sc[:, None] - pc[None, :]) ** 2).min(axis=1)
+        need = slot_of[d2 <= cut2]
+        assert np.isin(need, slots).all(), f"tile {t}: a sample within reach is not covered"
+    assert stored == lay["n_blocks"]
+
+
+def test_layout_without_cutoff_is_dense_and_aligned():
+    W, H, p = 320, 200, 150
+    s = o.uniform_sampling(W, H, p)
+    lay = gl.kb_layout(W, 0, W * H, s, h_loc=5.0, cutoff=False)
+    p_pad = (len(s) + 63) // 64 * 64
+    assert lay["strips"] == 1 and np.all(lay["tile_count"] == p_pad // 64)
+    assert np.array_equal(lay["starts"][: p_pad // 64], np.arange(0, p_pad, 64))
+    assert np.array_equal(lay["perm"][: len(s)], np.arange(len(s)))
+
+
+def test_layout_cutoff_shrinks_storage_at_4k():
+    """BASELINE config 4's geometry: the column-strip layout keeps ~10 % of the dense blocks (20 % with rows alone)."""
+    from oracle import oracle_c as oc
+    W, H, p = 3840, 2160, 1000
+    s = oc.random_sampling(W, H, p, 0)
+    dense = (W * H // TP) * 16
+    auto = gl.kb_layout(W, 0, W * H, s)
+    rows_only = gl.kb_layout(W, 0, W * H, s, strips=1)
+    assert auto["n_blocks"] == 26849 and rows_only["n_blocks"] < 0.25 * dense     # 26 849: what the B200 bench reports
+    assert auto["strips"] > 1 and auto["n_blocks"] < 0.6 * rows_only["n_blocks"]
