@@ -1,15 +1,20 @@
-"""GPU tuning harness for the eigensolver on a C4-like L_A (tools/LA_c4_probe.npy, built with D from a strided subsample)."""
+"""GPU tuning harness for the eigensolver on the L_A of the C4 workload (built on the device, downloaded, solved with numpy
+for reference)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import ipgl_b200 as gl
 
-A = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "LA_c4_probe.npy"))
-w, V = np.linalg.eigh(A)
-p = A.shape[0]
 os.environ["GLB200_VERBOSE"] = "1"
 with gl.Context(0) as ctx:
     ctx.set_option("verbose", 1)
+    ctx.set_synthetic_image(3840, 2160, 1, 1234)
+    ctx.sampling(gl.RANDOM, 1000, 0)
+    K_A, K_B = ctx.affinity()
+    L_A, L_B = ctx.laplacian(K_A, K_B)
+    A = L_A.download()
+    w, V = np.linalg.eigh(A)
+    p = A.shape[0]
     L = ctx.upload(gl.MAT_KA, A)
     for tol, inner in ((2e-6, 0), (2e-6, 1), (2e-6, 2), (1e-5, 0), (1e-5, 1), (5e-5, 1), (5e-5, 0)):
         ctx.set_option("jacobi_tol", tol)
