@@ -80,7 +80,9 @@ __global__ void k_affinity_A(const uint8_t* __restrict__ img, const uint32_t* __
 // K_B tile kernel.  Thread (tx = tid % 8, ty = tid / 8): 8 consecutive samples of the current 64-sample
 // chunk x pixels ty, ty+32, ... of the tile.  A warp stores 4 pixel rows x 128 contiguous bytes.
 template <int KIND, int C>
-__global__ void __launch_bounds__(AFF_THREADS, 2)
+// three CTAs per SM for grey images (80 registers), two for colour (the third would spill)
+#define AFF_CTAS_PER_SM(C) ((C) == 1 ? 3 : 2)
+__global__ void __launch_bounds__(AFF_THREADS, AFF_CTAS_PER_SM(C))
 k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int p_pad /* = p_int: internal sample slots */, int width,
              int64_t q0, int64_t q1, float a2, float b2,  // -log2(e)/h_loc^2, -log2(e)/h_val^2
              const int4* __restrict__ tab /* per tile: first entry of its block list, block count, storage offset */,
@@ -451,7 +453,7 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
     gl_mat* KA = gl_mat_new(ctx, GL_MAT_KA);
     gl_mat* KB = gl_mat_new(ctx, GL_MAT_KB);
     gl_buf *sf = nullptr, *partial = nullptr;
-    const int grid = ctx->sm_count * 2;
+    const int grid = ctx->sm_count * AFF_CTAS_PER_SM(C);
     int rc = GL_OK;
     do {
         KA->rows = KA->cols = KA->local_rows = p;
