@@ -16,14 +16,14 @@
 //   * coordinates and grey values are integers: differences are exact in fp32, the two bandwidth
 //     factors are applied to the exact squared distances, one ex2 per pair (the reference takes two exps
 //     and multiplies, hpc/affinity.c:99,107,110 -- equal up to rounding).
-//   * K_B is stored in BLOCKS of [512 pixels][64 samples] fp16 (a pixel row of a block = 128 contiguous bytes), and only
-//     the blocks that can hold a non-zero are stored: the samples are in ascending raster order, hence sorted by image
-//     row, so for a 512-pixel tile covering rows [ra, rb] the samples within R rows form a contiguous range, and
-//     everything outside it has exp(-dr^2/h_loc^2) < 2^-25, which fp16 storage flushes to zero anyway
-//     (R = floor(h_loc sqrt(25 ln 2)) + 1).  The tile table {first block, block count, block offset} is
-//     built on the host from the sample indices and cached.  Photometric affinity has no cutoff: every block is stored
-//     and the layout degenerates to a dense blocked matrix.  At 4K / p=1000 / h_loc=40 this keeps ~21 % of the blocks:
-//     the kernel evaluations, the K_B bytes and the extrapolation GEMM's K loop all shrink by that factor.
+//   * K_B is stored in BLOCKS of [512 pixels][64 sample slots] fp16 (a pixel row of a block = 128 contiguous bytes), and
+//     only blocks that can hold a non-zero are stored.  The kernels use an internal sample order (column strip, then
+//     raster index); for a 512-pixel tile the samples within reach R = floor(h_loc sqrt(25 ln 2)) + 1 in rows AND columns
+//     are a few contiguous runs of that order, everything else has exp(-d^2/h_loc^2) < 2^-25, which fp16 storage flushes
+//     to zero anyway.  The layout {tile table, block starts, permutation} is built on the host and cached
+//     (kb_layout_for below).  Photometric affinity has no cutoff: every block is stored and the layout degenerates to
+//     a dense blocked matrix.  At 4K / p=1000 / h_loc=40 this keeps ~10 % of the blocks: the kernel evaluations, the K_B
+//     bytes and the extrapolation GEMM's K loop all shrink by that factor.
 #include <algorithm>
 #include <cmath>
 

@@ -4,14 +4,18 @@
 //
 //   Phi[q, j] = sum_s K_B[q, s] * W[s, j],   W = -alpha * U * diag(1/mu)        (p x m)
 //
-//   * A operand  = K_B band, [pixels x p_pad] fp16, K-major  -> M = pixels (128 per CTA tile)
-//   * B operand  = W^T, [m_pad x p_pad] fp16, K-major, scaled by one power of two so that it sits at the
-//                  top of the fp16 range (W itself is ~1e-4 and would be subnormal); unscaled in the epilogue
+//   * A operand  = K_B band in its blocked storage ([block][512 pixels][64 sample slots] fp16, K-major; affinity.cu):
+//                  M = 128 pixels per tile, the K loop walks the tile's stored blocks only
+//   * B operand  = W^T, [m_pad x (p_pad + 64)] fp16, K-major, columns in K_B's internal sample order, scaled by one power
+//                  of two so that it sits at the top of the fp16 range (W itself is ~1e-4 and would be subnormal);
+//                  unscaled in the epilogue; a block's 64 rows of W start at the block's first sample slot
 //   * D          = fp32 accumulators in TMEM (2 x 256 columns, double buffered), written as fp16 Phi (|Phi| <~ 1:
 //                  fp16's 11-bit mantissa beats bf16's 8 and the filter sums cancel heavily)
-//   * TMA (SWIZZLE_128B) feeds a 4-stage shared-memory ring; one elected thread issues tcgen05.mma;
-//     four epilogue warps drain TMEM with tcgen05.ld, convert, stage swizzled rows in shared memory and
-//     TMA-store them while the next tile's MMAs run.
+//   * TMA (SWIZZLE_128B) feeds a shared-memory ring; one elected thread issues tcgen05.mma; the epilogue warps drain
+//     TMEM with tcgen05.ld, convert, stage swizzled rows in shared memory and TMA-store them while the next tile's MMAs
+//     run.  Long K loops: 4 stages, 4 epilogue warps; short K loops (blocked K_B): 3 stages, 8 epilogue warps, L2 prefetch.
+//   * optionally (gl_nystroem_filter) the epilogue also accumulates each row's product with the filter weights from the fp32
+//     accumulators, so that the filter needs no second pass over Phi -- and, with no Phi requested, nothing is stored.
 //   * every pixel's row is written at its raster position, so there is no permutation pass; the p sample
 //     rows are then overwritten with Phi_A (nystroem.c:25-34).
 // A plain CUDA-core kernel (option gemm=simple) computes the same thing for cross-checking in tests.
