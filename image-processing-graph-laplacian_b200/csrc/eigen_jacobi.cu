@@ -57,24 +57,28 @@ __device__ __forceinline__ void tournament(int step, int pair, int nb, int& a, i
 }
 
 // One panel pair (I, J): load the two panels, form the 16 x 16 Gram block, diagonalise it, rotate the panels.
-__device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I, int J, float tol, int inner_max, float* P, float* red, double* Bm,
-                                            double* Qm, double* cs, int* role, int* pq, float* s_off, unsigned* s_cta_off)
+// `pc` = rows of the pair that fit in shared memory at once: the whole panels when p <= pc (loaded once, rotated in place),
+// otherwise the Gram block is accumulated chunk by chunk and the chunks are fetched a second time for the rotation.
+__device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc, int I, int J, float tol, int inner_max, float* P, float* red,
+                                            double* Bm, double* Qm, double* cs, int* role, int* pq, float* s_off, unsigned* s_cta_off)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     const int bi = tid >> 4, bj = tid & 15;  // this thread's element of the 16 x 16 block
     float* GI = G + (size_t)I * p * JB;
     float* GJ = G + (size_t)J * p * JB;
-    // ---- load the panel pair (L2 loads: the data was written by other SMs) ----
-    for (int idx = tid; idx < 2 * p; idx += J_THREADS) {
-        const int r = idx >> 1, h = idx & 1;
-        float4 a = __ldcg((const float4*)(GI + (size_t)r * JB + h * 4));
-        float4 b = __ldcg((const float4*)(GJ + (size_t)r * JB + h * 4));
-        *(float4*)(P + (size_t)r * JP + h * 4) = a;
-        *(float4*)(P + (size_t)r * JP + JB + h * 4) = b;
-    }
+    const int nchunks = (p + pc - 1) / pc;
+    // rows [r0, r0 + n) of the panel pair -> P (L2 loads: the data was written by other SMs)
+    auto load_chunk = [&](int r0, int n) {
+        for (int idx = tid; idx < 2 * n; idx += J_THREADS) {
+            const int r = idx >> 1, h = idx & 1;
+            float4 a = __ldcg((const float4*)(GI + (size_t)(r0 + r) * JB + h * 4));
+            float4 b = __ldcg((const float4*)(GJ + (size_t)(r0 + r) * JB + h * 4));
+            *(float4*)(P + (size_t)r * JP + h * 4) = a;
+            *(float4*)(P + (size_t)r * JP + JB + h * 4) = b;
+        }
+    };
     if (tid == 0) *s_cta_off = 0u;
-    __syncthreads();
-    // ---- Gram block: 16 row groups x (4 x 4 register tiles) ----
+    // ---- Gram block: 16 row groups x (4 x 4 register tiles), accumulated over the chunks ----
     {
         const int rg = tid >> 4, ti = (tid >> 2) & 3, tj = tid & 3;
         float acc[4][4];
@@ -82,14 +86,20 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I,
         for (int x = 0; x < 4; ++x)
 #pragma unroll
             for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-        for (int r = rg; r < p; r += 16) {
-            const float4 a = *(const float4*)(P + (size_t)r * JP + 4 * ti);
-            const float4 b = *(const float4*)(P + (size_t)r * JP + 4 * tj);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        for (int c = 0; c < nchunks; ++c) {
+            const int r0 = c * pc, n = min(pc, p - r0);
+            if (c > 0) __syncthreads();   // the previous chunk's readers are done
+            load_chunk(r0, n);
+            __syncthreads();
+            for (int r = rg; r < n; r += 16) {
+                const float4 a = *(const float4*)(P + (size_t)r * JP + 4 * ti);
+                const float4 b = *(const float4*)(P + (size_t)r * JP + 4 * tj);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+                for (int x = 0; x < 4; ++x)
 #pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+                    for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+            }
         }
 #pragma unroll
         for (int x = 0; x < 4; ++x)
@@ -192,19 +202,27 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I,
 #pragma unroll
             for (int x = 0; x < 4; ++x) q[k][x] = (float)Qm[k * 17 + 4 * cgp + x];
         float* dst = (cgp < 2) ? (GI + cgp * 4) : (GJ + (cgp - 2) * 4);
-        for (int r = tid >> 2; r < p; r += J_THREADS / 4) {
-            const float4 v0 = *(const float4*)(P + (size_t)r * JP);
-            const float4 v1 = *(const float4*)(P + (size_t)r * JP + 4);
-            const float4 v2 = *(const float4*)(P + (size_t)r * JP + 8);
-            const float4 v3 = *(const float4*)(P + (size_t)r * JP + 12);
-            const float pv[JP] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w,
-                                  v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-            float o[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < nchunks; ++c) {
+            const int r0 = c * pc, n = min(pc, p - r0);
+            if (nchunks > 1) {            // the single chunk is still in P from the Gram pass
+                __syncthreads();
+                load_chunk(r0, n);
+                __syncthreads();
+            }
+            for (int r = tid >> 2; r < n; r += J_THREADS / 4) {
+                const float4 v0 = *(const float4*)(P + (size_t)r * JP);
+                const float4 v1 = *(const float4*)(P + (size_t)r * JP + 4);
+                const float4 v2 = *(const float4*)(P + (size_t)r * JP + 8);
+                const float4 v3 = *(const float4*)(P + (size_t)r * JP + 12);
+                const float pv[JP] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w,
+                                      v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int k = 0; k < JP; ++k)
+                for (int k = 0; k < JP; ++k)
 #pragma unroll
-                for (int x = 0; x < 4; ++x) o[x] = fmaf(pv[k], q[k][x], o[x]);
-            __stcg((float4*)(dst + (size_t)r * JB), make_float4(o[0], o[1], o[2], o[3]));
+                    for (int x = 0; x < 4; ++x) o[x] = fmaf(pv[k], q[k][x], o[x]);
+                __stcg((float4*)(dst + (size_t)(r0 + r) * JB), make_float4(o[0], o[1], o[2], o[3]));
+            }
         }
     }
     __syncthreads();
@@ -220,14 +238,15 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int I,
 //      and steps without an active pair cost nothing (no barrier).  When more than half of the pairs are active
 //      (photometric affinity) the round-robin tournament is used instead: (panels - 1) steps of panels / 2 pairs.
 __global__ void __launch_bounds__(J_THREADS, 1)
-k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, int inner_max, float* __restrict__ C /* [cp][cp], cp = nb * 8 */,
+k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memory */, int nb, int max_sweeps, float tol, int inner_max,
+         float* __restrict__ C /* [cp][cp], cp = nb * 8 */,
          float* __restrict__ pair_rel /* [nb][nb] */, int* __restrict__ step_cnt /* [max_sweeps][2 * nb] */,
          unsigned* __restrict__ sweep_off, int* __restrict__ sweeps_done)
 {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) float jsm[];
-    float* P = jsm;                          // [p][16]
-    float* red = P + (size_t)p * JP;         // [16][256]
+    float* P = jsm;                          // [pc][16]
+    float* red = P + (size_t)pc * JP;        // [16][256]
     double* Bm = (double*)(red + 16 * 256);  // [16][17]  Gram block, fp64 from here on: the rotations that are
     double* Qm = Bm + JP * 17;               // [16][17]  accumulated into Q must stay orthogonal to ~1e-16, or the
     double* cs = Qm + JP * 17;               // [8][2]    column norms (= eigenvalues) drift by ~1e-6 per update
@@ -355,7 +374,7 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, int in
                     int I, J;
                     tournament(step, pair, nb, I, J);
                     if (__ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
-                        jacobi_pair(G, p, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
+                        jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
                 }
                 grid.sync();
             }
@@ -367,7 +386,7 @@ k_jacobi(float* __restrict__ G, int p, int nb, int max_sweeps, float tol, int in
                     for (int c = blockIdx.x; c < ncand; c += gridDim.x) {
                         const int I = (c / d) * 2 * d + par * d + (c % d), J = I + d;
                         if (J < nb && __ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
-                            jacobi_pair(G, p, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
+                            jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
                     }
                     grid.sync();
                 }
@@ -519,12 +538,9 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
 {
     const int p = (int)L_A->rows;
     const int nb = (int)(round_up(p, JP) / JB);  // even number of panels
-    const size_t smem = sizeof(float) * ((size_t)p * JP + 16 * 256) + sizeof(double) * (2 * JP * 17 + 16) + sizeof(int) * (JP + 2 * JB);
-    if (smem > 227 * 1024) {
-        gl_set_error("eigensolve: p = %d needs %zu bytes of shared memory per CTA (limit 227 KB)", p, smem);
-        return GL_ERR_UNSUPPORTED;
-    }
-    GL_REQUIRE(p < (1 << 24), "eigensolve: p too large");
+    const int pc = p < 3072 ? p : 3072;   // panel rows per shared-memory chunk (larger p: two passes over the pair, see jacobi_pair)
+    const size_t smem = sizeof(float) * ((size_t)pc * JP + 16 * 256) + sizeof(double) * (2 * JP * 17 + 16) + sizeof(int) * (JP + 2 * JB);
+    GL_REQUIRE(p <= 8192, "eigensolve: p = %d is beyond what this build sorts and screens (8192)", p);
     gl_buf *G = nullptr, *lam = nullptr, *order = nullptr, *ctl = nullptr, *ray = nullptr, *part = nullptr;
     gl_buf *Cg = nullptr, *prel = nullptr, *scnt = nullptr;
     const int cols_pad = nb * JB;
@@ -566,7 +582,8 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         float* prp = (float*)prel->ptr;
         int* scp = (int*)scnt->ptr;
         int inner = ctx->jacobi_inner > 0 ? ctx->jacobi_inner : J_INNER_MAX;
-        void* args[] = {&Gp, &p_, &nb_, &ms, &tol, &inner, &Cp, &prp, &scp, &off, &done};
+        int pc_ = pc;
+        void* args[] = {&Gp, &p_, &pc_, &nb_, &ms, &tol, &inner, &Cp, &prp, &scp, &off, &done};
         {
             StageTimer kt(ctx, GL_T_K_JACOBI);
             GL_CUDA_BREAK(rc, cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));

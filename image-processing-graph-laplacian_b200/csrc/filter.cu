@@ -473,7 +473,14 @@ int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int
     const int64_t rows = phi->local_rows;
     const int m_pad = phi->m_pad;
     const FilterGeom g = filter_geom(m_pad);
-    GL_REQUIRE(g.NG <= 2, "filter: m_pad = %d too wide", m_pad);
+    const bool use_proj_pre = ctx->projection_mode == 0 && phi->proj && phi->channels == C && phi->image_epoch == ctx->image_epoch;
+    // the thread-per-column-group kernels (projection pass, generic apply) hold at most two groups per thread (m_pad <= 4096);
+    // wider Phi goes through the projection from the affinity sums and the column-chunked warp apply only
+    const bool needs_generic = !use_proj_pre || ctx->filter_apply_impl == 1 || g.G % 32 != 0;
+    if (g.NG > 2 && needs_generic) {
+        gl_set_error("filter: m_pad = %d is too wide for the stand-alone projection / generic apply kernels (<= 4096)", m_pad);
+        return GL_ERR_UNSUPPORTED;
+    }
     GL_REQUIRE((g.TPR & (g.TPR - 1)) == 0 || g.TPR % 32 == 0, "filter: unsupported column-group count %d", g.G);
     int grid = ctx->sm_count * 4;
     if ((int64_t)grid * g.RL * FL_RU > rows) grid = (int)ceil_div(rows, (int64_t)g.RL * FL_RU);
@@ -495,7 +502,7 @@ int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int
             float* zp = (float*)z->ptr;
             uint8_t* z8p = z8 ? (uint8_t*)z8->ptr : nullptr;
 #define FL_CASE(CC, NGG)                                                                                                      \
-    if (C == CC && g.NG == NGG)                                                                                               \
+    if (C == CC && (g.NG == NGG || (NGG == 1 && g.NG > 2)))                                                                   \
         rc = run_filter<CC, NGG>(ctx, phi, g, f, gain, clip_low, grid, (float*)partial->ptr, (float*)c->ptr, (float*)w->ptr, zp, z8p, use_proj);
             FL_CASE(1, 1) else FL_CASE(1, 2) else FL_CASE(3, 1) else FL_CASE(3, 2)
 #undef FL_CASE

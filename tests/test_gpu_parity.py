@@ -293,6 +293,30 @@ def test_config5_shape_colour_p2000(ctx):
         assert _rel(r2["z"], r["z"].astype(np.float64)) < 5e-5, impl
 
 
+def test_large_sample_count(ctx):
+    """The reference's default is p = 1 % of the pixels (hpc/image_processing.c:187), thousands of samples on its larger
+    inputs: p > 3072 runs the Jacobi pairs in two shared-memory chunks, m_pad > 4096 the wide-Phi filter paths."""
+    from oracle import cpu_pipeline as cp
+    W, H, p_req = 350, 300, 4000
+    img = o.synthetic_image(W, H, 1, seed=17)
+    s = oc.uniform_sampling(W, H, p_req)
+    assert len(s) > 3072
+    prm = gl.default_params(sample_size=p_req)
+    r = ctx.run(img, prm)
+    assert np.array_equal(ctx.get_samples(), s) and r["m"] == len(s) - 1
+    ref = cp.run(img, s)
+    err_mu = float(np.max(np.abs(r["mu"] - ref["mu"]) / ref["mu"]))
+    err_z, err_dz = _rel(r["z"], ref["z"]), _rel(r["z"] - img, ref["z"] - img)
+    print(f"large p: {W}x{H} p={len(s)}: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_mu <= TOL_MU and err_z <= TOL_Z and err_dz <= TOL_DZ
+    ctx.set_option("fuse_filter", 0)           # Nystroem, then the filter on the stored (wide) Phi
+    try:
+        r2 = ctx.run(img, prm)
+    finally:
+        ctx.set_option("fuse_filter", 1)
+    assert _rel(r2["z"], ref["z"]) <= TOL_Z and _rel(r2["z"] - img, ref["z"] - img) <= TOL_DZ
+
+
 def test_projection_and_apply_variants_agree(ctx, golden):
     """c = Phi^T y from the affinity sums (default) vs the stand-alone pass over Phi; warp-per-row vs generic apply."""
     for tag in ("barbara_uniform256", "lion_rgb_photometric500", "test_uniform100"):
