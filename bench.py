@@ -339,6 +339,9 @@ def main():
                warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
                dtype="f16 operands and Phi / f32 accumulate (K_A, D, L_A, eigenvalues, projection f64; eigenvectors f32)", data="synthetic",
                config=dict(workload=DESCR[args.workload], p=p, m=m, gram_schmidt=args.gram_schmidt,
+                           plan="the K_B block layout depends on the image size and the sample positions only; it is planned on the "
+                                "host at the first call (first_call_ms, with the device allocations) and reused while they do not "
+                                "change, like an FFT plan; a new sample draw on the same geometry costs ~1 ms of host time",
                            cache="working set (K_B + Phi = %.1f GB per GPU) far larger than the 126 MB L2; no flush needed"
                                  % (2 * band_px * (m_pad + (p + 63) // 64 * 64) / 1e9),
                            parallelism=f"pixel-row bands x{world}"),
@@ -348,7 +351,7 @@ def main():
                         ms_per_step=t_e2e / args.steps, result="filtered image as u8 (the reference's png bytes), per-rank band",
                         with_fp32_result=dict(value=n / (t_e2e_f32 / args.steps * 1e-3) / 1e6, ms_per_step=t_e2e_f32 / args.steps,
                                               d2h_bytes_per_step=band_px * channels * 4)),
-               gpu_launches=int(launches),
+               gpu_launches=int(launches), first_call_ms=first_call_ms,
                clocks=clk,
                roofline=roof,
                roofline_gemm_dense=roof_dense,

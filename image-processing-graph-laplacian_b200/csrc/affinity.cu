@@ -283,8 +283,11 @@ static void kb_layout_for(const KbGeom& geo, const std::vector<uint32_t>& sample
     if (!count_only) {
         out->tab.assign((size_t)tiles, make_int4(0, 0, 0, 0));
         out->starts.clear();
+        out->starts.reserve((size_t)tiles * 2);
         out->perm = perm;
     }
+    int64_t run_ra = -1, run_rb = -1;
+    std::vector<int64_t> run_lo(S, 0), run_hi(S, 0);
     for (int64_t t = 0; t < tiles; t += tile_stride) {
         const int64_t first_entry = out->total;
         int64_t prev_end = 0;
@@ -309,16 +312,22 @@ static void kb_layout_for(const KbGeom& geo, const std::vector<uint32_t>& sample
             if (ra == rb) { seg[0][0] = qa % W; seg[0][1] = qb % W; }
             else if (rb == ra + 1 && qb % W < qa % W) { seg[0][0] = qa % W; seg[0][1] = W - 1; seg[1][0] = 0; seg[1][1] = qb % W; nseg = 2; }
             else { seg[0][0] = 0; seg[0][1] = W - 1; }
+            if (ra != run_ra || rb != run_rb) {   // tiles of the same image rows share the per-strip runs
+                run_ra = ra;
+                run_rb = rb;
+                for (int s = 0; s < S; ++s) {
+                    const int* rb_ = row_int.data() + strip_begin[s];
+                    const int* re_ = row_int.data() + strip_begin[s + 1];
+                    run_lo[s] = strip_begin[s] + (std::lower_bound(rb_, re_, (int)std::max<int64_t>(ra - R, -1)) - rb_);
+                    run_hi[s] = strip_begin[s] + (std::upper_bound(rb_, re_, (int)std::min<int64_t>(rb + R, 0x7fffffff)) - rb_);
+                }
+            }
             for (int s = 0; s < S; ++s) {
+                if (run_hi[s] <= run_lo[s]) continue;
                 const int64_t c_lo = (int64_t)s * W / S, c_hi = (int64_t)(s + 1) * W / S - 1;   // columns of this strip (approx. bounds)
                 bool need = false;
                 for (int g = 0; g < nseg; ++g) need = need || (seg[g][0] - R <= c_hi + 1 && seg[g][1] + R >= c_lo - 1);
-                if (!need) continue;
-                const int* rb_ = row_int.data() + strip_begin[s];
-                const int* re_ = row_int.data() + strip_begin[s + 1];
-                const int64_t lo = strip_begin[s] + (std::lower_bound(rb_, re_, (int)std::max<int64_t>(ra - R, -1)) - rb_);
-                const int64_t hi = strip_begin[s] + (std::upper_bound(rb_, re_, (int)std::min<int64_t>(rb + R, 0x7fffffff)) - rb_);
-                if (hi > lo) emit(lo, hi);
+                if (need) emit(run_lo[s], run_hi[s]);
             }
             if (cnt == 0) emit(0, 1);   // keep one block so that the GEMM writes zeros
         }
@@ -393,7 +402,11 @@ static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
         return GL_OK;  // same geometry, samples and cutoff as last time: the cached layout stands
     KbLayout lay;
     const KbGeom geo = {W, ctx->q0, ctx->q1, ctx->p_pad};
-    const int best_S = kb_choose_and_build(geo, ctx->h_samples, cut, R, ctx->kb_strips, &lay);
+    // the strip count depends on the geometry and the sample density, not on where exactly the samples fell: it is chosen
+    // once per (geometry, p, reach) and reused when only the sample positions change (a new random draw costs one build)
+    int forced = ctx->kb_strips;
+    if (forced == 0 && ctx->tile_tab && !memcmp(key, ctx->tab_key, sizeof(key))) forced = ctx->tile_strips;
+    const int best_S = kb_choose_and_build(geo, ctx->h_samples, cut, R, forced, &lay);
     GL_REQUIRE(lay.total < 0x7fffffff / 512, "affinity: K_B has too many blocks for 32-bit tile coordinates");
     // upload: table, block starts, permutation (one staging pass through the pinned block each)
     gl_buf** dst[3] = {&ctx->tile_tab, &ctx->tile_starts, &ctx->tile_perm};
