@@ -293,6 +293,28 @@ def test_config5_shape_colour_p2000(ctx):
         assert _rel(r2["z"], r["z"].astype(np.float64)) < 5e-5, impl
 
 
+def test_new_sample_draws_on_the_same_geometry(ctx):
+    """The K_B layout is cached on (geometry, samples): a new random draw on the same image must rebuild it (with the strip
+    count chosen for the geometry) and still match the oracle; going back to the first draw must reproduce it bit for bit."""
+    from oracle import cpu_pipeline as cp
+    W, H, p, h_loc = 1200, 300, 400, 12.0
+    img = o.synthetic_image(W, H, 1, seed=8)
+    lay = gl.kb_layout(W, 0, W * H, oc.random_sampling(W, H, p, 1), h_loc=h_loc)
+    assert lay["strips"] > 1                                  # a wide image with a short reach: column strips are in play
+    first = None
+    for seed in (1, 2, 3, 1):
+        prm = gl.default_params(sampling=gl.RANDOM, sample_size=p, seed=seed, h_loc=h_loc)
+        r = ctx.run(img, prm)
+        s = oc.random_sampling(W, H, p, seed)
+        assert np.array_equal(ctx.get_samples(), s)
+        ref = cp.run(img, s, h_loc=h_loc)
+        assert np.max(np.abs(r["mu"] - ref["mu"]) / ref["mu"]) <= TOL_MU
+        assert _rel(r["z"], ref["z"]) <= TOL_Z and _rel(r["z"] - img, ref["z"] - img) <= TOL_DZ, seed
+        if first is None:
+            first = r["z"].copy()
+    assert np.array_equal(r["z"], first)
+
+
 def test_large_sample_count(ctx):
     """The reference's default is p = 1 % of the pixels (hpc/image_processing.c:187), thousands of samples on its larger
     inputs: p > 3072 runs the Jacobi pairs in two shared-memory chunks, m_pad > 4096 the wide-Phi filter paths."""
