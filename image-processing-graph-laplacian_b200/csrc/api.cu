@@ -468,7 +468,9 @@ int gl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** ei
 {
     GL_REQUIRE(ctx && L_A, "gl_eigensolve: null");
     GL_REQUIRE(L_A->kind == GL_MAT_KA && L_A->rows == L_A->cols, "gl_eigensolve: want a square p x p matrix");
-    if (m < 0 || m >= L_A->rows) m = (int)L_A->rows - 1;  // hpc/image_processing.c:102-106
+    // m in [1, p]; the reference's driver never asks for more than p - 1 (hpc/image_processing.c:102-106, applied by the
+    // callers), its Python prototype keeps all p (python/image_processing.py:287): both are served
+    if (m < 0 || m > L_A->rows) m = (int)L_A->rows - 1;
     GL_REQUIRE(m >= 1, "gl_eigensolve: m must be >= 1");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
     StageTimer t(ctx, GL_T_EIGEN);
@@ -838,7 +840,9 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
         if ((rc = gl_laplacian(ctx, K_A, K_B, &L_A, &L_B)) != GL_OK) break;
         gl_mat_destroy(K_A); K_A = nullptr;            // image_processing.c:210-211
         gl_mat_destroy(K_B); K_B = nullptr;
-        if ((rc = gl_eigensolve(ctx, L_A, prm->num_eigvals, &U, &mu, &mu_inv)) != GL_OK) break;
+        // GetNumberEigenvalues (hpc/image_processing.c:96-108): absent, negative or >= p means p - 1
+        const int m_req = (prm->num_eigvals < 0 || prm->num_eigvals >= (int)p) ? (int)p - 1 : prm->num_eigvals;
+        if ((rc = gl_eigensolve(ctx, L_A, m_req, &U, &mu, &mu_inv)) != GL_OK) break;
         gl_mat_destroy(L_A); L_A = nullptr;
         if ((rc = gl_diag_pow(ctx, mu, prm->power, &f_mu)) != GL_OK) break;  // MatPow(eigvals, .) as intended
         // without an orthonormalisation in between, the filter can ride on the extrapolation GEMM's epilogue: Phi is

@@ -146,7 +146,8 @@ GL_API int gl_get_samples(gl_ctx* ctx, uint32_t* indices_out, unsigned cap, unsi
 /* ---- a-2 .. a-9 stages ------------------------------------------------------------------------ */
 GL_API int gl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A, gl_mat** K_B);
 GL_API int gl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A, gl_mat** L_B);
-/* m smallest eigenpairs of symmetric positive definite L_A, ascending. eigvecs and/or eigvals_inv may be NULL. */
+/* m smallest eigenpairs of symmetric positive definite L_A, ascending, 1 <= m <= p (m < 0 or m > p: p - 1).
+ * eigvecs and/or eigvals_inv may be NULL. */
 GL_API int gl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv);
 /* Phi (n x m): sample rows = phi_A, other rows = L_B^T . phi_A . diag(eigvals_inv), already in raster order. */
 GL_API int gl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi);

@@ -10,10 +10,13 @@ Parity status: the reference ships no tests or golden vectors for this path
 absent).  The oracle is pinned instead against outputs of the reference's own
 importable Python modules run in the build container -- python/sampling/* and
 python/affinity_methods/{bilateral,photometric,spatial}.py -- via the fixtures
-written by tests/golden/make_golden.py.  Stages past the eigensolve have no
-runnable reference (hpc/image_processing.c:237-276 is commented out at HEAD):
-for those the parity is "unpinned by the reference", and the oracle restates
-the commented block bug-for-bug as SURVEY.md section 8c defines it.
+written by tests/golden/make_golden.py.  Stages past the eigensolve are commented
+out in the C program at HEAD (hpc/image_processing.c:237-276) but live in the
+Python prototype: tests/golden/make_golden_pyref.py runs the reference's own
+python/image_processing.py:image_processing(y) and run_pipeline(), given the
+prototype's constants, reproduces its output to 1e-10 (tests/test_oracle.py).
+Only the C block's constants (gain +3, f(lambda) = lambda, m = p - 1, clip above
+255) are "unpinned by the reference": they follow SURVEY.md section 8c.
 
 Each function cites the reference file:line it follows (paths relative to the
 reference root).
@@ -260,7 +263,8 @@ def gram_schmidt(X):
 
 
 def run_pipeline(img, sample_indices, m=None, kind=BILATERAL, h_loc=40.0, h_val=30.0,
-                 gain=3.0, power=1.0, orthonormalise=False, chunk=65536, return_phi=False):
+                 gain=3.0, power=1.0, orthonormalise=False, chunk=65536, return_phi=False,
+                 f_of_mu=None, clip=True, all_pairs=False):
     """The restored block hpc/image_processing.c:183-275 in fp64:
 
       s -> K_A, K_B (affinity.c:129-262) -> D, alpha, L_A (laplacian.c:14-42) ->
@@ -270,15 +274,24 @@ def run_pipeline(img, sample_indices, m=None, kind=BILATERAL, h_loc=40.0, h_val=
       no-op, utils.c:721, hence power=1), z[z>255] = 255 (display.c:76).
 
     Returns a dict.  z is float64 [H, W] or [H, W, C]; negatives are NOT clipped
-    (SURVEY 8c-iii)."""
+    (SURVEY 8c-iii).
+
+    The Python prototype runs the same stages with other constants
+    (python/image_processing.py:274-305): all p eigenpairs (`all_pairs`), the filter
+    function f(mu) = mu + 5 (`f_of_mu`), gain -1 and no clipping (`clip=False`); with
+    those arguments this function must reproduce the reference's own output, which is
+    what tests/test_oracle.py checks against tests/golden/pyref_*.npz."""
     imgc = _as_hwc(img)
     H, W, C = imgc.shape
     n = H * W
     s = np.asarray(sample_indices, dtype=np.int64)
     p = len(s)
-    if m is None or m < 0 or m >= p:
+    if all_pairs:
+        m = p                                       # python/image_processing.py:287-292 keeps every pair
+    elif m is None or m < 0 or m >= p:
         m = p - 1                                   # image_processing.c:102-106
     rest = non_sample_indices(n, s)
+    fmu = (lambda mu_: mu_[:, None] ** power) if f_of_mu is None else (lambda mu_: np.asarray(f_of_mu(mu_))[:, None])
 
     K_A = affinity_rows(imgc, s, s, kind, h_loc, h_val)
     rowsum_B = np.zeros(p)
@@ -300,7 +313,7 @@ def run_pipeline(img, sample_indices, m=None, kind=BILATERAL, h_loc=40.0, h_val=
         if orthonormalise:
             phi, _ = gram_schmidt(phi)
         c = phi.T @ y
-        z = y + gain * (phi @ ((mu[:, None] ** power) * c))
+        z = y + gain * (phi @ (fmu(mu) * c))
     else:
         # same arithmetic, streamed so Phi (n x m fp64) is never held
         c = U.T @ y[s]
@@ -308,7 +321,7 @@ def run_pipeline(img, sample_indices, m=None, kind=BILATERAL, h_loc=40.0, h_val=
             idx = rest[a:a + chunk]
             KB = affinity_rows(imgc, s, idx, kind, h_loc, h_val)
             c += Wm.T @ (KB @ y[idx])
-        w = (mu[:, None] ** power) * c             # m x C
+        w = fmu(mu) * c                            # m x C
         z = y.copy()
         z[s] += gain * (U @ w)
         Ww = Wm @ w                                # p x C
@@ -316,7 +329,8 @@ def run_pipeline(img, sample_indices, m=None, kind=BILATERAL, h_loc=40.0, h_val=
             idx = rest[a:a + chunk]
             KB = affinity_rows(imgc, s, idx, kind, h_loc, h_val)
             z[idx] += gain * (KB.T @ Ww)
-    z = np.minimum(z, 255.0)                       # AboveXSetY(z, 255, 255), display.c:76
+    if clip:
+        z = np.minimum(z, 255.0)                   # AboveXSetY(z, 255, 255), display.c:76
     z = z.reshape(H, W, C)
     out = dict(sample_indices=s.astype(np.uint32), K_A=K_A, D=D, alpha=alpha, L_A=L_A, mu=mu,
                U=U, z=z[:, :, 0] if np.asarray(img).ndim == 2 else z, m=m, p=p)

@@ -152,6 +152,35 @@ def test_pipeline_matches_golden(ctx, golden, tag):
     assert r["z"].max() <= 255.0
 
 
+@pytest.mark.parametrize("tag_py", ["pyref_test100", "pyref_lion_crop"])
+def test_against_the_reference_python_pipeline(ctx, golden, tag_py):
+    """The CUDA path against the output of the reference's OWN image_processing(y) (python/image_processing.py:244-357;
+    fixtures from tests/golden/make_golden_pyref.py): 1 % uniform samples, bilateral affinity, ALL p eigenpairs,
+    z = y - Phi (mu + 5) Phi^T y.  f(mu) = mu + 5 is not a power, so the image is assembled from two filter applications
+    on the same Phi: z = [y - Phi mu Phi^T y] + [y - 5 Phi Phi^T y] - y."""
+    g = golden(tag_py)
+    img, s = g["image"], g["sample_indices"]
+    H, W = img.shape
+    ctx.set_image(img)
+    got = ctx.sampling(gl.SPATIALLY_UNIFORM, int(W * H * 0.01))
+    assert np.array_equal(got, s)                                   # the reference module's own sample list, bit for bit
+    K_A, K_B = ctx.affinity()
+    L_A, L_B = ctx.laplacian(K_A, K_B)
+    U, mu, mu_inv = ctx.eigensolve(L_A, len(s))                     # every pair, like the prototype
+    assert mu.info.rows == len(s)
+    phi = ctx.nystroem(L_B, U, mu_inv)
+    z1 = ctx.filter(phi, ctx.diag_pow(mu, 1.0), gain=-1.0).astype(np.float64)
+    z0 = ctx.filter(phi, ctx.diag_pow(mu, 0.0), gain=-5.0).astype(np.float64)
+    z = z1 + z0 - img
+    ref = g["z"]
+    free = (z1 < 254.9) & (z0 < 254.9) & (ref < 254.9)              # the C filter clips above 255 (display.c:76), Python does not
+    assert free.mean() > 0.5                                       # test.png has a white (255) background: those pixels clip
+    err_z = float(np.linalg.norm((z - ref)[free]) / np.linalg.norm(ref[free]))
+    err_dz = float(np.linalg.norm(((z - img) - (ref - img))[free]) / np.linalg.norm((ref - img)[free]))
+    print(f"{tag_py}: against the reference python pipeline err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_z <= TOL_Z and err_dz <= TOL_DZ
+
+
 @pytest.mark.parametrize("tag", ["test_uniform100", "cat_small_random50"])
 def test_tcgen05_gemm_matches_cuda_core_checker(ctx, golden, tag):
     g = golden(tag)

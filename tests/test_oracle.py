@@ -139,3 +139,22 @@ def test_full_path_oracle_identities():
     assert abs(r["alpha"] - alpha) < 1e-15
     flat = np.full((10, 12), 77, dtype=np.uint8)
     assert np.allclose(o.run_full(flat)["z"], 77.0)
+
+
+@pytest.mark.parametrize("tag", ["pyref_test100", "pyref_lion_crop"])
+def test_oracle_reproduces_the_reference_python_pipeline(golden, tag):
+    """tests/golden/pyref_*.npz hold the output of the reference's OWN image_processing(y) (python/image_processing.py:
+    244-357, run by tests/golden/make_golden_pyref.py).  With the prototype's constants -- all p eigenpairs, f(mu) = mu + 5,
+    gain -1, no clipping -- the oracle must give the same image: this pins its Laplacian normalisation, eigenpair ordering,
+    Nystroem extrapolation, permutation back to raster order and filter algebra to reference code."""
+    from oracle import oracle_np as o
+    g = golden(tag)
+    img, s = g["image"], g["sample_indices"]
+    H, W = img.shape
+    assert np.array_equal(o.uniform_sampling(W, H, int(W * H * 0.01)), s)
+    for streamed in (False, True):                      # both code paths of the oracle (Phi held / streamed)
+        r = o.run_pipeline(img, s, all_pairs=True, f_of_mu=lambda mu: mu + 5.0, gain=-1.0, clip=False, return_phi=not streamed)
+        assert r["m"] == len(s)
+        err = np.linalg.norm(r["z"] - g["z"]) / np.linalg.norm(g["z"])
+        err_d = np.linalg.norm((r["z"] - img) - (g["z"] - img)) / np.linalg.norm(g["z"] - img)
+        assert err < 1e-10 and err_d < 1e-9, (tag, streamed, err, err_d)
