@@ -152,19 +152,23 @@ def test_pipeline_matches_golden(ctx, golden, tag):
     assert r["z"].max() <= 255.0
 
 
-@pytest.mark.parametrize("tag_py", ["pyref_test100", "pyref_lion_crop"])
+@pytest.mark.parametrize("tag_py", ["pyref_test100", "pyref_lion_crop", "pyref_lion_crop_photometric", "pyref_test100_spatial",
+                                    "pyref_lion_crop_random7"])
 def test_against_the_reference_python_pipeline(ctx, golden, tag_py):
     """The CUDA path against the output of the reference's OWN image_processing(y) (python/image_processing.py:244-357;
     fixtures from tests/golden/make_golden_pyref.py): 1 % uniform samples, bilateral affinity, ALL p eigenpairs,
     z = y - Phi (mu + 5) Phi^T y.  f(mu) = mu + 5 is not a power, so the image is assembled from two filter applications
     on the same Phi: z = [y - Phi mu Phi^T y] + [y - 5 Phi Phi^T y] - y."""
     g = golden(tag_py)
-    img, s = g["image"], g["sample_indices"]
+    img, s, kind, seed = g["image"], g["sample_indices"], str(g["kind"]), int(g["seed"])
+    # bandwidths hard-coded in the reference's plugins: bilateral 30 / 40, photometric 10, spatial 10
+    h_loc, h_val = {"bilateral": (40.0, 30.0), "photometric": (40.0, 10.0), "spatial": (10.0, 30.0)}[kind]
     H, W = img.shape
     ctx.set_image(img)
-    got = ctx.sampling(gl.SPATIALLY_UNIFORM, int(W * H * 0.01))
+    got = (ctx.sampling(gl.SPATIALLY_UNIFORM, int(W * H * 0.01)) if seed < 0
+           else ctx.sampling(gl.RANDOM, int(W * H * 0.01), seed=seed))
     assert np.array_equal(got, s)                                   # the reference module's own sample list, bit for bit
-    K_A, K_B = ctx.affinity()
+    K_A, K_B = ctx.affinity(kind, h_loc, h_val)
     L_A, L_B = ctx.laplacian(K_A, K_B)
     U, mu, mu_inv = ctx.eigensolve(L_A, len(s))                     # every pair, like the prototype
     assert mu.info.rows == len(s)
