@@ -413,6 +413,10 @@ class Context:
             return z, (z8[:, :, 0] if ch == 1 else z8)
         return z
 
+    def filter_resident(self, phi: Mat, f_eigvals: Mat, gain=3.0, clip_low=False):
+        """gl_filter with the result left on the device (no host copy): for timing the stage calls."""
+        _check(lib().gl_filter(self.h, phi.h, f_eigvals.h, gain, int(clip_low), None, None))
+
     # ---- whole path -------------------------------------------------------------------------
     def run(self, img, params: Params, z_out=None, z8_out=None, want_eigvals=True):
         """gl_run: H2D of `img`, all stages, D2H of z into z_out (float32 [H,W(,C)])."""

@@ -117,6 +117,8 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         else GL_REQUIRE(false, "option projection: want sums|recompute, got %s", value);
     } else if (!strcmp(key, "fuse_filter")) {
         ctx->fuse_filter = atoi(value) != 0;
+    } else if (!strcmp(key, "lazy_phi")) {
+        ctx->lazy_phi = atoi(value) != 0;
     } else if (!strcmp(key, "keep_phi")) {
         ctx->keep_phi = atoi(value) != 0;
     } else if (!strcmp(key, "filter_apply")) {
@@ -485,6 +487,10 @@ int gl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl
     GL_REQUIRE(phi_A->rows == L_B->p && eigvals_inv->rows == phi_A->cols, "gl_nystroem: shape mismatch");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
     StageTimer t(ctx, GL_T_NYSTROEM);
+    // Deferred by default: the handle is complete as far as the caller can tell, the matrix itself is computed when it is
+    // first needed.  The reference's driver calls Nystroem and then ComputeResultFromLaplacian (hpc/image_processing.c:
+    // 249-268): deferring lets gl_filter run both as ONE pass over Phi although they arrive as two calls.
+    if (ctx->lazy_phi && ctx->gemm_impl == 0) return gl_phi_defer(ctx, L_B, phi_A, eigvals_inv, phi);
     return gl_impl_nystroem(ctx, L_B, phi_A, eigvals_inv, phi);
 }
 
@@ -513,6 +519,10 @@ int gl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
 {
     GL_REQUIRE(ctx && phi && phi->kind == GL_MAT_PHI, "gl_orthonormalise: want a Phi handle");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (phi->def_LB) {
+        StageTimer tn(ctx, GL_T_NYSTROEM);
+        GL_CHECK(gl_phi_materialise(ctx, phi));
+    }
     StageTimer t(ctx, GL_T_GRAM_SCHMIDT);
     return gl_impl_orthonormalise(ctx, phi, norms_out);
 }
@@ -524,6 +534,24 @@ int gl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip
     GL_REQUIRE(f_eigvals->rows == phi->m, "gl_filter: %lld eigenvalues for %d columns", (long long)f_eigvals->rows, phi->m);
     GL_REQUIRE(phi->q0 == ctx->q0 && phi->local_rows == ctx->q1 - ctx->q0, "gl_filter: Phi does not belong to the current image");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (phi->def_LB) {
+        // Phi was deferred by gl_nystroem: compute it now -- with the filter riding on the GEMM's epilogue when that is possible
+        const gl_mat* LB = phi->def_LB;
+        const bool fuse = ctx->fuse_filter && ctx->projection_mode == 0 && ctx->gemm_impl == 0 && LB->aux &&
+                          LB->channels == ctx->channels && LB->image_epoch == ctx->image_epoch;
+        gl_fused_filter ff;
+        ff.f_eigvals = f_eigvals;
+        ff.gain = gain;
+        ff.clip_low = clip_low;
+        ff.z_f32 = z_f32;
+        ff.z_u8 = z_u8;
+        {
+            StageTimer t(ctx, GL_T_NYSTROEM);
+            if (fuse) ctx->ev_valid[GL_T_FILTER] = false;
+            GL_CHECK(gl_phi_materialise(ctx, phi, fuse ? &ff : nullptr));
+        }
+        if (fuse) return GL_OK;
+    }
     return gl_impl_filter(ctx, phi, f_eigvals, gain, clip_low, z_f32, z_u8);
 }
 
@@ -611,6 +639,9 @@ int gl_mat_destroy(gl_mat* m)
     if (m->perm) gl_buf_release(m->perm);
     if (m->dscale) gl_buf_release(m->dscale);
     if (m->proj) gl_buf_release(m->proj);
+    if (m->def_LB) gl_mat_destroy(m->def_LB);
+    if (m->def_U) gl_mat_destroy(m->def_U);
+    if (m->def_muinv) gl_mat_destroy(m->def_muinv);
     delete m;
     return GL_OK;
 }
@@ -678,6 +709,7 @@ int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap)
 {
     GL_REQUIRE(ctx && m && out, "gl_mat_download: null");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (m->kind == GL_MAT_PHI && m->def_LB) GL_CHECK(gl_phi_materialise(ctx, const_cast<gl_mat*>(m)));
     int64_t rows = m->rows, cols = m->cols;
     if (m->kind == GL_MAT_KB) { rows = m->local_rows; cols = m->p; }
     if (m->kind == GL_MAT_PHI) { rows = m->local_rows; cols = m->m; }

@@ -112,6 +112,8 @@ struct gl_mat {
     int aff_kind = 0;            // KB: the affinity that produced it (to rebuild K_A y_S in fp64)
     double aff_h_loc = 0, aff_h_val = 0;
     float phi_scale = 1.0f;      // PHI: stored value * phi_scale = logical (always 1; scale folded in the epilogue)
+    // PHI not computed yet (gl_nystroem with option lazy_phi): the retained inputs it will be computed from
+    gl_mat *def_LB = nullptr, *def_U = nullptr, *def_muinv = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -138,6 +140,7 @@ struct gl_ctx {
     int filter_apply_impl = 0;  // 0 = warp-per-row kernel when the shape allows, 1 = always the generic kernel
     int projection_mode = 0;  // 0 = c from the affinity sums (default), 1 = always recompute c with a pass over Phi
     int fuse_filter = 1;      // gl_run: apply the filter inside the extrapolation GEMM's epilogue when possible
+    int lazy_phi = 1;         // gl_nystroem returns a deferred Phi; gl_filter then runs extrapolation + filter as one pass
     int keep_phi = 1;         // gl_run with the fused filter: 1 = still write Phi to HBM (the reference's data flow), 0 = never store it
 
     // samples
@@ -227,6 +230,8 @@ struct gl_fused_filter {
     uint8_t* z_u8 = nullptr;
 };
 int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi, const gl_fused_filter* ff = nullptr);
+int gl_phi_defer(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi);
+int gl_phi_materialise(gl_ctx* ctx, gl_mat* phi, const gl_fused_filter* ff = nullptr);
 int gl_filter_weights_from_proj(gl_ctx* ctx, const double* proj, const double* f, double gain, int m, int m_pad, int C, float* w);
 int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int parts, const float* w, const float* U, int ldU,
                            int clip_low, float* z_f32, uint8_t* z_u8);

@@ -632,7 +632,24 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     return GL_OK;
 }
 
-int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi_out, const gl_fused_filter* ff)
+// shape and bookkeeping of the Phi that L_B, phi_A produce (no storage yet)
+void gl_phi_describe(gl_ctx* ctx, gl_mat* phi, const gl_mat* L_B, const gl_mat* phi_A)
+{
+    const int m = (int)phi_A->cols;
+    phi->rows = ctx->n;
+    phi->cols = m;
+    phi->local_rows = L_B->local_rows;
+    phi->ld = gl_m_pad(m);
+    phi->elem_bytes = 2;
+    phi->p = L_B->p;
+    phi->p_pad = L_B->p_pad;
+    phi->m = m;
+    phi->m_pad = gl_m_pad(m);
+    phi->q0 = L_B->q0;
+}
+
+// Computes Phi into the handle `phi` (described by gl_phi_describe); keep_phi = false: only the fused filter output `ff`.
+int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat* phi, bool keep_phi, const gl_fused_filter* ff)
 {
     const int p = L_B->p, p_pad = L_B->p_pad;
     const int m = (int)phi_A->cols;
@@ -640,26 +657,14 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
     const int64_t rows = L_B->local_rows;
     GL_REQUIRE(L_B->dscale, "nystroem: expected L_B (from gl_laplacian), got a bare K_B");
     GL_REQUIRE(rows > 0, "nystroem: empty band");
-    GL_REQUIRE(phi_out || ff, "nystroem: nothing to return");
+    GL_REQUIRE(keep_phi || ff, "nystroem: nothing to return");
+    GL_REQUIRE(L_B->tiles && L_B->starts && L_B->perm, "nystroem: K_B handle without its block layout");
 
-    gl_mat* phi = gl_mat_new(ctx, GL_MAT_PHI);
     gl_buf *Wt = nullptr, *colmax = nullptr, *scales = nullptr;
     int rc = GL_OK;
     do {
-        phi->rows = ctx->n;
-        phi->cols = m;
-        phi->local_rows = rows;
-        phi->ld = m_pad;
-        phi->elem_bytes = 2;
-        phi->p = p;
-        phi->p_pad = p_pad;
-        phi->m = m;
-        phi->m_pad = m_pad;
-        phi->q0 = L_B->q0;
-        const bool keep_phi = phi_out != nullptr;   // gl_nystroem_filter may be asked for z only: Phi then never leaves the chip
         if (keep_phi && (rc = gl_alloc(ctx, sizeof(__half) * (size_t)rows * m_pad, &phi->buf)) != GL_OK) break;
         const int k_dim = p_pad + 64;   // K_B's internal sample slots
-        GL_REQUIRE(L_B->tiles && L_B->starts && L_B->perm, "nystroem: K_B handle without its block layout");
         if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)m_pad * k_dim, &Wt)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad, &colmax)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * 4, &scales)) != GL_OK) break;
@@ -680,6 +685,7 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
             const int C = ctx->channels;
             gl_buf* kay = nullptr;
             if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)C * p_pad, &kay)) != GL_OK) break;
+            if (phi->proj) { gl_buf_release(phi->proj); phi->proj = nullptr; }
             if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m_pad * C, &phi->proj)) != GL_OK) { gl_buf_release(kay); break; }
             k_ka_times_y<<<p, 128, 0, ctx->stream>>>(nullptr, (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p,
                                                      p_pad, ctx->width, C, L_B->aff_kind, 1.0 / (L_B->aff_h_loc * L_B->aff_h_loc),
@@ -729,10 +735,49 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
     if (Wt) gl_buf_release(Wt);
     if (colmax) gl_buf_release(colmax);
     if (scales) gl_buf_release(scales);
+    return rc;
+}
+
+int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi_out, const gl_fused_filter* ff)
+{
+    gl_mat* phi = gl_mat_new(ctx, GL_MAT_PHI);
+    gl_phi_describe(ctx, phi, L_B, phi_A);
+    const int rc = gl_impl_nystroem_into(ctx, L_B, phi_A, eigvals_inv, phi, phi_out != nullptr, ff);
     if (rc != GL_OK || !phi_out) {
         gl_mat_destroy(phi);
         return rc;
     }
     *phi_out = phi;
+    return GL_OK;
+}
+
+// Nystroem() deferred: the handle only remembers its inputs (retained); gl_phi_materialise computes it when somebody needs
+// the matrix -- and when that somebody is the filter, the two stages run as one pass (gl_filter, api.cu)
+int gl_phi_defer(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi_out)
+{
+    GL_REQUIRE(L_B->dscale, "nystroem: expected L_B (from gl_laplacian), got a bare K_B");
+    GL_REQUIRE(L_B->local_rows > 0, "nystroem: empty band");
+    gl_mat* phi = gl_mat_new(ctx, GL_MAT_PHI);
+    gl_phi_describe(ctx, phi, L_B, phi_A);
+    phi->def_LB = L_B;
+    phi->def_U = phi_A;
+    phi->def_muinv = eigvals_inv;
+    L_B->refs++;
+    phi_A->refs++;
+    eigvals_inv->refs++;
+    *phi_out = phi;
+    return GL_OK;
+}
+
+int gl_phi_materialise(gl_ctx* ctx, gl_mat* phi, const gl_fused_filter* ff)
+{
+    if (!phi->def_LB) return GL_OK;
+    gl_mat *LB = phi->def_LB, *U = phi->def_U, *mi = phi->def_muinv;
+    const int rc = gl_impl_nystroem_into(ctx, LB, U, mi, phi, true, ff);
+    if (rc != GL_OK) return rc;
+    phi->def_LB = phi->def_U = phi->def_muinv = nullptr;
+    gl_mat_destroy(LB);
+    gl_mat_destroy(U);
+    gl_mat_destroy(mi);
     return GL_OK;
 }

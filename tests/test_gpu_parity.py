@@ -418,9 +418,19 @@ def test_fused_filter_matches_staged(ctx, golden, tag):
     phi_f, z_f = ctx.nystroem_filter(L_B, U, mu_inv, mu)
     none, z_n = ctx.nystroem_filter(L_B, U, mu_inv, mu, keep_phi=False)     # Phi never written: same z, bit for bit
     assert none is None and np.array_equal(z_n, z_f)
-    phi_s = ctx.nystroem(L_B, U, mu_inv)
-    assert np.array_equal(phi_f.download(), phi_s.download())
-    z_s = ctx.filter(phi_s, mu)
+    # the two reference calls, Nystroem then ComputeResultFromLaplacian: Phi is deferred and the filter call runs both as one pass
+    phi_l = ctx.nystroem(L_B, U, mu_inv)
+    z_l = ctx.filter(phi_l, mu)
+    assert np.array_equal(z_l, z_f)
+    assert np.array_equal(phi_l.download(), phi_f.download())
+    # and really apart (the matrix computed by the Nystroem call, then read back by the filter)
+    ctx.set_option("lazy_phi", 0)
+    try:
+        phi_s = ctx.nystroem(L_B, U, mu_inv)
+        assert np.array_equal(phi_f.download(), phi_s.download())
+        z_s = ctx.filter(phi_s, mu)
+    finally:
+        ctx.set_option("lazy_phi", 1)
     assert _rel(z_f, z_s.astype(np.float64)) < 2e-5
     assert _rel(z_f, z) <= TOL_Z
 
