@@ -326,6 +326,24 @@ def test_config5_shape_colour_p2000(ctx):
         assert _rel(r2["z"], r["z"].astype(np.float64)) < 5e-5, impl
 
 
+@pytest.mark.parametrize("W,H,p,method", [
+    (16, 16, 4, "uniform"),        # smaller than one 512-pixel tile, one eigenpair kept of ... 4 samples
+    (33, 17, 9, "random"),
+    (700, 2, 12, "random"),        # two image rows
+    (2, 300, 7, "random"),         # two image columns
+    (64, 64, 2, "random"),         # the minimum: p = 2, m = 1
+])
+def test_tiny_and_degenerate_shapes(ctx, W, H, p, method):
+    img = o.synthetic_image(W, H, 1, seed=W * 7 + H)
+    prm = gl.default_params(sampling=gl.RANDOM if method == "random" else gl.SPATIALLY_UNIFORM, sample_size=p, seed=5)
+    r = ctx.run(img, prm)
+    s = oc.random_sampling(W, H, p, 5) if method == "random" else oc.uniform_sampling(W, H, p)
+    assert np.array_equal(ctx.get_samples(), s) and r["p"] == len(s) and r["m"] == len(s) - 1
+    ref = o.run_pipeline(img, s)
+    assert np.max(np.abs(r["mu"] - ref["mu"]) / ref["mu"]) <= TOL_MU
+    assert _rel(r["z"], ref["z"]) <= TOL_Z and _rel(r["z"] - img, ref["z"] - img) <= TOL_DZ
+
+
 def test_new_sample_draws_on_the_same_geometry(ctx):
     """The K_B layout is cached on (geometry, samples): a new random draw on the same image must rebuild it (with the strip
     count chosen for the geometry) and still match the oracle; going back to the first draw must reproduce it bit for bit."""
