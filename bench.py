@@ -204,6 +204,7 @@ def main():
     K_A_, K_B_ = ctx.affinity(affinity)
     kb_info = K_B_.info
     stored_blocks = int(kb_info.stored_blocks)
+    kb_slots = int(kb_info.ld)                 # sample slots per stored block (64, or 32 with option kb_block)
     K_A_.destroy(); K_B_.destroy()
     barrier()
     clocks = ClockSampler(local_rank)
@@ -326,9 +327,9 @@ def main():
     f_aff = 2.0 * (2 + channels) * p * band_px
     m_pad = 64 if m <= 64 else (128 if m <= 128 else (m + 255) // 256 * 256)
     p_pad = (p + 63) // 64 * 64
-    dense_blocks = -(-band_px // 512) * (p_pad // 64)
-    f_ext_exec = 2.0 * stored_blocks * 512 * 64 * m_pad          # MMA work actually issued (padding included)
-    kb_bytes = stored_blocks * 512 * 64 * 2.0
+    dense_blocks = -(-band_px // 512) * (p_pad // kb_slots)
+    f_ext_exec = 2.0 * stored_blocks * 512 * kb_slots * m_pad          # MMA work actually issued (padding included)
+    kb_bytes = stored_blocks * 512 * kb_slots * 2.0
     gemm_bytes = kb_bytes + band_px * m_pad * 2.0                # K_B blocks read once + Phi written once
     gemm_tf = f_ext / (med["k_gemm"] * 1e-3) / 1e12 if med["k_gemm"] > 0 else 0.0
     gemm_tf_exec = f_ext_exec / (med["k_gemm"] * 1e-3) / 1e12 if med["k_gemm"] > 0 else 0.0

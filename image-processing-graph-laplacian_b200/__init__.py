@@ -117,7 +117,7 @@ def lib():
         L.gl_mat_download.argtypes = [vp, vp, vp, C.c_size_t]
         L.gl_mat_rowsums.argtypes = [vp, vp, vp, C.c_size_t]
         L.gl_mat_upload.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(vp)]
-        L.gl_kb_layout_host.argtypes = [C.c_int, C.c_int64, C.c_int64, vp, C.c_uint, C.c_double, C.c_int, C.c_int, ip,
+        L.gl_kb_layout_host.argtypes = [C.c_int, C.c_int64, C.c_int64, vp, C.c_uint, C.c_double, C.c_int, C.c_int, C.c_int, ip,
                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, vp, vp, vp]
         L.gl_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.gl_host_free.argtypes = [vp]
@@ -147,19 +147,19 @@ def default_params(**kw) -> Params:
     return p
 
 
-def kb_layout(width, q0, q1, samples, h_loc=40.0, cutoff=True, strips=0):
+def kb_layout(width, q0, q1, samples, h_loc=40.0, cutoff=True, strips=0, block=64):
     """Host-only: the block layout gl_affinity gives K_B (gl_kb_layout_host).  Returns a dict with strips, tile_first,
     tile_count, starts, perm."""
     s = np.ascontiguousarray(samples, dtype=np.uint32)
     S, nt, nb = C.c_int(), C.c_int64(), C.c_int64()
-    _check(lib().gl_kb_layout_host(width, q0, q1, s.ctypes.data, len(s), h_loc, int(cutoff), strips, C.byref(S), C.byref(nt),
+    _check(lib().gl_kb_layout_host(width, q0, q1, s.ctypes.data, len(s), h_loc, int(cutoff), strips, block, C.byref(S), C.byref(nt),
                                    C.byref(nb), None, None, None, None))
     first, count = np.empty(nt.value, np.int32), np.empty(nt.value, np.int32)
     starts = np.empty(nb.value, np.int32)
     perm = np.empty((len(s) + 63) // 64 * 64 + 64, np.uint32)
-    _check(lib().gl_kb_layout_host(width, q0, q1, s.ctypes.data, len(s), h_loc, int(cutoff), strips, C.byref(S), C.byref(nt),
+    _check(lib().gl_kb_layout_host(width, q0, q1, s.ctypes.data, len(s), h_loc, int(cutoff), strips, block, C.byref(S), C.byref(nt),
                                    C.byref(nb), first.ctypes.data, count.ctypes.data, starts.ctypes.data, perm.ctypes.data))
-    return dict(strips=S.value, tile_first=first, tile_count=count, starts=starts, perm=perm, n_blocks=nb.value)
+    return dict(strips=S.value, tile_first=first, tile_count=count, starts=starts, perm=perm, n_blocks=nb.value, block=block)
 
 
 def device_count() -> int:

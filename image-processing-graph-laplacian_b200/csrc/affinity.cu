@@ -77,9 +77,9 @@ __global__ void k_affinity_A(const uint8_t* __restrict__ img, const uint32_t* __
     KA[(size_t)i * p + j] = k;
 }
 
-// K_B tile kernel.  Thread (tx = tid % 8, ty = tid / 8): 8 consecutive samples of the current 64-sample
-// chunk x pixels ty, ty+32, ... of the tile.  A warp stores 4 pixel rows x 128 contiguous bytes.
-template <int KIND, int C>
+// K_B tile kernel.  KBS = sample slots per block (64 or 32).  Thread (tx = tid % (KBS/8), ty = tid / (KBS/8)): 8 consecutive
+// slots of the current block x pixels ty, ty + PXL, ... of the tile.  A warp stores 32/(KBS/8) pixel rows of KBS*2 contiguous bytes.
+template <int KIND, int C, int KBS>
 // three CTAs per SM for grey images (80 registers), two for colour (the third would spill)
 #define AFF_CTAS_PER_SM(C) ((C) == 1 ? 3 : 2)
 __global__ void __launch_bounds__(AFF_THREADS, AFF_CTAS_PER_SM(C))
@@ -92,9 +92,12 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
     extern __shared__ float aff_smem[];
     constexpr int NS = 1 + C;                  // sums per sample: D and T[ch]
     float* cta_sum = aff_smem;                 // [NS][p_pad]
-    float* ws = cta_sum + NS * p_pad;          // [2][NS][8 warps][64]
-    float* px = ws + 2 * NS * 8 * 64;          // [(2 + C)][AFF_TP] pixel features
-    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3, lane = tid & 31, warp = tid >> 5;
+    constexpr int TXN = KBS / 8;               // threads across the slots of a block
+    constexpr int PXL = AFF_THREADS / TXN;     // pixel lanes
+    constexpr int PPT = AFF_TP / PXL;          // pixels per thread per block
+    float* ws = cta_sum + NS * p_pad;          // [2][NS][8 warps][KBS]
+    float* px = ws + 2 * NS * 8 * KBS;         // [(2 + C)][AFF_TP] pixel features
+    const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < NS * p_pad; i += AFF_THREADS) cta_sum[i] = 0.f;
 
     const int64_t n_band = q1 - q0;
@@ -117,7 +120,7 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
         for (int ci = 0; ci < tl.y; ++ci) {
             const int sb = starts[tl.x + ci];          // multiple of 8: the float4 loads below stay aligned
             const int s0 = sb + (tx << 3);
-            __half* kb_blk = KB + ((size_t)(tl.z + ci) * AFF_TP) * 64 + (tx << 3);
+            __half* kb_blk = KB + ((size_t)(tl.z + ci) * AFF_TP) * KBS + (tx << 3);
             float sr[8], sc[8], sv[C][8];
             if (KIND != GL_PHOTOMETRIC) {
                 *(float4*)&sr[0] = *(const float4*)&sf[s0];
@@ -138,8 +141,8 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
                 for (int ch = 0; ch < C; ++ch) tacc[ch][k] = 0.f;
             }
 #pragma unroll 2
-            for (int i = 0; i < AFF_PPT; ++i) {
-                const int pi = ty + (i << 5);
+            for (int i = 0; i < PPT; ++i) {
+                const int pi = ty + i * PXL;
                 const int64_t q = base + pi;
                 const float pr = px[pi], pc = px[AFF_TP + pi];
                 float pv[C];
@@ -177,35 +180,34 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
                     __half2 h2 = __floats2half2_rn(kv[4], kv[5]), h3 = __floats2half2_rn(kv[6], kv[7]);
                     uint4 pk;
                     pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
-                    *(uint4*)&kb_blk[(size_t)pi * 64] = pk;
+                    *(uint4*)&kb_blk[(size_t)pi * KBS] = pk;
                 }
             }
             // row sums: fixed-order reduction (deterministic): lanes sharing tx, then the 8 warps
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
-                acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    tacc[ch][k] += __shfl_xor_sync(0xffffffffu, tacc[ch][k], 8);
-                    tacc[ch][k] += __shfl_xor_sync(0xffffffffu, tacc[ch][k], 16);
+                for (int o = TXN; o < 32; o <<= 1) {
+                    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) tacc[ch][k] += __shfl_xor_sync(0xffffffffu, tacc[ch][k], o);
                 }
             }
-            float* w = ws + flip * NS * 512;
-            if (lane < 8) {
+            float* w = ws + flip * NS * 8 * KBS;
+            if (lane < TXN) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    w[warp * 64 + (lane << 3) + k] = acc[k];
+                    w[warp * KBS + (lane << 3) + k] = acc[k];
 #pragma unroll
-                    for (int ch = 0; ch < C; ++ch) w[(1 + ch) * 512 + warp * 64 + (lane << 3) + k] = tacc[ch][k];
+                    for (int ch = 0; ch < C; ++ch) w[(1 + ch) * 8 * KBS + warp * KBS + (lane << 3) + k] = tacc[ch][k];
                 }
             }
             __syncthreads();
-            for (int i = tid; i < NS * 64; i += AFF_THREADS) {
-                const int which = i >> 6, sidx = i & 63;
+            for (int i = tid; i < NS * KBS; i += AFF_THREADS) {
+                const int which = i / KBS, sidx = i % KBS;
                 float sum = 0.f;
 #pragma unroll
-                for (int wi = 0; wi < 8; ++wi) sum += w[which * 512 + wi * 64 + sidx];
+                for (int wi = 0; wi < 8; ++wi) sum += w[which * 8 * KBS + wi * KBS + sidx];
                 cta_sum[which * p_pad + sb + sidx] += sum;
             }
             flip ^= 1;
@@ -254,6 +256,7 @@ struct KbGeom {
     int W;            // image width
     int64_t q0, q1;   // raster range of the band
     int p_pad;        // sample count rounded up to 64
+    int kbs;          // sample slots per block: 64 or 32
 };
 
 static void kb_layout_for(const KbGeom& geo, const std::vector<uint32_t>& samples, bool cut, int64_t R, int S, bool count_only, KbLayout* out,
@@ -297,7 +300,7 @@ static void kb_layout_for(const KbGeom& geo, const std::vector<uint32_t>& sample
             while (start < hi) {
                 if (!count_only) out->starts.push_back((int)start);
                 ++cnt;
-                start += 64;
+                start += geo.kbs;
                 prev_end = start;
             }
         };
@@ -366,12 +369,12 @@ static int kb_choose_and_build(const KbGeom& geo, const std::vector<uint32_t>& s
 
 // Host-only view of the layout (no GPU, no context): what gl_affinity would store for these samples.  Used by the CPU tests.
 extern "C" int gl_kb_layout_host(int width, int64_t q0, int64_t q1, const uint32_t* samples, unsigned p, double h_loc, int cutoff,
-                                 int strips, int* strips_out, int64_t* n_tiles, int64_t* n_blocks, int32_t* tile_first,
+                                 int strips, int block_slots, int* strips_out, int64_t* n_tiles, int64_t* n_blocks, int32_t* tile_first,
                                  int32_t* tile_count, int32_t* starts, uint32_t* perm)
 {
     GL_REQUIRE(samples && p >= 1 && width > 0 && q1 > q0 && h_loc > 0, "gl_kb_layout_host: bad arguments");
     for (unsigned i = 1; i < p; ++i) GL_REQUIRE(samples[i] > samples[i - 1], "gl_kb_layout_host: samples must be strictly ascending");
-    const KbGeom geo = {width, q0, q1, (int)round_up(p, 64)};
+    const KbGeom geo = {width, q0, q1, (int)round_up(p, 64), block_slots == 32 ? 32 : 64};
     std::vector<uint32_t> sv(samples, samples + p);
     KbLayout lay;
     const int S = kb_choose_and_build(geo, sv, cutoff != 0, kb_reach(h_loc), strips, &lay);
@@ -396,12 +399,13 @@ static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
     }
     const bool cut = ctx->kb_cutoff && kind != GL_PHOTOMETRIC;
     const int64_t R = kb_reach(h_loc);
-    const int64_t key[6] = {W, ctx->q0, ctx->q1, p, R, (cut ? 1 : 0) + 2 * ctx->kb_strips};
+    const int kbs = ctx->kb_block == 32 ? 32 : 64;
+    const int64_t key[6] = {W, ctx->q0, ctx->q1, p, R, (cut ? 1 : 0) + 2 * ctx->kb_strips + 1000 * kbs};
     if (ctx->tile_tab && !memcmp(key, ctx->tab_key, sizeof(key)) && ctx->tab_samples.size() == (size_t)p &&
         !memcmp(ctx->tab_samples.data(), ctx->h_samples.data(), sizeof(uint32_t) * p))
         return GL_OK;  // same geometry, samples and cutoff as last time: the cached layout stands
     KbLayout lay;
-    const KbGeom geo = {W, ctx->q0, ctx->q1, ctx->p_pad};
+    const KbGeom geo = {W, ctx->q0, ctx->q1, ctx->p_pad, kbs};
     // the strip count depends on the geometry and the sample density, not on where exactly the samples fell: it is chosen
     // once per (geometry, p, reach) and reused when only the sample positions change (a new random draw costs one build)
     int forced = ctx->kb_strips;
@@ -425,8 +429,25 @@ static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
     }
     ctx->tile_total_blocks = lay.total;
     ctx->tile_strips = best_S;
+    ctx->tile_kbs = kbs;
     memcpy(ctx->tab_key, key, sizeof(key));
     ctx->tab_samples = ctx->h_samples;
+    return GL_OK;
+}
+
+template <int KIND, int C, int KBS>
+static int launch_affinity_b(gl_ctx* ctx, double h_loc, double h_val, const float* sf, const int4* tab, const int* starts, __half* KB,
+                             float* partial, int grid)
+{
+    const int p_pad = ctx->p_pad + 64;   // the K_B kernel works on the internal sample slots (p_int)
+    const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_pad + 2 * (1 + C) * 8 * KBS + (size_t)(2 + C) * AFF_TP);
+    GL_CUDA_CHECK(cudaFuncSetAttribute(k_affinity_B<KIND, C, KBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const float log2e = 1.4426950408889634f;
+    StageTimer kt(ctx, GL_T_K_AFFINITY_B);
+    k_affinity_B<KIND, C, KBS><<<grid, AFF_THREADS, smem, ctx->stream>>>(
+        (const uint8_t*)ctx->img->ptr, sf, p_pad, ctx->width, ctx->q0, ctx->q1, (float)(-log2e / (h_loc * h_loc)),
+        (float)(-log2e / (h_val * h_val)), tab, starts, KB, partial);
+    GL_LAUNCH_CHECK(ctx);
     return GL_OK;
 }
 
@@ -439,15 +460,8 @@ static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float*
     k_affinity_A<KIND, C><<<ga, 128, 0, ctx->stream>>>((const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p,
                                                       ctx->width, 1.0 / (h_loc * h_loc), 1.0 / (h_val * h_val), KA);
     GL_LAUNCH_CHECK(ctx);
-    const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_pad + 2 * (1 + C) * 8 * 64 + (size_t)(2 + C) * AFF_TP);
-    GL_CUDA_CHECK(cudaFuncSetAttribute(k_affinity_B<KIND, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const float log2e = 1.4426950408889634f;
-    StageTimer kt(ctx, GL_T_K_AFFINITY_B);
-    k_affinity_B<KIND, C><<<grid, AFF_THREADS, smem, ctx->stream>>>(
-        (const uint8_t*)ctx->img->ptr, sf, p_pad, ctx->width, ctx->q0, ctx->q1, (float)(-log2e / (h_loc * h_loc)),
-        (float)(-log2e / (h_val * h_val)), tab, starts, KB, partial);
-    GL_LAUNCH_CHECK(ctx);
-    return GL_OK;
+    if (ctx->tile_kbs == 32) return launch_affinity_b<KIND, C, 32>(ctx, h_loc, h_val, sf, tab, starts, KB, partial, grid);
+    return launch_affinity_b<KIND, C, 64>(ctx, h_loc, h_val, sf, tab, starts, KB, partial, grid);
 }
 
 int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A_out, gl_mat** K_B_out)
@@ -476,7 +490,7 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         KB->rows = p;                   // logical K_B: p x (n - p); stored transposed for the whole band
         KB->cols = ctx->n - p;
         KB->local_rows = n_band;
-        KB->ld = 64;                    // blocked storage: a pixel row of a block is 64 samples
+        KB->ld = ctx->kb_block == 32 ? 32 : 64;   // blocked storage: a pixel row of a block is `ld` sample slots
         KB->elem_bytes = 2;
         KB->p = p;
         KB->p_pad = p_pad;
@@ -489,7 +503,8 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         KB->perm = ctx->tile_perm;
         KB->perm->refs++;
         KB->total_blocks = ctx->tile_total_blocks;
-        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)KB->total_blocks * AFF_TP * 64, &KB->buf)) != GL_OK) break;
+        KB->kbs = ctx->tile_kbs;
+        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)KB->total_blocks * AFF_TP * KB->kbs, &KB->buf)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)(1 + C) * p_pad, &KB->aux)) != GL_OK) break;  // [D | T[ch]]
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_int, &sf)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * (1 + C) * p_int, &partial)) != GL_OK) break;

@@ -96,6 +96,7 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
     if (const char* g = getenv("GLB200_GEMM")) gl_ctx_set_option(ctx, "gemm", g);
     if (const char* g = getenv("GLB200_CTA_GROUP")) gl_ctx_set_option(ctx, "cta_group", g);
     if (const char* g = getenv("GLB200_JACOBI_TOL")) gl_ctx_set_option(ctx, "jacobi_tol", g);
+    if (const char* g = getenv("GLB200_KB_BLOCK")) gl_ctx_set_option(ctx, "kb_block", g);
     *out = ctx;
     return GL_OK;
 }
@@ -139,6 +140,9 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         GL_REQUIRE(ctx->gemm_prefetch >= 0 && ctx->gemm_prefetch <= 16, "option gemm_prefetch: want 0..16");
     } else if (!strcmp(key, "kb_cutoff")) {
         ctx->kb_cutoff = atoi(value) != 0;
+    } else if (!strcmp(key, "kb_block")) {
+        ctx->kb_block = atoi(value);
+        GL_REQUIRE(ctx->kb_block == 64 || ctx->kb_block == 32, "option kb_block: want 64|32");
     } else if (!strcmp(key, "kb_strips")) {
         ctx->kb_strips = atoi(value);
         GL_REQUIRE(ctx->kb_strips >= 0 && ctx->kb_strips <= 64, "option kb_strips: want 0..64");
@@ -660,7 +664,7 @@ __global__ void k_half_to_f64(const __half* __restrict__ src, int64_t ld, int64_
 // K_B from its blocked storage ([block][512 pixels][64 sample slots], affinity.cu) to dense fp64 rows x cols in the caller's
 // sample order; sample slots that no stored block of the tile covers (entries below the fp16 flush-to-zero cutoff) read as 0
 __global__ void k_kb_blocked_to_f64(const __half* __restrict__ src, const int4* __restrict__ tab, const int* __restrict__ starts,
-                                    const uint32_t* __restrict__ perm, int p_int, int64_t rows, int64_t cols, double scale,
+                                    const uint32_t* __restrict__ perm, int kbs, int p_int, int64_t rows, int64_t cols, double scale,
                                     double* __restrict__ dst)
 {
     // one thread per (pixel row, internal slot): the slot's sample decides the output column
@@ -674,8 +678,8 @@ __global__ void k_kb_blocked_to_f64(const __half* __restrict__ src, const int4* 
     double v = 0.0;
     for (int k = 0; k < tl.y; ++k) {
         const int sb = starts[tl.x + k];
-        if (slot >= sb && slot < sb + 64) {
-            v = (double)__half2float(src[(((size_t)tl.z + k) * 512 + (size_t)(r & 511)) * 64 + (slot - sb)]);
+        if (slot >= sb && slot < sb + kbs) {
+            v = (double)__half2float(src[(((size_t)tl.z + k) * 512 + (size_t)(r & 511)) * kbs + (slot - sb)]);
             break;
         }
     }
@@ -733,8 +737,8 @@ int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap)
     case GL_MAT_KB: {
         const int p_int = m->p_pad + 64;
         k_kb_blocked_to_f64<<<(unsigned)ceil_div(rows * p_int, T), T, 0, ctx->stream>>>(
-            (const __half*)m->buf->ptr, (const int4*)m->tiles->ptr, (const int*)m->starts->ptr, (const uint32_t*)m->perm->ptr, p_int, rows,
-            cols, m->scale, d);
+            (const __half*)m->buf->ptr, (const int4*)m->tiles->ptr, (const int*)m->starts->ptr, (const uint32_t*)m->perm->ptr, m->kbs, p_int,
+            rows, cols, m->scale, d);
         break;
     }
     case GL_MAT_PHI:

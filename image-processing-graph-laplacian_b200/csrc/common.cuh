@@ -98,7 +98,8 @@ struct gl_mat {
     gl_buf* tiles = nullptr;     // KB: int4 per 512-pixel tile {first entry in `starts`, block count, storage offset, 0}
     gl_buf* starts = nullptr;    // KB: first internal sample slot of every stored block
     gl_buf* perm = nullptr;      // KB: internal sample slot -> index in the caller's sample list (u32 [p_pad + 64])
-    int64_t total_blocks = 0;    // KB: stored [512 x 64] blocks (see affinity.cu)
+    int64_t total_blocks = 0;    // KB: stored [512 x kbs] blocks (see affinity.cu)
+    int kbs = 64;                // KB: sample slots per block (64 or 32)
     gl_buf* dscale = nullptr;    // optional device double holding `scale` (L_B: -alpha), so no host sync is needed
     bool scale_on_host = true;   // false until the device value has been fetched
     int refs = 1;
@@ -155,6 +156,8 @@ struct gl_ctx {
     gl_buf* tile_starts = nullptr;
     gl_buf* tile_perm = nullptr;
     int tile_strips = 1;      // column strips of the cached layout
+    int tile_kbs = 64;        // sample slots per block of the cached layout
+    int kb_block = 64;        // option kb_block: 64 or 32 sample slots per stored K_B block
     int kb_strips = 0;        // option kb_strips: 0 = choose the strip count with the fewest blocks, n = force n strips
     std::vector<int4> h_tile_tab;
     std::vector<uint32_t> tab_samples;  // the samples and parameters the cached table was built from
@@ -251,7 +254,7 @@ struct gl_gemm_fuse {
 // A is either a dense [rows][k_pad] K-major matrix (a_tab == nullptr) or K_B's blocked storage with its tile table
 int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
                    const float* scales, const void* addend, void* D, const int4* a_tab = nullptr, int64_t a_total_blocks = 0,
-                   gl_gemm_fuse* fuse = nullptr, const int* a_starts = nullptr);
+                   gl_gemm_fuse* fuse = nullptr, const int* a_starts = nullptr, int a_kbs = 64);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -214,19 +214,19 @@ __global__ void __launch_bounds__(256) k_gemm_simple(const T* __restrict__ A, co
 
 // element (pixel row r, internal sample slot k) of K_B in its blocked storage; slots no stored block of the tile covers are zero
 __device__ __forceinline__ float kb_blocked_at(const __half* __restrict__ A, const int4* __restrict__ tab, const int* __restrict__ starts,
-                                               int64_t r, int k)
+                                               int kbs, int64_t r, int k)
 {
     const int4 tl = tab[r >> 9];
     for (int b = 0; b < tl.y; ++b) {
         const int sb = starts[tl.x + b];
-        if (k >= sb && k < sb + 64) return __half2float(A[(((size_t)tl.z + b) * 512 + (size_t)(r & 511)) * 64 + (k - sb)]);
+        if (k >= sb && k < sb + kbs) return __half2float(A[(((size_t)tl.z + b) * 512 + (size_t)(r & 511)) * kbs + (k - sb)]);
     }
     return 0.f;
 }
 
 __global__ void __launch_bounds__(256) k_gemm_simple_blocked(const __half* __restrict__ A, const int4* __restrict__ tab,
-                                                             const int* __restrict__ starts, const __half* __restrict__ Bt, int64_t M,
-                                                             int N, int K,
+                                                             const int* __restrict__ starts, int kbs, const __half* __restrict__ Bt,
+                                                             int64_t M, int N, int K,
                                                              const float* __restrict__ scales, __half* __restrict__ D)
 {
     __shared__ float As[32][33], Bs[32][33];
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) k_gemm_simple_blocked(const __half* __res
     for (int k0 = 0; k0 < K; k0 += 32) {
         for (int i = threadIdx.x; i < 32 * 32; i += 256) {
             const int r = i >> 5, c = i & 31;
-            As[r][c] = (m0 + r < M) ? kb_blocked_at(A, tab, starts, m0 + r, k0 + c) : 0.f;
+            As[r][c] = (m0 + r < M) ? kb_blocked_at(A, tab, starts, kbs, m0 + r, k0 + c) : 0.f;
             Bs[r][c] = (n0 + r < N) ? __half2float(Bt[(size_t)(n0 + r) * K + k0 + c]) : 0.f;
         }
         __syncthreads();
@@ -273,10 +273,10 @@ constexpr int C_SLAB_BYTES = 32 * 128;                     // 32 rows x 64 bf16
 // two shapes of the shared-memory budget (227 KB): a deep operand ring for long K loops (dense A, the epilogue has
 // slack: one store slab per epilogue warp), or a shorter ring with double-buffered store slabs for the short K loops of
 // the blocked K_B, where the epilogue is the critical path
-template <int STAGES, int CBUFS, int EPI_WARPS>
+template <int STAGES, int CBUFS, int EPI_WARPS, int BK = 64>
 constexpr int smem_bytes()
 {
-    return STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_WARPS * CBUFS * C_SLAB_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
+    return STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) * BK / 64 + EPI_WARPS * CBUFS * C_SLAB_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
 }
 
 // One persistent CTA per SM.  warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator,
@@ -285,7 +285,8 @@ constexpr int smem_bytes()
 // FC > 0 fuses the filter application into the epilogue (FC = image channels): besides storing the fp16 tile, every
 // epilogue thread accumulates dot(row of D, w[:, ch]) over its columns from the fp32 accumulators and writes one partial
 // per (N tile, column share) to zpart[part][row][ch]; filter.cu sums the partials in fixed order (deterministic).
-template <int STAGES, int CBUFS, int EPI_WARPS, int FC>
+// BK = elements of K per shared-memory stage: 64 (SWIZZLE_128B operands) or 32 (SWIZZLE_64B; K_B stored in 32-slot blocks).
+template <int STAGES, int CBUFS, int EPI_WARPS, int FC, int BK>
 __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, int m_tiles, int n_tiles, int k_blocks, int n_total, int block_n,
@@ -298,8 +299,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem_a + STAGES * A_STAGE_BYTES;
-    uint8_t* smem_c = smem_b + STAGES * B_STAGE_BYTES;
+    constexpr int A_STAGE = A_STAGE_BYTES * BK / 64, B_STAGE = B_STAGE_BYTES * BK / 64;
+    uint8_t* smem_b = smem_a + STAGES * A_STAGE;
+    uint8_t* smem_c = smem_b + STAGES * B_STAGE;
     uint64_t* bars = (uint64_t*)(smem_c + EPI_WARPS * CBUFS * C_SLAB_BYTES);
     // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then the TMEM base address
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
@@ -336,7 +338,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t stage_tx = (uint32_t)(A_STAGE_BYTES + block_n * BLOCK_K * 2);
+    const uint32_t stage_tx = (uint32_t)(A_STAGE + block_n * BK * 2);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -347,7 +349,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int mt = tile / n_tiles, nt = tile % n_tiles;
                 // dense A: K block kb of rows mt*128..; blocked A (K_B): stored block (offset + kb) of the 512-pixel tile, rows
                 // (mt % 4) * 128.. inside it, multiplying the 64 rows of W that start at the block's first sample slot
-                int kb_count = k_blocks, a_row = mt * BLOCK_M, a_row_step = 0, a_col_step = BLOCK_K;
+                int kb_count = k_blocks, a_row = mt * BLOCK_M, a_row_step = 0, a_col_step = BK;
                 const int* my_starts = nullptr;
                 if (a_tab) {
                     const int4 tl = a_tab[mt >> 2];
@@ -368,10 +370,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1, err, 1);
                     mbar_expect_tx(bar_full + 8 * stage, stage_tx);
-                    tma_load_2d(smem_u32(smem_a + stage * A_STAGE_BYTES), &map_a, bar_full + 8 * stage, kb * a_col_step,
+                    tma_load_2d(smem_u32(smem_a + stage * A_STAGE), &map_a, bar_full + 8 * stage, kb * a_col_step,
                                 a_row + kb * a_row_step);
-                    tma_load_2d(smem_u32(smem_b + stage * B_STAGE_BYTES), &map_b, bar_full + 8 * stage,
-                                my_starts ? my_starts[kb] : kb * BLOCK_K, nt * block_n);
+                    tma_load_2d(smem_u32(smem_b + stage * B_STAGE), &map_b, bar_full + 8 * stage,
+                                my_starts ? my_starts[kb] : kb * BK, nt * block_n);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -395,10 +397,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase, err, 3);
                     tcgen05_fence_after();
-                    const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-                    const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+                    const uint64_t da = make_smem_desc_k<BK>(smem_u32(smem_a + stage * A_STAGE));
+                    const uint64_t db = make_smem_desc_k<BK>(smem_u32(smem_b + stage * B_STAGE));
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in the >>4 address field
                         umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
                     }
@@ -548,8 +550,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // (ab_bf16: 0 = fp16, 1 = bf16).  k_pad % 64 == 0; n_pad is 64, 128 or a multiple of 256 (gl_m_pad).
 int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_pad, const void* Bt, int n_pad,
                    const float* scales, const void* addend, void* D, const int4* a_tab, int64_t a_total_blocks, gl_gemm_fuse* fuse,
-                   const int* a_starts)
+                   const int* a_starts, int a_kbs)
 {
+    GL_REQUIRE(a_kbs == 64 || (a_kbs == 32 && a_tab), "gemm: 32-slot blocks only exist for the blocked operand");
     GL_REQUIRE(!a_tab == !a_starts, "gemm: the blocked operand needs both its tile table and its block starts");
     GL_REQUIRE(k_pad % 64 == 0 && n_pad % 64 == 0, "gemm: k_pad %d / n_pad %d must be multiples of 64", k_pad, n_pad);
     GL_REQUIRE(!(fuse && ctx->gemm_impl == 1), "gemm: the CUDA-core checker has no fused filter");
@@ -558,8 +561,8 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
         GL_REQUIRE(ceil_div(rows, 32) < 2147483647ll, "gemm(simple): band too large");
         if (a_tab) {
             GL_REQUIRE(!ab_bf16 && !addend, "gemm(simple): the blocked operand is fp16 K_B without addend");
-            k_gemm_simple_blocked<<<grid, 256, 0, ctx->stream>>>((const __half*)A, a_tab, a_starts, (const __half*)Bt, rows, n_pad, k_pad,
-                                                                 scales, (__half*)D);
+            k_gemm_simple_blocked<<<grid, 256, 0, ctx->stream>>>((const __half*)A, a_tab, a_starts, a_kbs, (const __half*)Bt, rows, n_pad,
+                                                                 k_pad, scales, (__half*)D);
         } else if (ab_bf16)
             k_gemm_simple<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bt, rows, n_pad,
                                                                          k_pad, scales, (const __half*)addend,
@@ -574,11 +577,12 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     GL_REQUIRE(n_pad % block_n == 0, "gemm: n_pad %d is not a multiple of the N tile %d", n_pad, block_n);
     const CUtensorMapDataType dt = ab_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap map_a, map_b, map_d;
-    if (a_tab)  // K_B's blocked storage seen as one tall [blocks * 512][64] matrix
-        GL_CHECK(make_map_2d(&map_a, dt, A, (uint64_t)a_total_blocks * 512, 64, 64, tc::BLOCK_K, tc::BLOCK_M));
+    const CUtensorMapSwizzle sw = a_kbs == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    if (a_tab)  // K_B's blocked storage seen as one tall [blocks * 512][slots per block] matrix
+        GL_CHECK(make_map_2d(&map_a, dt, A, (uint64_t)a_total_blocks * 512, (uint64_t)a_kbs, (uint64_t)a_kbs, (uint32_t)a_kbs, tc::BLOCK_M, sw));
     else
         GL_CHECK(make_map_2d(&map_a, dt, A, (uint64_t)rows, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, tc::BLOCK_M));
-    GL_CHECK(make_map_2d(&map_b, dt, Bt, (uint64_t)n_pad, (uint64_t)k_pad, (uint64_t)k_pad, tc::BLOCK_K, (uint32_t)block_n));
+    GL_CHECK(make_map_2d(&map_b, dt, Bt, (uint64_t)n_pad, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)a_kbs, (uint32_t)block_n, sw));
     // (no D: the store map is never used; it is encoded over A's storage only to have a valid descriptor)
     GL_CHECK(make_map_2d(&map_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D ? D : A, (uint64_t)(D ? rows : 32), (uint64_t)(D ? n_pad : 64),
                          (uint64_t)(D ? n_pad : 64), 64, 32));
@@ -591,7 +595,7 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     int grid = ctx->sm_count;
     if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
     // short K loops (blocked K_B with few blocks per tile): the epilogue is the critical path
-    const bool short_k = a_tab != nullptr && a_total_blocks * 4 < (int64_t)m_tiles * 8;   // fewer than 8 K blocks per M tile on average
+    const bool short_k = a_tab != nullptr && a_total_blocks * 4 * a_kbs < (int64_t)m_tiles * 8 * 64;   // < 512 K elements per M tile on average
     const int pf = short_k ? ctx->gemm_prefetch : 0;   // with long K loops the ring already covers the latency; prefetch only adds L2 churn
     const bool deep = !(ctx->gemm_stages == 3 || (ctx->gemm_stages == 0 && short_k));
     const int FCH = fuse ? fuse->C : 0;
@@ -608,13 +612,19 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     const int store_d = D != nullptr;
     GL_REQUIRE(store_d || fuse, "gemm: no output requested");
     StageTimer kt(ctx, GL_T_K_GEMM);
-#define GEMM_LAUNCH(S, CB, EW, FC)                                                                                           \
+#define GEMM_LAUNCH_BK(S, CB, EW, FC, BK)                                                                                       \
     do {                                                                                                                       \
-        const int SM = tc::smem_bytes<S, CB, EW>() + w_bytes;                                                                  \
-        GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<S, CB, EW, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
-        tc::k_gemm_tcgen05<S, CB, EW, FC><<<grid, 128 + 32 * EW, SM, ctx->stream>>>(                                            \
+        const int SM = tc::smem_bytes<S, CB, EW, BK>() + w_bytes;                                                              \
+        GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<S, CB, EW, FC, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
+        tc::k_gemm_tcgen05<S, CB, EW, FC, BK><<<grid, 128 + 32 * EW, SM, ctx->stream>>>(                                        \
             map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad, block_n, ab_bf16, scales, (const __half*)addend, rows, a_tab, \
             a_starts, pf, fw, zp, store_d, (int*)err->ptr);                                                                                        \
+    } while (0)
+    // 32-slot blocks: stages are half as large, so the rings are twice as deep
+#define GEMM_LAUNCH(S, CB, EW, FC)                                \
+    do {                                                          \
+        if (a_kbs == 32) GEMM_LAUNCH_BK(2 * S, CB, EW, FC, 32);   \
+        else GEMM_LAUNCH_BK(S, CB, EW, FC, 64);                   \
     } while (0)
     if (!deep) {
         if (FCH == 1) GEMM_LAUNCH(3, 2, 8, 1);
@@ -627,6 +637,7 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
         else GEMM_LAUNCH(4, 2, 4, 0);
     }
 #undef GEMM_LAUNCH
+#undef GEMM_LAUNCH_BK
     gl_buf_release(err);
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;
@@ -718,7 +729,7 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
         }
         rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, k_dim, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
                             keep_phi ? phi->buf->ptr : nullptr, (const int4*)L_B->tiles->ptr, L_B->total_blocks, do_fuse ? &fuse : nullptr,
-                            (const int*)L_B->starts->ptr);
+                            (const int*)L_B->starts->ptr, L_B->kbs);
         if (rc == GL_OK && do_fuse)
             rc = gl_filter_fused_finish(ctx, phi, (const float*)zpart->ptr, fuse.parts, (const float*)wbuf->ptr, U, (int)phi_A->ld,
                                         ff->clip_low, ff->z_f32, ff->z_u8);

@@ -149,6 +149,21 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t w)
     return __half22float2(*(const __half2*)&w);
 }
 
+// The same for rows of BK 16-bit elements: BK = 64 -> SWIZZLE_128B (above), BK = 32 -> SWIZZLE_64B (rows of 64 bytes, 8-row groups
+// 512 bytes apart, layout type 4)
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc_k(uint32_t saddr)
+{
+    if (BK == 64) return make_smem_desc(saddr);
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;           // stride byte offset: 8 rows x 64 bytes
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                    // SWIZZLE_64B
+    return d;
+}
+
 // MN-major ("transposed") SWIZZLE_128B operand: the tile sits in shared memory as K rows of 64 M/N-contiguous elements
 // (128 bytes), 8-row groups 1024 bytes apart (stride byte offset), and successive 64-element M/N chunks `chunk_bytes`
 // apart (leading byte offset) -- the canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
@@ -192,7 +207,7 @@ static inline PFN_encodeTiled get_encode()
 
 // 2-D row-major 16-bit tensor [rows][cols] (cols contiguous), box = box_cols x box_rows, SWIZZLE_128B
 static inline int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                       uint32_t box_cols, uint32_t box_rows)
+                       uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
@@ -203,8 +218,8 @@ static inline int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const vo
     cuuint64_t strides[1] = {ld_elems * 2};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         gl_set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r, (unsigned long long)rows,
                      (unsigned long long)cols, (unsigned long long)ld_elems, box_cols, box_rows);

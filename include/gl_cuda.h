@@ -78,7 +78,7 @@ typedef struct gl_mat_info {
     int64_t ld;          /* leading dimension in elements of the stored layout */
     int elem_bytes;
     double scale;        /* logical value = scale * stored value (L_B = -alpha K_B shares K_B's buffer) */
-    int64_t stored_blocks; /* KB: [512 x 64] blocks held (of ceil(local_rows/512) * ceil(p/64) dense ones); else 0 */
+    int64_t stored_blocks; /* KB: [512 x ld] blocks held (ld = 64, or 32 with option kb_block; dense: ceil(local_rows/512) * ceil(p/ld)); else 0 */
 } gl_mat_info;
 
 /* Stage indices for gl_ctx_stage_ms (same vocabulary as the reference's stdout timers,
@@ -195,11 +195,11 @@ GL_API int gl_mat_upload(gl_ctx* ctx, int kind, const double* data, int64_t rows
 
 /* ---- inspection (host only, no GPU needed) ------------------------------------------------------------------------
  * The storage layout gl_affinity gives K_B for these (strictly ascending) samples over the raster range [q0, q1): per
- * 512-pixel tile `tile_count` blocks of 64 sample slots whose first slots are starts[tile_first ...]; perm[slot] = index
+ * 512-pixel tile `tile_count` blocks of `block_slots` sample slots whose first slots are starts[tile_first ...]; perm[slot] = index
  * of the sample in `samples` (0xffffffff: empty), p_pad + 64 slots with p_pad = p rounded up to 64.  Call once with the
  * arrays NULL to learn n_tiles / n_blocks.  strips = 0 lets the library choose the number of column strips. */
 GL_API int gl_kb_layout_host(int width, int64_t q0, int64_t q1, const uint32_t* samples, unsigned p, double h_loc, int cutoff,
-                             int strips, int* strips_out, int64_t* n_tiles, int64_t* n_blocks, int32_t* tile_first,
+                             int strips, int block_slots /* 64 or 32 */, int* strips_out, int64_t* n_tiles, int64_t* n_blocks, int32_t* tile_first,
                              int32_t* tile_count, int32_t* starts, uint32_t* perm);
 
 /* ---- pinned host memory for callers that want async copies ------------------------------------ */

@@ -467,7 +467,7 @@ def test_kb_cutoff_blocks(ctx):
             ctx.set_samples(s)
             K_A, K_B = ctx.affinity(gl.BILATERAL, h_loc, 30.0)
             info = K_B.info
-            dense_blocks = -(-img.size // 512) * -(-len(s) // 64)
+            dense_blocks = -(-img.size // 512) * (-(-len(s) // 64) * 64 // info.ld)     # info.ld: slots per block (64; 32 with kb_block)
             D = K_B.rowsums()
             L_A, L_B = ctx.laplacian(K_A, K_B)
             U, mu, mu_inv = ctx.eigensolve(L_A, -1)
@@ -491,6 +491,53 @@ def test_kb_cutoff_blocks(ctx):
     refp = oc.run_pipeline(img, s, h_loc=h_loc)
     assert np.max(np.abs(out[1]["mu"] - refp["mu"]) / refp["mu"]) <= TOL_MU
     assert _rel(out[1]["z"], refp["z"]) <= TOL_Z and _rel(out[1]["z"] - img, refp["z"] - img) <= TOL_DZ
+
+
+@pytest.mark.parametrize("W,H,ch,p,h_loc", [(640, 480, 1, 300, 12.0), (301, 203, 3, 130, 40.0), (1920, 1080, 1, 1000, 40.0)])
+def test_kb_block_32_matches_64(ctx, W, H, ch, p, h_loc):
+    """Option kb_block=32: K_B stored in 32-slot blocks (fewer padded slots; the GEMM runs with 32-deep K steps and
+    64-byte swizzled tiles).  K_B, eigenvalues and the filtered image must equal the 64-slot run; Phi through the
+    tcgen05 GEMM must equal the CUDA-core checker."""
+    img = o.synthetic_image(W, H, ch, seed=11)
+    s = oc.random_sampling(W, H, p, 5)
+    small = W * H * p < 1e8            # matrices are downloaded as fp64: only where that is a few hundred MB
+    cols = np.arange(0, W * H, 53)
+    out = {}
+    for blk in (64, 32):
+        ctx.set_option("kb_block", blk)
+        try:
+            ctx.set_image(img)
+            ctx.set_samples(s)
+            K_A, K_B = ctx.affinity(gl.BILATERAL, h_loc, 30.0)
+            assert K_B.info.ld == blk
+            L_A, L_B = ctx.laplacian(K_A, K_B)
+            U, mu, mu_inv = ctx.eigensolve(L_A, -1)
+            r = dict(D=K_B.rowsums(), mu=mu.download(), blocks=K_B.info.stored_blocks)
+            if small:
+                r["KB"] = K_B.download()[cols]
+                ctx.set_option("lazy_phi", 0)
+                r["phi"] = ctx.nystroem(L_B, U, mu_inv).download()
+                ctx.set_option("gemm", "simple")
+                r["chk"] = ctx.nystroem(L_B, U, mu_inv).download()
+                ctx.set_option("gemm", "tcgen05")
+                ctx.set_option("lazy_phi", 1)
+            r["z"] = ctx.filter(ctx.nystroem(L_B, U, mu_inv), mu).astype(np.float64)     # deferred Phi: the fused pass
+            out[blk] = r
+        finally:
+            ctx.set_option("gemm", "tcgen05")
+            ctx.set_option("lazy_phi", 1)
+            ctx.set_option("kb_block", 64)
+    a, b = out[64], out[32]
+    print(f"kb_block: stored slots {a['blocks'] * 64} (64) vs {b['blocks'] * 32} (32)")
+    assert np.max(np.abs(a["D"] - b["D"]) / a["D"]) < 1e-6
+    assert np.max(np.abs(a["mu"] - b["mu"]) / a["mu"]) < 1e-6
+    if small:
+        assert np.array_equal(a["KB"], b["KB"])
+        assert _rel(b["phi"], b["chk"]) < 2e-3 and _rel(a["phi"], a["chk"]) < 2e-3
+        assert _rel(b["phi"], a["phi"]) < 2e-3
+    y = img.astype(np.float64).reshape(a["z"].shape)
+    assert _rel(b["z"], a["z"]) < 1e-5
+    assert _rel(b["z"] - y, a["z"] - y) < 2e-3
 
 
 @pytest.mark.parametrize("W,H,ch,kind,h_loc,h_val", [

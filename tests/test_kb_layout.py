@@ -17,10 +17,12 @@ TP = 512
 def _covered(lay, t):
     """internal slots covered by tile t's blocks (each at most once)"""
     st = lay["starts"][lay["tile_first"][t]: lay["tile_first"][t] + lay["tile_count"][t]]
-    assert np.all(st % 8 == 0) and np.all(np.diff(st) >= 64), "blocks must be ascending, aligned to 8 and disjoint"
-    return st, np.concatenate([np.arange(s, s + 64) for s in st])
+    B = lay["block"]
+    assert np.all(st % 8 == 0) and np.all(np.diff(st) >= B), "blocks must be ascending, aligned to 8 and disjoint"
+    return st, np.concatenate([np.arange(s, s + B) for s in st])
 
 
+@pytest.mark.parametrize("block", [64, 32])
 @pytest.mark.parametrize("W,H,p,h_loc,method,band", [
     (3840, 400, 300, 40.0, "random", None),        # wide image: several column strips pay off
     (640, 480, 400, 12.0, "uniform", None),
@@ -28,12 +30,12 @@ def _covered(lay, t):
     (97, 61, 40, 40.0, "uniform", None),           # reach larger than the image: everything must be covered
     (200, 2000, 600, 10.0, "random", (1000, 2000)),
 ])
-def test_layout_covers_every_pair_within_reach_exactly_once(W, H, p, h_loc, method, band):
+def test_layout_covers_every_pair_within_reach_exactly_once(W, H, p, h_loc, method, band, block):
     s = o.random_sampling(W, H, p, 3) if method == "random" else o.uniform_sampling(W, H, p)
     p = len(s)
     r0, r1 = band if band else (0, H)
     q0, q1 = r0 * W, r1 * W
-    lay = gl.kb_layout(W, q0, q1, s, h_loc=h_loc)
+    lay = gl.kb_layout(W, q0, q1, s, h_loc=h_loc, block=block)
     p_pad = (p + 63) // 64 * 64
     perm = lay["perm"]
     assert perm.shape == (p_pad + 64,)
@@ -86,3 +88,6 @@ def test_layout_cutoff_shrinks_storage_at_4k():
     rows_only = gl.kb_layout(W, 0, W * H, s, strips=1)
     assert auto["n_blocks"] == 26849 and rows_only["n_blocks"] < 0.25 * dense     # 26 849: what the B200 bench reports
     assert auto["strips"] > 1 and auto["n_blocks"] < 0.6 * rows_only["n_blocks"]
+    half = gl.kb_layout(W, 0, W * H, s, block=32)                                  # 32-slot blocks: fewer stored slots
+    print("32-slot blocks:", half["n_blocks"], "strips", half["strips"], "vs 64-slot", auto["n_blocks"], auto["strips"])
+    assert half["n_blocks"] == 44779 and half["n_blocks"] * 32 < 0.85 * auto["n_blocks"] * 64    # 17 % fewer slots
