@@ -39,7 +39,7 @@ EXPORTS = [
     "gl_sampling_uniform", "gl_sampling_random", "gl_set_samples", "gl_get_samples",
     "gl_affinity", "gl_laplacian", "gl_eigensolve", "gl_nystroem", "gl_nystroem_filter", "gl_orthonormalise", "gl_filter",
     "gl_diag_inverse", "gl_diag_pow", "gl_full_affinity", "gl_full_laplacian", "gl_full_result", "gl_run", "gl_run_resident",
-    "gl_mat_info_get", "gl_mat_retain", "gl_mat_destroy", "gl_mat_download", "gl_mat_rowsums", "gl_mat_upload",
+    "gl_mat_info_get", "gl_mat_retain", "gl_mat_destroy", "gl_mat_download", "gl_mat_download_cols", "gl_mat_rowsums", "gl_mat_upload",
     "gl_host_alloc", "gl_host_free", "gl_kb_layout_host",
 ]
 
@@ -115,6 +115,7 @@ def lib():
         L.gl_mat_destroy.argtypes = [vp]
         L.gl_mat_retain.argtypes = [vp]
         L.gl_mat_download.argtypes = [vp, vp, vp, C.c_size_t]
+        L.gl_mat_download_cols.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_size_t]
         L.gl_mat_rowsums.argtypes = [vp, vp, vp, C.c_size_t]
         L.gl_mat_upload.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(vp)]
         L.gl_kb_layout_host.argtypes = [C.c_int, C.c_int64, C.c_int64, vp, C.c_uint, C.c_double, C.c_int, C.c_int, C.c_int, ip,
@@ -210,6 +211,14 @@ class Mat:
             shape = (i.rows, i.cols)
         out = np.empty(shape, dtype=np.float64)
         _check(lib().gl_mat_download(self.ctx.h, self.h, out.ctypes.data, out.size))
+        return out
+
+    def download_cols(self, col0: int, ncols: int = 1) -> np.ndarray:
+        """columns [col0, col0 + ncols) of a Phi (band rows), eigenvector or p x p matrix (WriteMatCol, hpc/display.c:85-100)"""
+        i = self.info
+        rows = i.local_rows if i.kind == MAT_PHI else i.rows
+        out = np.empty((rows, ncols), dtype=np.float64)
+        _check(lib().gl_mat_download_cols(self.ctx.h, self.h, col0, ncols, out.ctypes.data, out.size))
         return out
 
     def rowsums(self) -> np.ndarray:

@@ -701,6 +701,20 @@ __global__ void k_f64_to_colmajor_f32(const double* __restrict__ src, int64_t ro
     int64_t r = i / cols, c = i % cols;
     dst[c * ld + r] = (float)src[i];
 }
+// dst[r][c] = scale * src(r, col0 + c) for a strip of columns; layout: 0 fp16 row-major (Phi), 1 fp32 column-major (eigenvectors),
+// 2 fp64 row-major (K_A / L_A)
+__global__ void k_col_strip_to_f64(const void* __restrict__ src, int layout, int64_t ld, int64_t rows, int col0, int ncols, double scale,
+                                   double* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ncols) return;
+    const int64_t r = i / ncols, c = col0 + i % ncols;
+    double v;
+    if (layout == 0) v = (double)__half2float(((const __half*)src)[r * ld + c]);
+    else if (layout == 1) v = (double)((const float*)src)[c * ld + r];
+    else v = ((const double*)src)[r * ld + c];
+    dst[i] = scale * v;
+}
 __global__ void k_scale_f64(const double* __restrict__ src, int64_t count, double scale, double* __restrict__ dst)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -753,6 +767,35 @@ int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap)
     }
     GL_LAUNCH_CHECK(ctx);
     GL_CUDA_CHECK(cudaMemcpyAsync(out, d, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    gl_buf_release(tmp);
+    return GL_OK;
+}
+
+int gl_mat_download_cols(gl_ctx* ctx, const gl_mat* m, int col0, int ncols, double* out, size_t cap)
+{
+    GL_REQUIRE(ctx && m && out, "gl_mat_download_cols: null");
+    GL_REQUIRE(m->kind == GL_MAT_PHI || m->kind == GL_MAT_EIGVEC || m->kind == GL_MAT_KA,
+               "gl_mat_download_cols: want a Phi, eigenvector or p x p matrix, got kind %d", m->kind);
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (m->kind == GL_MAT_PHI && m->def_LB) GL_CHECK(gl_phi_materialise(ctx, const_cast<gl_mat*>(m)));
+    const int64_t rows = m->kind == GL_MAT_PHI ? m->local_rows : m->rows;
+    const int64_t cols = m->kind == GL_MAT_PHI ? m->m : m->cols;
+    GL_REQUIRE(col0 >= 0 && ncols >= 1 && (int64_t)col0 + ncols <= cols, "gl_mat_download_cols: columns [%d, %d) of %lld", col0,
+               col0 + ncols, (long long)cols);
+    const int64_t count = rows * ncols;
+    GL_REQUIRE((size_t)count <= cap, "gl_mat_download_cols: need room for %lld doubles, got %zu", (long long)count, cap);
+    if (!m->scale_on_host) {
+        gl_mat_info tmp_info;
+        GL_CHECK(gl_mat_info_get(m, &tmp_info));
+    }
+    gl_buf* tmp = nullptr;
+    GL_CHECK(gl_alloc(ctx, sizeof(double) * (size_t)count, &tmp));
+    const int layout = m->kind == GL_MAT_PHI ? 0 : (m->kind == GL_MAT_EIGVEC ? 1 : 2);
+    k_col_strip_to_f64<<<(unsigned)ceil_div(count, 256), 256, 0, ctx->stream>>>(m->buf->ptr, layout, m->ld, rows, col0, ncols,
+                                                                               layout == 1 ? 1.0 : m->scale, (double*)tmp->ptr);
+    GL_LAUNCH_CHECK(ctx);
+    GL_CUDA_CHECK(cudaMemcpyAsync(out, tmp->ptr, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
     GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     gl_buf_release(tmp);
     return GL_OK;

@@ -88,6 +88,8 @@ void OptionsInit(int argc, char** argv)
     if (OptionsGetScalar("-filter_pow", &dv)) { g_opt.filter_pow = dv; g_opt.filter_pow_set = 1; }
     g_opt.gram_schmidt = OptionsHasName("-gram_schmidt");
     g_opt.color = OptionsHasName("-color");
+    if (OptionsGetInt("-dump_eigvecs", &iv) && iv > 0) g_opt.dump_eigvecs = iv;
+    g_opt.dump_scaled = OptionsHasName("-dump_scaled");
     if (OptionsGetInt("-ngpus", &iv) && iv >= 1 && iv <= 64) g_opt.ngpus = iv;
     if (OptionsGetString("-synthetic", buf, sizeof buf)) sscanf(buf, "%dx%d", &g_opt.synthetic_w, &g_opt.synthetic_h);
 }

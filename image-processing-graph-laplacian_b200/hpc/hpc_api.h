@@ -43,6 +43,8 @@ void OrthonormaliseMat(Mat phi, PetscScalar* norms);
 /* ---- display.c (reference hpc/display.h:8-14) ------------------------------------------------------------------ */
 void WriteVec(Vec v, const char* const filename);
 void WriteDiagMat(Mat x, const char* const filename);
+void WriteMatCol(Mat x, const unsigned int col_num, const char* const filename);
+void WritePngMatCol(Mat x, const unsigned int col_num, const unsigned int width, const unsigned int height, const char* const filename);
 png_bytep* ComputeResultFromLaplacian(const png_bytep* const img_bytes, Mat phi, Mat Pi, const unsigned int width, const unsigned int height);
 png_bytep* ComputeResultFromEntireLaplacian(const png_bytep* const img_bytes, Mat Lapl, const unsigned int width, const unsigned int height);
 

@@ -7,7 +7,7 @@
  *   - the stages after the eigensolve (Nystroem, Permutation, MatPow, ComputeResultFromLaplacian) are live; the
  *     reference has them inside a comment and returns NULL (hpc/image_processing.c:237-276);
  *   - knobs the reference hard-codes are options (glhost.h): -sample_size, -sampling, -seed, -affinity, -h_loc,
- *     -h_val, -filter_gain, -filter_pow, -gram_schmidt, -color, -ngpus, -synthetic WxH, -o OUTPUT;
+ *     -h_val, -filter_gain, -filter_pow, -gram_schmidt, -dump_eigvecs K, -dump_scaled, -color, -ngpus, -synthetic WxH, -o OUTPUT;
  *   - "processes" are one forked process per GPU (-ngpus), not MPI ranks.
  */
 #include <stdio.h>
@@ -170,6 +170,15 @@ static png_bytep* ApproximationComputation(const RunOptions* o, png_bytep* img_b
     Mat eigvecs_perm = Permutation(eigvecs, sample_indices, p);
     MatDestroy(&eigvecs);
     eigvecs = eigvecs_perm;
+
+    /* hpc/image_processing.c:255-260 (eigenvectors 0..2 as text and as images; here on request: at 4K a column is 8.3 M lines) */
+    for (int k = 0; k < g_opt.dump_eigvecs && k < (int)m; ++k) {
+        char path[96];
+        snprintf(path, sizeof path, "results/eigenvector_%d_laplacian.txt", k);
+        WriteMatCol(eigvecs, (unsigned int)k, path);
+        snprintf(path, sizeof path, "results/eigenvector_%d_laplacian.png", k);
+        WritePngMatCol(eigvecs, (unsigned int)k, width, height, path);
+    }
 
     if (g_opt.gram_schmidt) {
         t0 = StageClock();

@@ -188,6 +188,10 @@ GL_API int gl_mat_destroy(gl_mat* m);  /* drop one reference (MatDestroy) */
 /* Download as fp64, logical values (scale applied), row-major rows x cols; for KB/PHI: this rank's band
  * rows x logical cols.  `cap` = number of doubles `out` can hold. */
 GL_API int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap);
+/* A strip of columns [col0, col0 + ncols) of a Phi (this rank's band rows), eigenvector or p x p matrix, as fp64 row-major
+ * rows x ncols (replaces MatGetColumnVector / GetFirstCols+GetLastCols in WriteMatCol / WritePngMatCol, hpc/display.c:85-126);
+ * a 4K Phi is 17 GB on the device and 66 GB as fp64, so the eigenvector dumps must not go through gl_mat_download. */
+GL_API int gl_mat_download_cols(gl_ctx* ctx, const gl_mat* m, int col0, int ncols, double* out, size_t cap);
 /* D = rowsum(K_A)+rowsum(K_B) carried by a KB handle (p doubles), already summed over ranks. */
 GL_API int gl_mat_rowsums(gl_ctx* ctx, const gl_mat* K_B, double* out, size_t cap);
 /* Upload a host fp64 row-major matrix as GL_MAT_KA / GL_MAT_EIGVEC / GL_MAT_DIAG (tests, host-built inputs). */

@@ -239,6 +239,26 @@ def test_gram_schmidt_wide_phi(ctx, gram):
     assert err_z <= TOL_Z and err_dz <= TOL_DZ
 
 
+def test_column_strip_download(ctx, golden):
+    """gl_mat_download_cols (what WriteMatCol / WritePngMatCol read, hpc/display.c:85-126) against the full download."""
+    g = golden("cat_small_random50")
+    ctx.set_image(g["image"])
+    ctx.set_samples(g["sample_indices"])
+    K_A, K_B = ctx.affinity(str(g["kind"]), float(g["h_loc"]), float(g["h_val"]))
+    L_A, L_B = ctx.laplacian(K_A, K_B)
+    U, mu, mu_inv = ctx.eigensolve(L_A, -1)
+    phi = ctx.nystroem(L_B, U, mu_inv)                   # deferred: the strip download has to materialise it
+    strip = phi.download_cols(3, 4)
+    full = phi.download()
+    assert strip.shape == (g["image"].size, 4) and np.array_equal(strip, full[:, 3:7])
+    assert np.array_equal(U.download_cols(0, 2), U.download()[:, :2])
+    assert np.array_equal(L_A.download_cols(7, 1), L_A.download()[:, 7:8])
+    with pytest.raises(gl.GLError):
+        phi.download_cols(full.shape[1] - 1, 2)
+    with pytest.raises(gl.GLError):
+        K_B.download_cols(0, 1)
+
+
 def test_stage_by_stage_phi_properties(ctx, golden):
     g = golden("cat_small_random50")
     img, s = g["image"], g["sample_indices"]

@@ -229,6 +229,44 @@ def test_binary_options(golden, tmp_path):
     assert np.max(np.abs(z8 - ref["z"].astype(np.uint8).astype(np.int32))) <= 1
 
 
+def _read_vec(path):
+    lines = open(path).read().split("\n")
+    assert lines[0].startswith("Vec Object:")
+    return np.array([float(x) for x in lines[2:] if x.strip()])
+
+
+def _same_up_to_sign(a, b, tol):
+    return min(np.linalg.norm(a - b), np.linalg.norm(a + b)) <= tol * np.linalg.norm(b)
+
+
+@pytest.mark.gpu
+def test_binary_eigenvector_dumps(golden, tmp_path):
+    """-dump_eigvecs K: WriteMatCol / WritePngMatCol of the extrapolated eigenvectors (hpc/image_processing.c:255-260,
+    hpc/display.c:85-126): text in the PETSc ASCII Vec layout, PNGs with the reference's byte cast or (-dump_scaled)
+    stretched to the column's range.  Columns are compared with the oracle's Phi up to sign."""
+    from oracle import oracle_np as o
+    g = golden("test_uniform100")
+    img = g["image"]
+    src = str(tmp_path / "in.png")
+    PIL.fromarray(img).save(src)
+    ref = o.run_pipeline(img, g["sample_indices"], return_phi=True)
+    _run_bin(tmp_path, ["-f", src, "-sample_size", str(int(g["p_req"])), "-dump_eigvecs", "3", "-dump_scaled"])
+    for k in range(3):
+        v = _read_vec(str(tmp_path / "results" / ("eigenvector_%d_laplacian.txt" % k)))
+        assert v.shape == (img.size,)
+        assert _same_up_to_sign(v, ref["phi"][:, k], 2e-3), k              # fp16 storage of Phi
+        png = np.asarray(PIL.open(str(tmp_path / "results" / ("eigenvector_%d_laplacian.png" % k)))).astype(np.float64)
+        assert png.shape == img.shape and png.min() == 0 and png.max() == 255
+        want = np.floor((v - v.min()) * (255.0 / (v.max() - v.min()))).reshape(img.shape)
+        assert np.max(np.abs(png - want)) <= 1
+    # without -dump_scaled: the reference's cast of O(1/sqrt(n)) entries gives a black image
+    _run_bin(tmp_path, ["-f", src, "-sample_size", str(int(g["p_req"])), "-dump_eigvecs", "1"])
+    assert np.asarray(PIL.open(str(tmp_path / "results" / "eigenvector_0_laplacian.png"))).max() <= 1
+    # the output image is the same with and without the dumps (Phi materialised early for them)
+    z8 = np.asarray(PIL.open(str(tmp_path / "results" / "output.png"))).astype(np.int32)
+    assert np.max(np.abs(z8 - o.quantise(g["z"]).astype(np.int32))) <= 1
+
+
 @pytest.mark.gpu
 def test_binary_two_ranks(golden, tmp_path):
     """-ngpus 2: one forked process per GPU (the reference's `mpiexec -n 2`), bands of rows, NCCL id through shared
@@ -247,3 +285,10 @@ def test_binary_two_ranks(golden, tmp_path):
     r = _run_bin(tmp_path, ["-f", src, "-sample_size", "256", "-ngpus", "2", "-gram_schmidt", "-o", out])
     z8 = np.asarray(PIL.open(out)).astype(np.int32)
     assert np.max(np.abs(z8 - o.quantise(g["z_gs"]).astype(np.int32))) <= 1
+    # eigenvector dump gathered from both bands equals the one-rank dump
+    _run_bin(tmp_path, ["-f", src, "-sample_size", "256", "-ngpus", "2", "-dump_eigvecs", "2", "-o", out])
+    two = [_read_vec(str(tmp_path / "results" / ("eigenvector_%d_laplacian.txt" % k))) for k in range(2)]
+    _run_bin(tmp_path, ["-f", src, "-sample_size", "256", "-dump_eigvecs", "2", "-o", out])
+    for k in range(2):
+        one = _read_vec(str(tmp_path / "results" / ("eigenvector_%d_laplacian.txt" % k)))
+        assert one.shape == (g["image"].size,) and _same_up_to_sign(two[k], one, 1e-3)
