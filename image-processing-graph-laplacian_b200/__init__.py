@@ -31,7 +31,7 @@ STAGES = ["h2d", "sampling", "affinity", "laplacian", "eigen", "nystroem", "gram
           "k_affinity_b", "k_gemm", "k_filter_project", "k_filter_apply", "k_jacobi"]
 
 EXPORTS = [
-    "gl_version", "gl_last_error", "gl_default_params", "gl_device_count", "gl_kernel_launches",
+    "gl_version", "gl_last_error", "gl_default_params", "gl_device_count", "gl_memory_stats", "gl_kernel_launches",
     "gl_ctx_create", "gl_ctx_destroy", "gl_ctx_sync", "gl_ctx_stage_ms", "gl_ctx_set_option", "gl_ctx_mark",
     "gl_ctx_mark_elapsed_ms",
     "gl_comm_unique_id", "gl_comm_init",
@@ -85,6 +85,7 @@ def lib():
         L.gl_ctx_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.gl_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
         L.gl_kernel_launches.argtypes = [vp, C.POINTER(C.c_longlong)]
+        L.gl_memory_stats.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int]
         L.gl_ctx_mark.argtypes = [vp, C.c_int]
         L.gl_ctx_mark_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.gl_comm_unique_id.argtypes = [vp]
@@ -280,6 +281,12 @@ class Context:
         ms = C.c_float()
         _check(lib().gl_ctx_mark_elapsed_ms(self.h, a, b, C.byref(ms)))
         return ms.value
+
+    def memory_stats(self, reset_peak=False) -> dict:
+        """bytes of device memory held by live handles / cached for reuse / peak live since the last reset"""
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _check(lib().gl_memory_stats(self.h, C.byref(a), C.byref(b), C.byref(c), int(reset_peak)))
+        return dict(live=a.value, cached=b.value, peak=c.value)
 
     def kernel_launches(self) -> int:
         n = C.c_longlong()

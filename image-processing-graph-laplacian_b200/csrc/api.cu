@@ -53,6 +53,16 @@ int gl_device_count(int* count)
     return GL_OK;
 }
 
+int gl_memory_stats(gl_ctx* ctx, size_t* live, size_t* cached, size_t* peak, int reset_peak)
+{
+    GL_REQUIRE(ctx, "gl_memory_stats: null");
+    if (live) *live = ctx->bytes_live;
+    if (cached) *cached = ctx->bytes_cached;
+    if (peak) *peak = ctx->bytes_peak;
+    if (reset_peak) ctx->bytes_peak = ctx->bytes_live;
+    return GL_OK;
+}
+
 int gl_kernel_launches(gl_ctx* ctx, long long* count)
 {
     GL_REQUIRE(ctx && count, "gl_kernel_launches: null");
@@ -97,6 +107,7 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
     if (const char* g = getenv("GLB200_CTA_GROUP")) gl_ctx_set_option(ctx, "cta_group", g);
     if (const char* g = getenv("GLB200_JACOBI_TOL")) gl_ctx_set_option(ctx, "jacobi_tol", g);
     if (const char* g = getenv("GLB200_KB_BLOCK")) gl_ctx_set_option(ctx, "kb_block", g);
+    if (const char* g = getenv("GLB200_EPI_WARPS")) gl_ctx_set_option(ctx, "gemm_epi_warps", g);
     *out = ctx;
     return GL_OK;
 }
@@ -140,6 +151,12 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         GL_REQUIRE(ctx->gemm_prefetch >= 0 && ctx->gemm_prefetch <= 16, "option gemm_prefetch: want 0..16");
     } else if (!strcmp(key, "kb_cutoff")) {
         ctx->kb_cutoff = atoi(value) != 0;
+    } else if (!strcmp(key, "phi_limit_mb")) {
+        ctx->phi_limit_mb = atoll(value);
+        GL_REQUIRE(ctx->phi_limit_mb >= 0, "option phi_limit_mb: want >= 0 (0 = no limit)");
+    } else if (!strcmp(key, "gemm_epi_warps")) {
+        ctx->gemm_epi_warps = atoi(value);
+        GL_REQUIRE(ctx->gemm_epi_warps == 0 || ctx->gemm_epi_warps == 8 || ctx->gemm_epi_warps == 16, "option gemm_epi_warps: want 0|8|16");
     } else if (!strcmp(key, "kb_block")) {
         ctx->kb_block = atoi(value);
         GL_REQUIRE(ctx->kb_block == 64 || ctx->kb_block == 32, "option kb_block: want 64|32");
@@ -273,6 +290,7 @@ int gl_alloc(gl_ctx* ctx, size_t bytes, gl_buf** out)
     b->bytes = got;
     b->owner = ctx;
     ctx->bytes_live += got;
+    if (ctx->bytes_live > ctx->bytes_peak) ctx->bytes_peak = ctx->bytes_live;
     *out = b;
     return GL_OK;
 }
@@ -931,8 +949,21 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
             ctx->ev_valid[GL_T_FILTER] = false;
             // option keep_phi=0: Phi is only a temporary of this one-call path, so its tiles can be consumed in the epilogue
             // and never written to HBM at all
-            if ((rc = gl_nystroem_filter(ctx, L_B, U, mu_inv, f_mu, prm->gain, prm->clip_low, ctx->keep_phi ? &phi : nullptr, z_f32,
-                                         z_u8)) != GL_OK) break;
+            // A Phi that does not fit (config 5 on one GPU: 67 M pixels x 2048 columns = 275 GB) is not stored either:
+            // the fused pass needs K_B and the row partials only.  phi_limit_mb forces that path (tests).
+            bool keep = ctx->keep_phi;
+            const size_t phi_bytes = (size_t)L_B->local_rows * (size_t)gl_m_pad((int)U->cols) * 2;
+            if (keep && ctx->phi_limit_mb > 0 && phi_bytes > (size_t)ctx->phi_limit_mb << 20) keep = false;
+            if (keep && ctx->phi_nomem_bytes && phi_bytes >= ctx->phi_nomem_bytes) keep = false;
+            rc = gl_nystroem_filter(ctx, L_B, U, mu_inv, f_mu, prm->gain, prm->clip_low, keep ? &phi : nullptr, z_f32, z_u8);
+            if (rc == GL_ERR_NOMEM && keep) {
+                if (ctx->verbose) fprintf(stderr, "[glb200] Phi (%.1f GB) does not fit: consumed in the GEMM epilogue, not stored\n", phi_bytes / 1e9);
+                keep = false;
+                ctx->phi_nomem_bytes = phi_bytes;
+                rc = gl_nystroem_filter(ctx, L_B, U, mu_inv, f_mu, prm->gain, prm->clip_low, nullptr, z_f32, z_u8);
+            }
+            ctx->last_phi_stored = keep;
+            if (rc != GL_OK) break;
         } else if ((rc = gl_nystroem(ctx, L_B, U, mu_inv, &phi)) != GL_OK) break;
         gl_mat_destroy(L_B); L_B = nullptr;
         gl_mat_destroy(U); U = nullptr;

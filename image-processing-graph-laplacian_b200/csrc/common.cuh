@@ -157,6 +157,10 @@ struct gl_ctx {
     gl_buf* tile_perm = nullptr;
     int tile_strips = 1;      // column strips of the cached layout
     int tile_kbs = 64;        // sample slots per block of the cached layout
+    int gemm_epi_warps = 0;   // option gemm_epi_warps: 0 or 8 = eight epilogue warps, 16 = sixteen (measured slower, kept for experiments)
+    long long phi_limit_mb = 0;   // option phi_limit_mb: gl_run stores no Phi larger than this (0 = no limit but the memory)
+    bool last_phi_stored = true;  // whether the last fused gl_run wrote Phi
+    size_t phi_nomem_bytes = 0;   // smallest Phi whose allocation failed on this context (0: none yet): not tried again
     int kb_block = 64;        // option kb_block: 64 or 32 sample slots per stored K_B block
     int kb_strips = 0;        // option kb_strips: 0 = choose the strip count with the fewest blocks, n = force n strips
     std::vector<int4> h_tile_tab;
@@ -167,7 +171,7 @@ struct gl_ctx {
 
     // size-keyed cache of freed device blocks (no cudaMalloc in steady state)
     std::multimap<size_t, void*> free_blocks;
-    size_t bytes_cached = 0, bytes_live = 0;
+    size_t bytes_cached = 0, bytes_live = 0, bytes_peak = 0;
 
     // stage timers
     cudaEvent_t ev_begin[GL_T_COUNT] = {}, ev_end[GL_T_COUNT] = {};

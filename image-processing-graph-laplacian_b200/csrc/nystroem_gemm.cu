@@ -447,16 +447,22 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int c_end = split ? c_hi : (ch == 0 ? n_size : 0);
             for (int c0 = (split ? c_lo : 0); c0 < c_end; c0 += 64) {
                 uint8_t* slab = slab0 + buf * C_SLAB_BYTES;
-                // both halves of the 64-column group in flight before the wait
-                uint32_t v[2][32];
+                // eight warps: both halves of the 64-column group in flight before the wait; sixteen warps (96 registers per
+                // thread): one half at a time, the other warps cover the TMEM latency
+                constexpr bool SEQ = EPI_WARPS > 8;
+                uint32_t v[SEQ ? 1 : 2][32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v[0]);
-                tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v[1]);
+                if (!SEQ) tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v[SEQ ? 0 : 1]);
                 // the TMA store that last read this slab must be done with it
                 if (store_d && lane == 0) tma_store_wait_read<CBUFS - 1>();
                 tmem_ld_wait();
                 __syncwarp();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    if (SEQ && h == 1) {
+                        tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v[0]);
+                        tmem_ld_wait();
+                    }
                     uint32_t pk[16];
                     if (addend != nullptr) {
                         // D = addend + scale * acc (orthonormalise.cu: Phi + Phi E); one 64-byte run of this thread's row
@@ -471,14 +477,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (int j = 0; j < 4; ++j) {
                                 const int i = 4 * i4 + j;
                                 const float2 ad = unpack_h2(aw[j]);
-                                pk[i] = pack_h2(fmaf(__uint_as_float(v[h][2 * i]), sc, ad.x), fmaf(__uint_as_float(v[h][2 * i + 1]), sc, ad.y));
+                                pk[i] = pack_h2(fmaf(__uint_as_float(v[SEQ ? 0 : h][2 * i]), sc, ad.x), fmaf(__uint_as_float(v[SEQ ? 0 : h][2 * i + 1]), sc, ad.y));
                             }
                         }
                     } else {
                         if (store_d) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
-                                pk[i] = pack_h2(__uint_as_float(v[h][2 * i]) * sc, __uint_as_float(v[h][2 * i + 1]) * sc);
+                                pk[i] = pack_h2(__uint_as_float(v[SEQ ? 0 : h][2 * i]) * sc, __uint_as_float(v[SEQ ? 0 : h][2 * i + 1]) * sc);
                         }
                         if (FC > 0) {
                             // 32 columns starting at nt * block_n + c0 + 32 h; weights read as broadcast float4s
@@ -490,7 +496,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 for (int q = 0; q < 2 * FC; ++q) *(float4*)&wr[4 * q] = wv[g8 * 2 * FC + q];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float val = __uint_as_float(v[h][8 * g8 + i]) * sc;
+                                    const float val = __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i]) * sc;
 #pragma unroll
                                     for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
                                 }
@@ -599,13 +605,16 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     const int pf = short_k ? ctx->gemm_prefetch : 0;   // with long K loops the ring already covers the latency; prefetch only adds L2 churn
     const bool deep = !(ctx->gemm_stages == 3 || (ctx->gemm_stages == 0 && short_k));
     const int FCH = fuse ? fuse->C : 0;
+    // sixteen epilogue warps (four column shares of 64; option gemm_epi_warps=16): measured 2-3 % slower than eight on both the
+    // grey and the colour filter (the epilogue is not bound by per-warp latency), kept as an experiment switch
+    const bool wide_epi = !deep && !addend && block_n == 256 && ctx->gemm_epi_warps == 16;
     const int w_bytes = FCH * 4 * tc::MAX_BLOCK_N * (int)sizeof(float);   // per epilogue warp: its columns of one tile
     if (fuse) {
         GL_REQUIRE(!addend && (FCH == 1 || FCH == 3), "gemm: fused filter wants 1 or 3 channels and no addend");
         GL_REQUIRE(ctx->gemm_impl == 0, "gemm: the CUDA-core checker has no fused filter");
         GL_REQUIRE((deep ? tc::smem_bytes<4, 1, 4>() : tc::smem_bytes<3, 2, 8>()) + w_bytes <= tc::SMEM_LIMIT,
                    "gemm: no shared memory left for the filter weights");
-        fuse->parts = n_tiles * (deep ? 1 : 2);
+        fuse->parts = n_tiles * (deep ? 1 : (wide_epi ? 4 : 2));
     }
     const float* fw = fuse ? fuse->w : nullptr;
     float* zp = fuse ? fuse->zpart : nullptr;
@@ -626,7 +635,11 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
         if (a_kbs == 32) GEMM_LAUNCH_BK(2 * S, CB, EW, FC, 32);   \
         else GEMM_LAUNCH_BK(S, CB, EW, FC, 64);                   \
     } while (0)
-    if (!deep) {
+    if (wide_epi) {
+        if (FCH == 1) GEMM_LAUNCH(3, 1, 16, 1);
+        else if (FCH == 3) GEMM_LAUNCH(3, 1, 16, 3);
+        else GEMM_LAUNCH(3, 1, 16, 0);
+    } else if (!deep) {
         if (FCH == 1) GEMM_LAUNCH(3, 2, 8, 1);
         else if (FCH == 3) GEMM_LAUNCH(3, 2, 8, 3);
         else GEMM_LAUNCH(3, 2, 8, 0);
@@ -719,7 +732,7 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
             const int C = ctx->channels;
             if (!phi->proj) { gl_set_error("nystroem: fused filter needs the affinity sums of the current image"); rc = GL_ERR_ARG; break; }
             if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad * C, &wbuf)) != GL_OK) break;
-            const int parts_max = 2 * (m_pad / (m_pad < 256 ? m_pad : 256));
+            const int parts_max = (ctx->gemm_epi_warps == 16 ? 4 : 2) * (m_pad / (m_pad < 256 ? m_pad : 256));
             if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)parts_max * rows * C, &zpart)) != GL_OK) { gl_buf_release(wbuf); break; }
             if ((rc = gl_filter_weights_from_proj(ctx, (const double*)phi->proj->ptr, (const double*)ff->f_eigvals->buf->ptr, ff->gain, m, m_pad,
                                                   C, (float*)wbuf->ptr)) != GL_OK) { gl_buf_release(wbuf); gl_buf_release(zpart); break; }
@@ -784,8 +797,20 @@ int gl_phi_materialise(gl_ctx* ctx, gl_mat* phi, const gl_fused_filter* ff)
 {
     if (!phi->def_LB) return GL_OK;
     gl_mat *LB = phi->def_LB, *U = phi->def_U, *mi = phi->def_muinv;
-    const int rc = gl_impl_nystroem_into(ctx, LB, U, mi, phi, true, ff);
+    // with the filter riding along, a Phi that does not fit (or exceeds option phi_limit_mb) is consumed in the epilogue and
+    // stays deferred; whoever needs the matrix itself later gets the allocation error then
+    bool keep = true;
+    const size_t bytes = (size_t)phi->local_rows * (size_t)phi->m_pad * 2;
+    if (ff && ctx->phi_limit_mb > 0 && bytes > (size_t)ctx->phi_limit_mb << 20) keep = false;
+    if (ff && ctx->phi_nomem_bytes && bytes >= ctx->phi_nomem_bytes) keep = false;
+    int rc = gl_impl_nystroem_into(ctx, LB, U, mi, phi, keep, ff);
+    if (rc == GL_ERR_NOMEM && keep && ff) {
+        keep = false;
+        ctx->phi_nomem_bytes = bytes;
+        rc = gl_impl_nystroem_into(ctx, LB, U, mi, phi, false, ff);
+    }
     if (rc != GL_OK) return rc;
+    if (!keep) return GL_OK;
     phi->def_LB = phi->def_U = phi->def_muinv = nullptr;
     gl_mat_destroy(LB);
     gl_mat_destroy(U);

@@ -110,6 +110,9 @@ GL_API int gl_version(void);
 GL_API const char* gl_last_error(void);             /* thread-local text of the last failure */
 GL_API void gl_default_params(gl_params* p);
 GL_API int gl_device_count(int* count);             /* sm_100 devices visible */
+/* Device memory of this context's allocator in bytes: held by live handles and workspaces, cached for reuse, and the peak
+ * of `live` since the context was made (or since the last call with reset_peak != 0).  Any pointer may be NULL. */
+GL_API int gl_memory_stats(gl_ctx* ctx, size_t* live, size_t* cached, size_t* peak, int reset_peak);
 GL_API int gl_kernel_launches(gl_ctx* ctx, long long* count); /* kernels of this library launched on ctx so far */
 
 /* ---- context ----------------------------------------------------------------------------- */

@@ -239,6 +239,33 @@ def test_gram_schmidt_wide_phi(ctx, gram):
     assert err_z <= TOL_Z and err_dz <= TOL_DZ
 
 
+def test_phi_that_does_not_fit_is_not_stored(ctx):
+    """gl_run falls back to consuming Phi in the GEMM epilogue when it cannot be stored (config 5 on one GPU would need
+    275 GB); option phi_limit_mb forces that path at a small size.  Same z bit for bit, and the peak device memory
+    stays below the size of Phi."""
+    W, H, p = 1024, 768, 600
+    img = o.synthetic_image(W, H, 1, seed=21)
+    ctx.set_image(img)
+    prm = gl.default_params(sampling=gl.RANDOM, sample_size=p, seed=4)
+    z_a = np.zeros((H, W), np.float32)
+    ctx.run_resident(prm, z_out=z_a)
+    phi_bytes = W * H * 768 * 2                   # m = 599 -> 768 columns of fp16
+    ctx.set_option("phi_limit_mb", 64)
+    try:
+        ctx.memory_stats(reset_peak=True)
+        z_b = np.zeros((H, W), np.float32)
+        r = ctx.run_resident(prm, z_out=z_b, want_eigvals=True)
+        peak = ctx.memory_stats()["peak"]
+    finally:
+        ctx.set_option("phi_limit_mb", 0)
+    assert r["m"] == p - 1
+    assert np.array_equal(z_a, z_b)
+    assert peak < phi_bytes, (peak, phi_bytes)
+    ctx.memory_stats(reset_peak=True)
+    ctx.run_resident(prm, z_out=z_b)
+    assert ctx.memory_stats()["peak"] > phi_bytes    # the default path does store it
+
+
 def test_column_strip_download(ctx, golden):
     """gl_mat_download_cols (what WriteMatCol / WritePngMatCol read, hpc/display.c:85-126) against the full download."""
     g = golden("cat_small_random50")
