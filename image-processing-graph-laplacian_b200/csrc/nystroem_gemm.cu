@@ -303,15 +303,25 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* smem_b = smem_a + STAGES * A_STAGE;
     uint8_t* smem_c = smem_b + STAGES * B_STAGE;
     uint64_t* bars = (uint64_t*)(smem_c + EPI_WARPS * CBUFS * C_SLAB_BYTES);
-    // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then the TMEM base address
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
-    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+    // bars: [0,S) full (A of the step, and B when the step loads one), [S,2S) A slot empty, [2S,3S) B slot empty,
+    // [3S,3S+2) tmem_full, [3S+2,3S+4) tmem_empty, then the TMEM base address
+    static_assert(3 * STAGES + 5 <= 32, "barrier block is 256 bytes");
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES), bar_bempty = smem_u32(bars + 2 * STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 3 * STAGES), bar_tempty = smem_u32(bars + 3 * STAGES + 2);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
     float* w_s = (float*)(bars + 32);   // after the 256-byte barrier block (FC > 0 only): per epilogue warp, the filter
                                         // weights of the columns it drains in the current tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = m_tiles * n_tiles;
+    // Work is handed out in groups: the (up to) four 128-row M tiles of one 512-pixel tile of K_B times one N tile.  They share
+    // their list of K blocks, so the B operand (the W rows of those blocks) is loaded ONCE per group and stays in its slots
+    // while the four A tiles stream past it, which halves the L2 -> shared-memory traffic of a tile -- the bound of this kernel
+    // once Phi is not stored.  A group with more blocks than B slots, and the dense A (groups of one M tile), stream B too.
+    // With Phi stored the kernel sits on the HBM write wall instead, and handing out single M tiles (the four N tiles of a row
+    // written by neighbouring CTAs at the same time) writes faster: groups of one.
+    const int GROUP = (a_tab && !store_d) ? 4 : 1;
+    const int TSH = a_tab ? (GROUP == 4 ? 0 : 2) : 0;     // group index -> index of its 512-pixel tile in a_tab
+    const int total_groups = ((m_tiles + GROUP - 1) / GROUP) * n_tiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -322,6 +332,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
@@ -338,43 +349,61 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t stage_tx = (uint32_t)(A_STAGE + block_n * BK * 2);
+    const uint32_t a_tx = (uint32_t)A_STAGE, b_tx = (uint32_t)(block_n * BK * 2);
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0;
+            int stage = 0;           // A ring
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / n_tiles, nt = tile % n_tiles;
-                // dense A: K block kb of rows mt*128..; blocked A (K_B): stored block (offset + kb) of the 512-pixel tile, rows
-                // (mt % 4) * 128.. inside it, multiplying the 64 rows of W that start at the block's first sample slot
-                int kb_count = k_blocks, a_row = mt * BLOCK_M, a_row_step = 0, a_col_step = BK;
+            int bpos = 0;            // B ring: slot of the next B load
+            uint32_t bloads = 0;     // bit s: parity of the number of loads into B slot s so far
+            for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+                const int T = grp / n_tiles, nt = grp % n_tiles;
+                // dense A: K block kb of rows T*128..; blocked A (K_B): stored block (offset + kb) of the 512-pixel tile T, rows
+                // i * 128.. inside it, multiplying the 64 rows of W that start at the block's first sample slot
+                int kb_count = k_blocks, cnt = 1, a_row0 = T * BLOCK_M, a_row_step = 0, a_col_step = BK;
                 const int* my_starts = nullptr;
                 if (a_tab) {
-                    const int4 tl = a_tab[mt >> 2];
+                    const int4 tl = a_tab[T >> TSH];
                     my_starts = a_starts + tl.x;
                     kb_count = tl.y;
-                    a_row = tl.z * 512 + (mt & 3) * BLOCK_M;
+                    cnt = GROUP == 4 ? min(4, m_tiles - 4 * T) : 1;
+                    a_row0 = tl.z * 512 + (GROUP == 4 ? 0 : (T & 3) * BLOCK_M);
                     a_row_step = 512;
                     a_col_step = 0;
                 }
+                const bool resident = cnt > 1 && kb_count <= STAGES;
                 if (a_tab && prefetch_tiles > 0) {
-                    const int ft = tile + prefetch_tiles * (int)gridDim.x;
-                    if (ft < total_tiles) {
-                        const int fmt = ft / n_tiles;
-                        const int4 fl = a_tab[fmt >> 2];
-                        for (int kb = 0; kb < fl.y; ++kb) tma_prefetch_2d(&map_a, 0, fl.z * 512 + (fmt & 3) * BLOCK_M + kb * 512);
+                    const int fg = grp + prefetch_tiles * (int)gridDim.x;
+                    if (fg < total_groups) {
+                        const int fT = fg / n_tiles;
+                        const int4 fl = a_tab[fT >> TSH];
+                        const int fcnt = GROUP == 4 ? min(4, m_tiles - 4 * fT) : 1;
+                        const int frow = GROUP == 4 ? 0 : (fT & 3) * BLOCK_M;
+                        for (int kb = 0; kb < fl.y; ++kb)
+                            for (int i = 0; i < fcnt; ++i) tma_prefetch_2d(&map_a, 0, (fl.z + kb) * 512 + frow + i * BLOCK_M);
                     }
                 }
-                for (int kb = 0; kb < kb_count; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1, err, 1);
-                    mbar_expect_tx(bar_full + 8 * stage, stage_tx);
-                    tma_load_2d(smem_u32(smem_a + stage * A_STAGE), &map_a, bar_full + 8 * stage, kb * a_col_step,
-                                a_row + kb * a_row_step);
-                    tma_load_2d(smem_u32(smem_b + stage * B_STAGE), &map_b, bar_full + 8 * stage,
-                                my_starts ? my_starts[kb] : kb * BK, nt * block_n);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                for (int i = 0; i < cnt; ++i) {
+                    for (int kb = 0; kb < kb_count; ++kb) {
+                        const bool load_b = !resident || i == 0;
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1, err, 1);
+                        int bslot = stage;     // groups of one: B travels with A in the same slot, one barrier pair
+                        if (load_b && GROUP == 4) {
+                            bslot = bpos;
+                            mbar_wait(bar_bempty + 8 * bslot, ((bloads >> bslot) & 1u) ^ 1u, err, 5);
+                            bloads ^= 1u << bslot;
+                            if (++bpos == STAGES) bpos = 0;
+                        }
+                        mbar_expect_tx(bar_full + 8 * stage, load_b ? a_tx + b_tx : a_tx);
+                        tma_load_2d(smem_u32(smem_a + stage * A_STAGE), &map_a, bar_full + 8 * stage, kb * a_col_step,
+                                    a_row0 + i * BLOCK_M + kb * a_row_step);
+                        if (load_b)
+                            tma_load_2d(smem_u32(smem_b + bslot * B_STAGE), &map_b, bar_full + 8 * stage,
+                                        my_starts ? my_starts[kb] : kb * BK, nt * block_n);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -383,31 +412,53 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int bpos = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int nt = tile % n_tiles;
-                const int kb_count = a_tab ? a_tab[(tile / n_tiles) >> 2].y : k_blocks;
+            for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+                const int T = grp / n_tiles, nt = grp % n_tiles;
+                int kb_count = k_blocks, cnt = 1;
+                if (a_tab) {
+                    kb_count = a_tab[T >> TSH].y;
+                    cnt = GROUP == 4 ? min(4, m_tiles - 4 * T) : 1;
+                }
+                const bool resident = cnt > 1 && kb_count <= STAGES;
                 const int n_size = min(block_n, n_total - nt * block_n);
                 const uint32_t idesc = make_idesc(BLOCK_M, n_size, (uint32_t)ab_bf16);
-                const int acc = it & 1;
-                const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, err, 2);
-                tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_BLOCK_N);
-                for (int kb = 0; kb < kb_count; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase, err, 3);
+                const int b0 = bpos;
+                for (int i = 0; i < cnt; ++i, ++it) {
+                    const int acc = it & 1;
+                    const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, err, 2);
                     tcgen05_fence_after();
-                    const uint64_t da = make_smem_desc_k<BK>(smem_u32(smem_a + stage * A_STAGE));
-                    const uint64_t db = make_smem_desc_k<BK>(smem_u32(smem_b + stage * B_STAGE));
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_BLOCK_N);
+                    for (int kb = 0; kb < kb_count; ++kb) {
+                        int bslot = stage;
+                        if (resident) {
+                            bslot = b0 + kb;
+                            if (bslot >= STAGES) bslot -= STAGES;
+                        } else if (GROUP == 4) {
+                            bslot = bpos;
+                            if (++bpos == STAGES) bpos = 0;
+                        }
+                        mbar_wait(bar_full + 8 * stage, phase, err, 3);
+                        tcgen05_fence_after();
+                        const uint64_t da = make_smem_desc_k<BK>(smem_u32(smem_a + stage * A_STAGE));
+                        const uint64_t db = make_smem_desc_k<BK>(smem_u32(smem_b + bslot * B_STAGE));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in the >>4 address field
-                        umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 32 bytes (16 fp16) along K inside the swizzle row: +2 in the >>4 address field
+                            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        umma_commit(bar_empty + 8 * stage);   // frees the A slot when these MMAs retire
+                        if (GROUP == 4 && (!resident || i == cnt - 1)) umma_commit(bar_bempty + 8 * bslot);   // and the B slot after its last reader
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(bar_tfull + 8 * acc);  // accumulator complete
                 }
-                umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+                if (resident) {
+                    bpos = b0 + kb_count;
+                    if (bpos >= STAGES) bpos -= STAGES;
+                }
             }
         }
     } else if (warp >= 4) {
@@ -419,8 +470,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const float sc = scales[1];
         int it = 0;
         int buf = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int mt = tile / n_tiles, nt = tile % n_tiles;
+        for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x)
+        for (int gi = 0, gcnt = min(GROUP, m_tiles - GROUP * (grp / n_tiles)); gi < gcnt; ++gi, ++it) {
+            const int mt = GROUP * (grp / n_tiles) + gi, nt = grp % n_tiles;
             const int n_size = min(block_n, n_total - nt * block_n);
             // n_size is a multiple of 128, or 64 (then only share 0 works)
             const int c_lo = ch * (n_size / SHARES), c_hi = c_lo + n_size / SHARES;
@@ -429,11 +481,11 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const bool split = n_size >= 64 * SHARES;
             const int c_base = split ? c_lo : 0;
             float* w_mine = w_s + (size_t)(warp - 4) * (MAX_BLOCK_N / SHARES) * (FC > 0 ? FC : 1);
-            if (FC > 0) {
-                // this warp's slice of the weights for this tile, fetched while the MMAs of the tile are still running
+            if (FC > 0 && gi == 0) {
+                // this warp's slice of the weights for this group's N tile, fetched while the MMAs are still running
                 const int ncols = split ? n_size / SHARES : (ch == 0 ? n_size : 0);
                 const float* src = fuse_w + (size_t)(nt * block_n + c_base) * FC;
-                for (int i = lane; i < ncols * FC; i += 32) w_mine[i] = __ldg(src + i);
+                for (int i = lane; i < ncols * FC; i += 32) w_mine[i] = __ldg(src + i) * sc;   // the GEMM's output scale folded in
                 __syncwarp();
             }
             mbar_wait(bar_tfull + 8 * acc, acc_phase, err, 4);
@@ -487,16 +539,17 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 pk[i] = pack_h2(__uint_as_float(v[SEQ ? 0 : h][2 * i]) * sc, __uint_as_float(v[SEQ ? 0 : h][2 * i + 1]) * sc);
                         }
                         if (FC > 0) {
-                            // 32 columns starting at nt * block_n + c0 + 32 h; weights read as broadcast float4s
-                            const float4* wv = (const float4*)(w_mine + (size_t)(c0 - c_base + 32 * h) * FC);
+                            // 32 columns starting at nt * block_n + c0 + 32 h; weights (already times the output scale) read as
+                            // broadcast 16-byte shared-memory loads: one FFMA per element and channel, nothing else
+                            const uint32_t wv = smem_u32(w_mine) + (uint32_t)((c0 - c_base + 32 * h) * FC * 4);
 #pragma unroll
                             for (int g8 = 0; g8 < 4; ++g8) {   // 8 columns = 8 * FC floats = 2 * FC float4
                                 float wr[8 * (FC > 0 ? FC : 1)];
 #pragma unroll
-                                for (int q = 0; q < 2 * FC; ++q) *(float4*)&wr[4 * q] = wv[g8 * 2 * FC + q];
+                                for (int q = 0; q < 2 * FC; ++q) lds_f4(wv + (uint32_t)((g8 * 2 * FC + q) * 16), &wr[4 * q]);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float val = __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i]) * sc;
+                                    const float val = __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i]);
 #pragma unroll
                                     for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
                                 }
@@ -599,7 +652,8 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     GL_CHECK(gl_alloc(ctx, sizeof(int) * 4, &err));
     cudaMemsetAsync(err->ptr, 0, sizeof(int) * 4, ctx->stream);
     int grid = ctx->sm_count;
-    if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
+    const int64_t groups = (int64_t)ceil_div(m_tiles, (a_tab && D == nullptr) ? 4 : 1) * n_tiles;   // the kernel's unit of work
+    if ((int64_t)grid > groups) grid = (int)groups;
     // short K loops (blocked K_B with few blocks per tile): the epilogue is the critical path
     const bool short_k = a_tab != nullptr && a_total_blocks * 4 * a_kbs < (int64_t)m_tiles * 8 * 64;   // < 512 K elements per M tile on average
     const int pf = short_k ? ctx->gemm_prefetch : 0;   // with long K loops the ring already covers the latency; prefetch only adds L2 churn

@@ -55,6 +55,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
 }
 
+// 16-byte load from shared memory by its 32-bit shared address (LDS.128; through a generic pointer the compiler emits LD.E)
+__device__ __forceinline__ void lds_f4(uint32_t addr, float* dst)
+{
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst[0]), "=f"(dst[1]), "=f"(dst[2]), "=f"(dst[3]) : "r"(addr));
+}
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1)
 {
     asm volatile(
