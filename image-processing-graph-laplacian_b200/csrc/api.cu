@@ -107,7 +107,6 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
     if (const char* g = getenv("GLB200_CTA_GROUP")) gl_ctx_set_option(ctx, "cta_group", g);
     if (const char* g = getenv("GLB200_JACOBI_TOL")) gl_ctx_set_option(ctx, "jacobi_tol", g);
     if (const char* g = getenv("GLB200_KB_BLOCK")) gl_ctx_set_option(ctx, "kb_block", g);
-    if (const char* g = getenv("GLB200_EPI_WARPS")) gl_ctx_set_option(ctx, "gemm_epi_warps", g);
     *out = ctx;
     return GL_OK;
 }
@@ -154,9 +153,6 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
     } else if (!strcmp(key, "phi_limit_mb")) {
         ctx->phi_limit_mb = atoll(value);
         GL_REQUIRE(ctx->phi_limit_mb >= 0, "option phi_limit_mb: want >= 0 (0 = no limit)");
-    } else if (!strcmp(key, "gemm_epi_warps")) {
-        ctx->gemm_epi_warps = atoi(value);
-        GL_REQUIRE(ctx->gemm_epi_warps == 0 || ctx->gemm_epi_warps == 8 || ctx->gemm_epi_warps == 16, "option gemm_epi_warps: want 0|8|16");
     } else if (!strcmp(key, "kb_block")) {
         ctx->kb_block = atoi(value);
         GL_REQUIRE(ctx->kb_block == 64 || ctx->kb_block == 32, "option kb_block: want 64|32");

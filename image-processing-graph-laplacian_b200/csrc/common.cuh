@@ -157,7 +157,6 @@ struct gl_ctx {
     gl_buf* tile_perm = nullptr;
     int tile_strips = 1;      // column strips of the cached layout
     int tile_kbs = 64;        // sample slots per block of the cached layout
-    int gemm_epi_warps = 0;   // option gemm_epi_warps: 0 or 8 = eight epilogue warps, 16 = sixteen (measured slower, kept for experiments)
     long long phi_limit_mb = 0;   // option phi_limit_mb: gl_run stores no Phi larger than this (0 = no limit but the memory)
     bool last_phi_stored = true;  // whether the last fused gl_run wrote Phi
     size_t phi_nomem_bytes = 0;   // smallest Phi whose allocation failed on this context (0: none yet): not tried again

@@ -286,7 +286,8 @@ constexpr int smem_bytes()
 // epilogue thread accumulates dot(row of D, w[:, ch]) over its columns from the fp32 accumulators and writes one partial
 // per (N tile, column share) to zpart[part][row][ch]; filter.cu sums the partials in fixed order (deterministic).
 // BK = elements of K per shared-memory stage: 64 (SWIZZLE_128B operands) or 32 (SWIZZLE_64B; K_B stored in 32-slot blocks).
-template <int STAGES, int CBUFS, int EPI_WARPS, int FC, int BK>
+// ST = false (only with FC > 0): D is consumed by the fused filter and never written -- no packing, no store slabs, no TMA stores.
+template <int STAGES, int CBUFS, int EPI_WARPS, int FC, int BK, bool ST>
 __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, int m_tiles, int n_tiles, int k_blocks, int n_total, int block_n,
@@ -294,8 +295,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const int4* __restrict__ a_tab /* K_B tile table, or null for a dense A */,
                const int* __restrict__ a_starts /* K_B: first W row (sample slot) of every stored block */, int prefetch_tiles,
                const float* __restrict__ fuse_w /* [n_total][FC] */, float* __restrict__ zpart /* [parts][m_rows][FC] */,
-               int store_d /* 0: D is consumed by the fused filter only and never written */, int* __restrict__ err)
+               int* __restrict__ err)
 {
+    static_assert(ST || FC > 0, "a GEMM that neither stores nor filters has no output");
+    constexpr bool store_d = ST;
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -491,11 +494,11 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(bar_tfull + 8 * acc, acc_phase, err, 4);
             tcgen05_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * MAX_BLOCK_N);
-            float dot[FC > 0 ? FC : 1][4];   // four independent accumulation chains per channel (column mod 4): the FMAs pipeline
+            float dot[FC > 0 ? FC : 1][8];   // eight accumulation chains per channel (column mod 8), advanced two at a time by FFMA2
 #pragma unroll
             for (int q = 0; q < (FC > 0 ? FC : 1); ++q)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) dot[q][u] = 0.f;
+                for (int u = 0; u < 8; ++u) dot[q][u] = 0.f;
             const int c_end = split ? c_hi : (ch == 0 ? n_size : 0);
             for (int c0 = (split ? c_lo : 0); c0 < c_end; c0 += 64) {
                 uint8_t* slab = slab0 + buf * C_SLAB_BYTES;
@@ -516,7 +519,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         tmem_ld_wait();
                     }
                     uint32_t pk[16];
-                    if (addend != nullptr) {
+                    if (ST && addend != nullptr) {
                         // D = addend + scale * acc (orthonormalise.cu: Phi + Phi E); one 64-byte run of this thread's row
                         const int64_t row = (int64_t)mt * BLOCK_M + wq * 32 + lane;
                         const bool ok = row < m_rows;
@@ -547,11 +550,21 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 float wr[8 * (FC > 0 ? FC : 1)];
 #pragma unroll
                                 for (int q = 0; q < 2 * FC; ++q) lds_f4(wv + (uint32_t)((g8 * 2 * FC + q) * 16), &wr[4 * q]);
+                                if (FC == 1) {
+                                    // one channel: accumulator and weight pairs are register pairs already, two columns per FFMA2
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float val = __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i]);
+                                    for (int i = 0; i < 8; i += 2)
+                                        ffma2(dot[0][i], dot[0][i + 1], __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i]),
+                                              __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i + 1]), wr[i], wr[i + 1]);
+                                } else {
+                                    // three channels: the weights of a column pair are not adjacent, pairing them costs more moves than
+                                    // the FFMA2 saves (measured); four chains per channel
 #pragma unroll
-                                    for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float val = __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i]);
+#pragma unroll
+                                        for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
+                                    }
                                 }
                             }
                         }
@@ -585,7 +598,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int part = nt * SHARES + ch;
 #pragma unroll
                     for (int q = 0; q < FC; ++q)
-                        zpart[((size_t)part * m_rows + row) * FC + q] = (dot[q][0] + dot[q][1]) + (dot[q][2] + dot[q][3]);
+                        zpart[((size_t)part * m_rows + row) * FC + q] =
+                            ((dot[q][0] + dot[q][1]) + (dot[q][2] + dot[q][3])) + ((dot[q][4] + dot[q][5]) + (dot[q][6] + dot[q][7]));
                 }
             }
         }
@@ -659,52 +673,49 @@ int gl_gemm_kmajor(gl_ctx* ctx, const void* A, int ab_bf16, int64_t rows, int k_
     const int pf = short_k ? ctx->gemm_prefetch : 0;   // with long K loops the ring already covers the latency; prefetch only adds L2 churn
     const bool deep = !(ctx->gemm_stages == 3 || (ctx->gemm_stages == 0 && short_k));
     const int FCH = fuse ? fuse->C : 0;
-    // sixteen epilogue warps (four column shares of 64; option gemm_epi_warps=16): measured 2-3 % slower than eight on both the
-    // grey and the colour filter (the epilogue is not bound by per-warp latency), kept as an experiment switch
-    const bool wide_epi = !deep && !addend && block_n == 256 && ctx->gemm_epi_warps == 16;
     const int w_bytes = FCH * 4 * tc::MAX_BLOCK_N * (int)sizeof(float);   // per epilogue warp: its columns of one tile
     if (fuse) {
         GL_REQUIRE(!addend && (FCH == 1 || FCH == 3), "gemm: fused filter wants 1 or 3 channels and no addend");
         GL_REQUIRE(ctx->gemm_impl == 0, "gemm: the CUDA-core checker has no fused filter");
         GL_REQUIRE((deep ? tc::smem_bytes<4, 1, 4>() : tc::smem_bytes<3, 2, 8>()) + w_bytes <= tc::SMEM_LIMIT,
                    "gemm: no shared memory left for the filter weights");
-        fuse->parts = n_tiles * (deep ? 1 : (wide_epi ? 4 : 2));
+        fuse->parts = n_tiles * (deep ? 1 : 2);
     }
     const float* fw = fuse ? fuse->w : nullptr;
     float* zp = fuse ? fuse->zpart : nullptr;
     const int store_d = D != nullptr;
     GL_REQUIRE(store_d || fuse, "gemm: no output requested");
     StageTimer kt(ctx, GL_T_K_GEMM);
-#define GEMM_LAUNCH_BK(S, CB, EW, FC, BK)                                                                                       \
+#define GEMM_LAUNCH_ST(S, CB, EW, FC, BK, ST)                                                                                   \
     do {                                                                                                                       \
         const int SM = tc::smem_bytes<S, CB, EW, BK>() + w_bytes;                                                              \
-        GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<S, CB, EW, FC, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
-        tc::k_gemm_tcgen05<S, CB, EW, FC, BK><<<grid, 128 + 32 * EW, SM, ctx->stream>>>(                                        \
+        GL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_gemm_tcgen05<S, CB, EW, FC, BK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
+        tc::k_gemm_tcgen05<S, CB, EW, FC, BK, ST><<<grid, 128 + 32 * EW, SM, ctx->stream>>>(                                    \
             map_a, map_b, map_d, m_tiles, n_tiles, k_blocks, n_pad, block_n, ab_bf16, scales, (const __half*)addend, rows, a_tab, \
-            a_starts, pf, fw, zp, store_d, (int*)err->ptr);                                                                                        \
+            a_starts, pf, fw, zp, (int*)err->ptr);                                                                             \
     } while (0)
     // 32-slot blocks: stages are half as large, so the rings are twice as deep
-#define GEMM_LAUNCH(S, CB, EW, FC)                                \
-    do {                                                          \
-        if (a_kbs == 32) GEMM_LAUNCH_BK(2 * S, CB, EW, FC, 32);   \
-        else GEMM_LAUNCH_BK(S, CB, EW, FC, 64);                   \
+#define GEMM_LAUNCH(S, CB, EW, FC, ST)                                \
+    do {                                                              \
+        if (a_kbs == 32) GEMM_LAUNCH_ST(2 * S, CB, EW, FC, 32, ST);   \
+        else GEMM_LAUNCH_ST(S, CB, EW, FC, 64, ST);                   \
     } while (0)
-    if (wide_epi) {
-        if (FCH == 1) GEMM_LAUNCH(3, 1, 16, 1);
-        else if (FCH == 3) GEMM_LAUNCH(3, 1, 16, 3);
-        else GEMM_LAUNCH(3, 1, 16, 0);
-    } else if (!deep) {
-        if (FCH == 1) GEMM_LAUNCH(3, 2, 8, 1);
-        else if (FCH == 3) GEMM_LAUNCH(3, 2, 8, 3);
-        else GEMM_LAUNCH(3, 2, 8, 0);
+    if (!deep) {
+        if (FCH == 1 && store_d) GEMM_LAUNCH(3, 2, 8, 1, true);
+        else if (FCH == 1) GEMM_LAUNCH(3, 2, 8, 1, false);
+        else if (FCH == 3 && store_d) GEMM_LAUNCH(3, 2, 8, 3, true);
+        else if (FCH == 3) GEMM_LAUNCH(3, 2, 8, 3, false);
+        else GEMM_LAUNCH(3, 2, 8, 0, true);
     } else {
         // the deep ring leaves room for the weights only with single store slabs (the epilogue has slack here)
-        if (FCH == 1) GEMM_LAUNCH(4, 1, 4, 1);
-        else if (FCH == 3) GEMM_LAUNCH(4, 1, 4, 3);
-        else GEMM_LAUNCH(4, 2, 4, 0);
+        if (FCH == 1 && store_d) GEMM_LAUNCH(4, 1, 4, 1, true);
+        else if (FCH == 1) GEMM_LAUNCH(4, 1, 4, 1, false);
+        else if (FCH == 3 && store_d) GEMM_LAUNCH(4, 1, 4, 3, true);
+        else if (FCH == 3) GEMM_LAUNCH(4, 1, 4, 3, false);
+        else GEMM_LAUNCH(4, 2, 4, 0, true);
     }
 #undef GEMM_LAUNCH
-#undef GEMM_LAUNCH_BK
+#undef GEMM_LAUNCH_ST
     gl_buf_release(err);
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;
@@ -786,7 +797,7 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
             const int C = ctx->channels;
             if (!phi->proj) { gl_set_error("nystroem: fused filter needs the affinity sums of the current image"); rc = GL_ERR_ARG; break; }
             if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad * C, &wbuf)) != GL_OK) break;
-            const int parts_max = (ctx->gemm_epi_warps == 16 ? 4 : 2) * (m_pad / (m_pad < 256 ? m_pad : 256));
+            const int parts_max = 2 * (m_pad / (m_pad < 256 ? m_pad : 256));
             if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)parts_max * rows * C, &zpart)) != GL_OK) { gl_buf_release(wbuf); break; }
             if ((rc = gl_filter_weights_from_proj(ctx, (const double*)phi->proj->ptr, (const double*)ff->f_eigvals->buf->ptr, ff->gain, m, m_pad,
                                                   C, (float*)wbuf->ptr)) != GL_OK) { gl_buf_release(wbuf); gl_buf_release(zpart); break; }

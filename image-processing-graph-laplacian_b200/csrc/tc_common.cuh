@@ -55,6 +55,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
 }
 
+// two fp32 FMAs in one instruction (FFMA2, sm_100): (d0, d1) += (a0, a1) * (b0, b1), each lane rounded as a plain fma
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1)
+{
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // 16-byte load from shared memory by its 32-bit shared address (LDS.128; through a generic pointer the compiler emits LD.E)
 __device__ __forceinline__ void lds_f4(uint32_t addr, float* dst)
 {
