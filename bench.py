@@ -46,6 +46,7 @@ DESCR = {
     "c5s": "synthetic 8192x1024 colour (one eighth of config 5), p=2000 random, m=1999",
 }
 SEED_IMG, SEED_SAMPLES = 1234, 0
+NOSTORE_TRAFFIC = None   # dram bytes of the Phi-free GEMM from the ncu full-set capture (profiles/), filled in when captured
 
 
 def load_peaks():
@@ -304,10 +305,13 @@ def main():
         staged_calls()
     ctx.mark(7)
     staged_abi_ms = ctx.elapsed_ms(6, 7) / args.steps
-    # (1b) the fused path WITHOUT writing Phi (option keep_phi=0): Phi tiles live in tensor memory only
-    ctx.set_option("keep_phi", 0)
-    nophi = leg(4, ("nystroem", "k_gemm", "total"))
-    ctx.set_option("keep_phi", 1)
+    # (1b) the fused path that ALSO writes Phi to HBM (option keep_phi=1, the reference's data flow; the default consumes the
+    # Phi tiles in the GEMM epilogue and never stores them)
+    phistore = None
+    if phi_fits:
+        ctx.set_option("keep_phi", 1)
+        phistore = leg(4, ("nystroem", "k_gemm", "total"))
+        ctx.set_option("keep_phi", 0)
     # (3) the extrapolation GEMM with every K_B block stored and multiplied (option kb_cutoff=0): the tensor-pipe number
     dense_gemm_ms = None
     try:
@@ -339,7 +343,10 @@ def main():
     dense_blocks = -(-band_px // 512) * (p_pad // kb_slots)
     f_ext_exec = 2.0 * stored_blocks * 512 * kb_slots * m_pad          # MMA work actually issued (padding included)
     kb_bytes = stored_blocks * 512 * kb_slots * 2.0
-    gemm_bytes = kb_bytes + (band_px * m_pad * 2.0 if phi_fits else 0.0)    # K_B blocks read once + Phi written once
+    n_parts = 2 * max(1, m_pad // 256)                            # row partials of the fused filter: [parts][rows][channels] fp32
+    zpart_bytes = band_px * channels * 4.0 * n_parts
+    gemm_bytes = kb_bytes + zpart_bytes                          # default: K_B blocks read once + the row partials written (no Phi)
+    gemm_bytes_stored = kb_bytes + zpart_bytes + band_px * m_pad * 2.0   # option keep_phi=1: + Phi written once
     gemm_tf = f_ext / (med["k_gemm"] * 1e-3) / 1e12 if med["k_gemm"] > 0 else 0.0
     gemm_tf_exec = f_ext_exec / (med["k_gemm"] * 1e-3) / 1e12 if med["k_gemm"] > 0 else 0.0
     gemm_gbs = gemm_bytes / (med["k_gemm"] * 1e-3) / 1e9 if med["k_gemm"] > 0 else 0.0
@@ -350,18 +357,32 @@ def main():
     aff_ext_tf = (f_aff + f_ext) / ((med["k_affinity_b"] + med["k_gemm"]) * 1e-3) / 1e12
 
     # ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
-    NCU_TRAFFIC = {("c4", 1, "cutoff"): (19.14e9, "profiles/r01_ncu_full_c4_v5.txt"),
+    NCU_TRAFFIC = {("c4", 1, "nostore"): (NOSTORE_TRAFFIC, "profiles/r01_ncu_full_c4_v6.txt"),
+                   ("c4", 1, "stored"): (19.14e9, "profiles/r01_ncu_full_c4_v5.txt"),
                    ("c4", 1, "dense"): (33.9e9, "profiles/r01_ncu_full_c4.txt")}
     kept = stored_blocks / max(1, dense_blocks)
+    roof_stored = None
     if kept < 0.5:
-        # with the spatial cutoff the GEMM's K loop is short and the kernel is bound by the bytes it moves: the stored K_B
-        # blocks read once and Phi written once
-        tr = NCU_TRAFFIC.get((args.workload, world, "cutoff"))
-        roof = dict(kernel="k_gemm_tcgen05 (Nystroem extrapolation over the stored K_B blocks)", bound="hbm", achieved=gemm_gbs,
-                    peak=peaks["hbm"], unit="GB/s", frac=gemm_gbs / peaks["hbm"], traffic=tr[0] if tr else None,
-                    traffic_source=tr[1] if tr else None, peak_source=peaks["source"] + " copy bandwidth", ms=med["k_gemm"],
-                    bytes=gemm_bytes, note="91 %% of these bytes are WRITES (Phi); a pure 17 GB write (torch fill) runs at 3.94 TB/s on "
-                    "this part, the kernel writes at %.2f TB/s" % (band_px * m_pad * 2.0 / (med["k_gemm"] * 1e-3) / 1e12))
+        # With the spatial cutoff and Phi not stored, the GEMM moves little (the stored K_B blocks in, row partials out) and is
+        # bound by the tensor work it ISSUES: every stored 64-slot block is multiplied whole, padding included.
+        tr = NCU_TRAFFIC.get((args.workload, world, "nostore"))
+        roof = dict(kernel="k_gemm_tcgen05 (Nystroem extrapolation over the stored K_B blocks, filter fused, Phi not stored)",
+                    bound="tensor", achieved=gemm_tf_exec, peak=peaks["tf_sustained"], unit="TFLOP/s",
+                    frac=gemm_tf_exec / peaks["tf_sustained"], traffic=tr[0] if tr else None, traffic_source=tr[1] if tr else None,
+                    peak_source=peaks["source"] + " bf16 sustained", ms=med["k_gemm"], flop=f_ext_exec,
+                    flop_dense_equivalent=f_ext, algorithmic_bytes=gemm_bytes,
+                    note="flop = MMA work issued over the stored K_B blocks (2 * stored slots * 512 pixels * m_pad); the blocks the "
+                         "spatial cutoff drops hold only values fp16 flushes to zero, so the dense-equivalent work is "
+                         "flop_dense_equivalent; HBM traffic of this kernel is %.2f GB (%.0f GB/s)" % (gemm_bytes / 1e9, gemm_gbs))
+        if phistore:
+            tr = NCU_TRAFFIC.get((args.workload, world, "stored"))
+            gbs_st = gemm_bytes_stored / (phistore["k_gemm"] * 1e-3) / 1e9
+            roof_stored = dict(kernel="k_gemm_tcgen05 with option keep_phi=1 (Phi written to HBM as well)", bound="hbm", achieved=gbs_st,
+                               peak=peaks["hbm"], unit="GB/s", frac=gbs_st / peaks["hbm"], traffic=tr[0] if tr else None,
+                               traffic_source=tr[1] if tr else None, peak_source=peaks["source"] + " copy bandwidth",
+                               ms=phistore["k_gemm"], bytes=gemm_bytes_stored,
+                               note="91 %% of these bytes are WRITES (Phi); a pure 17 GB write (torch fill) runs at 3.94 TB/s on this part, "
+                                    "the kernel writes at %.2f TB/s" % (band_px * m_pad * 2.0 / (phistore["k_gemm"] * 1e-3) / 1e12))
     else:
         tr = NCU_TRAFFIC.get((args.workload, world, "dense"))
         roof = dict(kernel="k_gemm_tcgen05 (Nystroem extrapolation)", bound="tensor", achieved=gemm_tf, peak=peaks["tf_sustained"],
@@ -380,8 +401,11 @@ def main():
                            plan="the K_B block layout depends on the image size and the sample positions only; it is planned on the "
                                 "host at the first call (first_call_ms, with the device allocations) and reused while they do not "
                                 "change, like an FFT plan; a new sample draw on the same geometry costs ~1 ms of host time",
-                           cache="working set (K_B + Phi = %.1f GB per GPU) far larger than the 126 MB L2; no flush needed"
-                                 % (2 * band_px * (m_pad + (p + 63) // 64 * 64) / 1e9),
+                           cache=("every step writes and then reads %.2f GB of K_B blocks and row partials per GPU through the 126 MB L2, "
+                                  "which evicts the input image between steps; no flush needed" % ((2 * kb_bytes + 2 * zpart_bytes) / 1e9)
+                                  if 2 * kb_bytes + 2 * zpart_bytes > 4 * 126e6 else
+                                  "the working set of a step (%.0f MB per GPU) fits the 126 MB L2 and is NOT flushed between steps: "
+                                  "small-image numbers are L2-warm" % ((2 * kb_bytes + 2 * zpart_bytes) / 1e6)),
                            parallelism=f"pixel-row bands x{world}"),
                e2e=dict(value=e2e_val, unit="Mpixel/s",
                         h2d_bytes_per_step=(n * channels if world == 1 else (band_px + p) * channels),   # N > 1: a rank uploads its band + the sample pixels
@@ -392,6 +416,7 @@ def main():
                gpu_launches=int(launches), first_call_ms=first_call_ms, phi_stored=phi_fits,
                clocks=clk,
                roofline=roof,
+               roofline_phi_stored=roof_stored,
                roofline_gemm_dense=roof_dense,
                roofline_filter=dict(kernel="k_filter_project + k_filter_apply (stand-alone GEMV pair, option projection=recompute)",
                                     bound="hbm", achieved=filt_gbs, peak=peaks["hbm"], unit="GB/s", frac=filt_gbs / peaks["hbm"],
@@ -405,16 +430,17 @@ def main():
                stage_calls_ms=dict(ms_per_step=staged_abi_ms, mpixel_per_s=n / (staged_abi_ms * 1e-3) / 1e6,
                                    note="the reference's call sequence made stage by stage through the ABI (as the C host does): "
                                         "Nystroem returns a deferred Phi and the filter call runs both as one pass"),
-               no_phi_store_ms=dict(nophi, mpixel_per_s=n / (nophi["total"] * 1e-3) / 1e6,
-                                    note="option keep_phi=0: Phi is consumed by the fused filter in the GEMM epilogue and never written to "
-                                         "HBM (same z bit for bit); NOT the headline, which keeps the reference's data flow and stores Phi"),
+               phi_stored_ms=(dict(phistore, mpixel_per_s=n / (phistore["total"] * 1e-3) / 1e6,
+                                   note="option keep_phi=1: the fused pass also writes Phi to HBM, as the reference's Nystroem stage does "
+                                        "(same z bit for bit); the default consumes the Phi tiles in the GEMM epilogue and never stores them, "
+                                        "since nothing on the path reads them back") if phistore else None),
                affinity_plus_extrapolation_tflops=aff_ext_tf,
                kb_cutoff=dict(stored_blocks=stored_blocks, dense_blocks=int(dense_blocks), kept=stored_blocks / max(1, dense_blocks),
                               note="64-sample blocks of K_B whose entries fp16 flushes to zero (sample further than h_loc*sqrt(25 ln 2) "
                                    "from the 512-pixel tile in rows or columns; samples ordered by column strip, then row) are "
                                    "neither computed, stored nor multiplied"),
                gemm=dict(ms=med["k_gemm"], flop_dense_equivalent=f_ext, flop_executed=f_ext_exec, tflops_dense_equivalent=gemm_tf,
-                         tflops_executed=gemm_tf_exec, bytes=gemm_bytes, gbs=gemm_gbs),
+                         tflops_executed=gemm_tf_exec, bytes=gemm_bytes, gbs=gemm_gbs, phi_stored=False),
                stage_ms={k: round(v, 4) for k, v in stage.items()},
                kernel_ms_median={k: round(v, 4) for k, v in med.items()})
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

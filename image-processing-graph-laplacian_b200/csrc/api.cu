@@ -943,8 +943,8 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
         const bool fused = ctx->fuse_filter && !prm->gram_schmidt && ctx->projection_mode == 0 && ctx->gemm_impl == 0;
         if (fused) {
             ctx->ev_valid[GL_T_FILTER] = false;
-            // option keep_phi=0: Phi is only a temporary of this one-call path, so its tiles can be consumed in the epilogue
-            // and never written to HBM at all
+            // Phi is only a temporary of this one-call path (no argument returns it): its tiles are consumed in the epilogue
+            // and never written to HBM, unless option keep_phi=1 asks for the reference's data flow
             // A Phi that does not fit (config 5 on one GPU: 67 M pixels x 2048 columns = 275 GB) is not stored either:
             // the fused pass needs K_B and the row partials only.  phi_limit_mb forces that path (tests).
             bool keep = ctx->keep_phi;

@@ -142,7 +142,8 @@ struct gl_ctx {
     int projection_mode = 0;  // 0 = c from the affinity sums (default), 1 = always recompute c with a pass over Phi
     int fuse_filter = 1;      // gl_run: apply the filter inside the extrapolation GEMM's epilogue when possible
     int lazy_phi = 1;         // gl_nystroem returns a deferred Phi; gl_filter then runs extrapolation + filter as one pass
-    int keep_phi = 1;         // gl_run with the fused filter: 1 = still write Phi to HBM (the reference's data flow), 0 = never store it
+    int keep_phi = 0;         // fused filter (gl_run, gl_filter on a deferred Phi): 0 = Phi tiles are consumed in the GEMM epilogue and never
+                              // written to HBM (nobody reads them; a later consumer recomputes), 1 = write Phi as well (the reference's data flow)
 
     // samples
     unsigned p = 0;

@@ -862,9 +862,10 @@ int gl_phi_materialise(gl_ctx* ctx, gl_mat* phi, const gl_fused_filter* ff)
 {
     if (!phi->def_LB) return GL_OK;
     gl_mat *LB = phi->def_LB, *U = phi->def_U, *mi = phi->def_muinv;
-    // with the filter riding along, a Phi that does not fit (or exceeds option phi_limit_mb) is consumed in the epilogue and
-    // stays deferred; whoever needs the matrix itself later gets the allocation error then
-    bool keep = true;
+    // with the filter riding along, Phi is consumed in the epilogue and stays deferred: nobody has asked for the matrix itself
+    // yet, and whoever does later (download, column dumps, orthonormalisation) makes this call again without a filter.
+    // Option keep_phi=1 stores it in the same pass -- unless it does not fit or exceeds option phi_limit_mb.
+    bool keep = ff ? ctx->keep_phi != 0 : true;
     const size_t bytes = (size_t)phi->local_rows * (size_t)phi->m_pad * 2;
     if (ff && ctx->phi_limit_mb > 0 && bytes > (size_t)ctx->phi_limit_mb << 20) keep = false;
     if (ff && ctx->phi_nomem_bytes && bytes >= ctx->phi_nomem_bytes) keep = false;

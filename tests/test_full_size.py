@@ -87,11 +87,11 @@ def test_c4_properties(ctx, base):
 def test_c4_variants_agree(ctx, base):
     ref = base["z"].astype(np.float64)
     img = ctx.get_image().astype(np.float64)
-    ctx.set_option("keep_phi", 0)           # Phi consumed in the GEMM epilogue and never stored: identical z
+    ctx.set_option("keep_phi", 1)           # Phi written to HBM as well (default: consumed in the GEMM epilogue only): identical z
     try:
         r = _run(ctx)
     finally:
-        ctx.set_option("keep_phi", 1)
+        ctx.set_option("keep_phi", 0)
     assert np.array_equal(r["z"], base["z"])
     for key, val in (("fuse_filter", 0), ("kb_cutoff", 0)):
         ctx.set_option(key, val)

@@ -239,10 +239,10 @@ def test_gram_schmidt_wide_phi(ctx, gram):
     assert err_z <= TOL_Z and err_dz <= TOL_DZ
 
 
-def test_phi_that_does_not_fit_is_not_stored(ctx):
-    """gl_run falls back to consuming Phi in the GEMM epilogue when it cannot be stored (config 5 on one GPU would need
-    275 GB); option phi_limit_mb forces that path at a small size.  Same z bit for bit, and the peak device memory
-    stays below the size of Phi."""
+def test_phi_is_stored_only_on_request_and_when_it_fits(ctx):
+    """gl_run consumes Phi in the GEMM epilogue without storing it (peak device memory stays below the size of Phi);
+    option keep_phi=1 writes it as well, same z bit for bit -- unless it cannot be stored (config 5 on one GPU would
+    need 275 GB; option phi_limit_mb forces that case at a small size)."""
     W, H, p = 1024, 768, 600
     img = o.synthetic_image(W, H, 1, seed=21)
     ctx.set_image(img)
@@ -250,20 +250,24 @@ def test_phi_that_does_not_fit_is_not_stored(ctx):
     z_a = np.zeros((H, W), np.float32)
     ctx.run_resident(prm, z_out=z_a)
     phi_bytes = W * H * 768 * 2                   # m = 599 -> 768 columns of fp16
-    ctx.set_option("phi_limit_mb", 64)
+    z_b = np.zeros((H, W), np.float32)
+    ctx.memory_stats(reset_peak=True)
+    r = ctx.run_resident(prm, z_out=z_b, want_eigvals=True)
+    assert r["m"] == p - 1 and np.array_equal(z_a, z_b)
+    assert ctx.memory_stats()["peak"] < phi_bytes    # the default does not store Phi
+    ctx.set_option("keep_phi", 1)
     try:
         ctx.memory_stats(reset_peak=True)
-        z_b = np.zeros((H, W), np.float32)
-        r = ctx.run_resident(prm, z_out=z_b, want_eigvals=True)
-        peak = ctx.memory_stats()["peak"]
+        ctx.run_resident(prm, z_out=z_b)
+        assert ctx.memory_stats()["peak"] > phi_bytes    # keep_phi=1 does
+        assert np.array_equal(z_a, z_b)
+        ctx.set_option("phi_limit_mb", 64)               # ... unless it exceeds the limit
+        ctx.memory_stats(reset_peak=True)
+        ctx.run_resident(prm, z_out=z_b)
+        assert ctx.memory_stats()["peak"] < phi_bytes and np.array_equal(z_a, z_b)
     finally:
+        ctx.set_option("keep_phi", 0)
         ctx.set_option("phi_limit_mb", 0)
-    assert r["m"] == p - 1
-    assert np.array_equal(z_a, z_b)
-    assert peak < phi_bytes, (peak, phi_bytes)
-    ctx.memory_stats(reset_peak=True)
-    ctx.run_resident(prm, z_out=z_b)
-    assert ctx.memory_stats()["peak"] > phi_bytes    # the default path does store it
 
 
 def test_column_strip_download(ctx, golden):
