@@ -152,12 +152,15 @@ GL_API int gl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A, gl_
 /* m smallest eigenpairs of symmetric positive definite L_A, ascending, 1 <= m <= p (m < 0 or m > p: p - 1).
  * eigvecs and/or eigvals_inv may be NULL. */
 GL_API int gl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv);
-/* Phi (n x m): sample rows = phi_A, other rows = L_B^T . phi_A . diag(eigvals_inv), already in raster order. */
+/* Phi (n x m): sample rows = phi_A, other rows = L_B^T . phi_A . diag(eigvals_inv), already in raster order.
+ * The handle is DEFERRED (option lazy_phi=0: computed at once): it retains its three inputs and the matrix is computed by
+ * its first consumer -- gl_filter runs extrapolation and filter as one pass and stores nothing (option keep_phi=1: stores
+ * Phi in that pass), gl_mat_download / gl_mat_download_cols / gl_orthonormalise run the plain GEMM and keep the matrix. */
 GL_API int gl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi);
 /* gl_nystroem and gl_filter in ONE pass over Phi: the filter weights gain * f o (Phi^T y) are formed first (Phi^T y
- * from the affinity stage's sums), the extrapolation GEMM writes Phi and accumulates each row's product with the weights
- * in its epilogue, so Phi is never read back.  Needs L_B of the CURRENT image; same outputs as the two calls.  `phi` may be
- * NULL: Phi is then not written to memory at all (its tiles only ever exist in tensor memory). */
+ * from the affinity stage's sums) and the extrapolation GEMM accumulates each row's product with the weights in its
+ * epilogue, so Phi is never read back.  Needs L_B of the CURRENT image; same outputs as the two calls.  `phi` != NULL:
+ * Phi is written as well and returned; NULL: it is not written to memory at all (its tiles only ever exist in tensor memory). */
 GL_API int gl_nystroem_filter(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat* f_eigvals, double gain,
                               int clip_low, gl_mat** phi, float* z_f32, uint8_t* z_u8);
 GL_API int gl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out /* m, may be NULL */);
@@ -176,7 +179,9 @@ GL_API int gl_full_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, g
 GL_API int gl_full_laplacian(gl_ctx* ctx, gl_mat* K, gl_mat** L);
 GL_API int gl_full_result(gl_ctx* ctx, gl_mat* L, float* z_f32, uint8_t* z_u8);
 
-/* ---- whole path in one call (what hpc/image_processing.c:183-277 sequences) ------------------- */
+/* ---- whole path in one call (what hpc/image_processing.c:183-277 sequences) -------------------
+ * Phi is a temporary of this call: without -gram_schmidt it is consumed tile by tile by the fused filter and not stored
+ * (option keep_phi=1 stores it; z is the same bit for bit). */
 /* (world > 1: every rank passes the WHOLE host image; a rank copies only its band of rows and the sampled pixels to its GPU.) */
 GL_API int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, const gl_params* prm,
                   float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out, double* eigvals_out /* m, may be NULL */);
