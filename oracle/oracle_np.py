@@ -180,7 +180,8 @@ def synthetic_image(width: int, height: int, channels: int = 1, seed: int = 1234
 # a-2  Affinity
 # ----------------------------------------------------------------------------
 
-BILATERAL, PHOTOMETRIC, SPATIAL = "bilateral", "photometric", "spatial"
+BILATERAL, PHOTOMETRIC, SPATIAL, NLM = "bilateral", "photometric", "spatial", "nlm"
+NLM_KSZ, NLM_SIGMA = 7, 1.2     # python/affinity_methods/NLM.py:13,19 (patch size, Gaussian weight of the patch elements)
 
 
 def _as_hwc(img: np.ndarray) -> np.ndarray:
@@ -196,6 +197,8 @@ def affinity_rows(img, sample_indices, cols, kind=BILATERAL, h_loc=40.0, h_val=3
     spatial}.py.  The reference multiplies two exponentials (affinity.c:99,107,
     110); colour (no counterpart in the reference) sums the
     squared channel differences in the photometric term."""
+    if kind == NLM:
+        return nlm_affinity_rows(img, sample_indices, cols, h_val)
     img = _as_hwc(img).astype(np.float64)
     H, W, C = img.shape
     flat = img.reshape(H * W, C)
@@ -213,6 +216,47 @@ def affinity_rows(img, sample_indices, cols, kind=BILATERAL, h_loc=40.0, h_val=3
             dv2 += (flat[s, ch][:, None] - flat[q, ch][None, :]) ** 2
         K *= np.exp(-dv2 / (h_val * h_val))
     return K
+
+
+def nlm_patch_weights() -> np.ndarray:
+    """matlab_style_gauss2D((7,7), 1.2) normalised to sum 1 (python/utils.py:19-32, NLM.py:19-21), as [7][7]."""
+    m = (NLM_KSZ - 1) / 2.0
+    y, x = np.ogrid[-m:m + 1, -m:m + 1]
+    h = np.exp(-(x * x + y * y) / (2.0 * NLM_SIGMA * NLM_SIGMA))
+    h[h < np.finfo(h.dtype).eps * h.max()] = 0
+    h /= h.sum()
+    return h / h.sum()          # NLM.py:21 normalises once more
+
+
+def nlm_affinity_rows(img, sample_indices, cols, h=3.0):
+    """Non-local-means patch affinity K(samples, cols), fp64 (python/affinity_methods/NLM.py:9-37):
+    K = exp(-sum_k (G_k (P_s[k] - P_q[k]))^2 / h^2) over the 7x7 patches P around the two pixels of the symmetrically
+    padded image (np.pad 'symmetric', NLM.py:18), G the normalised Gaussian patch weights, h = 3 (NLM.py:12).
+    Rows AND columns are raster indices here; the reference's columns come out in column-major pixel order
+    (im2col of the transposed image, NLM.py:22) although its callers read them as raster indices -- see
+    tests/golden/make_golden_nlm.py and tests/test_oracle.py for the map that pins this function to the reference."""
+    img = np.asarray(img)
+    assert img.ndim == 2 or img.shape[2] == 1, "NLM affinity is defined on one channel (the reference filters luminance)"
+    y = img.reshape(img.shape[0], img.shape[1]).astype(np.float64)
+    H, W = y.shape
+    rad = (NLM_KSZ - 1) // 2
+    pad = np.pad(y, (rad, rad), "symmetric")
+    G = nlm_patch_weights()
+    s = np.asarray(sample_indices, dtype=np.int64)
+    q = np.asarray(cols, dtype=np.int64)
+
+    def patches(idx):
+        r, c = idx // W, idx % W
+        out = np.empty((len(idx), NLM_KSZ, NLM_KSZ))
+        for a in range(NLM_KSZ):
+            for b in range(NLM_KSZ):
+                out[:, a, b] = pad[r + a, c + b] * G[a, b]
+        return out.reshape(len(idx), -1)
+    Ps, Pq = patches(s), patches(q)
+    d2 = np.empty((len(s), len(q)))
+    for i in range(len(s)):
+        d2[i] = ((Pq - Ps[i][None, :]) ** 2).sum(axis=1)
+    return np.exp(-d2 / (h * h))
 
 
 def non_sample_indices(n: int, sample_indices) -> np.ndarray:

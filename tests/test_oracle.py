@@ -1,5 +1,7 @@
 """CPU tests: the oracle (numpy + C) against the golden fixtures that were
 produced by the reference's own Python modules (tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -167,3 +169,25 @@ def test_oracle_reproduces_the_reference_python_pipeline(golden, tag):
         err = np.linalg.norm(r["z"] - g["z"]) / np.linalg.norm(g["z"])
         err_d = np.linalg.norm((r["z"] - img) - (g["z"] - img)) / np.linalg.norm(g["z"] - img)
         assert err < 1e-9 and err_d < 1e-8, (tag, streamed, err, err_d)
+
+
+@pytest.mark.parametrize("name", ["sq24", "rect"])
+def test_nlm_oracle_matches_the_reference_module(name):
+    """python/affinity_methods/NLM.py run by tests/golden/make_golden_nlm.py.  The reference's rows are samples in raster
+    order, its columns pixels in COLUMN-major order (im2col of the transposed image, NLM.py:22); the oracle uses raster
+    order for both.  Through that index map the two agree to rounding; read as raster columns (what the reference's
+    callers do, python/image_processing.py:60-64) they do not, not even on a square image."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"pyref_nlm_{name}.npz"))
+    img, s, K = g["image"], g["sample_indices"], g["K_AB"]
+    M, N = img.shape
+    mine = o.nlm_affinity_rows(img, s, np.arange(M * N), 3.0)
+    r, c = np.divmod(np.arange(M * N), N)
+    assert np.max(np.abs(mine - K[:, c * M + r])) < 1e-13
+    assert np.max(np.abs(mine - K)) > 0.1
+    # properties of the intended matrix: symmetric sample block with a unit diagonal, values in (0, 1]
+    K_A = mine[:, s]
+    assert np.allclose(K_A, K_A.T, atol=1e-15) and np.allclose(np.diag(K_A), 1.0)
+    assert mine.min() > 0 and mine.max() <= 1.0
+    # and the whole oracle pipeline runs on it
+    out = o.run_pipeline(img, s, kind=o.NLM, h_val=3.0)
+    assert np.all(np.diff(out["mu"]) >= 0) and out["mu"][0] > 0 and np.isfinite(out["z"]).all()
