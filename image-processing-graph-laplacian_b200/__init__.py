@@ -21,8 +21,9 @@ LIB_PATH = os.path.join(_HERE, "libglcuda.so")
 # gl_status
 OK, ERR_CUDA, ERR_ARG, ERR_NOMEM, ERR_NCCL, ERR_UNSUPPORTED, ERR_NOTCONVERGED = range(7)
 # gl_affinity_kind -- names follow python/affinity_methods/__init__.py:6
-SPATIAL, PHOTOMETRIC, BILATERAL = "spatial", "photometric", "bilateral"
-AFFINITY_KINDS = {BILATERAL: 0, PHOTOMETRIC: 1, SPATIAL: 2}
+SPATIAL, PHOTOMETRIC, BILATERAL, NLM = "spatial", "photometric", "bilateral", "NLM"     # python/affinity_methods/__init__.py:6
+AFFINITY_KINDS = {BILATERAL: 0, PHOTOMETRIC: 1, SPATIAL: 2, NLM: 3, "nlm": 3}
+NLM_H = 3.0    # python/affinity_methods/NLM.py:12
 # sampling -- names follow python/sampling/__init__.py:4
 RANDOM, SPATIALLY_UNIFORM = "random", "spatially_uniform"
 # gl_mat_kind
@@ -140,6 +141,8 @@ def default_params(**kw) -> Params:
     for k, v in kw.items():
         if k == "affinity":
             p.affinity_kind = AFFINITY_KINDS[v]
+            if p.affinity_kind == AFFINITY_KINDS[NLM] and "h_val" not in kw:
+                p.h_val = NLM_H            # the patch kernel's h (NLM.py:12); h_loc is unused
         elif k == "sampling":
             p.sampling_random = 1 if v == RANDOM else 0
         else:
@@ -347,7 +350,10 @@ class Context:
         return out
 
     # ---- stages (names follow the reference's hpc/ entry points) -----------------------------
-    def affinity(self, kind=BILATERAL, h_loc=40.0, h_val=30.0):
+    def affinity(self, kind=BILATERAL, h_loc=40.0, h_val=None):
+        """h_val: the photometric bandwidth (30, hpc/affinity.c:117) or, for NLM, the patch kernel's h (3, NLM.py:12)"""
+        if h_val is None:
+            h_val = NLM_H if AFFINITY_KINDS[kind] == AFFINITY_KINDS[NLM] else 30.0
         a, b = C.c_void_p(), C.c_void_p()
         _check(lib().gl_affinity(self.h, AFFINITY_KINDS[kind], h_loc, h_val, C.byref(a), C.byref(b)))
         return Mat(self, a), Mat(self, b)
@@ -466,7 +472,7 @@ class Context:
 def image_processing(y, cr=None, cb=None, ctx: Context | None = None, **kwargs):
     """Filter the luma plane `y` (u8 [H,W]) like the reference's image_processing(y, cr, cb, **kwargs):
     kwargs['sampling'] in {'spatially_uniform','random'}, kwargs['affinity'] in {'bilateral','photometric',
-    'spatial'}; 1 % of the pixels are sampled unless kwargs['sample_size'] is given.  Cr/Cb pass through
+    'spatial','NLM'}; 1 % of the pixels are sampled unless kwargs['sample_size'] is given.  Cr/Cb pass through
     untouched (python/image_processing.py:411-424).  Returns (z, cr, cb) with z float32 [H,W].
 
     The filter is the C code's z = y + 3 Phi Lambda Phi^T y (hpc/display.c:64-73); pass gain=-1, power=...
@@ -516,4 +522,4 @@ def image_processing_rgb(rgb, ctx: Context | None = None, **kwargs):
 
 
 sampling_methods = {RANDOM: RANDOM, SPATIALLY_UNIFORM: SPATIALLY_UNIFORM}
-affinity_methods = {SPATIAL: SPATIAL, PHOTOMETRIC: PHOTOMETRIC, BILATERAL: BILATERAL}
+affinity_methods = {SPATIAL: SPATIAL, NLM: NLM, BILATERAL: BILATERAL, PHOTOMETRIC: PHOTOMETRIC}

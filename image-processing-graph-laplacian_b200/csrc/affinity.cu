@@ -397,7 +397,7 @@ static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
         GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         ctx->h_samples_valid = true;
     }
-    const bool cut = ctx->kb_cutoff && kind != GL_PHOTOMETRIC;
+    const bool cut = ctx->kb_cutoff && kind != GL_PHOTOMETRIC && kind != GL_NLM;   // no spatial term, no cutoff
     const int64_t R = kb_reach(h_loc);
     const int kbs = ctx->kb_block == 32 ? 32 : 64;
     const int64_t key[6] = {W, ctx->q0, ctx->q1, p, R, (cut ? 1 : 0) + 2 * ctx->kb_strips + 1000 * kbs};
@@ -464,13 +464,44 @@ static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float*
     return launch_affinity_b<KIND, C, 64>(ctx, h_loc, h_val, sf, tab, starts, KB, partial, grid);
 }
 
+// kay[ch][i] = (K_A y_S)[i][ch] in fp64: the sample pixels' share of T = [K_A K_B] y, which the filter's projection takes out
+// again (nystroem_gemm.cu: the sample rows of Phi are Phi_A, not the extrapolation).  One block per sample row.
+__global__ void k_ka_times_y(const double* __restrict__ KA, const uint8_t* __restrict__ img, const uint32_t* __restrict__ samples, int p,
+                             int p_pad, int C, double* __restrict__ kay)
+{
+    const int i = blockIdx.x;
+    __shared__ double red[3][32];
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int j = threadIdx.x; j < p; j += blockDim.x) {
+        const double k = KA[(size_t)i * p + j];
+        const size_t b = samples[j];
+        for (int ch = 0; ch < C; ++ch) acc[ch] += k * (double)img[b * C + ch];
+    }
+    for (int ch = 0; ch < C; ++ch) {
+        double v = warp_sum(acc[ch]);
+        if ((threadIdx.x & 31) == 0) red[ch][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+        kay[(size_t)threadIdx.x * p_pad + i] = v;
+    }
+}
+
+// affinity_nlm.cu
+size_t gl_nlm_smem_bytes(int p_int);
+int gl_nlm_affinity_launch(gl_ctx* ctx, double h, int p_int, double* KA, const int4* tab, const int* starts, const uint32_t* perm, __half* KB,
+                           float* partial, int grid);
+
 int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A_out, gl_mat** K_B_out)
 {
     const int p = (int)ctx->p, p_pad = ctx->p_pad, C = ctx->channels;
     const int p_int = p_pad + 64;   // internal sample slots (a block may start at any multiple of 8 below p)
     const int64_t n_band = ctx->q1 - ctx->q0;
     {
-        const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_int + 2 * (1 + C) * 8 * 64 + (size_t)(2 + C) * AFF_TP);
+        const size_t smem = kind == GL_NLM ? gl_nlm_smem_bytes(p_int)
+                                           : sizeof(float) * ((size_t)(1 + C) * p_int + 2 * (1 + C) * 8 * 64 + (size_t)(2 + C) * AFF_TP);
         if (smem > 227 * 1024) {
             gl_set_error("affinity: p = %d samples need %zu bytes of shared memory per CTA (limit 227 KB)", p, smem);
             return GL_ERR_UNSUPPORTED;
@@ -480,7 +511,7 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
     gl_mat* KA = gl_mat_new(ctx, GL_MAT_KA);
     gl_mat* KB = gl_mat_new(ctx, GL_MAT_KB);
     gl_buf *sf = nullptr, *partial = nullptr;
-    const int grid = ctx->sm_count * AFF_CTAS_PER_SM(C);
+    const int grid = ctx->sm_count * (kind == GL_NLM ? 1 : AFF_CTAS_PER_SM(C));
     int rc = GL_OK;
     do {
         KA->rows = KA->cols = KA->local_rows = p;
@@ -505,14 +536,16 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         KB->total_blocks = ctx->tile_total_blocks;
         KB->kbs = ctx->tile_kbs;
         if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)KB->total_blocks * AFF_TP * KB->kbs, &KB->buf)) != GL_OK) break;
-        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)(1 + C) * p_pad, &KB->aux)) != GL_OK) break;  // [D | T[ch]]
+        if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)(1 + 2 * C) * p_pad, &KB->aux)) != GL_OK) break;  // [D | T[ch] | (K_A y_S)[ch]]
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_int, &sf)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * (1 + C) * p_int, &partial)) != GL_OK) break;
 
-        k_sample_features<<<(unsigned)ceil_div(p_int, 256), 256, 0, ctx->stream>>>(
-            (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, (const uint32_t*)KB->perm->ptr, p_int, ctx->width, C,
-            (float*)sf->ptr);
-        ctx->launches++;
+        if (kind != GL_NLM) {
+            k_sample_features<<<(unsigned)ceil_div(p_int, 256), 256, 0, ctx->stream>>>(
+                (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, (const uint32_t*)KB->perm->ptr, p_int, ctx->width, C,
+                (float*)sf->ptr);
+            ctx->launches++;
+        }
 
 #define AFF_CASE(K, CC)                                                                                              \
     if (kind == K && C == CC)                                                                                        \
@@ -520,10 +553,17 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
                                     (const int*)KB->starts->ptr, (__half*)KB->buf->ptr, (float*)partial->ptr, grid);
         AFF_CASE(GL_BILATERAL, 1) else AFF_CASE(GL_BILATERAL, 3) else AFF_CASE(GL_PHOTOMETRIC, 1)
         else AFF_CASE(GL_PHOTOMETRIC, 3) else AFF_CASE(GL_SPATIAL, 1) else AFF_CASE(GL_SPATIAL, 3)
+        else if (kind == GL_NLM)
+            rc = gl_nlm_affinity_launch(ctx, h_val, p_int, (double*)KA->buf->ptr, (const int4*)KB->tiles->ptr, (const int*)KB->starts->ptr,
+                                        (const uint32_t*)KB->perm->ptr, (__half*)KB->buf->ptr, (float*)partial->ptr, grid);
+        else { gl_set_error("affinity: kind %d with %d channels is not supported", kind, C); rc = GL_ERR_UNSUPPORTED; }
 #undef AFF_CASE
         if (rc != GL_OK) break;
 
-        GL_CUDA_BREAK(rc, cudaMemsetAsync(KB->aux->ptr, 0, sizeof(double) * (size_t)(1 + C) * p_pad, ctx->stream));
+        GL_CUDA_BREAK(rc, cudaMemsetAsync(KB->aux->ptr, 0, sizeof(double) * (size_t)(1 + 2 * C) * p_pad, ctx->stream));
+        k_ka_times_y<<<p, 128, 0, ctx->stream>>>((const double*)KA->buf->ptr, (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr,
+                                                 p, p_pad, C, (double*)KB->aux->ptr + (size_t)(1 + C) * p_pad);
+        GL_LAUNCH_CHECK(ctx);
         k_reduce_partials<<<(unsigned)ceil_div((1 + C) * p_int, 8), 256, 0, ctx->stream>>>(
             (const float*)partial->ptr, grid, p_int, 1 + C, (const uint32_t*)KB->perm->ptr, p_pad, (double*)KB->aux->ptr);
         GL_LAUNCH_CHECK(ctx);

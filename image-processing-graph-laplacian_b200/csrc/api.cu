@@ -468,7 +468,7 @@ int gl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A,
 {
     GL_REQUIRE(ctx && K_A && K_B, "gl_affinity: null");
     GL_REQUIRE(ctx->n > 0 && ctx->p >= 2, "gl_affinity: need an image and samples first");
-    GL_REQUIRE(kind >= GL_BILATERAL && kind <= GL_SPATIAL, "gl_affinity: bad kind %d", kind);
+    GL_REQUIRE(kind >= GL_BILATERAL && kind <= GL_NLM, "gl_affinity: bad kind %d", kind);
     GL_REQUIRE(h_loc > 0 && h_val > 0, "gl_affinity: bandwidths must be positive");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
     StageTimer t(ctx, GL_T_AFFINITY);
@@ -577,7 +577,7 @@ int gl_full_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
 {
     GL_REQUIRE(ctx && K, "gl_full_affinity: null");
     GL_REQUIRE(ctx->n > 0, "gl_full_affinity: set an image first");
-    GL_REQUIRE(kind >= GL_BILATERAL && kind <= GL_SPATIAL, "gl_full_affinity: bad kind %d", kind);
+    GL_REQUIRE(kind >= GL_BILATERAL && kind <= GL_SPATIAL, "gl_full_affinity: bad kind %d (the matrix-free full mode has the three kinds of hpc/affinity.c)", kind);
     GL_REQUIRE(h_loc > 0 && h_val > 0, "gl_full_affinity: bandwidths must be positive");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
     StageTimer t(ctx, GL_T_AFFINITY);

@@ -93,44 +93,8 @@ __global__ void k_phi_sample_rows(const float* __restrict__ U, int ld, int p, in
 // c = Phi^T y from the affinity stage's image-weighted sums, all in fp64 (one block per eigenvector j):
 //   c[j][ch] = sum_i U[i][j] y[s_i][ch]  +  sum_i W[i][j] (T[ch][i] - (K_A y_S)[i][ch]),   W = -alpha U / mu
 // T = [K_A K_B] y over ALL pixels (affinity.cu); removing K_A y_S leaves K_B y_B because the sample pixels' rows of
-// Phi are Phi_A, not the extrapolation (nystroem.c:25-34).  kay[ch][i] = (K_A y_S)[i][ch] comes from k_ka_times_y.
-__global__ void k_ka_times_y(const double* __restrict__ LA_unused, const uint8_t* __restrict__ img, const uint32_t* __restrict__ samples,
-                             int p, int p_pad, int width, int C, int kind, double inv_hl2, double inv_hv2, double* __restrict__ kay)
-{
-    // recomputes K_A rows in fp64 (K_A itself is usually destroyed by now, hpc/image_processing.c:210)
-    const int i = blockIdx.x;
-    __shared__ double red[3][32];
-    double acc[3] = {0.0, 0.0, 0.0};
-    const uint32_t a = samples[i];
-    for (int j = threadIdx.x; j < p; j += blockDim.x) {
-        const uint32_t b = samples[j];
-        double k = 1.0;
-        if (kind != GL_PHOTOMETRIC) {
-            const double dr = (double)(a / width) - (double)(b / width), dc = (double)(a % width) - (double)(b % width);
-            k *= exp(-(dr * dr + dc * dc) * inv_hl2);
-        }
-        if (kind != GL_SPATIAL) {
-            double d2 = 0.0;
-            for (int ch = 0; ch < C; ++ch) {
-                const double dv = (double)img[(size_t)a * C + ch] - (double)img[(size_t)b * C + ch];
-                d2 += dv * dv;
-            }
-            k *= exp(-d2 * inv_hv2);
-        }
-        for (int ch = 0; ch < C; ++ch) acc[ch] += k * (double)img[(size_t)b * C + ch];
-    }
-    for (int ch = 0; ch < C; ++ch) {
-        double v = warp_sum(acc[ch]);
-        if ((threadIdx.x & 31) == 0) red[ch][threadIdx.x >> 5] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < C) {
-        double v = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
-        kay[(size_t)threadIdx.x * p_pad + i] = v;
-    }
-}
-
+// Phi are Phi_A, not the extrapolation (nystroem.c:25-34).  kay[ch][i] = (K_A y_S)[i][ch] was stored behind D and T by the
+// affinity stage (affinity.cu: k_ka_times_y).
 __global__ void k_proj_from_sums(const float* __restrict__ U, int ld, int p, int p_pad, int m, const double* __restrict__ mu_inv,
                                  const double* __restrict__ neg_alpha, const double* __restrict__ DT /* [1+C][p_pad] */,
                                  const double* __restrict__ kay /* [C][p_pad] */, const uint8_t* __restrict__ img,
@@ -772,20 +736,13 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
         // projection c = Phi^T y from the affinity sums (valid while the image and the samples are unchanged)
         if (L_B->aux && L_B->channels == ctx->channels && L_B->image_epoch == ctx->image_epoch) {
             const int C = ctx->channels;
-            gl_buf* kay = nullptr;
-            if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)C * p_pad, &kay)) != GL_OK) break;
             if (phi->proj) { gl_buf_release(phi->proj); phi->proj = nullptr; }
-            if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m_pad * C, &phi->proj)) != GL_OK) { gl_buf_release(kay); break; }
-            k_ka_times_y<<<p, 128, 0, ctx->stream>>>(nullptr, (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p,
-                                                     p_pad, ctx->width, C, L_B->aff_kind, 1.0 / (L_B->aff_h_loc * L_B->aff_h_loc),
-                                                     1.0 / (L_B->aff_h_val * L_B->aff_h_val), (double*)kay->ptr);
-            ctx->launches++;
+            if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)m_pad * C, &phi->proj)) != GL_OK) break;
+            const double* kay = (const double*)L_B->aux->ptr + (size_t)(1 + C) * p_pad;   // (K_A y_S), behind D and T
             k_proj_from_sums<<<m_pad, 128, 0, ctx->stream>>>(U, (int)phi_A->ld, p, p_pad, m, mu_inv, neg_alpha,
-                                                            (const double*)L_B->aux->ptr, (const double*)kay->ptr,
-                                                            (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, C,
-                                                            (double*)phi->proj->ptr);
+                                                            (const double*)L_B->aux->ptr, kay, (const uint8_t*)ctx->img->ptr,
+                                                            (const uint32_t*)ctx->samples->ptr, C, (double*)phi->proj->ptr);
             ctx->launches++;
-            gl_buf_release(kay);
             phi->channels = C;
             phi->image_epoch = ctx->image_epoch;
         }

@@ -75,6 +75,10 @@ void OptionsInit(int argc, char** argv)
     if (OptionsGetString("-affinity", buf, sizeof buf)) {
         if (!strcmp(buf, "photometric")) g_opt.affinity_kind = GL_PHOTOMETRIC;
         else if (!strcmp(buf, "spatial")) g_opt.affinity_kind = GL_SPATIAL;
+        else if (!strcmp(buf, "nlm") || !strcmp(buf, "NLM")) {
+            g_opt.affinity_kind = GL_NLM;    /* python/affinity_methods/NLM.py */
+            g_opt.h_val = 3.0;               /* NLM.py:12 (overridden by -h_val) */
+        }
         else if (strcmp(buf, "bilateral")) fprintf(stderr, "Unknown -affinity %s, using bilateral\n", buf);
     }
     if (OptionsGetString("-sampling", buf, sizeof buf)) g_opt.sampling_random = !strcmp(buf, "random");

@@ -55,7 +55,10 @@ enum gl_status {
 enum gl_affinity_kind { /* hpc/affinity.c:115-122 picks bilateral; the two others are commented there */
     GL_BILATERAL = 0,   /* exp(-|dpos|^2/h_loc^2) * exp(-|dval|^2/h_val^2) */
     GL_PHOTOMETRIC = 1, /* exp(-|dval|^2/h_val^2) */
-    GL_SPATIAL = 2      /* exp(-|dpos|^2/h_loc^2) */
+    GL_SPATIAL = 2,     /* exp(-|dpos|^2/h_loc^2) */
+    GL_NLM = 3          /* non-local means, python/affinity_methods/NLM.py: exp(-|G o (patch_a - patch_b)|^2 / h_val^2) over 7x7 patches
+                           of the symmetrically padded image, G = normalised Gaussian weights (sigma 1.2); grey only; the
+                           reference's h is 3 */
 };
 
 enum gl_mat_kind {

@@ -4,6 +4,8 @@ fixtures (reference python modules + oracle) and against the oracle on seeded sy
 Tolerances (BASELINE.json north_star): sampled indices bit-exact; leading eigenvalues rel <= 1e-4;
 filtered image rel L2 <= 1e-3.  The filtered image differs from the input by only ~0.2-1 %, so the
 tests additionally bound the relative error of the CHANGE z - y."""
+import os
+
 import numpy as np
 import pytest
 
@@ -237,6 +239,61 @@ def test_gram_schmidt_wide_phi(ctx, gram):
     print(f"gs wide ({gram}): orth={err_q:.2e} norms={err_n:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
     assert err_q < 1e-3 and err_n < 2e-3
     assert err_z <= TOL_Z and err_dz <= TOL_DZ
+
+
+@pytest.mark.parametrize("name", ["sq24", "rect"])
+def test_nlm_affinity_against_the_reference_module(ctx, name):
+    """The NLM patch affinity (python/affinity_methods/NLM.py) on the device against the reference module's own output
+    (tests/golden/pyref_nlm_*.npz, columns mapped from its column-major pixel order to raster order, see
+    tests/test_oracle.py) and against the oracle; then the whole path on it."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"pyref_nlm_{name}.npz"))
+    img, s, K = g["image"], g["sample_indices"], g["K_AB"]
+    M, N = img.shape
+    r, c = np.divmod(np.arange(M * N), N)
+    K_ref = K[:, c * M + r]                                   # [p][n] in raster columns
+    ctx.set_image(img)
+    ctx.set_samples(s)
+    K_A, K_B = ctx.affinity(gl.NLM)                           # h = 3 (NLM.py:12)
+    ka, kb, D = K_A.download(), K_B.download(), K_B.rowsums()
+    assert np.max(np.abs(ka - K_ref[:, s])) < 1e-6            # fp64 on fp32 patch weights
+    assert np.max(np.abs(kb.T - K_ref)) < 6e-4                # fp16 storage
+    assert np.max(np.abs(D - K_ref.sum(axis=1)) / K_ref.sum(axis=1)) < 1e-5
+    L_A, L_B = ctx.laplacian(K_A, K_B)
+    U, mu, mu_inv = ctx.eigensolve(L_A, -1)
+    z = ctx.filter(ctx.nystroem(L_B, U, mu_inv), mu).astype(np.float64)
+    ref = o.run_pipeline(img, s, kind=o.NLM, h_val=3.0)
+    err_mu = np.max(np.abs(mu.download() - ref["mu"]) / ref["mu"])
+    err_z, err_dz = _rel(z, ref["z"]), _rel(z - img, ref["z"] - img)
+    print(f"nlm {name}: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_mu <= TOL_MU and err_z <= TOL_Z and err_dz <= TOL_DZ
+    # one call, through the params
+    prm = gl.default_params(affinity=gl.NLM, sample_size=len(s))
+    z2 = np.zeros(img.shape, np.float32)
+    ctx.run_resident(prm, z_out=z2)
+    assert _rel(z2, z) < 1e-5
+
+
+def test_nlm_affinity_medium_image(ctx):
+    """NLM on an image with several tiles and sample blocks (ragged last tile, p not a multiple of 64) against the oracle."""
+    W, H, p = 173, 141, 150
+    img = (o.synthetic_image(W, H, 1, seed=8) // 8 + 100).astype(np.uint8)     # low contrast: the h = 3 kernel stays alive
+    s = oc.random_sampling(W, H, p, 2)
+    ctx.set_image(img)
+    ctx.set_samples(s)
+    K_A, K_B = ctx.affinity("nlm", h_val=6.0)
+    cols = np.arange(0, W * H, 7)
+    ref = o.nlm_affinity_rows(img, s, cols, 6.0)
+    kb = K_B.download()[cols]
+    assert np.max(np.abs(kb.T - ref)) < 6e-4
+    ref_D = sum(o.nlm_affinity_rows(img, s, np.arange(a, min(a + 4096, W * H)), 6.0).sum(axis=1) for a in range(0, W * H, 4096))
+    assert np.max(np.abs(K_B.rowsums() - ref_D) / ref_D) < 1e-5
+    assert np.max(np.abs(K_A.download() - o.nlm_affinity_rows(img, s, s, 6.0))) < 1e-6
+    with pytest.raises(gl.GLError):
+        ctx.full_affinity("nlm")                # the matrix-free full mode has the C program's three kinds only
+    ctx.set_image(np.repeat(img[:, :, None], 3, axis=2))
+    ctx.set_samples(s)
+    with pytest.raises(gl.GLError):
+        ctx.affinity("nlm")                     # one channel only
 
 
 def test_phi_is_stored_only_on_request_and_when_it_fits(ctx):
