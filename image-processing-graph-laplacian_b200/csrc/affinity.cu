@@ -117,6 +117,7 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
         }
         __syncthreads();
         const int4 tl = tab[tile];
+        const bool single_row = base / width == (min(base + AFF_TP, q1) - 1) / width;
         for (int ci = 0; ci < tl.y; ++ci) {
             const int sb = starts[tl.x + ci];          // multiple of 8: the float4 loads below stay aligned
             const int s0 = sb + (tx << 3);
@@ -134,24 +135,40 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
                 *(float4*)&sv[ch][4] = *(const float4*)&sf[(2 + ch) * p_pad + s0 + 4];
             }
             float acc[8], tacc[C][8];
+            // the row part of the exponent, a2 * dr^2: when the tile lies in one image row (the usual case on wide images) it is
+            // the same for all of the thread's pixels and is taken out of the pair loop; otherwise it is refreshed per pixel
+            float rterm[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 acc[k] = 0.f;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) tacc[ch][k] = 0.f;
+                rterm[k] = 0.f;
+                if (KIND != GL_PHOTOMETRIC) {
+                    const float dr = px[0] - sr[k];
+                    rterm[k] = dr * dr * a2;
+                }
             }
 #pragma unroll 2
             for (int i = 0; i < PPT; ++i) {
                 const int pi = ty + i * PXL;
                 const int64_t q = base + pi;
-                const float pr = px[pi], pc = px[AFF_TP + pi];
+                const float pc = px[AFF_TP + pi];
                 float pv[C];
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) pv[ch] = px[(2 + ch) * AFF_TP + pi];
+                if (KIND != GL_PHOTOMETRIC && !single_row) {
+                    const float pr = px[pi];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float dr = pr - sr[k];
+                        rterm[k] = dr * dr * a2;
+                    }
+                }
                 float kv[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    float x = 0.f;
+                    float x = rterm[k];
                     if (KIND != GL_SPATIAL) {
                         float d = pv[0] - sv[0][k];
                         float t = d * d;
@@ -160,12 +177,11 @@ k_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sf, int 
                             d = pv[ch] - sv[ch][k];
                             t = fmaf(d, d, t);
                         }
-                        x = t * b2;
+                        x = fmaf(t, b2, x);
                     }
                     if (KIND != GL_PHOTOMETRIC) {
-                        float dr = pr - sr[k], dc = pc - sc[k];
-                        float t = fmaf(dc, dc, dr * dr);
-                        x = fmaf(t, a2, x);
+                        const float dc = pc - sc[k];
+                        x = fmaf(dc * dc, a2, x);
                     }
                     kv[k] = fast_exp2(x);
                 }
