@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=index,name,memory.total --format=csv > gpurun_out/gpu.txt
 echo "== multi-GPU tests =="
 timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -q -rA --tb=short --timeout 600 > gpurun_out/tests_mgpu.log 2>&1
 grep -E 'passed|failed|FAILED|SKIPPED|world=|Error|error' gpurun_out/tests_mgpu.log | cut -c1-300 | tail -30
-for n in 2 4 8; do
+for n in ${NLIST:-2 4 8}; do
   if [ $n -le $N ]; then
     echo "== bench C4 N=$n =="
     if [ $n -eq 1 ]; then
