@@ -466,22 +466,16 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int c_end = split ? c_hi : (ch == 0 ? n_size : 0);
             for (int c0 = (split ? c_lo : 0); c0 < c_end; c0 += 64) {
                 uint8_t* slab = slab0 + buf * C_SLAB_BYTES;
-                // eight warps: both halves of the 64-column group in flight before the wait; sixteen warps (96 registers per
-                // thread): one half at a time, the other warps cover the TMEM latency
-                constexpr bool SEQ = EPI_WARPS > 8;
-                uint32_t v[SEQ ? 1 : 2][32];
+                // both halves of the 64-column group in flight before the wait
+                uint32_t v[2][32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v[0]);
-                if (!SEQ) tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v[SEQ ? 0 : 1]);
+                tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v[1]);
                 // the TMA store that last read this slab must be done with it
                 if (store_d && lane == 0) tma_store_wait_read<CBUFS - 1>();
                 tmem_ld_wait();
                 __syncwarp();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    if (SEQ && h == 1) {
-                        tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v[0]);
-                        tmem_ld_wait();
-                    }
                     uint32_t pk[16];
                     if (ST && addend != nullptr) {
                         // D = addend + scale * acc (orthonormalise.cu: Phi + Phi E); one 64-byte run of this thread's row
@@ -496,14 +490,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (int j = 0; j < 4; ++j) {
                                 const int i = 4 * i4 + j;
                                 const float2 ad = unpack_h2(aw[j]);
-                                pk[i] = pack_h2(fmaf(__uint_as_float(v[SEQ ? 0 : h][2 * i]), sc, ad.x), fmaf(__uint_as_float(v[SEQ ? 0 : h][2 * i + 1]), sc, ad.y));
+                                pk[i] = pack_h2(fmaf(__uint_as_float(v[h][2 * i]), sc, ad.x), fmaf(__uint_as_float(v[h][2 * i + 1]), sc, ad.y));
                             }
                         }
                     } else {
                         if (store_d) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
-                                pk[i] = pack_h2(__uint_as_float(v[SEQ ? 0 : h][2 * i]) * sc, __uint_as_float(v[SEQ ? 0 : h][2 * i + 1]) * sc);
+                                pk[i] = pack_h2(__uint_as_float(v[h][2 * i]) * sc, __uint_as_float(v[h][2 * i + 1]) * sc);
                         }
                         if (FC > 0) {
                             // 32 columns starting at nt * block_n + c0 + 32 h; weights (already times the output scale) read as
@@ -518,14 +512,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                     // one channel: accumulator and weight pairs are register pairs already, two columns per FFMA2
 #pragma unroll
                                     for (int i = 0; i < 8; i += 2)
-                                        ffma2(dot[0][i], dot[0][i + 1], __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i]),
-                                              __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i + 1]), wr[i], wr[i + 1]);
+                                        ffma2(dot[0][i], dot[0][i + 1], __uint_as_float(v[h][8 * g8 + i]),
+                                              __uint_as_float(v[h][8 * g8 + i + 1]), wr[i], wr[i + 1]);
                                 } else {
                                     // three channels: the weights of a column pair are not adjacent, pairing them costs more moves than
                                     // the FFMA2 saves (measured); four chains per channel
 #pragma unroll
                                     for (int i = 0; i < 8; ++i) {
-                                        const float val = __uint_as_float(v[SEQ ? 0 : h][8 * g8 + i]);
+                                        const float val = __uint_as_float(v[h][8 * g8 + i]);
 #pragma unroll
                                         for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
                                     }

@@ -6,7 +6,7 @@
 #include "petsc_compat.h"
 
 typedef struct GLHostOptions {
-    int affinity_kind;       /* -affinity bilateral|photometric|spatial */
+    int affinity_kind;       /* -affinity bilateral|photometric|spatial|nlm */
     double h_loc, h_val;     /* -h_loc, -h_val */
     int sampling_random;     /* -sampling uniform|random */
     unsigned seed;           /* -seed */

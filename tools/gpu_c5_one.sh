@@ -8,7 +8,7 @@ GLB200_VERBOSE=0 timeout 900 python bench.py --workload c5 --steps 3 --warmup 3 
 python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/bench_c5_n1.json').read().strip().splitlines()[-1])
-for k in ('value', 'ms_per_step', 'e2e', 'phi_stored', 'stage_ms', 'kb_cutoff', 'first_call_ms', 'no_phi_store_ms', 'stage_calls_ms'):
+for k in ('value', 'ms_per_step', 'e2e', 'phi_stored', 'stage_ms', 'kb_cutoff', 'first_call_ms', 'phi_stored_ms', 'stage_calls_ms'):
     print(k, '=', d.get(k))
 PY
 tail -5 gpurun_out/bench_c5_n1.err | cut -c1-400
