@@ -175,8 +175,14 @@ int GLHostInit(int argc, char** argv, int* rank, int* size)
 
 png_bytep* GLHostSharedImage(unsigned int width, unsigned int height)
 {
+    static unsigned int capacity = 0;    /* the row table grows with the tallest view asked for (images, column dumps) */
     if ((size_t)width * height > g_shared_bytes) return NULL;
-    if (!g_shared_rows) g_shared_rows = (png_bytep*)malloc(sizeof(png_bytep) * height);
+    if (height > capacity) {
+        png_bytep* rows = (png_bytep*)realloc(g_shared_rows, sizeof(png_bytep) * height);
+        if (!rows) return NULL;
+        g_shared_rows = rows;
+        capacity = height;
+    }
     for (unsigned int i = 0; i < height; ++i) g_shared_rows[i] = g_shared + (size_t)i * width;
     return g_shared_rows;
 }
