@@ -191,3 +191,37 @@ def test_nlm_oracle_matches_the_reference_module(name):
     # and the whole oracle pipeline runs on it
     out = o.run_pipeline(img, s, kind=o.NLM, h_val=3.0)
     assert np.all(np.diff(out["mu"]) >= 0) and out["mu"][0] > 0 and np.isfinite(out["z"]).all()
+
+
+def test_prototype_building_blocks_match_the_reference_functions():
+    """oracle/proto_np.py against the reference's own affinity / nystroem / permutation / orthogonalisation / sinkhorn
+    (python/image_processing.py:35-129, run by tests/golden/make_golden_proto.py).  Eigenvector signs are free, so the
+    comparisons go through sign-invariant quantities."""
+    from oracle import proto_np as pr
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pyref_proto.npz"))
+    img, s = g["image"], g["sample_indices"]
+    H, W = img.shape
+    n, p = H * W, len(s)
+    # affinity(): the bilateral plugin with its constants (h_spatial 40, h_photo 30), split into K_A | K_B
+    K_AB = o.affinity_rows(img, s, np.arange(n), "bilateral", 40.0, 30.0)
+    K_A, K_B = pr.split_affinity(K_AB, s)
+    assert np.max(np.abs(K_A - g["K_A"])) < 1e-13 and np.max(np.abs(K_B - g["K_B"])) < 1e-13
+    # nystroem(): same spectrum, same Phi diag(Pi) Phi^T
+    phi, Pi = pr.nystroem(K_A, K_B)
+    assert np.max(np.abs(Pi - g["Pi"]) / g["Pi"]) < 1e-10
+
+    def recon(F, w):
+        return (F * w) @ F.T
+    assert np.max(np.abs(recon(phi, Pi) - recon(g["phi"], g["Pi"]))) < 1e-8
+    # permutation(): row movement only -- apply it to the reference's own phi
+    assert np.array_equal(pr.permutation(g["phi"], s), g["phi_perm"])
+    # orthogonalisation(): orthonormal columns, capped eigenvalues, same projector-weighted matrix
+    V, Pi_V = pr.orthogonalisation(K_A, K_B)
+    assert np.max(np.abs(V.T @ V - np.eye(p))) < 1e-8
+    assert np.max(np.abs(Pi_V - g["Pi_V"])) < 1e-10
+    assert np.max(np.abs(np.abs(V) - np.abs(g["V"]))) < 1e-6 or np.max(np.abs(recon(V, Pi_V) - recon(g["V"], g["Pi_V"]))) < 1e-8
+    # sinkhorn(): sign-free by construction
+    W_A, W_B = pr.sinkhorn(g["phi"], g["Pi"])
+    assert np.max(np.abs(W_A - g["W_A"])) < 1e-9 and np.max(np.abs(W_B - g["W_B"])) < 1e-9
+    W_A2, _ = pr.sinkhorn(phi, Pi)                        # and from the oracle's own eigenvectors
+    assert np.max(np.abs(W_A2 - g["W_A"])) < 1e-6
