@@ -56,14 +56,18 @@ static Vec GatherMatCol(Mat x, const unsigned int col_num)
     int r0 = 0, r1 = 0;
     if (gl_get_band(GLHostContext(), &r0, &r1) != GL_OK) GLHostFatal("GatherMatCol");
     const size_t width = r1 > r0 ? (size_t)info.local_rows / (size_t)(r1 - r0) : 0;   /* band = image rows r0..r1 */
+    GLHostSharedBegin();
     if (info.local_rows > 0 &&
         gl_mat_download_cols(GLHostContext(), x, (int)col_num, 1, shared + (size_t)r0 * width, (size_t)info.local_rows) != GL_OK)
         GLHostFatal("GatherMatCol");
     GLHostBandDone();
-    if (GLHostRank() != 0) return NULL;
-    GLHostWaitBands();
-    Vec v = VecCreateHost(n);
-    memcpy(v->data, shared, sizeof(double) * (size_t)n);
+    Vec v = NULL;
+    if (GLHostRank() == 0) {
+        GLHostWaitBands();
+        v = VecCreateHost(n);
+        memcpy(v->data, shared, sizeof(double) * (size_t)n);
+    }
+    GLHostSharedRelease();
     return v;
 }
 
@@ -125,15 +129,19 @@ png_bytep* ComputeResultFromLaplacian(const png_bytep* const img_bytes, Mat phi,
         fprintf(stderr, "ComputeResultFromLaplacian: image too large for the shared output buffer\n");
         exit(1);
     }
+    GLHostSharedBegin();
     if (gl_filter(GLHostContext(), phi, Pi, g_opt.filter_gain, 0, NULL, shared[0]) != GL_OK) GLHostFatal("ComputeResultFromLaplacian");
     GLHostBandDone();
-    if (GLHostRank() != 0) return NULL;
-    GLHostWaitBands();
-    png_bytep* out = (png_bytep*)malloc(sizeof(png_bytep) * height);
-    for (unsigned int i = 0; i < height; ++i) {
-        out[i] = (png_bytep)malloc(row_bytes);
-        memcpy(out[i], shared[i], row_bytes);
+    png_bytep* out = NULL;
+    if (GLHostRank() == 0) {
+        GLHostWaitBands();
+        out = (png_bytep*)malloc(sizeof(png_bytep) * height);
+        for (unsigned int i = 0; i < height; ++i) {
+            out[i] = (png_bytep)malloc(row_bytes);
+            memcpy(out[i], shared[i], row_bytes);
+        }
     }
+    GLHostSharedRelease();
     return out;
 }
 
@@ -147,14 +155,18 @@ png_bytep* ComputeResultFromEntireLaplacian(const png_bytep* const img_bytes, Ma
         fprintf(stderr, "ComputeResultFromEntireLaplacian: image too large for the shared output buffer\n");
         exit(1);
     }
+    GLHostSharedBegin();
     if (gl_full_result(GLHostContext(), Lapl, NULL, shared[0]) != GL_OK) GLHostFatal("ComputeResultFromEntireLaplacian");
     GLHostBandDone();
-    if (GLHostRank() != 0) return NULL;
-    GLHostWaitBands();
-    png_bytep* out = (png_bytep*)malloc(sizeof(png_bytep) * height);
-    for (unsigned int i = 0; i < height; ++i) {
-        out[i] = (png_bytep)malloc(row_bytes);
-        memcpy(out[i], shared[i], row_bytes);
+    png_bytep* out = NULL;
+    if (GLHostRank() == 0) {
+        GLHostWaitBands();
+        out = (png_bytep*)malloc(sizeof(png_bytep) * height);
+        for (unsigned int i = 0; i < height; ++i) {
+            out[i] = (png_bytep)malloc(row_bytes);
+            memcpy(out[i], shared[i], row_bytes);
+        }
     }
+    GLHostSharedRelease();
     return out;
 }

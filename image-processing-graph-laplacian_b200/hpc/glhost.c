@@ -1,4 +1,5 @@
 #include "glhost.h"
+#include "glshare.h"
 
 #include <signal.h>
 #include <stdarg.h>
@@ -18,7 +19,7 @@ static gl_ctx* g_ctx = NULL;
 static int g_rank = 0, g_size = 1;
 static pid_t g_children[64];
 static pid_t g_parent = 0;   /* rank 0's pid, as seen by the forked ranks */
-static volatile int* g_bands_done = NULL;   /* shared counter: ranks that have written their band of the output image */
+static GLShare g_share;                     /* hand-over of the shared mapping (glshare.h) */
 static unsigned char* g_shared = NULL;
 static size_t g_shared_bytes = 0;
 static png_bytep* g_shared_rows = NULL;
@@ -144,7 +145,8 @@ int GLHostInit(int argc, char** argv, int* rank, int* size)
     unsigned char* id = (unsigned char*)mmap(NULL, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     if (id == MAP_FAILED) return 1;
     volatile int* id_ready = (volatile int*)(id + 256);
-    g_bands_done = (volatile int*)(id + 512);
+    g_share.done = (volatile int*)(id + 512);
+    g_share.consumed = (volatile int*)(id + 768);
     g_shared_bytes = (size_t)1 << 31;  /* reserve 2 GiB of address space; pages are touched on demand */
     g_shared = (unsigned char*)mmap(NULL, g_shared_bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (g_shared == MAP_FAILED) return 1;
@@ -156,6 +158,9 @@ int GLHostInit(int argc, char** argv, int* rank, int* size)
         if (pid == 0) { g_rank = r; break; }
         g_children[r] = pid;
     }
+    g_share.rank = g_rank;
+    g_share.size = g_size;
+    g_share.gen = 0;
     if (gl_ctx_create(&g_ctx, g_rank, g_rank, g_size) != GL_OK) GLHostFatal("gl_ctx_create");
     if (g_size > 1) {
         if (g_rank == 0) {
@@ -187,30 +192,33 @@ png_bytep* GLHostSharedImage(unsigned int width, unsigned int height)
     return g_shared_rows;
 }
 
-/* Every rank calls this once its band of the shared output image is written; rank 0 then waits for all of them.
- * (Not a waitpid: the ranks still have to tear their NCCL communicator down together in GLHostFinalize.) */
-void GLHostBandDone(void)
+/* The shared mapping is handed over with the protocol of glshare.h: Begin (wait until rank 0 has read the previous content),
+ * write, BandDone, [rank 0: WaitBands, read], Release.  (Not a waitpid: the ranks still have to tear their NCCL communicator
+ * down together in GLHostFinalize.) */
+void GLHostSharedBegin(void) { GLShareBegin(&g_share); }
+
+void GLHostBandDone(void) { GLShareDone(&g_share); }
+
+static int a_rank_died(void* unused)
 {
-    __sync_synchronize();
-    __sync_fetch_and_add((int*)g_bands_done, 1);
+    (void)unused;
+    for (int r = 1; r < g_size; ++r) {   /* a rank that died will never report: do not wait for ever */
+        int st = 0;
+        if (waitpid(g_children[r], &st, WNOHANG) == g_children[r]) {
+            fprintf(stderr, "rank %d ended before writing its band\n", r);
+            return 1;
+        }
+    }
+    return 0;
 }
 
 void GLHostWaitBands(void)
 {
     if (g_rank != 0) return;
-    while (*g_bands_done < g_size) {
-        for (int r = 1; r < g_size; ++r) {   /* a rank that died will never report: do not wait for ever */
-            int st = 0;
-            if (waitpid(g_children[r], &st, WNOHANG) == g_children[r]) {
-                fprintf(stderr, "rank %d ended before writing its band\n", r);
-                exit(1);
-            }
-        }
-        usleep(200);
-    }
-    __sync_synchronize();
-    *g_bands_done = 0;
+    if (GLShareWait(&g_share, a_rank_died, NULL)) exit(1);
 }
+
+void GLHostSharedRelease(void) { GLShareRelease(&g_share); }
 
 void GLHostFinalize(void)
 {

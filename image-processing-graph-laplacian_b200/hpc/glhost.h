@@ -36,8 +36,12 @@ int GLHostInit(int argc, char** argv, int* rank, int* size);
 void GLHostFinalize(void);
 /* output image rows shared by all ranks (anonymous shared mapping made before the fork) */
 png_bytep* GLHostSharedImage(unsigned int width, unsigned int height);
-void GLHostBandDone(void);        /* every rank: my band of the shared output image is written */
+/* hand-over of that mapping, usable any number of times per run (glshare.h): every rank brackets its write with
+ * SharedBegin / BandDone, rank 0 reads between WaitBands and SharedRelease, the others call SharedRelease right away */
+void GLHostSharedBegin(void);     /* every rank: wait until rank 0 has read the previous content */
+void GLHostBandDone(void);        /* every rank: my part of the shared buffer is written */
 void GLHostWaitBands(void);       /* rank 0: wait until every rank has reported */
+void GLHostSharedRelease(void);   /* every rank: done with this use (rank 0: after reading) */
 double GLHostWtime(void);
 void GLHostPrintf(const char* fmt, ...);          /* rank-0 stdout, like PetscPrintf(PETSC_COMM_WORLD, ...) */
 #endif

@@ -147,6 +147,18 @@ def test_host_binary_fails_loudly_without_gpu(tmp_path):
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
 
 
+def test_shared_buffer_handover_between_ranks(tmp_path):
+    """hpc/glshare.h: the protocol by which the forked ranks fill the shared output image -- and, one after the other,
+    every eigenvector column dump -- and rank 0 reads it.  Plain processes, no GPU: 4 ranks, 400 hand-overs with random
+    delays; rank 0 must see exactly the current generation in every slot."""
+    exe = str(tmp_path / "share_harness")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-Werror", "-I", HPC, os.path.join(os.path.dirname(os.path.abspath(__file__)), "share_harness.c"),
+                           "-o", exe])
+    for size in (1, 2, 4):
+        r = subprocess.run([exe, str(size), "400"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and r.stdout.strip() == "ok", (size, r.stdout, r.stderr)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the binary on a GPU
 # ---------------------------------------------------------------------------------------------------------------
