@@ -1,12 +1,12 @@
 // Non-local-means patch affinity, the fourth plugin of the reference's Python prototype
-// (python/affinity_methods/NLM.py:9-37, registered in python/affinity_methods/__init__.py:8-13):
+// (python/affinity_methods/NLM.py:9-34, registered in python/affinity_methods/__init__.py:8-13):
 //     K(s, q) = exp(-sum_k (G_k (P_s[k] - P_q[k]))^2 / h^2)
-// over the 7x7 patches P around the two pixels of the symmetrically padded image (np.pad 'symmetric', NLM.py:18), G the
-// Gaussian patch weights of sigma 1.2 normalised to sum 1 (python/utils.py:19-32, NLM.py:19-21), h = 3 in the reference
+// over the 7x7 patches P around the two pixels of the symmetrically padded image (np.pad 'symmetric', NLM.py:16), G the
+// Gaussian patch weights of sigma 1.2 normalised to sum 1 (python/utils.py:19-32, NLM.py:17-19), h = 3 in the reference
 // (NLM.py:12; here the h_val argument).  One channel (the reference filters the luminance).
 //
 // Rows and columns are raster indices.  The reference's columns come out in column-major pixel order (im2col of the transposed
-// image, NLM.py:22) although its callers read them as raster indices; tests/test_oracle.py pins the oracle to the reference
+// image, NLM.py:21) although its callers read them as raster indices; tests/test_oracle.py pins the oracle to the reference
 // through that index map and the CUDA path to the oracle.
 //
 // Same outputs and conventions as affinity.cu: K_A fp64 p x p, K_B in the blocked fp16 layout [block][512 pixels][64 slots]
@@ -185,7 +185,7 @@ k_nlm_affinity_B(const uint8_t* __restrict__ img, const float* __restrict__ sp /
 
 static NlmWeights nlm_weights_host()
 {
-    // matlab_style_gauss2D((7,7), 1.2) (python/utils.py:19-32), normalised again as NLM.py:21 does
+    // matlab_style_gauss2D((7,7), 1.2) (python/utils.py:19-32), normalised again as NLM.py:19 does
     double h[NLM_KK], mx = 0.0, sum = 0.0;
     for (int a = 0; a < NLM_K; ++a)
         for (int b = 0; b < NLM_K; ++b) {

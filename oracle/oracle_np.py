@@ -181,7 +181,7 @@ def synthetic_image(width: int, height: int, channels: int = 1, seed: int = 1234
 # ----------------------------------------------------------------------------
 
 BILATERAL, PHOTOMETRIC, SPATIAL, NLM = "bilateral", "photometric", "spatial", "nlm"
-NLM_KSZ, NLM_SIGMA = 7, 1.2     # python/affinity_methods/NLM.py:13,19 (patch size, Gaussian weight of the patch elements)
+NLM_KSZ, NLM_SIGMA = 7, 1.2     # python/affinity_methods/NLM.py:13,17 (patch size, Gaussian weight of the patch elements)
 
 
 def _as_hwc(img: np.ndarray) -> np.ndarray:
@@ -219,21 +219,21 @@ def affinity_rows(img, sample_indices, cols, kind=BILATERAL, h_loc=40.0, h_val=3
 
 
 def nlm_patch_weights() -> np.ndarray:
-    """matlab_style_gauss2D((7,7), 1.2) normalised to sum 1 (python/utils.py:19-32, NLM.py:19-21), as [7][7]."""
+    """matlab_style_gauss2D((7,7), 1.2) normalised to sum 1 (python/utils.py:19-32, NLM.py:17-19), as [7][7]."""
     m = (NLM_KSZ - 1) / 2.0
     y, x = np.ogrid[-m:m + 1, -m:m + 1]
     h = np.exp(-(x * x + y * y) / (2.0 * NLM_SIGMA * NLM_SIGMA))
     h[h < np.finfo(h.dtype).eps * h.max()] = 0
     h /= h.sum()
-    return h / h.sum()          # NLM.py:21 normalises once more
+    return h / h.sum()          # NLM.py:19 normalises once more
 
 
 def nlm_affinity_rows(img, sample_indices, cols, h=3.0):
-    """Non-local-means patch affinity K(samples, cols), fp64 (python/affinity_methods/NLM.py:9-37):
+    """Non-local-means patch affinity K(samples, cols), fp64 (python/affinity_methods/NLM.py:9-34):
     K = exp(-sum_k (G_k (P_s[k] - P_q[k]))^2 / h^2) over the 7x7 patches P around the two pixels of the symmetrically
-    padded image (np.pad 'symmetric', NLM.py:18), G the normalised Gaussian patch weights, h = 3 (NLM.py:12).
+    padded image (np.pad 'symmetric', NLM.py:16), G the normalised Gaussian patch weights, h = 3 (NLM.py:12).
     Rows AND columns are raster indices here; the reference's columns come out in column-major pixel order
-    (im2col of the transposed image, NLM.py:22) although its callers read them as raster indices -- see
+    (im2col of the transposed image, NLM.py:21) although its callers read them as raster indices -- see
     tests/golden/make_golden_nlm.py and tests/test_oracle.py for the map that pins this function to the reference."""
     img = np.asarray(img)
     assert img.ndim == 2 or img.shape[2] == 1, "NLM affinity is defined on one channel (the reference filters luminance)"

@@ -1,8 +1,8 @@
-"""Golden vectors for the NLM patch affinity from the reference's OWN module (python/affinity_methods/NLM.py:9-37), run in
+"""Golden vectors for the NLM patch affinity from the reference's OWN module (python/affinity_methods/NLM.py:9-34), run in
 the build container: K_AB = NLM_affinity(y, sample_indices) for two small grey images (one of them not square).
 
 What the reference's function returns, established by reading it and checked by tests/test_oracle.py: row i is sample i
-(raster index -> (row, col) with num2xy, NLM.py:28), but the COLUMNS follow im2col(img.T) (NLM.py:22), i.e. column j is
+(raster index -> (row, col) with num2xy, NLM.py:26), but the COLUMNS follow im2col(img.T) (NLM.py:21), i.e. column j is
 the pixel with COLUMN-major index j = col * M + row, while every caller treats j as a raster index
 (python/image_processing.py:60-64).  The oracle and the CUDA kernel use raster order for both (the evidently intended
 matrix); the fixture keeps the reference's output untouched and the test applies the index map.

@@ -174,7 +174,7 @@ def test_oracle_reproduces_the_reference_python_pipeline(golden, tag):
 @pytest.mark.parametrize("name", ["sq24", "rect"])
 def test_nlm_oracle_matches_the_reference_module(name):
     """python/affinity_methods/NLM.py run by tests/golden/make_golden_nlm.py.  The reference's rows are samples in raster
-    order, its columns pixels in COLUMN-major order (im2col of the transposed image, NLM.py:22); the oracle uses raster
+    order, its columns pixels in COLUMN-major order (im2col of the transposed image, NLM.py:21); the oracle uses raster
     order for both.  Through that index map the two agree to rounding; read as raster columns (what the reference's
     callers do, python/image_processing.py:60-64) they do not, not even on a square image."""
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"pyref_nlm_{name}.npz"))
