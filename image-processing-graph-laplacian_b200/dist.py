@@ -59,3 +59,14 @@ def max_over_ranks(values, dist=None, device="cpu") -> list[float]:
     t = torch.tensor(vals, dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return [float(v) for v in t.cpu().tolist()]
+
+
+def sum_over_ranks(values, dist=None, device="cpu") -> list[float]:
+    """Element-wise sum over ranks (fp64): per-band error sums of a parity check become whole-image sums."""
+    vals = [float(v) for v in values]
+    if dist is None:
+        return vals
+    import torch
+    t = torch.tensor(vals, dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.cpu().tolist()]
