@@ -111,8 +111,8 @@ def lib():
         L.gl_full_result.argtypes = [vp, vp, vp, vp]
         L.gl_diag_inverse.argtypes = [vp, vp, C.POINTER(vp)]
         L.gl_diag_pow.argtypes = [vp, vp, C.c_double, C.POINTER(vp)]
-        L.gl_run.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(Params), vp, vp, C.POINTER(C.c_uint), ip, vp]
-        L.gl_run_resident.argtypes = [vp, C.POINTER(Params), vp, vp, C.POINTER(C.c_uint), ip, vp]
+        L.gl_run.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(Params), vp, vp, C.POINTER(C.c_uint), ip, vp, C.c_size_t]
+        L.gl_run_resident.argtypes = [vp, C.POINTER(Params), vp, vp, C.POINTER(C.c_uint), ip, vp, C.c_size_t]
         L.gl_mat_info_get.argtypes = [vp, C.POINTER(MatInfo)]
         L.gl_mat_destroy.argtypes = [vp]
         L.gl_mat_retain.argtypes = [vp]
@@ -451,18 +451,19 @@ class Context:
         elif z_out is False:        # no fp32 result wanted (u8 only)
             z_out = None
         p, m = C.c_uint(), C.c_int()
-        cap = params.sample_size if params.sample_size else int(H * W * 0.01)
-        mu = np.zeros(max(cap * 2 + 64, 64), dtype=np.float64) if want_eigvals else None
+        # the solver serves at most 8192 samples (uniform sampling may return up to ~4x the requested count); the library checks
+        # the capacity it is given
+        mu = np.zeros(min(H * W, 8192), dtype=np.float64) if want_eigvals else None
         _check(lib().gl_run(self.h, img.ctypes.data, W, H, ch, C.byref(params), z_out.ctypes.data if z_out is not None else None,
                             z8_out.ctypes.data if z8_out is not None else None, C.byref(p), C.byref(m),
-                            mu.ctypes.data if want_eigvals else None))
+                            mu.ctypes.data if want_eigvals else None, mu.size if want_eigvals else 0))
         return dict(z=z_out, p=p.value, m=m.value, mu=mu[:m.value] if want_eigvals else None)
 
     def run_resident(self, params: Params, z_out=None, want_eigvals=False):
         p, m = C.c_uint(), C.c_int()
-        mu = np.zeros(16384, dtype=np.float64) if want_eigvals else None
+        mu = np.zeros(8192, dtype=np.float64) if want_eigvals else None
         _check(lib().gl_run_resident(self.h, C.byref(params), z_out.ctypes.data if z_out is not None else None, None,
-                                     C.byref(p), C.byref(m), mu.ctypes.data if want_eigvals else None))
+                                     C.byref(p), C.byref(m), mu.ctypes.data if want_eigvals else None, mu.size if want_eigvals else 0))
         return dict(p=p.value, m=m.value, mu=mu[:m.value] if want_eigvals else None)
 
 

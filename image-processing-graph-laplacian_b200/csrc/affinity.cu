@@ -587,6 +587,7 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         if ((rc = gl_allreduce_f64(ctx, (double*)KB->aux->ptr, (size_t)(1 + C) * p_pad)) != GL_OK) break;
         KB->channels = C;
         KB->image_epoch = ctx->image_epoch;
+        KB->sample_epoch = ctx->sample_epoch;
         KB->aff_kind = kind;
         KB->aff_h_loc = h_loc;
         KB->aff_h_val = h_val;

@@ -444,6 +444,7 @@ int gl_set_samples(gl_ctx* ctx, const uint32_t* indices, unsigned count)
     GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->p = count;
     ctx->p_pad = p_pad;
+    ctx->sample_epoch++;
     ctx->h_samples.assign(indices, indices + count);
     ctx->h_samples_valid = true;
     return GL_OK;
@@ -911,7 +912,7 @@ static int upload_sample_pixels(gl_ctx* ctx)
 extern "C" {
 
 int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out,
-                    double* eigvals_out)
+                    double* eigvals_out, size_t eigvals_cap)
 {
     GL_REQUIRE(ctx && prm, "gl_run_resident: null");
     GL_REQUIRE(ctx->n > 0, "gl_run_resident: no image on the device");
@@ -970,7 +971,8 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
         }
         if (p_out) *p_out = p;
         if (m_out) *m_out = (int)mu->rows;
-        if (eigvals_out) rc = gl_mat_download(ctx, mu, eigvals_out, (size_t)mu->rows);
+        // uniform sampling may return up to ~4x the requested count (hpc/sampling.c:8-13), so the caller's buffer is checked
+        if (eigvals_out) rc = gl_mat_download(ctx, mu, eigvals_out, eigvals_cap);
     } while (0);
     gl_mat_destroy(K_A); gl_mat_destroy(K_B); gl_mat_destroy(L_A); gl_mat_destroy(L_B);
     gl_mat_destroy(U); gl_mat_destroy(mu); gl_mat_destroy(mu_inv); gl_mat_destroy(phi); gl_mat_destroy(f_mu);
@@ -981,12 +983,13 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
 }
 
 int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, const gl_params* prm, float* z_f32,
-           uint8_t* z_u8, unsigned* p_out, int* m_out, double* eigvals_out)
+           uint8_t* z_u8, unsigned* p_out, int* m_out, double* eigvals_out, size_t eigvals_cap)
 {
     GL_REQUIRE(ctx && pixels, "gl_run: null");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaEventRecord(ctx->ev_begin[GL_T_TOTAL], ctx->stream);
-    if (ctx->world == 1) {
+    if (ctx->world == 1 || prm->affinity_kind == GL_NLM) {
+        // (NLM reads 7x7 patches around every band pixel and every sample, wherever it lies: every rank takes the whole image)
         GL_CHECK(gl_set_image(ctx, pixels, width, height, channels));
     } else {
         // a rank of a multi-GPU run needs its own band of rows and the sampled pixels, nothing else: upload the band now, the
@@ -998,7 +1001,7 @@ int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channe
         ctx->host_pixels = pixels;
     }
     ctx->total_started = true;
-    const int rc = gl_run_resident(ctx, prm, z_f32, z_u8, p_out, m_out, eigvals_out);
+    const int rc = gl_run_resident(ctx, prm, z_f32, z_u8, p_out, m_out, eigvals_out, eigvals_cap);
     ctx->host_pixels = nullptr;
     return rc;
 }

@@ -110,6 +110,7 @@ struct gl_mat {
     int channels = 0;            // KB: channels of the image-weighted sums T in aux; PHI: channels of proj
     gl_buf* proj = nullptr;      // PHI: c = Phi^T y, fp64 [m_pad][channels], from the T sums (nystroem) -- see filter.cu
     unsigned long long image_epoch = 0;  // image the sums / proj belong to
+    unsigned long long sample_epoch = 0; // KB: the sample set it was computed from
     int aff_kind = 0;            // KB: the affinity that produced it (to rebuild K_A y_S in fp64)
     double aff_h_loc = 0, aff_h_val = 0;
     float phi_scale = 1.0f;      // PHI: stored value * phi_scale = logical (always 1; scale folded in the epilogue)
@@ -138,6 +139,7 @@ struct gl_ctx {
     const uint8_t* host_pixels = nullptr;  // during a multi-GPU gl_run: the caller's host image (band + sample pixels are uploaded)
 
     unsigned long long image_epoch = 0;  // bumped by every gl_set_*image
+    unsigned long long sample_epoch = 0; // bumped by every new sample set (gl_sampling_*, gl_set_samples)
     int filter_apply_impl = 0;  // 0 = warp-per-row kernel when the shape allows, 1 = always the generic kernel
     int projection_mode = 0;  // 0 = c from the affinity sums (default), 1 = always recompute c with a pass over Phi
     int fuse_filter = 1;      // gl_run: apply the filter inside the extrapolation GEMM's epilogue when possible

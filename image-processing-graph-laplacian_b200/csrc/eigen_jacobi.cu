@@ -494,8 +494,10 @@ __global__ void __launch_bounds__(1024, 1) k_jacobi_sort(const double* __restric
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         unsigned long long k = ~0ull;
         if (i < p) {
-            // positive doubles order like their bit patterns; keep 40 bits of the value, 24 of the index
+            // order-preserving key for signed doubles (gl_eigensolve accepts any symmetric matrix, also an indefinite one): flip all
+            // bits of a negative value, set the sign bit of a non-negative one; keep 40 bits of the value, 24 of the index
             unsigned long long bits = (unsigned long long)__double_as_longlong(lam[i]);
+            bits = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
             k = (bits & ~0xffffffull) | (unsigned)i;
         }
         skeys[i] = k;

@@ -706,6 +706,9 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
     GL_REQUIRE(rows > 0, "nystroem: empty band");
     GL_REQUIRE(keep_phi || ff, "nystroem: nothing to return");
     GL_REQUIRE(L_B->tiles && L_B->starts && L_B->perm, "nystroem: K_B handle without its block layout");
+    // the sample rows of Phi, the projection and the filter's sample rows read ctx->samples: they must still be the samples
+    // K_B (and the eigenvectors) were computed from -- a deferred Phi may be computed long after gl_nystroem returned
+    GL_REQUIRE(L_B->sample_epoch == ctx->sample_epoch, "nystroem: the samples changed since this K_B was computed");
 
     gl_buf *Wt = nullptr, *colmax = nullptr, *scales = nullptr;
     int rc = GL_OK;

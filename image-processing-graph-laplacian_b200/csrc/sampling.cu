@@ -33,6 +33,7 @@ static int set_sample_buffer(gl_ctx* ctx, unsigned count)
     ctx->p = count;
     ctx->p_pad = p_pad;
     ctx->h_samples_valid = false;
+    ctx->sample_epoch++;
     return GL_OK;
 }
 

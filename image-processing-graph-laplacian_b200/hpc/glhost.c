@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <sys/prctl.h>
 #include <sys/time.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -104,17 +105,24 @@ gl_ctx* GLHostContext(void) { return g_ctx; }
 int GLHostRank(void) { return g_rank; }
 int GLHostSize(void) { return g_size; }
 
+/* rank 0 takes every other rank down with it (MPI_Abort semantics): they may be blocked inside a collective or a hand-over
+ * that will never complete.  Async-signal-safe: kill and _exit only. */
+static void kill_ranks_and_exit(int sig)
+{
+    (void)sig;
+    for (int r = 1; r < g_size; ++r)
+        if (g_children[r] > 0) kill(g_children[r], SIGTERM);
+    _exit(1);
+}
+
 void GLHostFatal(const char* where)
 {
     fprintf(stderr, "[rank %d] %s: %s\n", g_rank, where, gl_last_error());
-    /* the other ranks may be waiting for this one inside a collective: take them down too (MPI_Abort semantics) */
     if (g_size > 1) {
-        if (g_rank == 0) {
-            for (int r = 1; r < g_size; ++r)
-                if (g_children[r] > 0) kill(g_children[r], SIGTERM);
-        } else if (g_parent > 1) {
-            kill(g_parent, SIGTERM);
-        }
+        if (g_rank == 0) kill_ranks_and_exit(0);
+        /* a failing rank > 0 tells rank 0, whose SIGTERM handler ends all the others (and PR_SET_PDEATHSIG ends whoever is left
+         * when rank 0 is gone) */
+        if (g_parent > 1) kill(g_parent, SIGTERM);
     }
     exit(1);
 }
@@ -155,9 +163,17 @@ int GLHostInit(int argc, char** argv, int* rank, int* size)
     for (int r = 1; r < g_size; ++r) {
         pid_t pid = fork();
         if (pid < 0) return 1;
-        if (pid == 0) { g_rank = r; break; }
+        if (pid == 0) {
+            g_rank = r;
+            /* never outlive rank 0: the kernel delivers SIGTERM when the parent dies (checked once for a parent already gone) */
+            prctl(PR_SET_PDEATHSIG, SIGTERM);
+            if (getppid() != g_parent) _exit(1);
+            break;
+        }
         g_children[r] = pid;
     }
+    if (g_rank == 0 && g_size > 1) signal(SIGTERM, kill_ranks_and_exit);
+    g_share.parent = g_rank == 0 ? 0 : g_parent;
     g_share.rank = g_rank;
     g_share.size = g_size;
     g_share.gen = 0;

@@ -8,6 +8,7 @@
  * Header-only and free of CUDA so that tests/test_host.py can exercise it with plain forked processes. */
 #ifndef GLB200_GLSHARE_H
 #define GLB200_GLSHARE_H
+#include <sys/types.h>
 #include <unistd.h>
 
 typedef struct GLShare {
@@ -15,12 +16,17 @@ typedef struct GLShare {
     volatile int* consumed;  /* shared */
     int rank, size;
     int gen;                 /* uses this process has completed */
+    pid_t parent;            /* ranks > 0: pid of rank 0's process (0 = not checked); a rank whose parent is gone gives up */
 } GLShare;
 
 /* every rank, before it writes its part */
 static inline void GLShareBegin(GLShare* s)
 {
-    while (*s->consumed < s->gen) usleep(100);
+    while (*s->consumed < s->gen) {
+        /* rank 0 died (it alone advances `consumed`): nobody will ever read this generation */
+        if (s->rank != 0 && s->parent > 0 && getppid() != s->parent) _exit(1);
+        usleep(100);
+    }
     __sync_synchronize();
 }
 

@@ -187,10 +187,11 @@ GL_API int gl_full_result(gl_ctx* ctx, gl_mat* L, float* z_f32, uint8_t* z_u8);
  * (option keep_phi=1 stores it; z is the same bit for bit). */
 /* (world > 1: every rank passes the WHOLE host image; a rank copies only its band of rows and the sampled pixels to its GPU.) */
 GL_API int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, const gl_params* prm,
-                  float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out, double* eigvals_out /* m, may be NULL */);
+                  float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out, double* eigvals_out /* may be NULL */,
+                  size_t eigvals_cap /* doubles eigvals_out can hold; GL_ERR_ARG if the m eigenvalues do not fit */);
 /* Same, image already on the device (gl_set_image / gl_set_synthetic_image); no host copies unless z_* given. */
 GL_API int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out,
-                           double* eigvals_out);
+                           double* eigvals_out, size_t eigvals_cap);
 
 /* ---- matrices ---------------------------------------------------------------------------------- */
 GL_API int gl_mat_info_get(const gl_mat* m, gl_mat_info* info);

@@ -12,6 +12,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     out_dir, W, H, ch, p_req, sampling, gs = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6], int(sys.argv[7])
+    affinity = sys.argv[8] if len(sys.argv) > 8 else "bilateral"
     import torch
     import torch.distributed as dist
 
@@ -25,7 +26,12 @@ def main():
     gd.init_comm(ctx, dist, device="cuda")
     ctx.set_synthetic_image(W, H, ch, 77)
     img = ctx.get_image()
-    prm = gl.default_params(sampling=sampling, sample_size=p_req, seed=3, gram_schmidt=gs)
+    if affinity == "NLM":
+        img = (img // 8 + 100).astype(np.uint8)              # low contrast: the h = 3 patch kernel stays alive
+    # gl_run must bring everything it reads to the device itself: leave a DIFFERENT image resident, so that a rank reading
+    # pixels it never uploaded (outside its band, other than the samples) would compute from the wrong data
+    ctx.set_synthetic_image(W, H, ch, 999)
+    prm = gl.default_params(sampling=sampling, sample_size=p_req, seed=3, gram_schmidt=gs, affinity=affinity)
     z = np.zeros(img.shape, dtype=np.float32)
     r = ctx.run(img, prm, z_out=z)
     r2 = ctx.run(img, prm, z_out=np.zeros_like(z))           # run twice: the comm must survive reuse

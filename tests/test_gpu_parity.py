@@ -720,6 +720,49 @@ def test_errors(ctx):
         ctx.sampling(gl.RANDOM, 64 * 64 + 1)
 
 
+def test_eigenvalue_buffer_is_checked(ctx):
+    """Uniform sampling returns up to ~4x the requested count (hpc/sampling.c:8-13): gl_run must not write more eigenvalues
+    than the caller's buffer holds (100x100 with 1124 requested gives p = 2401)."""
+    import ctypes as C
+    img = o.synthetic_image(100, 100, 1, seed=3)
+    prm = gl.default_params(sample_size=1124)
+    r = ctx.run(img, prm)
+    assert r["p"] == 2401 and r["m"] == 2400 and len(r["mu"]) == 2400 and np.all(np.diff(r["mu"]) >= 0)
+    small = np.zeros(100, dtype=np.float64)
+    guard = small.copy()
+    p, m = C.c_uint(), C.c_int()
+    rc = gl.lib().gl_run(ctx.h, img.ctypes.data, 100, 100, 1, C.byref(prm), None, None, C.byref(p), C.byref(m), small.ctypes.data, 100)
+    assert rc == gl.ERR_ARG and np.array_equal(small, guard)
+
+
+def test_indefinite_matrix_eigenvalues_ascending(ctx):
+    """gl_eigensolve on an uploaded symmetric indefinite matrix: negative eigenvalues sort below the positive ones."""
+    rng = np.random.default_rng(5)
+    q, _ = np.linalg.qr(rng.standard_normal((96, 96)))
+    lam = np.concatenate([-np.linspace(0.5, 3.0, 40), np.linspace(0.2, 5.0, 56)])
+    A = (q * lam) @ q.T
+    A = 0.5 * (A + A.T)
+    U, mu, _ = ctx.eigensolve(ctx.upload(gl.MAT_KA, A), 96)
+    got = mu.download()
+    assert np.all(np.diff(got) >= 0)
+    assert np.max(np.abs(got - np.sort(lam))) < 1e-5
+
+
+def test_deferred_phi_rejects_changed_samples(ctx, golden):
+    """A deferred Phi is computed by its first consumer from the samples of the context: resampling in between must fail
+    loudly instead of mixing the old eigenvectors with new sample indices."""
+    g = golden("cat_small_random50")
+    ctx.set_image(g["image"])
+    ctx.set_samples(g["sample_indices"])
+    K_A, K_B = ctx.affinity()
+    L_A, L_B = ctx.laplacian(K_A, K_B)
+    U, mu, mu_inv = ctx.eigensolve(L_A, -1)
+    phi = ctx.nystroem(L_B, U, mu_inv)
+    ctx.sampling(gl.RANDOM, len(g["sample_indices"]), seed=11)
+    with pytest.raises(gl.GLError):
+        ctx.filter(phi, mu)
+
+
 def test_repeatability_and_launch_count(ctx, golden):
     g = golden("cat_small_random50")
     n0 = ctx.kernel_launches()

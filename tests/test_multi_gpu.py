@@ -18,14 +18,14 @@ def _gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def _launch(tmp_path, world, W, H, ch, p_req, sampling, gs=0):
+def _launch(tmp_path, world, W, H, ch, p_req, sampling, gs=0, affinity="bilateral"):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), str(tmp_path), str(W), str(H), str(ch), str(p_req),
-           sampling, str(gs)]
+           sampling, str(gs), affinity]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-4000:]
     return [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
@@ -60,4 +60,26 @@ def test_band_sharded_matches_oracle(tmp_path, world, W, H, ch, p_req, sampling,
     err_z = float(np.linalg.norm(z - refz) / np.linalg.norm(refz))
     err_dz = float(np.linalg.norm((z - img) - (refz - img)) / np.linalg.norm(refz - img))
     print(f"world={world} {W}x{H}x{ch} gs={gs}: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_mu <= 1e-4 and err_z <= 1e-3 and err_dz <= 5e-3
+
+
+def test_band_sharded_nlm_from_a_fresh_host_image(tmp_path):
+    """gl_run with the NLM patch affinity on 2 GPUs: the 7x7 patches around band pixels and samples reach outside a rank's band,
+    so every rank must have the whole image (the band-only upload left them uninitialised)."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import oracle_c as oc
+    from oracle import oracle_np as o
+    W, H, p_req = 120, 90, 60
+    parts = _launch(tmp_path, 2, W, H, 1, p_req, "random", 0, "NLM")
+    img = (o.synthetic_image(W, H, 1, seed=77) // 8 + 100).astype(np.uint8)
+    s = oc.random_sampling(W, H, p_req, 3)
+    ref = o.run_pipeline(img, s, kind=o.NLM, h_val=3.0)
+    z = np.concatenate([p["z"] for p in parts], axis=0).astype(np.float64)
+    assert np.array_equal(parts[0]["mu"], parts[1]["mu"])
+    err_mu = float(np.max(np.abs(parts[0]["mu"] - ref["mu"]) / ref["mu"]))
+    refz = np.asarray(ref["z"], dtype=np.float64)
+    err_z = float(np.linalg.norm(z - refz) / np.linalg.norm(refz))
+    err_dz = float(np.linalg.norm((z - img) - (refz - img)) / np.linalg.norm(refz - img))
+    print(f"NLM world=2: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
     assert err_mu <= 1e-4 and err_z <= 1e-3 and err_dz <= 5e-3
