@@ -274,8 +274,9 @@ def main():
     ctx.sampling(sampling, p_req, SEED_SAMPLES)
     K_A_, K_B_ = ctx.affinity(affinity)
     kb_info = K_B_.info
-    stored_blocks = int(kb_info.stored_blocks)
-    kb_slots = int(kb_info.ld)                 # sample slots per stored block (64, or 32 with option kb_block)
+    kb_layout = "patch" if int(kb_info.layout) == 1 else "blocked"
+    stored_pairs = int(kb_info.stored_pairs)   # (pixel, sample slot) pairs K_B holds on this rank, padding included
+    mma_pairs = int(kb_info.mma_pairs)         # pairs the extrapolation multiplies (x 2 m_pad flop)
     K_A_.destroy(); K_B_.destroy()
     barrier()
     clocks = ClockSampler(local_rank)
@@ -411,9 +412,9 @@ def main():
     f_aff = 2.0 * (2 + channels) * p * band_px
     m_pad = 64 if m <= 64 else (128 if m <= 128 else (m + 255) // 256 * 256)
     p_pad = (p + 63) // 64 * 64
-    dense_blocks = -(-band_px // 512) * (p_pad // kb_slots)
-    f_ext_exec = 2.0 * stored_blocks * 512 * kb_slots * m_pad          # MMA work actually issued (padding included)
-    kb_bytes = stored_blocks * 512 * kb_slots * 2.0
+    dense_pairs = band_px * p_pad
+    f_ext_exec = 2.0 * mma_pairs * m_pad          # MMA work actually issued (padding included)
+    kb_bytes = stored_pairs * 2.0
     n_parts = 2 * max(1, m_pad // 256)                            # row partials of the fused filter: [parts][rows][channels] fp32
     zpart_bytes = band_px * channels * 4.0 * n_parts
     gemm_bytes = kb_bytes + zpart_bytes                          # default: K_B blocks read once + the row partials written (no Phi)
@@ -428,7 +429,7 @@ def main():
     # BASELINE.json's second metric on EXECUTED flops: the affinity contraction over the stored pairs (2 d per pair) + the MMA work
     # issued by the extrapolation; the dense-equivalent figure (what a kernel without the spatial cutoff would have to do) beside it
     t_ae = (med["k_affinity_b"] + med["k_gemm"]) * 1e-3
-    f_aff_exec = 2.0 * (2 + channels) * stored_blocks * 512 * kb_slots
+    f_aff_exec = 2.0 * (2 + channels) * stored_pairs
     aff_ext_tf = (f_aff_exec + f_ext_exec) / t_ae / 1e12
     aff_ext_tf_dense_equiv = (f_aff + f_ext) / t_ae / 1e12
 
@@ -436,7 +437,7 @@ def main():
     NCU_TRAFFIC = {("c4", 1, "nostore"): (NOSTORE_TRAFFIC, "profiles/r01_ncu_full_c4_v6.txt"),
                    ("c4", 1, "stored"): (19.14e9, "profiles/r01_ncu_full_c4_v5.txt"),
                    ("c4", 1, "dense"): (33.9e9, "profiles/r01_ncu_full_c4.txt")}
-    kept = stored_blocks / max(1, dense_blocks)
+    kept = stored_pairs / max(1, dense_pairs)
     roof_stored = None
     if kept < 0.5:
         # With the spatial cutoff and Phi not stored, the GEMM moves little (the stored K_B blocks in, row partials out) and is
@@ -510,10 +511,11 @@ def main():
                                                        note="executed = flops the two kernels issue (padding of the stored K_B slots included); "
                                                             "dense_equivalent = 2 d p n + 2 p m (n - p) over the same time: NOT a hardware rate, "
                                                             "the spatial cutoff skips pairs whose affinity fp16 flushes to zero"),
-               kb_cutoff=dict(stored_blocks=stored_blocks, dense_blocks=int(dense_blocks), kept=stored_blocks / max(1, dense_blocks),
-                              note="64-sample blocks of K_B whose entries fp16 flushes to zero (sample further than h_loc*sqrt(25 ln 2) "
-                                   "from the 512-pixel tile in rows or columns; samples ordered by column strip, then row) are "
-                                   "neither computed, stored nor multiplied"),
+               kb_cutoff=dict(layout=kb_layout, stored_pairs=stored_pairs, mma_pairs=mma_pairs, dense_pairs=int(dense_pairs), kept=kept,
+                              slots_per_pixel=stored_pairs / max(1, band_px),
+                              note="(pixel, sample) pairs further apart than h_loc*sqrt(25 ln 2) have an affinity fp16 flushes to zero; they are "
+                                   "neither computed, stored nor multiplied.  patch layout: per 64 x 16 pixel patch a gathered list of the "
+                                   "samples in reach, padded to 32 slots; blocked layout: 64-slot runs of a sorted sample order per 512 pixels"),
                gemm=dict(ms=med["k_gemm"], flop_dense_equivalent=f_ext, flop_executed=f_ext_exec, tflops_dense_equivalent=gemm_tf,
                          tflops_executed=gemm_tf_exec, bytes=gemm_bytes, gbs=gemm_gbs, phi_stored=False),
                stage_ms={k: round(v, 4) for k, v in stage.items()},

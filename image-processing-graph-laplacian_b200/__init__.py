@@ -60,7 +60,8 @@ class Params(C.Structure):
 
 class MatInfo(C.Structure):
     _fields_ = [("kind", C.c_int), ("rows", C.c_int64), ("cols", C.c_int64), ("local_rows", C.c_int64),
-                ("ld", C.c_int64), ("elem_bytes", C.c_int), ("scale", C.c_double), ("stored_blocks", C.c_int64)]
+                ("ld", C.c_int64), ("elem_bytes", C.c_int), ("scale", C.c_double), ("stored_blocks", C.c_int64),
+                ("layout", C.c_int), ("stored_pairs", C.c_int64), ("mma_pairs", C.c_int64)]
 
 
 _lib = None

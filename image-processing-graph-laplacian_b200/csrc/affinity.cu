@@ -468,14 +468,20 @@ static int launch_affinity_b(gl_ctx* ctx, double h_loc, double h_val, const floa
 }
 
 template <int KIND, int C>
-static int launch_affinity(gl_ctx* ctx, double h_loc, double h_val, const float* sf, double* KA, const int4* tab, const int* starts,
-                           __half* KB, float* partial, int grid)
+static int launch_affinity_a(gl_ctx* ctx, double h_loc, double h_val, double* KA)
 {
-    const int p = (int)ctx->p, p_pad = ctx->p_pad + 64;   // the K_B kernel works on the internal sample slots (p_int)
+    const int p = (int)ctx->p;
     dim3 ga((unsigned)ceil_div(p, 128), (unsigned)p);
     k_affinity_A<KIND, C><<<ga, 128, 0, ctx->stream>>>((const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p,
                                                       ctx->width, 1.0 / (h_loc * h_loc), 1.0 / (h_val * h_val), KA);
     GL_LAUNCH_CHECK(ctx);
+    return GL_OK;
+}
+
+template <int KIND, int C>
+static int launch_affinity_kb(gl_ctx* ctx, double h_loc, double h_val, const float* sf, const int4* tab, const int* starts,
+                              __half* KB, float* partial, int grid)
+{
     if (ctx->tile_kbs == 32) return launch_affinity_b<KIND, C, 32>(ctx, h_loc, h_val, sf, tab, starts, KB, partial, grid);
     return launch_affinity_b<KIND, C, 64>(ctx, h_loc, h_val, sf, tab, starts, KB, partial, grid);
 }
@@ -510,12 +516,95 @@ size_t gl_nlm_smem_bytes(int p_int);
 int gl_nlm_affinity_launch(gl_ctx* ctx, double h, int p_int, double* KA, const int4* tab, const int* starts, const uint32_t* perm, __half* KB,
                            float* partial, int grid);
 
+// K_A (fp64, p x p) for the non-patch kinds
+static int affinity_a(gl_ctx* ctx, int kind, double h_loc, double h_val, double* KA)
+{
+    const int C = ctx->channels;
+#define AFF_A(K, CC) \
+    if (kind == K && C == CC) return launch_affinity_a<K, CC>(ctx, h_loc, h_val, KA);
+    AFF_A(GL_BILATERAL, 1) AFF_A(GL_BILATERAL, 3) AFF_A(GL_PHOTOMETRIC, 1) AFF_A(GL_PHOTOMETRIC, 3) AFF_A(GL_SPATIAL, 1) AFF_A(GL_SPATIAL, 3)
+#undef AFF_A
+    gl_set_error("affinity: kind %d with %d channels is not supported", kind, C);
+    return GL_ERR_UNSUPPORTED;
+}
+
+// The blocked storage of K_B (layout + tiles) into the handle; `DT` (may be null) receives the band-partial sums D / T in the caller's
+// sample order ([1 + C][p_pad] doubles, zeroed here).  NLM also writes K_A (it shares the patch staging), the other kinds do not.
+static int affinity_blocked_fill(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat* KB, double* KA_for_nlm, double* DT)
+{
+    const int p_pad = ctx->p_pad, C = ctx->channels;
+    const int p_int = p_pad + 64;   // internal sample slots (a block may start at any multiple of 8 below p)
+    gl_buf *sf = nullptr, *partial = nullptr;
+    const int grid = ctx->sm_count * (kind == GL_NLM ? 1 : AFF_CTAS_PER_SM(C));
+    int rc = GL_OK;
+    do {
+        if ((rc = build_tile_table(ctx, kind, h_loc)) != GL_OK) break;
+        KB->tiles = ctx->tile_tab;      // shared with the context's cache (a new layout is a new set of buffers)
+        KB->tiles->refs++;
+        KB->starts = ctx->tile_starts;
+        KB->starts->refs++;
+        KB->perm = ctx->tile_perm;
+        KB->perm->refs++;
+        KB->total_blocks = ctx->tile_total_blocks;
+        KB->kbs = ctx->tile_kbs;
+        KB->ld = KB->kbs;
+        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)KB->total_blocks * AFF_TP * KB->kbs, &KB->buf)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_int, &sf)) != GL_OK) break;
+        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * (1 + C) * p_int, &partial)) != GL_OK) break;
+        if (kind != GL_NLM) {
+            k_sample_features<<<(unsigned)ceil_div(p_int, 256), 256, 0, ctx->stream>>>(
+                (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, (const uint32_t*)KB->perm->ptr, p_int, ctx->width, C,
+                (float*)sf->ptr);
+            ctx->launches++;
+        }
+#define AFF_CASE(K, CC)                                                                                              \
+    if (kind == K && C == CC)                                                                                        \
+        rc = launch_affinity_kb<K, CC>(ctx, h_loc, h_val, (const float*)sf->ptr, (const int4*)KB->tiles->ptr,        \
+                                       (const int*)KB->starts->ptr, (__half*)KB->buf->ptr, (float*)partial->ptr, grid);
+        AFF_CASE(GL_BILATERAL, 1) else AFF_CASE(GL_BILATERAL, 3) else AFF_CASE(GL_PHOTOMETRIC, 1)
+        else AFF_CASE(GL_PHOTOMETRIC, 3) else AFF_CASE(GL_SPATIAL, 1) else AFF_CASE(GL_SPATIAL, 3)
+        else if (kind == GL_NLM) {
+            gl_buf* ka_tmp = nullptr;
+            if (!KA_for_nlm) {      // (a lazily rebuilt NLM K_B: K_A is recomputed into scratch)
+                if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)ctx->p * ctx->p, &ka_tmp)) != GL_OK) break;
+                KA_for_nlm = (double*)ka_tmp->ptr;
+            }
+            rc = gl_nlm_affinity_launch(ctx, h_val, p_int, KA_for_nlm, (const int4*)KB->tiles->ptr, (const int*)KB->starts->ptr,
+                                        (const uint32_t*)KB->perm->ptr, (__half*)KB->buf->ptr, (float*)partial->ptr, grid);
+            if (ka_tmp) gl_buf_release(ka_tmp);
+        }
+        else { gl_set_error("affinity: kind %d with %d channels is not supported", kind, C); rc = GL_ERR_UNSUPPORTED; }
+#undef AFF_CASE
+        if (rc != GL_OK) break;
+        if (DT) {
+            GL_CUDA_BREAK(rc, cudaMemsetAsync(DT, 0, sizeof(double) * (size_t)(1 + C) * p_pad, ctx->stream));
+            k_reduce_partials<<<(unsigned)ceil_div((1 + C) * p_int, 8), 256, 0, ctx->stream>>>(
+                (const float*)partial->ptr, grid, p_int, 1 + C, (const uint32_t*)KB->perm->ptr, p_pad, DT);
+            ctx->launches++;
+            if (cudaGetLastError() != cudaSuccess) { gl_set_error("affinity: kernel launch failed"); rc = GL_ERR_CUDA; }
+        }
+    } while (0);
+    if (sf) gl_buf_release(sf);
+    if (partial) gl_buf_release(partial);
+    return rc;
+}
+
+int gl_kb_require_blocked(gl_ctx* ctx, gl_mat* KB)
+{
+    if (KB->buf) return GL_OK;
+    GL_REQUIRE(KB->pt_buf, "K_B handle without storage");
+    GL_REQUIRE(KB->image_epoch == ctx->image_epoch && KB->sample_epoch == ctx->sample_epoch && KB->q0 == ctx->q0 && KB->p == (int)ctx->p,
+               "K_B: the blocked storage is computed on demand from the image and the samples, which have changed since gl_affinity");
+    return affinity_blocked_fill(ctx, KB->aff_kind, KB->aff_h_loc, KB->aff_h_val, KB, nullptr, nullptr);
+}
+
 int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A_out, gl_mat** K_B_out)
 {
     const int p = (int)ctx->p, p_pad = ctx->p_pad, C = ctx->channels;
-    const int p_int = p_pad + 64;   // internal sample slots (a block may start at any multiple of 8 below p)
+    const int p_int = p_pad + 64;
     const int64_t n_band = ctx->q1 - ctx->q0;
-    {
+    const bool patch = gl_patch_applicable(ctx, kind) && !ctx->want_blocked;
+    if (!patch) {
         const size_t smem = kind == GL_NLM ? gl_nlm_smem_bytes(p_int)
                                            : sizeof(float) * ((size_t)(1 + C) * p_int + 2 * (1 + C) * 8 * 64 + (size_t)(2 + C) * AFF_TP);
         if (smem > 227 * 1024) {
@@ -526,8 +615,6 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
 
     gl_mat* KA = gl_mat_new(ctx, GL_MAT_KA);
     gl_mat* KB = gl_mat_new(ctx, GL_MAT_KB);
-    gl_buf *sf = nullptr, *partial = nullptr;
-    const int grid = ctx->sm_count * (kind == GL_NLM ? 1 : AFF_CTAS_PER_SM(C));
     int rc = GL_OK;
     do {
         KA->rows = KA->cols = KA->local_rows = p;
@@ -537,63 +624,31 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         KB->rows = p;                   // logical K_B: p x (n - p); stored transposed for the whole band
         KB->cols = ctx->n - p;
         KB->local_rows = n_band;
-        KB->ld = ctx->kb_block == 32 ? 32 : 64;   // blocked storage: a pixel row of a block is `ld` sample slots
+        KB->ld = patch ? 32 : (ctx->kb_block == 32 ? 32 : 64);   // sample slots per stored row of a block / tile
         KB->elem_bytes = 2;
         KB->p = p;
         KB->p_pad = p_pad;
         KB->q0 = ctx->q0;
-        if ((rc = build_tile_table(ctx, kind, h_loc)) != GL_OK) break;
-        KB->tiles = ctx->tile_tab;      // shared with the context's cache (a new layout is a new set of buffers)
-        KB->tiles->refs++;
-        KB->starts = ctx->tile_starts;
-        KB->starts->refs++;
-        KB->perm = ctx->tile_perm;
-        KB->perm->refs++;
-        KB->total_blocks = ctx->tile_total_blocks;
-        KB->kbs = ctx->tile_kbs;
-        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)KB->total_blocks * AFF_TP * KB->kbs, &KB->buf)) != GL_OK) break;
+        KB->aff_kind = kind;
+        KB->aff_h_loc = h_loc;
+        KB->aff_h_val = h_val;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)(1 + 2 * C) * p_pad, &KB->aux)) != GL_OK) break;  // [D | T[ch] | (K_A y_S)[ch]]
-        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_int, &sf)) != GL_OK) break;
-        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)grid * (1 + C) * p_int, &partial)) != GL_OK) break;
-
-        if (kind != GL_NLM) {
-            k_sample_features<<<(unsigned)ceil_div(p_int, 256), 256, 0, ctx->stream>>>(
-                (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, (const uint32_t*)KB->perm->ptr, p_int, ctx->width, C,
-                (float*)sf->ptr);
-            ctx->launches++;
+        if (kind != GL_NLM && (rc = affinity_a(ctx, kind, h_loc, h_val, (double*)KA->buf->ptr)) != GL_OK) break;
+        if (patch) rc = gl_patch_affinity(ctx, kind, h_loc, h_val, KB);
+        else {
+            GL_CUDA_BREAK(rc, cudaMemsetAsync(KB->aux->ptr, 0, sizeof(double) * (size_t)(1 + 2 * C) * p_pad, ctx->stream));
+            rc = affinity_blocked_fill(ctx, kind, h_loc, h_val, KB, (double*)KA->buf->ptr, (double*)KB->aux->ptr);
         }
-
-#define AFF_CASE(K, CC)                                                                                              \
-    if (kind == K && C == CC)                                                                                        \
-        rc = launch_affinity<K, CC>(ctx, h_loc, h_val, (const float*)sf->ptr, (double*)KA->buf->ptr, (const int4*)KB->tiles->ptr, \
-                                    (const int*)KB->starts->ptr, (__half*)KB->buf->ptr, (float*)partial->ptr, grid);
-        AFF_CASE(GL_BILATERAL, 1) else AFF_CASE(GL_BILATERAL, 3) else AFF_CASE(GL_PHOTOMETRIC, 1)
-        else AFF_CASE(GL_PHOTOMETRIC, 3) else AFF_CASE(GL_SPATIAL, 1) else AFF_CASE(GL_SPATIAL, 3)
-        else if (kind == GL_NLM)
-            rc = gl_nlm_affinity_launch(ctx, h_val, p_int, (double*)KA->buf->ptr, (const int4*)KB->tiles->ptr, (const int*)KB->starts->ptr,
-                                        (const uint32_t*)KB->perm->ptr, (__half*)KB->buf->ptr, (float*)partial->ptr, grid);
-        else { gl_set_error("affinity: kind %d with %d channels is not supported", kind, C); rc = GL_ERR_UNSUPPORTED; }
-#undef AFF_CASE
         if (rc != GL_OK) break;
-
-        GL_CUDA_BREAK(rc, cudaMemsetAsync(KB->aux->ptr, 0, sizeof(double) * (size_t)(1 + 2 * C) * p_pad, ctx->stream));
         k_ka_times_y<<<p, 128, 0, ctx->stream>>>((const double*)KA->buf->ptr, (const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr,
                                                  p, p_pad, C, (double*)KB->aux->ptr + (size_t)(1 + C) * p_pad);
-        GL_LAUNCH_CHECK(ctx);
-        k_reduce_partials<<<(unsigned)ceil_div((1 + C) * p_int, 8), 256, 0, ctx->stream>>>(
-            (const float*)partial->ptr, grid, p_int, 1 + C, (const uint32_t*)KB->perm->ptr, p_pad, (double*)KB->aux->ptr);
         GL_LAUNCH_CHECK(ctx);
         // ONE allreduce of the band-partial sums: D (p doubles) and T (C x p doubles)
         if ((rc = gl_allreduce_f64(ctx, (double*)KB->aux->ptr, (size_t)(1 + C) * p_pad)) != GL_OK) break;
         KB->channels = C;
         KB->image_epoch = ctx->image_epoch;
         KB->sample_epoch = ctx->sample_epoch;
-        KB->aff_kind = kind;
-        KB->aff_h_loc = h_loc;
-        KB->aff_h_val = h_val;
     } while (0);
-    if (sf) gl_buf_release(sf);
-    if (partial) gl_buf_release(partial);
     if (rc != GL_OK) {
         gl_mat_destroy(KA);
         gl_mat_destroy(KB);

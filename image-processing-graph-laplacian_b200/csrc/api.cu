@@ -107,6 +107,7 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
     if (const char* g = getenv("GLB200_CTA_GROUP")) gl_ctx_set_option(ctx, "cta_group", g);
     if (const char* g = getenv("GLB200_JACOBI_TOL")) gl_ctx_set_option(ctx, "jacobi_tol", g);
     if (const char* g = getenv("GLB200_KB_BLOCK")) gl_ctx_set_option(ctx, "kb_block", g);
+    if (const char* g = getenv("GLB200_KB_LAYOUT")) gl_ctx_set_option(ctx, "kb_layout", g);
     *out = ctx;
     return GL_OK;
 }
@@ -150,6 +151,10 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         GL_REQUIRE(ctx->gemm_prefetch >= 0 && ctx->gemm_prefetch <= 16, "option gemm_prefetch: want 0..16");
     } else if (!strcmp(key, "kb_cutoff")) {
         ctx->kb_cutoff = atoi(value) != 0;
+    } else if (!strcmp(key, "kb_layout")) {
+        if (!strcmp(value, "patch")) ctx->kb_layout = 1;
+        else if (!strcmp(value, "blocked")) ctx->kb_layout = 0;
+        else GL_REQUIRE(false, "option kb_layout: want patch|blocked, got %s", value);
     } else if (!strcmp(key, "phi_limit_mb")) {
         ctx->phi_limit_mb = atoll(value);
         GL_REQUIRE(ctx->phi_limit_mb >= 0, "option phi_limit_mb: want >= 0 (0 = no limit)");
@@ -637,6 +642,11 @@ int gl_mat_info_get(const gl_mat* m, gl_mat_info* info)
     }
     info->scale = m->scale;
     info->stored_blocks = m->total_blocks;
+    info->layout = m->kind == GL_MAT_KB && m->pt_buf ? 1 : 0;
+    // (pixel, sample slot) pairs held, padding included: the affinity kernel evaluates and the extrapolation multiplies these
+    info->stored_pairs = m->kind != GL_MAT_KB ? 0 : (m->pt_buf ? m->pt_blocks * 8 * 128 * 32 : m->total_blocks * 512 * (int64_t)m->kbs);
+    // pairs the extrapolation multiplies (x 2 m_pad flop each): the patch kernel skips the empty upper half of a last block
+    info->mma_pairs = m->kind != GL_MAT_KB ? 0 : (m->pt_buf ? m->pt_ksteps * 128 * 16 : info->stored_pairs);
     return GL_OK;
 }
 
@@ -656,6 +666,9 @@ int gl_mat_destroy(gl_mat* m)
     if (m->tiles) gl_buf_release(m->tiles);
     if (m->starts) gl_buf_release(m->starts);
     if (m->perm) gl_buf_release(m->perm);
+    if (m->pt_info) gl_buf_release(m->pt_info);
+    if (m->pt_slots) gl_buf_release(m->pt_slots);
+    if (m->pt_buf) gl_buf_release(m->pt_buf);
     if (m->dscale) gl_buf_release(m->dscale);
     if (m->proj) gl_buf_release(m->proj);
     if (m->def_LB) gl_mat_destroy(m->def_LB);
@@ -764,6 +777,12 @@ int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap)
         k_scale_f64<<<blocks, T, 0, ctx->stream>>>((const double*)m->buf->ptr, count, m->scale, d);
         break;
     case GL_MAT_KB: {
+        if (m->pt_buf) {   // patch layout (patch.cu)
+            const int rcp = gl_patch_download(ctx, m, m->scale, d);
+            if (rcp != GL_OK) { gl_buf_release(tmp); return rcp; }
+            ctx->launches--;   // (counted again by the check below)
+            break;
+        }
         const int p_int = m->p_pad + 64;
         k_kb_blocked_to_f64<<<(unsigned)ceil_div(rows * p_int, T), T, 0, ctx->stream>>>(
             (const __half*)m->buf->ptr, (const int4*)m->tiles->ptr, (const int*)m->starts->ptr, (const uint32_t*)m->perm->ptr, m->kbs, p_int,
@@ -930,7 +949,13 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
     gl_mat *U = nullptr, *mu = nullptr, *mu_inv = nullptr, *phi = nullptr, *f_mu = nullptr;
     int rc = GL_OK;
     do {
-        if ((rc = gl_affinity(ctx, prm->affinity_kind, prm->h_loc, prm->h_val, &K_A, &K_B)) != GL_OK) break;
+        // the patch layout of K_B serves the fused extrapolation + filter only; a run that needs Phi itself (orthonormalisation,
+        // stages apart, Phi kept) asks for the blocked layout right away instead of computing it on demand later
+        const bool will_fuse = ctx->fuse_filter && !prm->gram_schmidt && ctx->projection_mode == 0 && ctx->gemm_impl == 0 && !ctx->keep_phi;
+        ctx->want_blocked = !will_fuse;
+        rc = gl_affinity(ctx, prm->affinity_kind, prm->h_loc, prm->h_val, &K_A, &K_B);
+        ctx->want_blocked = false;
+        if (rc != GL_OK) break;
         if ((rc = gl_laplacian(ctx, K_A, K_B, &L_A, &L_B)) != GL_OK) break;
         gl_mat_destroy(K_A); K_A = nullptr;            // image_processing.c:210-211
         gl_mat_destroy(K_B); K_B = nullptr;

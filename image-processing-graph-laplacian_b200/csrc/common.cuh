@@ -98,6 +98,13 @@ struct gl_mat {
     gl_buf* tiles = nullptr;     // KB: int4 per 512-pixel tile {first entry in `starts`, block count, storage offset, 0}
     gl_buf* starts = nullptr;    // KB: first internal sample slot of every stored block
     gl_buf* perm = nullptr;      // KB: internal sample slot -> index in the caller's sample list (u32 [p_pad + 64])
+    // KB, patch layout (patch.cu): per 64 x 16 pixel patch a gathered sample list; null when the handle holds the blocked layout only
+    gl_buf* pt_info = nullptr;   // int4 per patch {first slot block, blocks, samples in reach, 0}
+    gl_buf* pt_slots = nullptr;  // u32 [pt_blocks][32]: sample index of every slot (0xffffffff: empty)
+    gl_buf* pt_buf = nullptr;    // fp16 A tiles [pt_blocks * 8][128 pixels][32 slots]
+    int64_t pt_blocks = 0;
+    int64_t pt_ksteps = 0;       // 16-slot K steps over all M tiles (the MMA work the extrapolation issues: x 128 x m_pad x 16 x 2 flop)
+    int pt_npatch = 0;
     int64_t total_blocks = 0;    // KB: stored [512 x kbs] blocks (see affinity.cu)
     int kbs = 64;                // KB: sample slots per block (64 or 32)
     gl_buf* dscale = nullptr;    // optional device double holding `scale` (L_B: -alpha), so no host sync is needed
@@ -170,6 +177,8 @@ struct gl_ctx {
     int64_t tab_key[6] = {-1, -1, -1, -1, -1, -1};
     int64_t tile_total_blocks = 0;
     int kb_cutoff = 1;        // option kb_cutoff: 1 = skip sample blocks whose K_B entries fp16 flushes to zero, 0 = dense
+    int kb_layout = 1;        // option kb_layout: 1 = patch layout for the spatially decaying affinities (patch.cu), 0 = always blocked
+    bool want_blocked = false;  // set by gl_run_resident around gl_affinity when the path will need Phi itself (no fused filter)
 
     // size-keyed cache of freed device blocks (no cudaMalloc in steady state)
     std::multimap<size_t, void*> free_blocks;
@@ -222,6 +231,16 @@ struct StageTimer {
 int gl_allreduce_f64(gl_ctx* ctx, double* dev, size_t count);
 int gl_allreduce_f32(gl_ctx* ctx, float* dev, size_t count);
 void gl_comm_destroy(gl_ctx* ctx);
+
+// patch layout (patch.cu)
+bool gl_patch_applicable(const gl_ctx* ctx, int kind);
+int gl_patch_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat* KB);
+int gl_patch_download(gl_ctx* ctx, const gl_mat* KB, double scale, double* dst_dev);
+struct gl_gemm_fuse;
+int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int ldU, int m, const double* mu_inv, const float* scales,
+                             gl_gemm_fuse* fuse);
+// computes the blocked storage of a K_B handle that holds the patch layout only (same image and samples required)
+int gl_kb_require_blocked(gl_ctx* ctx, gl_mat* KB);
 
 // stage implementations (one .cu each)
 int gl_impl_sampling_uniform(gl_ctx* ctx, unsigned requested, unsigned* actual);

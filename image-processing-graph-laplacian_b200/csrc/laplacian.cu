@@ -68,7 +68,10 @@ int gl_impl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A_out, g
     gl_mat* LB = gl_mat_new(ctx, GL_MAT_KB);
     *LB = *K_B;              // same shape/bookkeeping ...
     LB->refs = 1;
-    LB->buf->refs++;         // ... sharing the storage
+    if (LB->buf) LB->buf->refs++;         // ... sharing the storage
+    if (LB->pt_info) LB->pt_info->refs++;
+    if (LB->pt_slots) LB->pt_slots->refs++;
+    if (LB->pt_buf) LB->pt_buf->refs++;
     if (LB->aux) LB->aux->refs++;
     if (LB->tiles) LB->tiles->refs++;
     if (LB->starts) LB->starts->refs++;

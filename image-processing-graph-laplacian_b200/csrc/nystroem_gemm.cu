@@ -705,17 +705,21 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
     GL_REQUIRE(L_B->dscale, "nystroem: expected L_B (from gl_laplacian), got a bare K_B");
     GL_REQUIRE(rows > 0, "nystroem: empty band");
     GL_REQUIRE(keep_phi || ff, "nystroem: nothing to return");
-    GL_REQUIRE(L_B->tiles && L_B->starts && L_B->perm, "nystroem: K_B handle without its block layout");
     // the sample rows of Phi, the projection and the filter's sample rows read ctx->samples: they must still be the samples
     // K_B (and the eigenvectors) were computed from -- a deferred Phi may be computed long after gl_nystroem returned
     GL_REQUIRE(L_B->sample_epoch == ctx->sample_epoch, "nystroem: the samples changed since this K_B was computed");
+    // K_B in its patch layout (patch.cu) feeds the fused extrapolation + filter directly; everything that needs Phi itself goes
+    // through the blocked storage, computed on demand when the handle does not hold it yet
+    const bool use_patch = L_B->pt_buf != nullptr && ff != nullptr && !keep_phi && ctx->gemm_impl == 0;
+    if (!use_patch) GL_CHECK(gl_kb_require_blocked(ctx, L_B));
+    GL_REQUIRE(use_patch || (L_B->tiles && L_B->starts && L_B->perm), "nystroem: K_B handle without its block layout");
 
     gl_buf *Wt = nullptr, *colmax = nullptr, *scales = nullptr;
     int rc = GL_OK;
     do {
         if (keep_phi && (rc = gl_alloc(ctx, sizeof(__half) * (size_t)rows * m_pad, &phi->buf)) != GL_OK) break;
         const int k_dim = p_pad + 64;   // K_B's internal sample slots
-        if ((rc = gl_alloc(ctx, sizeof(__half) * (size_t)m_pad * k_dim, &Wt)) != GL_OK) break;
+        if (!use_patch && (rc = gl_alloc(ctx, sizeof(__half) * (size_t)m_pad * k_dim, &Wt)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad, &colmax)) != GL_OK) break;
         if ((rc = gl_alloc(ctx, sizeof(float) * 4, &scales)) != GL_OK) break;
 
@@ -726,9 +730,11 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
         GL_LAUNCH_CHECK(ctx);
         k_w_scale<<<1, 1024, 0, ctx->stream>>>((const float*)colmax->ptr, m, (float*)scales->ptr);
         GL_LAUNCH_CHECK(ctx);
-        k_w_write<<<m_pad, 256, 0, ctx->stream>>>(U, (int)phi_A->ld, m, k_dim, (const uint32_t*)L_B->perm->ptr, mu_inv, neg_alpha,
-                                                  (const float*)scales->ptr, (__half*)Wt->ptr);
-        GL_LAUNCH_CHECK(ctx);
+        if (!use_patch) {
+            k_w_write<<<m_pad, 256, 0, ctx->stream>>>(U, (int)phi_A->ld, m, k_dim, (const uint32_t*)L_B->perm->ptr, mu_inv, neg_alpha,
+                                                      (const float*)scales->ptr, (__half*)Wt->ptr);
+            GL_LAUNCH_CHECK(ctx);
+        }
 
         // projection c = Phi^T y from the affinity sums (valid while the image and the samples are unchanged)
         if (L_B->aux && L_B->channels == ctx->channels && L_B->image_epoch == ctx->image_epoch) {
@@ -759,9 +765,12 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
             fuse.zpart = (float*)zpart->ptr;
             fuse.C = C;
         }
-        rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, k_dim, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
-                            keep_phi ? phi->buf->ptr : nullptr, (const int4*)L_B->tiles->ptr, L_B->total_blocks, do_fuse ? &fuse : nullptr,
-                            (const int*)L_B->starts->ptr, L_B->kbs);
+        if (use_patch)
+            rc = gl_patch_nystroem_filter(ctx, L_B, U, (int)phi_A->ld, m, mu_inv, (const float*)scales->ptr, &fuse);
+        else
+            rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, k_dim, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
+                                keep_phi ? phi->buf->ptr : nullptr, (const int4*)L_B->tiles->ptr, L_B->total_blocks, do_fuse ? &fuse : nullptr,
+                                (const int*)L_B->starts->ptr, L_B->kbs);
         if (rc == GL_OK && do_fuse)
             rc = gl_filter_fused_finish(ctx, phi, (const float*)zpart->ptr, fuse.parts, (const float*)wbuf->ptr, U, (int)phi_A->ld,
                                         ff->clip_low, ff->z_f32, ff->z_u8);

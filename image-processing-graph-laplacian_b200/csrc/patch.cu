@@ -1,0 +1,737 @@
+// The PATCH layout of K_B and the kernels built on it: the default path of the spatially decaying affinities (bilateral, spatial).
+//
+// A sample further than r_c = h_loc sqrt(25 ln 2) from a pixel has exp(-d^2/h_loc^2) < 2^-25, which the fp16 K_B flushes to zero
+// (SURVEY H1).  At 4K / p = 1000 / h_loc = 40 a pixel has ~12 samples within reach out of 1000, so K_B is 99 % structural zeros.
+// The blocked layout (affinity.cu) covers them with contiguous runs of a sorted sample order and still stores ~106 slots per
+// pixel; here every PATCH of 64 x 16 pixels gets its own GATHERED list of the samples within r_c of the patch rectangle
+// (ascending sample index, padded to blocks of 32 slots: ~14 samples -> one block), and
+//
+//   K_B   is stored as A tiles [128 pixels = 2 patch rows][32 slots] fp16 (8 KB, the K-major A operand of one MMA tile),
+//         tile (first_block(patch) * 8 + mt * nb + b) for M tile mt and slot block b of the patch;
+//   W     = -alpha U Lambda^-1 is kept SAMPLE-major [p_pad][m_pad] fp16, so that the W rows of a patch's samples are gathered
+//         straight into the MN-major B operand [32 slots][256 columns] in shared memory, once per (patch, N tile), and stay
+//         there for the patch's eight M tiles;
+//   Phi   tile = A . B on tcgen05 (128 x 256 x 16, fp32 accumulators in tensor memory, 1 or 2 K steps), consumed by the fused
+//         filter epilogue (row dots with the weights g f(lambda) o c) and never written to HBM.
+//
+// Replaces, for these affinities: ComputeAffinityMatrices' K_B part (hpc/affinity.c:196-262), Nystroem (hpc/nystroem.c:5-69),
+// Permutation (hpc/utils.c:134-173) and ComputeResultFromLaplacian's two products (hpc/display.c:64-73).  Whoever needs the
+// matrices themselves (Phi download, orthonormalisation, K_B without cutoff) goes through the blocked path (affinity.cu,
+// nystroem_gemm.cu), which stays the checker of this one.
+//
+// The lists are built on the device from the device-resident sample indices (no host planning).
+#include <cmath>
+
+#include "tc_common.cuh"
+
+namespace pt {
+
+constexpr int G = 8;              // M tiles per patch
+constexpr int PW = 64, PR = 16;   // patch: 64 columns x 16 rows; M tile = 2 rows of it
+constexpr int SLOTS = 32;         // sample slots per block
+constexpr int A_TILE_BYTES = 128 * SLOTS * 2;     // 8 KB
+constexpr int B_BLOCK_BYTES = SLOTS * 256 * 2;    // 16 KB: 4 chunks of [32 K rows][64 columns = 128 B]
+constexpr int B_CHUNK_BYTES = SLOTS * 128;        // 4 KB
+constexpr int SA = 8;             // A ring stages
+constexpr int SB = 4;             // B block slots
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
+
+struct Geom {
+    int width, row0, band_rows;   // image width, first image row of the band, rows in the band
+    int pcols, prows, npatch;
+    float rc2;                    // squared reach (pixels^2): samples further than this from the patch rectangle are dropped
+};
+
+// squared distance from sample (sr, sc) to the patch rectangle (image coordinates)
+__device__ __forceinline__ float patch_dist2(const Geom& g, int patch, int sr, int sc)
+{
+    const int py = patch / g.pcols, px = patch - py * g.pcols;
+    const int r_lo = g.row0 + py * PR, r_hi = min(g.row0 + g.band_rows, r_lo + PR) - 1;
+    const int c_lo = px * PW, c_hi = min(g.width, c_lo + PW) - 1;
+    const int dy = max(max(r_lo - sr, sr - r_hi), 0), dx = max(max(c_lo - sc, sc - c_hi), 0);
+    return (float)dy * (float)dy + (float)dx * (float)dx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lists: count -> scan -> fill (one warp per patch; ascending sample index, deterministic)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_patch_count(Geom g, const uint32_t* __restrict__ samples, int p, int4* __restrict__ pinfo)
+{
+    const int patch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (patch >= g.npatch) return;
+    int cnt = 0;
+    for (int i0 = 0; i0 < p; i0 += 32) {
+        const int i = i0 + lane;
+        bool in = false;
+        if (i < p) {
+            const uint32_t q = samples[i];
+            in = patch_dist2(g, patch, (int)(q / (uint32_t)g.width), (int)(q % (uint32_t)g.width)) <= g.rc2;
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, in));
+    }
+    if (lane == 0) pinfo[patch] = make_int4(0, max(1, (cnt + SLOTS - 1) / SLOTS), cnt, 0);
+}
+
+// exclusive scan of the block counts (one CTA); total[0] = blocks in all, total[1] = 16-slot K steps the extrapolation will issue
+// (per M tile of a patch: 2 per full block, 1 for a last block with at most 16 samples)
+__global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* __restrict__ pinfo, int* __restrict__ total)
+{
+    __shared__ int part[1024];
+    __shared__ unsigned long long ksum;
+    if (threadIdx.x == 0) ksum = 0ull;
+    const int per = (npatch + 1023) / 1024;
+    const int a = threadIdx.x * per, b = min(npatch, a + per);
+    int s = 0;
+    unsigned long long ks = 0;
+    for (int i = a; i < b; ++i) {
+        const int4 pi = pinfo[i];
+        s += pi.y;
+        const int mtc = min(G, (g.band_rows - (i / g.pcols) * PR + 1) >> 1);
+        const int last = pi.z - SLOTS * (pi.y - 1);
+        ks += (unsigned long long)mtc * (unsigned long long)(2 * (pi.y - 1) + (last > 16 ? 2 : 1));
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    atomicAdd(&ksum, ks);
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (int i = a; i < b; ++i) {
+        const int nb = pinfo[i].y;
+        pinfo[i].x = run;
+        run += nb;
+    }
+    if (threadIdx.x == 1023) {
+        total[0] = part[1023];
+        *(unsigned long long*)(total + 2) = ksum;   // (its last addition happened before the scan's barriers)
+    }
+}
+
+__global__ void __launch_bounds__(256) k_patch_fill(Geom g, const uint32_t* __restrict__ samples, int p, const int4* __restrict__ pinfo,
+                                                    uint32_t* __restrict__ slots)
+{
+    const int patch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (patch >= g.npatch) return;
+    const int4 pi = pinfo[patch];
+    uint32_t* out = slots + (size_t)pi.x * SLOTS;
+    int pos = 0;
+    for (int i0 = 0; i0 < p; i0 += 32) {
+        const int i = i0 + lane;
+        bool in = false;
+        if (i < p) {
+            const uint32_t q = samples[i];
+            in = patch_dist2(g, patch, (int)(q / (uint32_t)g.width), (int)(q % (uint32_t)g.width)) <= g.rc2;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (in) out[pos + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)i;
+        pos += __popc(bal);
+    }
+    for (int j = pos + lane; j < pi.y * SLOTS; j += 32) out[j] = 0xffffffffu;
+}
+
+// sample features in the caller's order, SoA with stride p_pad: [0] row, [1] col, [2..2+C) values
+__global__ void k_patch_sample_features(const uint8_t* __restrict__ img, const uint32_t* __restrict__ samples, int p, int p_pad, int width,
+                                        int channels, float* __restrict__ sf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p_pad) return;
+    if (i < p) {
+        const uint32_t q = samples[i];
+        sf[i] = (float)(q / (uint32_t)width);
+        sf[p_pad + i] = (float)(q % (uint32_t)width);
+        for (int ch = 0; ch < channels; ++ch) sf[(2 + ch) * p_pad + i] = (float)img[(size_t)q * channels + ch];
+    } else {
+        for (int k = 0; k < 2 + channels; ++k) sf[k * p_pad + i] = 1e18f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// affinity: K_B tiles + the row sums D and image-weighted sums T (from the fp32 values, before the fp16 rounding)
+// ---------------------------------------------------------------------------------------------
+// thread (tx = tid & 3: eight consecutive slots of the block, ty = tid >> 2: column ty of the patch, its 16 rows): the column part
+// of the exponent is the same for all of the thread's pixels and leaves the pair loop.  A warp stores 8 pixel rows of 64 bytes =
+// 512 contiguous bytes.
+template <int KIND, int C>
+__global__ void __launch_bounds__(256, C == 1 ? 3 : 2)
+k_patch_affinity(Geom g, const uint8_t* __restrict__ img, const float* __restrict__ sf, int p_pad, float a2, float b2,
+                 const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots, __half* __restrict__ KB,
+                 float* __restrict__ partial /* [gridDim.x][1 + C][p_pad] */)
+{
+    extern __shared__ float pa_smem[];
+    constexpr int NS = 1 + C;
+    float* cta_sum = pa_smem;                  // [NS][p_pad]
+    float* ws = cta_sum + NS * p_pad;          // [NS][8 warps][SLOTS]
+    float* px = ws + NS * 8 * SLOTS;           // [C][PW * PR] pixel values
+    __shared__ uint32_t sid[SLOTS];
+    const int tid = threadIdx.x, tx = tid & 3, ty = tid >> 2, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < NS * p_pad; i += 256) cta_sum[i] = 0.f;
+
+    for (int patch = blockIdx.x; patch < g.npatch; patch += gridDim.x) {
+        const int py = patch / g.pcols, pxi = patch - py * g.pcols;
+        const int r_base = py * PR, c_base = pxi * PW;     // band-local row, column
+        const int4 pi = pinfo[patch];
+        __syncthreads();   // the previous patch's readers of px / sid are done
+        for (int i = tid; i < PW * PR; i += 256) {
+            const int r = r_base + (i >> 6), c = c_base + (i & 63);
+            const bool in = r < g.band_rows && c < g.width;
+            const size_t q = (size_t)(g.row0 + (in ? r : 0)) * g.width + (in ? c : 0);
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) px[ch * PW * PR + i] = (float)img[q * C + ch];
+        }
+        const float pc = (float)(c_base + ty);
+        const bool col_ok = c_base + ty < g.width;
+        for (int b = 0; b < pi.y; ++b) {
+            if (tid < SLOTS) sid[tid] = slots[(size_t)(pi.x + b) * SLOTS + tid];
+            __syncthreads();
+            float sr[8], sv[C][8], cterm[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t s = sid[tx * 8 + k];
+                const bool empty = s == 0xffffffffu;   // an empty slot gets features at 1e18: its exponent is hugely negative, K = 0
+                const int si = empty ? 0 : (int)s;
+                sr[k] = empty ? 1e18f : sf[si];
+                const float sc = empty ? 1e18f : sf[p_pad + si];
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) sv[ch][k] = empty ? 1e18f : sf[(2 + ch) * p_pad + si];
+                cterm[k] = 0.f;
+                if (KIND != GL_PHOTOMETRIC) {
+                    const float dc = pc - sc;
+                    cterm[k] = dc * dc * a2;   // (an empty slot: -inf -> K = 0)
+                }
+            }
+            float acc[8], tacc[C][8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                acc[k] = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) tacc[ch][k] = 0.f;
+            }
+            __half* kb_patch = KB + ((size_t)pi.x * G) * 128 * SLOTS;
+#pragma unroll 2
+            for (int i = 0; i < PR; ++i) {
+                const int mt = i >> 1;
+                if (r_base + 2 * mt >= g.band_rows) break;      // M tiles wholly below the band are neither stored nor multiplied
+                const bool ok = col_ok && r_base + i < g.band_rows;
+                const float pr = (float)(g.row0 + r_base + i);
+                float pv[C];
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) pv[ch] = px[ch * PW * PR + i * PW + ty];
+                float kv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float x = cterm[k];
+                    if (KIND != GL_PHOTOMETRIC) {
+                        const float dr = pr - sr[k];
+                        x = fmaf(dr * dr, a2, x);
+                    }
+                    if (KIND != GL_SPATIAL) {
+                        float d = pv[0] - sv[0][k];
+                        float t = d * d;
+#pragma unroll
+                        for (int ch = 1; ch < C; ++ch) {
+                            d = pv[ch] - sv[ch][k];
+                            t = fmaf(d, d, t);
+                        }
+                        x = fmaf(t, b2, x);
+                    }
+                    kv[k] = ok ? fast_exp2(x) : 0.f;
+                    acc[k] += kv[k];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) tacc[ch][k] = fmaf(kv[k], pv[ch], tacc[ch][k]);
+                }
+                __half2 h0 = __floats2half2_rn(kv[0], kv[1]), h1 = __floats2half2_rn(kv[2], kv[3]);
+                __half2 h2 = __floats2half2_rn(kv[4], kv[5]), h3 = __floats2half2_rn(kv[6], kv[7]);
+                uint4 pk;
+                pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+                *(uint4*)&kb_patch[((size_t)(mt * pi.y + b) * 128 + (size_t)((i & 1) * PW + ty)) * SLOTS + tx * 8] = pk;
+            }
+            // sums: lanes sharing tx (xor 4, 8, 16), then the 8 warps through shared memory, in a fixed order (deterministic)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) tacc[ch][k] += __shfl_xor_sync(0xffffffffu, tacc[ch][k], o);
+                }
+            }
+            if (lane < 4) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    ws[warp * SLOTS + lane * 8 + k] = acc[k];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) ws[(1 + ch) * 8 * SLOTS + warp * SLOTS + lane * 8 + k] = tacc[ch][k];
+                }
+            }
+            __syncthreads();
+            if (tid < NS * SLOTS) {
+                const int which = tid / SLOTS, sl = tid % SLOTS;
+                const uint32_t s = sid[sl];
+                if (s != 0xffffffffu) {
+                    float sum = 0.f;
+#pragma unroll
+                    for (int wi = 0; wi < 8; ++wi) sum += ws[which * 8 * SLOTS + wi * SLOTS + sl];
+                    cta_sum[which * p_pad + s] += sum;
+                }
+            }
+            __syncthreads();   // ws / sid are rewritten by the next block
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < NS * p_pad; i += 256) partial[(size_t)blockIdx.x * NS * p_pad + i] = cta_sum[i];
+}
+
+// DT[which][j] = sum over CTAs in fixed order (fp64); one warp per output
+__global__ void k_patch_reduce(const float* __restrict__ partial, int nblocks, int p, int p_pad, int ns, double* __restrict__ DT)
+{
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= ns * p_pad) return;
+    const int which = i / p_pad, j = i - which * p_pad;
+    if (j >= p) return;
+    double acc = 0.0;
+    for (int b = lane; b < nblocks; b += 32) acc += (double)partial[(size_t)b * ns * p_pad + i];
+    acc = warp_sum(acc);
+    if (lane == 0) DT[(size_t)which * p_pad + j] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// W rows: W[s][j] = -alpha U[s][j] / mu_j * 2^e (fp16), sample-major [p_pad][m_pad]; 32 x 32 transpose tiles of the column-major U
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_w_rows(const float* __restrict__ U, int ld, int p, int m, int p_pad, int m_pad,
+                                               const double* __restrict__ mu_inv, const double* __restrict__ neg_alpha,
+                                               const float* __restrict__ scales, __half* __restrict__ W)
+{
+    __shared__ float t[32][33];
+    const int s0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, tyy = threadIdx.x >> 5;
+    for (int jj = tyy; jj < 32; jj += 8) {
+        const int j = j0 + jj, s = s0 + tx;
+        float v = 0.f;
+        if (j < m && s < p) v = U[(size_t)j * ld + s] * ((float)(neg_alpha[0] * mu_inv[j]) * scales[0]);
+        t[jj][tx] = v;
+    }
+    __syncthreads();
+    for (int ss = tyy; ss < 32; ss += 8) {
+        const int s = s0 + ss, j = j0 + tx;
+        if (s < p_pad && j < m_pad) W[(size_t)s * m_pad + j] = __float2half_rn(t[tx][ss]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// extrapolation + fused filter
+// ---------------------------------------------------------------------------------------------
+// One persistent CTA per SM; CTA b works on N tile nt = b % n_tiles of the patches b / n_tiles, + gridDim.x / n_tiles, ...: its
+// filter weights never change.  warp 0: TMA producer of the A tiles; warp 1: MMA issuer; warps 2-3: gather the W rows of the
+// patch's samples into the B slots (warp 2 allocates the tensor memory first); warps 4-11: epilogue, warp w drains TMEM lanes
+// 32 (w % 4) .. +31 (= 32 pixels of one patch row) and half of the accumulator's columns.
+template <int FC, int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots,
+                 const __half* __restrict__ W, int m_pad, int n_tiles, const float* __restrict__ scales,
+                 const float* __restrict__ fuse_w /* [m_pad][FC] */, float* __restrict__ zpart /* [2 n_tiles][m_rows][FC] */,
+                 int64_t m_rows, int* __restrict__ err)
+{
+    using namespace tc;
+    extern __shared__ uint8_t pn_smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)pn_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem_a + SA * A_TILE_BYTES;
+    uint64_t* bars = (uint64_t*)(smem_b + SB * B_BLOCK_BYTES);
+    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + SA);
+    const uint32_t bar_bfull = smem_u32(bars + 2 * SA), bar_bempty = smem_u32(bars + 2 * SA + SB);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * SA + 2 * SB), bar_tempty = smem_u32(bars + 2 * SA + 2 * SB + 2);
+    static_assert(2 * SA + 2 * SB + 4 + 1 <= 32, "barrier block is 256 bytes");
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * SA + 2 * SB + 4);
+    float* w_s = (float*)(bars + 32);   // [BN][FC] filter weights of this CTA's N tile, times the GEMM's output scale
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x % n_tiles, first_patch = blockIdx.x / n_tiles, patch_step = gridDim.x / n_tiles;
+
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, 2); mbar_init(bar_bempty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        const float sc = scales[1];
+        for (int i = threadIdx.x; i < BN * FC; i += THREADS) w_s[i] = __ldg(fuse_w + (size_t)nt * BN * FC + i) * sc;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== A producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
+                const int4 pi = pinfo[patch];
+                const int py = patch / g.pcols;
+                const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
+                const int tile0 = pi.x * G;
+                for (int mt = 0; mt < mtc; ++mt)
+                    for (int b = 0; b < pi.y; ++b) {
+                        mbar_wait(bar_aempty + 8 * stage, phase ^ 1, err, 1);
+                        mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)A_TILE_BYTES);
+                        tma_load_2d(smem_u32(smem_a + stage * A_TILE_BYTES), &map_a, bar_afull + 8 * stage, 0, (tile0 + mt * pi.y + b) * 128);
+                        if (++stage == SA) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0, bpos = 0, it = 0;
+            uint32_t phase = 0, buses = 0;   // buses bit s: parity of the number of fills of B slot s consumed so far
+            const uint32_t idesc = make_idesc(BLOCK_M, BN, 0) | (1u << 16);   // B is MN-major
+            for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
+                const int4 pi = pinfo[patch];
+                const int py = patch / g.pcols;
+                const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
+                const bool resident = pi.y <= SB;
+                const int b0 = bpos;
+                for (int mt = 0; mt < mtc; ++mt, ++it) {
+                    const int acc = it & 1;
+                    mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1), err, 2);
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                    for (int b = 0; b < pi.y; ++b) {
+                        int bs;
+                        if (resident) { bs = b0 + b; if (bs >= SB) bs -= SB; }
+                        else { bs = bpos; if (++bpos == SB) bpos = 0; }
+                        mbar_wait(bar_afull + 8 * stage, phase, err, 3);
+                        if (!resident || mt == 0) mbar_wait(bar_bfull + 8 * bs, (buses >> bs) & 1u, err, 6);
+                        tcgen05_fence_after();
+                        const int kk = (pi.z - SLOTS * b) > 16 ? 2 : 1;
+                        const uint64_t da = make_smem_desc_k<32>(smem_u32(smem_a + stage * A_TILE_BYTES));
+                        const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + bs * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
+                        for (int k = 0; k < kk; ++k)
+                            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
+                        umma_commit(bar_aempty + 8 * stage);
+                        if (!resident || mt == mtc - 1) {
+                            umma_commit(bar_bempty + 8 * bs);
+                            buses ^= 1u << bs;
+                        }
+                        if (++stage == SA) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_tfull + 8 * acc);
+                }
+                if (resident) { bpos = b0 + pi.y; if (bpos >= SB) bpos -= SB; }
+            }
+        }
+    } else if (warp < 4) {
+        // ===== B gather: rows of W for the slots of a block, written in the MN-major SWIZZLE_128B layout =====
+        const int t = threadIdx.x - 64;          // 0..63
+        const int u = t & 31, kh = t >> 5;       // 16-byte unit of the 512-byte row part, which of the two rows of a pass
+        int bpos = 0;
+        uint32_t bloads = 0;
+        for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
+            const int4 pi = pinfo[patch];
+            const int py = patch / g.pcols;
+            const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
+            const int reps = pi.y <= SB ? 1 : mtc;
+            for (int rep = 0; rep < reps; ++rep)
+                for (int b = 0; b < pi.y; ++b) {
+                    mbar_wait(bar_bempty + 8 * bpos, ((bloads >> bpos) & 1u) ^ 1u, err, 5);
+                    bloads ^= 1u << bpos;
+                    uint8_t* dst = smem_b + bpos * B_BLOCK_BYTES;
+                    const uint32_t* sl = slots + (size_t)(pi.x + b) * SLOTS;
+#pragma unroll 4
+                    for (int pass = 0; pass < SLOTS / 2; ++pass) {
+                        const int k = pass * 2 + kh;
+                        const uint32_t s = __ldg(sl + k);
+                        uint4 val = make_uint4(0, 0, 0, 0);
+                        if (s != 0xffffffffu && u * 8 < BN) val = __ldg((const uint4*)(W + (size_t)s * m_pad + (size_t)nt * BN) + u);
+                        *(uint4*)(dst + (u >> 3) * B_CHUNK_BYTES + k * 128 + (((u & 7) ^ (k & 7)) << 4)) = val;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_bfull + 8 * bpos);
+                    if (++bpos == SB) bpos = 0;
+                }
+        }
+    } else {
+        // ===== epilogue =====
+        const int wq = warp & 3, share = (warp - 4) >> 2;
+        constexpr int COLS = BN >= 128 ? BN / 2 : BN;          // columns per share (BN = 64: share 0 takes them all)
+        const bool active = BN >= 128 || share == 0;
+        constexpr int NCH = COLS / 32;
+        const uint32_t wbase = smem_u32(w_s) + (uint32_t)((BN >= 128 ? share * COLS : 0) * FC * 4);
+        int it = 0;
+        for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
+            const int py = patch / g.pcols, pxi = patch - py * g.pcols;
+            const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
+            for (int mt = 0; mt < mtc; ++mt, ++it) {
+                const int acc = it & 1;
+                mbar_wait(bar_tfull + 8 * acc, (uint32_t)((it >> 1) & 1), err, 4);
+                tcgen05_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + (BN >= 128 ? share * COLS : 0));
+                float dot[FC][8];
+#pragma unroll
+                for (int q = 0; q < FC; ++q)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dot[q][i] = 0.f;
+                uint32_t v[2][32];
+                if (active) tmem_ld_32x32b_x32(t_row, v[0]);
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    tmem_ld_wait();
+                    if (k + 1 < NCH) {
+                        if (active) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * (k + 1)), v[(k + 1) & 1]);
+                    } else {
+                        // every tcgen05.ld of this accumulator has completed: hand it back before the last chunk's arithmetic
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    }
+                    if (active) {
+                        const uint32_t wv = wbase + (uint32_t)(32 * k * FC * 4);
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            float wr[8 * FC];
+#pragma unroll
+                            for (int q = 0; q < 2 * FC; ++q) lds_f4(wv + (uint32_t)((g8 * 2 * FC + q) * 16), &wr[4 * q]);
+                            if (FC == 1) {
+#pragma unroll
+                                for (int i = 0; i < 8; i += 2)
+                                    ffma2(dot[0][i], dot[0][i + 1], __uint_as_float(v[k & 1][8 * g8 + i]), __uint_as_float(v[k & 1][8 * g8 + i + 1]),
+                                          wr[i], wr[i + 1]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float val = __uint_as_float(v[k & 1][8 * g8 + i]);
+#pragma unroll
+                                    for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
+                                }
+                            }
+                        }
+                    }
+                }
+                // this thread's pixel: tile pixel wq * 32 + lane -> patch row 2 mt + (wq >> 1), column (wq & 1) * 32 + lane
+                const int r = py * PR + 2 * mt + (wq >> 1), c = pxi * PW + (wq & 1) * 32 + lane;
+                if (r < g.band_rows && c < g.width) {
+                    const int64_t row = (int64_t)r * g.width + c;
+                    const int part = nt * 2 + share;
+#pragma unroll
+                    for (int q = 0; q < FC; ++q)
+                        zpart[((size_t)part * m_rows + row) * FC + q] =
+                            ((dot[q][0] + dot[q][1]) + (dot[q][2] + dot[q][3])) + ((dot[q][4] + dot[q][5]) + (dot[q][6] + dot[q][7]));
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+constexpr int nystroem_smem(int fc) { return SA * A_TILE_BYTES + SB * B_BLOCK_BYTES + 256 + 256 * fc * 4 + 1024; }
+
+// K_B from the patch layout to dense fp64 [band pixels][p] in the caller's sample order (dst zeroed beforehand)
+__global__ void k_patch_to_f64(Geom g, const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots, const __half* __restrict__ KB, int p,
+                               double scale, double* __restrict__ dst)
+{
+    const int patch = blockIdx.x;
+    const int4 pi = pinfo[patch];
+    const int py = patch / g.pcols, pxi = patch - py * g.pcols;
+    for (int e = threadIdx.x; e < PW * PR * pi.y * SLOTS; e += blockDim.x) {
+        const int sl = e % (pi.y * SLOTS), pix = e / (pi.y * SLOTS);
+        const int r = py * PR + (pix >> 6), c = pxi * PW + (pix & 63);
+        if (r >= g.band_rows || c >= g.width) continue;
+        const uint32_t s = slots[(size_t)pi.x * SLOTS + sl];
+        if (s == 0xffffffffu) continue;
+        const int mt = (pix >> 6) >> 1, b = sl / SLOTS;
+        const size_t tile = (size_t)pi.x * G + (size_t)mt * pi.y + b;
+        const __half v = KB[(tile * 128 + (size_t)(((pix >> 6) & 1) * PW + (pix & 63))) * SLOTS + (sl % SLOTS)];
+        dst[((size_t)r * g.width + c) * p + s] = scale * (double)__half2float(v);
+    }
+}
+
+}  // namespace pt
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static pt::Geom patch_geom(const gl_ctx* ctx, double h_loc)
+{
+    pt::Geom g;
+    g.width = ctx->width;
+    g.row0 = ctx->row0;
+    g.band_rows = ctx->row1 - ctx->row0;
+    g.pcols = (int)ceil_div(ctx->width, pt::PW);
+    g.prows = (int)ceil_div(g.band_rows, pt::PR);
+    g.npatch = g.pcols * g.prows;
+    // exp(-d^2 / h_loc^2) < 2^-25  <=>  d^2 > 25 ln 2 h_loc^2 ; one pixel of slack on the radius
+    const double rc = h_loc * std::sqrt(25.0 * 0.6931471805599453) + 1.0;
+    g.rc2 = rc < 3e4 ? (float)(rc * rc) : 9e8f;
+    return g;
+}
+
+// whether the patch path serves this affinity on this context
+bool gl_patch_applicable(const gl_ctx* ctx, int kind)
+{
+    return ctx->kb_layout == 1 && ctx->kb_cutoff && (kind == GL_BILATERAL || kind == GL_SPATIAL) && ctx->gemm_impl == 0;
+}
+
+template <int KIND, int C>
+static int launch_patch_affinity(gl_ctx* ctx, const pt::Geom& g, double h_loc, double h_val, const float* sf, gl_mat* KB, float* partial, int grid)
+{
+    const int p_pad = ctx->p_pad;
+    const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_pad + (size_t)(1 + C) * 8 * pt::SLOTS + (size_t)C * pt::PW * pt::PR);
+    GL_CUDA_CHECK(cudaFuncSetAttribute(pt::k_patch_affinity<KIND, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const float log2e = 1.4426950408889634f;
+    StageTimer kt(ctx, GL_T_K_AFFINITY_B);
+    pt::k_patch_affinity<KIND, C><<<grid, 256, smem, ctx->stream>>>(g, (const uint8_t*)ctx->img->ptr, sf, p_pad, (float)(-log2e / (h_loc * h_loc)),
+                                                                   (float)(-log2e / (h_val * h_val)), (const int4*)KB->pt_info->ptr,
+                                                                   (const uint32_t*)KB->pt_slots->ptr, (__half*)KB->pt_buf->ptr, partial);
+    GL_LAUNCH_CHECK(ctx);
+    return GL_OK;
+}
+
+// Fills the patch-layout part of the K_B handle (lists, tiles) and the band-partial sums D / T into KB->aux (not yet reduced over
+// ranks: the caller adds K_A y and runs the allreduce, as for the blocked layout).
+int gl_patch_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat* KB)
+{
+    const int p = (int)ctx->p, p_pad = ctx->p_pad, C = ctx->channels;
+    const pt::Geom g = patch_geom(ctx, h_loc);
+    {
+        const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_pad + (size_t)(1 + C) * 8 * pt::SLOTS + (size_t)C * pt::PW * pt::PR);
+        if (smem > 200 * 1024) {
+            gl_set_error("affinity: p = %d samples need %zu bytes of shared memory per CTA", p, smem);
+            return GL_ERR_UNSUPPORTED;
+        }
+    }
+    gl_buf *total = nullptr, *sf = nullptr, *partial = nullptr;
+    int rc = GL_OK;
+    do {
+        GL_BREAK(rc, gl_alloc(ctx, sizeof(int4) * (size_t)g.npatch, &KB->pt_info));
+        GL_BREAK(rc, gl_alloc(ctx, sizeof(int) * 4, &total));
+        GL_BREAK(rc, gl_ensure_pinned(ctx, 64));
+        const unsigned wgrid = (unsigned)ceil_div(g.npatch, 8);
+        pt::k_patch_count<<<wgrid, 256, 0, ctx->stream>>>(g, (const uint32_t*)ctx->samples->ptr, p, (int4*)KB->pt_info->ptr);
+        ctx->launches++;
+        pt::k_patch_scan<<<1, 1024, 0, ctx->stream>>>(g, g.npatch, (int4*)KB->pt_info->ptr, (int*)total->ptr);
+        ctx->launches++;
+        // the storage is sized by the number of blocks: one small read-back (the only host round trip of the stage)
+        GL_BREAK(rc, gl_ensure_pinned(ctx, 64));
+        GL_CUDA_BREAK(rc, cudaMemcpyAsync(ctx->pinned, total->ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GL_CUDA_BREAK(rc, cudaStreamSynchronize(ctx->stream));
+        const int64_t blocks = *(const int*)ctx->pinned;
+        KB->pt_ksteps = (int64_t) * (const unsigned long long*)((const int*)ctx->pinned + 2);
+        if (blocks <= 0 || blocks * pt::G * 128 >= 0x7fffffffll) {
+            gl_set_error("affinity: %lld sample blocks do not fit 32-bit tile coordinates", (long long)blocks);
+            rc = GL_ERR_UNSUPPORTED;
+            break;
+        }
+        KB->pt_blocks = blocks;
+        KB->pt_npatch = g.npatch;
+        GL_BREAK(rc, gl_alloc(ctx, sizeof(uint32_t) * (size_t)blocks * pt::SLOTS, &KB->pt_slots));
+        GL_BREAK(rc, gl_alloc(ctx, (size_t)blocks * pt::G * pt::A_TILE_BYTES, &KB->pt_buf));
+        pt::k_patch_fill<<<wgrid, 256, 0, ctx->stream>>>(g, (const uint32_t*)ctx->samples->ptr, p, (const int4*)KB->pt_info->ptr,
+                                                        (uint32_t*)KB->pt_slots->ptr);
+        ctx->launches++;
+        GL_BREAK(rc, gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_pad, &sf));
+        pt::k_patch_sample_features<<<(unsigned)ceil_div(p_pad, 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->img->ptr,
+                                                                                            (const uint32_t*)ctx->samples->ptr, p, p_pad,
+                                                                                            ctx->width, C, (float*)sf->ptr);
+        ctx->launches++;
+        int grid = ctx->sm_count * (C == 1 ? 3 : 2);
+        if (grid > g.npatch) grid = g.npatch;
+        GL_BREAK(rc, gl_alloc(ctx, sizeof(float) * (size_t)grid * (1 + C) * p_pad, &partial));
+#define PT_CASE(K, CC) \
+    if (kind == K && C == CC) rc = launch_patch_affinity<K, CC>(ctx, g, h_loc, h_val, (const float*)sf->ptr, KB, (float*)partial->ptr, grid);
+        PT_CASE(GL_BILATERAL, 1) else PT_CASE(GL_BILATERAL, 3) else PT_CASE(GL_SPATIAL, 1) else PT_CASE(GL_SPATIAL, 3)
+        else { gl_set_error("affinity(patch): kind %d with %d channels is not served", kind, C); rc = GL_ERR_UNSUPPORTED; }
+#undef PT_CASE
+        if (rc != GL_OK) break;
+        GL_CUDA_BREAK(rc, cudaMemsetAsync(KB->aux->ptr, 0, sizeof(double) * (size_t)(1 + 2 * C) * p_pad, ctx->stream));
+        pt::k_patch_reduce<<<(unsigned)ceil_div((1 + C) * p_pad, 8), 256, 0, ctx->stream>>>((const float*)partial->ptr, grid, p, p_pad, 1 + C,
+                                                                                           (double*)KB->aux->ptr);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { gl_set_error("affinity(patch): kernel launch failed"); rc = GL_ERR_CUDA; }
+    } while (0);
+    if (total) gl_buf_release(total);
+    if (sf) gl_buf_release(sf);
+    if (partial) gl_buf_release(partial);
+    return rc;
+}
+
+int gl_patch_download(gl_ctx* ctx, const gl_mat* KB, double scale, double* dst_dev)
+{
+    const pt::Geom g = patch_geom(ctx, KB->aff_h_loc);
+    GL_REQUIRE(g.npatch == KB->pt_npatch && KB->q0 == ctx->q0, "K_B download: the handle does not belong to the current image geometry");
+    GL_CUDA_CHECK(cudaMemsetAsync(dst_dev, 0, sizeof(double) * (size_t)KB->local_rows * KB->p, ctx->stream));
+    pt::k_patch_to_f64<<<g.npatch, 256, 0, ctx->stream>>>(g, (const int4*)KB->pt_info->ptr, (const uint32_t*)KB->pt_slots->ptr,
+                                                         (const __half*)KB->pt_buf->ptr, KB->p, scale, dst_dev);
+    GL_LAUNCH_CHECK(ctx);
+    return GL_OK;
+}
+
+// extrapolation + fused filter over the patch layout: zpart[parts][rows][C] partial row dots (fuse->parts is set)
+int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int ldU, int m, const double* mu_inv, const float* scales,
+                             gl_gemm_fuse* fuse)
+{
+    const int p = L_B->p, p_pad = L_B->p_pad, m_pad = gl_m_pad(m), C = fuse->C;
+    const pt::Geom g = patch_geom(ctx, L_B->aff_h_loc);
+    GL_REQUIRE(g.npatch == L_B->pt_npatch && L_B->q0 == ctx->q0, "nystroem(patch): K_B does not belong to the current image geometry");
+    GL_REQUIRE(C == 1 || C == 3, "nystroem(patch): 1 or 3 channels");
+    const int BN = m_pad < 256 ? m_pad : 256;
+    const int n_tiles = m_pad / BN;
+    gl_buf *Wr = nullptr, *err = nullptr;
+    int rc = GL_OK;
+    do {
+        GL_BREAK(rc, gl_alloc(ctx, sizeof(__half) * (size_t)p_pad * m_pad, &Wr));
+        GL_BREAK(rc, gl_alloc(ctx, sizeof(int) * 4, &err));
+        GL_CUDA_BREAK(rc, cudaMemsetAsync(err->ptr, 0, sizeof(int) * 4, ctx->stream));
+        dim3 wg((unsigned)ceil_div(p_pad, 32), (unsigned)ceil_div(m_pad, 32));
+        pt::k_w_rows<<<wg, 256, 0, ctx->stream>>>(U, ldU, p, m, p_pad, m_pad, mu_inv, (const double*)L_B->dscale->ptr, scales, (__half*)Wr->ptr);
+        ctx->launches++;
+        CUtensorMap map_a;
+        GL_BREAK(rc, make_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, L_B->pt_buf->ptr, (uint64_t)L_B->pt_blocks * pt::G * 128, pt::SLOTS,
+                                 pt::SLOTS, pt::SLOTS, 128, CU_TENSOR_MAP_SWIZZLE_64B));
+        int grid = ctx->sm_count / n_tiles * n_tiles;
+        if (grid < n_tiles) grid = n_tiles;
+        if (grid / n_tiles > g.npatch) grid = g.npatch * n_tiles;
+        fuse->parts = 2 * n_tiles;
+        const int SM = pt::nystroem_smem(C);
+        StageTimer kt(ctx, GL_T_K_GEMM);
+#define PT_LAUNCH(FC, BNN)                                                                                                          \
+    do {                                                                                                                            \
+        GL_CUDA_BREAK(rc, cudaFuncSetAttribute(pt::k_patch_nystroem<FC, BNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));    \
+        pt::k_patch_nystroem<FC, BNN><<<grid, pt::THREADS, SM, ctx->stream>>>(map_a, g, (const int4*)L_B->pt_info->ptr,             \
+                                                                              (const uint32_t*)L_B->pt_slots->ptr, (const __half*)Wr->ptr, \
+                                                                              m_pad, n_tiles, scales, fuse->w, fuse->zpart,         \
+                                                                              L_B->local_rows, (int*)err->ptr);                     \
+    } while (0)
+        if (C == 1 && BN == 256) PT_LAUNCH(1, 256);
+        else if (C == 1 && BN == 128) PT_LAUNCH(1, 128);
+        else if (C == 1) PT_LAUNCH(1, 64);
+        else if (BN == 256) PT_LAUNCH(3, 256);
+        else if (BN == 128) PT_LAUNCH(3, 128);
+        else PT_LAUNCH(3, 64);
+#undef PT_LAUNCH
+        if (rc != GL_OK) break;
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { gl_set_error("nystroem(patch): kernel launch failed"); rc = GL_ERR_CUDA; }
+    } while (0);
+    if (Wr) gl_buf_release(Wr);
+    if (err) gl_buf_release(err);
+    return rc;
+}

@@ -81,7 +81,10 @@ typedef struct gl_mat_info {
     int64_t ld;          /* leading dimension in elements of the stored layout */
     int elem_bytes;
     double scale;        /* logical value = scale * stored value (L_B = -alpha K_B shares K_B's buffer) */
-    int64_t stored_blocks; /* KB: [512 x ld] blocks held (ld = 64, or 32 with option kb_block; dense: ceil(local_rows/512) * ceil(p/ld)); else 0 */
+    int64_t stored_blocks; /* KB, blocked layout: [512 x ld] blocks held (ld = 64, or 32 with option kb_block; dense: ceil(local_rows/512) * ceil(p/ld)); else 0 */
+    int layout;            /* KB: 0 = blocked storage (csrc/affinity.cu), 1 = patch layout (csrc/patch.cu: gathered sample lists per 64 x 16 pixel patch) */
+    int64_t stored_pairs;  /* KB: (pixel, sample slot) pairs held, padding included */
+    int64_t mma_pairs;     /* KB: (pixel, sample slot) pairs the extrapolation multiplies (x 2 m_pad flop each) */
 } gl_mat_info;
 
 /* Stage indices for gl_ctx_stage_ms (same vocabulary as the reference's stdout timers,
