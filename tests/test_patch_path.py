@@ -62,7 +62,7 @@ def test_patch_kb_and_sums_match_oracle(ctx, W, H, ch, p, kind, method, h_loc):
         _, K_B2 = ctx.affinity(kind, h_loc=h_loc)
         assert K_B2.info.layout == 0
         kb2 = K_B2.download()
-        assert np.max(np.abs(kb2 - kb)) < 1e-6                        # same fp32 values rounded to fp16; below the cutoff both are 0
+        assert np.max(np.abs(kb2 - kb)) < 5e-4                        # at most one fp16 ulp apart (the exponent is summed in another order)
         assert np.max(np.abs(K_B2.rowsums() - D) / D) < 1e-6
     finally:
         ctx.set_option("kb_layout", "patch")
