@@ -407,12 +407,7 @@ extern "C" int gl_kb_layout_host(int width, int64_t q0, int64_t q1, const uint32
 static int build_tile_table(gl_ctx* ctx, int kind, double h_loc)
 {
     const int p = (int)ctx->p, W = ctx->width;
-    if (!ctx->h_samples_valid) {
-        ctx->h_samples.resize(p);
-        GL_CUDA_CHECK(cudaMemcpyAsync(ctx->h_samples.data(), ctx->samples->ptr, sizeof(uint32_t) * p, cudaMemcpyDeviceToHost, ctx->stream));
-        GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        ctx->h_samples_valid = true;
-    }
+    GL_CHECK(gl_host_samples(ctx));
     const bool cut = ctx->kb_cutoff && kind != GL_PHOTOMETRIC && kind != GL_NLM;   // no spatial term, no cutoff
     const int64_t R = kb_reach(h_loc);
     const int kbs = ctx->kb_block == 32 ? 32 : 64;

@@ -101,6 +101,11 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
         GL_CUDA_CHECK(cudaEventCreate(&ctx->ev_end[i]));
     }
     for (int i = 0; i < 8; ++i) GL_CUDA_CHECK(cudaEventCreate(&ctx->marks[i]));
+    GL_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->stat_ev, cudaEventDisableTiming));
+    GL_CUDA_CHECK(cudaMallocHost((void**)&ctx->hstat, sizeof(int) * GL_DS_COUNT));
+    memset(ctx->hstat, 0, sizeof(int) * GL_DS_COUNT);
+    GL_CHECK(gl_alloc(ctx, sizeof(int) * GL_DS_COUNT, &ctx->dstat));
+    GL_CUDA_CHECK(cudaMemsetAsync(ctx->dstat->ptr, 0, sizeof(int) * GL_DS_COUNT, ctx->stream));
     const char* v = getenv("GLB200_VERBOSE");
     ctx->verbose = v ? atoi(v) : 0;
     if (const char* g = getenv("GLB200_GEMM")) gl_ctx_set_option(ctx, "gemm", g);
@@ -185,7 +190,7 @@ int gl_ctx_sync(gl_ctx* ctx)
     GL_REQUIRE(ctx, "gl_ctx_sync: null");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
     GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    return GL_OK;
+    return gl_status_check(ctx, nullptr);   // what an asynchronous gl_run_resident had to report, if anything
 }
 
 int gl_ctx_destroy(gl_ctx* ctx)
@@ -199,6 +204,9 @@ int gl_ctx_destroy(gl_ctx* ctx)
     if (ctx->tile_tab) gl_buf_release(ctx->tile_tab);
     if (ctx->tile_starts) gl_buf_release(ctx->tile_starts);
     if (ctx->tile_perm) gl_buf_release(ctx->tile_perm);
+    if (ctx->dstat) gl_buf_release(ctx->dstat);
+    if (ctx->hstat) cudaFreeHost(ctx->hstat);
+    if (ctx->stat_ev) cudaEventDestroy(ctx->stat_ev);
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
     ctx->free_blocks.clear();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -320,6 +328,59 @@ int gl_ensure_pinned(gl_ctx* ctx, size_t bytes)
     size_t want = (size_t)round_up((int64_t)bytes, 1 << 16);
     GL_CUDA_CHECK(cudaMallocHost(&ctx->pinned, want));
     ctx->pinned_bytes = want;
+    return GL_OK;
+}
+
+int gl_status_begin(gl_ctx* ctx)
+{
+    GL_CUDA_CHECK(cudaMemsetAsync(ctx->dstat->ptr, 0, sizeof(int) * GL_DS_COUNT, ctx->stream));
+    return GL_OK;
+}
+
+int gl_status_flush(gl_ctx* ctx)
+{
+    GL_CUDA_CHECK(cudaMemcpyAsync(ctx->hstat, ctx->dstat->ptr, sizeof(int) * GL_DS_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA_CHECK(cudaEventRecord(ctx->stat_ev, ctx->stream));
+    ctx->stat_pending = true;
+    return GL_OK;
+}
+
+int gl_status_check(gl_ctx* ctx, bool* pt_overflow)
+{
+    if (pt_overflow) *pt_overflow = false;
+    if (!ctx->stat_pending) return GL_OK;
+    GL_CUDA_CHECK(cudaEventSynchronize(ctx->stat_ev));
+    ctx->stat_pending = false;
+    const int* h = ctx->hstat;
+    if (h[GL_DS_SAMPLING] != 0) {
+        gl_set_error("random sampling kernel failed (status %d)", h[GL_DS_SAMPLING]);
+        return h[GL_DS_SAMPLING] == 1 ? GL_ERR_UNSUPPORTED : GL_ERR_CUDA;
+    }
+    if (h[GL_DS_PT_OVERFLOW] != 0) {
+        // the sample lists needed more blocks than were set aside: nothing was computed; forget the capacity (the next run asks
+        // the device first).  The caller that can, runs the step again.
+        ctx->pt_cap_blocks = 0;
+        if (pt_overflow) { *pt_overflow = true; return GL_OK; }
+        gl_set_error("K_B sample lists outgrew their storage (%d blocks): run again", h[GL_DS_PT_BLOCKS]);
+        return GL_ERR_NOMEM;
+    }
+    if (h[GL_DS_JACOBI] != 0) {
+        float off;
+        memcpy(&off, &h[GL_DS_JACOBI_OFF], sizeof(float));
+        gl_set_error("eigensolve: not converged after %d sweeps (off-orthogonality %.3g > %.3g)", h[GL_DS_JACOBI_SWEEPS], off, ctx->jacobi_tol);
+        return GL_ERR_NOTCONVERGED;
+    }
+    return GL_OK;
+}
+
+int gl_host_samples(gl_ctx* ctx)
+{
+    if (ctx->h_samples_valid) return GL_OK;
+    GL_REQUIRE(ctx->samples && ctx->p > 0, "no samples");
+    ctx->h_samples.resize(ctx->p);
+    GL_CUDA_CHECK(cudaMemcpyAsync(ctx->h_samples.data(), ctx->samples->ptr, sizeof(uint32_t) * ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_samples_valid = true;
     return GL_OK;
 }
 
@@ -905,6 +966,7 @@ __global__ void k_scatter_sample_pixels(uint8_t* __restrict__ img, const uint32_
 static int upload_sample_pixels(gl_ctx* ctx)
 {
     const int p = (int)ctx->p, C = ctx->channels;
+    GL_CHECK(gl_host_samples(ctx));
     GL_REQUIRE(ctx->h_samples_valid && (int)ctx->h_samples.size() == p, "gl_run: no host copy of the sample indices");
     gl_buf* vals = nullptr;
     GL_CHECK(gl_alloc(ctx, (size_t)p * C, &vals));
@@ -930,14 +992,14 @@ static int upload_sample_pixels(gl_ctx* ctx)
 
 extern "C" {
 
-int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out,
-                    double* eigvals_out, size_t eigvals_cap)
+}  // extern "C"
+
+// One pass of the whole path.  The stages run in "asynchronous mode": none of them stops for the host (sampling status, size of
+// the K_B sample lists, convergence report of the eigensolve go to the deferred status block), so the host enqueues the ~30
+// launches of a step ahead of the device.
+static int run_resident_once(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out,
+                             double* eigvals_out, size_t eigvals_cap)
 {
-    GL_REQUIRE(ctx && prm, "gl_run_resident: null");
-    GL_REQUIRE(ctx->n > 0, "gl_run_resident: no image on the device");
-    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
-    if (!ctx->total_started) cudaEventRecord(ctx->ev_begin[GL_T_TOTAL], ctx->stream);
-    ctx->total_started = false;
 
     unsigned requested = prm->sample_size ? prm->sample_size : (unsigned)((double)ctx->n * 0.01);  // image_processing.c:187
     unsigned p = 0;
@@ -1001,6 +1063,36 @@ int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_
     } while (0);
     gl_mat_destroy(K_A); gl_mat_destroy(K_B); gl_mat_destroy(L_A); gl_mat_destroy(L_B);
     gl_mat_destroy(U); gl_mat_destroy(mu); gl_mat_destroy(mu_inv); gl_mat_destroy(phi); gl_mat_destroy(f_mu);
+    return rc;
+}
+
+extern "C" {
+
+int gl_run_resident(gl_ctx* ctx, const gl_params* prm, float* z_f32, uint8_t* z_u8, unsigned* p_out, int* m_out,
+                    double* eigvals_out, size_t eigvals_cap)
+{
+    GL_REQUIRE(ctx && prm, "gl_run_resident: null");
+    GL_REQUIRE(ctx->n > 0, "gl_run_resident: no image on the device");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (!ctx->total_started) cudaEventRecord(ctx->ev_begin[GL_T_TOTAL], ctx->stream);
+    ctx->total_started = false;
+    // what the previous asynchronous run had to report (normally already there: this does not wait for the device)
+    bool overflow = false;
+    GL_CHECK(gl_status_check(ctx, &overflow));
+    int rc = GL_OK;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        GL_CHECK(gl_status_begin(ctx));
+        ctx->async_mode = true;
+        rc = run_resident_once(ctx, prm, z_f32, z_u8, p_out, m_out, eigvals_out, eigvals_cap);
+        ctx->async_mode = false;
+        if (rc != GL_OK) break;
+        GL_CHECK(gl_status_flush(ctx));
+        if (!(z_f32 || z_u8 || eigvals_out)) break;     // nothing comes back to the host: the status is read at the next call
+        // results were copied to the host: they are valid only if the deferred status says so
+        rc = gl_status_check(ctx, &overflow);
+        if (rc != GL_OK || !overflow) break;
+        // (the K_B sample lists outgrew the storage set aside from the previous run: once more, asking the device first)
+    }
     cudaEventRecord(ctx->ev_end[GL_T_TOTAL], ctx->stream);
     ctx->ev_valid[GL_T_TOTAL] = true;
     if (rc == GL_OK && (z_f32 || z_u8)) GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -195,6 +195,17 @@ struct gl_ctx {
 
     gl_nccl* comm = nullptr;
 
+    // Deferred status (gl_run_resident): inside the one-call path the stages do not stop for the host; what they would have
+    // reported lands in `dstat` on the device and is read back with the results, or at the next call (GL_DS_* slots)
+    bool async_mode = false;
+    gl_buf* dstat = nullptr;      // int [GL_DS_COUNT]
+    int* hstat = nullptr;         // pinned mirror
+    cudaEvent_t stat_ev = nullptr;
+    bool stat_pending = false;
+    // patch layout: blocks to allocate without asking the device first, learnt from the last run with the same key
+    int64_t pt_cap_blocks = 0;
+    int64_t pt_cap_key[5] = {-1, -1, -1, -1, -1};
+
     // options
     int gemm_impl = 0;        // 0 = tcgen05 (default), 1 = simple CUDA-core checker kernel
     int gemm_cta_group = 1;   // 1 or 2
@@ -211,6 +222,14 @@ struct gl_ctx {
     float jacobi_tol = 5e-5f;
     int verbose = 0;
 };
+
+enum { GL_DS_SAMPLING = 0, GL_DS_PT_OVERFLOW = 1, GL_DS_PT_BLOCKS = 2, GL_DS_JACOBI = 3, GL_DS_JACOBI_SWEEPS = 4, GL_DS_JACOBI_OFF = 5,
+       GL_DS_PT_KSTEPS = 6 /* and 7: u64 */, GL_DS_PT_MAXNB = 8 /* most slot blocks of any patch */, GL_DS_COUNT = 16 };
+int gl_status_begin(gl_ctx* ctx);                    // zero the device words (start of an asynchronous run)
+int gl_status_flush(gl_ctx* ctx);                    // enqueue their copy to the host
+int gl_status_check(gl_ctx* ctx, bool* pt_overflow); // wait for the copy and turn the words into a status / error message
+// host mirror of the sample indices (fetched from the device on first use after a device-side sampling)
+int gl_host_samples(gl_ctx* ctx);
 
 int gl_alloc(gl_ctx* ctx, size_t bytes, gl_buf** out);
 void gl_buf_release(gl_buf* b);

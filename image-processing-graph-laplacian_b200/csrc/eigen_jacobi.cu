@@ -536,6 +536,17 @@ __global__ void k_jacobi_extract(const float* __restrict__ G, const double* __re
     }
 }
 
+// deferred convergence report (gl_run_resident): the words the host would have read, turned into the status block on the device
+__global__ void k_jacobi_status(const unsigned* __restrict__ ctl, int max_sweeps, float tol, int* __restrict__ dstat)
+{
+    const int sweeps = (int)ctl[max_sweeps + 1];
+    const unsigned last_bits = sweeps < max_sweeps ? ctl[sweeps] : ctl[max_sweeps - 1];
+    const float last = __uint_as_float(last_bits);
+    dstat[GL_DS_JACOBI_SWEEPS] = sweeps;
+    dstat[GL_DS_JACOBI_OFF] = (int)last_bits;
+    dstat[GL_DS_JACOBI] = (sweeps >= max_sweeps || last > tol) ? 1 : 0;
+}
+
 int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv)
 {
     const int p = (int)L_A->rows;
@@ -632,6 +643,11 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
                                                      (double*)mu->buf->ptr, (double*)mui->buf->ptr);
         GL_LAUNCH_CHECK(ctx);
 
+        if (ctx->async_mode) {   // the report goes to the deferred status block; nobody waits here
+            k_jacobi_status<<<1, 1, 0, ctx->stream>>>((const unsigned*)ctl->ptr, max_sweeps, ctx->jacobi_tol, (int*)ctx->dstat->ptr);
+            GL_LAUNCH_CHECK(ctx);
+            break;
+        }
         // convergence report (one small D2H; the solve itself never synchronises with the host)
         GL_BREAK(rc, gl_ensure_pinned(ctx, sizeof(unsigned) * (size_t)(max_sweeps + 4)));
         GL_CUDA_BREAK(rc, cudaMemcpyAsync(ctx->pinned, ctl->ptr, sizeof(unsigned) * (size_t)(max_sweeps + 4), cudaMemcpyDeviceToHost,

@@ -7,7 +7,8 @@
 // (ascending sample index, padded to blocks of 32 slots: ~14 samples -> one block), and
 //
 //   K_B   is stored as A tiles [128 pixels = 2 patch rows][32 slots] fp16 (8 KB, the K-major A operand of one MMA tile),
-//         tile (first_block(patch) * 8 + mt * nb + b) for M tile mt and slot block b of the patch;
+//         tile (first_block(patch) * 8 + mt * nb + b) for M tile mt and slot block b of the patch, loaded by one SWIZZLE_64B tensor-map
+//         copy (a pre-swizzled tile fetched by a plain 8 KB bulk copy was measured 10 % slower, profiles/r02_patch_timeline.md);
 //   W     = -alpha U Lambda^-1 is kept SAMPLE-major [p_pad][m_pad] fp16, so that the W rows of a patch's samples are gathered
 //         straight into the MN-major B operand [32 slots][256 columns] in shared memory, once per (patch, N tile), and stay
 //         there for the patch's eight M tiles;
@@ -34,7 +35,7 @@ constexpr int B_BLOCK_BYTES = SLOTS * 256 * 2;    // 16 KB: 4 chunks of [32 K ro
 constexpr int B_CHUNK_BYTES = SLOTS * 128;        // 4 KB
 constexpr int SA = 8;             // A ring stages
 constexpr int SB = 4;             // B block slots
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;       // epilogue warps: 4 TMEM lane quarters x 2 column shares
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 
 struct Geom {
@@ -75,18 +76,21 @@ __global__ void __launch_bounds__(256) k_patch_count(Geom g, const uint32_t* __r
 
 // exclusive scan of the block counts (one CTA); total[0] = blocks in all, total[1] = 16-slot K steps the extrapolation will issue
 // (per M tile of a patch: 2 per full block, 1 for a last block with at most 16 samples)
-__global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* __restrict__ pinfo, int* __restrict__ total)
+__global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* __restrict__ pinfo, int* __restrict__ total, long long cap_blocks,
+                                                     int* __restrict__ dstat)
 {
     __shared__ int part[1024];
     __shared__ unsigned long long ksum;
-    if (threadIdx.x == 0) ksum = 0ull;
+    __shared__ int max_nb;
+    if (threadIdx.x == 0) { ksum = 0ull; max_nb = 0; }
     const int per = (npatch + 1023) / 1024;
     const int a = threadIdx.x * per, b = min(npatch, a + per);
-    int s = 0;
+    int s = 0, nbmax = 0;
     unsigned long long ks = 0;
     for (int i = a; i < b; ++i) {
         const int4 pi = pinfo[i];
         s += pi.y;
+        nbmax = max(nbmax, pi.y);
         const int mtc = min(G, (g.band_rows - (i / g.pcols) * PR + 1) >> 1);
         const int last = pi.z - SLOTS * (pi.y - 1);
         ks += (unsigned long long)mtc * (unsigned long long)(2 * (pi.y - 1) + (last > 16 ? 2 : 1));
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* _
     part[threadIdx.x] = s;
     __syncthreads();
     atomicAdd(&ksum, ks);
+    atomicMax(&max_nb, nbmax);
     for (int o = 1; o < 1024; o <<= 1) {
         const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
         __syncthreads();
@@ -109,12 +114,19 @@ __global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* _
     if (threadIdx.x == 1023) {
         total[0] = part[1023];
         *(unsigned long long*)(total + 2) = ksum;   // (its last addition happened before the scan's barriers)
+        // storage set aside without asking (cap_blocks > 0): too small -> every kernel of the patch path returns at once and the
+        // host, which reads the status block with the results, runs the step again
+        dstat[GL_DS_PT_BLOCKS] = part[1023];
+        dstat[GL_DS_PT_MAXNB] = max_nb;
+        *(unsigned long long*)(dstat + GL_DS_PT_KSTEPS) = ksum;
+        dstat[GL_DS_PT_OVERFLOW] = (cap_blocks > 0 && (long long)part[1023] > cap_blocks) ? 1 : 0;
     }
 }
 
 __global__ void __launch_bounds__(256) k_patch_fill(Geom g, const uint32_t* __restrict__ samples, int p, const int4* __restrict__ pinfo,
-                                                    uint32_t* __restrict__ slots)
+                                                    uint32_t* __restrict__ slots, const int* __restrict__ dstat)
 {
+    if (dstat[GL_DS_PT_OVERFLOW]) return;
     const int patch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (patch >= g.npatch) return;
     const int4 pi = pinfo[patch];
@@ -160,8 +172,9 @@ template <int KIND, int C>
 __global__ void __launch_bounds__(256, C == 1 ? 3 : 2)
 k_patch_affinity(Geom g, const uint8_t* __restrict__ img, const float* __restrict__ sf, int p_pad, float a2, float b2,
                  const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots, __half* __restrict__ KB,
-                 float* __restrict__ partial /* [gridDim.x][1 + C][p_pad] */)
+                 float* __restrict__ partial /* [gridDim.x][1 + C][p_pad] */, const int* __restrict__ dstat)
 {
+    if (dstat[GL_DS_PT_OVERFLOW]) return;
     extern __shared__ float pa_smem[];
     constexpr int NS = 1 + C;
     float* cta_sum = pa_smem;                  // [NS][p_pad]
@@ -325,18 +338,48 @@ __global__ void __launch_bounds__(256) k_w_rows(const float* __restrict__ U, int
 // ---------------------------------------------------------------------------------------------
 // extrapolation + fused filter
 // ---------------------------------------------------------------------------------------------
+// contiguous global -> shared bulk copy (1-D TMA), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
 // One persistent CTA per SM; CTA b works on N tile nt = b % n_tiles of the patches b / n_tiles, + gridDim.x / n_tiles, ...: its
-// filter weights never change.  warp 0: TMA producer of the A tiles; warp 1: MMA issuer; warps 2-3: gather the W rows of the
-// patch's samples into the B slots (warp 2 allocates the tensor memory first); warps 4-11: epilogue, warp w drains TMEM lanes
-// 32 (w % 4) .. +31 (= 32 pixels of one patch row) and half of the accumulator's columns.
+// filter weights never change.  Roles (12 warps):
+//   warp 0      producer: one 8 KB bulk copy per A tile into a ring of SA slots
+//   warp 1      MMA issuer (one thread): per M tile one or two tcgen05.mma per slot block, commits that free the operand slots and
+//               announce the accumulator
+//   warps 2-3   gather the W rows of each patch's samples into the B slots (cp.async, MN-major SWIZZLE_128B image); warp 2 allocates
+//               the tensor memory first
+//   warps 4-11  epilogue: warp w drains TMEM lanes 32 (w % 4) .. +31 (= 32 pixels of one patch row) and half of the accumulator's
+//               columns, in chunks of 32 columns with the next chunk's tcgen05.ld in flight during the arithmetic; the accumulator
+//               goes back to the issuer before the last chunk is multiplied
+// What bounds it (profiles/r02_patch_timeline.md): with K loops of one or two steps the per-tile hand-overs -- every mbarrier wait,
+// tcgen05.mma, tcgen05.commit and tcgen05.ld round trip costs its thread 50-200 cycles -- not the tensor pipe (10 % busy), the
+// operand traffic or the epilogue's arithmetic.  Variants with two issuer threads, sixteen epilogue warps in two groups, operand
+// slots released by the epilogue, and 64-column loads were all measured slower or equal (same file).
+// Debug instrumentation of the kernel below (timeline of CTA 0, experiment switches) is compiled in only with -DGLB200_PT_DEBUG
+// (make PT_DEBUG=1): in the serial issuer loop even predicated-off clock reads cost ~10 % of the kernel.
+#ifdef GLB200_PT_DEBUG
+#define PT_PROF(cond, stmt) do { if (cond) { stmt; } } while (0)
+#define PT_DBG(bit) (dbg & (bit))
+#else
+#define PT_PROF(cond, stmt) do { (void)sizeof(cond); } while (0)
+#define PT_DBG(bit) false
+#endif
+
 template <int FC, int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots,
                  const __half* __restrict__ W, int m_pad, int n_tiles, const float* __restrict__ scales,
                  const float* __restrict__ fuse_w /* [m_pad][FC] */, float* __restrict__ zpart /* [2 n_tiles][m_rows][FC] */,
-                 int64_t m_rows, int* __restrict__ err)
+                 int64_t m_rows, int* __restrict__ err, long long* __restrict__ prof /* debug timeline of CTA 0, or null */,
+                 const int* __restrict__ dstat, int dbg /* experiments: bit 0 = no epilogue arithmetic, bit 1 = no zpart store */)
 {
     using namespace tc;
+    if (dstat[GL_DS_PT_OVERFLOW]) return;
     extern __shared__ uint8_t pn_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)pn_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -393,6 +436,10 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
+        // This thread is the serial part of the pipeline: every instruction in this loop is on the critical path (compiled-out debug
+        // predicates alone cost 10 %).  Measured orders (profiles/r02_patch_timeline.md): accumulator first, then operands, then the
+        // slot commits and the accumulator commit last is the fastest; waiting for the operands first, or announcing the
+        // accumulator before freeing the slots, was 20 % slower.
         if (lane == 0) {
             int stage = 0, bpos = 0, it = 0;
             uint32_t phase = 0, buses = 0;   // buses bit s: parity of the number of fills of B slot s consumed so far
@@ -401,12 +448,15 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                 const int4 pi = pinfo[patch];
                 const int py = patch / g.pcols;
                 const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
-                const bool resident = pi.y <= SB;
+                const bool resident = pi.y <= SB;      // the patch's W rows stay in their slots for all of its M tiles
                 const int b0 = bpos;
                 for (int mt = 0; mt < mtc; ++mt, ++it) {
                     const int acc = it & 1;
+                    const bool pf = prof && blockIdx.x == 0 && it < 64;
+                    PT_PROF(pf, prof[it * 8 + 0] = clock64());
                     mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1), err, 2);
                     tcgen05_fence_after();
+                    PT_PROF(pf, prof[it * 8 + 1] = clock64());
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                     for (int b = 0; b < pi.y; ++b) {
                         int bs;
@@ -415,19 +465,21 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                         mbar_wait(bar_afull + 8 * stage, phase, err, 3);
                         if (!resident || mt == 0) mbar_wait(bar_bfull + 8 * bs, (buses >> bs) & 1u, err, 6);
                         tcgen05_fence_after();
-                        const int kk = (pi.z - SLOTS * b) > 16 ? 2 : 1;
+                        PT_PROF(pf && b == 0, prof[it * 8 + 7] = clock64());
+                        const int kk = (pi.z - SLOTS * b) > 16 ? 2 : 1;     // a last block with at most 16 samples: one K step
                         const uint64_t da = make_smem_desc_k<32>(smem_u32(smem_a + stage * A_TILE_BYTES));
                         const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + bs * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
                         for (int k = 0; k < kk; ++k)
                             umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
-                        umma_commit(bar_aempty + 8 * stage);
-                        if (!resident || mt == mtc - 1) {
+                        umma_commit(bar_aempty + 8 * stage);   // frees the A slot when these MMAs retire
+                        if (!resident || mt == mtc - 1) {      // and the B slot after its last reader
                             umma_commit(bar_bempty + 8 * bs);
                             buses ^= 1u << bs;
                         }
                         if (++stage == SA) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(bar_tfull + 8 * acc);
+                    PT_PROF(pf, prof[it * 8 + 2] = clock64());
                 }
                 if (resident) { bpos = b0 + pi.y; if (bpos >= SB) bpos -= SB; }
             }
@@ -447,15 +499,40 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                 for (int b = 0; b < pi.y; ++b) {
                     mbar_wait(bar_bempty + 8 * bpos, ((bloads >> bpos) & 1u) ^ 1u, err, 5);
                     bloads ^= 1u << bpos;
-                    uint8_t* dst = smem_b + bpos * B_BLOCK_BYTES;
+                    const uint32_t dst_s = smem_u32(smem_b + bpos * B_BLOCK_BYTES);
                     const uint32_t* sl = slots + (size_t)(pi.x + b) * SLOTS;
-#pragma unroll 4
+                    if (PT_DBG(8)) {
+                        // (experiment) register-staged loads, eight rows in flight per thread
+                        uint8_t* dst = smem_b + bpos * B_BLOCK_BYTES;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            uint4 val[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int k = (half * 8 + j) * 2 + kh;
+                                const uint32_t s = __ldg(sl + k);
+                                val[j] = make_uint4(0, 0, 0, 0);
+                                if (s != 0xffffffffu && u * 8 < BN) val[j] = __ldg((const uint4*)(W + (size_t)s * m_pad + (size_t)nt * BN) + u);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int k = (half * 8 + j) * 2 + kh;
+                                *(uint4*)(dst + (u >> 3) * B_CHUNK_BYTES + k * 128 + (((u & 7) ^ (k & 7)) << 4)) = val[j];
+                            }
+                        }
+                    } else {
+                    // sixteen 16-byte cp.async per thread, all in flight at once (no registers hold the data); an empty slot and
+                    // the chunks beyond a narrow N tile are zero-filled (source size 0)
+#pragma unroll
                     for (int pass = 0; pass < SLOTS / 2; ++pass) {
                         const int k = pass * 2 + kh;
                         const uint32_t s = __ldg(sl + k);
-                        uint4 val = make_uint4(0, 0, 0, 0);
-                        if (s != 0xffffffffu && u * 8 < BN) val = __ldg((const uint4*)(W + (size_t)s * m_pad + (size_t)nt * BN) + u);
-                        *(uint4*)(dst + (u >> 3) * B_CHUNK_BYTES + k * 128 + (((u & 7) ^ (k & 7)) << 4)) = val;
+                        const bool live = s != 0xffffffffu && u * 8 < BN;
+                        const __half* src = W + (size_t)(live ? s : 0) * m_pad + (size_t)nt * BN + (live ? u * 8 : 0);
+                        const uint32_t d = dst_s + (uint32_t)((u >> 3) * B_CHUNK_BYTES + k * 128 + (((u & 7) ^ (k & 7)) << 4));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(live ? 16 : 0) : "memory");
+                    }
+                    asm volatile("cp.async.wait_all;" ::: "memory");
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -476,8 +553,11 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
             const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
             for (int mt = 0; mt < mtc; ++mt, ++it) {
                 const int acc = it & 1;
+                const bool pf = prof && blockIdx.x == 0 && it < 64 && warp == 4 && lane == 0;
+                PT_PROF(pf, prof[it * 8 + 3] = clock64());
                 mbar_wait(bar_tfull + 8 * acc, (uint32_t)((it >> 1) & 1), err, 4);
                 tcgen05_fence_after();
+                PT_PROF(pf, prof[it * 8 + 4] = clock64());
                 const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + (BN >= 128 ? share * COLS : 0));
                 float dot[FC][8];
 #pragma unroll
@@ -496,8 +576,9 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                         tcgen05_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                        PT_PROF(pf, prof[it * 8 + 5] = clock64());
                     }
-                    if (active) {
+                    if (active && !PT_DBG(1)) {
                         const uint32_t wv = wbase + (uint32_t)(32 * k * FC * 4);
 #pragma unroll
                         for (int g8 = 0; g8 < 4; ++g8) {
@@ -522,7 +603,7 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                 }
                 // this thread's pixel: tile pixel wq * 32 + lane -> patch row 2 mt + (wq >> 1), column (wq & 1) * 32 + lane
                 const int r = py * PR + 2 * mt + (wq >> 1), c = pxi * PW + (wq & 1) * 32 + lane;
-                if (r < g.band_rows && c < g.width) {
+                if (r < g.band_rows && c < g.width && !PT_DBG(2)) {
                     const int64_t row = (int64_t)r * g.width + c;
                     const int part = nt * 2 + share;
 #pragma unroll
@@ -530,6 +611,7 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                         zpart[((size_t)part * m_rows + row) * FC + q] =
                             ((dot[q][0] + dot[q][1]) + (dot[q][2] + dot[q][3])) + ((dot[q][4] + dot[q][5]) + (dot[q][6] + dot[q][7]));
                 }
+                PT_PROF(pf, prof[it * 8 + 6] = clock64());
             }
         }
     }
@@ -600,7 +682,8 @@ static int launch_patch_affinity(gl_ctx* ctx, const pt::Geom& g, double h_loc, d
     StageTimer kt(ctx, GL_T_K_AFFINITY_B);
     pt::k_patch_affinity<KIND, C><<<grid, 256, smem, ctx->stream>>>(g, (const uint8_t*)ctx->img->ptr, sf, p_pad, (float)(-log2e / (h_loc * h_loc)),
                                                                    (float)(-log2e / (h_val * h_val)), (const int4*)KB->pt_info->ptr,
-                                                                   (const uint32_t*)KB->pt_slots->ptr, (__half*)KB->pt_buf->ptr, partial);
+                                                                   (const uint32_t*)KB->pt_slots->ptr, (__half*)KB->pt_buf->ptr, partial,
+                                                                   (const int*)ctx->dstat->ptr);
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;
 }
@@ -627,25 +710,34 @@ int gl_patch_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat*
         const unsigned wgrid = (unsigned)ceil_div(g.npatch, 8);
         pt::k_patch_count<<<wgrid, 256, 0, ctx->stream>>>(g, (const uint32_t*)ctx->samples->ptr, p, (int4*)KB->pt_info->ptr);
         ctx->launches++;
-        pt::k_patch_scan<<<1, 1024, 0, ctx->stream>>>(g, g.npatch, (int4*)KB->pt_info->ptr, (int*)total->ptr);
+        // Storage is sized by the number of slot blocks, which only the device knows.  A stand-alone gl_affinity reads it back (one
+        // small round trip); inside gl_run_resident the count of the last run with the same geometry, sample count and reach, plus a
+        // quarter, is set aside without asking -- the scan kernel checks it and raises the overflow word if it was not enough.
+        const int64_t key[5] = {g.width, g.band_rows, g.row0, p, (int64_t)g.rc2};
+        const bool have_cap = ctx->async_mode && ctx->pt_cap_blocks > 0 && !memcmp(key, ctx->pt_cap_key, sizeof(key));
+        pt::k_patch_scan<<<1, 1024, 0, ctx->stream>>>(g, g.npatch, (int4*)KB->pt_info->ptr, (int*)total->ptr, have_cap ? ctx->pt_cap_blocks : 0,
+                                                      (int*)ctx->dstat->ptr);
         ctx->launches++;
-        // the storage is sized by the number of blocks: one small read-back (the only host round trip of the stage)
-        GL_BREAK(rc, gl_ensure_pinned(ctx, 64));
-        GL_CUDA_BREAK(rc, cudaMemcpyAsync(ctx->pinned, total->ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        GL_CUDA_BREAK(rc, cudaStreamSynchronize(ctx->stream));
-        const int64_t blocks = *(const int*)ctx->pinned;
-        KB->pt_ksteps = (int64_t) * (const unsigned long long*)((const int*)ctx->pinned + 2);
-        if (blocks <= 0 || blocks * pt::G * 128 >= 0x7fffffffll) {
-            gl_set_error("affinity: %lld sample blocks do not fit 32-bit tile coordinates", (long long)blocks);
-            rc = GL_ERR_UNSUPPORTED;
-            break;
+        int64_t blocks = ctx->pt_cap_blocks;
+        if (!have_cap) {
+            GL_CUDA_BREAK(rc, cudaMemcpyAsync(ctx->pinned, total->ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            GL_CUDA_BREAK(rc, cudaStreamSynchronize(ctx->stream));
+            blocks = *(const int*)ctx->pinned;
+            KB->pt_ksteps = (int64_t) * (const unsigned long long*)((const int*)ctx->pinned + 2);
+            if (blocks <= 0 || (blocks + blocks / 4 + 64) * pt::G * 128 >= 0x7fffffffll) {
+                gl_set_error("affinity: %lld sample blocks do not fit 32-bit tile indices", (long long)blocks);
+                rc = GL_ERR_UNSUPPORTED;
+                break;
+            }
+            ctx->pt_cap_blocks = blocks + blocks / 4 + 64;
+            memcpy(ctx->pt_cap_key, key, sizeof(key));
         }
-        KB->pt_blocks = blocks;
+        KB->pt_blocks = blocks;          // (with have_cap: the capacity; the exact count is in the status block)
         KB->pt_npatch = g.npatch;
         GL_BREAK(rc, gl_alloc(ctx, sizeof(uint32_t) * (size_t)blocks * pt::SLOTS, &KB->pt_slots));
         GL_BREAK(rc, gl_alloc(ctx, (size_t)blocks * pt::G * pt::A_TILE_BYTES, &KB->pt_buf));
         pt::k_patch_fill<<<wgrid, 256, 0, ctx->stream>>>(g, (const uint32_t*)ctx->samples->ptr, p, (const int4*)KB->pt_info->ptr,
-                                                        (uint32_t*)KB->pt_slots->ptr);
+                                                        (uint32_t*)KB->pt_slots->ptr, (const int*)ctx->dstat->ptr);
         ctx->launches++;
         GL_BREAK(rc, gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_pad, &sf));
         pt::k_patch_sample_features<<<(unsigned)ceil_div(p_pad, 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->img->ptr,
@@ -694,22 +786,28 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
     GL_REQUIRE(C == 1 || C == 3, "nystroem(patch): 1 or 3 channels");
     const int BN = m_pad < 256 ? m_pad : 256;
     const int n_tiles = m_pad / BN;
-    gl_buf *Wr = nullptr, *err = nullptr;
+    gl_buf *Wr = nullptr, *err = nullptr, *prof = nullptr;
+    const bool want_prof = getenv("GLB200_PT_PROF") != nullptr;   // debug: timeline of CTA 0's first tiles on stderr
+    const int dbg = getenv("GLB200_PT_DBG") ? atoi(getenv("GLB200_PT_DBG")) : 0;
     int rc = GL_OK;
     do {
+        if (want_prof) {
+            GL_BREAK(rc, gl_alloc(ctx, sizeof(long long) * 64 * 9, &prof));
+            GL_CUDA_BREAK(rc, cudaMemsetAsync(prof->ptr, 0, sizeof(long long) * 64 * 9, ctx->stream));
+        }
         GL_BREAK(rc, gl_alloc(ctx, sizeof(__half) * (size_t)p_pad * m_pad, &Wr));
         GL_BREAK(rc, gl_alloc(ctx, sizeof(int) * 4, &err));
         GL_CUDA_BREAK(rc, cudaMemsetAsync(err->ptr, 0, sizeof(int) * 4, ctx->stream));
         dim3 wg((unsigned)ceil_div(p_pad, 32), (unsigned)ceil_div(m_pad, 32));
         pt::k_w_rows<<<wg, 256, 0, ctx->stream>>>(U, ldU, p, m, p_pad, m_pad, mu_inv, (const double*)L_B->dscale->ptr, scales, (__half*)Wr->ptr);
         ctx->launches++;
-        CUtensorMap map_a;
-        GL_BREAK(rc, make_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, L_B->pt_buf->ptr, (uint64_t)L_B->pt_blocks * pt::G * 128, pt::SLOTS,
-                                 pt::SLOTS, pt::SLOTS, 128, CU_TENSOR_MAP_SWIZZLE_64B));
         int grid = ctx->sm_count / n_tiles * n_tiles;
         if (grid < n_tiles) grid = n_tiles;
         if (grid / n_tiles > g.npatch) grid = g.npatch * n_tiles;
         fuse->parts = 2 * n_tiles;
+        CUtensorMap map_a;
+        GL_BREAK(rc, make_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, L_B->pt_buf->ptr, (uint64_t)L_B->pt_blocks * pt::G * 128, pt::SLOTS,
+                                 pt::SLOTS, pt::SLOTS, 128, CU_TENSOR_MAP_SWIZZLE_64B));
         const int SM = pt::nystroem_smem(C);
         StageTimer kt(ctx, GL_T_K_GEMM);
 #define PT_LAUNCH(FC, BNN)                                                                                                          \
@@ -718,7 +816,9 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
         pt::k_patch_nystroem<FC, BNN><<<grid, pt::THREADS, SM, ctx->stream>>>(map_a, g, (const int4*)L_B->pt_info->ptr,             \
                                                                               (const uint32_t*)L_B->pt_slots->ptr, (const __half*)Wr->ptr, \
                                                                               m_pad, n_tiles, scales, fuse->w, fuse->zpart,         \
-                                                                              L_B->local_rows, (int*)err->ptr);                     \
+                                                                              L_B->local_rows, (int*)err->ptr,                      \
+                                                                              prof ? (long long*)prof->ptr : nullptr,               \
+                                                                              (const int*)ctx->dstat->ptr, dbg);                    \
     } while (0)
         if (C == 1 && BN == 256) PT_LAUNCH(1, 256);
         else if (C == 1 && BN == 128) PT_LAUNCH(1, 128);
@@ -730,7 +830,19 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
         if (rc != GL_OK) break;
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { gl_set_error("nystroem(patch): kernel launch failed"); rc = GL_ERR_CUDA; }
+        if (prof) {
+            static long long h[64 * 9];
+            cudaMemcpyAsync(h, prof->ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            fprintf(stderr, "[pt prof] tile: mma(wait_acc_free, wait_operands, issue+commits) | epi(idle_before, wait_full, load, fma) | cycles per tile\n");
+            for (int t = 8; t < 40; ++t) {
+                const long long* r = h + t * 8;
+                fprintf(stderr, "[pt prof] %2d: mma %5lld %5lld %5lld | epi %5lld %5lld %5lld %5lld | per tile %5lld\n", t, r[1] - r[0], r[7] - r[1],
+                        r[2] - r[7], r[3] - (r - 8)[6], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[6] - (r - 8)[6]);
+            }
+        }
     } while (0);
+    if (prof) gl_buf_release(prof);
     if (Wr) gl_buf_release(Wr);
     if (err) gl_buf_release(err);
     return rc;

@@ -250,11 +250,22 @@ int gl_impl_sampling_random(gl_ctx* ctx, unsigned requested, uint32_t seed, unsi
         return GL_ERR_UNSUPPORTED;
     }
     GL_CHECK(set_sample_buffer(ctx, requested));
+    const size_t smem = RS_MAXCAND * (8 + 4 + 2 + 2);
+    GL_CUDA_CHECK(cudaFuncSetAttribute(k_random_sampling, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ctx->async_mode) {
+        // inside gl_run_resident: the kernel's status word goes to the deferred status block, nobody waits for it here; the host
+        // mirror of the indices is fetched only if somebody asks (gl_host_samples)
+        int* st = (int*)ctx->dstat->ptr + GL_DS_SAMPLING;
+        GL_CUDA_CHECK(cudaMemsetAsync(st, 0xff, sizeof(int), ctx->stream));
+        k_random_sampling<<<1, RS_THREADS, smem, ctx->stream>>>(seed, (uint32_t)ctx->n, requested, (uint32_t)ctx->p_pad,
+                                                               (uint32_t*)ctx->samples->ptr, st);
+        GL_LAUNCH_CHECK(ctx);
+        if (actual) *actual = requested;
+        return GL_OK;
+    }
     gl_buf* st = nullptr;
     GL_CHECK(gl_alloc(ctx, sizeof(int), &st));
     GL_CUDA_CHECK(cudaMemsetAsync(st->ptr, 0xff, sizeof(int), ctx->stream));
-    const size_t smem = RS_MAXCAND * (8 + 4 + 2 + 2);
-    GL_CUDA_CHECK(cudaFuncSetAttribute(k_random_sampling, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_random_sampling<<<1, RS_THREADS, smem, ctx->stream>>>(seed, (uint32_t)ctx->n, requested, (uint32_t)ctx->p_pad,
                                                            (uint32_t*)ctx->samples->ptr, (int*)st->ptr);
     GL_LAUNCH_CHECK(ctx);

@@ -87,18 +87,14 @@ def test_c4_properties(ctx, base):
 def test_c4_variants_agree(ctx, base):
     ref = base["z"].astype(np.float64)
     img = ctx.get_image().astype(np.float64)
-    ctx.set_option("keep_phi", 1)           # Phi written to HBM as well (default: consumed in the GEMM epilogue only): identical z
-    try:
-        r = _run(ctx)
-    finally:
-        ctx.set_option("keep_phi", 0)
-    assert np.array_equal(r["z"], base["z"])
-    for key, val in (("fuse_filter", 0), ("kb_cutoff", 0)):
+    # keep_phi=1: Phi written to HBM as well, which takes the blocked layout of K_B (default: patch layout, Phi consumed in the
+    # epilogue only); kb_layout=blocked: the blocked layout with the fused filter; fuse_filter=0: stages apart; kb_cutoff=0: dense K_B
+    for key, val, back in (("keep_phi", 1, 0), ("kb_layout", "blocked", "patch"), ("fuse_filter", 0, 1), ("kb_cutoff", 0, 1)):
         ctx.set_option(key, val)
         try:
             r = _run(ctx)
         finally:
-            ctx.set_option(key, 1)
+            ctx.set_option(key, back)
         assert _rel(r["z"], ref) < 2e-5, key
         assert _rel(r["z"] - img, ref - img) < 2e-3, key
         assert np.max(np.abs(r["mu"] - base["mu"]) / base["mu"]) < 1e-6, key
