@@ -434,12 +434,37 @@ def main():
     aff_ext_tf_dense_equiv = (f_aff + f_ext) / t_ae / 1e12
 
     # ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
-    NCU_TRAFFIC = {("c4", 1, "nostore"): (NOSTORE_TRAFFIC, "profiles/r01_ncu_full_c4_v6.txt"),
+    NCU_TRAFFIC = {("c4", 1, "patch"): (0.5358e9 + 0.2434e9, "profiles/r02_ncu_patch_c4.txt"),
+                   ("c4", 1, "nostore"): (NOSTORE_TRAFFIC, "profiles/r01_ncu_full_c4_v6.txt"),
                    ("c4", 1, "stored"): (19.14e9, "profiles/r01_ncu_full_c4_v5.txt"),
                    ("c4", 1, "dense"): (33.9e9, "profiles/r01_ncu_full_c4.txt")}
     kept = stored_pairs / max(1, dense_pairs)
     roof_stored = None
-    if kept < 0.5:
+    if kb_layout == "patch":
+        # Patch layout (csrc/patch.cu): per 64 x 16 pixel patch a gathered list of the samples in reach (one block of 32 slots almost
+        # everywhere), 1-2 tcgen05.mma 128 x 256 x 16 per accumulator tile, fused filter epilogue.  Neither roofline of the contract
+        # bounds this kernel: it is held by the serial hand-over chain of a tile (profiles/r02_patch_timeline.md).  It is reported on
+        # the tensor roofline with the MMA work actually issued; `speed_of_light` lists the three resource bounds beside it.
+        tr = NCU_TRAFFIC.get((args.workload, world, "patch"))
+        fma = band_px * m_pad * channels                       # fp32 FMAs of the fused filter epilogue (one per Phi element and channel)
+        fma_peak = 85.3 * 148 * 1.965e9                        # measured: 85.3 FMA/clock/SM with FFMA2 (tools/probe_tmem.cu), 148 SMs, 1965 MHz
+        sol = dict(tensor_ms=f_ext_exec / (peaks["tf_burst"] * 1e12) * 1e3, hbm_ms=gemm_bytes / (peaks["hbm"] * 1e9) * 1e3,
+                   epilogue_fma_ms=fma / fma_peak * 1e3)
+        sol["bound_ms"] = max(sol.values())
+        sol["frac_of_bound"] = sol["bound_ms"] / med["k_gemm"] if med["k_gemm"] > 0 else 0.0
+        sol["note"] = ("lower bounds of this kernel's time from its three resources: tensor pipe (issued MMA flops / measured burst peak), HBM "
+                       "(K_B tiles + row partials / measured copy bandwidth), CUDA cores (one fp32 FMA per Phi element for the fused filter / "
+                       "measured 85.3 FMA per clock per SM: three register-pair operands per FFMA2 make the register file the limit)")
+        roof = dict(kernel="k_patch_nystroem (Nystroem extrapolation over the K_B patch tiles on tcgen05, filter fused, Phi not stored)",
+                    bound="tensor", achieved=gemm_tf_exec, peak=peaks["tf_burst"], unit="TFLOP/s", frac=gemm_tf_exec / peaks["tf_burst"],
+                    traffic=tr[0] if tr else None, traffic_source=tr[1] if tr else None,
+                    peak_source=peaks["source"] + " bf16 burst (a ~1 ms kernel at full clocks, no power cap)", ms=med["k_gemm"],
+                    flop=f_ext_exec, flop_dense_equivalent=f_ext, algorithmic_bytes=gemm_bytes, hbm_gbs=gemm_gbs,
+                    speed_of_light=sol,
+                    note="flop = MMA work issued (2 x multiplied (pixel, slot) pairs x m_pad); round 1's blocked layout issued 5.5x as much "
+                         "for the same result (1.80e12 flop in 1.67 ms = 0.65 of peak).  The kernel is latency-bound: K loops of one or two "
+                         "steps leave nothing to hide the per-tile hand-overs behind (tensor pipe 10 % busy, ncu)")
+    elif kept < 0.5:
         # With the spatial cutoff and Phi not stored, the GEMM moves little (the stored K_B blocks in, row partials out) and is
         # bound by the tensor work it ISSUES: every stored 64-slot block is multiplied whole, padding included.
         tr = NCU_TRAFFIC.get((args.workload, world, "nostore"))

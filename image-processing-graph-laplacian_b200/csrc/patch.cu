@@ -97,8 +97,16 @@ __global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* _
     }
     part[threadIdx.x] = s;
     __syncthreads();
-    atomicAdd(&ksum, ks);
-    atomicMax(&max_nb, nbmax);
+    // (one shared-memory atomic per warp: 1 024 threads on one 64-bit word is a 50 us CAS queue)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ks += __shfl_xor_sync(0xffffffffu, ks, o);
+        nbmax = max(nbmax, __shfl_xor_sync(0xffffffffu, nbmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&ksum, ks);
+        atomicMax(&max_nb, nbmax);
+    }
     for (int o = 1; o < 1024; o <<= 1) {
         const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
         __syncthreads();
