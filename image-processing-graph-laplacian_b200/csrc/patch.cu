@@ -35,7 +35,7 @@ constexpr int B_BLOCK_BYTES = SLOTS * 256 * 2;    // 16 KB: 4 chunks of [32 K ro
 constexpr int B_CHUNK_BYTES = SLOTS * 128;        // 4 KB
 constexpr int SA = 8;             // A ring stages
 constexpr int SB = 4;             // B block slots
-constexpr int EPI_WARPS = 8;       // epilogue warps: 4 TMEM lane quarters x 2 column shares
+constexpr int EPI_WARPS = 8;       // epilogue warps per group: 4 TMEM lane quarters x 2 column shares
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 
 struct Geom {
@@ -396,17 +396,22 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
     const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + SA);
     const uint32_t bar_bfull = smem_u32(bars + 2 * SA), bar_bempty = smem_u32(bars + 2 * SA + SB);
     const uint32_t bar_tfull = smem_u32(bars + 2 * SA + 2 * SB), bar_tempty = smem_u32(bars + 2 * SA + 2 * SB + 2);
-    static_assert(2 * SA + 2 * SB + 4 + 1 <= 32, "barrier block is 256 bytes");
+    static_assert(2 * SA + 2 * SB + 4 + 1 <= 64, "barrier block is 512 bytes");
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * SA + 2 * SB + 4);
-    float* w_s = (float*)(bars + 32);   // [BN][FC] filter weights of this CTA's N tile, times the GEMM's output scale
+    float* w_s = (float*)(bars + 64);   // [BN][FC] filter weights of this CTA's N tile, times the GEMM's output scale
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = blockIdx.x % n_tiles, first_patch = blockIdx.x / n_tiles, patch_step = gridDim.x / n_tiles;
+    // Two issuer threads and two epilogue groups (one of each per accumulator) while every patch's W rows stay resident (at most SB
+    // slot blocks per patch).  With more, a tile's operands make more than one lap of the rings, and an issuer a tile ahead of the
+    // other would wait on a barrier phase two laps away, which a parity wait cannot tell from the current one: issuer 0 then works alone.
+    const bool two = dstat[GL_DS_PT_MAXNB] <= SB;
 
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-        for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, 2); mbar_init(bar_bempty + 8 * s, 1); }
+        // a B slot is released by TWO arrivals: a patch's last two tiles run on different accumulators under different issuers
+        for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 2); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -442,60 +447,73 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                     }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        // This thread is the serial part of the pipeline: every instruction in this loop is on the critical path (compiled-out debug
-        // predicates alone cost 10 %).  Measured orders (profiles/r02_patch_timeline.md): accumulator first, then operands, then the
-        // slot commits and the accumulator commit last is the fastest; waiting for the operands first, or announcing the
-        // accumulator before freeing the slots, was 20 % slower.
+    } else if (warp == 1 || warp == 3) {
+        // ===== MMA issuers =====
+        // These threads are the serial part of the pipeline: every instruction in this loop is on the critical path (compiled-out debug
+        // predicates alone cost 10 %).  Order measured fastest: accumulator, operands, MMAs, slot commits, accumulator commit.
         if (lane == 0) {
+            const int me = warp == 1 ? 0 : 1;
             int stage = 0, bpos = 0, it = 0;
             uint32_t phase = 0, buses = 0;   // buses bit s: parity of the number of fills of B slot s consumed so far
             const uint32_t idesc = make_idesc(BLOCK_M, BN, 0) | (1u << 16);   // B is MN-major
+            int4 pi_next = first_patch < g.npatch ? pinfo[first_patch] : make_int4(0, 1, 0, 0);
             for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
-                const int4 pi = pinfo[patch];
+                const int4 pi = pi_next;               // (fetched a patch ahead: an L2 round trip in this loop is 5 % of a patch's time)
+                if (patch + patch_step < g.npatch) pi_next = pinfo[patch + patch_step];
                 const int py = patch / g.pcols;
                 const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
                 const bool resident = pi.y <= SB;      // the patch's W rows stay in their slots for all of its M tiles
                 const int b0 = bpos;
+                bool b_seen = false;                   // resident W rows: waited for once per patch by each issuer
+                // resident W rows go back after the patch's last two tiles, one arrival from each (both from the one tile of a 1-tile
+                // patch, and both from issuer 0 when it works alone)
+                const int my_last = !two ? mtc - 1 : ((((it + mtc - 1) & 1) == me) ? mtc - 1 : mtc - 2);
                 for (int mt = 0; mt < mtc; ++mt, ++it) {
                     const int acc = it & 1;
-                    const bool pf = prof && blockIdx.x == 0 && it < 64;
-                    PT_PROF(pf, prof[it * 8 + 0] = clock64());
-                    mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1), err, 2);
-                    tcgen05_fence_after();
-                    PT_PROF(pf, prof[it * 8 + 1] = clock64());
+                    const bool mine = two ? acc == me : me == 0;
+                    const bool pf = prof && blockIdx.x == 0 && it < 64 && mine;
+                    if (mine) {
+                        PT_PROF(pf, prof[it * 8 + 0] = clock64());
+                        mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1), err, 2);
+                        tcgen05_fence_after();
+                        PT_PROF(pf, prof[it * 8 + 1] = clock64());
+                    }
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                     for (int b = 0; b < pi.y; ++b) {
                         int bs;
                         if (resident) { bs = b0 + b; if (bs >= SB) bs -= SB; }
                         else { bs = bpos; if (++bpos == SB) bpos = 0; }
-                        mbar_wait(bar_afull + 8 * stage, phase, err, 3);
-                        if (!resident || mt == 0) mbar_wait(bar_bfull + 8 * bs, (buses >> bs) & 1u, err, 6);
-                        tcgen05_fence_after();
-                        PT_PROF(pf && b == 0, prof[it * 8 + 7] = clock64());
-                        const int kk = (pi.z - SLOTS * b) > 16 ? 2 : 1;     // a last block with at most 16 samples: one K step
-                        const uint64_t da = make_smem_desc_k<32>(smem_u32(smem_a + stage * A_TILE_BYTES));
-                        const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + bs * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
-                        for (int k = 0; k < kk; ++k)
-                            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
-                        umma_commit(bar_aempty + 8 * stage);   // frees the A slot when these MMAs retire
-                        if (!resident || mt == mtc - 1) {      // and the B slot after its last reader
-                            umma_commit(bar_bempty + 8 * bs);
-                            buses ^= 1u << bs;
+                        if (mine) {
+                            mbar_wait(bar_afull + 8 * stage, phase, err, 3);
+                            if (!resident || !b_seen) mbar_wait(bar_bfull + 8 * bs, (buses >> bs) & 1u, err, 6);
+                            tcgen05_fence_after();
+                            PT_PROF(pf && b == 0, prof[it * 8 + 7] = clock64());
+                            const int kk = (pi.z - SLOTS * b) > 16 ? 2 : 1;     // a last block with at most 16 samples: one K step
+                            const uint64_t da = make_smem_desc_k<32>(smem_u32(smem_a + stage * A_TILE_BYTES));
+                            const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + bs * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
+                            for (int k = 0; k < kk; ++k)
+                                umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
+                            umma_commit(bar_aempty + 8 * stage);   // frees the A slot when these MMAs retire
+                            if (!resident || mt == my_last) {
+                                umma_commit(bar_bempty + 8 * bs);
+                                if (!resident || !two || mtc == 1) umma_commit(bar_bempty + 8 * bs);
+                            }
                         }
+                        if (!resident || mt == mtc - 1) buses ^= 1u << bs;
                         if (++stage == SA) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(bar_tfull + 8 * acc);
-                    PT_PROF(pf, prof[it * 8 + 2] = clock64());
+                    if (mine) {
+                        b_seen = true;
+                        umma_commit(bar_tfull + 8 * acc);
+                        PT_PROF(pf, prof[it * 8 + 2] = clock64());
+                    }
                 }
                 if (resident) { bpos = b0 + pi.y; if (bpos >= SB) bpos -= SB; }
             }
         }
-    } else if (warp < 4) {
+    } else if (warp == 2) {
         // ===== B gather: rows of W for the slots of a block, written in the MN-major SWIZZLE_128B layout =====
-        const int t = threadIdx.x - 64;          // 0..63
-        const int u = t & 31, kh = t >> 5;       // 16-byte unit of the 512-byte row part, which of the two rows of a pass
+        const int u = lane;                      // 16-byte unit of the 512-byte row part of this N tile
         int bpos = 0;
         uint32_t bloads = 0;
         for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
@@ -508,40 +526,18 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                     mbar_wait(bar_bempty + 8 * bpos, ((bloads >> bpos) & 1u) ^ 1u, err, 5);
                     bloads ^= 1u << bpos;
                     const uint32_t dst_s = smem_u32(smem_b + bpos * B_BLOCK_BYTES);
-                    const uint32_t* sl = slots + (size_t)(pi.x + b) * SLOTS;
-                    if (PT_DBG(8)) {
-                        // (experiment) register-staged loads, eight rows in flight per thread
-                        uint8_t* dst = smem_b + bpos * B_BLOCK_BYTES;
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            uint4 val[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int k = (half * 8 + j) * 2 + kh;
-                                const uint32_t s = __ldg(sl + k);
-                                val[j] = make_uint4(0, 0, 0, 0);
-                                if (s != 0xffffffffu && u * 8 < BN) val[j] = __ldg((const uint4*)(W + (size_t)s * m_pad + (size_t)nt * BN) + u);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int k = (half * 8 + j) * 2 + kh;
-                                *(uint4*)(dst + (u >> 3) * B_CHUNK_BYTES + k * 128 + (((u & 7) ^ (k & 7)) << 4)) = val[j];
-                            }
-                        }
-                    } else {
-                    // sixteen 16-byte cp.async per thread, all in flight at once (no registers hold the data); an empty slot and
+                    const uint32_t my_slot = __ldg(slots + (size_t)(pi.x + b) * SLOTS + lane);
+                    // thirty-two 16-byte cp.async per thread, all in flight at once (no registers hold the data); an empty slot and
                     // the chunks beyond a narrow N tile are zero-filled (source size 0)
-#pragma unroll
-                    for (int pass = 0; pass < SLOTS / 2; ++pass) {
-                        const int k = pass * 2 + kh;
-                        const uint32_t s = __ldg(sl + k);
+#pragma unroll 8
+                    for (int k = 0; k < SLOTS; ++k) {
+                        const uint32_t s = __shfl_sync(0xffffffffu, my_slot, k);
                         const bool live = s != 0xffffffffu && u * 8 < BN;
                         const __half* src = W + (size_t)(live ? s : 0) * m_pad + (size_t)nt * BN + (live ? u * 8 : 0);
                         const uint32_t d = dst_s + (uint32_t)((u >> 3) * B_CHUNK_BYTES + k * 128 + (((u & 7) ^ (k & 7)) << 4));
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(live ? 16 : 0) : "memory");
                     }
                     asm volatile("cp.async.wait_all;" ::: "memory");
-                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_bfull + 8 * bpos);
@@ -550,11 +546,37 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
         }
     } else {
         // ===== epilogue =====
+        // The accumulator is read out in ONE go -- all of this warp's columns requested back to back, one wait -- and handed back
+        // before any arithmetic: the time from "accumulator full" to "accumulator free" is on the serial chain of the tile
+        // (profiles/r02_patch_timeline.md), four waited-for tcgen05.ld round trips with the arithmetic between them were most of it.
+        // (Three channels need the registers for the dots: they keep the chunked order.)
         const int wq = warp & 3, share = (warp - 4) >> 2;
         constexpr int COLS = BN >= 128 ? BN / 2 : BN;          // columns per share (BN = 64: share 0 takes them all)
         const bool active = BN >= 128 || share == 0;
         constexpr int NCH = COLS / 32;
+        constexpr bool AT_ONCE = FC == 1;
         const uint32_t wbase = smem_u32(w_s) + (uint32_t)((BN >= 128 ? share * COLS : 0) * FC * 4);
+        auto mul32 = [&](const uint32_t (&v)[32], int k, float (&dot)[FC][8]) {
+            const uint32_t wv = wbase + (uint32_t)(32 * k * FC * 4);
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+                float wr[8 * FC];
+#pragma unroll
+                for (int q = 0; q < 2 * FC; ++q) lds_f4(wv + (uint32_t)((g8 * 2 * FC + q) * 16), &wr[4 * q]);
+                if (FC == 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2)
+                        ffma2(dot[0][i], dot[0][i + 1], __uint_as_float(v[8 * g8 + i]), __uint_as_float(v[8 * g8 + i + 1]), wr[i], wr[i + 1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float val = __uint_as_float(v[8 * g8 + i]);
+#pragma unroll
+                        for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
+                    }
+                }
+            }
+        };
         int it = 0;
         for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
             const int py = patch / g.pcols, pxi = patch - py * g.pcols;
@@ -572,41 +594,37 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                 for (int q = 0; q < FC; ++q)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dot[q][i] = 0.f;
-                uint32_t v[2][32];
-                if (active) tmem_ld_32x32b_x32(t_row, v[0]);
+                if (AT_ONCE) {
+                    uint32_t v[NCH][32];
+                    if (active) {
 #pragma unroll
-                for (int k = 0; k < NCH; ++k) {
-                    tmem_ld_wait();
-                    if (k + 1 < NCH) {
-                        if (active) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * (k + 1)), v[(k + 1) & 1]);
-                    } else {
-                        // every tcgen05.ld of this accumulator has completed: hand it back before the last chunk's arithmetic
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-                        PT_PROF(pf, prof[it * 8 + 5] = clock64());
+                        for (int k = 0; k < NCH; ++k) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * k), v[k]);
                     }
+                    tmem_ld_wait();
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    PT_PROF(pf, prof[it * 8 + 5] = clock64());
                     if (active && !PT_DBG(1)) {
-                        const uint32_t wv = wbase + (uint32_t)(32 * k * FC * 4);
 #pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
-                            float wr[8 * FC];
+                        for (int k = 0; k < NCH; ++k) mul32(v[k], k, dot);
+                    }
+                } else {
+                    uint32_t v[2][32];
+                    if (active) tmem_ld_32x32b_x32(t_row, v[0]);
 #pragma unroll
-                            for (int q = 0; q < 2 * FC; ++q) lds_f4(wv + (uint32_t)((g8 * 2 * FC + q) * 16), &wr[4 * q]);
-                            if (FC == 1) {
-#pragma unroll
-                                for (int i = 0; i < 8; i += 2)
-                                    ffma2(dot[0][i], dot[0][i + 1], __uint_as_float(v[k & 1][8 * g8 + i]), __uint_as_float(v[k & 1][8 * g8 + i + 1]),
-                                          wr[i], wr[i + 1]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float val = __uint_as_float(v[k & 1][8 * g8 + i]);
-#pragma unroll
-                                    for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
-                                }
-                            }
+                    for (int k = 0; k < NCH; ++k) {
+                        tmem_ld_wait();
+                        if (k + 1 < NCH) {
+                            if (active) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * (k + 1)), v[(k + 1) & 1]);
+                        } else {
+                            // every tcgen05.ld of this accumulator has completed: hand it back before the last chunk's arithmetic
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                            PT_PROF(pf, prof[it * 8 + 5] = clock64());
                         }
+                        if (active && !PT_DBG(1)) mul32(v[k & 1], k, dot);
                     }
                 }
                 // this thread's pixel: tile pixel wq * 32 + lane -> patch row 2 mt + (wq >> 1), column (wq & 1) * 32 + lane
@@ -632,7 +650,7 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
     }
 }
 
-constexpr int nystroem_smem(int fc) { return SA * A_TILE_BYTES + SB * B_BLOCK_BYTES + 256 + 256 * fc * 4 + 1024; }
+constexpr int nystroem_smem(int fc) { return SA * A_TILE_BYTES + SB * B_BLOCK_BYTES + 512 + 256 * fc * 4 + 1024; }
 
 // K_B from the patch layout to dense fp64 [band pixels][p] in the caller's sample order (dst zeroed beforehand)
 __global__ void k_patch_to_f64(Geom g, const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots, const __half* __restrict__ KB, int p,
