@@ -255,9 +255,9 @@ void gl_comm_destroy(gl_ctx* ctx);
 bool gl_patch_applicable(const gl_ctx* ctx, int kind);
 int gl_patch_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat* KB);
 int gl_patch_download(gl_ctx* ctx, const gl_mat* KB, double scale, double* dst_dev);
-struct gl_gemm_fuse;
+bool gl_patch_nystroem_fits(int m, int C);
 int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int ldU, int m, const double* mu_inv, const float* scales,
-                             gl_gemm_fuse* fuse);
+                             const float* w, int C, int clip_low, float* z, uint8_t* z8);
 // computes the blocked storage of a K_B handle that holds the patch layout only (same image and samples required)
 int gl_kb_require_blocked(gl_ctx* ctx, gl_mat* KB);
 
@@ -280,8 +280,10 @@ int gl_impl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_in
 int gl_phi_defer(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi);
 int gl_phi_materialise(gl_ctx* ctx, gl_mat* phi, const gl_fused_filter* ff = nullptr);
 int gl_filter_weights_from_proj(gl_ctx* ctx, const double* proj, const double* f, double gain, int m, int m_pad, int C, float* w);
+// parts > 0: z = y + the sum of `parts` row partials in zpart; parts == 0: z_dev / z8_dev already hold the band's filtered pixels (the
+// patch kernel wrote them).  Either way the sample pixels' rows are patched and the result is copied to the host destinations.
 int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int parts, const float* w, const float* U, int ldU,
-                           int clip_low, float* z_f32, uint8_t* z_u8);
+                           int clip_low, float* z_f32, uint8_t* z_u8, gl_buf* z_dev = nullptr, gl_buf* z8_dev = nullptr);
 int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out);
 int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip_low, float* z_f32, uint8_t* z_u8);
 int gl_impl_diag_map(gl_ctx* ctx, gl_mat* d, int op, double arg, gl_mat** out);

@@ -377,21 +377,23 @@ __global__ void k_filter_sample_rows(const float* __restrict__ U, int ldU, int p
 }
 
 int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int parts, const float* w, const float* U, int ldU,
-                           int clip_low, float* z_f32, uint8_t* z_u8)
+                           int clip_low, float* z_f32, uint8_t* z_u8, gl_buf* z_dev, gl_buf* z8_dev)
 {
     const int C = ctx->channels;
     const int64_t rows = phi->local_rows;
-    gl_buf *z = nullptr, *z8 = nullptr;
+    gl_buf *z = z_dev, *z8 = z8_dev;      // (ownership passes to this function)
     int rc = GL_OK;
     do {
-        if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)rows * C, &z)) != GL_OK) break;
-        if (z_u8 && (rc = gl_alloc(ctx, (size_t)rows * C, &z8)) != GL_OK) break;
+        if (!z && (rc = gl_alloc(ctx, sizeof(float) * (size_t)rows * C, &z)) != GL_OK) break;
+        if (z_u8 && !z8 && (rc = gl_alloc(ctx, (size_t)rows * C, &z8)) != GL_OK) break;
         {
             StageTimer t(ctx, GL_T_FILTER);
             const uint8_t* y = (const uint8_t*)ctx->img->ptr + (size_t)phi->q0 * C;
-            k_filter_sum_parts<<<(unsigned)ceil_div(rows * C, 256), 256, 0, ctx->stream>>>(zpart, parts, rows, C, y, clip_low, (float*)z->ptr,
-                                                                                          z8 ? (uint8_t*)z8->ptr : nullptr);
-            GL_LAUNCH_CHECK(ctx);
+            if (parts > 0) {
+                k_filter_sum_parts<<<(unsigned)ceil_div(rows * C, 256), 256, 0, ctx->stream>>>(zpart, parts, rows, C, y, clip_low, (float*)z->ptr,
+                                                                                              z8 ? (uint8_t*)z8->ptr : nullptr);
+                GL_LAUNCH_CHECK(ctx);
+            }
             k_filter_sample_rows<<<phi->p, 128, 0, ctx->stream>>>(U, ldU, phi->p, phi->m, (const uint32_t*)ctx->samples->ptr, phi->q0,
                                                                  phi->q0 + rows, C, w, (const uint8_t*)ctx->img->ptr, clip_low,
                                                                  (float*)z->ptr, z8 ? (uint8_t*)z8->ptr : nullptr);

@@ -710,7 +710,8 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
     GL_REQUIRE(L_B->sample_epoch == ctx->sample_epoch, "nystroem: the samples changed since this K_B was computed");
     // K_B in its patch layout (patch.cu) feeds the fused extrapolation + filter directly; everything that needs Phi itself goes
     // through the blocked storage, computed on demand when the handle does not hold it yet
-    const bool use_patch = L_B->pt_buf != nullptr && ff != nullptr && !keep_phi && ctx->gemm_impl == 0;
+    const bool use_patch = L_B->pt_buf != nullptr && ff != nullptr && !keep_phi && ctx->gemm_impl == 0 &&
+                           gl_patch_nystroem_fits(m, ctx->channels);
     if (!use_patch) GL_CHECK(gl_kb_require_blocked(ctx, L_B));
     GL_REQUIRE(use_patch || (L_B->tiles && L_B->starts && L_B->perm), "nystroem: K_B handle without its block layout");
 
@@ -758,22 +759,33 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
             if (!phi->proj) { gl_set_error("nystroem: fused filter needs the affinity sums of the current image"); rc = GL_ERR_ARG; break; }
             if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)m_pad * C, &wbuf)) != GL_OK) break;
             const int parts_max = 2 * (m_pad / (m_pad < 256 ? m_pad : 256));
-            if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)parts_max * rows * C, &zpart)) != GL_OK) { gl_buf_release(wbuf); break; }
+            if (!use_patch && (rc = gl_alloc(ctx, sizeof(float) * (size_t)parts_max * rows * C, &zpart)) != GL_OK) { gl_buf_release(wbuf); break; }
             if ((rc = gl_filter_weights_from_proj(ctx, (const double*)phi->proj->ptr, (const double*)ff->f_eigvals->buf->ptr, ff->gain, m, m_pad,
                                                   C, (float*)wbuf->ptr)) != GL_OK) { gl_buf_release(wbuf); gl_buf_release(zpart); break; }
             fuse.w = (const float*)wbuf->ptr;
-            fuse.zpart = (float*)zpart->ptr;
+            fuse.zpart = zpart ? (float*)zpart->ptr : nullptr;
             fuse.C = C;
         }
-        if (use_patch)
-            rc = gl_patch_nystroem_filter(ctx, L_B, U, (int)phi_A->ld, m, mu_inv, (const float*)scales->ptr, &fuse);
-        else
+        if (use_patch) {
+            // the patch kernel writes the band's filtered pixels itself; the finish only patches the sample pixels' rows
+            const int C = ctx->channels;
+            gl_buf *zd = nullptr, *z8d = nullptr;
+            if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)rows * C, &zd)) == GL_OK && ff->z_u8) rc = gl_alloc(ctx, (size_t)rows * C, &z8d);
+            if (rc == GL_OK)
+                rc = gl_patch_nystroem_filter(ctx, L_B, U, (int)phi_A->ld, m, mu_inv, (const float*)scales->ptr, (const float*)wbuf->ptr, C,
+                                              ff->clip_low, (float*)zd->ptr, z8d ? (uint8_t*)z8d->ptr : nullptr);
+            if (rc == GL_OK)
+                rc = gl_filter_fused_finish(ctx, phi, nullptr, 0, (const float*)wbuf->ptr, U, (int)phi_A->ld, ff->clip_low, ff->z_f32, ff->z_u8,
+                                            zd, z8d);
+            else { if (zd) gl_buf_release(zd); if (z8d) gl_buf_release(z8d); }
+        } else {
             rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, k_dim, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,
                                 keep_phi ? phi->buf->ptr : nullptr, (const int4*)L_B->tiles->ptr, L_B->total_blocks, do_fuse ? &fuse : nullptr,
                                 (const int*)L_B->starts->ptr, L_B->kbs);
-        if (rc == GL_OK && do_fuse)
-            rc = gl_filter_fused_finish(ctx, phi, (const float*)zpart->ptr, fuse.parts, (const float*)wbuf->ptr, U, (int)phi_A->ld,
-                                        ff->clip_low, ff->z_f32, ff->z_u8);
+            if (rc == GL_OK && do_fuse)
+                rc = gl_filter_fused_finish(ctx, phi, (const float*)zpart->ptr, fuse.parts, (const float*)wbuf->ptr, U, (int)phi_A->ld,
+                                            ff->clip_low, ff->z_f32, ff->z_u8);
+        }
         if (wbuf) gl_buf_release(wbuf);
         if (zpart) gl_buf_release(zpart);
         if (rc != GL_OK) break;

@@ -33,8 +33,8 @@ constexpr int SLOTS = 32;         // sample slots per block
 constexpr int A_TILE_BYTES = 128 * SLOTS * 2;     // 8 KB
 constexpr int B_BLOCK_BYTES = SLOTS * 256 * 2;    // 16 KB: 4 chunks of [32 K rows][64 columns = 128 B]
 constexpr int B_CHUNK_BYTES = SLOTS * 128;        // 4 KB
-constexpr int SA = 8;             // A ring stages
-constexpr int SB = 4;             // B block slots
+constexpr int SA = 6;             // A ring stages
+constexpr int SBT = 8;            // B units: [32 slots][256 columns of one N tile], 16 KB each
 constexpr int EPI_WARPS = 8;       // epilogue warps per group: 4 TMEM lane quarters x 2 column shares
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 
@@ -354,37 +354,36 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  : "memory");
 }
 
-// One persistent CTA per SM; CTA b works on N tile nt = b % n_tiles of the patches b / n_tiles, + gridDim.x / n_tiles, ...: its
-// filter weights never change.  Roles (12 warps):
-//   warp 0      producer: one 8 KB bulk copy per A tile into a ring of SA slots
-//   warp 1      MMA issuer (one thread): per M tile one or two tcgen05.mma per slot block, commits that free the operand slots and
-//               announce the accumulator
-//   warps 2-3   gather the W rows of each patch's samples into the B slots (cp.async, MN-major SWIZZLE_128B image); warp 2 allocates
-//               the tensor memory first
-//   warps 4-11  epilogue: warp w drains TMEM lanes 32 (w % 4) .. +31 (= 32 pixels of one patch row) and half of the accumulator's
-//               columns, in chunks of 32 columns with the next chunk's tcgen05.ld in flight during the arithmetic; the accumulator
-//               goes back to the issuer before the last chunk is multiplied
-// What bounds it (profiles/r02_patch_timeline.md): with K loops of one or two steps the per-tile hand-overs -- every mbarrier wait,
-// tcgen05.mma, tcgen05.commit and tcgen05.ld round trip costs its thread 50-200 cycles -- not the tensor pipe (10 % busy), the
-// operand traffic or the epilogue's arithmetic.  Variants with two issuer threads, sixteen epilogue warps in two groups, operand
-// slots released by the epilogue, and 64-column loads were all measured slower or equal (same file).
-// Debug instrumentation of the kernel below (timeline of CTA 0, experiment switches) is compiled in only with -DGLB200_PT_DEBUG
-// (make PT_DEBUG=1): in the serial issuer loop even predicated-off clock reads cost ~10 % of the kernel.
+// Experiment switches of the kernel below are compiled in only with -DGLB200_PT_DEBUG (make PT_DEBUG=1): in the serial issuer loop
+// even predicated-off instrumentation costs ~10 % of the kernel.
 #ifdef GLB200_PT_DEBUG
-#define PT_PROF(cond, stmt) do { if (cond) { stmt; } } while (0)
 #define PT_DBG(bit) (dbg & (bit))
 #else
-#define PT_PROF(cond, stmt) do { (void)sizeof(cond); } while (0)
 #define PT_DBG(bit) false
 #endif
 
+// One persistent CTA per SM works through whole patches (b, b + gridDim.x, ...).  For a patch: its W rows for ALL N tiles are
+// gathered once (one 16 KB unit per N tile and slot block), each A tile is loaded once per M tile and multiplied against every N
+// tile, and the epilogue carries a pixel's dot product across the N tiles in registers -- so the filtered pixel z = y + Phi_row . w
+// is written by this kernel (no partial sums in HBM, no summation pass) and an A tile crosses L2 -> shared memory once instead of
+// once per N tile.  Roles (12 warps):
+//   warp 0      producer: one SWIZZLE_64B tensor-map copy (8 KB) per A tile into a ring of SA slots
+//   warps 1, 3  MMA issuers (one thread each), issuer w owns accumulator w = every other (M tile, N tile).  These threads are the
+//               serial part of the pipeline: every operation they execute costs 50-150 cycles (tools/probe_issue.cu), and with K
+//               loops of one or two steps nothing hides that (profiles/r02_patch_timeline.md).  Two issuers only when the N tiles
+//               come in pairs and every patch's operands stay resident; otherwise issuer 0 works alone.
+//   warp 2      allocates the tensor memory, then gathers the W rows (cp.async, MN-major SWIZZLE_128B image) into the B units
+//   warps 4-11  epilogue: warp w drains TMEM lanes 32 (w % 4) .. +31 (= 32 pixels of one patch row) and half of the accumulator's
+//               columns -- all of them requested back to back, one wait, accumulator handed back, THEN the arithmetic; after the last N
+//               tile the two column halves of a pixel meet in shared memory and the filtered pixel is stored.
 template <int FC, int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots,
                  const __half* __restrict__ W, int m_pad, int n_tiles, const float* __restrict__ scales,
-                 const float* __restrict__ fuse_w /* [m_pad][FC] */, float* __restrict__ zpart /* [2 n_tiles][m_rows][FC] */,
-                 int64_t m_rows, int* __restrict__ err, long long* __restrict__ prof /* debug timeline of CTA 0, or null */,
-                 const int* __restrict__ dstat, int dbg /* experiments: bit 0 = no epilogue arithmetic, bit 1 = no zpart store */)
+                 const float* __restrict__ fuse_w /* [m_pad][FC] */, const uint8_t* __restrict__ img /* band rows, [pixel][FC] */,
+                 int clip_low, float* __restrict__ z /* [band pixels][FC] */, uint8_t* __restrict__ z8 /* or null */,
+                 int* __restrict__ err, long long* __restrict__ prof /* debug timeline of CTA 0, or null */,
+                 const int* __restrict__ dstat, int dbg /* experiments: bit 0 = no epilogue arithmetic, bit 1 = no stores */)
 {
     using namespace tc;
     if (dstat[GL_DS_PT_OVERFLOW]) return;
@@ -392,26 +391,27 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
     uint8_t* smem = (uint8_t*)(((uintptr_t)pn_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + SA * A_TILE_BYTES;
-    uint64_t* bars = (uint64_t*)(smem_b + SB * B_BLOCK_BYTES);
+    uint64_t* bars = (uint64_t*)(smem_b + SBT * B_BLOCK_BYTES);
     const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + SA);
-    const uint32_t bar_bfull = smem_u32(bars + 2 * SA), bar_bempty = smem_u32(bars + 2 * SA + SB);
-    const uint32_t bar_tfull = smem_u32(bars + 2 * SA + 2 * SB), bar_tempty = smem_u32(bars + 2 * SA + 2 * SB + 2);
-    static_assert(2 * SA + 2 * SB + 4 + 1 <= 64, "barrier block is 512 bytes");
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * SA + 2 * SB + 4);
-    float* w_s = (float*)(bars + 64);   // [BN][FC] filter weights of this CTA's N tile, times the GEMM's output scale
+    const uint32_t bar_bfull = smem_u32(bars + 2 * SA), bar_bempty = smem_u32(bars + 2 * SA + SBT);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * SA + 2 * SBT), bar_tempty = smem_u32(bars + 2 * SA + 2 * SBT + 2);
+    static_assert(2 * SA + 2 * SBT + 4 + 1 <= 64, "barrier block is 512 bytes");
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * SA + 2 * SBT + 4);
+    float* xch = (float*)(bars + 64);            // [4 quarters][32 lanes][FC]: column share 1 hands its part of a pixel's dot to share 0
+    float* w_s = xch + 4 * 32 * FC;              // [m_pad][FC] filter weights, times the GEMM's output scale
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nt = blockIdx.x % n_tiles, first_patch = blockIdx.x / n_tiles, patch_step = gridDim.x / n_tiles;
-    // Two issuer threads and two epilogue groups (one of each per accumulator) while every patch's W rows stay resident (at most SB
-    // slot blocks per patch).  With more, a tile's operands make more than one lap of the rings, and an issuer a tile ahead of the
-    // other would wait on a barrier phase two laps away, which a parity wait cannot tell from the current one: issuer 0 then works alone.
-    const bool two = dstat[GL_DS_PT_MAXNB] <= SB;
+    const int first_patch = blockIdx.x, patch_step = gridDim.x;
+    const int max_nb = dstat[GL_DS_PT_MAXNB];
+    // every patch keeps its operands resident (A tiles of an M tile in half the ring, W units of all N tiles in the B units)?
+    const bool all_resident = max_nb * 2 <= SA && max_nb * n_tiles <= SBT;
+    const bool two = all_resident && (n_tiles & 1) == 0;
 
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-        // a B slot is released by TWO arrivals: a patch's last two tiles run on different accumulators under different issuers
-        for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 2); }
+        // an A slot is released by TWO arrivals (its M tile is multiplied by both issuers; a lone issuer arrives twice)
+        for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 2); }
+        for (int s = 0; s < SBT; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -421,13 +421,14 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
     }
     {
         const float sc = scales[1];
-        for (int i = threadIdx.x; i < BN * FC; i += THREADS) w_s[i] = __ldg(fuse_w + (size_t)nt * BN * FC + i) * sc;
+        for (int i = threadIdx.x; i < m_pad * FC; i += THREADS) w_s[i] = __ldg(fuse_w + i) * sc;
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // per patch: nb slot blocks, mtc M tiles; resident = operands loaded once per M tile (A) / per patch (W units)
     if (warp == 0) {
         // ===== A producer =====
         if (lane == 0) {
@@ -438,126 +439,140 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                 const int py = patch / g.pcols;
                 const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
                 const int tile0 = pi.x * G;
+                const bool resident = pi.y * 2 <= SA && pi.y * n_tiles <= SBT;
+                const int reps = resident ? 1 : n_tiles;          // not resident: the A tiles stream past once per N tile
                 for (int mt = 0; mt < mtc; ++mt)
-                    for (int b = 0; b < pi.y; ++b) {
-                        mbar_wait(bar_aempty + 8 * stage, phase ^ 1, err, 1);
-                        mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)A_TILE_BYTES);
-                        tma_load_2d(smem_u32(smem_a + stage * A_TILE_BYTES), &map_a, bar_afull + 8 * stage, 0, (tile0 + mt * pi.y + b) * 128);
-                        if (++stage == SA) { stage = 0; phase ^= 1; }
-                    }
+                    for (int rep = 0; rep < reps; ++rep)
+                        for (int b = 0; b < pi.y; ++b) {
+                            mbar_wait(bar_aempty + 8 * stage, phase ^ 1, err, 1);
+                            mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)A_TILE_BYTES);
+                            tma_load_2d(smem_u32(smem_a + stage * A_TILE_BYTES), &map_a, bar_afull + 8 * stage, 0, (tile0 + mt * pi.y + b) * 128);
+                            if (++stage == SA) { stage = 0; phase ^= 1; }
+                        }
             }
         }
     } else if (warp == 1 || warp == 3) {
         // ===== MMA issuers =====
-        // These threads are the serial part of the pipeline: every instruction in this loop is on the critical path (compiled-out debug
-        // predicates alone cost 10 %).  Order measured fastest: accumulator, operands, MMAs, slot commits, accumulator commit.
-        if (lane == 0) {
+        if (lane == 0 && (two || warp == 1)) {
             const int me = warp == 1 ? 0 : 1;
             int stage = 0, bpos = 0, it = 0;
-            uint32_t phase = 0, buses = 0;   // buses bit s: parity of the number of fills of B slot s consumed so far
+            uint32_t phase = 0, buses = 0;   // buses bit s: parity of the number of fills of B unit slot s consumed so far
             const uint32_t idesc = make_idesc(BLOCK_M, BN, 0) | (1u << 16);   // B is MN-major
-            int4 pi_next = first_patch < g.npatch ? pinfo[first_patch] : make_int4(0, 1, 0, 0);
             for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
-                const int4 pi = pi_next;               // (fetched a patch ahead: an L2 round trip in this loop is 5 % of a patch's time)
-                if (patch + patch_step < g.npatch) pi_next = pinfo[patch + patch_step];
+                const int4 pi = pinfo[patch];
                 const int py = patch / g.pcols;
                 const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
-                const bool resident = pi.y <= SB;      // the patch's W rows stay in their slots for all of its M tiles
+                const int nb = pi.y;
+                const bool resident = nb * 2 <= SA && nb * n_tiles <= SBT;
                 const int b0 = bpos;
-                bool b_seen = false;                   // resident W rows: waited for once per patch by each issuer
-                // resident W rows go back after the patch's last two tiles, one arrival from each (both from the one tile of a 1-tile
-                // patch, and both from issuer 0 when it works alone)
-                const int my_last = !two ? mtc - 1 : ((((it + mtc - 1) & 1) == me) ? mtc - 1 : mtc - 2);
-                for (int mt = 0; mt < mtc; ++mt, ++it) {
-                    const int acc = it & 1;
-                    const bool mine = two ? acc == me : me == 0;
-                    const bool pf = prof && blockIdx.x == 0 && it < 64 && mine;
-                    if (mine) {
-                        PT_PROF(pf, prof[it * 8 + 0] = clock64());
-                        mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1), err, 2);
-                        tcgen05_fence_after();
-                        PT_PROF(pf, prof[it * 8 + 1] = clock64());
-                    }
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-                    for (int b = 0; b < pi.y; ++b) {
-                        int bs;
-                        if (resident) { bs = b0 + b; if (bs >= SB) bs -= SB; }
-                        else { bs = bpos; if (++bpos == SB) bpos = 0; }
+                uint32_t b_seen = 0;                   // resident W units this issuer has already waited for in this patch
+                for (int mt = 0; mt < mtc; ++mt) {
+                    const int stage_m = stage;         // first A slot of this M tile (resident)
+                    const uint32_t phase_m = phase;
+                    bool a_seen = false;
+                    for (int nt = 0; nt < n_tiles; ++nt, ++it) {
+                        const int acc = it & 1;
+                        const bool mine = !two || acc == me;
                         if (mine) {
-                            mbar_wait(bar_afull + 8 * stage, phase, err, 3);
-                            if (!resident || !b_seen) mbar_wait(bar_bfull + 8 * bs, (buses >> bs) & 1u, err, 6);
+                            mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1), err, 2);
                             tcgen05_fence_after();
-                            PT_PROF(pf && b == 0, prof[it * 8 + 7] = clock64());
-                            const int kk = (pi.z - SLOTS * b) > 16 ? 2 : 1;     // a last block with at most 16 samples: one K step
-                            const uint64_t da = make_smem_desc_k<32>(smem_u32(smem_a + stage * A_TILE_BYTES));
-                            const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + bs * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
-                            for (int k = 0; k < kk; ++k)
-                                umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
-                            umma_commit(bar_aempty + 8 * stage);   // frees the A slot when these MMAs retire
-                            if (!resident || mt == my_last) {
-                                umma_commit(bar_bempty + 8 * bs);
-                                if (!resident || !two || mtc == 1) umma_commit(bar_bempty + 8 * bs);
-                            }
                         }
-                        if (!resident || mt == mtc - 1) buses ^= 1u << bs;
-                        if (++stage == SA) { stage = 0; phase ^= 1; }
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                        for (int b = 0; b < nb; ++b) {
+                            int as, bs;
+                            uint32_t aph;
+                            if (resident) {
+                                as = stage_m + b; aph = phase_m;
+                                if (as >= SA) { as -= SA; aph ^= 1u; }
+                                bs = b0 + nt * nb + b;
+                                if (bs >= SBT) bs -= SBT;
+                            } else {
+                                as = stage; aph = phase;
+                                bs = bpos;
+                                if (++bpos == SBT) bpos = 0;
+                            }
+                            if (mine) {
+                                if (!resident || !a_seen) mbar_wait(bar_afull + 8 * as, aph, err, 3);
+                                if (!resident || !((b_seen >> (nt * nb + b)) & 1u)) mbar_wait(bar_bfull + 8 * bs, (buses >> bs) & 1u, err, 6);
+                                tcgen05_fence_after();
+                                const int kk = (pi.z - SLOTS * b) > 16 ? 2 : 1;     // a last block with at most 16 samples: one K step
+                                const uint64_t da = make_smem_desc_k<32>(smem_u32(smem_a + as * A_TILE_BYTES));
+                                const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + bs * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
+                                for (int k = 0; k < kk; ++k)
+                                    umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
+                                if (!resident) {
+                                    umma_commit(bar_aempty + 8 * as);
+                                    umma_commit(bar_aempty + 8 * as);
+                                    umma_commit(bar_bempty + 8 * bs);
+                                } else {
+                                    b_seen |= 1u << (nt * nb + b);
+                                    // the W unit goes back after the patch's last M tile (every use of it was this issuer's: in order)
+                                    if (mt == mtc - 1) umma_commit(bar_bempty + 8 * bs);
+                                    // the A slot after this issuer's last N tile of the M tile; the other issuer's arrival completes it
+                                    const int my_last_nt = !two ? n_tiles - 1 : (((it - nt + n_tiles - 1) & 1) == me ? n_tiles - 1 : n_tiles - 2);
+                                    if (nt == my_last_nt) {
+                                        umma_commit(bar_aempty + 8 * as);
+                                        if (!two) umma_commit(bar_aempty + 8 * as);
+                                    }
+                                }
+                            }
+                            if (!resident || mt == mtc - 1) buses ^= 1u << bs;
+                            if (!resident) { if (++stage == SA) { stage = 0; phase ^= 1; } }
+                        }
+                        if (mine) {
+                            a_seen = true;
+                            umma_commit(bar_tfull + 8 * acc);
+                        }
                     }
-                    if (mine) {
-                        b_seen = true;
-                        umma_commit(bar_tfull + 8 * acc);
-                        PT_PROF(pf, prof[it * 8 + 2] = clock64());
-                    }
+                    if (resident) { stage += nb; if (stage >= SA) { stage -= SA; phase ^= 1; } }
                 }
-                if (resident) { bpos = b0 + pi.y; if (bpos >= SB) bpos -= SB; }
+                if (resident) { bpos = b0 + nb * n_tiles; if (bpos >= SBT) bpos -= SBT; }
             }
         }
     } else if (warp == 2) {
-        // ===== B gather: rows of W for the slots of a block, written in the MN-major SWIZZLE_128B layout =====
-        const int u = lane;                      // 16-byte unit of the 512-byte row part of this N tile
+        // ===== B gather: rows of W for the slots of a block and the columns of an N tile, in the MN-major SWIZZLE_128B layout =====
+        const int u = lane;                      // 16-byte unit of the 512-byte row part of an N tile
         int bpos = 0;
         uint32_t bloads = 0;
         for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
             const int4 pi = pinfo[patch];
             const int py = patch / g.pcols;
             const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
-            const int reps = pi.y <= SB ? 1 : mtc;
+            const bool resident = pi.y * 2 <= SA && pi.y * n_tiles <= SBT;
+            const int reps = resident ? 1 : mtc;
             for (int rep = 0; rep < reps; ++rep)
-                for (int b = 0; b < pi.y; ++b) {
-                    mbar_wait(bar_bempty + 8 * bpos, ((bloads >> bpos) & 1u) ^ 1u, err, 5);
-                    bloads ^= 1u << bpos;
-                    const uint32_t dst_s = smem_u32(smem_b + bpos * B_BLOCK_BYTES);
-                    const uint32_t my_slot = __ldg(slots + (size_t)(pi.x + b) * SLOTS + lane);
-                    // thirty-two 16-byte cp.async per thread, all in flight at once (no registers hold the data); an empty slot and
-                    // the chunks beyond a narrow N tile are zero-filled (source size 0)
+                for (int nt = 0; nt < n_tiles; ++nt)
+                    for (int b = 0; b < pi.y; ++b) {
+                        mbar_wait(bar_bempty + 8 * bpos, ((bloads >> bpos) & 1u) ^ 1u, err, 5);
+                        bloads ^= 1u << bpos;
+                        const uint32_t dst_s = smem_u32(smem_b + bpos * B_BLOCK_BYTES);
+                        const uint32_t my_slot = __ldg(slots + (size_t)(pi.x + b) * SLOTS + lane);
+                        // thirty-two 16-byte cp.async per thread, all in flight at once (no registers hold the data); an empty slot
+                        // and the chunks beyond a narrow N tile are zero-filled (source size 0)
 #pragma unroll 8
-                    for (int k = 0; k < SLOTS; ++k) {
-                        const uint32_t s = __shfl_sync(0xffffffffu, my_slot, k);
-                        const bool live = s != 0xffffffffu && u * 8 < BN;
-                        const __half* src = W + (size_t)(live ? s : 0) * m_pad + (size_t)nt * BN + (live ? u * 8 : 0);
-                        const uint32_t d = dst_s + (uint32_t)((u >> 3) * B_CHUNK_BYTES + k * 128 + (((u & 7) ^ (k & 7)) << 4));
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(live ? 16 : 0) : "memory");
+                        for (int k = 0; k < SLOTS; ++k) {
+                            const uint32_t s = __shfl_sync(0xffffffffu, my_slot, k);
+                            const bool live = s != 0xffffffffu && u * 8 < BN;
+                            const __half* src = W + (size_t)(live ? s : 0) * m_pad + (size_t)nt * BN + (live ? u * 8 : 0);
+                            const uint32_t d = dst_s + (uint32_t)((u >> 3) * B_CHUNK_BYTES + k * 128 + (((u & 7) ^ (k & 7)) << 4));
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(live ? 16 : 0) : "memory");
+                        }
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_bfull + 8 * bpos);
+                        if (++bpos == SBT) bpos = 0;
                     }
-                    asm volatile("cp.async.wait_all;" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_bfull + 8 * bpos);
-                    if (++bpos == SB) bpos = 0;
-                }
         }
     } else {
         // ===== epilogue =====
-        // The accumulator is read out in ONE go -- all of this warp's columns requested back to back, one wait -- and handed back
-        // before any arithmetic: the time from "accumulator full" to "accumulator free" is on the serial chain of the tile
-        // (profiles/r02_patch_timeline.md), four waited-for tcgen05.ld round trips with the arithmetic between them were most of it.
-        // (Three channels need the registers for the dots: they keep the chunked order.)
         const int wq = warp & 3, share = (warp - 4) >> 2;
         constexpr int COLS = BN >= 128 ? BN / 2 : BN;          // columns per share (BN = 64: share 0 takes them all)
         const bool active = BN >= 128 || share == 0;
         constexpr int NCH = COLS / 32;
         constexpr bool AT_ONCE = FC == 1;
         const uint32_t wbase = smem_u32(w_s) + (uint32_t)((BN >= 128 ? share * COLS : 0) * FC * 4);
-        auto mul32 = [&](const uint32_t (&v)[32], int k, float (&dot)[FC][8]) {
-            const uint32_t wv = wbase + (uint32_t)(32 * k * FC * 4);
+        auto mul32 = [&](const uint32_t (&v)[32], uint32_t wv, float (&dot)[FC][8]) {
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
                 float wr[8 * FC];
@@ -577,67 +592,83 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                 }
             }
         };
+        float* my_x = xch + (wq * 32 + lane) * FC;
         int it = 0;
         for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
             const int py = patch / g.pcols, pxi = patch - py * g.pcols;
             const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
-            for (int mt = 0; mt < mtc; ++mt, ++it) {
-                const int acc = it & 1;
-                const bool pf = prof && blockIdx.x == 0 && it < 64 && warp == 4 && lane == 0;
-                PT_PROF(pf, prof[it * 8 + 3] = clock64());
-                mbar_wait(bar_tfull + 8 * acc, (uint32_t)((it >> 1) & 1), err, 4);
-                tcgen05_fence_after();
-                PT_PROF(pf, prof[it * 8 + 4] = clock64());
-                const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + (BN >= 128 ? share * COLS : 0));
+            for (int mt = 0; mt < mtc; ++mt) {
                 float dot[FC][8];
 #pragma unroll
                 for (int q = 0; q < FC; ++q)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dot[q][i] = 0.f;
-                if (AT_ONCE) {
-                    uint32_t v[NCH][32];
-                    if (active) {
-#pragma unroll
-                        for (int k = 0; k < NCH; ++k) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * k), v[k]);
-                    }
-                    tmem_ld_wait();
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-                    PT_PROF(pf, prof[it * 8 + 5] = clock64());
-                    if (active && !PT_DBG(1)) {
-#pragma unroll
-                        for (int k = 0; k < NCH; ++k) mul32(v[k], k, dot);
-                    }
-                } else {
-                    uint32_t v[2][32];
-                    if (active) tmem_ld_32x32b_x32(t_row, v[0]);
-#pragma unroll
-                    for (int k = 0; k < NCH; ++k) {
-                        tmem_ld_wait();
-                        if (k + 1 < NCH) {
-                            if (active) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * (k + 1)), v[(k + 1) & 1]);
-                        } else {
-                            // every tcgen05.ld of this accumulator has completed: hand it back before the last chunk's arithmetic
-                            tcgen05_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-                            PT_PROF(pf, prof[it * 8 + 5] = clock64());
-                        }
-                        if (active && !PT_DBG(1)) mul32(v[k & 1], k, dot);
-                    }
-                }
-                // this thread's pixel: tile pixel wq * 32 + lane -> patch row 2 mt + (wq >> 1), column (wq & 1) * 32 + lane
+                // this thread's pixel: tile pixel wq * 32 + lane -> patch row 2 mt + (wq >> 1), column (wq & 1) * 32 + lane; its input
+                // value is requested now, long before it is needed (an L2 round trip at the end of the M tile would be on the chain)
                 const int r = py * PR + 2 * mt + (wq >> 1), c = pxi * PW + (wq & 1) * 32 + lane;
-                if (r < g.band_rows && c < g.width && !PT_DBG(2)) {
-                    const int64_t row = (int64_t)r * g.width + c;
-                    const int part = nt * 2 + share;
+                const bool px_ok = share == 0 && r < g.band_rows && c < g.width;
+                const size_t o = ((size_t)r * g.width + c) * FC;
+                float yv[FC];
 #pragma unroll
-                    for (int q = 0; q < FC; ++q)
-                        zpart[((size_t)part * m_rows + row) * FC + q] =
-                            ((dot[q][0] + dot[q][1]) + (dot[q][2] + dot[q][3])) + ((dot[q][4] + dot[q][5]) + (dot[q][6] + dot[q][7]));
+                for (int q = 0; q < FC; ++q) yv[q] = px_ok ? (float)__ldg(img + o + q) : 0.f;
+                for (int nt = 0; nt < n_tiles; ++nt, ++it) {
+                    const int acc = it & 1;
+                    mbar_wait(bar_tfull + 8 * acc, (uint32_t)((it >> 1) & 1), err, 4);
+                    tcgen05_fence_after();
+                    const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + (BN >= 128 ? share * COLS : 0));
+                    const uint32_t wt = wbase + (uint32_t)(nt * BN * FC * 4);
+                    if (AT_ONCE) {
+                        uint32_t v[NCH][32];
+                        if (active) {
+#pragma unroll
+                            for (int k = 0; k < NCH; ++k) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * k), v[k]);
+                        }
+                        tmem_ld_wait();
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                        if (active && !PT_DBG(1)) {
+#pragma unroll
+                            for (int k = 0; k < NCH; ++k) mul32(v[k], wt + (uint32_t)(32 * k * FC * 4), dot);
+                        }
+                    } else {
+                        uint32_t v[2][32];
+                        if (active) tmem_ld_32x32b_x32(t_row, v[0]);
+#pragma unroll
+                        for (int k = 0; k < NCH; ++k) {
+                            tmem_ld_wait();
+                            if (k + 1 < NCH) {
+                                if (active) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * (k + 1)), v[(k + 1) & 1]);
+                            } else {
+                                // every tcgen05.ld of this accumulator has completed: hand it back before the last chunk's arithmetic
+                                tcgen05_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                            }
+                            if (active && !PT_DBG(1)) mul32(v[k & 1], wt + (uint32_t)(32 * k * FC * 4), dot);
+                        }
+                    }
                 }
-                PT_PROF(pf, prof[it * 8 + 6] = clock64());
+                // the pixel's dot over all columns: share 1 hands its part to share 0 (same quarter, same lane), which stores
+                // z = min(y + dot, 255) (AboveXSetY(z, 255, 255), display.c:76) -- fixed summation order, bit-reproducible
+                float part[FC];
+#pragma unroll
+                for (int q = 0; q < FC; ++q)
+                    part[q] = ((dot[q][0] + dot[q][1]) + (dot[q][2] + dot[q][3])) + ((dot[q][4] + dot[q][5]) + (dot[q][6] + dot[q][7]));
+                if (share == 1) {
+#pragma unroll
+                    for (int q = 0; q < FC; ++q) my_x[q] = part[q];
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
+                if (px_ok && !PT_DBG(2)) {
+#pragma unroll
+                    for (int q = 0; q < FC; ++q) {
+                        float val = fminf(yv[q] + (part[q] + my_x[q]), 255.f);
+                        if (clip_low) val = fmaxf(val, 0.f);
+                        z[o + q] = val;
+                        if (z8) z8[o + q] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);
+                    }
+                }
             }
         }
     }
@@ -650,7 +681,7 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
     }
 }
 
-constexpr int nystroem_smem(int fc) { return SA * A_TILE_BYTES + SB * B_BLOCK_BYTES + 512 + 256 * fc * 4 + 1024; }
+constexpr int nystroem_smem(int fc, int m_pad) { return SA * A_TILE_BYTES + SBT * B_BLOCK_BYTES + 512 + 4 * 32 * fc * 4 + m_pad * fc * 4 + 1024; }
 
 // K_B from the patch layout to dense fp64 [band pixels][p] in the caller's sample order (dst zeroed beforehand)
 __global__ void k_patch_to_f64(Geom g, const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots, const __half* __restrict__ KB, int p,
@@ -802,18 +833,24 @@ int gl_patch_download(gl_ctx* ctx, const gl_mat* KB, double scale, double* dst_d
     return GL_OK;
 }
 
-// extrapolation + fused filter over the patch layout: zpart[parts][rows][C] partial row dots (fuse->parts is set)
+// whether the fused patch kernel serves this spectrum width (its filter weights for all N tiles live in shared memory)
+bool gl_patch_nystroem_fits(int m, int C) { return pt::nystroem_smem(C, gl_m_pad(m)) <= tc::SMEM_LIMIT; }
+
+// extrapolation + fused filter over the patch layout: z (and z8) of the band's pixels are written by the kernel; the sample pixels'
+// rows are patched afterwards by the caller (gl_filter_fused_finish with parts = 0)
 int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int ldU, int m, const double* mu_inv, const float* scales,
-                             gl_gemm_fuse* fuse)
+                             const float* w, int C, int clip_low, float* z, uint8_t* z8)
 {
-    const int p = L_B->p, p_pad = L_B->p_pad, m_pad = gl_m_pad(m), C = fuse->C;
+    const int p = L_B->p, p_pad = L_B->p_pad, m_pad = gl_m_pad(m);
     const pt::Geom g = patch_geom(ctx, L_B->aff_h_loc);
     GL_REQUIRE(g.npatch == L_B->pt_npatch && L_B->q0 == ctx->q0, "nystroem(patch): K_B does not belong to the current image geometry");
     GL_REQUIRE(C == 1 || C == 3, "nystroem(patch): 1 or 3 channels");
     const int BN = m_pad < 256 ? m_pad : 256;
     const int n_tiles = m_pad / BN;
+    const int SM = pt::nystroem_smem(C, m_pad);
+    GL_REQUIRE(SM <= tc::SMEM_LIMIT, "nystroem(patch): %d eigenpairs x %d channels of filter weights do not fit in shared memory", m, C);
     gl_buf *Wr = nullptr, *err = nullptr, *prof = nullptr;
-    const bool want_prof = getenv("GLB200_PT_PROF") != nullptr;   // debug: timeline of CTA 0's first tiles on stderr
+    const bool want_prof = getenv("GLB200_PT_PROF") != nullptr;   // debug (make PT_DEBUG=1): timeline of CTA 0's first tiles on stderr
     const int dbg = getenv("GLB200_PT_DBG") ? atoi(getenv("GLB200_PT_DBG")) : 0;
     int rc = GL_OK;
     do {
@@ -827,23 +864,20 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
         dim3 wg((unsigned)ceil_div(p_pad, 32), (unsigned)ceil_div(m_pad, 32));
         pt::k_w_rows<<<wg, 256, 0, ctx->stream>>>(U, ldU, p, m, p_pad, m_pad, mu_inv, (const double*)L_B->dscale->ptr, scales, (__half*)Wr->ptr);
         ctx->launches++;
-        int grid = ctx->sm_count / n_tiles * n_tiles;
-        if (grid < n_tiles) grid = n_tiles;
-        if (grid / n_tiles > g.npatch) grid = g.npatch * n_tiles;
-        fuse->parts = 2 * n_tiles;
+        int grid = ctx->sm_count;
+        if (grid > g.npatch) grid = g.npatch;
         CUtensorMap map_a;
         GL_BREAK(rc, make_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, L_B->pt_buf->ptr, (uint64_t)L_B->pt_blocks * pt::G * 128, pt::SLOTS,
                                  pt::SLOTS, pt::SLOTS, 128, CU_TENSOR_MAP_SWIZZLE_64B));
-        const int SM = pt::nystroem_smem(C);
+        const uint8_t* y = (const uint8_t*)ctx->img->ptr + (size_t)L_B->q0 * C;
         StageTimer kt(ctx, GL_T_K_GEMM);
 #define PT_LAUNCH(FC, BNN)                                                                                                          \
     do {                                                                                                                            \
         GL_CUDA_BREAK(rc, cudaFuncSetAttribute(pt::k_patch_nystroem<FC, BNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));    \
         pt::k_patch_nystroem<FC, BNN><<<grid, pt::THREADS, SM, ctx->stream>>>(map_a, g, (const int4*)L_B->pt_info->ptr,             \
                                                                               (const uint32_t*)L_B->pt_slots->ptr, (const __half*)Wr->ptr, \
-                                                                              m_pad, n_tiles, scales, fuse->w, fuse->zpart,         \
-                                                                              L_B->local_rows, (int*)err->ptr,                      \
-                                                                              prof ? (long long*)prof->ptr : nullptr,               \
+                                                                              m_pad, n_tiles, scales, w, y, clip_low, z, z8,        \
+                                                                              (int*)err->ptr, prof ? (long long*)prof->ptr : nullptr, \
                                                                               (const int*)ctx->dstat->ptr, dbg);                    \
     } while (0)
         if (C == 1 && BN == 256) PT_LAUNCH(1, 256);
@@ -856,17 +890,6 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
         if (rc != GL_OK) break;
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { gl_set_error("nystroem(patch): kernel launch failed"); rc = GL_ERR_CUDA; }
-        if (prof) {
-            static long long h[64 * 9];
-            cudaMemcpyAsync(h, prof->ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
-            fprintf(stderr, "[pt prof] tile: mma(wait_acc_free, wait_operands, issue+commits) | epi(idle_before, wait_full, load, fma) | cycles per tile\n");
-            for (int t = 8; t < 40; ++t) {
-                const long long* r = h + t * 8;
-                fprintf(stderr, "[pt prof] %2d: mma %5lld %5lld %5lld | epi %5lld %5lld %5lld %5lld | per tile %5lld\n", t, r[1] - r[0], r[7] - r[1],
-                        r[2] - r[7], r[3] - (r - 8)[6], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[6] - (r - 8)[6]);
-            }
-        }
     } while (0);
     if (prof) gl_buf_release(prof);
     if (Wr) gl_buf_release(Wr);
