@@ -241,9 +241,12 @@ __global__ void __launch_bounds__(J_THREADS, 1)
 k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memory */, int nb, int max_sweeps, float tol, int inner_max,
          float* __restrict__ C /* [cp][cp], cp = nb * 8 */,
          float* __restrict__ pair_rel /* [nb][nb] */, int* __restrict__ step_cnt /* [max_sweeps][2 * nb] */,
-         unsigned* __restrict__ sweep_off, int* __restrict__ sweeps_done)
+         unsigned* __restrict__ sweep_off, int* __restrict__ sweeps_done, long long* __restrict__ jprof /* debug: phase clocks of CTA 0, or null */)
 {
     cg::grid_group grid = cg::this_grid();
+    int jp = 0;
+#define JPROF() do { if (jprof && blockIdx.x == 0 && threadIdx.x == 0 && jp < 60) jprof[jp++] = clock64(); } while (0)
+    JPROF();
     extern __shared__ __align__(16) float jsm[];
     float* P = jsm;                          // [pc][16]
     float* red = P + (size_t)pc * JP;        // [16][256]
@@ -280,9 +283,11 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                     for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
                 const int lp = tid >> 5, lr = tid & 31;          // panel within the tile, row within the chunk
                 const int pa = ti * 8 + lp, pb = tj * 8 + lp;
-                for (int r0 = 0; r0 < p; r0 += 32) {
+                // rows of the two panels this thread stages; the NEXT chunk's loads are in flight while the current one is multiplied
+                // (an L2 round trip per 32-row chunk, unhidden, made this screen 3x slower than its arithmetic)
+                auto fetch = [&](int r0, float4& a0, float4& a1, float4& b0, float4& b1) {
                     const int r = r0 + lr;
-                    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+                    a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; b0 = a0; b1 = a0;
                     if (r < p) {
                         if (pa < nb) {
                             a0 = __ldcg((const float4*)(G + ((size_t)pa * p + r) * JB));
@@ -293,12 +298,17 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                             b1 = __ldcg((const float4*)(G + ((size_t)pb * p + r) * JB + 4));
                         }
                     }
+                };
+                float4 a0, a1, b0, b1;
+                fetch(0, a0, a1, b0, b1);
+                for (int r0 = 0; r0 < p; r0 += 32) {
                     __syncthreads();
                     *(float4*)&As[lr * 68 + lp * 8] = a0;
                     *(float4*)&As[lr * 68 + lp * 8 + 4] = a1;
                     *(float4*)&Bs[lr * 68 + lp * 8] = b0;
                     *(float4*)&Bs[lr * 68 + lp * 8 + 4] = b1;
                     __syncthreads();
+                    if (r0 + 32 < p) fetch(r0 + 32, a0, a1, b0, b1);
 #pragma unroll 8
                     for (int k = 0; k < 32; ++k) {
                         const float4 a = *(const float4*)&As[k * 68 + ty * 4];
@@ -319,6 +329,7 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
             }
         }
         grid.sync();
+        JPROF();
         // ---- B. panel-pair screen ----
         {
             float cta_max = 0.f;
@@ -364,6 +375,7 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
             if ((tid & 31) == 0 && cta_max > 0.f) atomicMax(&sweep_off[sweep], __float_as_uint(cta_max));
         }
         grid.sync();
+        JPROF();
         const float off = __uint_as_float(__ldcg(&sweep_off[sweep]));
         if (off <= tol) break;
         // ---- C. rotations ----
@@ -389,9 +401,12 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                             jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
                     }
                     grid.sync();
+                    JPROF();
                 }
         }
     }
+    JPROF();
+    if (jprof && blockIdx.x == 0 && tid == 0) jprof[63] = jp;
     if (blockIdx.x == 0 && tid == 0) *sweeps_done = sweep;
 }
 
@@ -596,12 +611,28 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         int* scp = (int*)scnt->ptr;
         int inner = ctx->jacobi_inner > 0 ? ctx->jacobi_inner : J_INNER_MAX;
         int pc_ = pc;
-        void* args[] = {&Gp, &p_, &pc_, &nb_, &ms, &tol, &inner, &Cp, &prp, &scp, &off, &done};
+        gl_buf* jprof = nullptr;
+        long long* jpp = nullptr;
+        if (getenv("GLB200_JACOBI_PROF")) {
+            GL_BREAK(rc, gl_alloc(ctx, sizeof(long long) * 64, &jprof));
+            GL_CUDA_BREAK(rc, cudaMemsetAsync(jprof->ptr, 0, sizeof(long long) * 64, ctx->stream));
+            jpp = (long long*)jprof->ptr;
+        }
+        void* args[] = {&Gp, &p_, &pc_, &nb_, &ms, &tol, &inner, &Cp, &prp, &scp, &off, &done, &jpp};
         {
             StageTimer kt(ctx, GL_T_K_JACOBI);
             GL_CUDA_BREAK(rc, cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));
         }
         ctx->launches++;
+        if (jprof) {
+            long long h[64];
+            cudaMemcpyAsync(h, jprof->ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            fprintf(stderr, "[jacobi prof] %lld marks, cycles between:", h[63]);
+            for (int i = 1; i < (int)h[63]; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+            fprintf(stderr, "  total %lld\n", h[h[63] - 1] - h[0]);
+            gl_buf_release(jprof);
+        }
 
         k_jacobi_norms<<<(unsigned)ceil_div(p, 8), 256, 0, ctx->stream>>>((const float*)G->ptr, p, (double*)lam->ptr);
         GL_LAUNCH_CHECK(ctx);
