@@ -28,7 +28,14 @@ namespace cg = cooperative_groups;
 #define J_THREADS 256
 #define J_INNER_MAX 12
 
-__global__ void k_jacobi_init(const double* __restrict__ A, int p, int nb, float* __restrict__ G)
+// Row-chunk occupancy of the panels.  L_A of this pipeline is banded (couplings between spatially close samples only; in raster order
+// of the samples that is a band of ~15 % of the rows), and a Jacobi rotation of two panels only mixes their rows: a panel's rows that are
+// zero in both stay zero.  Every panel carries a 32-bit mask of the row chunks (cr = ceil(p / 32) rows each) that may hold a non-zero;
+// the Gram screen, the pair Gram blocks and the rotations skip the rest.  Entries below 1e-20 (the diagonal is ~1) are flushed to zero
+// when G is set up, so that "zero" is exact.
+__device__ __forceinline__ int jacobi_chunk_rows(int p) { return (p + 31) / 32; }
+
+__global__ void k_jacobi_init(const double* __restrict__ A, int p, int nb, float* __restrict__ G, unsigned* __restrict__ pmask)
 {
     // G[panel][r][c] = A[r][panel*8 + c]; zero columns beyond p
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,7 +46,10 @@ __global__ void k_jacobi_init(const double* __restrict__ A, int p, int nb, float
     int r = (int)(t % p);
     int panel = (int)(t / p);
     int col = panel * JB + c;
-    G[idx] = col < p ? (float)A[(size_t)r * p + col] : 0.f;
+    float v = col < p ? (float)A[(size_t)r * p + col] : 0.f;
+    if (fabsf(v) < 1e-20f) v = 0.f;
+    G[idx] = v;
+    if (v != 0.f) atomicOr(&pmask[panel], 1u << (r / jacobi_chunk_rows(p)));
 }
 
 // round-robin tournament over nb (even) panels: step in [0, nb-1), pair in [0, nb/2)
@@ -60,24 +70,36 @@ __device__ __forceinline__ void tournament(int step, int pair, int nb, int& a, i
 // `pc` = rows of the pair that fit in shared memory at once: the whole panels when p <= pc (loaded once, rotated in place),
 // otherwise the Gram block is accumulated chunk by chunk and the chunks are fetched a second time for the rotation.
 __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc, int I, int J, float tol, int inner_max, float* P, float* red,
-                                            double* Bm, double* Qm, double* cs, int* role, int* pq, float* s_off, unsigned* s_cta_off)
+                                            double* Bm, double* Qm, double* cs, int* role, int* pq, float* s_off, unsigned* s_cta_off,
+                                            unsigned* __restrict__ pmask)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     const int bi = tid >> 4, bj = tid & 15;  // this thread's element of the 16 x 16 block
     float* GI = G + (size_t)I * p * JB;
     float* GJ = G + (size_t)J * p * JB;
     const int nchunks = (p + pc - 1) / pc;
+    // Only the row chunks in which one of the two panels may be non-zero take part (single-pass case: the whole pair in shared
+    // memory); they are held compactly: compact row k of the pair = row (k % cr) of the (k / cr)-th occupied chunk.
+    const int cr = jacobi_chunk_rows(p);
+    const unsigned occ = nchunks == 1 ? (__ldcg(&pmask[I]) | __ldcg(&pmask[J])) : 0xffffffffu;
+    const int n_occ = nchunks == 1 ? __popc(occ) * cr : p;
+    auto actual_row = [&](int k) -> int { return nchunks == 1 ? (int)__fns(occ, 0, k / cr + 1) * cr + k % cr : k; };
     // rows [r0, r0 + n) of the panel pair -> P (L2 loads: the data was written by other SMs)
     auto load_chunk = [&](int r0, int n) {
         for (int idx = tid; idx < 2 * n; idx += J_THREADS) {
             const int r = idx >> 1, h = idx & 1;
-            float4 a = __ldcg((const float4*)(GI + (size_t)(r0 + r) * JB + h * 4));
-            float4 b = __ldcg((const float4*)(GJ + (size_t)(r0 + r) * JB + h * 4));
+            const int ra = actual_row(r0 + r);
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (ra < p) {
+                a = __ldcg((const float4*)(GI + (size_t)ra * JB + h * 4));
+                b = __ldcg((const float4*)(GJ + (size_t)ra * JB + h * 4));
+            }
             *(float4*)(P + (size_t)r * JP + h * 4) = a;
             *(float4*)(P + (size_t)r * JP + JB + h * 4) = b;
         }
     };
-    if (tid == 0) *s_cta_off = 0u;
+    __shared__ unsigned s_occ[2];
+    if (tid == 0) { *s_cta_off = 0u; s_occ[0] = 0u; s_occ[1] = 0u; }
     // ---- Gram block: 16 row groups x (4 x 4 register tiles), accumulated over the chunks ----
     {
         const int rg = tid >> 4, ti = (tid >> 2) & 3, tj = tid & 3;
@@ -87,7 +109,7 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
 #pragma unroll
             for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
         for (int c = 0; c < nchunks; ++c) {
-            const int r0 = c * pc, n = min(pc, p - r0);
+            const int r0 = c * pc, n = nchunks == 1 ? n_occ : min(pc, p - r0);
             if (c > 0) __syncthreads();   // the previous chunk's readers are done
             load_chunk(r0, n);
             __syncthreads();
@@ -203,13 +225,15 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
             for (int x = 0; x < 4; ++x) q[k][x] = (float)Qm[k * 17 + 4 * cgp + x];
         float* dst = (cgp < 2) ? (GI + cgp * 4) : (GJ + (cgp - 2) * 4);
         for (int c = 0; c < nchunks; ++c) {
-            const int r0 = c * pc, n = min(pc, p - r0);
+            const int r0 = c * pc, n = nchunks == 1 ? n_occ : min(pc, p - r0);
             if (nchunks > 1) {            // the single chunk is still in P from the Gram pass
                 __syncthreads();
                 load_chunk(r0, n);
                 __syncthreads();
             }
             for (int r = tid >> 2; r < n; r += J_THREADS / 4) {
+                const int ra = actual_row(r0 + r);
+                if (ra >= p) continue;
                 const float4 v0 = *(const float4*)(P + (size_t)r * JP);
                 const float4 v1 = *(const float4*)(P + (size_t)r * JP + 4);
                 const float4 v2 = *(const float4*)(P + (size_t)r * JP + 8);
@@ -221,8 +245,21 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
                 for (int k = 0; k < JP; ++k)
 #pragma unroll
                     for (int x = 0; x < 4; ++x) o[x] = fmaf(pv[k], q[k][x], o[x]);
-                __stcg((float4*)(dst + (size_t)(r0 + r) * JB), make_float4(o[0], o[1], o[2], o[3]));
+                // what a small-angle rotation spills into rows that were zero is second order: flushed below 1e-12 (the tolerance
+                // of the solve is 5e-5), so that the occupancy masks keep following the band instead of filling up within a sweep
+                bool nz = false;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    if (fabsf(o[x]) < 1e-12f) o[x] = 0.f;
+                    nz = nz || o[x] != 0.f;
+                }
+                __stcg((float4*)(dst + (size_t)ra * JB), make_float4(o[0], o[1], o[2], o[3]));
+                if (nz && nchunks == 1) atomicOr(cgp < 2 ? &s_occ[0] : &s_occ[1], 1u << (ra / cr));
             }
+        }
+        if (nchunks == 1) {
+            __syncthreads();
+            if (tid == 0) { pmask[I] = s_occ[0]; pmask[J] = s_occ[1]; }
         }
     }
     __syncthreads();
@@ -241,7 +278,8 @@ __global__ void __launch_bounds__(J_THREADS, 1)
 k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memory */, int nb, int max_sweeps, float tol, int inner_max,
          float* __restrict__ C /* [cp][cp], cp = nb * 8 */,
          float* __restrict__ pair_rel /* [nb][nb] */, int* __restrict__ step_cnt /* [max_sweeps][2 * nb] */,
-         unsigned* __restrict__ sweep_off, int* __restrict__ sweeps_done, long long* __restrict__ jprof /* debug: phase clocks of CTA 0, or null */)
+         unsigned* __restrict__ sweep_off, int* __restrict__ sweeps_done, long long* __restrict__ jprof /* debug: phase clocks of CTA 0, or null */,
+         unsigned* __restrict__ pmask /* [nb] occupied row chunks of every panel */)
 {
     cg::grid_group grid = cg::this_grid();
     int jp = 0;
@@ -299,16 +337,30 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                         }
                     }
                 };
+                // row chunks in which BOTH tiles may be non-zero (the others contribute nothing to C)
+                unsigned mi = 0u, mj = 0u;
+                for (int q = 0; q < 8; ++q) {
+                    if (ti * 8 + q < nb) mi |= __ldcg(&pmask[ti * 8 + q]);
+                    if (tj * 8 + q < nb) mj |= __ldcg(&pmask[tj * 8 + q]);
+                }
+                const unsigned both = mi & mj;
+                const int cr = jacobi_chunk_rows(p);
+                const int nsub = (cr + 31) / 32;                 // 32-row staging steps per row chunk
+                const int steps = __popc(both) * nsub;
+                auto step_row0 = [&](int s_) -> int { return (int)__fns(both, 0, s_ / nsub + 1) * cr + (s_ % nsub) * 32; };
+                auto step_rows = [&](int s_) -> int { return min(32, cr - (s_ % nsub) * 32); };
                 float4 a0, a1, b0, b1;
-                fetch(0, a0, a1, b0, b1);
-                for (int r0 = 0; r0 < p; r0 += 32) {
+                if (steps > 0) fetch(step_row0(0), a0, a1, b0, b1);
+                for (int st = 0; st < steps; ++st) {
+                    const int nrow = step_rows(st);
                     __syncthreads();
-                    *(float4*)&As[lr * 68 + lp * 8] = a0;
-                    *(float4*)&As[lr * 68 + lp * 8 + 4] = a1;
-                    *(float4*)&Bs[lr * 68 + lp * 8] = b0;
-                    *(float4*)&Bs[lr * 68 + lp * 8 + 4] = b1;
+                    const bool live = lr < nrow;
+                    *(float4*)&As[lr * 68 + lp * 8] = live ? a0 : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *(float4*)&As[lr * 68 + lp * 8 + 4] = live ? a1 : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *(float4*)&Bs[lr * 68 + lp * 8] = live ? b0 : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *(float4*)&Bs[lr * 68 + lp * 8 + 4] = live ? b1 : make_float4(0.f, 0.f, 0.f, 0.f);
                     __syncthreads();
-                    if (r0 + 32 < p) fetch(r0 + 32, a0, a1, b0, b1);
+                    if (st + 1 < steps) fetch(step_row0(st + 1), a0, a1, b0, b1);
 #pragma unroll 8
                     for (int k = 0; k < 32; ++k) {
                         const float4 a = *(const float4*)&As[k * 68 + ty * 4];
@@ -386,7 +438,7 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                     int I, J;
                     tournament(step, pair, nb, I, J);
                     if (__ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
-                        jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
+                        jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off, pmask);
                 }
                 grid.sync();
             }
@@ -398,7 +450,7 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                     for (int c = blockIdx.x; c < ncand; c += gridDim.x) {
                         const int I = (c / d) * 2 * d + par * d + (c % d), J = I + d;
                         if (J < nb && __ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
-                            jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off);
+                            jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off, pmask);
                     }
                     grid.sync();
                     JPROF();
@@ -566,11 +618,13 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
 {
     const int p = (int)L_A->rows;
     const int nb = (int)(round_up(p, JP) / JB);  // even number of panels
-    const int pc = p < 3072 ? p : 3072;   // panel rows per shared-memory chunk (larger p: two passes over the pair, see jacobi_pair)
+    // panel rows per shared-memory chunk: the whole pair (its 32 row chunks of ceil(p / 32) rows) up to p = 3072, larger p: two passes
+    // over the pair (see jacobi_pair)
+    const int pc = p < 3072 ? 32 * (int)ceil_div(p, 32) : 3072;
     const size_t smem = sizeof(float) * ((size_t)pc * JP + 16 * 256) + sizeof(double) * (2 * JP * 17 + 16) + sizeof(int) * (JP + 2 * JB);
     GL_REQUIRE(p <= 8192, "eigensolve: p = %d is beyond what this build sorts and screens (8192)", p);
     gl_buf *G = nullptr, *lam = nullptr, *order = nullptr, *ctl = nullptr, *ray = nullptr, *part = nullptr;
-    gl_buf *Cg = nullptr, *prel = nullptr, *scnt = nullptr;
+    gl_buf *Cg = nullptr, *prel = nullptr, *scnt = nullptr, *pmaskb = nullptr;
     const int cols_pad = nb * JB;
     const int row_tiles = (int)ceil_div(p, 64);
     gl_mat *U = nullptr, *mu = nullptr, *mui = nullptr;
@@ -589,8 +643,10 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         if ((rc = gl_alloc(ctx, sizeof(int) * (size_t)max_sweeps * 2 * nb, &scnt)) != GL_OK) break;
         GL_CUDA_BREAK(rc, cudaMemsetAsync(scnt->ptr, 0, sizeof(int) * (size_t)max_sweeps * 2 * nb, ctx->stream));
         const int64_t total = (int64_t)nb * p * JB;
+        if ((rc = gl_alloc(ctx, sizeof(unsigned) * (size_t)nb, &pmaskb)) != GL_OK) break;
+        GL_CUDA_BREAK(rc, cudaMemsetAsync(pmaskb->ptr, 0, sizeof(unsigned) * (size_t)nb, ctx->stream));
         k_jacobi_init<<<(unsigned)ceil_div(total, 256), 256, 0, ctx->stream>>>((const double*)L_A->buf->ptr, p, nb,
-                                                                               (float*)G->ptr);
+                                                                               (float*)G->ptr, (unsigned*)pmaskb->ptr);
         GL_LAUNCH_CHECK(ctx);
 
         GL_CUDA_BREAK(rc, cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -618,7 +674,8 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
             GL_CUDA_BREAK(rc, cudaMemsetAsync(jprof->ptr, 0, sizeof(long long) * 64, ctx->stream));
             jpp = (long long*)jprof->ptr;
         }
-        void* args[] = {&Gp, &p_, &pc_, &nb_, &ms, &tol, &inner, &Cp, &prp, &scp, &off, &done, &jpp};
+        unsigned* pmp = (unsigned*)pmaskb->ptr;
+        void* args[] = {&Gp, &p_, &pc_, &nb_, &ms, &tol, &inner, &Cp, &prp, &scp, &off, &done, &jpp, &pmp};
         {
             StageTimer kt(ctx, GL_T_K_JACOBI);
             GL_CUDA_BREAK(rc, cudaLaunchCooperativeKernel((void*)k_jacobi, dim3(grid), dim3(J_THREADS), args, smem, ctx->stream));
@@ -703,6 +760,7 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
     if (Cg) gl_buf_release(Cg);
     if (prel) gl_buf_release(prel);
     if (scnt) gl_buf_release(scnt);
+    if (pmaskb) gl_buf_release(pmaskb);
     if (ray) gl_buf_release(ray);
     if (part) gl_buf_release(part);
     if (rc != GL_OK) {
