@@ -38,7 +38,7 @@ EXPORTS = [
     "gl_comm_unique_id", "gl_comm_init",
     "gl_set_image", "gl_set_image_rows", "gl_set_synthetic_image", "gl_get_image", "gl_get_band",
     "gl_sampling_uniform", "gl_sampling_random", "gl_set_samples", "gl_get_samples",
-    "gl_affinity", "gl_laplacian", "gl_eigensolve", "gl_nystroem", "gl_nystroem_filter", "gl_orthonormalise", "gl_filter",
+    "gl_affinity", "gl_laplacian", "gl_eigensolve", "gl_inverse_iteration", "gl_nystroem", "gl_nystroem_filter", "gl_orthonormalise", "gl_filter",
     "gl_diag_inverse", "gl_diag_pow", "gl_full_affinity", "gl_full_laplacian", "gl_full_result", "gl_run", "gl_run_resident",
     "gl_mat_info_get", "gl_mat_retain", "gl_mat_destroy", "gl_mat_download", "gl_mat_download_cols", "gl_mat_rowsums", "gl_mat_upload",
     "gl_host_alloc", "gl_host_free", "gl_kb_layout_host",
@@ -103,6 +103,8 @@ def lib():
         L.gl_affinity.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(vp), C.POINTER(vp)]
         L.gl_laplacian.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp)]
         L.gl_eigensolve.argtypes = [vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.gl_inverse_iteration.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip,
+                                           C.POINTER(C.c_double)]
         L.gl_nystroem.argtypes = [vp, vp, vp, vp, C.POINTER(vp)]
         L.gl_nystroem_filter.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_int, C.POINTER(vp), vp, vp]
         L.gl_orthonormalise.argtypes = [vp, vp, vp]
@@ -368,6 +370,14 @@ class Context:
         u, d, di = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(lib().gl_eigensolve(self.h, L_A.h, m, C.byref(u), C.byref(d), C.byref(di)))
         return Mat(self, u), Mat(self, d), Mat(self, di)
+
+    def inverse_iteration(self, L_A: Mat, m=-1, opti_gs=1, epsilon=0.1, max_iterations=1000):
+        """InversePowerIteration (hpc/inverse_power_it.c:86-252): returns (eigvecs, eigvals, eigvals_inv, iterations, residual)."""
+        u, d, di = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        it, res = C.c_int(), C.c_double()
+        _check(lib().gl_inverse_iteration(self.h, L_A.h, m, opti_gs, epsilon, max_iterations, C.byref(u), C.byref(d), C.byref(di),
+                                          C.byref(it), C.byref(res)))
+        return Mat(self, u), Mat(self, d), Mat(self, di), it.value, res.value
 
     def nystroem(self, L_B: Mat, phi_A: Mat, eigvals_inv: Mat):
         p = C.c_void_p()

@@ -109,7 +109,6 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
     const char* v = getenv("GLB200_VERBOSE");
     ctx->verbose = v ? atoi(v) : 0;
     if (const char* g = getenv("GLB200_GEMM")) gl_ctx_set_option(ctx, "gemm", g);
-    if (const char* g = getenv("GLB200_CTA_GROUP")) gl_ctx_set_option(ctx, "cta_group", g);
     if (const char* g = getenv("GLB200_JACOBI_TOL")) gl_ctx_set_option(ctx, "jacobi_tol", g);
     if (const char* g = getenv("GLB200_KB_BLOCK")) gl_ctx_set_option(ctx, "kb_block", g);
     if (const char* g = getenv("GLB200_KB_LAYOUT")) gl_ctx_set_option(ctx, "kb_layout", g);
@@ -124,10 +123,6 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
         if (!strcmp(value, "tcgen05")) ctx->gemm_impl = 0;
         else if (!strcmp(value, "simple")) ctx->gemm_impl = 1;
         else GL_REQUIRE(false, "option gemm: want tcgen05|simple, got %s", value);
-    } else if (!strcmp(key, "cta_group")) {
-        int g = atoi(value);
-        GL_REQUIRE(g == 1 || g == 2, "option cta_group: want 1|2");
-        ctx->gemm_cta_group = g;
     } else if (!strcmp(key, "projection")) {
         if (!strcmp(value, "sums")) ctx->projection_mode = 0;
         else if (!strcmp(value, "recompute")) ctx->projection_mode = 1;
@@ -562,6 +557,20 @@ int gl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** ei
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
     StageTimer t(ctx, GL_T_EIGEN);
     return gl_impl_eigensolve(ctx, L_A, m, eigvecs, eigvals, eigvals_inv);
+}
+
+int gl_inverse_iteration(gl_ctx* ctx, gl_mat* L_A, int m, int opti_gs, double epsilon, int max_iterations, gl_mat** eigvecs, gl_mat** eigvals,
+                         gl_mat** eigvals_inv, int* iterations_out, double* residual_out)
+{
+    GL_REQUIRE(ctx && L_A, "gl_inverse_iteration: null");
+    GL_REQUIRE(L_A->kind == GL_MAT_KA && L_A->rows == L_A->cols, "gl_inverse_iteration: want a square p x p matrix");
+    if (m < 0 || m > L_A->rows) m = (int)L_A->rows - 1;       // GetNumberEigenvalues, hpc/image_processing.c:96-108
+    GL_REQUIRE(m >= 1, "gl_inverse_iteration: m must be >= 1");
+    GL_REQUIRE(epsilon > 0.0 && max_iterations >= 1, "gl_inverse_iteration: epsilon must be positive, max_iterations >= 1");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_EIGEN);
+    return gl_impl_inverse_iteration(ctx, L_A, m, opti_gs, epsilon, max_iterations, eigvecs, eigvals, eigvals_inv, iterations_out,
+                                     residual_out);
 }
 
 int gl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl_mat** phi)

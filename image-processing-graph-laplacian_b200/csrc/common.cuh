@@ -208,7 +208,6 @@ struct gl_ctx {
 
     // options
     int gemm_impl = 0;        // 0 = tcgen05 (default), 1 = simple CUDA-core checker kernel
-    int gemm_cta_group = 1;   // 1 or 2
     int gram_impl = 0;        // orthonormalise: 0 = tcgen05 Gram when m_pad % 256 == 0, 1 = always the CUDA-core tiles
     int gram_lbo = 8192;      // leading byte offset of the MN-major operand descriptors (tuning/debug)
     int gemm_stages = 0;      // 0 = automatic, 3 | 4 = force that ring depth (tuning)
@@ -268,6 +267,12 @@ int gl_impl_synthetic(gl_ctx* ctx, uint32_t seed);
 int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K_A, gl_mat** K_B);
 int gl_impl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A, gl_mat** L_B);
 int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv);
+int gl_impl_inverse_iteration(gl_ctx* ctx, gl_mat* L_A, int m, int opti_gs, double epsilon, int max_iterations, gl_mat** eigvecs,
+                              gl_mat** eigvals, gl_mat** eigvals_inv, int* iterations_out, double* residual_out);
+// small dense fp64 algebra (dense_small.cu): C = alpha op(A) op(B) + beta C, row-major
+int gl_dgemm(gl_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, int ta, const double* B, int ldb, int tb, double beta,
+             double* C, int ldc);
+int gl_chol_inverse_upper(gl_ctx* ctx, double* G, int m, int ld, double* T, int* status_dev);
 // request to apply the filter inside the extrapolation GEMM (gl_nystroem_filter)
 struct gl_fused_filter {
     gl_mat* f_eigvals = nullptr;

@@ -384,6 +384,32 @@ __global__ void k_et_scales(float* s)
     s[1] = ldexpf(1.f, -ET_SCALE_LOG2);
 }
 
+// R = chol(G) in place (upper triangle of the m x m fp64 matrix G with leading dimension ld, G = R^T R) and T = R^-1 (upper,
+// same shape, zeroed here).  *status_dev (zeroed by the caller) receives the first non-positive pivot + 1.  Used by the
+// orthonormalisation (CholeskyQR) and by the inverse subspace iteration (A^-1 = T T^T, dense_small.cu).
+int gl_chol_inverse_upper(gl_ctx* ctx, double* G, int m, int ld, double* T, int* status_dev)
+{
+    const int nblk = (int)ceil_div(m, CB);
+    gl_buf* Tdiag = nullptr;
+    GL_CHECK(gl_alloc(ctx, sizeof(double) * (size_t)nblk * CB * CB, &Tdiag));
+    for (int kb = 0; kb < nblk; ++kb) {
+        k_chol_diag<<<1, CB * CB, 0, ctx->stream>>>(G, ld, m, kb, (double*)Tdiag->ptr, status_dev);
+        ctx->launches++;
+        const int nrem = nblk - kb - 1;
+        if (nrem > 0) {
+            k_chol_row<<<nrem, CB * CB, 0, ctx->stream>>>(G, ld, m, kb, (const double*)Tdiag->ptr);
+            k_chol_trail<<<nrem * (nrem + 1) / 2, CB * CB, 0, ctx->stream>>>(G, ld, m, kb, nrem);
+            ctx->launches += 2;
+        }
+    }
+    cudaMemsetAsync(T, 0, sizeof(double) * (size_t)m * ld, ctx->stream);
+    k_upper_inverse_blocked<<<nblk, CB * CB, 0, ctx->stream>>>(G, m, ld, (const double*)Tdiag->ptr, T);
+    ctx->launches++;
+    gl_buf_release(Tdiag);
+    if (cudaGetLastError() != cudaSuccess) { gl_set_error("Cholesky: kernel launch failed"); return GL_ERR_CUDA; }
+    return GL_OK;
+}
+
 int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
 {
     const int m = phi->m, m_pad = phi->m_pad;
@@ -400,7 +426,6 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
     if (tc_gram) slabs = (int)ceil_div(ceil_div(rows, 64), kb_per_item);
 
     gl_buf *partial = nullptr, *G = nullptr, *T = nullptr, *Et = nullptr, *Q = nullptr, *st = nullptr, *norms = nullptr, *sc = nullptr;
-    gl_buf* Tdiag = nullptr;
     int rc = GL_OK;
     do {
         if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)slabs * m_pad * m_pad, &partial)) != GL_OK) break;
@@ -439,24 +464,7 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
         GL_LAUNCH_CHECK(ctx);
         if ((rc = gl_allreduce_f64(ctx, (double*)G->ptr, (size_t)m_pad * m_pad)) != GL_OK) break;
 
-        {
-            const int nblk = (int)ceil_div(m, CB);
-            if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)nblk * CB * CB, &Tdiag)) != GL_OK) break;
-            for (int kb = 0; kb < nblk; ++kb) {
-                k_chol_diag<<<1, CB * CB, 0, ctx->stream>>>((double*)G->ptr, m_pad, m, kb, (double*)Tdiag->ptr, (int*)st->ptr);
-                ctx->launches++;
-                const int nrem = nblk - kb - 1;
-                if (nrem > 0) {
-                    k_chol_row<<<nrem, CB * CB, 0, ctx->stream>>>((double*)G->ptr, m_pad, m, kb, (const double*)Tdiag->ptr);
-                    k_chol_trail<<<nrem * (nrem + 1) / 2, CB * CB, 0, ctx->stream>>>((double*)G->ptr, m_pad, m, kb, nrem);
-                    ctx->launches += 2;
-                }
-            }
-            GL_CUDA_BREAK(rc, cudaMemsetAsync(T->ptr, 0, sizeof(double) * (size_t)m_pad * m_pad, ctx->stream));
-            k_upper_inverse_blocked<<<nblk, CB * CB, 0, ctx->stream>>>((const double*)G->ptr, m, m_pad, (const double*)Tdiag->ptr,
-                                                                       (double*)T->ptr);
-            GL_LAUNCH_CHECK(ctx);
-        }
+        if ((rc = gl_chol_inverse_upper(ctx, (double*)G->ptr, m, m_pad, (double*)T->ptr, (int*)st->ptr)) != GL_OK) break;
         dim3 ge((unsigned)ceil_div(m_pad, 128), (unsigned)m_pad);
         k_build_et<<<ge, 128, 0, ctx->stream>>>((const double*)T->ptr, m, m_pad, m_pad, (__half*)Et->ptr,
                                                 (const double*)G->ptr, (double*)norms->ptr);
@@ -500,6 +508,5 @@ int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out)
     if (st) gl_buf_release(st);
     if (norms) gl_buf_release(norms);
     if (sc) gl_buf_release(sc);
-    if (Tdiag) gl_buf_release(Tdiag);
     return rc;
 }

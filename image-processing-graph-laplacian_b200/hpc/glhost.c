@@ -96,6 +96,7 @@ void OptionsInit(int argc, char** argv)
     g_opt.color = OptionsHasName("-color");
     if (OptionsGetInt("-dump_eigvecs", &iv) && iv > 0) g_opt.dump_eigvecs = iv;
     g_opt.dump_scaled = OptionsHasName("-dump_scaled");
+    g_opt.inverse_iteration = OptionsHasName("-inverse_iteration");
     if (OptionsGetInt("-ngpus", &iv) && iv >= 1 && iv <= 64) g_opt.ngpus = iv;
     if (OptionsGetString("-synthetic", buf, sizeof buf)) sscanf(buf, "%dx%d", &g_opt.synthetic_w, &g_opt.synthetic_h);
 }

@@ -17,6 +17,7 @@ typedef struct GLHostOptions {
     int gram_schmidt;        /* -gram_schmidt */
     int dump_eigvecs;        /* -dump_eigvecs K: write the first K extrapolated eigenvectors (hpc/image_processing.c:255-260 writes 3) */
     int dump_scaled;         /* -dump_scaled: eigenvector PNGs use the column's [min, max] as [0, 255] */
+    int inverse_iteration;   /* -inverse_iteration: the reference's inverse subspace iteration instead of the converged solver */
     int color;               /* -color: keep RGB, photometric term on the three channels */
     int ngpus;               /* -ngpus */
     int synthetic_w, synthetic_h; /* -synthetic WxH */

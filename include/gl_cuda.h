@@ -158,6 +158,15 @@ GL_API int gl_laplacian(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** L_A, gl_
 /* m smallest eigenpairs of symmetric positive definite L_A, ascending, 1 <= m <= p (m < 0 or m > p: p - 1).
  * eigvecs and/or eigvals_inv may be NULL. */
 GL_API int gl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv);
+/* The reference's own eigensolver, hpc/inverse_power_it.c:86-252 (InversePowerIteration), with its options -opti_gs and
+ * -inv_it_epsilon (hpc/image_processing.c:124-152): inverse subspace iteration on m vectors, orthonormalised every opti_gs-th
+ * step, until |(I - X X^T) A X|_F <= epsilon; lambda_i = 1 / (norm of iterate i before normalisation), eigenvectors = the
+ * normalised iterates, in the order the iteration leaves them (no sort, as in the reference).  The linear solves are exact
+ * (Cholesky of the SPD L_A) where the reference runs GMRES; the start is a fixed pseudo-random matrix where the reference seeds
+ * PETSc's generator with the MPI rank.  m << p is what this solver is for (-num_eigvals); gl_eigensolve stays the default (all
+ * pairs, converged).  GL_ERR_NOTCONVERGED after max_iterations outer steps.  iterations_out / residual_out may be NULL. */
+GL_API int gl_inverse_iteration(gl_ctx* ctx, gl_mat* L_A, int m, int opti_gs, double epsilon, int max_iterations, gl_mat** eigvecs,
+                                gl_mat** eigvals, gl_mat** eigvals_inv, int* iterations_out, double* residual_out);
 /* Phi (n x m): sample rows = phi_A, other rows = L_B^T . phi_A . diag(eigvals_inv), already in raster order.
  * The handle is DEFERRED (option lazy_phi=0: computed at once): it retains its three inputs and the matrix is computed by
  * its first consumer -- gl_filter runs extrapolation and filter as one pass and stores nothing (option keep_phi=1: stores

@@ -306,6 +306,48 @@ def gram_schmidt(X):
     return X, norms
 
 
+def inverse_iteration_start(p, m):
+    """The fixed pseudo-random start X_0 (p x m, uniform in (0, 1)) shared with the device solver (csrc/dense_small.cu: k_ii_start).
+    The reference fills X_0 from PETSc's generator seeded with the MPI rank (hpc/inverse_power_it.c:27-34), which nothing outside
+    PETSc can reproduce and which makes its result depend on the process count."""
+    idx = (np.arange(p * m, dtype=np.uint64) + np.uint64(0x9E3779B9)) & np.uint64(0xFFFFFFFF)
+    h = _hash32(idx.astype(np.uint32))
+    return (((h >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0).reshape(p, m)
+
+
+def inverse_power_iteration(A, m, opti_gs=1, epsilon=0.1, X0=None, max_iterations=1000):
+    """InversePowerIteration, hpc/inverse_power_it.c:86-252, with exact solves in place of its GMRES + additive-Schwarz ones:
+
+      X_0 random, orthonormalised (:94-95); r = |(I - X X^T) A X|_F (ComputeResidualsNorm :49-80);
+      while r > epsilon: X <- A^-1 X (:163-166); keep a copy (:169); every opti_gs-th step OrthonormaliseVecs with the norms out
+      (:172-175); recompute r (:178); one more orthonormalisation if the last step skipped it (:183-186);
+      lambda_i = 1 / norms[i] (:204); eigenvectors = the kept pre-orthonormalisation iterates, normalised (:230-235).
+
+    Returns (lambda, vectors, outer iterations, last residual)."""
+    A = np.asarray(A, dtype=np.float64)
+    p = A.shape[0]
+    X = inverse_iteration_start(p, m) if X0 is None else np.array(X0, dtype=np.float64, copy=True)
+    opti_gs = max(1, int(opti_gs))
+    X, norms = gram_schmidt(X)
+    Xb = X.copy()
+
+    def residual(Xk):
+        AX = A @ Xk
+        return float(np.linalg.norm(AX - Xk @ (Xk.T @ AX)))
+
+    r, it = residual(X), 0
+    while r > epsilon and it < max_iterations:
+        it += 1
+        X = np.linalg.solve(A, X)
+        Xb = X.copy()
+        if it % opti_gs == 0:
+            X, norms = gram_schmidt(X)
+        r = residual(X)
+    if opti_gs != 1 and it % opti_gs != 0:
+        X, norms = gram_schmidt(X)
+    return 1.0 / norms, Xb / np.linalg.norm(Xb, axis=0), it, r
+
+
 def run_pipeline(img, sample_indices, m=None, kind=BILATERAL, h_loc=40.0, h_val=30.0,
                  gain=3.0, power=1.0, orthonormalise=False, chunk=65536, return_phi=False,
                  f_of_mu=None, clip=True, all_pairs=False):

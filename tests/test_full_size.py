@@ -98,3 +98,34 @@ def test_c4_variants_agree(ctx, base):
         assert _rel(r["z"], ref) < 2e-5, key
         assert _rel(r["z"] - img, ref - img) < 2e-3, key
         assert np.max(np.abs(r["mu"] - base["mu"]) / base["mu"]) < 1e-6, key
+
+
+def test_c5_against_full_size_oracle():
+    """BASELINE.json config 5 (synthetic 8192x8192 colour, p=2000 random samples, m=1999) on ONE GPU (Phi would be 275 GB: it is
+    consumed tile by tile and never stored), against the compact golden written by the CPU oracle (tests/golden/make_golden_c5.py)."""
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c5_full.npz")
+    if not os.path.exists(gold):
+        pytest.skip("tests/golden/c5_full.npz not generated")
+    g = np.load(gold)
+    W5, H5, C5, P5 = int(g["width"]), int(g["height"]), int(g["channels"]), int(g["p"])
+    c = gl.Context(0)
+    try:
+        c.set_synthetic_image(W5, H5, C5, int(g["seed_img"]))
+        prm = gl.default_params(sampling=gl.RANDOM, sample_size=P5, seed=int(g["seed_samples"]))
+        z = np.zeros((H5, W5, C5), dtype=np.float32)
+        r = c.run_resident(prm, z_out=z, want_eigvals=True)
+        assert np.array_equal(c.get_samples(), g["sample_indices"])
+        assert r["p"] == P5 and r["m"] == P5 - 1
+        err_mu = float(np.max(np.abs(r["mu"] - g["mu"]) / g["mu"]))
+        n = W5 * H5
+        idx = np.arange(0, n, int(g["stride"]))
+        img = c.get_image().reshape(n, C5)
+        y = img[idx].astype(np.float64)
+        zz = z.reshape(n, C5)[idx].astype(np.float64)
+        zr = g["z_lattice"].astype(np.float64)
+        err_z, err_dz = _rel(zz, zr), _rel(zz - y, zr - y)
+        err_sum = abs(float(z.astype(np.float64).sum()) - float(g["sum_z"])) / float(g["sum_z"])
+        print(f"C5 full size: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e} err_sum={err_sum:.2e}")
+        assert err_mu <= 1e-4 and err_z <= 1e-3 and err_dz <= 5e-3 and err_sum <= 1e-6
+    finally:
+        c.close()

@@ -768,6 +768,32 @@ def test_deferred_phi_rejects_changed_samples(ctx, golden):
         ctx.filter(phi, mu)
 
 
+@pytest.mark.parametrize("m,opti_gs,eps", [(8, 1, 1e-7), (20, 1, 0.1), (12, 2, 1e-5), (49, 1, 1e-6)])
+def test_inverse_iteration_matches_the_restatement(ctx, golden, m, opti_gs, eps):
+    """gl_inverse_iteration (the reference's InversePowerIteration, hpc/inverse_power_it.c:86-252, on the device) against
+    oracle_np.inverse_power_iteration from the same start: same number of outer iterations, same eigenvalues 1/norm, same subspace;
+    with a tight epsilon the eigenvalues are the converged smallest ones."""
+    g = golden("cat_small_random50")
+    ctx.set_image(g["image"])
+    ctx.set_samples(g["sample_indices"])
+    K_A, K_B = ctx.affinity()
+    L_A, L_B = ctx.laplacian(K_A, K_B)
+    A = L_A.download()
+    U, mu, mu_inv, it, res = ctx.inverse_iteration(L_A, m, opti_gs, eps)
+    rmu, rV, rit, rres = o.inverse_power_iteration(A, m, opti_gs, eps)
+    assert it == rit and res <= eps
+    got_mu, got_U = mu.download(), U.download()
+    assert np.max(np.abs(got_mu - rmu) / rmu) < 1e-6
+    assert np.max(np.abs(mu_inv.download() * got_mu - 1.0)) < 1e-12
+    assert np.max(np.abs(np.abs(got_U) - np.abs(rV))) < 1e-5                        # same iterates (fp32 storage), column by column
+    if eps <= 1e-6:     # (the rule stops on the subspace: close eigenvalues inside it are only roughly separated, as in the reference)
+        lam = np.linalg.eigvalsh(A)[:m]
+        assert np.max(np.abs(np.sort(got_mu) - lam) / lam) < 5e-2
+    # the pairs feed the rest of the path like those of gl_eigensolve
+    z = ctx.filter(ctx.nystroem(L_B, U, mu_inv), mu)
+    assert np.isfinite(z).all()
+
+
 def test_repeatability_and_launch_count(ctx, golden):
     g = golden("cat_small_random50")
     n0 = ctx.kernel_launches()

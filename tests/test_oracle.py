@@ -225,3 +225,29 @@ def test_prototype_building_blocks_match_the_reference_functions():
     assert np.max(np.abs(W_A - g["W_A"])) < 1e-9 and np.max(np.abs(W_B - g["W_B"])) < 1e-9
     W_A2, _ = pr.sinkhorn(phi, Pi)                        # and from the oracle's own eigenvectors
     assert np.max(np.abs(W_A2 - g["W_A"])) < 1e-6
+
+
+def test_inverse_power_iteration_restatement():
+    """oracle_np.inverse_power_iteration (hpc/inverse_power_it.c:86-252 with exact solves): with a tight epsilon it returns the m
+    smallest eigenpairs of an SPD matrix in ascending order (pinned to numpy's eigh); with the reference's default epsilon = 0.1
+    it stops early with the residual it promises; opti_gs > 1 orthonormalises less often and ends with one more pass (:183-186)."""
+    from oracle import oracle_np as o
+    rng = np.random.default_rng(3)
+    q, _ = np.linalg.qr(rng.standard_normal((60, 60)))
+    lam = np.sort(rng.uniform(0.2, 2.0, 60))
+    A = (q * lam) @ q.T
+    A = 0.5 * (A + A.T)
+    mu, V, it, r = o.inverse_power_iteration(A, 6, 1, 1e-10)
+    assert r <= 1e-10 and it > 3
+    # the stopping rule measures the invariance of the SUBSPACE: the subspace is converged, well separated eigenvalues come out
+    # exactly as 1/norm, close ones (0.3032 / 0.3047 here) only as well as the single vectors have separated by then
+    assert np.max(np.abs(mu[:3] - lam[:3]) / lam[:3]) < 1e-9
+    assert np.max(np.abs(mu - lam[:6]) / lam[:6]) < 1e-2
+    Qv, _ = np.linalg.qr(V)              # (the returned vectors are the normalised iterates BEFORE orthonormalisation, :230-235)
+    assert np.linalg.norm(Qv @ Qv.T - q[:, :6] @ q[:, :6].T) < 1e-6
+    mu2, V2, it2, r2 = o.inverse_power_iteration(A, 6, 1, 0.1)
+    assert r2 <= 0.1 and it2 < it
+    mu3, V3, it3, r3 = o.inverse_power_iteration(A, 6, 3, 1e-8)
+    assert r3 <= 1e-8 and np.max(np.abs(mu3 - lam[:6]) / lam[:6]) < 2e-2
+    X0 = o.inverse_iteration_start(5, 3)
+    assert X0.shape == (5, 3) and X0.min() > 0 and X0.max() < 1 and len(np.unique(X0)) == 15
