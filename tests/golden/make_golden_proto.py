@@ -6,10 +6,13 @@ reference's OWN functions in python/image_processing.py, run in the build contai
     permutation(phi, s)            :35-50    rows back to raster order
     orthogonalisation(K_A, K_B)    :112-129  one-shot orthogonal Nystroem eigenvectors V, eigenvalues min(Pi_Q, 1)
     sinkhorn(phi, Pi)              :92-109   100 Sinkhorn iterations on Phi Pi Phi^T, then W_A, W_B
+    smoothing_matrix(s, phi, Pi)   :151-194  W = I + alpha (K - D) of K = Phi Pi Phi^T, eigenpairs of its sample block, extended (V, L)
+    smoothing(y, s, phi, Pi)       :197-219  z = V L V^T y
+    sharpening(y, s, phi, Pi)      :222-241  z = (1 + beta) W^2 y - beta W^3 y, W = V L V^T, beta = 1.5
 
 The module's matplotlib / scipy.misc imports are stubbed exactly as in make_golden_pyref.py; nothing numerical is touched.
 Writes tests/golden/pyref_proto.npz.  The oracle restatements (oracle/proto_np.py) are pinned to it by tests/test_oracle.py;
-no device kernel exists for these blocks yet."""
+the device versions (csrc/proto.cu) are compared with the same file by tests/test_proto_gpu.py."""
 import os
 import sys
 import types
@@ -49,7 +52,11 @@ if __name__ == "__main__":
     phi_perm = ref.permutation(phi, s)
     V, Pi_V = ref.orthogonalisation(K_A.copy(), K_B.copy())
     W_A, W_B = ref.sinkhorn(phi, Pi)
+    ref.display_or_save = lambda *a, **k: None                                   # smoothing() saves three eigenvector pictures
+    V_s, L_s = ref.smoothing_matrix(s, phi.copy(), Pi.copy())
+    z_smooth = ref.smoothing(y, s, phi.copy(), Pi.copy())
+    z_sharp = ref.sharpening(y, s, phi.copy(), Pi.copy())
     out = os.path.join(HERE, "pyref_proto.npz")
     np.savez_compressed(out, image=y.astype(np.uint8), sample_indices=np.asarray(s, dtype=np.uint32), K_A=K_A, K_B=K_B, phi=phi, Pi=Pi,
-                        phi_perm=phi_perm, V=V, Pi_V=Pi_V, W_A=W_A, W_B=W_B)
+                        phi_perm=phi_perm, V=V, Pi_V=Pi_V, W_A=W_A, W_B=W_B, V_s=V_s, L_s=L_s, z_smooth=z_smooth, z_sharp=z_sharp)
     print("wrote", out, y.shape, "p =", len(s), "Pi", Pi[:3], "Pi_V", Pi_V[:3])

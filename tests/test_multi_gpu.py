@@ -83,3 +83,27 @@ def test_band_sharded_nlm_from_a_fresh_host_image(tmp_path):
     err_dz = float(np.linalg.norm((z - img) - (refz - img)) / np.linalg.norm(refz - img))
     print(f"NLM world=2: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
     assert err_mu <= 1e-4 and err_z <= 1e-3 and err_dz <= 5e-3
+
+
+@pytest.mark.parametrize("tag,world", [("lion_rgb_photometric500", 2), ("barbara_uniform256", 2), ("cat_small_random50", 4)])
+def test_golden_configs_band_sharded(tmp_path, tag, world):
+    """BASELINE.json config 3 (input/lion.png as RGB, photometric affinity, p = 500) on 2 GPUs -- and configs 2 and 1 sharded as
+    well -- against the same committed fixtures the single-GPU suite uses (tests/golden/make_golden.py)."""
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    parts = _launch(tmp_path, world, "golden:" + tag, 0, 0, 0, "-")
+    g = np.load(os.path.join(ROOT, "tests", "golden", tag + ".npz"))
+    img = g["image"]
+    src = np.repeat(img[:, :, None], 3, axis=2) if int(g["rgb"]) else img
+    z = np.concatenate([p["z"] for p in parts], axis=0).astype(np.float64)
+    assert z.shape == src.shape
+    for p in parts:
+        assert np.array_equal(p["s"], g["sample_indices"])
+        assert np.array_equal(p["mu"], parts[0]["mu"])
+        assert float(p["outside"][0]) == 0.0
+    refz = g["z"].astype(np.float64)
+    err_mu = float(np.max(np.abs(parts[0]["mu"] - g["mu"]) / g["mu"]))
+    err_z = float(np.linalg.norm(z - refz) / np.linalg.norm(refz))
+    err_dz = float(np.linalg.norm((z - src) - (refz - src)) / np.linalg.norm(refz - src))
+    print(f"{tag} world={world}: err_mu={err_mu:.2e} err_z={err_z:.2e} err_dz={err_dz:.2e}")
+    assert err_mu <= 1e-4 and err_z <= 1e-3 and err_dz <= 5e-3
