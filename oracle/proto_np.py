@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY (like the rest of oracle/): numpy restatements of the experimental building blocks of the
-reference's Python prototype that no device kernel covers yet -- kept here, pinned to the reference's own
-functions through tests/golden/pyref_proto.npz (tests/golden/make_golden_proto.py), as the checker for when they are built.
+reference's Python prototype, pinned to the reference's own functions through tests/golden/pyref_proto.npz
+(tests/golden/make_golden_proto.py): the checker of the device versions in csrc/proto.cu (tests/test_proto_gpu.py).
 
 Each function cites the lines of /root/reference/python/image_processing.py it follows.  Eigenvector columns are only
 defined up to sign (and up to rotations inside repeated eigenvalues), so callers compare invariants: Phi diag(Pi) Phi^T,
@@ -61,3 +61,36 @@ def sinkhorn(phi, Pi, iterations=100):
         r = np.nan_to_num(1.0 / (phi @ (Pi * (phi.T @ c))))
     W_AB = (r[:N, None] * phi[:N] * Pi) @ (phi * c[:, None]).T
     return W_AB[:, :N], W_AB[:, N:]
+
+
+def smoothing_matrix(sample_indices, phi, Pi):
+    """smoothing_matrix() (:151-194).  phi has the sample rows first (nystroem()'s order).  K = Phi diag(Pi) Phi^T is only needed
+    through its degrees D = K 1 = Phi (Pi o (Phi^T 1)), alpha = 1 / mean(D), and the first p rows of W = I + alpha (K - diag D):
+    W_A = I + alpha (Phi_A Pi Phi_A^T - diag D_A), W_B = alpha Phi_A Pi Phi_B^T.  Then the eigenpairs (L, Phi_WA) of W_A, descending
+    (:183-185), their extension V = [Phi_WA; W_B^T Phi_WA diag(1/L)] (:186-190), rows permuted back to raster order (:191)."""
+    s = np.asarray(sample_indices, dtype=np.int64)
+    p = len(s)
+    D = phi @ (Pi * (phi.T @ np.ones(phi.shape[0])))
+    alpha = 1.0 / np.mean(D)
+    W_A = np.eye(p) + alpha * ((phi[:p] * Pi) @ phi[:p].T - np.diag(D[:p]))
+    W_B = alpha * (phi[:p] * Pi) @ phi[p:].T
+    L, U = np.linalg.eigh(W_A)
+    L, U = L[::-1], U[:, ::-1]
+    V = np.concatenate((U, W_B.T @ (U / L)))
+    return permutation(V, s), L
+
+
+def smoothing(y, sample_indices, phi, Pi):
+    """smoothing() (:197-219): z = V diag(L) V^T y with (V, L) = smoothing_matrix()."""
+    V, L = smoothing_matrix(sample_indices, phi, Pi)
+    yv = np.asarray(y, dtype=np.float64).reshape(-1)
+    return (V @ (L * (V.T @ yv))).reshape(np.shape(y))
+
+
+def sharpening(y, sample_indices, phi, Pi, beta=1.5):
+    """sharpening() (:222-241): with W = V diag(L) V^T, z = (1 + beta) W^2 y - beta W^3 y, beta = 1.5 (:231)."""
+    V, L = smoothing_matrix(sample_indices, phi, Pi)
+    yv = np.asarray(y, dtype=np.float64).reshape(-1)
+    W = lambda x: V @ (L * (V.T @ x))
+    w2 = W(W(yv))
+    return ((1.0 + beta) * w2 - beta * W(w2)).reshape(np.shape(y))

@@ -225,6 +225,12 @@ def test_prototype_building_blocks_match_the_reference_functions():
     assert np.max(np.abs(W_A - g["W_A"])) < 1e-9 and np.max(np.abs(W_B - g["W_B"])) < 1e-9
     W_A2, _ = pr.sinkhorn(phi, Pi)                        # and from the oracle's own eigenvectors
     assert np.max(np.abs(W_A2 - g["W_A"])) < 1e-6
+    # smoothing_matrix() / smoothing() / sharpening() (:151-241) from the reference's own (phi, Pi)
+    V_s, L_s = pr.smoothing_matrix(s, g["phi"], g["Pi"])
+    assert np.max(np.abs(L_s - g["L_s"])) < 1e-12 and np.max(np.abs(np.abs(V_s) - np.abs(g["V_s"]))) < 1e-9
+    y = g["image"].astype(np.float64)
+    assert np.max(np.abs(pr.smoothing(y, s, g["phi"], g["Pi"]) - g["z_smooth"])) < 1e-9
+    assert np.max(np.abs(pr.sharpening(y, s, g["phi"], g["Pi"]) - g["z_sharp"])) < 1e-9
 
 
 def test_inverse_power_iteration_restatement():
