@@ -42,6 +42,7 @@ EXPORTS = [
     "gl_diag_inverse", "gl_diag_pow", "gl_full_affinity", "gl_full_laplacian", "gl_full_result", "gl_run", "gl_run_resident",
     "gl_mat_info_get", "gl_mat_retain", "gl_mat_destroy", "gl_mat_download", "gl_mat_download_cols", "gl_mat_rowsums", "gl_mat_upload",
     "gl_host_alloc", "gl_host_free", "gl_kb_layout_host",
+    "gl_sinkhorn", "gl_orthogonalisation", "gl_smoothing_matrix", "gl_matrix_filter",
 ]
 
 
@@ -109,6 +110,10 @@ def lib():
         L.gl_nystroem_filter.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_int, C.POINTER(vp), vp, vp]
         L.gl_orthonormalise.argtypes = [vp, vp, vp]
         L.gl_filter.argtypes = [vp, vp, vp, C.c_double, C.c_int, vp, vp]
+        L.gl_sinkhorn.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+        L.gl_orthogonalisation.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp)]
+        L.gl_smoothing_matrix.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp)]
+        L.gl_matrix_filter.argtypes = [vp, vp, vp, vp, C.c_int, vp]
         L.gl_full_affinity.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
         L.gl_full_laplacian.argtypes = [vp, vp, C.POINTER(vp)]
         L.gl_full_result.argtypes = [vp, vp, vp, vp]
@@ -408,6 +413,44 @@ class Context:
         o = C.c_void_p()
         _check(lib().gl_diag_inverse(self.h, d.h, C.byref(o)))
         return Mat(self, o)
+
+    # ---- the prototype's experimental blocks (python/image_processing.py:90-241; csrc/proto.cu) ---------------
+    def sinkhorn(self, phi: Mat, Pi: Mat, iterations=100):
+        """sinkhorn(phi, Pi) (:90-107) on a stored Phi in raster order: returns the handles (W_A [p x p], W_ABt [band pixels x p]);
+        W_ABt.download()[j, i] is the prototype's W_AB[i, j] with its columns back in raster order."""
+        a, b = C.c_void_p(), C.c_void_p()
+        _check(lib().gl_sinkhorn(self.h, phi.h, Pi.h, iterations, C.byref(a), C.byref(b)))
+        return Mat(self, a), Mat(self, b)
+
+    def orthogonalisation(self, K_A: Mat, K_B: Mat):
+        """orthogonalisation(A, B) (:110-127): returns the handles (V [band pixels x p, raster order], Pi [p])."""
+        v, d = C.c_void_p(), C.c_void_p()
+        _check(lib().gl_orthogonalisation(self.h, K_A.h, K_B.h, C.byref(v), C.byref(d)))
+        return Mat(self, v), Mat(self, d)
+
+    def smoothing_matrix(self, phi: Mat, Pi: Mat):
+        """smoothing_matrix(sample_indices, phi, Pi) (:151-194): returns the handles (V [band pixels x p, raster order], L [p])."""
+        v, d = C.c_void_p(), C.c_void_p()
+        _check(lib().gl_smoothing_matrix(self.h, phi.h, Pi.h, C.byref(v), C.byref(d)))
+        return Mat(self, v), Mat(self, d)
+
+    def matrix_filter(self, V: Mat, L: Mat, coef):
+        """z = sum_k coef[k] (V diag(L) V^T)^k y for the current image, float32 [H, W(, C)], not clipped."""
+        H, W, ch = self.shape
+        z = np.zeros((H, W, ch), dtype=np.float32)
+        c = np.ascontiguousarray(coef, dtype=np.float64)
+        _check(lib().gl_matrix_filter(self.h, V.h, L.h, c.ctypes.data, len(c), z.ctypes.data))
+        return z[:, :, 0] if ch == 1 else z
+
+    def smoothing(self, phi: Mat, Pi: Mat):
+        """smoothing(y, sample_indices, phi, Pi) (:197-219): z = V L V^T y with (V, L) = smoothing_matrix."""
+        V, L = self.smoothing_matrix(phi, Pi)
+        return self.matrix_filter(V, L, [0.0, 1.0])
+
+    def sharpening(self, phi: Mat, Pi: Mat, beta=1.5):
+        """sharpening(y, sample_indices, phi, Pi) (:222-241): z = (1 + beta) W^2 y - beta W^3 y, W = V L V^T, beta = 1.5 (:231)."""
+        V, L = self.smoothing_matrix(phi, Pi)
+        return self.matrix_filter(V, L, [0.0, 0.0, 1.0 + beta, -beta])
 
     # ---- the reference's -no_approx mode (matrix-free) -----------------------------------------------
     def full_affinity(self, kind=BILATERAL, h_loc=40.0, h_val=30.0) -> Mat:

@@ -580,6 +580,15 @@ int gl_nystroem(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigvals_inv, gl
                "gl_nystroem: wrong handle kinds");
     GL_REQUIRE(phi_A->rows == L_B->p && eigvals_inv->rows == phi_A->cols, "gl_nystroem: shape mismatch");
     GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (!L_B->dscale) {
+        // a bare K_B (the prototype's nystroem(K_A, K_B), python/image_processing.py:69-88): the factor is 1 instead of -alpha
+        GL_CHECK(gl_alloc(ctx, 2 * sizeof(double), &L_B->dscale));
+        GL_CHECK(gl_ensure_pinned(ctx, 2 * sizeof(double)));
+        ((double*)ctx->pinned)[0] = L_B->scale;
+        ((double*)ctx->pinned)[1] = -L_B->scale;
+        GL_CUDA_CHECK(cudaMemcpyAsync(L_B->dscale->ptr, ctx->pinned, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
     StageTimer t(ctx, GL_T_NYSTROEM);
     // Deferred by default: the handle is complete as far as the caller can tell, the matrix itself is computed when it is
     // first needed.  The reference's driver calls Nystroem and then ComputeResultFromLaplacian (hpc/image_processing.c:
@@ -647,6 +656,37 @@ int gl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip
         if (fuse) return GL_OK;
     }
     return gl_impl_filter(ctx, phi, f_eigvals, gain, clip_low, z_f32, z_u8);
+}
+
+// ---- the prototype's experimental blocks (proto.cu) ----------------------------------------------------------
+int gl_sinkhorn(gl_ctx* ctx, gl_mat* phi, gl_mat* Pi, int iterations, gl_mat** W_A, gl_mat** W_ABt)
+{
+    GL_REQUIRE(ctx && phi && Pi, "gl_sinkhorn: null");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return gl_impl_sinkhorn(ctx, phi, Pi, iterations, W_A, W_ABt);
+}
+
+int gl_orthogonalisation(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** V, gl_mat** Pi)
+{
+    GL_REQUIRE(ctx && K_A && K_B, "gl_orthogonalisation: null");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return gl_impl_orthogonalisation(ctx, K_A, K_B, V, Pi);
+}
+
+int gl_smoothing_matrix(gl_ctx* ctx, gl_mat* phi, gl_mat* Pi, gl_mat** V, gl_mat** L)
+{
+    GL_REQUIRE(ctx && phi && Pi, "gl_smoothing_matrix: null");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return gl_impl_smoothing_matrix(ctx, phi, Pi, V, L);
+}
+
+int gl_matrix_filter(gl_ctx* ctx, gl_mat* V, gl_mat* L, const double* coef, int ncoef, float* z_f32)
+{
+    GL_REQUIRE(ctx && V && L, "gl_matrix_filter: null");
+    GL_REQUIRE(V->q0 == ctx->q0 && V->local_rows == ctx->q1 - ctx->q0, "gl_matrix_filter: V does not belong to the current image");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, GL_T_FILTER);
+    return gl_impl_matrix_filter(ctx, V, L, coef, ncoef, z_f32);
 }
 
 int gl_full_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K)
@@ -790,6 +830,13 @@ __global__ void k_colmajor_f32_to_f64(const float* __restrict__ src, int64_t ld,
     if (i >= rows * cols) return;
     int64_t r = i / cols, c = i % cols;
     dst[i] = (double)src[c * ld + r];
+}
+__global__ void k_f64_to_half_padded(const double* __restrict__ src, int64_t rows, int64_t cols, int64_t ld, __half* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ld) return;
+    int64_t r = i / ld, c = i % ld;
+    dst[i] = __float2half_rn(c < cols ? (float)src[r * cols + c] : 0.f);
 }
 __global__ void k_f64_to_colmajor_f32(const double* __restrict__ src, int64_t rows, int64_t cols, int64_t ld,
                                       float* __restrict__ dst)
@@ -947,6 +994,26 @@ int gl_mat_upload(gl_ctx* ctx, int kind, const double* data, int64_t rows, int64
         cudaMemsetAsync(m->buf->ptr, 0, sizeof(float) * (size_t)(m->ld * cols), ctx->stream);
         k_f64_to_colmajor_f32<<<(unsigned)ceil_div(count, 256), 256, 0, ctx->stream>>>((const double*)stage->ptr, rows, cols,
                                                                                       m->ld, (float*)m->buf->ptr);
+        GL_LAUNCH_CHECK(ctx);
+        gl_buf_release(stage);
+    } else if (kind == GL_MAT_PHI) {
+        // this rank's band rows x cols of a Phi in raster order (tests, host-built bases for gl_filter / the prototype blocks)
+        const int64_t band = ctx->q1 - ctx->q0;
+        if (rows != band || !ctx->samples) {
+            gl_buf_release(stage);
+            delete m;
+            GL_REQUIRE(false, "gl_mat_upload: a Phi needs the %lld rows of this rank's band (got %lld) and a sample set", (long long)band,
+                       (long long)rows);
+        }
+        const int m_pad = gl_m_pad((int)cols);
+        m->rows = ctx->n;
+        m->ld = m_pad;
+        m->elem_bytes = 2;
+        m->p = (int)ctx->p; m->p_pad = ctx->p_pad; m->m = (int)cols; m->m_pad = m_pad; m->q0 = ctx->q0;
+        int rc = gl_alloc(ctx, sizeof(__half) * (size_t)rows * m_pad, &m->buf);
+        if (rc != GL_OK) { gl_buf_release(stage); delete m; return rc; }
+        k_f64_to_half_padded<<<(unsigned)ceil_div(rows * m_pad, 256), 256, 0, ctx->stream>>>((const double*)stage->ptr, rows, cols, m_pad,
+                                                                                           (__half*)m->buf->ptr);
         GL_LAUNCH_CHECK(ctx);
         gl_buf_release(stage);
     } else {

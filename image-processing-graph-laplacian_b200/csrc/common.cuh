@@ -295,6 +295,11 @@ int gl_impl_diag_map(gl_ctx* ctx, gl_mat* d, int op, double arg, gl_mat** out);
 int gl_impl_full_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat** K);
 int gl_impl_full_laplacian(gl_ctx* ctx, gl_mat* K, gl_mat** L);
 int gl_impl_full_result(gl_ctx* ctx, gl_mat* L, float* z_f32, uint8_t* z_u8);
+// the prototype's experimental blocks (proto.cu)
+int gl_impl_sinkhorn(gl_ctx* ctx, gl_mat* phi, gl_mat* Pi, int iterations, gl_mat** W_A, gl_mat** W_ABt);
+int gl_impl_smoothing_matrix(gl_ctx* ctx, gl_mat* phi, gl_mat* Pi, gl_mat** V, gl_mat** L);
+int gl_impl_matrix_filter(gl_ctx* ctx, gl_mat* V, gl_mat* L, const double* coef, int ncoef, float* z_f32);
+int gl_impl_orthogonalisation(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** V, gl_mat** Pi);
 // optional fusion of the filter application into the GEMM epilogue (nystroem_gemm.cu / filter.cu)
 struct gl_gemm_fuse {
     const float* w = nullptr;   // [n_pad][C] filter weights gain * f(lambda) o c

@@ -515,33 +515,32 @@ int gl_impl_sinkhorn(gl_ctx* ctx, gl_mat* phi, gl_mat* Pi, int iterations, gl_ma
         ctx->launches++;
     }
     // W_AB^T for every band pixel: c_j (Phi[j] . Mt[i]); stored relative to max r * max c so that fp16 keeps its precision
-    double hr[2] = {0, 1}, hc[2] = {0, 1};
+    double rmax = 1.0, cmax = 1.0;
     ALLOC(red, double, 4);
+    ALLOC(mxd, double, 2 * ctx->world);
     if (rc == GL_OK) {
         k_sum_absmax<<<1, 1024, 0, ctx->stream>>>(r, rows, red);
         k_sum_absmax<<<1, 1024, 0, ctx->stream>>>(c, rows, red + 2);
         ctx->launches += 2;
-        double mx[2];
-        rc = fetch(ctx, red, 4, hr);   // hr = {sum r, max r}, then {sum c, max c}
-        if (rc == GL_OK) {
-            memcpy(mx, (const double*)ctx->pinned + 2, sizeof(mx));
-            hc[0] = mx[0]; hc[1] = mx[1];
-        }
+        double h4[4];
+        rc = fetch(ctx, red, 4, h4);   // {sum r, max r, sum c, max c}
+        rmax = h4[1];
+        cmax = h4[3];
     }
-    if (rc == GL_OK && ctx->world > 1) {   // the same scale on every rank
-        ALLOC(mxd, double, 2 * ctx->world);
-        GL_CUDA_CHECK(cudaMemsetAsync(mxd, 0, sizeof(double) * 2 * ctx->world, ctx->stream));
-        double mine[2] = {hr[1], hc[1]};
-        GL_CUDA_CHECK(cudaMemcpyAsync(mxd + 2 * ctx->rank, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+    if (rc == GL_OK && ctx->world > 1) {   // the same scales on every rank
+        std::vector<double> all(2 * ctx->world, 0.0);
+        all[2 * ctx->rank] = rmax;
+        all[2 * ctx->rank + 1] = cmax;
+        GL_CUDA_CHECK(cudaMemcpyAsync(mxd, all.data(), sizeof(double) * all.size(), cudaMemcpyHostToDevice, ctx->stream));
         GL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        GL_CHECK(gl_allreduce_f64(ctx, mxd, (size_t)2 * ctx->world));
-        std::vector<double> all(2 * ctx->world);
-        GL_CHECK(fetch(ctx, mxd, 2 * ctx->world, all.data()));
-        for (int k = 0; k < ctx->world; ++k) { hr[1] = std::max(hr[1], all[2 * k]); hc[1] = std::max(hc[1], all[2 * k + 1]); }
+        GL_CHECK(gl_allreduce_f64(ctx, mxd, all.size()));
+        GL_CHECK(fetch(ctx, mxd, (int)all.size(), all.data()));
+        for (int k = 0; k < ctx->world; ++k) { rmax = std::max(rmax, all[2 * k]); cmax = std::max(cmax, all[2 * k + 1]); }
     }
     gl_mat* WB = nullptr;
     if (rc == GL_OK) {
-        const double rmax = (hr[1] > 0 && std::isfinite(hr[1])) ? hr[1] : 1.0, cmax = (hc[1] > 0 && std::isfinite(hc[1])) ? hc[1] : 1.0;
+        if (!(rmax > 0 && std::isfinite(rmax))) rmax = 1.0;
+        if (!(cmax > 0 && std::isfinite(cmax))) cmax = 1.0;
         int ex;
         std::frexp(rmax, &ex);
         rc = phi_times_small(ctx, phi, Mt, p, c, 1.0 / cmax, std::ldexp(1.0, 12 - ex), nullptr, &WB);
@@ -689,7 +688,6 @@ int gl_impl_orthogonalisation(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** V_
     ALLOC(Z2, double, pp);
     ALLOC(red, double, 2);
     // Y_0 = A / s, Z_0 = I;  T = (3 I - Z Y) / 2;  Y <- Y T, Z <- T Z;  Y -> (A/s)^1/2, Z -> (A/s)^-1/2
-    GL_CHECK(gl_dgemm(ctx, p, p, p, 1.0, A, p, 0, A, p, 1, 0.0, T, p));      // only for |A|_F^2 = trace(A A^T) ... cheaper: direct
     k_sum_absmax<<<1, 1024, 0, ctx->stream>>>(A, (int64_t)pp, red);
     GL_LAUNCH_CHECK(ctx);
     double h[2];
@@ -769,9 +767,8 @@ int gl_impl_orthogonalisation(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** V_
         ctx->launches++;
         GL_BREAK(rc, eig_desc(ctx, Qm, &UQ, &PQ, nullptr));
         // M = X Phi_Q Pi_Q^-1/2  (p x p)
-        double *U64 = Y2, *M = Z2, *isq = nullptr, *AM = nullptr;
+        double *U64 = Y2, *M = Z2, *isq = nullptr;
         GL_BREAK(rc, bufs.get(ctx, sizeof(double) * (size_t)p, (void**)&isq));
-        GL_BREAK(rc, bufs.get(ctx, sizeof(double) * pp, (void**)&AM));
         k_cm32_to_rm64<<<nblk((int64_t)pp), 256, 0, ctx->stream>>>((const float*)UQ->buf->ptr, (int)UQ->ld, p, p, U64);
         k_map_diag<<<nblk(p), 256, 0, ctx->stream>>>((const double*)PQ->buf->ptr, p, 1, isq);
         ctx->launches += 2;
@@ -799,7 +796,6 @@ int gl_impl_orthogonalisation(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** V_
         GL_BREAK(rc, gl_alloc(ctx, sizeof(double) * (size_t)p, &Pi->buf));
         k_map_diag<<<nblk(p), 256, 0, ctx->stream>>>((const double*)PQ->buf->ptr, p, 2, (double*)Pi->buf->ptr);
         ctx->launches++;
-        (void)AM;
     } while (0);
     gl_mat_destroy(Qm);
     if (UQ) gl_mat_destroy(UQ);

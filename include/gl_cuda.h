@@ -186,6 +186,29 @@ GL_API int gl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, i
 GL_API int gl_diag_inverse(gl_ctx* ctx, gl_mat* d, gl_mat** out);
 GL_API int gl_diag_pow(gl_ctx* ctx, gl_mat* d, double power, gl_mat** out);
 
+/* ---- the experimental blocks of the reference's Python prototype (csrc/proto.cu) ---------------------------------
+ * They work on a STORED Phi in raster order (from gl_nystroem -- also on a bare K_B with the eigenpairs of K_A, which is the
+ * prototype's nystroem(K_A, K_B), python/image_processing.py:69-88 -- or uploaded with gl_mat_upload(GL_MAT_PHI)) and on the
+ * context's current samples; the prototype's "sample rows first" order and its permutation() do not exist here.
+ *   gl_sinkhorn          <- sinkhorn(phi, Pi)                python/image_processing.py:90-107
+ *   gl_orthogonalisation <- orthogonalisation(A, B)          python/image_processing.py:110-127
+ *   gl_smoothing_matrix  <- smoothing_matrix(s, phi, Pi)     python/image_processing.py:151-194
+ *   gl_matrix_filter     <- smoothing / sharpening           python/image_processing.py:197-241 */
+/* `iterations` (the prototype: 100) alternating scalings r, c of K = Phi diag(Pi) Phi^T from r = 1, then the sample rows of
+ * diag(r) K diag(c): W_A (p x p, GL_MAT_KA) and, for every pixel j of this rank's band, W_ABt[j][i] = (diag(r) K diag(c))[s_i][j]
+ * (Phi-shaped, band pixels x p; the prototype's W_B is its transpose without the sample pixels' rows).  Either may be NULL. */
+GL_API int gl_sinkhorn(gl_ctx* ctx, gl_mat* phi, gl_mat* Pi, int iterations, gl_mat** W_A, gl_mat** W_ABt);
+/* One-shot orthogonal Nystroem extension of the affinity blocks gl_affinity returned for the current image and samples:
+ * V (Phi-shaped, band pixels x p, orthonormal columns over the whole image, raster order) and Pi = min(eigenvalues of
+ * A + A^-1/2 B B^T A^-1/2, 1), descending.  Bilateral / photometric / spatial affinity; K_A must be positive definite. */
+GL_API int gl_orthogonalisation(gl_ctx* ctx, gl_mat* K_A, gl_mat* K_B, gl_mat** V, gl_mat** Pi);
+/* From the approximation K = Phi diag(Pi) Phi^T: D = K 1, alpha = 1 / mean(D), W = I + alpha (K - diag D); eigenpairs (L, descending)
+ * of its sample block and their Nystroem extension V (Phi-shaped, band pixels x p, sample rows = the eigenvectors). */
+GL_API int gl_smoothing_matrix(gl_ctx* ctx, gl_mat* phi, gl_mat* Pi, gl_mat** V, gl_mat** L);
+/* z = sum_k coef[k] W^k y for W = V diag(L) V^T and the current image y (every channel), not clipped: smoothing() is
+ * coef = {0, 1}, sharpening() is {0, 0, 1 + beta, -beta} with beta = 1.5.  z_f32: n * C floats, this rank's band at its raster offset. */
+GL_API int gl_matrix_filter(gl_ctx* ctx, gl_mat* V, gl_mat* L, const double* coef, int ncoef, float* z_f32);
+
 /* ---- the reference's -no_approx mode, matrix-free (csrc/full_filter.cu) ----------------------------------
  *   gl_full_affinity  <- ComputeEntireAffinityMatrix       hpc/affinity.c:264-336
  *   gl_full_laplacian <- ComputeEntireLaplacianMatrix      hpc/laplacian.c:44-65
@@ -218,7 +241,8 @@ GL_API int gl_mat_download(gl_ctx* ctx, const gl_mat* m, double* out, size_t cap
 GL_API int gl_mat_download_cols(gl_ctx* ctx, const gl_mat* m, int col0, int ncols, double* out, size_t cap);
 /* D = rowsum(K_A)+rowsum(K_B) carried by a KB handle (p doubles), already summed over ranks. */
 GL_API int gl_mat_rowsums(gl_ctx* ctx, const gl_mat* K_B, double* out, size_t cap);
-/* Upload a host fp64 row-major matrix as GL_MAT_KA / GL_MAT_EIGVEC / GL_MAT_DIAG (tests, host-built inputs). */
+/* Upload a host fp64 row-major matrix as GL_MAT_KA / GL_MAT_EIGVEC / GL_MAT_DIAG, or as GL_MAT_PHI (this rank's band rows x cols, raster
+ * order; needs the image geometry and a sample set) (tests, host-built inputs). */
 GL_API int gl_mat_upload(gl_ctx* ctx, int kind, const double* data, int64_t rows, int64_t cols, gl_mat** out);
 
 /* ---- inspection (host only, no GPU needed) ------------------------------------------------------------------------
