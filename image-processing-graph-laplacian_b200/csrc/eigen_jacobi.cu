@@ -71,10 +71,12 @@ __device__ __forceinline__ void tournament(int step, int pair, int nb, int& a, i
 // otherwise the Gram block is accumulated chunk by chunk and the chunks are fetched a second time for the rotation.
 __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc, int I, int J, float tol, int inner_max, float* P, float* red,
                                             double* Bm, double* Qm, double* cs, int* role, int* pq, float* s_off, unsigned* s_cta_off,
-                                            unsigned* __restrict__ pmask)
+                                            unsigned* __restrict__ pmask, long long* __restrict__ pprof = nullptr)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     const int bi = tid >> 4, bj = tid & 15;  // this thread's element of the 16 x 16 block
+#define PPROF(k) do { if (pprof && tid == 0) pprof[k] = clock64(); } while (0)
+    PPROF(0);
     float* GI = G + (size_t)I * p * JB;
     float* GJ = G + (size_t)J * p * JB;
     const int nchunks = (p + pc - 1) / pc;
@@ -83,7 +85,15 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
     const int cr = jacobi_chunk_rows(p);
     const unsigned occ = nchunks == 1 ? (__ldcg(&pmask[I]) | __ldcg(&pmask[J])) : 0xffffffffu;
     const int n_occ = nchunks == 1 ? __popc(occ) * cr : p;
-    auto actual_row = [&](int k) -> int { return nchunks == 1 ? (int)__fns(occ, 0, k / cr + 1) * cr + k % cr : k; };
+    // (the k-th occupied chunk comes from a small table: __fns is a software loop, and sat in every row of the loads and the apply)
+    __shared__ int s_list[32];
+    if (nchunks == 1 && tid < 32 && ((occ >> tid) & 1u)) s_list[__popc(occ & ((1u << tid) - 1u))] = tid;
+    __syncthreads();
+    auto actual_row = [&](int k) -> int {
+        if (nchunks != 1) return k;
+        const int ch = k / cr;
+        return s_list[ch] * cr + (k - ch * cr);
+    };
     // rows [r0, r0 + n) of the panel pair -> P (L2 loads: the data was written by other SMs)
     auto load_chunk = [&](int r0, int n) {
         for (int idx = tid; idx < 2 * n; idx += J_THREADS) {
@@ -129,6 +139,7 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
             for (int y = 0; y < 4; ++y) red[rg * 256 + (4 * ti + x) * 16 + 4 * tj + y] = acc[x][y];
     }
     __syncthreads();
+    PPROF(1);
     {
         double s = 0.0;
 #pragma unroll
@@ -151,6 +162,7 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
     __syncthreads();
     const float pair_off = __uint_as_float(*s_cta_off);
     // ---- diagonalise the 16 x 16 block: cyclic two-sided Jacobi, Q accumulates the rotations ----
+    PPROF(2);
     if (pair_off > 0.25f * tol) {
         if (tid == 0) *s_off = 0.f;
         __syncthreads();
@@ -216,6 +228,7 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
             __syncthreads();
             if (inner_off <= 0.1f * tol) break;
         }
+        PPROF(3);
         // ---- apply: [G_I G_J] <- [G_I G_J] Q, streamed straight back to global ----
         const int cgp = tid & 3;
         float q[JP][4];
@@ -263,6 +276,8 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
         }
     }
     __syncthreads();
+    PPROF(4);
+#undef PPROF
 }
 
 // The whole solve in ONE cooperative launch.  Per sweep:
@@ -295,6 +310,8 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
     int* pq = role + JP;                     // [8][2]
     __shared__ float s_off;
     __shared__ unsigned s_cta_off;
+    __shared__ short s_cls[2 * 1024];        // non-empty (distance, parity) classes of the sweep: nb <= 1024 panels (p <= 8192)
+    __shared__ int s_ncls, s_wcnt[J_THREADS / 32];
 
     const int tid = threadIdx.x;
     const int cp = nb * JB;
@@ -347,12 +364,18 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                 const int cr = jacobi_chunk_rows(p);
                 const int nsub = (cr + 31) / 32;                 // 32-row staging steps per row chunk
                 const int steps = __popc(both) * nsub;
-                auto step_row0 = [&](int s_) -> int { return (int)__fns(both, 0, s_ / nsub + 1) * cr + (s_ % nsub) * 32; };
-                auto step_rows = [&](int s_) -> int { return min(32, cr - (s_ % nsub) * 32); };
+                // cursor of the step being FETCHED (one ahead of the step being multiplied): lowest remaining chunk, sub-step in it
+                unsigned rest = both;
+                int sub = 0, nrow_next = 0;
                 float4 a0, a1, b0, b1;
-                if (steps > 0) fetch(step_row0(0), a0, a1, b0, b1);
+                auto fetch_next = [&]() {
+                    nrow_next = min(32, cr - sub * 32);
+                    fetch((__ffs(rest) - 1) * cr + sub * 32, a0, a1, b0, b1);
+                    if (++sub == nsub) { sub = 0; rest &= rest - 1u; }
+                };
+                if (steps > 0) fetch_next();
                 for (int st = 0; st < steps; ++st) {
-                    const int nrow = step_rows(st);
+                    const int nrow = nrow_next;
                     __syncthreads();
                     const bool live = lr < nrow;
                     *(float4*)&As[lr * 68 + lp * 8] = live ? a0 : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -360,7 +383,7 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                     *(float4*)&Bs[lr * 68 + lp * 8] = live ? b0 : make_float4(0.f, 0.f, 0.f, 0.f);
                     *(float4*)&Bs[lr * 68 + lp * 8 + 4] = live ? b1 : make_float4(0.f, 0.f, 0.f, 0.f);
                     __syncthreads();
-                    if (st + 1 < steps) fetch(step_row0(st + 1), a0, a1, b0, b1);
+                    if (st + 1 < steps) fetch_next();
 #pragma unroll 8
                     for (int k = 0; k < 32; ++k) {
                         const float4 a = *(const float4*)&As[k * 68 + ty * 4];
@@ -443,18 +466,39 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                 grid.sync();
             }
         } else {
-            for (int d = 1; d < nb; ++d)
-                for (int par = 0; par < 2; ++par) {
-                    if (__ldcg(&cnt[2 * d + par]) == 0) continue;   // uniform over the grid: no barrier needed
+            // the non-empty classes, gathered once (polling cnt[] class by class cost an L2 round trip for each of the 2 (nb - 1) classes,
+            // ~110 000 cycles per sweep at p = 1000, most of them empty); every CTA builds the same list in the same order
+            __syncthreads();
+            if (tid == 0) s_ncls = 0;
+            __syncthreads();
+            for (int base = 2; base < 2 * nb; base += J_THREADS) {
+                const int k = base + tid;
+                const bool live = k < 2 * nb && __ldcg(&cnt[k]) != 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, live);
+                if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(bal);
+                __syncthreads();
+                int before = s_ncls;
+                for (int w = 0; w < (tid >> 5); ++w) before += s_wcnt[w];
+                if (live) s_cls[before + __popc(bal & ((1u << (tid & 31)) - 1u))] = (short)k;
+                __syncthreads();
+                if (tid == 0) { int t = 0; for (int w = 0; w < J_THREADS / 32; ++w) t += s_wcnt[w]; s_ncls += t; }
+                __syncthreads();
+            }
+            const int ncls = s_ncls;
+            for (int ci = 0; ci < ncls; ++ci) {
+                {
+                    const int d = s_cls[ci] >> 1, par = s_cls[ci] & 1;
                     const int ncand = ((nb + 2 * d - 1) / (2 * d)) * d;
                     for (int c = blockIdx.x; c < ncand; c += gridDim.x) {
                         const int I = (c / d) * 2 * d + par * d + (c % d), J = I + d;
                         if (J < nb && __ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
-                            jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off, pmask);
+                            jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off, pmask,
+                                        (jprof && blockIdx.x == 0) ? jprof + 40 : nullptr);
                     }
                     grid.sync();
                     JPROF();
                 }
+            }
         }
     }
     JPROF();
@@ -484,12 +528,29 @@ __global__ void k_jacobi_norms(const float* __restrict__ G, int p, double* __res
 __global__ void __launch_bounds__(256) k_rayleigh_partial(const double* __restrict__ A, const float* __restrict__ G, int p,
                                                           double* __restrict__ part /* [row_tiles][cols_pad] */, int cols_pad,
                                                           int cols /* columns that exist in G */,
-                                                          const unsigned char* __restrict__ nz /* [row_tiles][ceil(p/16)] or null */)
+                                                          const unsigned char* __restrict__ nz /* [row_tiles][ceil(p/16)] or null */,
+                                                          const unsigned* __restrict__ pmask /* occupied row chunks of G's panels, or null */,
+                                                          int nb)
 {
     __shared__ double As[16][64 + 1], Us[16][64 + 1];
     __shared__ double red[16][64];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int j0 = blockIdx.x * 64, i0 = blockIdx.y * 64;
+    // row chunks in which any of this tile's 64 columns of G may be non-zero: rows outside contribute neither to V = A G (as the k
+    // index) nor to the numerator sum_i G[i][c] V[i][c] (as the row index) -- a tile whose 64 rows miss them all has nothing to add
+    unsigned gm = 0xffffffffu;
+    const int cr = jacobi_chunk_rows(p);
+    if (pmask) {
+        gm = 0u;
+        for (int q = 0; q < 8; ++q) if (blockIdx.x * 8 + q < nb) gm |= pmask[blockIdx.x * 8 + q];
+        const int ca = i0 / cr, cb = min(i0 + 63, p - 1) / cr;
+        unsigned rows_mask = 0u;
+        for (int c = ca; c <= cb; ++c) rows_mask |= 1u << c;
+        if (!(gm & rows_mask)) {
+            if (threadIdx.x < 64) part[(size_t)blockIdx.y * cols_pad + j0 + threadIdx.x] = 0.0;
+            return;
+        }
+    }
     double acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -498,6 +559,7 @@ __global__ void __launch_bounds__(256) k_rayleigh_partial(const double* __restri
     const int nz_ld = (p + 15) >> 4;
     for (int k0 = 0; k0 < p; k0 += 16) {
         if (nz && !nz[(size_t)blockIdx.y * nz_ld + (k0 >> 4)]) continue;   // this chunk of A is all zeros (block-uniform)
+        if (!((gm >> (k0 / cr)) & 1u) && !((gm >> (min(k0 + 15, p - 1) / cr)) & 1u)) continue;   // these rows of G are zero in all 64 columns
         for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
             const int kk = idx & 15, ii = idx >> 4;          // A[i0+ii][k0+kk], 16 contiguous doubles per row
             const int i = i0 + ii, k = k0 + kk;
@@ -687,7 +749,8 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
             cudaStreamSynchronize(ctx->stream);
             fprintf(stderr, "[jacobi prof] %lld marks, cycles between:", h[63]);
             for (int i = 1; i < (int)h[63]; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
-            fprintf(stderr, "  total %lld\n", h[h[63] - 1] - h[0]);
+            fprintf(stderr, "  total %lld | last pair of CTA 0: gram %lld reduce+off %lld inner %lld apply %lld\n", h[h[63] - 1] - h[0], h[41] - h[40],
+                    h[42] - h[41], h[43] - h[42], h[44] - h[43]);
             gl_buf_release(jprof);
         }
 
@@ -697,7 +760,8 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
             dim3 gr((unsigned)ceil_div(cols_pad, 64), (unsigned)row_tiles);
             k_rayleigh_partial<<<gr, 256, 0, ctx->stream>>>((const double*)L_A->buf->ptr, (const float*)G->ptr, p, (double*)part->ptr,
                                                             cols_pad + 64, cols_pad,
-                                                            L_A->aux ? (const unsigned char*)L_A->aux->ptr : nullptr);
+                                                            L_A->aux ? (const unsigned char*)L_A->aux->ptr : nullptr,
+                                                            p < 3072 ? (const unsigned*)pmaskb->ptr : nullptr, nb);
             GL_LAUNCH_CHECK(ctx);
             k_rayleigh_finish<<<(unsigned)ceil_div(p, 128), 128, 0, ctx->stream>>>((const double*)part->ptr, row_tiles, cols_pad + 64, p,
                                                                                    (const double*)lam->ptr, (double*)ray->ptr);
