@@ -114,6 +114,23 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def timed_steps(ctx, steps, step):
+    """Device time of exactly `steps` steps in ms: every step sits between its own pair of CUDA events on the library stream, and between
+    two steps the L2 is flushed (256 MB of scratch written on the same stream, outside the event pairs), so that no step finds anything
+    of the previous one in the cache.  Nothing synchronises with the host inside the loop; the event pairs are read afterwards."""
+    total, done = 0.0, 0
+    while done < steps:
+        n = min(60, steps - done)          # 128 event slots
+        for i in range(n):
+            ctx.flush_l2()
+            ctx.mark(2 * i)
+            step()
+            ctx.mark(2 * i + 1)
+        total += sum(ctx.elapsed_ms(2 * i, 2 * i + 1) for i in range(n))
+        done += n
+    return total
+
+
 def sample_band_rows(width, height, p_req):
     """Rows of the bounded CPU sample: one sixteenth of config 4's image (135 of 2160 rows, 0.52 Mpixel, ~1e12 GEMM flops), the
     same amount of work for the other workloads; never fewer than 4 rows nor more than the image."""
@@ -125,8 +142,7 @@ def workload_config(name, gram_schmidt=0):
     width, height, channels, p_req, sampling, affinity = WORKLOADS[name]
     return dict(workload=DESCR[name], width=width, height=height, channels=channels, p_requested=p_req, sampling=sampling,
                 affinity=affinity, seed_image=SEED_IMG, seed_samples=SEED_SAMPLES, gram_schmidt=gram_schmidt,
-                l2="no flush between steps: every step streams far more than the 126 MB L2 (K_B tiles, row partials)"
-                   if width * height >= 1 << 21 else "small image: the step's working set fits the L2 and is NOT flushed (L2-warm numbers)")
+                l2="flushed between timed steps: 2 x the L2 size of scratch written on the library stream before every step, outside the step's event pair")
 
 
 def cpu_sample(width, height, channels, p_req, sampling, affinity, band_rows):
@@ -284,12 +300,8 @@ def main():
         clocks.start()
     l0 = ctx.kernel_launches()
     barrier()
-    ctx.mark(0)
-    for _ in range(args.steps):
-        ctx.run_resident(prm)
-    ctx.mark(1)
+    t_dev = timed_steps(ctx, args.steps, lambda: ctx.run_resident(prm))
     barrier()
-    t_dev = ctx.elapsed_ms(0, 1)
     launches = ctx.kernel_launches() - l0
     stage = ctx.stage_ms()          # last step's per-stage / per-kernel CUDA-event times
     # a second pass that reads the per-stage timers every step (the read synchronises, so it is kept out of the
@@ -311,18 +323,10 @@ def main():
     for _ in range(2):
         ctx.run(img_pin.array, prm, z_out=False, z8_out=z8_pin.array, want_eigvals=False)
     barrier()
-    ctx.mark(2)
-    for _ in range(args.steps):
-        ctx.run(img_pin.array, prm, z_out=False, z8_out=z8_pin.array, want_eigvals=False)
-    ctx.mark(3)
+    t_e2e = timed_steps(ctx, args.steps, lambda: ctx.run(img_pin.array, prm, z_out=False, z8_out=z8_pin.array, want_eigvals=False))
     barrier()
-    t_e2e = ctx.elapsed_ms(2, 3)
-    ctx.mark(4)
-    for _ in range(args.steps):
-        ctx.run(img_pin.array, prm, z_out=z_pin.array, want_eigvals=False)
-    ctx.mark(5)
+    t_e2e_f32 = timed_steps(ctx, args.steps, lambda: ctx.run(img_pin.array, prm, z_out=z_pin.array, want_eigvals=False))
     barrier()
-    t_e2e_f32 = ctx.elapsed_ms(4, 5)
     clk = clocks.stop() if rank == 0 else None
     parity = parity_vs_golden(args.workload, ctx, prm, width, height, channels, gd, dist)
 
@@ -436,7 +440,7 @@ def main():
     aff_ext_tf_dense_equiv = (f_aff + f_ext) / t_ae / 1e12
 
     # ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
-    NCU_TRAFFIC = {("c4", 1, "patch"): (None, "profiles/r02_ncu_patch_c4.txt"),
+    NCU_TRAFFIC = {("c4", 1, "patch"): (573.9e6, "profiles/r02_ncu_full_c4_v2.txt"),   # 542.4 MB read + 31.5 MB written
                    ("c4", 1, "nostore"): (NOSTORE_TRAFFIC, "profiles/r01_ncu_full_c4_v6.txt"),
                    ("c4", 1, "stored"): (19.14e9, "profiles/r01_ncu_full_c4_v5.txt"),
                    ("c4", 1, "dense"): (33.9e9, "profiles/r01_ncu_full_c4.txt")}
@@ -455,7 +459,7 @@ def main():
         sol["bound_ms"] = max(sol.values())
         sol["frac_of_bound"] = sol["bound_ms"] / med["k_gemm"] if med["k_gemm"] > 0 else 0.0
         sol["note"] = ("lower bounds of this kernel's time from its three resources: tensor pipe (issued MMA flops / measured burst peak), HBM "
-                       "(K_B tiles + row partials / measured copy bandwidth), CUDA cores (one fp32 FMA per Phi element for the fused filter / "
+                       "(K_B tiles and the image in, the result out / measured copy bandwidth), CUDA cores (one fp32 FMA per Phi element for the fused filter / "
                        "measured 85.3 FMA per clock per SM: three register-pair operands per FFMA2 make the register file the limit)")
         roof = dict(kernel="k_patch_nystroem (Nystroem extrapolation over the K_B patch tiles on tcgen05, filter fused, Phi not stored)",
                     bound="tensor", achieved=gemm_tf_exec, peak=peaks["tf_burst"], unit="TFLOP/s", frac=gemm_tf_exec / peaks["tf_burst"],

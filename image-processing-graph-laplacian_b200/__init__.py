@@ -34,7 +34,7 @@ STAGES = ["h2d", "sampling", "affinity", "laplacian", "eigen", "nystroem", "gram
 EXPORTS = [
     "gl_version", "gl_last_error", "gl_default_params", "gl_device_count", "gl_memory_stats", "gl_kernel_launches",
     "gl_ctx_create", "gl_ctx_destroy", "gl_ctx_sync", "gl_ctx_stage_ms", "gl_ctx_set_option", "gl_ctx_mark",
-    "gl_ctx_mark_elapsed_ms",
+    "gl_ctx_mark_elapsed_ms", "gl_ctx_flush_l2",
     "gl_comm_unique_id", "gl_comm_init",
     "gl_set_image", "gl_set_image_rows", "gl_set_synthetic_image", "gl_get_image", "gl_get_band",
     "gl_sampling_uniform", "gl_sampling_random", "gl_set_samples", "gl_get_samples",
@@ -91,6 +91,7 @@ def lib():
         L.gl_memory_stats.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int]
         L.gl_ctx_mark.argtypes = [vp, C.c_int]
         L.gl_ctx_mark_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.gl_ctx_flush_l2.argtypes = [vp, C.c_size_t]
         L.gl_comm_unique_id.argtypes = [vp]
         L.gl_comm_init.argtypes = [vp, vp]
         L.gl_set_image.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
@@ -287,6 +288,10 @@ class Context:
 
     def mark(self, slot):
         _check(lib().gl_ctx_mark(self.h, slot))
+
+    def flush_l2(self, nbytes=0):
+        """write scratch (default: twice the L2 size) on the context stream: evicts the L2 between timed iterations"""
+        _check(lib().gl_ctx_flush_l2(self.h, nbytes))
 
     def elapsed_ms(self, a, b) -> float:
         ms = C.c_float()

@@ -100,7 +100,7 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
         GL_CUDA_CHECK(cudaEventCreate(&ctx->ev_begin[i]));
         GL_CUDA_CHECK(cudaEventCreate(&ctx->ev_end[i]));
     }
-    for (int i = 0; i < 8; ++i) GL_CUDA_CHECK(cudaEventCreate(&ctx->marks[i]));
+    for (int i = 0; i < GL_MARKS; ++i) GL_CUDA_CHECK(cudaEventCreate(&ctx->marks[i]));
     GL_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->stat_ev, cudaEventDisableTiming));
     GL_CUDA_CHECK(cudaMallocHost((void**)&ctx->hstat, sizeof(int) * GL_DS_COUNT));
     memset(ctx->hstat, 0, sizeof(int) * GL_DS_COUNT);
@@ -200,6 +200,7 @@ int gl_ctx_destroy(gl_ctx* ctx)
     if (ctx->tile_starts) gl_buf_release(ctx->tile_starts);
     if (ctx->tile_perm) gl_buf_release(ctx->tile_perm);
     if (ctx->dstat) gl_buf_release(ctx->dstat);
+    if (ctx->flush_buf) gl_buf_release(ctx->flush_buf);
     if (ctx->hstat) cudaFreeHost(ctx->hstat);
     if (ctx->stat_ev) cudaEventDestroy(ctx->stat_ev);
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
@@ -209,7 +210,7 @@ int gl_ctx_destroy(gl_ctx* ctx)
         cudaEventDestroy(ctx->ev_begin[i]);
         cudaEventDestroy(ctx->ev_end[i]);
     }
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->marks[i]);
+    for (int i = 0; i < GL_MARKS; ++i) cudaEventDestroy(ctx->marks[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GL_OK;
@@ -228,16 +229,32 @@ int gl_ctx_stage_ms(gl_ctx* ctx, float* ms)
 
 int gl_ctx_mark(gl_ctx* ctx, int slot)
 {
-    GL_REQUIRE(ctx && slot >= 0 && slot < 8, "gl_ctx_mark: bad slot");
+    GL_REQUIRE(ctx && slot >= 0 && slot < GL_MARKS, "gl_ctx_mark: bad slot");
     GL_CUDA_CHECK(cudaEventRecord(ctx->marks[slot], ctx->stream));
     return GL_OK;
 }
 
 int gl_ctx_mark_elapsed_ms(gl_ctx* ctx, int a, int b, float* ms)
 {
-    GL_REQUIRE(ctx && ms && a >= 0 && a < 8 && b >= 0 && b < 8, "gl_ctx_mark_elapsed_ms: bad args");
+    GL_REQUIRE(ctx && ms && a >= 0 && a < GL_MARKS && b >= 0 && b < GL_MARKS, "gl_ctx_mark_elapsed_ms: bad args");
     GL_CUDA_CHECK(cudaEventSynchronize(ctx->marks[b]));
     GL_CUDA_CHECK(cudaEventElapsedTime(ms, ctx->marks[a], ctx->marks[b]));
+    return GL_OK;
+}
+
+// Writes `bytes` of scratch on the context stream (benchmarks: evicts the L2 between timed iterations; 0 = twice the L2 size).
+int gl_ctx_flush_l2(gl_ctx* ctx, size_t bytes)
+{
+    GL_REQUIRE(ctx, "gl_ctx_flush_l2: null");
+    GL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (bytes == 0) {
+        int l2 = 0;
+        GL_CUDA_CHECK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device));
+        bytes = (size_t)2 * (size_t)(l2 > 0 ? l2 : (128 << 20));
+    }
+    if (ctx->flush_buf && ctx->flush_buf->bytes < bytes) { gl_buf_release(ctx->flush_buf); ctx->flush_buf = nullptr; }
+    if (!ctx->flush_buf) GL_CHECK(gl_alloc(ctx, bytes, &ctx->flush_buf));
+    GL_CUDA_CHECK(cudaMemsetAsync(ctx->flush_buf->ptr, 0x5a, bytes, ctx->stream));
     return GL_OK;
 }
 

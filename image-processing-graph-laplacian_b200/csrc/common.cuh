@@ -129,6 +129,7 @@ struct gl_mat {
 // context
 // ---------------------------------------------------------------------------------------------
 struct gl_nccl;  // comm.cu
+#define GL_MARKS 128
 
 struct gl_ctx {
     int device = 0, rank = 0, world = 1;
@@ -187,7 +188,8 @@ struct gl_ctx {
     // stage timers
     cudaEvent_t ev_begin[GL_T_COUNT] = {}, ev_end[GL_T_COUNT] = {};
     bool ev_valid[GL_T_COUNT] = {};
-    cudaEvent_t marks[8] = {};
+    cudaEvent_t marks[GL_MARKS] = {};
+    gl_buf* flush_buf = nullptr;   // scratch of gl_ctx_flush_l2
 
     // pinned staging for small D2H/H2D
     void* pinned = nullptr;

@@ -269,7 +269,7 @@ k_patch_affinity(Geom g, const uint8_t* __restrict__ img, const float* __restric
                 __half2 h2 = __floats2half2_rn(kv[4], kv[5]), h3 = __floats2half2_rn(kv[6], kv[7]);
                 uint4 pk;
                 pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
-                *(uint4*)&kb_patch[((size_t)(mt * pi.y + b) * 128 + (size_t)((i & 1) * PW + ty)) * SLOTS + tx * 8] = pk;
+                if (KB) *(uint4*)&kb_patch[((size_t)(mt * pi.y + b) * 128 + (size_t)((i & 1) * PW + ty)) * SLOTS + tx * 8] = pk;
             }
             // sums: lanes sharing tx (xor 4, 8, 16), then the 8 warps through shared memory, in a fixed order (deterministic)
 #pragma unroll
@@ -739,7 +739,10 @@ static int launch_patch_affinity(gl_ctx* ctx, const pt::Geom& g, double h_loc, d
     StageTimer kt(ctx, GL_T_K_AFFINITY_B);
     pt::k_patch_affinity<KIND, C><<<grid, 256, smem, ctx->stream>>>(g, (const uint8_t*)ctx->img->ptr, sf, p_pad, (float)(-log2e / (h_loc * h_loc)),
                                                                    (float)(-log2e / (h_val * h_val)), (const int4*)KB->pt_info->ptr,
-                                                                   (const uint32_t*)KB->pt_slots->ptr, (__half*)KB->pt_buf->ptr, partial,
+                                                                   (const uint32_t*)KB->pt_slots->ptr,
+                                                                   // (measurement switch: the sums-only pass a fused affinity + extrapolation
+                                                                   // kernel would still need before the eigensolve; z is garbage with it)
+                                                                   getenv("GLB200_PT_SUMS_ONLY") ? nullptr : (__half*)KB->pt_buf->ptr, partial,
                                                                    (const int*)ctx->dstat->ptr);
     GL_LAUNCH_CHECK(ctx);
     return GL_OK;

@@ -127,9 +127,12 @@ GL_API int gl_ctx_destroy(gl_ctx* ctx);
 GL_API int gl_ctx_sync(gl_ctx* ctx);
 GL_API int gl_ctx_stage_ms(gl_ctx* ctx, float* ms /* [GL_T_COUNT] */); /* CUDA-event times of the last run of each stage */
 GL_API int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value); /* tuning knobs, see DESIGN.md */
-/* CUDA-event marks on the context stream (slot 0..7) and the device time between two of them. */
+/* CUDA-event marks on the context stream (slot 0..127) and the device time between two of them. */
 GL_API int gl_ctx_mark(gl_ctx* ctx, int slot);
 GL_API int gl_ctx_mark_elapsed_ms(gl_ctx* ctx, int slot_a, int slot_b, float* ms);
+/* Benchmarks: write `bytes` of scratch on the context stream so that nothing of the previous iteration stays in the L2
+ * (0 = twice the device's L2 size). */
+GL_API int gl_ctx_flush_l2(gl_ctx* ctx, size_t bytes);
 /* NCCL bootstrap (world > 1): rank 0 makes a 128-byte id, the host shares it, every rank joins. */
 GL_API int gl_comm_unique_id(void* id128);
 GL_API int gl_comm_init(gl_ctx* ctx, const void* id128);
