@@ -604,6 +604,64 @@ __global__ void __launch_bounds__(256) k_rayleigh_partial(const double* __restri
     }
 }
 
+// The same quotients when the occupancy masks of G's panels are valid (p < 3072), one CTA per column: g_c is non-zero only in the
+// occupied row chunks of its panel (~15 % of the rows at 4K), so (A g_c)_i is needed for those rows i only and sums over those k
+// only -- p x occ x occ products instead of p^3 / 3.  Also writes the column norm (k_jacobi_norms) -- one launch instead of three.
+// Fixed summation order: every rank of a multi-GPU run gets identical bits.
+__global__ void __launch_bounds__(256) k_rayleigh_cols(const double* __restrict__ A, const float* __restrict__ G, int p,
+                                                       const unsigned* __restrict__ pmask, double* __restrict__ lam, double* __restrict__ mu)
+{
+    extern __shared__ double gs[];   // [p] the column, zero outside its occupied chunks
+    __shared__ double red[8];
+    __shared__ double s_n2;
+    const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* col = G + (size_t)(c / JB) * p * JB + (c % JB);
+    const unsigned occ = pmask[c / JB];
+    const int cr = jacobi_chunk_rows(p);
+    double nn = 0.0;
+    for (int r = tid; r < p; r += 256) {
+        const double v = ((occ >> (r / cr)) & 1u) ? (double)col[(size_t)r * JB] : 0.0;
+        gs[r] = v;
+        nn += v * v;
+    }
+    nn = warp_sum(nn);
+    if (lane == 0) red[warp] = nn;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        s_n2 = t;
+    }
+    __syncthreads();
+    double num = 0.0;
+    for (int ch = 0; ch < 32; ++ch) {
+        if (!((occ >> ch) & 1u)) continue;
+        const int i1 = min(p, (ch + 1) * cr);
+        for (int i = ch * cr + warp; i < i1; i += 8) {
+            const double gi = gs[i];
+            if (gi == 0.0) continue;                       // (uniform over the warp)
+            const double* Ai = A + (size_t)i * p;
+            double sacc = 0.0;
+            for (int ch2 = 0; ch2 < 32; ++ch2) {
+                if (!((occ >> ch2) & 1u)) continue;
+                const int k1 = min(p, (ch2 + 1) * cr);
+                for (int k = ch2 * cr + lane; k < k1; k += 32) sacc = fma(Ai[k], gs[k], sacc);
+            }
+            sacc = warp_sum(sacc);
+            num = fma(gi, sacc, num);
+        }
+    }
+    __syncthreads();
+    if (lane == 0) red[warp] = num;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        lam[c] = sqrt(s_n2);
+        mu[c] = t / s_n2;
+    }
+}
+
 // mu_c = sum_tiles(part) / lam_c^2 ; also keeps lam (the norm) for the normalisation
 __global__ void k_rayleigh_finish(const double* __restrict__ part, int row_tiles, int cols_pad, int p,
                                   const double* __restrict__ lam, double* __restrict__ mu)
@@ -754,6 +812,11 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
             gl_buf_release(jprof);
         }
 
+        if (p < 3072) {   // the panels' occupancy masks are maintained: one launch, only the occupied rows of every column
+            k_rayleigh_cols<<<p, 256, sizeof(double) * (size_t)p, ctx->stream>>>((const double*)L_A->buf->ptr, (const float*)G->ptr, p,
+                                                                               (const unsigned*)pmaskb->ptr, (double*)lam->ptr, (double*)ray->ptr);
+            GL_LAUNCH_CHECK(ctx);
+        } else {
         k_jacobi_norms<<<(unsigned)ceil_div(p, 8), 256, 0, ctx->stream>>>((const float*)G->ptr, p, (double*)lam->ptr);
         GL_LAUNCH_CHECK(ctx);
         {
@@ -766,6 +829,7 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
             k_rayleigh_finish<<<(unsigned)ceil_div(p, 128), 128, 0, ctx->stream>>>((const double*)part->ptr, row_tiles, cols_pad + 64, p,
                                                                                    (const double*)lam->ptr, (double*)ray->ptr);
             GL_LAUNCH_CHECK(ctx);
+        }
         }
         int N = 2;
         while (N < p) N <<= 1;

@@ -54,6 +54,26 @@ __device__ __forceinline__ float patch_dist2(const Geom& g, int patch, int sr, i
     return (float)dy * (float)dy + (float)dx * (float)dx;
 }
 
+// The samples are in ascending raster order, i.e. sorted by image row: the ones that can reach a patch (rows within ceil(r_c) of its
+// rows) are one contiguous run [lo, hi) of the list, found by two binary searches -- at 4K that is 15 % of the samples.
+__device__ __forceinline__ int sample_lower_bound(const uint32_t* __restrict__ samples, int p, long long q)
+{
+    int lo = 0, hi = p;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)samples[mid] < q) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ void sample_window(const Geom& g, int patch, const uint32_t* __restrict__ samples, int p, int& lo, int& hi)
+{
+    const int py = patch / g.pcols;
+    const int r_lo = g.row0 + py * PR, r_hi = min(g.row0 + g.band_rows, r_lo + PR) - 1;
+    const int R = (int)ceilf(sqrtf(g.rc2)) + 1;
+    lo = sample_lower_bound(samples, p, (long long)max(0, r_lo - R) * g.width);
+    hi = sample_lower_bound(samples, p, (long long)(r_hi + R + 1) * g.width);
+}
+
 // ---------------------------------------------------------------------------------------------
 // lists: count -> scan -> fill (one warp per patch; ascending sample index, deterministic)
 // ---------------------------------------------------------------------------------------------
@@ -61,11 +81,12 @@ __global__ void __launch_bounds__(256) k_patch_count(Geom g, const uint32_t* __r
 {
     const int patch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (patch >= g.npatch) return;
-    int cnt = 0;
-    for (int i0 = 0; i0 < p; i0 += 32) {
+    int cnt = 0, lo, hi;
+    sample_window(g, patch, samples, p, lo, hi);
+    for (int i0 = lo; i0 < hi; i0 += 32) {
         const int i = i0 + lane;
         bool in = false;
-        if (i < p) {
+        if (i < hi) {
             const uint32_t q = samples[i];
             in = patch_dist2(g, patch, (int)(q / (uint32_t)g.width), (int)(q % (uint32_t)g.width)) <= g.rc2;
         }
@@ -139,11 +160,12 @@ __global__ void __launch_bounds__(256) k_patch_fill(Geom g, const uint32_t* __re
     if (patch >= g.npatch) return;
     const int4 pi = pinfo[patch];
     uint32_t* out = slots + (size_t)pi.x * SLOTS;
-    int pos = 0;
-    for (int i0 = 0; i0 < p; i0 += 32) {
+    int pos = 0, lo, hi;
+    sample_window(g, patch, samples, p, lo, hi);
+    for (int i0 = lo; i0 < hi; i0 += 32) {
         const int i = i0 + lane;
         bool in = false;
-        if (i < p) {
+        if (i < hi) {
             const uint32_t q = samples[i];
             in = patch_dist2(g, patch, (int)(q / (uint32_t)g.width), (int)(q % (uint32_t)g.width)) <= g.rc2;
         }
