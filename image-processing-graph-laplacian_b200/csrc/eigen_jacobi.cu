@@ -49,7 +49,11 @@ __global__ void k_jacobi_init(const double* __restrict__ A, int p, int nb, float
     float v = col < p ? (float)A[(size_t)r * p + col] : 0.f;
     if (fabsf(v) < 1e-20f) v = 0.f;
     G[idx] = v;
-    if (v != 0.f) atomicOr(&pmask[panel], 1u << (r / jacobi_chunk_rows(p)));
+    // one atomic per warp and (panel, chunk) instead of one per non-zero element: a warp covers 4 consecutive rows of one panel
+    const unsigned bit = v != 0.f ? 1u << (r / jacobi_chunk_rows(p)) : 0u;
+    const unsigned peers = __match_any_sync(__activemask(), panel);
+    const unsigned bits = __reduce_or_sync(peers, bit);
+    if (bits && (threadIdx.x & 31) == __ffs(peers) - 1) atomicOr(&pmask[panel], bits);
 }
 
 // round-robin tournament over nb (even) panels: step in [0, nb-1), pair in [0, nb/2)

@@ -108,13 +108,21 @@ __global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* _
     const int a = threadIdx.x * per, b = min(npatch, a + per);
     int s = 0, nbmax = 0;
     unsigned long long ks = 0;
-    for (int i = a; i < b; ++i) {
-        const int4 pi = pinfo[i];
-        s += pi.y;
-        nbmax = max(nbmax, pi.y);
-        const int mtc = min(G, (g.band_rows - (i / g.pcols) * PR + 1) >> 1);
-        const int last = pi.z - SLOTS * (pi.y - 1);
-        ks += (unsigned long long)mtc * (unsigned long long)(2 * (pi.y - 1) + (last > 16 ? 2 : 1));
+    for (int i0 = a; i0 < b; i0 += 8) {      // eight loads in flight (one after the other they were eight L2 round trips per thread)
+        int4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = i0 + k < b ? pinfo[i0 + k] : make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k;
+            if (i >= b) break;
+            const int4 pi = v[k];
+            s += pi.y;
+            nbmax = max(nbmax, pi.y);
+            const int mtc = min(G, (g.band_rows - (i / g.pcols) * PR + 1) >> 1);
+            const int last = pi.z - SLOTS * (pi.y - 1);
+            ks += (unsigned long long)mtc * (unsigned long long)(2 * (pi.y - 1) + (last > 16 ? 2 : 1));
+        }
     }
     part[threadIdx.x] = s;
     __syncthreads();
@@ -135,10 +143,16 @@ __global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* _
         __syncthreads();
     }
     int run = threadIdx.x ? part[threadIdx.x - 1] : 0;
-    for (int i = a; i < b; ++i) {
-        const int nb = pinfo[i].y;
-        pinfo[i].x = run;
-        run += nb;
+    for (int i0 = a; i0 < b; i0 += 8) {
+        int nbv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nbv[k] = i0 + k < b ? pinfo[i0 + k].y : 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k >= b) break;
+            pinfo[i0 + k].x = run;
+            run += nbv[k];
+        }
     }
     if (threadIdx.x == 1023) {
         total[0] = part[1023];
