@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* _
                                                      int* __restrict__ dstat)
 {
     __shared__ int part[1024];
-    __shared__ unsigned long long ksum;
+    __shared__ unsigned long long ksum, wks[32];
     __shared__ int max_nb;
     if (threadIdx.x == 0) { ksum = 0ull; max_nb = 0; }
     const int per = (npatch + 1023) / 1024;
@@ -126,14 +126,14 @@ __global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* _
     }
     part[threadIdx.x] = s;
     __syncthreads();
-    // (one shared-memory atomic per warp: 1 024 threads on one 64-bit word is a 50 us CAS queue)
+    // (no 64-bit shared-memory atomics: they are CAS loops, and even one per warp queued for ~20 us; per-warp words, summed by one thread)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ks += __shfl_xor_sync(0xffffffffu, ks, o);
         nbmax = max(nbmax, __shfl_xor_sync(0xffffffffu, nbmax, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&ksum, ks);
+        wks[threadIdx.x >> 5] = ks;
         atomicMax(&max_nb, nbmax);
     }
     for (int o = 1; o < 1024; o <<= 1) {
@@ -155,6 +155,11 @@ __global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* _
         }
     }
     if (threadIdx.x == 1023) {
+        {   // (wks was written before the scan's barriers)
+            unsigned long long t = 0ull;
+            for (int w = 0; w < 32; ++w) t += wks[w];
+            ksum = t;
+        }
         total[0] = part[1023];
         *(unsigned long long*)(total + 2) = ksum;   // (its last addition happened before the scan's barriers)
         // storage set aside without asking (cap_blocks > 0): too small -> every kernel of the patch path returns at once and the
