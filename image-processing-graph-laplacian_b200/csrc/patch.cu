@@ -496,9 +496,87 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
         // ===== MMA issuers =====
         if (lane == 0 && (two || warp == 1)) {
             const int me = warp == 1 ? 0 : 1;
+#ifdef GLB200_PT_DEBUG
+            long long pa[6] = {0, 0, 0, 0, 0, 0}, pt0 = 0, pt1;   // phase clocks of this issuer: tempty wait, operand waits, MMA issue, commits, tiles
+#define PT_T(k) do { if (prof) { pt1 = clock64(); pa[k] += pt1 - pt0; pt0 = pt1; } } while (0)
+            if (prof) pt0 = clock64();
+#else
+#define PT_T(k) do { } while (0)
+#endif
             int stage = 0, bpos = 0, it = 0;
             uint32_t phase = 0, buses = 0;   // buses bit s: parity of the number of fills of B unit slot s consumed so far
             const uint32_t idesc = make_idesc(BLOCK_M, BN, 0) | (1u << 16);   // B is MN-major
+            if (two) {
+                // ---- the common case, written out lean: every patch resident, N tiles in pairs.  Issuer `me` owns accumulator `me`
+                // and the N tiles of its parity; this thread is the serial resource of the SM (one scalar instruction every ~5 cycles),
+                // so nothing is recomputed per tile that can be kept per M tile or per patch, and it never walks the other issuer's
+                // tiles.  B unit u (in the order the gather warp fills them) lives in slot u & 7, fill u >> 3.
+                static_assert(SBT == 8, "unit slot arithmetic");
+                uint32_t own = 0, useq = 0;
+                int4 pi_next = first_patch < g.npatch ? pinfo[first_patch] : make_int4(0, 1, 0, 0);
+                for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
+                    const int4 pi = pi_next;
+                    if (patch + patch_step < g.npatch) pi_next = pinfo[patch + patch_step];    // in flight while this patch is multiplied
+                    const int py = patch / g.pcols;
+                    const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
+                    const int nb = pi.y;
+                    const int kk_last = (pi.z - SLOTS * (nb - 1)) > 16 ? 2 : 1;
+                    for (int mt = 0; mt < mtc; ++mt) {
+                        uint64_t da[SA / 2];
+                        uint32_t abar[SA / 2];
+#pragma unroll
+                        for (int b = 0; b < SA / 2; ++b) {
+                            if (b >= nb) break;
+                            int as = stage + b;
+                            uint32_t aph = phase;
+                            if (as >= SA) { as -= SA; aph ^= 1u; }
+                            mbar_wait(bar_afull + 8 * as, aph, err, 3);
+                            da[b] = make_smem_desc_k<32>(smem_u32(smem_a + as * A_TILE_BYTES));
+                            abar[b] = bar_aempty + 8 * as;
+                        }
+                        for (int nt = me; nt < n_tiles; nt += 2) {
+                            const uint32_t u0 = useq + (uint32_t)(nt * nb);
+                            if (mt == 0) {
+#pragma unroll
+                                for (int b = 0; b < SA / 2; ++b)
+                                    if (b < nb) mbar_wait(bar_bfull + 8 * ((u0 + b) & 7u), ((u0 + b) >> 3) & 1u, err, 6);
+                            }
+                            PT_T(1);
+                            mbar_wait(bar_tempty + 8 * me, (own & 1u) ^ 1u, err, 2);
+                            tcgen05_fence_after();
+                            PT_T(0);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(me * 256);
+#pragma unroll
+                            for (int b = 0; b < SA / 2; ++b) {
+                                if (b >= nb) break;
+                                const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + ((u0 + b) & 7u) * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
+                                const int kk = b == nb - 1 ? kk_last : 2;
+                                for (int k = 0; k < kk; ++k)
+                                    umma_f16(d_tmem, da[b] + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
+                            }
+                            PT_T(2);
+                            umma_commit(bar_tfull + 8 * me);
+                            ++own;
+                            if (mt == mtc - 1) {    // the W units of this N tile go back after the patch's last M tile
+#pragma unroll
+                                for (int b = 0; b < SA / 2; ++b)
+                                    if (b < nb) umma_commit(bar_bempty + 8 * ((u0 + b) & 7u));
+                            }
+                            PT_T(3);
+#ifdef GLB200_PT_DEBUG
+                            pa[5] += 1;
+#endif
+                        }
+#pragma unroll
+                        for (int b = 0; b < SA / 2; ++b)
+                            if (b < nb) umma_commit(abar[b]);      // (the other issuer's arrival completes the release)
+                        stage += nb;
+                        if (stage >= SA) { stage -= SA; phase ^= 1u; }
+                        PT_T(4);
+                    }
+                    useq += (uint32_t)(nb * n_tiles);
+                }
+            } else
             for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
                 const int4 pi = pinfo[patch];
                 const int py = patch / g.pcols;
@@ -515,8 +593,10 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                         const int acc = it & 1;
                         const bool mine = !two || acc == me;
                         if (mine) {
+                            PT_T(4);   // everything between two own tiles that is not one of the phases below (loop, other issuer's tiles)
                             mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1), err, 2);
                             tcgen05_fence_after();
+                            PT_T(0);
                         }
                         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                         for (int b = 0; b < nb; ++b) {
@@ -536,11 +616,13 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                                 if (!resident || !a_seen) mbar_wait(bar_afull + 8 * as, aph, err, 3);
                                 if (!resident || !((b_seen >> (nt * nb + b)) & 1u)) mbar_wait(bar_bfull + 8 * bs, (buses >> bs) & 1u, err, 6);
                                 tcgen05_fence_after();
+                                PT_T(1);
                                 const int kk = (pi.z - SLOTS * b) > 16 ? 2 : 1;     // a last block with at most 16 samples: one K step
                                 const uint64_t da = make_smem_desc_k<32>(smem_u32(smem_a + as * A_TILE_BYTES));
                                 const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + bs * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
                                 for (int k = 0; k < kk; ++k)
                                     umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
+                                PT_T(2);
                                 if (!resident) {
                                     umma_commit(bar_aempty + 8 * as);
                                     umma_commit(bar_aempty + 8 * as);
@@ -563,12 +645,20 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                         if (mine) {
                             a_seen = true;
                             umma_commit(bar_tfull + 8 * acc);
+                            PT_T(3);
+#ifdef GLB200_PT_DEBUG
+                            pa[5] += 1;
+#endif
                         }
                     }
                     if (resident) { stage += nb; if (stage >= SA) { stage -= SA; phase ^= 1; } }
                 }
                 if (resident) { bpos = b0 + nb * n_tiles; if (bpos >= SBT) bpos -= SBT; }
             }
+#ifdef GLB200_PT_DEBUG
+            if (prof && blockIdx.x == 0) for (int k = 0; k < 6; ++k) prof[me * 8 + k] = pa[k];
+#endif
+#undef PT_T
         }
     } else if (warp == 2) {
         // ===== B gather: rows of W for the slots of a block and the columns of an N tile, in the MN-major SWIZZLE_128B layout =====
@@ -634,6 +724,13 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
             }
         };
         float* my_x = xch + (wq * 32 + lane) * FC;
+#ifdef GLB200_PT_DEBUG
+        long long ea[6] = {0, 0, 0, 0, 0, 0}, et0 = 0, et1;   // tfull wait, tcgen05.ld (issue + wait), hand-back, arithmetic, end of M tile, tiles
+#define PE_T(k) do { if (prof) { et1 = clock64(); ea[k] += et1 - et0; et0 = et1; } } while (0)
+        if (prof) et0 = clock64();
+#else
+#define PE_T(k) do { } while (0)
+#endif
         int it = 0;
         for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
             const int py = patch / g.pcols, pxi = patch - py * g.pcols;
@@ -656,6 +753,7 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                     const int acc = it & 1;
                     mbar_wait(bar_tfull + 8 * acc, (uint32_t)((it >> 1) & 1), err, 4);
                     tcgen05_fence_after();
+                    PE_T(0);
                     const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + (BN >= 128 ? share * COLS : 0));
                     const uint32_t wt = wbase + (uint32_t)(nt * BN * FC * 4);
                     if (AT_ONCE) {
@@ -665,13 +763,19 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                             for (int k = 0; k < NCH; ++k) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * k), v[k]);
                         }
                         tmem_ld_wait();
+                        PE_T(1);
                         tcgen05_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                        PE_T(2);
                         if (active && !PT_DBG(1)) {
 #pragma unroll
                             for (int k = 0; k < NCH; ++k) mul32(v[k], wt + (uint32_t)(32 * k * FC * 4), dot);
                         }
+                        PE_T(3);
+#ifdef GLB200_PT_DEBUG
+                        ea[5] += 1;
+#endif
                     } else {
                         uint32_t v[2][32];
                         if (active) tmem_ld_32x32b_x32(t_row, v[0]);
@@ -710,8 +814,13 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                         if (z8) z8[o + q] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);
                     }
                 }
+                PE_T(4);
             }
         }
+#ifdef GLB200_PT_DEBUG
+        if (prof && blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 8)) for (int k = 0; k < 6; ++k) prof[16 + (warp == 8) * 8 + k] = ea[k];
+#endif
+#undef PE_T
     }
 
     tcgen05_fence_before();
@@ -935,7 +1044,22 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { gl_set_error("nystroem(patch): kernel launch failed"); rc = GL_ERR_CUDA; }
     } while (0);
-    if (prof) gl_buf_release(prof);
+    if (prof) {
+        long long h[32];
+        cudaMemcpyAsync(h, prof->ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        for (int i = 0; i < 2; ++i)
+            if (h[i * 8 + 5] > 0)
+                fprintf(stderr, "[pt prof] issuer %d: %lld tiles; cycles per own tile: accumulator free %lld | operands %lld | mma issue %lld | commit %lld | rest %lld\n", i,
+                        h[i * 8 + 5], h[i * 8 + 0] / h[i * 8 + 5], h[i * 8 + 1] / h[i * 8 + 5], h[i * 8 + 2] / h[i * 8 + 5], h[i * 8 + 3] / h[i * 8 + 5],
+                        h[i * 8 + 4] / h[i * 8 + 5]);
+        for (int i = 0; i < 2; ++i)
+            if (h[16 + i * 8 + 5] > 0)
+                fprintf(stderr, "[pt prof] epilogue warp %d: %lld tiles; cycles per tile: accumulator full %lld | tcgen05.ld %lld | hand back %lld | arithmetic %lld | end of M tile %lld\n",
+                        4 + 4 * i, h[16 + i * 8 + 5], h[16 + i * 8 + 0] / h[16 + i * 8 + 5], h[16 + i * 8 + 1] / h[16 + i * 8 + 5],
+                        h[16 + i * 8 + 2] / h[16 + i * 8 + 5], h[16 + i * 8 + 3] / h[16 + i * 8 + 5], h[16 + i * 8 + 4] / h[16 + i * 8 + 5]);
+        gl_buf_release(prof);
+    }
     if (Wr) gl_buf_release(Wr);
     if (err) gl_buf_release(err);
     return rc;
