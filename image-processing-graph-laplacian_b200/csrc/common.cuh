@@ -178,6 +178,7 @@ struct gl_ctx {
     int64_t tab_key[6] = {-1, -1, -1, -1, -1, -1};
     int64_t tile_total_blocks = 0;
     int kb_cutoff = 1;        // option kb_cutoff: 1 = skip sample blocks whose K_B entries fp16 flushes to zero, 0 = dense
+    int pt_dual = 1;          // option pt_dual: 1 = the patch extrapolation runs as two pipelines per SM when every patch is resident (one channel)
     int kb_layout = 1;        // option kb_layout: 1 = patch layout for the spatially decaying affinities (patch.cu), 0 = always blocked
     bool want_blocked = false;  // set by gl_run_resident around gl_affinity when the path will need Phi itself (no fused filter)
 

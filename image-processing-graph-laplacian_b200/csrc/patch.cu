@@ -424,10 +424,12 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
                  const float* __restrict__ fuse_w /* [m_pad][FC] */, const uint8_t* __restrict__ img /* band rows, [pixel][FC] */,
                  int clip_low, float* __restrict__ z /* [band pixels][FC] */, uint8_t* __restrict__ z8 /* or null */,
                  int* __restrict__ err, long long* __restrict__ prof /* debug timeline of CTA 0, or null */,
-                 const int* __restrict__ dstat, int dbg /* experiments: bit 0 = no epilogue arithmetic, bit 1 = no stores */)
+                 const int* __restrict__ dstat, int dbg /* experiments: bit 0 = no epilogue arithmetic, bit 1 = no stores */,
+                 int skip_if_resident /* the dual-pipeline kernel was launched for the all-resident case: leave it to that one */)
 {
     using namespace tc;
     if (dstat[GL_DS_PT_OVERFLOW]) return;
+    if (skip_if_resident && dstat[GL_DS_PT_MAXNB] * 2 <= SA && dstat[GL_DS_PT_MAXNB] * n_tiles <= SBT) return;
     extern __shared__ uint8_t pn_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)pn_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -831,7 +833,286 @@ k_patch_nystroem(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* 
     }
 }
 
-constexpr int nystroem_smem(int fc, int m_pad) { return SA * A_TILE_BYTES + SBT * B_BLOCK_BYTES + 512 + 4 * 32 * fc * 4 + m_pad * fc * 4 + 1024; }
+// ---------------------------------------------------------------------------------------------
+// The same extrapolation + filter as TWO independent pipelines per SM (every patch resident; the kernel above stays for the rest).
+// Pipeline g = {issuer g, accumulator g, epilogue group g of eight warps} takes every other M tile of the CTA's patches with all its N
+// tiles: a pixel's dot product never leaves its group (no rendezvous between the groups), and while group g multiplies the tile it
+// has just read, its accumulator is already being refilled -- by its own issuer, whose chain (wake-up, MMA, commit, wake-up of the
+// epilogue) no longer has to fit into the other accumulator's epilogue.  What the two pipelines share: the A ring (a slot belongs to
+// one M tile, hence to one issuer), the W units of the patch (released when both issuers are through with the patch) and the SM's
+// FMA and shared-memory pipes -- the bound that is left (profiles/r02_patch_timeline.md).
+// 20 warps: 0 producer, 1 and 3 issuers, 2 tensor-memory allocation + W gather, 4-11 epilogue group 0, 12-19 epilogue group 1.
+// ---------------------------------------------------------------------------------------------
+constexpr int THREADS2 = 128 + 2 * 32 * EPI_WARPS;
+
+template <int FC, int BN>
+__global__ void __launch_bounds__(THREADS2, 1)
+k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots,
+                      const __half* __restrict__ W, int m_pad, int n_tiles, const float* __restrict__ scales,
+                      const float* __restrict__ fuse_w /* [m_pad][FC] */, const uint8_t* __restrict__ img /* band rows, [pixel][FC] */,
+                      int clip_low, float* __restrict__ z /* [band pixels][FC] */, uint8_t* __restrict__ z8 /* or null */,
+                      int* __restrict__ err, const int* __restrict__ dstat)
+{
+    using namespace tc;
+    static_assert(SBT == 8, "unit slot arithmetic");
+    if (dstat[GL_DS_PT_OVERFLOW]) return;
+    const int max_nb = dstat[GL_DS_PT_MAXNB];
+    if (!(max_nb * 2 <= SA && max_nb * n_tiles <= SBT)) return;      // not every patch resident: the general kernel runs instead
+    extern __shared__ uint8_t pn_smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)pn_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem_a + SA * A_TILE_BYTES;
+    uint64_t* bars = (uint64_t*)(smem_b + SBT * B_BLOCK_BYTES);
+    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + SA);
+    const uint32_t bar_bfull = smem_u32(bars + 2 * SA), bar_bempty = smem_u32(bars + 2 * SA + SBT);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * SA + 2 * SBT), bar_tempty = smem_u32(bars + 2 * SA + 2 * SBT + 2);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * SA + 2 * SBT + 4);
+    float* xch = (float*)(bars + 64);            // [2 groups][4 quarters][32 lanes][FC]
+    float* w_s = xch + 2 * 4 * 32 * FC;          // [m_pad][FC] filter weights, times the GEMM's output scale
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first_patch = blockIdx.x, patch_step = gridDim.x;
+
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }      // a slot belongs to one issuer
+        for (int s = 0; s < SBT; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 2); }     // a W unit to both
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        const float sc = scales[1];
+        for (int i = threadIdx.x; i < m_pad * FC; i += THREADS2) w_s[i] = __ldg(fuse_w + i) * sc;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== A producer: the tiles of every M tile, in order =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
+                const int4 pi = pinfo[patch];
+                const int py = patch / g.pcols;
+                const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
+                const int tile0 = pi.x * G;
+                for (int mt = 0; mt < mtc; ++mt)
+                    for (int b = 0; b < pi.y; ++b) {
+                        mbar_wait(bar_aempty + 8 * stage, phase ^ 1, err, 1);
+                        mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)A_TILE_BYTES);
+                        tma_load_2d(smem_u32(smem_a + stage * A_TILE_BYTES), &map_a, bar_afull + 8 * stage, 0, (tile0 + mt * pi.y + b) * 128);
+                        if (++stage == SA) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ===== MMA issuers: issuer `me` owns accumulator `me` and the M tiles of its parity =====
+        if (lane == 0) {
+            const int me = warp == 1 ? 0 : 1;
+            const uint32_t idesc = make_idesc(BLOCK_M, BN, 0) | (1u << 16);   // B is MN-major
+            const uint32_t d_tmem = tmem_base + (uint32_t)(me * 256);
+            uint32_t own = 0, useq = 0, mseq = 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            int4 pi_next = first_patch < g.npatch ? pinfo[first_patch] : make_int4(0, 1, 0, 0);
+            for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
+                const int4 pi = pi_next;
+                if (patch + patch_step < g.npatch) pi_next = pinfo[patch + patch_step];
+                const int py = patch / g.pcols;
+                const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
+                const int nb = pi.y;
+                const int kk_last = (pi.z - SLOTS * (nb - 1)) > 16 ? 2 : 1;
+                bool touched = false;
+                for (int mt = 0; mt < mtc; ++mt, ++mseq) {
+                    if ((mseq & 1u) == (uint32_t)me) {
+                        uint64_t da[SA / 2];
+                        uint32_t abar[SA / 2];
+#pragma unroll
+                        for (int b = 0; b < SA / 2; ++b) {
+                            if (b >= nb) break;
+                            int as = stage + b;
+                            uint32_t aph = phase;
+                            if (as >= SA) { as -= SA; aph ^= 1u; }
+                            mbar_wait(bar_afull + 8 * as, aph, err, 3);
+                            da[b] = make_smem_desc_k<32>(smem_u32(smem_a + as * A_TILE_BYTES));
+                            abar[b] = bar_aempty + 8 * as;
+                        }
+                        for (int nt = 0; nt < n_tiles; ++nt) {
+                            const uint32_t u0 = useq + (uint32_t)(nt * nb);
+                            uint64_t db[SA / 2];
+#pragma unroll
+                            for (int b = 0; b < SA / 2; ++b) {
+                                if (b >= nb) break;
+                                if (!touched) mbar_wait(bar_bfull + 8 * ((u0 + b) & 7u), ((u0 + b) >> 3) & 1u, err, 6);
+                                db[b] = make_smem_desc_mn(smem_u32(smem_b + ((u0 + b) & 7u) * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
+                            }
+                            mbar_wait(bar_tempty + 8 * me, (own & 1u) ^ 1u, err, 2);
+                            tcgen05_fence_after();
+#pragma unroll
+                            for (int b = 0; b < SA / 2; ++b) {
+                                if (b >= nb) break;
+                                const int kk = b == nb - 1 ? kk_last : 2;
+                                for (int k = 0; k < kk; ++k)
+                                    umma_f16(d_tmem, da[b] + (uint64_t)(2 * k), db[b] + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
+                            }
+                            umma_commit(bar_tfull + 8 * me);
+                            ++own;
+                        }
+                        touched = true;
+#pragma unroll
+                        for (int b = 0; b < SA / 2; ++b)
+                            if (b < nb) umma_commit(abar[b]);
+                    }
+                    stage += nb;
+                    if (stage >= SA) { stage -= SA; phase ^= 1u; }
+                }
+                // The W units go back when BOTH issuers are through with the patch.  tcgen05.commit arrives once this thread's MMAs are
+                // complete; an issuer that had no M tile in the patch first makes sure the unit was filled (its arrival must land in
+                // this fill's phase, not in the previous one's), then arrives plainly.
+                const uint32_t nu = (uint32_t)(nb * n_tiles);
+                for (uint32_t u = useq; u < useq + nu; ++u) {
+                    if (touched) umma_commit(bar_bempty + 8 * (u & 7u));
+                    else {
+                        mbar_wait(bar_bfull + 8 * (u & 7u), (u >> 3) & 1u, err, 6);
+                        mbar_arrive(bar_bempty + 8 * (u & 7u));
+                    }
+                }
+                useq += nu;
+            }
+        }
+    } else if (warp == 2) {
+        // ===== B gather (as in the kernel above, resident case) =====
+        const int u = lane;
+        int bpos = 0;
+        uint32_t bloads = 0;
+        for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
+            const int4 pi = pinfo[patch];
+            for (int nt = 0; nt < n_tiles; ++nt)
+                for (int b = 0; b < pi.y; ++b) {
+                    mbar_wait(bar_bempty + 8 * bpos, ((bloads >> bpos) & 1u) ^ 1u, err, 5);
+                    bloads ^= 1u << bpos;
+                    const uint32_t dst_s = smem_u32(smem_b + bpos * B_BLOCK_BYTES);
+                    const uint32_t my_slot = __ldg(slots + (size_t)(pi.x + b) * SLOTS + lane);
+#pragma unroll 8
+                    for (int k = 0; k < SLOTS; ++k) {
+                        const uint32_t s = __shfl_sync(0xffffffffu, my_slot, k);
+                        const bool live = s != 0xffffffffu && u * 8 < BN;
+                        const __half* src = W + (size_t)(live ? s : 0) * m_pad + (size_t)nt * BN + (live ? u * 8 : 0);
+                        const uint32_t d = dst_s + (uint32_t)((u >> 3) * B_CHUNK_BYTES + k * 128 + (((u & 7) ^ (k & 7)) << 4));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(live ? 16 : 0) : "memory");
+                    }
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_bfull + 8 * bpos);
+                    if (++bpos == SBT) bpos = 0;
+                }
+        }
+    } else {
+        // ===== epilogue groups =====
+        const int grp = (warp - 4) >> 3, wq = warp & 3, share = ((warp - 4) >> 2) & 1;
+        constexpr int COLS = BN >= 128 ? BN / 2 : BN;          // columns per share (BN = 64: share 0 takes them all)
+        const bool active = BN >= 128 || share == 0;
+        constexpr int NCH = COLS / 32;
+        const uint32_t wbase = smem_u32(w_s) + (uint32_t)((BN >= 128 ? share * COLS : 0) * FC * 4);
+        auto mul32 = [&](const uint32_t (&v)[32], uint32_t wv, float (&dot)[FC][8]) {
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+                float wr[8 * FC];
+#pragma unroll
+                for (int q = 0; q < 2 * FC; ++q) lds_f4(wv + (uint32_t)((g8 * 2 * FC + q) * 16), &wr[4 * q]);
+                if (FC == 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2)
+                        ffma2(dot[0][i], dot[0][i + 1], __uint_as_float(v[8 * g8 + i]), __uint_as_float(v[8 * g8 + i + 1]), wr[i], wr[i + 1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float val = __uint_as_float(v[8 * g8 + i]);
+#pragma unroll
+                        for (int q = 0; q < FC; ++q) dot[q][i & 3] = fmaf(val, wr[i * FC + q], dot[q][i & 3]);
+                    }
+                }
+            }
+        };
+        float* my_x = xch + ((grp * 4 + wq) * 32 + lane) * FC;
+        uint32_t own = 0, mseq = 0;
+        for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
+            const int py = patch / g.pcols, pxi = patch - py * g.pcols;
+            const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
+            for (int mt = 0; mt < mtc; ++mt, ++mseq) {
+                if ((mseq & 1u) != (uint32_t)grp) continue;
+                float dot[FC][8];
+#pragma unroll
+                for (int q = 0; q < FC; ++q)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dot[q][i] = 0.f;
+                const int r = py * PR + 2 * mt + (wq >> 1), c = pxi * PW + (wq & 1) * 32 + lane;
+                const bool px_ok = share == 0 && r < g.band_rows && c < g.width;
+                const size_t o = ((size_t)r * g.width + c) * FC;
+                float yv[FC];
+#pragma unroll
+                for (int q = 0; q < FC; ++q) yv[q] = px_ok ? (float)__ldg(img + o + q) : 0.f;
+                for (int nt = 0; nt < n_tiles; ++nt, ++own) {
+                    mbar_wait(bar_tfull + 8 * grp, own & 1u, err, 4);
+                    tcgen05_fence_after();
+                    const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * 256 + (BN >= 128 ? share * COLS : 0));
+                    const uint32_t wt = wbase + (uint32_t)(nt * BN * FC * 4);
+                    uint32_t v[2][32];
+                    if (active) tmem_ld_32x32b_x32(t_row, v[0]);
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        tmem_ld_wait();
+                        if (k + 1 < NCH) {
+                            if (active) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * (k + 1)), v[(k + 1) & 1]);
+                        } else {
+                            // every tcgen05.ld of this accumulator has completed: hand it back before the last chunk's arithmetic
+                            tcgen05_fence_before();
+                            if (lane == 0) mbar_arrive(bar_tempty + 8 * grp);
+                        }
+                        if (active) mul32(v[k & 1], wt + (uint32_t)(32 * k * FC * 4), dot);
+                    }
+                }
+                float part[FC];
+#pragma unroll
+                for (int q = 0; q < FC; ++q)
+                    part[q] = ((dot[q][0] + dot[q][1]) + (dot[q][2] + dot[q][3])) + ((dot[q][4] + dot[q][5]) + (dot[q][6] + dot[q][7]));
+                if (share == 1) {
+#pragma unroll
+                    for (int q = 0; q < FC; ++q) my_x[q] = part[q];
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + grp * 4 + wq) : "memory");
+                if (px_ok) {
+#pragma unroll
+                    for (int q = 0; q < FC; ++q) {
+                        float val = fminf(yv[q] + (part[q] + my_x[q]), 255.f);
+                        if (clip_low) val = fmaxf(val, 0.f);
+                        z[o + q] = val;
+                        if (z8) z8[o + q] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);
+                    }
+                }
+                // (share 1 may not write my_x again before share 0 has read it: with a single N tile nothing else orders the two)
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + grp * 4 + wq) : "memory");
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+constexpr int nystroem_smem(int fc, int m_pad) { return SA * A_TILE_BYTES + SBT * B_BLOCK_BYTES + 512 + 2 * 4 * 32 * fc * 4 + m_pad * fc * 4 + 1024; }
 
 // K_B from the patch layout to dense fp64 [band pixels][p] in the caller's sample order (dst zeroed beforehand)
 __global__ void k_patch_to_f64(Geom g, const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots, const __half* __restrict__ KB, int p,
@@ -1024,6 +1305,25 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
                                  pt::SLOTS, pt::SLOTS, 128, CU_TENSOR_MAP_SWIZZLE_64B));
         const uint8_t* y = (const uint8_t*)ctx->img->ptr + (size_t)L_B->q0 * C;
         StageTimer kt(ctx, GL_T_K_GEMM);
+        // One channel: two pipelines per SM when every patch is resident (decided on the device: the general kernel, launched right
+        // after, returns at once in that case and does all the work otherwise).
+        const bool dual = C == 1 && ctx->pt_dual && !want_prof && dbg == 0;
+        if (dual) {
+#define PT_LAUNCH2(BNN)                                                                                                                \
+    do {                                                                                                                               \
+        GL_CUDA_BREAK(rc, cudaFuncSetAttribute(pt::k_patch_nystroem_dual<1, BNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));   \
+        pt::k_patch_nystroem_dual<1, BNN><<<grid, pt::THREADS2, SM, ctx->stream>>>(map_a, g, (const int4*)L_B->pt_info->ptr,           \
+                                                                                   (const uint32_t*)L_B->pt_slots->ptr, (const __half*)Wr->ptr, \
+                                                                                   m_pad, n_tiles, scales, w, y, clip_low, z, z8,      \
+                                                                                   (int*)err->ptr, (const int*)ctx->dstat->ptr);       \
+    } while (0)
+            if (BN == 256) PT_LAUNCH2(256);
+            else if (BN == 128) PT_LAUNCH2(128);
+            else PT_LAUNCH2(64);
+#undef PT_LAUNCH2
+            if (rc != GL_OK) break;
+            ctx->launches++;
+        }
 #define PT_LAUNCH(FC, BNN)                                                                                                          \
     do {                                                                                                                            \
         GL_CUDA_BREAK(rc, cudaFuncSetAttribute(pt::k_patch_nystroem<FC, BNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));    \
@@ -1031,7 +1331,7 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
                                                                               (const uint32_t*)L_B->pt_slots->ptr, (const __half*)Wr->ptr, \
                                                                               m_pad, n_tiles, scales, w, y, clip_low, z, z8,        \
                                                                               (int*)err->ptr, prof ? (long long*)prof->ptr : nullptr, \
-                                                                              (const int*)ctx->dstat->ptr, dbg);                    \
+                                                                              (const int*)ctx->dstat->ptr, dbg, dual ? 1 : 0);      \
     } while (0)
         if (C == 1 && BN == 256) PT_LAUNCH(1, 256);
         else if (C == 1 && BN == 128) PT_LAUNCH(1, 128);
