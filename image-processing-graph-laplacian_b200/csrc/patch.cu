@@ -851,7 +851,7 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
                       const __half* __restrict__ W, int m_pad, int n_tiles, const float* __restrict__ scales,
                       const float* __restrict__ fuse_w /* [m_pad][FC] */, const uint8_t* __restrict__ img /* band rows, [pixel][FC] */,
                       int clip_low, float* __restrict__ z /* [band pixels][FC] */, uint8_t* __restrict__ z8 /* or null */,
-                      int* __restrict__ err, const int* __restrict__ dstat)
+                      int* __restrict__ err, const int* __restrict__ dstat, long long* __restrict__ prof /* PT_DEBUG: phase clocks of CTA 0 */)
 {
     using namespace tc;
     static_assert(SBT == 8, "unit slot arithmetic");
@@ -867,8 +867,8 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
     const uint32_t bar_bfull = smem_u32(bars + 2 * SA), bar_bempty = smem_u32(bars + 2 * SA + SBT);
     const uint32_t bar_tfull = smem_u32(bars + 2 * SA + 2 * SBT), bar_tempty = smem_u32(bars + 2 * SA + 2 * SBT + 2);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * SA + 2 * SBT + 4);
-    float* xch = (float*)(bars + 64);            // [2 groups][4 quarters][32 lanes][FC]
-    float* w_s = xch + 2 * 4 * 32 * FC;          // [m_pad][FC] filter weights, times the GEMM's output scale
+    float* xch = (float*)(bars + 64);            // [2 slots][2 groups][4 quarters][32 lanes][FC]
+    float* w_s = xch + 2 * 2 * 4 * 32 * FC;          // [m_pad][FC] filter weights, times the GEMM's output scale
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int first_patch = blockIdx.x, patch_step = gridDim.x;
@@ -921,6 +921,13 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
             uint32_t own = 0, useq = 0, mseq = 0;
             int stage = 0;
             uint32_t phase = 0;
+#ifdef GLB200_PT_DEBUG
+            long long pa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt0 = 0, pt1;
+#define PT_T(k) do { if (prof) { pt1 = clock64(); pa[k] += pt1 - pt0; pt0 = pt1; } } while (0)
+            if (prof) pt0 = clock64();
+#else
+#define PT_T(k) do { } while (0)
+#endif
             int4 pi_next = first_patch < g.npatch ? pinfo[first_patch] : make_int4(0, 1, 0, 0);
             for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
                 const int4 pi = pi_next;
@@ -934,6 +941,7 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
                     if ((mseq & 1u) == (uint32_t)me) {
                         uint64_t da[SA / 2];
                         uint32_t abar[SA / 2];
+                        PT_T(7);
 #pragma unroll
                         for (int b = 0; b < SA / 2; ++b) {
                             if (b >= nb) break;
@@ -944,6 +952,7 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
                             da[b] = make_smem_desc_k<32>(smem_u32(smem_a + as * A_TILE_BYTES));
                             abar[b] = bar_aempty + 8 * as;
                         }
+                        PT_T(6);
                         for (int nt = 0; nt < n_tiles; ++nt) {
                             const uint32_t u0 = useq + (uint32_t)(nt * nb);
                             uint64_t db[SA / 2];
@@ -953,8 +962,10 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
                                 if (!touched) mbar_wait(bar_bfull + 8 * ((u0 + b) & 7u), ((u0 + b) >> 3) & 1u, err, 6);
                                 db[b] = make_smem_desc_mn(smem_u32(smem_b + ((u0 + b) & 7u) * B_BLOCK_BYTES), (uint32_t)B_CHUNK_BYTES);
                             }
+                            PT_T(1);
                             mbar_wait(bar_tempty + 8 * me, (own & 1u) ^ 1u, err, 2);
                             tcgen05_fence_after();
+                            PT_T(0);
 #pragma unroll
                             for (int b = 0; b < SA / 2; ++b) {
                                 if (b >= nb) break;
@@ -962,8 +973,13 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
                                 for (int k = 0; k < kk; ++k)
                                     umma_f16(d_tmem, da[b] + (uint64_t)(2 * k), db[b] + (uint64_t)(128 * k), idesc, (uint32_t)((b | k) != 0));
                             }
+                            PT_T(2);
                             umma_commit(bar_tfull + 8 * me);
                             ++own;
+                            PT_T(3);
+#ifdef GLB200_PT_DEBUG
+                            pa[5] += 1;
+#endif
                         }
                         touched = true;
 #pragma unroll
@@ -985,7 +1001,12 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
                     }
                 }
                 useq += nu;
+                PT_T(4);
             }
+#ifdef GLB200_PT_DEBUG
+            if (prof && blockIdx.x == 0) for (int q = 0; q < 8; ++q) prof[me * 8 + q] = pa[q];
+#endif
+#undef PT_T
         }
     } else if (warp == 2) {
         // ===== B gather (as in the kernel above, resident case) =====
@@ -1043,7 +1064,14 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
             }
         };
         float* my_x = xch + ((grp * 4 + wq) * 32 + lane) * FC;
-        uint32_t own = 0, mseq = 0;
+        uint32_t own = 0, mseq = 0, mslot = 0;
+#ifdef GLB200_PT_DEBUG
+        long long ea[6] = {0, 0, 0, 0, 0, 0}, et0 = 0, et1;
+#define PE_T(k) do { if (prof) { et1 = clock64(); ea[k] += et1 - et0; et0 = et1; } } while (0)
+        if (prof) et0 = clock64();
+#else
+#define PE_T(k) do { } while (0)
+#endif
         for (int patch = first_patch; patch < g.npatch; patch += patch_step) {
             const int py = patch / g.pcols, pxi = patch - py * g.pcols;
             const int mtc = min(G, (g.band_rows - py * PR + 1) >> 1);
@@ -1057,12 +1085,20 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
                 const int r = py * PR + 2 * mt + (wq >> 1), c = pxi * PW + (wq & 1) * 32 + lane;
                 const bool px_ok = share == 0 && r < g.band_rows && c < g.width;
                 const size_t o = ((size_t)r * g.width + c) * FC;
-                float yv[FC];
+                // the pixel's input value: requested now as a raw byte and converted only when z is formed -- a conversion right here
+                // would wait for the load (an L2 / HBM round trip of ~1 000 cycles at the start of every M tile: it showed up as 415
+                // cycles per tile in the phase clocks)
+                uint32_t yraw[FC];
 #pragma unroll
-                for (int q = 0; q < FC; ++q) yv[q] = px_ok ? (float)__ldg(img + o + q) : 0.f;
+                for (int q = 0; q < FC; ++q) {
+                    yraw[q] = 0u;
+                    if (px_ok) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(yraw[q]) : "l"(img + o + q));
+                }
                 for (int nt = 0; nt < n_tiles; ++nt, ++own) {
+                    PE_T(4);
                     mbar_wait(bar_tfull + 8 * grp, own & 1u, err, 4);
                     tcgen05_fence_after();
+                    PE_T(0);
                     const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * 256 + (BN >= 128 ? share * COLS : 0));
                     const uint32_t wt = wbase + (uint32_t)(nt * BN * FC * 4);
                     uint32_t v[2][32];
@@ -1074,34 +1110,46 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
                             if (active) tmem_ld_32x32b_x32(t_row + (uint32_t)(32 * (k + 1)), v[(k + 1) & 1]);
                         } else {
                             // every tcgen05.ld of this accumulator has completed: hand it back before the last chunk's arithmetic
+                            PE_T(1);
                             tcgen05_fence_before();
                             if (lane == 0) mbar_arrive(bar_tempty + 8 * grp);
+                            PE_T(2);
                         }
                         if (active) mul32(v[k & 1], wt + (uint32_t)(32 * k * FC * 4), dot);
                     }
+                    PE_T(3);
+#ifdef GLB200_PT_DEBUG
+                    ea[5] += 1;
+#endif
                 }
                 float part[FC];
 #pragma unroll
                 for (int q = 0; q < FC; ++q)
                     part[q] = ((dot[q][0] + dot[q][1]) + (dot[q][2] + dot[q][3])) + ((dot[q][4] + dot[q][5]) + (dot[q][6] + dot[q][7]));
+                // share 1 hands its part to share 0 through one of two alternating slots: share 1 writes a slot again two M tiles later,
+                // i.e. after the next barrier, which share 0 reaches only after it has read this one
+                float* xs = my_x + (mslot & 1u) * (2 * 4 * 32 * FC);
+                ++mslot;
                 if (share == 1) {
 #pragma unroll
-                    for (int q = 0; q < FC; ++q) my_x[q] = part[q];
+                    for (int q = 0; q < FC; ++q) xs[q] = part[q];
                 }
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + grp * 4 + wq) : "memory");
                 if (px_ok) {
 #pragma unroll
                     for (int q = 0; q < FC; ++q) {
-                        float val = fminf(yv[q] + (part[q] + my_x[q]), 255.f);
+                        float val = fminf((float)(yraw[q] & 0xffu) + (part[q] + xs[q]), 255.f);
                         if (clip_low) val = fmaxf(val, 0.f);
                         z[o + q] = val;
                         if (z8) z8[o + q] = (uint8_t)fminf(fmaxf(val, 0.f), 255.f);
                     }
                 }
-                // (share 1 may not write my_x again before share 0 has read it: with a single N tile nothing else orders the two)
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + grp * 4 + wq) : "memory");
             }
         }
+#ifdef GLB200_PT_DEBUG
+        if (prof && blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 12)) for (int q = 0; q < 6; ++q) prof[16 + (warp == 12) * 8 + q] = ea[q];
+#endif
+#undef PE_T
     }
 
     tcgen05_fence_before();
@@ -1112,7 +1160,7 @@ k_patch_nystroem_dual(const __grid_constant__ CUtensorMap map_a, Geom g, const i
     }
 }
 
-constexpr int nystroem_smem(int fc, int m_pad) { return SA * A_TILE_BYTES + SBT * B_BLOCK_BYTES + 512 + 2 * 4 * 32 * fc * 4 + m_pad * fc * 4 + 1024; }
+constexpr int nystroem_smem(int fc, int m_pad) { return SA * A_TILE_BYTES + SBT * B_BLOCK_BYTES + 512 + 4 * 4 * 32 * fc * 4 + m_pad * fc * 4 + 1024; }
 
 // K_B from the patch layout to dense fp64 [band pixels][p] in the caller's sample order (dst zeroed beforehand)
 __global__ void k_patch_to_f64(Geom g, const int4* __restrict__ pinfo, const uint32_t* __restrict__ slots, const __half* __restrict__ KB, int p,
@@ -1307,7 +1355,7 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
         StageTimer kt(ctx, GL_T_K_GEMM);
         // One channel: two pipelines per SM when every patch is resident (decided on the device: the general kernel, launched right
         // after, returns at once in that case and does all the work otherwise).
-        const bool dual = C == 1 && ctx->pt_dual && !want_prof && dbg == 0;
+        const bool dual = C == 1 && ctx->pt_dual && dbg == 0;
         if (dual) {
 #define PT_LAUNCH2(BNN)                                                                                                                \
     do {                                                                                                                               \
@@ -1315,7 +1363,8 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
         pt::k_patch_nystroem_dual<1, BNN><<<grid, pt::THREADS2, SM, ctx->stream>>>(map_a, g, (const int4*)L_B->pt_info->ptr,           \
                                                                                    (const uint32_t*)L_B->pt_slots->ptr, (const __half*)Wr->ptr, \
                                                                                    m_pad, n_tiles, scales, w, y, clip_low, z, z8,      \
-                                                                                   (int*)err->ptr, (const int*)ctx->dstat->ptr);       \
+                                                                                   (int*)err->ptr, (const int*)ctx->dstat->ptr,        \
+                                                                                   prof ? (long long*)prof->ptr : nullptr);            \
     } while (0)
             if (BN == 256) PT_LAUNCH2(256);
             else if (BN == 128) PT_LAUNCH2(128);
@@ -1350,12 +1399,12 @@ int gl_patch_nystroem_filter(gl_ctx* ctx, const gl_mat* L_B, const float* U, int
         cudaStreamSynchronize(ctx->stream);
         for (int i = 0; i < 2; ++i)
             if (h[i * 8 + 5] > 0)
-                fprintf(stderr, "[pt prof] issuer %d: %lld tiles; cycles per own tile: accumulator free %lld | operands %lld | mma issue %lld | commit %lld | rest %lld\n", i,
+                fprintf(stderr, "[pt prof] issuer %d: %lld tiles; cycles per own tile: accumulator free %lld | operands %lld | mma issue %lld | commit %lld | rest %lld | (dual: A wait %lld, before it %lld)\n", i,
                         h[i * 8 + 5], h[i * 8 + 0] / h[i * 8 + 5], h[i * 8 + 1] / h[i * 8 + 5], h[i * 8 + 2] / h[i * 8 + 5], h[i * 8 + 3] / h[i * 8 + 5],
-                        h[i * 8 + 4] / h[i * 8 + 5]);
+                        h[i * 8 + 4] / h[i * 8 + 5], h[i * 8 + 6] / h[i * 8 + 5], h[i * 8 + 7] / h[i * 8 + 5]);
         for (int i = 0; i < 2; ++i)
             if (h[16 + i * 8 + 5] > 0)
-                fprintf(stderr, "[pt prof] epilogue warp %d: %lld tiles; cycles per tile: accumulator full %lld | tcgen05.ld %lld | hand back %lld | arithmetic %lld | end of M tile %lld\n",
+                fprintf(stderr, "[pt prof] epilogue warp %d: %lld tiles; cycles per tile: accumulator full %lld | loads (+ 3/4 of the arithmetic, dual kernel) %lld | hand back %lld | arithmetic (rest) %lld | end of M tile %lld\n",
                         4 + 4 * i, h[16 + i * 8 + 5], h[16 + i * 8 + 0] / h[16 + i * 8 + 5], h[16 + i * 8 + 1] / h[16 + i * 8 + 5],
                         h[16 + i * 8 + 2] / h[16 + i * 8 + 5], h[16 + i * 8 + 3] / h[16 + i * 8 + 5], h[16 + i * 8 + 4] / h[16 + i * 8 + 5]);
         gl_buf_release(prof);
