@@ -440,7 +440,7 @@ def main():
     aff_ext_tf_dense_equiv = (f_aff + f_ext) / t_ae / 1e12
 
     # ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
-    NCU_TRAFFIC = {("c4", 1, "patch"): (573.9e6, "profiles/r02_ncu_full_c4_v2.txt"),   # 542.4 MB read + 31.5 MB written
+    NCU_TRAFFIC = {("c4", 1, "patch"): (578.0e6, "profiles/r02_ncu_full_c4_v3.txt"),   # 542.4 MB read + 35.6 MB written
                    ("c4", 1, "nostore"): (NOSTORE_TRAFFIC, "profiles/r01_ncu_full_c4_v6.txt"),
                    ("c4", 1, "stored"): (19.14e9, "profiles/r01_ncu_full_c4_v5.txt"),
                    ("c4", 1, "dense"): (33.9e9, "profiles/r01_ncu_full_c4.txt")}
@@ -461,15 +461,16 @@ def main():
         sol["note"] = ("lower bounds of this kernel's time from its three resources: tensor pipe (issued MMA flops / measured burst peak), HBM "
                        "(K_B tiles and the image in, the result out / measured copy bandwidth), CUDA cores (one fp32 FMA per Phi element for the fused filter / "
                        "measured 85.3 FMA per clock per SM: three register-pair operands per FFMA2 make the register file the limit)")
-        roof = dict(kernel="k_patch_nystroem (Nystroem extrapolation over the K_B patch tiles on tcgen05, filter fused, Phi not stored)",
+        roof = dict(kernel="k_patch_nystroem_dual (Nystroem extrapolation over the K_B patch tiles on tcgen05, two pipelines per SM, filter fused, Phi not stored)",
                     bound="tensor", achieved=gemm_tf_exec, peak=peaks["tf_burst"], unit="TFLOP/s", frac=gemm_tf_exec / peaks["tf_burst"],
                     traffic=tr[0] if tr else None, traffic_source=tr[1] if tr else None,
                     peak_source=peaks["source"] + " bf16 burst (a ~1 ms kernel at full clocks, no power cap)", ms=med["k_gemm"],
                     flop=f_ext_exec, flop_dense_equivalent=f_ext, algorithmic_bytes=gemm_bytes, hbm_gbs=gemm_gbs,
                     speed_of_light=sol,
                     note="flop = MMA work issued (2 x multiplied (pixel, slot) pairs x m_pad); round 1's blocked layout issued 5.5x as much "
-                         "for the same result (1.80e12 flop in 1.67 ms = 0.65 of peak).  The kernel is latency-bound: K loops of one or two "
-                         "steps leave nothing to hide the per-tile hand-overs behind (tensor pipe 10 % busy, ncu)")
+                         "for the same result (1.80e12 flop in 1.67 ms = 0.65 of peak).  The kernel is bound by its fused filter epilogue (CUDA-core FMAs + "
+                         "weight loads, ~0.5 ms of it) and the hand-over chain of a tile, not by the tensor pipe (K loops of one or two steps): "
+                         "see speed_of_light and profiles/r02_patch_timeline.md")
     elif kept < 0.5:
         # With the spatial cutoff and Phi not stored, the GEMM moves little (the stored K_B blocks in, row partials out) and is
         # bound by the tensor work it ISSUES: every stored 64-slot block is multiplied whole, padding included.
