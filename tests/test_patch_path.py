@@ -138,3 +138,24 @@ def test_patch_staged_calls_and_lazy_blocked_storage(ctx):
     assert _rel(P @ (P.T @ y), ref["phi"] @ (ref["phi"].T @ y)) < 2e-2                       # projector parity (signs are arbitrary)
     z2 = ctx.filter(phi, mu).astype(np.float64)                      # now from the stored Phi
     assert _rel(z2, z) < 2e-5
+
+
+@pytest.mark.parametrize("W,H,p,m,h_loc", [(640, 353, 400, -1, 30.0), (450, 300, 300, 256, 40.0), (700, 90, 500, 700, 8.0)])
+def test_patch_dual_pipelines_match_the_general_kernel(ctx, W, H, p, m, h_loc):
+    """Option pt_dual: the extrapolation as two pipelines per SM (k_patch_nystroem_dual: every patch resident, one channel) against
+    the general kernel on the same K_B -- same MMAs, same order of the row dots, so the same bits; N tiles of 256 columns (one and
+    several), odd M-tile counts at the band's lower edge, patches with two slot blocks (h_loc 40 on a small image)."""
+    img = o.synthetic_image(W, H, 1, seed=21)
+    ctx.set_image(img)
+    prm = gl.default_params(sampling=gl.RANDOM, sample_size=p, seed=2, num_eigvals=m, h_loc=h_loc)
+    z1, z0 = np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
+    ctx.run_resident(prm, z_out=z1)
+    ctx.set_option("pt_dual", 0)
+    try:
+        ctx.run_resident(prm, z_out=z0)
+    finally:
+        ctx.set_option("pt_dual", 1)
+    assert np.array_equal(z1, z0)
+    s = oc.random_sampling(W, H, p, 2)
+    ref = o.run_pipeline(img, s, m=None if m < 0 else m, h_loc=h_loc)
+    assert _rel(z1, ref["z"]) <= TOL_Z and _rel(z1.astype(np.float64) - img, ref["z"] - img) <= TOL_DZ
