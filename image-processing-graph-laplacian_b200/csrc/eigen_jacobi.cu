@@ -168,19 +168,25 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
     // ---- diagonalise the 16 x 16 block: cyclic two-sided Jacobi, Q accumulates the rotations ----
     PPROF(2);
     if (pair_off > 0.25f * tol) {
-        if (tid == 0) *s_off = 0.f;
-        __syncthreads();
-        for (int isw = 0; isw < inner_max; ++isw) {
-            for (int st = 0; st < JP - 1; ++st) {
-                if (tid < JB) {
+        // One warp diagonalises the block with warp-level barriers only: with all 256 threads on it, every one of the 15 steps of a
+        // sweep cost three CTA barriers around a few dozen fp64 operations per thread (1 060 cycles per step, 60 % of a pair's time).
+        // Lane (k, sub) = (lane >> 2, lane & 3) works for pair k of the step: it computes the pair's rotation itself (the four lanes of
+        // a pair redundantly, from the same three entries), then B <- B J and Q <- Q J on rows 4 sub .. 4 sub + 3 of the pair's two
+        // columns, then B <- J^T B on columns 4 sub .. 4 sub + 3 of the pair's two rows -- in place: within a half step no two lanes
+        // touch the same entry.
+        if (tid < 32) {
+            const int k = lane >> 2, sub = lane & 3;
+            for (int isw = 0; isw < inner_max; ++isw) {
+                float sw_off = 0.f;
+                for (int st = 0; st < JP - 1; ++st) {
                     int a, b;
-                    tournament(st, tid, JP, a, b);
+                    tournament(st, k, JP, a, b);
                     const double app = Bm[a * 17 + a], aqq = Bm[b * 17 + b], apq = Bm[a * 17 + b];
-                    double c = 1.0, s = 0.0;
+                    double c = 1.0, sn = 0.0;
                     if (app > 0.0 && aqq > 0.0) {
-                        // The rotation ANGLE only has to be about right (fp32: fast rsqrt / divide instead of chains of
-                        // fp64 sqrt and divide, which dominated the step); the rotation itself must be orthogonal to fp64
-                        // accuracy, so c = (1 + t^2)^-1/2 is polished with two Newton steps in fp64 and s = t c.
+                        // The rotation ANGLE only has to be about right (fp32: fast rsqrt / divide instead of chains of fp64 sqrt and
+                        // divide); the rotation itself must be orthogonal to fp64 accuracy, so c = (1 + t^2)^-1/2 is polished with two
+                        // Newton steps in fp64 and s = t c.
                         const float rel = fabsf((float)apq) * rsqrtf((float)app * (float)aqq);
                         if (rel > 1e-12f) {
                             const float tau = __fdividef((float)(aqq - app), 2.f * (float)apq);
@@ -191,47 +197,36 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
                             y = y * fma(-0.5 * x, y * y, 1.5);
                             y = y * fma(-0.5 * x, y * y, 1.5);
                             c = y;
-                            s = t * y;
+                            sn = t * y;
                         }
-                        if (rel > *s_off) atomicMax((unsigned*)s_off, __float_as_uint(rel));
+                        sw_off = fmaxf(sw_off, rel);
                     }
-                    cs[2 * tid] = c;
-                    cs[2 * tid + 1] = s;
-                    pq[2 * tid] = a;
-                    pq[2 * tid + 1] = b;
-                    role[a] = tid << 1;
-                    role[b] = (tid << 1) | 1;
-                }
-                __syncthreads();
-                double nb_, nq_;
-                {
-                    const int ri = role[bi], rj = role[bj];
-                    const int ki = ri >> 1, kj = rj >> 1;
-                    const double ci = cs[2 * ki], si = cs[2 * ki + 1], cj = cs[2 * kj], sj = cs[2 * kj + 1];
-                    const int ip = pq[2 * ki], iq = pq[2 * ki + 1], jp = pq[2 * kj], jq = pq[2 * kj + 1];
-                    double x_ip, x_iq;  // (B J)[ip][bj], (B J)[iq][bj]
-                    if ((rj & 1) == 0) {
-                        x_ip = cj * Bm[ip * 17 + jp] - sj * Bm[ip * 17 + jq];
-                        x_iq = cj * Bm[iq * 17 + jp] - sj * Bm[iq * 17 + jq];
-                        nq_ = cj * Qm[bi * 17 + jp] - sj * Qm[bi * 17 + jq];
-                    } else {
-                        x_ip = sj * Bm[ip * 17 + jp] + cj * Bm[ip * 17 + jq];
-                        x_iq = sj * Bm[iq * 17 + jp] + cj * Bm[iq * 17 + jq];
-                        nq_ = sj * Qm[bi * 17 + jp] + cj * Qm[bi * 17 + jq];
+                    __syncwarp();      // every lane has read its pair's entries before the columns are overwritten
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int r = 4 * sub + rr;
+                        const double ba = Bm[r * 17 + a], bb = Bm[r * 17 + b], qa = Qm[r * 17 + a], qb = Qm[r * 17 + b];
+                        Bm[r * 17 + a] = c * ba - sn * bb;
+                        Bm[r * 17 + b] = sn * ba + c * bb;
+                        Qm[r * 17 + a] = c * qa - sn * qb;
+                        Qm[r * 17 + b] = sn * qa + c * qb;
                     }
-                    nb_ = ((ri & 1) == 0) ? (ci * x_ip - si * x_iq) : (si * x_ip + ci * x_iq);
+                    __syncwarp();
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 4 * sub + jj;
+                        const double xa = Bm[a * 17 + j], xb = Bm[b * 17 + j];
+                        Bm[a * 17 + j] = c * xa - sn * xb;
+                        Bm[b * 17 + j] = sn * xa + c * xb;
+                    }
+                    __syncwarp();
                 }
-                __syncthreads();
-                Bm[bi * 17 + bj] = nb_;
-                Qm[bi * 17 + bj] = nq_;
-                __syncthreads();
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sw_off = fmaxf(sw_off, __shfl_xor_sync(0xffffffffu, sw_off, o));
+                if (sw_off <= 0.1f * tol) break;
             }
-            const float inner_off = *s_off;
-            __syncthreads();
-            if (tid == 0) *s_off = 0.f;
-            __syncthreads();
-            if (inner_off <= 0.1f * tol) break;
         }
+        __syncthreads();
         PPROF(3);
         // ---- apply: [G_I G_J] <- [G_I G_J] Q, streamed straight back to global ----
         const int cgp = tid & 3;
