@@ -628,9 +628,14 @@ int gl_impl_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat**
         KB->aff_h_loc = h_loc;
         KB->aff_h_val = h_val;
         if ((rc = gl_alloc(ctx, sizeof(double) * (size_t)(1 + 2 * C) * p_pad, &KB->aux)) != GL_OK) break;  // [D | T[ch] | (K_A y_S)[ch]]
-        if (kind != GL_NLM && (rc = affinity_a(ctx, kind, h_loc, h_val, (double*)KA->buf->ptr)) != GL_OK) break;
-        if (patch) rc = gl_patch_affinity(ctx, kind, h_loc, h_val, KB);
-        else {
+        // (patch path: the sample lists are built first -- they need no pixels, so gl_run's image upload runs under them --, K_A after)
+        if (!patch) GL_BREAK(rc, gl_image_ready(ctx));
+        if (!patch && kind != GL_NLM && (rc = affinity_a(ctx, kind, h_loc, h_val, (double*)KA->buf->ptr)) != GL_OK) break;
+        if (patch) {
+            rc = gl_patch_affinity(ctx, kind, h_loc, h_val, KB);
+            if (rc == GL_OK) rc = gl_image_ready(ctx);
+            if (rc == GL_OK) rc = affinity_a(ctx, kind, h_loc, h_val, (double*)KA->buf->ptr);
+        } else {
             GL_CUDA_BREAK(rc, cudaMemsetAsync(KB->aux->ptr, 0, sizeof(double) * (size_t)(1 + 2 * C) * p_pad, ctx->stream));
             rc = affinity_blocked_fill(ctx, kind, h_loc, h_val, KB, (double*)KA->buf->ptr, (double*)KB->aux->ptr);
         }

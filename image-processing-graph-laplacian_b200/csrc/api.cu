@@ -96,6 +96,9 @@ int gl_ctx_create(gl_ctx** out, int device, int rank, int world)
     ctx->world = world;
     ctx->sm_count = prop.multiProcessorCount;
     GL_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    GL_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    GL_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming));
+    GL_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_prev, cudaEventDisableTiming));
     for (int i = 0; i < GL_T_COUNT; ++i) {
         GL_CUDA_CHECK(cudaEventCreate(&ctx->ev_begin[i]));
         GL_CUDA_CHECK(cudaEventCreate(&ctx->ev_end[i]));
@@ -213,6 +216,9 @@ int gl_ctx_destroy(gl_ctx* ctx)
         cudaEventDestroy(ctx->ev_end[i]);
     }
     for (int i = 0; i < GL_MARKS; ++i) cudaEventDestroy(ctx->marks[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
+    if (ctx->ev_prev) cudaEventDestroy(ctx->ev_prev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GL_OK;
@@ -328,6 +334,14 @@ void gl_buf_release(gl_buf* b)
     ctx->bytes_cached += b->bytes;
     ctx->bytes_live -= b->bytes;
     delete b;
+}
+
+int gl_image_ready(gl_ctx* ctx)
+{
+    if (!ctx->h2d_pending) return GL_OK;
+    ctx->h2d_pending = false;
+    GL_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d, 0));
+    return GL_OK;
 }
 
 int gl_ensure_pinned(gl_ctx* ctx, size_t bytes)
@@ -1202,7 +1216,17 @@ int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channe
     cudaEventRecord(ctx->ev_begin[GL_T_TOTAL], ctx->stream);
     if (ctx->world == 1 || prm->affinity_kind == GL_NLM) {
         // (NLM reads 7x7 patches around every band pixel and every sample, wherever it lies: every rank takes the whole image)
-        GL_CHECK(gl_set_image(ctx, pixels, width, height, channels));
+        // The upload goes on the copy stream, behind whatever the context stream still has in flight on the old image; the stages wait
+        // for it only where they first read pixels (gl_image_ready), so sampling and the patch lists run under it.
+        GL_CHECK(set_image_geometry(ctx, width, height, channels));
+        GL_CUDA_CHECK(cudaEventRecord(ctx->ev_prev, ctx->stream));
+        GL_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_prev, 0));
+        GL_CUDA_CHECK(cudaEventRecord(ctx->ev_begin[GL_T_H2D], ctx->copy_stream));
+        GL_CUDA_CHECK(cudaMemcpyAsync(ctx->img->ptr, pixels, (size_t)(ctx->n * channels), cudaMemcpyHostToDevice, ctx->copy_stream));
+        GL_CUDA_CHECK(cudaEventRecord(ctx->ev_end[GL_T_H2D], ctx->copy_stream));
+        ctx->ev_valid[GL_T_H2D] = true;
+        GL_CUDA_CHECK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
+        ctx->h2d_pending = true;
     } else {
         // a rank of a multi-GPU run needs its own band of rows and the sampled pixels, nothing else: upload the band now, the
         // p sample values right after the sampling stage (gl_run_resident); the rest of ctx->img is not meaningful
@@ -1214,6 +1238,7 @@ int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channe
     }
     ctx->total_started = true;
     const int rc = gl_run_resident(ctx, prm, z_f32, z_u8, p_out, m_out, eigvals_out, eigvals_cap);
+    gl_image_ready(ctx);     // (a run that failed before its first pixel read: the upload still orders before later work)
     ctx->host_pixels = nullptr;
     return rc;
 }

@@ -144,6 +144,11 @@ struct gl_ctx {
     int row0 = 0, row1 = 0;  // band of image rows owned by this rank
     int64_t q0 = 0, q1 = 0;  // raster range of the band
     gl_buf* img = nullptr;   // u8 [n * channels]
+    // gl_run's image upload runs on its own stream so that the stages that do not read pixels (sampling, the patch lists) overlap it;
+    // gl_image_ready() makes ctx->stream wait for it, and is called before the first kernel of a run that reads ctx->img
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_prev = nullptr;
+    bool h2d_pending = false;
     const uint8_t* host_pixels = nullptr;  // during a multi-GPU gl_run: the caller's host image (band + sample pixels are uploaded)
 
     unsigned long long image_epoch = 0;  // bumped by every gl_set_*image
@@ -234,6 +239,7 @@ int gl_status_check(gl_ctx* ctx, bool* pt_overflow); // wait for the copy and tu
 int gl_host_samples(gl_ctx* ctx);
 
 int gl_alloc(gl_ctx* ctx, size_t bytes, gl_buf** out);
+int gl_image_ready(gl_ctx* ctx);   // ctx->stream waits for a pending image upload (no-op otherwise)
 void gl_buf_release(gl_buf* b);
 gl_mat* gl_mat_new(gl_ctx* ctx, int kind);
 int gl_ensure_pinned(gl_ctx* ctx, size_t bytes);

@@ -278,8 +278,10 @@ k_patch_affinity(Geom g, const uint8_t* __restrict__ img, const float* __restric
             for (int i = 0; i < PR; ++i) {
                 const int mt = i >> 1;
                 if (r_base + 2 * mt >= g.band_rows) break;      // M tiles wholly below the band are neither stored nor multiplied
+                // a pixel outside the image / band gets a row coordinate at 1e18: its spatial exponent is hugely negative and K = 0 without
+                // a select per pair (both kinds served here have the spatial term; 1e36 * a2 stays finite)
                 const bool ok = col_ok && r_base + i < g.band_rows;
-                const float pr = (float)(g.row0 + r_base + i);
+                const float pr = ok ? (float)(g.row0 + r_base + i) : 1e18f;
                 float pv[C];
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) pv[ch] = px[ch * PW * PR + i * PW + ty];
@@ -301,7 +303,7 @@ k_patch_affinity(Geom g, const uint8_t* __restrict__ img, const float* __restric
                         }
                         x = fmaf(t, b2, x);
                     }
-                    kv[k] = ok ? fast_exp2(x) : 0.f;
+                    kv[k] = fast_exp2(x);
                     acc[k] += kv[k];
 #pragma unroll
                     for (int ch = 0; ch < C; ++ch) tacc[ch][k] = fmaf(kv[k], pv[ch], tacc[ch][k]);
@@ -1279,6 +1281,7 @@ int gl_patch_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat*
                                                         (uint32_t*)KB->pt_slots->ptr, (const int*)ctx->dstat->ptr);
         ctx->launches++;
         GL_BREAK(rc, gl_alloc(ctx, sizeof(float) * (size_t)(2 + C) * p_pad, &sf));
+        GL_BREAK(rc, gl_image_ready(ctx));      // from here on pixels are read
         pt::k_patch_sample_features<<<(unsigned)ceil_div(p_pad, 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->img->ptr,
                                                                                             (const uint32_t*)ctx->samples->ptr, p, p_pad,
                                                                                             ctx->width, C, (float*)sf->ptr);
