@@ -514,7 +514,7 @@ def main():
                e2e=dict(value=e2e_val, unit="Mpixel/s",
                         h2d_bytes_per_step=(n * channels if world == 1 else (band_px + p) * channels),   # N > 1: a rank uploads its band + the sample pixels
                         d2h_bytes_per_step=band_px * channels,
-                        ms_per_step=t_e2e / args.steps, result="filtered image as u8 (the reference's png bytes), per-rank band",
+                        ms_per_step=t_e2e / args.steps, result="filtered image as u8 (the reference's png bytes), per-rank band; with the patch path the kernel stores the bytes straight into the pinned host image (they cross PCIe under the kernel, no separate copy), the input image is uploaded on a copy stream under the sampling and list-building stages",
                         with_fp32_result=dict(value=n / (t_e2e_f32 / args.steps * 1e-3) / 1e6, ms_per_step=t_e2e_f32 / args.steps,
                                               d2h_bytes_per_step=band_px * channels * 4)),
                gpu_launches=int(launches), first_call_ms=first_call_ms, phi_stored=phi_fits,

@@ -167,6 +167,8 @@ int gl_ctx_set_option(gl_ctx* ctx, const char* key, const char* value)
     } else if (!strcmp(key, "kb_strips")) {
         ctx->kb_strips = atoi(value);
         GL_REQUIRE(ctx->kb_strips >= 0 && ctx->kb_strips <= 64, "option kb_strips: want 0..64");
+    } else if (!strcmp(key, "z8_direct")) {
+        ctx->z8_direct = atoi(value) != 0;
     } else if (!strcmp(key, "pt_dual")) {
         ctx->pt_dual = atoi(value) != 0;
     } else if (!strcmp(key, "eig_largest")) {

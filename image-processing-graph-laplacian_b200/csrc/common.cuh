@@ -184,6 +184,7 @@ struct gl_ctx {
     int64_t tile_total_blocks = 0;
     int kb_cutoff = 1;        // option kb_cutoff: 1 = skip sample blocks whose K_B entries fp16 flushes to zero, 0 = dense
     int pt_dual = 1;          // option pt_dual: 1 = the patch extrapolation runs as two pipelines per SM when every patch is resident (one channel)
+    int z8_direct = 1;        // option z8_direct: the fused patch path writes the u8 result straight into a pinned host destination (no D2H copy)
     int kb_layout = 1;        // option kb_layout: 1 = patch layout for the spatially decaying affinities (patch.cu), 0 = always blocked
     bool want_blocked = false;  // set by gl_run_resident around gl_affinity when the path will need Phi itself (no fused filter)
 
@@ -296,8 +297,11 @@ int gl_phi_materialise(gl_ctx* ctx, gl_mat* phi, const gl_fused_filter* ff = nul
 int gl_filter_weights_from_proj(gl_ctx* ctx, const double* proj, const double* f, double gain, int m, int m_pad, int C, float* w);
 // parts > 0: z = y + the sum of `parts` row partials in zpart; parts == 0: z_dev / z8_dev already hold the band's filtered pixels (the
 // patch kernel wrote them).  Either way the sample pixels' rows are patched and the result is copied to the host destinations.
+// z8_direct: the u8 result was (and the sample rows are) written by the kernels straight into the caller's pinned host image (its band
+// starts at this pointer): no device copy of it exists and nothing is copied afterwards
 int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int parts, const float* w, const float* U, int ldU,
-                           int clip_low, float* z_f32, uint8_t* z_u8, gl_buf* z_dev = nullptr, gl_buf* z8_dev = nullptr);
+                           int clip_low, float* z_f32, uint8_t* z_u8, gl_buf* z_dev = nullptr, gl_buf* z8_dev = nullptr,
+                           uint8_t* z8_direct = nullptr);
 int gl_impl_orthonormalise(gl_ctx* ctx, gl_mat* phi, double* norms_out);
 int gl_impl_filter(gl_ctx* ctx, gl_mat* phi, gl_mat* f_eigvals, double gain, int clip_low, float* z_f32, uint8_t* z_u8);
 int gl_impl_diag_map(gl_ctx* ctx, gl_mat* d, int op, double arg, gl_mat** out);

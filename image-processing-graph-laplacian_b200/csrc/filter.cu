@@ -377,7 +377,7 @@ __global__ void k_filter_sample_rows(const float* __restrict__ U, int ldU, int p
 }
 
 int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int parts, const float* w, const float* U, int ldU,
-                           int clip_low, float* z_f32, uint8_t* z_u8, gl_buf* z_dev, gl_buf* z8_dev)
+                           int clip_low, float* z_f32, uint8_t* z_u8, gl_buf* z_dev, gl_buf* z8_dev, uint8_t* z8_direct)
 {
     const int C = ctx->channels;
     const int64_t rows = phi->local_rows;
@@ -385,18 +385,19 @@ int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int par
     int rc = GL_OK;
     do {
         if (!z && (rc = gl_alloc(ctx, sizeof(float) * (size_t)rows * C, &z)) != GL_OK) break;
-        if (z_u8 && !z8 && (rc = gl_alloc(ctx, (size_t)rows * C, &z8)) != GL_OK) break;
+        if (z_u8 && !z8 && !z8_direct && (rc = gl_alloc(ctx, (size_t)rows * C, &z8)) != GL_OK) break;
+        uint8_t* z8p = z8_direct ? z8_direct : (z8 ? (uint8_t*)z8->ptr : nullptr);
         {
             StageTimer t(ctx, GL_T_FILTER);
             const uint8_t* y = (const uint8_t*)ctx->img->ptr + (size_t)phi->q0 * C;
             if (parts > 0) {
                 k_filter_sum_parts<<<(unsigned)ceil_div(rows * C, 256), 256, 0, ctx->stream>>>(zpart, parts, rows, C, y, clip_low, (float*)z->ptr,
-                                                                                              z8 ? (uint8_t*)z8->ptr : nullptr);
+                                                                                              z8p);
                 GL_LAUNCH_CHECK(ctx);
             }
             k_filter_sample_rows<<<phi->p, 128, 0, ctx->stream>>>(U, ldU, phi->p, phi->m, (const uint32_t*)ctx->samples->ptr, phi->q0,
                                                                  phi->q0 + rows, C, w, (const uint8_t*)ctx->img->ptr, clip_low,
-                                                                 (float*)z->ptr, z8 ? (uint8_t*)z8->ptr : nullptr);
+                                                                 (float*)z->ptr, z8p);
             GL_LAUNCH_CHECK(ctx);
         }
         ctx->ev_valid[GL_T_K_FILTER_PROJECT] = false;
@@ -406,10 +407,10 @@ int gl_filter_fused_finish(gl_ctx* ctx, gl_mat* phi, const float* zpart, int par
             if (z_f32)
                 GL_CUDA_BREAK(rc, cudaMemcpyAsync(z_f32 + (size_t)phi->q0 * C, z->ptr, sizeof(float) * (size_t)rows * C, cudaMemcpyDeviceToHost,
                                               ctx->stream));
-            if (z_u8)
+            if (z_u8 && !z8_direct)
                 GL_CUDA_BREAK(rc, cudaMemcpyAsync(z_u8 + (size_t)phi->q0 * C, z8->ptr, (size_t)rows * C, cudaMemcpyDeviceToHost, ctx->stream));
         }
-        if (z_f32 || z_u8) GL_CUDA_BREAK(rc, cudaStreamSynchronize(ctx->stream));
+        if (z_f32 || z_u8 || z8_direct) GL_CUDA_BREAK(rc, cudaStreamSynchronize(ctx->stream));
     } while (0);
     if (z) gl_buf_release(z);
     if (z8) gl_buf_release(z8);

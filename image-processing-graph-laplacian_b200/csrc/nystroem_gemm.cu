@@ -770,13 +770,23 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
             // the patch kernel writes the band's filtered pixels itself; the finish only patches the sample pixels' rows
             const int C = ctx->channels;
             gl_buf *zd = nullptr, *z8d = nullptr;
-            if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)rows * C, &zd)) == GL_OK && ff->z_u8) rc = gl_alloc(ctx, (size_t)rows * C, &z8d);
+            // A u8 destination in pinned host memory is written by the kernel itself, pixel by pixel as the patches finish (32 contiguous
+            // bytes per warp store over PCIe): the 8 MB device-to-host copy that followed the kernel disappears under it.
+            uint8_t* z8_direct = nullptr;
+            if (ff->z_u8 && ctx->z8_direct) {
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, ff->z_u8) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+                    z8_direct = (uint8_t*)at.devicePointer + (size_t)L_B->q0 * C;
+                else
+                    (void)cudaGetLastError();
+            }
+            if ((rc = gl_alloc(ctx, sizeof(float) * (size_t)rows * C, &zd)) == GL_OK && ff->z_u8 && !z8_direct) rc = gl_alloc(ctx, (size_t)rows * C, &z8d);
             if (rc == GL_OK)
                 rc = gl_patch_nystroem_filter(ctx, L_B, U, (int)phi_A->ld, m, mu_inv, (const float*)scales->ptr, (const float*)wbuf->ptr, C,
-                                              ff->clip_low, (float*)zd->ptr, z8d ? (uint8_t*)z8d->ptr : nullptr);
+                                              ff->clip_low, (float*)zd->ptr, z8_direct ? z8_direct : (z8d ? (uint8_t*)z8d->ptr : nullptr));
             if (rc == GL_OK)
                 rc = gl_filter_fused_finish(ctx, phi, nullptr, 0, (const float*)wbuf->ptr, U, (int)phi_A->ld, ff->clip_low, ff->z_f32, ff->z_u8,
-                                            zd, z8d);
+                                            zd, z8d, z8_direct);
             else { if (zd) gl_buf_release(zd); if (z8d) gl_buf_release(z8d); }
         } else {
             rc = gl_gemm_kmajor(ctx, L_B->buf->ptr, 0, rows, k_dim, Wt->ptr, m_pad, (const float*)scales->ptr, nullptr,

@@ -159,3 +159,28 @@ def test_patch_dual_pipelines_match_the_general_kernel(ctx, W, H, p, m, h_loc):
     s = oc.random_sampling(W, H, p, 2)
     ref = o.run_pipeline(img, s, m=None if m < 0 else m, h_loc=h_loc)
     assert _rel(z1, ref["z"]) <= TOL_Z and _rel(z1.astype(np.float64) - img, ref["z"] - img) <= TOL_DZ
+
+
+def test_u8_result_straight_into_pinned_host_memory(ctx):
+    """gl_run with a u8 destination in pinned host memory: the fused patch kernel writes the filtered bytes itself (option z8_direct,
+    no device-to-host copy afterwards); same bytes as through a pageable destination, which takes the copy."""
+    W, H, p = 640, 353, 400
+    img = o.synthetic_image(W, H, 1, seed=33)
+    prm = gl.default_params(sampling=gl.RANDOM, sample_size=p, seed=5, h_loc=30.0)
+    z8_page = np.zeros((H, W), np.uint8)
+    ctx.run(img, prm, z_out=False, z8_out=z8_page, want_eigvals=False)
+    pin = gl.PinnedArray((H, W), np.uint8)
+    try:
+        pin.array[...] = 7
+        ctx.run(img, prm, z_out=False, z8_out=pin.array, want_eigvals=False)
+        assert np.array_equal(pin.array, z8_page)
+        ctx.set_option("z8_direct", 0)
+        pin.array[...] = 9
+        ctx.run(img, prm, z_out=False, z8_out=pin.array, want_eigvals=False)
+        assert np.array_equal(pin.array, z8_page)
+    finally:
+        ctx.set_option("z8_direct", 1)
+        pin.free()
+    zf = np.zeros((H, W), np.float32)
+    ctx.run(img, prm, z_out=zf, want_eigvals=False)
+    assert np.array_equal(z8_page, np.clip(zf, 0, 255).astype(np.uint8))
