@@ -1073,7 +1073,45 @@ __global__ void k_scatter_sample_pixels(uint8_t* __restrict__ img, const uint32_
     img[(size_t)samples[i / C] * C + (i % C)] = vals[i];
 }
 
-// multi-GPU gl_run: the values of the p sampled pixels, gathered from the caller's host image, placed into ctx->img
+__global__ void k_gather_sample_pixels(const uint8_t* __restrict__ img, const uint32_t* __restrict__ samples, int p, int C, int64_t q0, int64_t q1,
+                                       float* __restrict__ vals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p * C) return;
+    const int64_t q = samples[i / C];
+    vals[i] = (q >= q0 && q < q1) ? (float)img[(size_t)q * C + (i % C)] : 0.f;
+}
+__global__ void k_scatter_sample_pixels_f32(uint8_t* __restrict__ img, const uint32_t* __restrict__ samples, const float* __restrict__ vals, int p, int C)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p * C) return;
+    img[(size_t)samples[i / C] * C + (i % C)] = (uint8_t)vals[i];
+}
+
+// multi-GPU gl_run: every rank has uploaded its own band of rows only; the p sampled pixels lie in all bands.  Each rank contributes the
+// values of the samples it holds (zero for the others) to ONE small allreduce and writes the sums into its image -- no host in between
+// (the earlier version fetched the indices, gathered the values from the caller's host image and uploaded them: two round trips).
+static int exchange_sample_pixels(gl_ctx* ctx)
+{
+    const int p = (int)ctx->p, C = ctx->channels;
+    gl_buf* vals = nullptr;
+    GL_CHECK(gl_alloc(ctx, sizeof(float) * (size_t)p * C, &vals));
+    const unsigned blocks = (unsigned)ceil_div(p * C, 256);
+    k_gather_sample_pixels<<<blocks, 256, 0, ctx->stream>>>((const uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, p, C, ctx->q0, ctx->q1,
+                                                            (float*)vals->ptr);
+    ctx->launches++;
+    int rc = gl_allreduce_f32(ctx, (float*)vals->ptr, (size_t)p * C);
+    if (rc == GL_OK) {
+        k_scatter_sample_pixels_f32<<<blocks, 256, 0, ctx->stream>>>((uint8_t*)ctx->img->ptr, (const uint32_t*)ctx->samples->ptr, (const float*)vals->ptr, p, C);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { gl_set_error("gl_run: exchanging the sample pixels failed"); rc = GL_ERR_CUDA; }
+    }
+    gl_buf_release(vals);
+    return rc;
+}
+
+// (the same through the host, kept for a context whose communicator is not up: the values of the p sampled pixels, gathered from the
+// caller's host image, placed into ctx->img)
 static int upload_sample_pixels(gl_ctx* ctx)
 {
     const int p = (int)ctx->p, C = ctx->channels;
@@ -1116,7 +1154,10 @@ static int run_resident_once(gl_ctx* ctx, const gl_params* prm, float* z_f32, ui
     unsigned p = 0;
     if (prm->sampling_random) GL_CHECK(gl_sampling_random(ctx, requested, prm->seed, &p));
     else GL_CHECK(gl_sampling_uniform(ctx, requested, &p));
-    if (ctx->host_pixels) GL_CHECK(upload_sample_pixels(ctx));
+    if (ctx->host_pixels) {
+        GL_CHECK(gl_image_ready(ctx));      // the band upload (copy stream) before anything touches ctx->img
+        GL_CHECK(ctx->comm ? exchange_sample_pixels(ctx) : upload_sample_pixels(ctx));
+    }
 
     gl_mat *K_A = nullptr, *K_B = nullptr, *L_A = nullptr, *L_B = nullptr;
     gl_mat *U = nullptr, *mu = nullptr, *mu_inv = nullptr, *phi = nullptr, *f_mu = nullptr;
@@ -1233,9 +1274,15 @@ int gl_run(gl_ctx* ctx, const uint8_t* pixels, int width, int height, int channe
         // a rank of a multi-GPU run needs its own band of rows and the sampled pixels, nothing else: upload the band now, the
         // p sample values right after the sampling stage (gl_run_resident); the rest of ctx->img is not meaningful
         GL_CHECK(set_image_geometry(ctx, width, height, channels));
-        StageTimer t(ctx, GL_T_H2D);
+        GL_CUDA_CHECK(cudaEventRecord(ctx->ev_prev, ctx->stream));
+        GL_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_prev, 0));
+        GL_CUDA_CHECK(cudaEventRecord(ctx->ev_begin[GL_T_H2D], ctx->copy_stream));
         GL_CUDA_CHECK(cudaMemcpyAsync((uint8_t*)ctx->img->ptr + (size_t)ctx->q0 * channels, pixels + (size_t)ctx->q0 * channels,
-                                      (size_t)(ctx->q1 - ctx->q0) * channels, cudaMemcpyHostToDevice, ctx->stream));
+                                      (size_t)(ctx->q1 - ctx->q0) * channels, cudaMemcpyHostToDevice, ctx->copy_stream));
+        GL_CUDA_CHECK(cudaEventRecord(ctx->ev_end[GL_T_H2D], ctx->copy_stream));
+        ctx->ev_valid[GL_T_H2D] = true;
+        GL_CUDA_CHECK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
+        ctx->h2d_pending = true;
         ctx->host_pixels = pixels;
     }
     ctx->total_started = true;
