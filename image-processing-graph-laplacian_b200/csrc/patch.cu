@@ -100,74 +100,72 @@ __global__ void __launch_bounds__(256) k_patch_count(Geom g, const uint32_t* __r
 __global__ void __launch_bounds__(1024) k_patch_scan(Geom g, int npatch, int4* __restrict__ pinfo, int* __restrict__ total, long long cap_blocks,
                                                      int* __restrict__ dstat)
 {
-    __shared__ int part[1024];
-    __shared__ unsigned long long ksum, wks[32];
-    __shared__ int max_nb;
-    if (threadIdx.x == 0) { ksum = 0ull; max_nb = 0; }
+    // Warp w owns the contiguous run of `per` x 32 patches [w per 32, (w + 1) per 32); in every iteration its lanes read 32 consecutive
+    // records (512 contiguous bytes: with one thread per run of `per` records every load touched its own sector, and the single SM
+    // that runs this kernel spent 20 us on them).  Pass 1: block counts per warp; scan of the 32 warp totals; pass 2: the records again,
+    // warp-scanned, offsets written.
+    __shared__ int wsum[32], wbase[33];
+    __shared__ unsigned long long wks[32];
+    __shared__ int wmax[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (npatch + 1023) / 1024;
-    const int a = threadIdx.x * per, b = min(npatch, a + per);
+    const int a = warp * per * 32, b = min(npatch, a + per * 32);
     int s = 0, nbmax = 0;
     unsigned long long ks = 0;
-    for (int i0 = a; i0 < b; i0 += 8) {      // eight loads in flight (one after the other they were eight L2 round trips per thread)
-        int4 v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = i0 + k < b ? pinfo[i0 + k] : make_int4(0, 0, 0, 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int i = i0 + k;
-            if (i >= b) break;
-            const int4 pi = v[k];
-            s += pi.y;
-            nbmax = max(nbmax, pi.y);
-            const int mtc = min(G, (g.band_rows - (i / g.pcols) * PR + 1) >> 1);
-            const int last = pi.z - SLOTS * (pi.y - 1);
-            ks += (unsigned long long)mtc * (unsigned long long)(2 * (pi.y - 1) + (last > 16 ? 2 : 1));
-        }
+    for (int i = a + lane; i < b; i += 32) {
+        const int4 pi = pinfo[i];
+        s += pi.y;
+        nbmax = max(nbmax, pi.y);
+        const int mtc = min(G, (g.band_rows - (i / g.pcols) * PR + 1) >> 1);
+        const int last = pi.z - SLOTS * (pi.y - 1);
+        ks += (unsigned long long)mtc * (unsigned long long)(2 * (pi.y - 1) + (last > 16 ? 2 : 1));
     }
-    part[threadIdx.x] = s;
-    __syncthreads();
-    // (no 64-bit shared-memory atomics: they are CAS loops, and even one per warp queued for ~20 us; per-warp words, summed by one thread)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
         ks += __shfl_xor_sync(0xffffffffu, ks, o);
         nbmax = max(nbmax, __shfl_xor_sync(0xffffffffu, nbmax, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        wks[threadIdx.x >> 5] = ks;
-        atomicMax(&max_nb, nbmax);
-    }
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    int run = threadIdx.x ? part[threadIdx.x - 1] : 0;
-    for (int i0 = a; i0 < b; i0 += 8) {
-        int nbv[8];
+    if (lane == 0) { wsum[warp] = s; wks[warp] = ks; wmax[warp] = nbmax; }
+    __syncthreads();
+    if (warp == 0) {
+        const int v = wsum[lane];
+        int incl = v;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) nbv[k] = i0 + k < b ? pinfo[i0 + k].y : 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (i0 + k >= b) break;
-            pinfo[i0 + k].x = run;
-            run += nbv[k];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
+        wbase[lane] = incl - v;
+        if (lane == 31) wbase[32] = incl;
     }
-    if (threadIdx.x == 1023) {
-        {   // (wks was written before the scan's barriers)
-            unsigned long long t = 0ull;
-            for (int w = 0; w < 32; ++w) t += wks[w];
-            ksum = t;
+    __syncthreads();
+    int run = wbase[warp];
+    for (int i0 = a; i0 < b; i0 += 32) {
+        const int i = i0 + lane;
+        const int nb = i < b ? pinfo[i].y : 0;
+        int incl = nb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        total[0] = part[1023];
-        *(unsigned long long*)(total + 2) = ksum;   // (its last addition happened before the scan's barriers)
+        if (i < b) pinfo[i].x = run + incl - nb;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long ksum = 0ull;
+        int max_nb = 0;
+        for (int w = 0; w < 32; ++w) { ksum += wks[w]; max_nb = max(max_nb, wmax[w]); }
+        const int blocks = wbase[32];
+        total[0] = blocks;
+        *(unsigned long long*)(total + 2) = ksum;
         // storage set aside without asking (cap_blocks > 0): too small -> every kernel of the patch path returns at once and the
         // host, which reads the status block with the results, runs the step again
-        dstat[GL_DS_PT_BLOCKS] = part[1023];
+        dstat[GL_DS_PT_BLOCKS] = blocks;
         dstat[GL_DS_PT_MAXNB] = max_nb;
         *(unsigned long long*)(dstat + GL_DS_PT_KSTEPS) = ksum;
-        dstat[GL_DS_PT_OVERFLOW] = (cap_blocks > 0 && (long long)part[1023] > cap_blocks) ? 1 : 0;
+        dstat[GL_DS_PT_OVERFLOW] = (cap_blocks > 0 && (long long)blocks > cap_blocks) ? 1 : 0;
     }
 }
 

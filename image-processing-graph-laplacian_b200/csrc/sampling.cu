@@ -179,7 +179,9 @@ k_random_sampling(uint32_t seed, uint32_t n, uint32_t p, uint32_t p_pad, uint32_
             if (tid == 0) s_accepted = base + total;
             __syncthreads();
         }
-        const int A = s_accepted;
+        // numpy looks at exactly s_target draws in this round (python/sampling/random.py:9-12: p values, then p - len(unique) more, ...);
+        // what the twist produced beyond them waits for the next round -- and the sort is over 1 024 keys instead of 2 048 at p = 1000
+        const int A = min(s_accepted, s_target);
         int N = 2;
         while (N < A) N <<= 1;
         // ---- sort (value, position) ----
