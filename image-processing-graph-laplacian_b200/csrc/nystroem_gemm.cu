@@ -773,7 +773,9 @@ int gl_impl_nystroem_into(gl_ctx* ctx, gl_mat* L_B, gl_mat* phi_A, gl_mat* eigva
             // A u8 destination in pinned host memory is written by the kernel itself, pixel by pixel as the patches finish (32 contiguous
             // bytes per warp store over PCIe): the 8 MB device-to-host copy that followed the kernel disappears under it.
             uint8_t* z8_direct = nullptr;
-            if (ff->z_u8 && ctx->z8_direct) {
+            // (one channel only: three interleaved byte stores per pixel turn into partial-sector writes over PCIe -- config 5 on 8 GPUs
+            // fell from 8 107 to 2 556 Mpixel/s end to end with them)
+            if (ff->z_u8 && ctx->z8_direct && C == 1) {
                 cudaPointerAttributes at;
                 if (cudaPointerGetAttributes(&at, ff->z_u8) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
                     z8_direct = (uint8_t*)at.devicePointer + (size_t)L_B->q0 * C;
