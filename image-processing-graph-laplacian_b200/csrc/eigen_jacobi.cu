@@ -176,11 +176,19 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
         // touch the same entry.
         if (tid < 32) {
             const int k = lane >> 2, sub = lane & 3;
+            // A panel's own 8 x 8 blocks are diagonalised when its HOME pair (2k, 2k+1) is visited; every other visit rotates only
+            // the 64 cross pairs (8 steps of 8 disjoint pairs (k, 8 + (k + st) mod 8) instead of the 15 of the full cyclic sweep).
+            // What a cross rotation spills into the panels' own blocks is second order and is swept up by the next home visit:
+            // same number of outer sweeps on every fixture and config 4 (tools/emulate_jacobi_cross.py), 47 % less of the
+            // serial fp64 rotation chain that bounds a pair.
+            const bool cross_only = !(J == I + 1 && (I & 1) == 0);
+            const int nst = cross_only ? JB : JP - 1;
             for (int isw = 0; isw < inner_max; ++isw) {
                 float sw_off = 0.f;
-                for (int st = 0; st < JP - 1; ++st) {
+                for (int st = 0; st < nst; ++st) {
                     int a, b;
-                    tournament(st, k, JP, a, b);
+                    if (cross_only) { a = k; b = JB + ((k + st) & (JB - 1)); }
+                    else tournament(st, k, JP, a, b);
                     const double app = Bm[a * 17 + a], aqq = Bm[b * 17 + b], apq = Bm[a * 17 + b];
                     double c = 1.0, sn = 0.0;
                     if (app > 0.0 && aqq > 0.0) {

@@ -212,9 +212,30 @@ __global__ void k_patch_sample_features(const uint8_t* __restrict__ img, const u
 // ---------------------------------------------------------------------------------------------
 // affinity: K_B tiles + the row sums D and image-weighted sums T (from the fp32 values, before the fp16 rounding)
 // ---------------------------------------------------------------------------------------------
-// thread (tx = tid & 3: eight consecutive slots of the block, ty = tid >> 2: column ty of the patch, its 16 rows): the column part
-// of the exponent is the same for all of the thread's pixels and leaves the pair loop.  A warp stores 8 pixel rows of 64 bytes =
-// 512 contiguous bytes.
+// Slot group tx (eight consecutive slots of the block) is uniform per WARP, so that a group without a sample costs nothing: at
+// config 4 a patch has 13.8 samples in reach on average, and with the slot groups spread over the lanes (round 2's first cut) half
+// of every warp's pairs were empty slots.  A block with at most 16 samples ("narrow": its slots 16..31 are never multiplied, the
+// extrapolation takes one K step) is split as warp -> (group w & 1, column half (w >> 1) & 1, rows 8 (w >> 2) .. + 8); a fuller one
+// as warp -> (group w & 3, column half w >> 2, all 16 rows).  A lane is one pixel column: the column part of the exponent is the
+// same for all of the thread's pixels and leaves the pair loop.  A pixel's 8 values leave as one 16-byte store into the A-tile
+// position the MMA will read (the four groups of a pixel row fill its 64 bytes between them; L2 merges the sectors).
+
+// Warp-wide sums of 8 values per lane with 9 shuffles (the halves a lane does not keep travel): on return lane L holds the sum over
+// the warp of v[(L >> 2) & 7].  Fixed tree: deterministic.
+__device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane)
+{
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float a[4], b[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = (h16 ? v[4 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, h16 ? v[j] : v[4 + j], 16);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) b[j] = (h8 ? a[2 + j] : a[j]) + __shfl_xor_sync(0xffffffffu, h8 ? a[j] : a[2 + j], 8);
+    float c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, h4 ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+}
+
 template <int KIND, int C>
 __global__ void __launch_bounds__(256, C == 1 ? 3 : 2)
 k_patch_affinity(Geom g, const uint8_t* __restrict__ img, const float* __restrict__ sf, int p_pad, float a2, float b2,
@@ -225,124 +246,188 @@ k_patch_affinity(Geom g, const uint8_t* __restrict__ img, const float* __restric
     extern __shared__ float pa_smem[];
     constexpr int NS = 1 + C;
     float* cta_sum = pa_smem;                  // [NS][p_pad]
-    float* ws = cta_sum + NS * p_pad;          // [NS][8 warps][SLOTS]
-    float* px = ws + NS * 8 * SLOTS;           // [C][PW * PR] pixel values
-    __shared__ uint32_t sid[SLOTS];
-    const int tid = threadIdx.x, tx = tid & 3, ty = tid >> 2, lane = tid & 31, warp = tid >> 5;
+    float* ws = cta_sum + NS * p_pad;          // 2 x [NS][8 warps][8 slots of the warp's group] (room for [NS][8][SLOTS])
+    float* px = ws + NS * 8 * SLOTS;           // 2 x [C][PW * PR] pixel values
+    __shared__ uint32_t sid[3][SLOTS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < NS * p_pad; i += 256) cta_sum[i] = 0.f;
 
-    for (int patch = blockIdx.x; patch < g.npatch; patch += gridDim.x) {
+    // The global loads a patch starts with (its list header, its first block of sample indices, its pixels) are issued a patch ahead
+    // and land in registers under the previous patch's arithmetic (ncu: a quarter of this kernel's stall samples sat on the pixel
+    // load, another fifth on its three barriers per block).  Shared buffers rotate (sid x 3, ws x 2, px x 2), which leaves ONE barrier
+    // per block: what a block's arithmetic reads was written before the previous barrier, what its closing sums read is not
+    // rewritten before the next one.
+    const int stride = gridDim.x;
+    int patch = blockIdx.x;
+    if (patch >= g.npatch) return;
+    // (the bytes stay untouched in their registers until store_pixels: anything computed on them here would wait for the loads)
+    auto load_pixels = [&](int pt_, uint8_t (&r)[C][4]) {
+        const int py = pt_ / g.pcols, pxi = pt_ - py * g.pcols;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = tid + 256 * j;
+            const int rr = py * PR + (i >> 6), c = pxi * PW + (i & 63);
+            const bool in = rr < g.band_rows && c < g.width;
+            const size_t q = (size_t)(g.row0 + (in ? rr : 0)) * g.width + (in ? c : 0);
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) r[ch][j] = img[q * C + ch];
+        }
+    };
+    auto store_pixels = [&](float* dst, const uint8_t (&r)[C][4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) dst[ch * PW * PR + tid + 256 * j] = (float)r[ch][j];
+    };
+    // list headers and sample indices travel global -> shared without a register (cp.async): header of local patch k in spi[k % 3],
+    // fetched two patches ahead; a block's indices fetched a block ahead; both waited for right before the block's barrier
+    __shared__ int4 spi[3];
+    auto async_copy = [](void* dst, const void* src, int bytes) {
+        if (bytes == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(dst)), "l"(src) : "memory");
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(dst)), "l"(src) : "memory");
+    };
+    {
+        uint8_t r0[C][4];
+        load_pixels(patch, r0);
+        const int4 pi0 = pinfo[patch];
+        if (tid == 0) {
+            spi[0] = pi0;
+            spi[1] = patch + stride < g.npatch ? pinfo[patch + stride] : make_int4(0, 1, 0, 0);
+        }
+        if (tid < SLOTS) sid[0][tid] = slots[(size_t)pi0.x * SLOTS + tid];
+        store_pixels(px, r0);
+    }
+    __syncthreads();
+    int cur_s = 0, cur_w = 0, cur_p = 0, kp = 0;   // kp = local patch counter mod 3
+
+    for (; patch < g.npatch; patch += stride) {
         const int py = patch / g.pcols, pxi = patch - py * g.pcols;
         const int r_base = py * PR, c_base = pxi * PW;     // band-local row, column
-        const int4 pi = pinfo[patch];
-        __syncthreads();   // the previous patch's readers of px / sid are done
-        for (int i = tid; i < PW * PR; i += 256) {
-            const int r = r_base + (i >> 6), c = c_base + (i & 63);
-            const bool in = r < g.band_rows && c < g.width;
-            const size_t q = (size_t)(g.row0 + (in ? r : 0)) * g.width + (in ? c : 0);
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) px[ch * PW * PR + i] = (float)img[q * C + ch];
-        }
-        const float pc = (float)(c_base + ty);
-        const bool col_ok = c_base + ty < g.width;
+        const int nxt = patch + stride;
+        const int kp1 = kp == 2 ? 0 : kp + 1, kp2 = kp1 == 2 ? 0 : kp1 + 1;
+        const int4 pi = spi[kp];
+        const int pin_x = spi[kp1].x;      // (meaningful only while nxt < npatch)
+        if (tid == 0 && nxt + stride < g.npatch) async_copy(&spi[kp2], pinfo + (nxt + stride), 16);
+        uint8_t pxr[C][4];
+        if (nxt < g.npatch) load_pixels(nxt, pxr);
+        __half* kb_patch = KB + ((size_t)pi.x * G) * 128 * SLOTS;
+        const float* pxc = px + cur_p * (C * PW * PR);
         for (int b = 0; b < pi.y; ++b) {
-            if (tid < SLOTS) sid[tid] = slots[(size_t)(pi.x + b) * SLOTS + tid];
-            __syncthreads();
-            float sr[8], sv[C][8], cterm[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t s = sid[tx * 8 + k];
-                const bool empty = s == 0xffffffffu;   // an empty slot gets features at 1e18: its exponent is hugely negative, K = 0
-                const int si = empty ? 0 : (int)s;
-                sr[k] = empty ? 1e18f : sf[si];
-                const float sc = empty ? 1e18f : sf[p_pad + si];
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) sv[ch][k] = empty ? 1e18f : sf[(2 + ch) * p_pad + si];
-                cterm[k] = 0.f;
-                if (KIND != GL_PHOTOMETRIC) {
-                    const float dc = pc - sc;
-                    cterm[k] = dc * dc * a2;   // (an empty slot: -inf -> K = 0)
+            const uint32_t* sidc = sid[cur_s];
+            float* wsc = ws + cur_w * (NS * 8 * 8);
+            const bool last_b = b + 1 == pi.y;
+            const int nxt_s = cur_s == 2 ? 0 : cur_s + 1;
+            // what the next block (of this patch, or the first one of the next patch) reads
+            if (tid < SLOTS && (!last_b || nxt < g.npatch))
+                async_copy(&sid[nxt_s][tid], slots + ((size_t)(last_b ? pin_x : pi.x + b + 1) * SLOTS + tid), 4);
+            const int cnt = min(SLOTS, pi.z - SLOTS * b);    // samples of this block: slots 0 .. cnt - 1 (k_patch_fill fills from 0 upwards)
+            const bool narrow = cnt <= 16;
+            const int tx = narrow ? (warp & 1) : (warp & 3);
+            const int ty = (narrow ? ((warp >> 1) & 1) : (warp >> 2)) * 32 + lane;
+            const int i0 = narrow ? (warp >> 2) * 8 : 0, i1 = narrow ? i0 + 8 : PR;
+            const float pc = (float)(c_base + ty);
+            const bool col_ok = c_base + ty < g.width;
+            if (tx * 8 >= cnt) {
+                // a group without a sample inside a K step that is multiplied: zeros, no arithmetic
+                if (KB) {
+                    for (int i = i0; i < i1; ++i) {
+                        const int mt = i >> 1;
+                        if (r_base + 2 * mt >= g.band_rows) break;
+                        *(uint4*)&kb_patch[((size_t)(mt * pi.y + b) * 128 + (size_t)((i & 1) * PW + ty)) * SLOTS + tx * 8] = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
-            }
-            float acc[8], tacc[C][8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                acc[k] = 0.f;
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) tacc[ch][k] = 0.f;
-            }
-            __half* kb_patch = KB + ((size_t)pi.x * G) * 128 * SLOTS;
-#pragma unroll 2
-            for (int i = 0; i < PR; ++i) {
-                const int mt = i >> 1;
-                if (r_base + 2 * mt >= g.band_rows) break;      // M tiles wholly below the band are neither stored nor multiplied
-                // a pixel outside the image / band gets a row coordinate at 1e18: its spatial exponent is hugely negative and K = 0 without
-                // a select per pair (both kinds served here have the spatial term; 1e36 * a2 stays finite)
-                const bool ok = col_ok && r_base + i < g.band_rows;
-                const float pr = ok ? (float)(g.row0 + r_base + i) : 1e18f;
-                float pv[C];
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) pv[ch] = px[ch * PW * PR + i * PW + ty];
-                float kv[8];
+            } else {
+                float sr[8], sv[C][8], cterm[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    float x = cterm[k];
+                    const uint32_t s = sidc[tx * 8 + k];
+                    const bool empty = s == 0xffffffffu;   // an empty slot gets features at 1e18: its exponent is hugely negative, K = 0
+                    const int si = empty ? 0 : (int)s;
+                    sr[k] = empty ? 1e18f : sf[si];
+                    const float sc = empty ? 1e18f : sf[p_pad + si];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) sv[ch][k] = empty ? 1e18f : sf[(2 + ch) * p_pad + si];
+                    cterm[k] = 0.f;
                     if (KIND != GL_PHOTOMETRIC) {
-                        const float dr = pr - sr[k];
-                        x = fmaf(dr * dr, a2, x);
+                        const float dc = pc - sc;
+                        cterm[k] = dc * dc * a2;   // (an empty slot: -inf -> K = 0)
                     }
-                    if (KIND != GL_SPATIAL) {
-                        float d = pv[0] - sv[0][k];
-                        float t = d * d;
-#pragma unroll
-                        for (int ch = 1; ch < C; ++ch) {
-                            d = pv[ch] - sv[ch][k];
-                            t = fmaf(d, d, t);
-                        }
-                        x = fmaf(t, b2, x);
-                    }
-                    kv[k] = fast_exp2(x);
-                    acc[k] += kv[k];
-#pragma unroll
-                    for (int ch = 0; ch < C; ++ch) tacc[ch][k] = fmaf(kv[k], pv[ch], tacc[ch][k]);
                 }
-                __half2 h0 = __floats2half2_rn(kv[0], kv[1]), h1 = __floats2half2_rn(kv[2], kv[3]);
-                __half2 h2 = __floats2half2_rn(kv[4], kv[5]), h3 = __floats2half2_rn(kv[6], kv[7]);
-                uint4 pk;
-                pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
-                if (KB) *(uint4*)&kb_patch[((size_t)(mt * pi.y + b) * 128 + (size_t)((i & 1) * PW + ty)) * SLOTS + tx * 8] = pk;
-            }
-            // sums: lanes sharing tx (xor 4, 8, 16), then the 8 warps through shared memory, in a fixed order (deterministic)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-#pragma unroll
-                    for (int ch = 0; ch < C; ++ch) tacc[ch][k] += __shfl_xor_sync(0xffffffffu, tacc[ch][k], o);
-                }
-            }
-            if (lane < 4) {
+                float acc[8], tacc[C][8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    ws[warp * SLOTS + lane * 8 + k] = acc[k];
+                    acc[k] = 0.f;
 #pragma unroll
-                    for (int ch = 0; ch < C; ++ch) ws[(1 + ch) * 8 * SLOTS + warp * SLOTS + lane * 8 + k] = tacc[ch][k];
+                    for (int ch = 0; ch < C; ++ch) tacc[ch][k] = 0.f;
+                }
+#pragma unroll 2
+                for (int i = i0; i < i1; ++i) {
+                    const int mt = i >> 1;
+                    if (r_base + 2 * mt >= g.band_rows) break;      // M tiles wholly below the band are neither stored nor multiplied
+                    // a pixel outside the image / band gets a row coordinate at 1e18: its spatial exponent is hugely negative and K = 0
+                    // without a select per pair (both kinds served here have the spatial term; 1e36 * a2 stays finite)
+                    const bool ok = col_ok && r_base + i < g.band_rows;
+                    const float pr = ok ? (float)(g.row0 + r_base + i) : 1e18f;
+                    float pv[C];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) pv[ch] = pxc[ch * PW * PR + i * PW + ty];
+                    float kv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float x = cterm[k];
+                        if (KIND != GL_PHOTOMETRIC) {
+                            const float dr = pr - sr[k];
+                            x = fmaf(dr * dr, a2, x);
+                        }
+                        if (KIND != GL_SPATIAL) {
+                            float d = pv[0] - sv[0][k];
+                            float t = d * d;
+#pragma unroll
+                            for (int ch = 1; ch < C; ++ch) {
+                                d = pv[ch] - sv[ch][k];
+                                t = fmaf(d, d, t);
+                            }
+                            x = fmaf(t, b2, x);
+                        }
+                        kv[k] = fast_exp2(x);
+                        acc[k] += kv[k];
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) tacc[ch][k] = fmaf(kv[k], pv[ch], tacc[ch][k]);
+                    }
+                    __half2 h0 = __floats2half2_rn(kv[0], kv[1]), h1 = __floats2half2_rn(kv[2], kv[3]);
+                    __half2 h2 = __floats2half2_rn(kv[4], kv[5]), h3 = __floats2half2_rn(kv[6], kv[7]);
+                    uint4 pk;
+                    pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+                    if (KB) *(uint4*)&kb_patch[((size_t)(mt * pi.y + b) * 128 + (size_t)((i & 1) * PW + ty)) * SLOTS + tx * 8] = pk;
+                }
+                // sums: over the warp's 32 columns (and its rows), then over the warps of the group through shared memory, in a fixed
+                // order (deterministic)
+                const float s0 = warp_sum8(acc, lane);
+                if ((lane & 3) == 0) wsc[warp * 8 + ((lane >> 2) & 7)] = s0;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float s1 = warp_sum8(tacc[ch], lane);
+                    if ((lane & 3) == 0) wsc[((1 + ch) * 8 + warp) * 8 + ((lane >> 2) & 7)] = s1;
                 }
             }
+            if (last_b && nxt < g.npatch) store_pixels(px + (cur_p ^ 1) * (C * PW * PR), pxr);
+            if (tid < SLOTS) asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
             if (tid < NS * SLOTS) {
                 const int which = tid / SLOTS, sl = tid % SLOTS;
-                const uint32_t s = sid[sl];
+                const uint32_t s = sidc[sl];
                 if (s != 0xffffffffu) {
+                    // (a non-empty slot's group is active in every warp that owns it: narrow -> warps grp, grp + 2, ..; else grp, grp + 4)
                     float sum = 0.f;
-#pragma unroll
-                    for (int wi = 0; wi < 8; ++wi) sum += ws[which * 8 * SLOTS + wi * SLOTS + sl];
+                    for (int wi = sl >> 3; wi < 8; wi += narrow ? 2 : 4) sum += wsc[(which * 8 + wi) * 8 + (sl & 7)];
                     cta_sum[which * p_pad + s] += sum;
                 }
             }
-            __syncthreads();   // ws / sid are rewritten by the next block
+            cur_s = nxt_s;
+            cur_w ^= 1;
         }
+        cur_p ^= 1;
+        kp = kp1;
     }
     __syncthreads();
     for (int i = tid; i < NS * p_pad; i += 256) partial[(size_t)blockIdx.x * NS * p_pad + i] = cta_sum[i];
@@ -1212,7 +1297,7 @@ template <int KIND, int C>
 static int launch_patch_affinity(gl_ctx* ctx, const pt::Geom& g, double h_loc, double h_val, const float* sf, gl_mat* KB, float* partial, int grid)
 {
     const int p_pad = ctx->p_pad;
-    const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_pad + (size_t)(1 + C) * 8 * pt::SLOTS + (size_t)C * pt::PW * pt::PR);
+    const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_pad + (size_t)(1 + C) * 8 * pt::SLOTS + (size_t)2 * C * pt::PW * pt::PR);
     GL_CUDA_CHECK(cudaFuncSetAttribute(pt::k_patch_affinity<KIND, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const float log2e = 1.4426950408889634f;
     StageTimer kt(ctx, GL_T_K_AFFINITY_B);
@@ -1234,7 +1319,7 @@ int gl_patch_affinity(gl_ctx* ctx, int kind, double h_loc, double h_val, gl_mat*
     const int p = (int)ctx->p, p_pad = ctx->p_pad, C = ctx->channels;
     const pt::Geom g = patch_geom(ctx, h_loc);
     {
-        const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_pad + (size_t)(1 + C) * 8 * pt::SLOTS + (size_t)C * pt::PW * pt::PR);
+        const size_t smem = sizeof(float) * ((size_t)(1 + C) * p_pad + (size_t)(1 + C) * 8 * pt::SLOTS + (size_t)2 * C * pt::PW * pt::PR);
         if (smem > 200 * 1024) {
             gl_set_error("affinity: p = %d samples need %zu bytes of shared memory per CTA", p, smem);
             return GL_ERR_UNSUPPORTED;
