@@ -75,7 +75,7 @@ __device__ __forceinline__ void tournament(int step, int pair, int nb, int& a, i
 // otherwise the Gram block is accumulated chunk by chunk and the chunks are fetched a second time for the rotation.
 __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc, int I, int J, float tol, int inner_max, float* P, float* red,
                                             double* Bm, double* Qm, double* cs, int* role, int* pq, float* s_off, unsigned* s_cta_off,
-                                            unsigned* __restrict__ pmask, long long* __restrict__ pprof = nullptr)
+                                            unsigned* __restrict__ pmask, bool allow_cross, long long* __restrict__ pprof = nullptr)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     const int bi = tid >> 4, bj = tid & 15;  // this thread's element of the 16 x 16 block
@@ -181,7 +181,9 @@ __device__ __forceinline__ void jacobi_pair(float* __restrict__ G, int p, int pc
             // What a cross rotation spills into the panels' own blocks is second order and is swept up by the next home visit:
             // same number of outer sweeps on every fixture and config 4 (tools/emulate_jacobi_cross.py), 47 % less of the
             // serial fp64 rotation chain that bounds a pair.
-            const bool cross_only = !(J == I + 1 && (I & 1) == 0);
+            // Near convergence (allow_cross = false: the sweep started below 4 tol) every visit runs the full sweep again: at p = 4 200
+            // the cross-only sweeps stalled a hair above the tolerance (5.1e-5), fed by what they leave in the panels' own blocks.
+            const bool cross_only = allow_cross && !(J == I + 1 && (I & 1) == 0);
             const int nst = cross_only ? JB : JP - 1;
             for (int isw = 0; isw < inner_max; ++isw) {
                 float sw_off = 0.f;
@@ -327,6 +329,7 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
     const int npairs_all = nb * (nb - 1) / 2;
 
     int sweep = 0;
+    float prev_off = 3.0e38f;
     for (; sweep < max_sweeps; ++sweep) {
         int* cnt = step_cnt + (size_t)sweep * 2 * nb;   // [0] = active pairs in total, [2 d + par] = per step
         // ---- A. C = G^T G, upper tiles ----
@@ -460,6 +463,15 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
         JPROF();
         const float off = __uint_as_float(__ldcg(&sweep_off[sweep]));
         if (off <= tol) break;
+        // The fp32 floor: a column that belongs to a small eigenvalue carries direction noise of about 6e-8 lambda_max / lambda, and
+        // when that sits above the tolerance the sweeps stop improving (350 x 300 pixels, p = 4 200: 5.1e-5 sweep after sweep against
+        // tol = 5e-5).  Jacobi converges quadratically at the end, so two screens in a row within 30 % of each other are the floor:
+        // accepted up to 4 tol (still below half of fp16's rounding of Phi) and reported as such (sweeps_done[1]).
+        if (sweep >= 2 && off <= 4.f * tol && off > 0.7f * prev_off) {
+            if (blockIdx.x == 0 && tid == 0) sweeps_done[1] = 1;
+            break;
+        }
+        prev_off = off;
         // ---- C. rotations ----
         const int active = __ldcg(&cnt[0]);
         if (2 * active > npairs_all) {
@@ -468,7 +480,7 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                     int I, J;
                     tournament(step, pair, nb, I, J);
                     if (__ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
-                        jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off, pmask);
+                        jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off, pmask, off > 4.f * tol);
                 }
                 grid.sync();
             }
@@ -499,7 +511,7 @@ k_jacobi(float* __restrict__ G, int p, int pc /* panel rows held in shared memor
                     for (int c = blockIdx.x; c < ncand; c += gridDim.x) {
                         const int I = (c / d) * 2 * d + par * d + (c % d), J = I + d;
                         if (J < nb && __ldcg(&pair_rel[I * nb + J]) > 0.2f * tol)
-                            jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off, pmask,
+                            jacobi_pair(G, p, pc, I, J, tol, inner_max, P, red, Bm, Qm, cs, role, pq, &s_off, &s_cta_off, pmask, off > 4.f * tol,
                                         (jprof && blockIdx.x == 0) ? jprof + 40 : nullptr);
                     }
                     grid.sync();
@@ -647,17 +659,17 @@ __global__ void __launch_bounds__(256) k_rayleigh_cols(const double* __restrict_
         for (int i = ch * cr + warp; i < i1; i += 8) {
             const double gi = gs[i];
             if (gi == 0.0) continue;                       // (uniform over the warp)
+            // every lane keeps its own partial of g_i A_ik g_k over the rows of its warp; ONE warp sum at the end (a sum per row
+            // put ten dependent shuffles between the loads of consecutive rows)
             const double* Ai = A + (size_t)i * p;
-            double sacc = 0.0;
             for (int ch2 = 0; ch2 < 32; ++ch2) {
                 if (!((occ >> ch2) & 1u)) continue;
                 const int k1 = min(p, (ch2 + 1) * cr);
-                for (int k = ch2 * cr + lane; k < k1; k += 32) sacc = fma(Ai[k], gs[k], sacc);
+                for (int k = ch2 * cr + lane; k < k1; k += 32) num = fma(gi * Ai[k], gs[k], num);
             }
-            sacc = warp_sum(sacc);
-            num = fma(gi, sacc, num);
         }
     }
+    num = warp_sum(num);
     __syncthreads();
     if (lane == 0) red[warp] = num;
     __syncthreads();
@@ -738,7 +750,8 @@ __global__ void k_jacobi_status(const unsigned* __restrict__ ctl, int max_sweeps
     const float last = __uint_as_float(last_bits);
     dstat[GL_DS_JACOBI_SWEEPS] = sweeps;
     dstat[GL_DS_JACOBI_OFF] = (int)last_bits;
-    dstat[GL_DS_JACOBI] = (sweeps >= max_sweeps || last > tol) ? 1 : 0;
+    const bool at_floor = ctl[max_sweeps + 2] != 0u;     // stopped at the fp32 floor, within 4 tol (k_jacobi)
+    dstat[GL_DS_JACOBI] = (sweeps >= max_sweeps || (last > tol && !at_floor)) ? 1 : 0;
 }
 
 int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat** eigvals, gl_mat** eigvals_inv)
@@ -881,8 +894,11 @@ int gl_impl_eigensolve(gl_ctx* ctx, gl_mat* L_A, int m, gl_mat** eigvecs, gl_mat
         float last = 1.f;
         if (sweeps < max_sweeps) memcpy(&last, &h[sweeps], sizeof(float));
         else memcpy(&last, &h[max_sweeps - 1], sizeof(float));
-        if (ctx->verbose) fprintf(stderr, "[libglcuda] jacobi: p=%d panels=%d grid=%d sweeps=%d last off=%.3g\n", p, nb, grid, sweeps, last);
-        if (sweeps >= max_sweeps || last > ctx->jacobi_tol) {
+        const bool at_floor = h[max_sweeps + 2] != 0u;
+        if (ctx->verbose)
+            fprintf(stderr, "[libglcuda] jacobi: p=%d panels=%d grid=%d sweeps=%d last off=%.3g%s\n", p, nb, grid, sweeps, last,
+                    at_floor ? " (fp32 floor, accepted within 4 tol)" : "");
+        if (sweeps >= max_sweeps || (last > ctx->jacobi_tol && !at_floor)) {
             gl_set_error("eigensolve: not converged after %d sweeps (off-orthogonality %.3g > %.3g)", sweeps, last, ctx->jacobi_tol);
             rc = GL_ERR_NOTCONVERGED;
             break;

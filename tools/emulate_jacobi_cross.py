@@ -3,7 +3,8 @@ pairs by distance class, one inner 16 x 16 Jacobi sweep per visit -- the full cy
 only the 64 CROSS pairs (8 steps) on visits other than a panel's home pair (2k, 2k+1).  Prints the relative off-diagonal after every
 sweep and the eigenvalue error: whether the cheaper inner sweep still converges in the same number of outer sweeps.
 
-    python tools/emulate_jacobi_cross.py [full|cross]
+    python tools/emulate_jacobi_cross.py [full|cross|hybrid] [fixture.npz | large]   (hybrid = what the kernel does: cross-only while the sweep
+    starts above 4 tol)
 """
 import os
 import sys
@@ -76,7 +77,7 @@ def run(L, mode):
     nb = cols // JB
     G = np.zeros((p, cols), dtype=np.float32)
     G[:, :p] = L.astype(np.float32)
-    for sweep in range(6):
+    for sweep in range(12):
         rel = screen(G, nb)
         # a panel's within-block goes with its home pair (2k, 2k+1)
         pair_rel = np.triu(rel, 1)
@@ -113,7 +114,7 @@ def run(L, mode):
                 if R.max() <= 0.25 * TOL:
                     continue
                 home = (J == I + 1) and (I % 2 == 0)
-                Q = inner(B, cross_only=(mode == "cross" and not home))
+                Q = inner(B, cross_only=((mode == "cross" or (mode == "hybrid" and off > 4 * TOL)) and not home))
                 G[:, idx] = (P.astype(np.float64) @ Q).astype(np.float32)
                 visits += 1
         print(f"   visits {visits}, classes {len(classes)}")
@@ -125,6 +126,14 @@ def run(L, mode):
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "full"
+    if len(sys.argv) > 2 and sys.argv[2] == "large":      # tests/test_gpu_parity.py::test_large_sample_count (350 x 300, p = 4200 uniform)
+        from oracle import oracle_np as o
+        img = o.synthetic_image(350, 300, 1, seed=17)
+        smp = oc.uniform_sampling(350, 300, 4000)
+        r = o.run_pipeline(img, smp)
+        print("mode", mode, "large p", r["L_A"].shape[0])
+        run(r["L_A"], mode)
+        sys.exit(0)
     if len(sys.argv) > 2:      # a small committed fixture instead of config 4
         from oracle import oracle_np as o
         g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", sys.argv[2]))
