@@ -13,3 +13,6 @@ echo "== launch list =="
 timeout 600 python tools/run_c4_once.py 5 > gpurun_out/once.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_final.csv python tools/run_c4_once.py 5 > gpurun_out/ncu_final.log 2>&1
 echo "launch list rc=$?"; cat gpurun_out/once.log | tail -2
+echo "== ncu --set full: the kernels that changed last (patch affinity, Jacobi, Rayleigh) =="
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_patch_affinity|k_jacobi$|k_rayleigh_cols' --launch-skip 3 -c 3 -o gpurun_out/r02_final_small python tools/run_c4_once.py 3 > gpurun_out/ncu_final_small.log 2>&1
+echo "ncu full rc=$?"
