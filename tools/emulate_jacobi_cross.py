@@ -120,8 +120,9 @@ def run(L, mode):
         print(f"   visits {visits}, classes {len(classes)}")
     lam = np.sort(np.linalg.norm(G[:, :p].astype(np.float64), axis=0))
     mu = np.linalg.eigvalsh(L)
-    print("max rel eigenvalue error (column norms, before the Rayleigh refinement):", np.max(np.abs(lam[1:] - mu[1:]) / mu[1:]))
-    return sweep
+    err = float(np.max(np.abs(lam[1:] - mu[1:]) / mu[1:]))
+    print("max rel eigenvalue error (column norms, before the Rayleigh refinement):", err)
+    return sweep, float(off), err
 
 
 if __name__ == "__main__":
